@@ -1,0 +1,29 @@
+# Builds the product library skirt_b200/libskirtgpu.so (CUDA, sm_100a) and the test oracles.
+NVCC ?= /usr/local/cuda/bin/nvcc
+HOSTCXX := /usr/bin/g++
+ARCH := -gencode arch=compute_100a,code=sm_100a
+# -fmad=false: no FMA contraction, so that fp64 geometry matches the reference bit for bit
+NVFLAGS := $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -lineinfo -fmad=false --expt-relaxed-constexpr \
+           -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function -Xptxas -v
+CSRC := skirt_b200/csrc
+OBJS := $(CSRC)/build/engine.o $(CSRC)/build/path_kernels.o $(CSRC)/build/mc_kernels.o
+HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/skirtgpu.h
+NCCL_INC ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'include'))" 2>/dev/null)
+NCCL_LIB ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'lib'))" 2>/dev/null)
+
+all: skirt_b200/libskirtgpu.so oracle
+
+$(CSRC)/build/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(CSRC)/build
+	$(NVCC) $(NVFLAGS) -I$(NCCL_INC) -c $< -o $@ 2> $(CSRC)/build/$*.ptxas.log || (cat $(CSRC)/build/$*.ptxas.log; false)
+
+skirt_b200/libskirtgpu.so: $(OBJS)
+	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJS) -ldl
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf $(CSRC)/build skirt_b200/libskirtgpu.so
+	$(MAKE) -C oracle clean
+.PHONY: all oracle clean

@@ -1,0 +1,167 @@
+/* skirtgpu.h -- C ABI of the B200-native photon-packet engine (libskirtgpu.so).
+ *
+ * This is the drop-in boundary for SKIRT's propagation hot path.  The
+ * reference has no FFI; its seam is C++ virtual dispatch on SimulationItem subclasses.  Each entry
+ * point below names the reference interface it replaces (file:line relative to the reference
+ * tree); INTEGRATION.md shows the adapter a SKIRT maintainer would add on the reference side.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 on success or a non-zero
+ * status, and skg_last_error() then returns a message (the reference-side adapter turns that into
+ * `throw FATALERROR(msg)`, FatalError.hpp:47).  All floating point data is IEEE binary64, all
+ * indices int32 unless stated, exactly as in the reference.  Pointers are HOST
+ * pointers unless the parameter name starts with `d_` (device pointers on the engine's GPU).
+ * Engine calls must come from one host thread at a time per engine (same rule as Parallel::call,
+ * Parallel.cpp:79-80).  There is no CPU fallback: creation fails without a CUDA device.
+ */
+#ifndef SKIRTGPU_H
+#define SKIRTGPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct skg_engine skg_engine;
+
+/* ---- engine life cycle ------------------------------------------------------------------------ */
+int skg_engine_create(int device, skg_engine** out);
+void skg_engine_destroy(skg_engine* e);
+const char* skg_last_error(void);
+int skg_version(void);
+
+/* ---- dust grids: replace DustGrid::path / whichcell / randomPositionInCell (DustGrid.hpp:89-106) -- */
+
+/* CartesianDustGrid (CartesianDustGrid.cpp:28-43): bin borders _xv[Nx+1], _yv[Ny+1], _zv[Nz+1];
+ * cell number m = k + Nz*j + Nz*Ny*i (CartesianDustGrid.cpp:326-329). */
+int skg_grid_cartesian(skg_engine* e, const double* xv, int Nx, const double* yv, int Ny, const double* zv, int Nz);
+
+/* TreeDustGrid (TreeDustGrid.cpp:50-164): the node vector _tree flattened in id order.
+ *   kind   : 0 OctTreeDustGrid, 1 BinTreeDustGrid
+ *   search : 0 TopDown, 1 Neighbor, 2 Bookkeeping (TreeDustGrid.hpp:155; Bookkeeping is octree-only)
+ *   box[6*l..] = xmin,ymin,zmin,xmax,ymax,zmax of node l (TreeNode : Box)
+ *   child0[l]  = id of the first child (children have consecutive ids, OctTreeNode.cpp:38-49), -1 for leaves
+ *   parent[l]  = id of the father, -1 for the root;  cell[l] = _cellnumberv[l] (m for leaves, else -1)
+ *   dir[l]     = BinTreeNode::_dir (0 x, 1 y, 2 z), ignored for octrees
+ *   nbrStart[6*l+w] .. nbrStart[6*l+w+1] index nbrIds: TreeNode::_neighbors[w] IN STORED ORDER
+ *                (walls BACK,FRONT,LEFT,RIGHT,BOTTOM,TOP = 0..5, TreeNode.hpp:100); may be NULL unless search==1 */
+int skg_grid_tree(skg_engine* e, int kind, int search, int Nnodes, const double* box, const int* child0,
+                  const int* parent, const int* cell, const int* dir, const int* nbrStart, const int* nbrIds);
+
+/* AdaptiveMesh (AdaptiveMesh.cpp:21-57, AdaptiveMeshNode.cpp:14-80): nodes numbered so that the
+ * children of a node are consecutive in local Morton order (k*Ny+j)*Nx+i starting at child0[l].
+ *   nxyz[3*l..] = _Nx,_Ny,_Nz (0 for leaves); cell[l] = _m; wallNbr[6*l+w] = neighbour node beyond wall w or -1 */
+int skg_grid_amesh(skg_engine* e, int Nnodes, const double* box, const int* nxyz, const int* child0,
+                   const int* cell, const int* wallNbr);
+
+/* VoronoiMesh (VoronoiMesh.cpp:310-393): particles[3*m..], neighbour lists in Voro++ order (ids >= 0
+ * cells, -1..-6 domain walls), block lists indexed i*nb*nb+j*nb+k, per-block kd-trees (blkTree[b] =
+ * root kd node or -1; node arrays kdM (cell), kdAxis, kdUp, kdLeft, kdRight with -1 = none) and the
+ * enclosing box of every cell (for randomPosition, VoronoiMesh.cpp:591-606). */
+int skg_grid_voronoi(skg_engine* e, int Ncells, const double* particles, const int* nbrStart, const int* nbrIds,
+                     const double* extent, int nb, const int* blkStart, const int* blkIds, const int* blkTree,
+                     int Nkd, const int* kdM, const int* kdAxis, const int* kdUp, const int* kdLeft,
+                     const int* kdRight, const double* cellBox);
+
+int skg_num_cells(skg_engine* e);
+
+/* ---- medium: DustSystem::_rhovv (DustSystem.hpp:434) + DustMix kappa tables (DustMix.cpp:55-90) ---- */
+/* rho[m*Ncomp+h]; kext/ksca/g[h*Nlambda+ell] */
+int skg_medium(skg_engine* e, int Ncells, int Ncomp, int Nlambda, const double* rho, const double* kext,
+               const double* ksca, const double* g);
+
+/* ---- deterministic geometry: batched DustGrid::path() + DustGridPath::fillOpticalDepth() ------------ */
+/* Replaces DustSystem::fillOpticalDepth (DustSystem.cpp:959-980) for n rays at once.
+ * Step 1 counts the segments of every ray and returns CSR offsets (offsets[n+1], int64) and the total;
+ * step 2 fills m/ds/s/dtau/tau (DustGridPath::Segment, DustGridPath.hpp:161-167) for the same rays.
+ * ell[n] may be NULL (geometry only: dtau = tau = 0) or point to ONE value when ell_stride == 0. */
+#define SKG_HOST 0
+#define SKG_DEVICE 1
+int skg_path_count(skg_engine* e, int mem, int64_t n, const double* r, const double* k, int64_t* offsets, int64_t* total);
+int skg_path_fill(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
+                  const int64_t* offsets, int* m, double* ds, double* s, double* dtau, double* tau);
+/* DustSystem::opticaldepth(pp, distance) (DustSystem.cpp:984-1000); distance may be NULL (= DBL_MAX) */
+int skg_opticaldepth(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
+                     const double* distance, double* tau);
+/* DustGrid::whichcell (DustGrid.hpp:89) */
+int skg_whichcell(skg_engine* e, int mem, int64_t n, const double* r, int* m);
+/* number of "stuck packet" escapes / terminations since engine creation (the reference logs warnings,
+ * TreeDustGrid.cpp:437-454, AdaptiveMesh.cpp:348-365) */
+int skg_stuck_counts(skg_engine* e, int64_t* escaped, int64_t* terminated);
+
+/* ---- sources: StellarSystem::launch (StellarSystem.cpp:116-158) -------------------------------------- */
+enum { SKG_GEOM_EXPDISK = 1, SKG_GEOM_SERSIC = 2 };
+typedef struct skg_source
+{
+    int geometry;          /* SKG_GEOM_* */
+    /* ExpDiskGeometry (ExpDiskGeometry.cpp:134-161): p[0]=hR p[1]=hz p[2]=Rmax p[3]=zmax p[4]=Rmin
+     * SersicGeometry + SpheroidalGeometryDecorator: p[0]=Reff p[1]=flattening q; table = inverse-CDF grid */
+    double p[8];
+    /* SpiralStructureGeometryDecorator (SpiralStructureGeometryDecorator.cpp:177-192); arms == 0: none */
+    int spiral_arms, spiral_index;
+    double spiral_pitch, spiral_radius, spiral_phase, spiral_weight;
+    /* tabulated radial CDF for Sersic (SersicGeometry.cpp:44-62): rv[ntab], Xv[ntab] (host pointers) */
+    int ntab;
+    const double* rv;
+    const double* Xv;
+} skg_source;
+/* L[h*Nlambda+ell] = StellarComp::luminosity(ell) of component h */
+int skg_sources(skg_engine* e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias);
+
+/* ---- instruments: DistantInstrument / SingleFrameInstrument / Frame-, SED-, SimpleInstrument ---------- */
+enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3 };
+typedef struct skg_instrument
+{
+    int kind;
+    double distance, inclination, azimuth, positionAngle;       /* DistantInstrument.hpp */
+    int Nxp, Nyp;                                                /* SingleFrameInstrument */
+    double fovxp, fovyp, xpc, ypc;
+} skg_instrument;
+int skg_instruments(skg_engine* e, int n, const skg_instrument* instr);
+
+/* ---- photon shooting: MonteCarloSimulation::runstellaremission (MonteCarloSimulation.cpp:251-301) ------ */
+typedef struct skg_mc_params
+{
+    double packages;            /* packets per wavelength for THIS engine (the caller splits the budget over GPUs) */
+    double luminosityScale;     /* L per packet = luminosity(ell) / Npp_total ; pass Npp_total here */
+    double minWeightReduction;  /* MonteCarloSimulation.cpp:32, default 1e4 */
+    double minScattEvents;      /* default 0 */
+    double scattBias;           /* xi, default 0.5 */
+    int storeAbsorption;        /* DustSystem::storeabsorptionrates() */
+    uint64_t seed;              /* Philox key; replaces Random's seed (Random.cpp:21) */
+    uint64_t streamOffset;      /* first global packet index of this engine (disjoint Philox counters per GPU) */
+    int ellBegin, ellEnd;       /* wavelength range [ellBegin, ellEnd) to shoot */
+} skg_mc_params;
+typedef struct skg_mc_stats
+{
+    uint64_t packets;           /* launched */
+    uint64_t pathSegments;      /* packet-steps (addSegment calls) over all traversals */
+    uint64_t paths;             /* traversals (full, propagation and peel-off) */
+    uint64_t scatterings;
+    double kernel_ms;           /* device time of the shooting kernels (CUDA events) */
+} skg_mc_stats;
+int skg_run_stellar(skg_engine* e, const skg_mc_params* p, skg_mc_stats* stats);
+
+/* accumulators (replace LockFree::add targets: Instrument _ftotv/_Ftotv, DustSystem _Labsvv) */
+int skg_reset_results(skg_engine* e);
+/* frame cube [Nxp*Nyp*Nlambda] (index l + ell*Nframep, FrameInstrument.cpp:38-39), sed [Nlambda];
+ * add != 0: add into the host array (so that Instrument::write() runs unchanged afterwards) */
+int skg_fetch_frame(skg_engine* e, int instrument, double* frame, int add);
+int skg_fetch_sed(skg_engine* e, int instrument, double* sed, int add);
+int skg_fetch_labs(skg_engine* e, double* labs /* [Ncells*Nlambda] */, int add);
+/* device views of the accumulators, for collectives issued by the host (NCCL through torch.distributed) */
+int skg_device_accumulators(skg_engine* e, int which /*0 labs, 1.. instruments*/, int part /*0 frame,1 sed*/,
+                            double** d_ptr, int64_t* count);
+
+/* ---- multi-GPU: replaces ProcessManager::sum / sum_all (ProcessManager.cpp:122-140) ------------------- */
+/* NCCL communicator over one engine per GPU/process.  unique_id is the 128-byte ncclUniqueId that rank 0
+ * obtained from skg_comm_unique_id and distributed by any means (MPI_Bcast, torch.distributed, a file). */
+int skg_comm_unique_id(void* unique_id_128);
+int skg_comm_init(skg_engine* e, int rank, int nranks, const void* unique_id_128);
+/* in-place sum over all ranks of every accumulator (Labs table, frames, SEDs) on the engine's stream */
+int skg_allreduce_results(skg_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

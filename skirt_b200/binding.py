@@ -1,0 +1,295 @@
+"""ctypes binding of include/skirtgpu.h (the drop-in C ABI).  Host arrays are numpy; device arrays are
+passed as raw pointers (e.g. torch.Tensor.data_ptr()).  Every non-zero status becomes EngineError, the
+Python analogue of the reference adapter's `throw FATALERROR(msg)` (FatalError.hpp:47)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libskirtgpu.so")
+_lib = None
+
+SKG_HOST, SKG_DEVICE = 0, 1
+GEOM_EXPDISK, GEOM_SERSIC = 1, 2
+INSTR_FRAME, INSTR_SED, INSTR_SIMPLE = 1, 2, 3
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+class SkgSource(C.Structure):
+    _fields_ = [("geometry", C.c_int), ("p", C.c_double * 8),
+                ("spiral_arms", C.c_int), ("spiral_index", C.c_int),
+                ("spiral_pitch", C.c_double), ("spiral_radius", C.c_double),
+                ("spiral_phase", C.c_double), ("spiral_weight", C.c_double),
+                ("ntab", C.c_int), ("rv", C.c_void_p), ("Xv", C.c_void_p)]
+
+
+class SkgInstrument(C.Structure):
+    _fields_ = [("kind", C.c_int), ("distance", C.c_double), ("inclination", C.c_double),
+                ("azimuth", C.c_double), ("positionAngle", C.c_double),
+                ("Nxp", C.c_int), ("Nyp", C.c_int),
+                ("fovxp", C.c_double), ("fovyp", C.c_double), ("xpc", C.c_double), ("ypc", C.c_double)]
+
+
+class SkgMcParams(C.Structure):
+    _fields_ = [("packages", C.c_double), ("luminosityScale", C.c_double), ("minWeightReduction", C.c_double),
+                ("minScattEvents", C.c_double), ("scattBias", C.c_double), ("storeAbsorption", C.c_int),
+                ("seed", C.c_uint64), ("streamOffset", C.c_uint64), ("ellBegin", C.c_int), ("ellEnd", C.c_int)]
+
+
+class SkgMcStats(C.Structure):
+    _fields_ = [("packets", C.c_uint64), ("pathSegments", C.c_uint64), ("paths", C.c_uint64),
+                ("scatterings", C.c_uint64), ("kernel_ms", C.c_double)]
+
+
+def lib_available():
+    return os.path.exists(LIB_PATH)
+
+
+def load_library():
+    """Loads libskirtgpu.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise EngineError(f"{LIB_PATH} is missing: build it with `make` or __graft_entry__.build(); "
+                              "there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        L.skg_last_error.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))      # raw device pointer
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+class Engine:
+    """One engine per GPU (skg_engine).  Mirrors the call sequence of the reference's setup:
+    grid -> medium (DustSystem) -> sources (StellarSystem) -> instruments -> run."""
+
+    def __init__(self, device=0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        self._chk(self._lib.skg_engine_create(int(device), C.byref(h)))
+        self.h = h
+        self.device = device
+        self.Nlambda = 0
+        self._keep = []
+
+    def _chk(self, rc):
+        if rc:
+            raise EngineError(self._lib.skg_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self._lib.skg_engine_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- grids ---------------------------------------------------------------------------------
+    def grid_cartesian(self, xv, yv, zv):
+        xv, yv, zv = _f64(xv), _f64(yv), _f64(zv)
+        self._chk(self._lib.skg_grid_cartesian(self.h, _vp(xv), len(xv) - 1, _vp(yv), len(yv) - 1, _vp(zv), len(zv) - 1))
+
+    def grid_tree(self, kind, search, box, child0, parent, cell, dir=None, nbrStart=None, nbrIds=None):
+        box = _f64(box); child0 = _i32(child0); parent = _i32(parent); cell = _i32(cell)
+        dir = None if dir is None else _i32(dir)
+        nbrStart = None if nbrStart is None else _i32(nbrStart)
+        nbrIds = None if nbrIds is None else _i32(nbrIds if len(nbrIds) else [0])
+        self._chk(self._lib.skg_grid_tree(self.h, int(kind), int(search), len(child0), _vp(box), _vp(child0), _vp(parent),
+                                          _vp(cell), _vp(dir), _vp(nbrStart), _vp(nbrIds)))
+
+    def grid_amesh(self, box, nxyz, child0, cell, wallNbr):
+        box = _f64(box); nxyz = _i32(nxyz); child0 = _i32(child0); cell = _i32(cell); wallNbr = _i32(wallNbr)
+        self._chk(self._lib.skg_grid_amesh(self.h, len(child0), _vp(box), _vp(nxyz), _vp(child0), _vp(cell), _vp(wallNbr)))
+
+    def grid_voronoi(self, t):
+        a = {k: (_f64(v) if k in ("particles", "cellBox", "extent") else _i32(v) if isinstance(v, np.ndarray) else v)
+             for k, v in t.items()}
+        nkd = len(a["kdM"])
+        pad = lambda v: v if len(v) else np.zeros(1, np.int32)
+        self._chk(self._lib.skg_grid_voronoi(
+            self.h, len(a["particles"]), _vp(a["particles"]), _vp(a["nbrStart"]), _vp(pad(a["nbrIds"])), _vp(a["extent"]),
+            int(a["nb"]), _vp(a["blkStart"]), _vp(pad(a["blkIds"])), _vp(a["blkTree"]), nkd, _vp(pad(a["kdM"])),
+            _vp(pad(a["kdAxis"])), _vp(pad(a["kdUp"])), _vp(pad(a["kdLeft"])), _vp(pad(a["kdRight"])), _vp(a.get("cellBox"))))
+
+    def set_grid(self, t):
+        """t: dict in the layout produced by the host-side grid builders (kind + tables)."""
+        kind = t["kind"]
+        if kind == "cartesian":
+            self.grid_cartesian(t["xv"], t["yv"], t["zv"])
+        elif kind in ("octtree", "bintree"):
+            self.grid_tree(0 if kind == "octtree" else 1, t["search"], t["box"], t["child0"], t["parent"], t["cell"],
+                           t.get("dir"), t.get("nbrStart"), t.get("nbrIds"))
+        elif kind == "amesh":
+            self.grid_amesh(t["box"], t["nxyz"], t["child0"], t["cell"], t["wallNbr"])
+        elif kind == "voronoi":
+            self.grid_voronoi(t)
+        else:
+            raise EngineError(f"unknown grid kind {kind}")
+
+    @property
+    def Ncells(self):
+        return self._lib.skg_num_cells(self.h)
+
+    def medium(self, rho, kext, ksca=None, g=None):
+        rho = _f64(rho); kext = _f64(kext)
+        if rho.ndim == 1:
+            rho = rho[:, None]
+        kext = np.atleast_2d(kext)
+        Ncells, Ncomp = rho.shape
+        Nlambda = kext.shape[1]
+        ksca = None if ksca is None else _f64(np.atleast_2d(ksca))
+        g = None if g is None else _f64(np.atleast_2d(g))
+        self._chk(self._lib.skg_medium(self.h, Ncells, Ncomp, Nlambda, _vp(rho), _vp(kext), _vp(ksca), _vp(g)))
+        self.Nlambda = Nlambda
+        self.Ncomp = Ncomp
+
+    # ---- deterministic geometry ------------------------------------------------------------------
+    def path_batch(self, r, k, ell=None):
+        """Batched DustGrid::path()+fillOpticalDepth() for host rays -> CSR dict (numpy)."""
+        r = _f64(r).reshape(-1, 3); k = _f64(k).reshape(-1, 3); n = len(r)
+        off = np.zeros(n + 1, np.int64); total = C.c_int64()
+        self._chk(self._lib.skg_path_count(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), _vp(off), C.byref(total)))
+        t = max(total.value, 1)
+        m = np.zeros(t, np.int32); ds = np.zeros(t); s = np.zeros(t); dtau = np.zeros(t); tau = np.zeros(t)
+        ellp, stride = None, 0
+        if ell is not None:
+            ella = _i32(np.atleast_1d(ell)); ellp = _vp(ella); stride = 1 if len(ella) == n and n > 1 else 0
+            if len(ella) not in (1, n):
+                raise EngineError("ell must be a scalar or have one entry per ray")
+        self._chk(self._lib.skg_path_fill(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), ellp, stride, _vp(off),
+                                          _vp(m), _vp(ds), _vp(s), _vp(dtau), _vp(tau)))
+        tt = total.value
+        return dict(offsets=off, m=m[:tt], ds=ds[:tt], s=s[:tt], dtau=dtau[:tt], tau=tau[:tt])
+
+    def path_count_device(self, n, d_r, d_k, d_offsets):
+        total = C.c_int64()
+        self._chk(self._lib.skg_path_count(self.h, SKG_DEVICE, C.c_int64(n), _vp(d_r), _vp(d_k), _vp(d_offsets), C.byref(total)))
+        return total.value
+
+    def path_fill_device(self, n, d_r, d_k, d_ell, ell_stride, d_offsets, d_m, d_ds, d_s, d_dtau, d_tau):
+        self._chk(self._lib.skg_path_fill(self.h, SKG_DEVICE, C.c_int64(n), _vp(d_r), _vp(d_k), _vp(d_ell), int(ell_stride),
+                                          _vp(d_offsets), _vp(d_m), _vp(d_ds), _vp(d_s), _vp(d_dtau), _vp(d_tau)))
+
+    def opticaldepth(self, r, k, ell, distance=None):
+        r = _f64(r).reshape(-1, 3); k = _f64(k).reshape(-1, 3); n = len(r)
+        ella = _i32(np.atleast_1d(ell)); stride = 1 if len(ella) == n and n > 1 else 0
+        d = None if distance is None else _f64(distance)
+        tau = np.zeros(n)
+        self._chk(self._lib.skg_opticaldepth(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), _vp(ella), stride, _vp(d), _vp(tau)))
+        return tau
+
+    def whichcell(self, r):
+        r = _f64(r).reshape(-1, 3); m = np.zeros(len(r), np.int32)
+        self._chk(self._lib.skg_whichcell(self.h, SKG_HOST, C.c_int64(len(r)), _vp(r), _vp(m)))
+        return m
+
+    def stuck_counts(self):
+        a = C.c_int64(); b = C.c_int64()
+        self._chk(self._lib.skg_stuck_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    # ---- Monte Carlo -----------------------------------------------------------------------------
+    def sources(self, comps, L, emission_bias=0.5):
+        """comps: list of dicts(geometry=..., p=[...], spiral=dict|None, rv=..., Xv=...); L[Ncomp, Nlambda]."""
+        L = _f64(np.atleast_2d(L))
+        arr = (SkgSource * len(comps))()
+        keep = []
+        for i, c in enumerate(comps):
+            s = arr[i]
+            s.geometry = int(c["geometry"])
+            p = list(c.get("p", [])) + [0.0] * 8
+            for j in range(8):
+                s.p[j] = float(p[j])
+            sp = c.get("spiral")
+            if sp:
+                s.spiral_arms = int(sp["arms"]); s.spiral_index = int(sp["index"]); s.spiral_pitch = float(sp["pitch"])
+                s.spiral_radius = float(sp["radius"]); s.spiral_phase = float(sp["phase"]); s.spiral_weight = float(sp["weight"])
+            if c.get("rv") is not None:
+                rv = _f64(c["rv"]); Xv = _f64(c["Xv"]); keep += [rv, Xv]
+                s.ntab = len(rv); s.rv = rv.ctypes.data; s.Xv = Xv.ctypes.data
+        self._chk(self._lib.skg_sources(self.h, len(comps), arr, L.shape[1], _vp(L), C.c_double(emission_bias)))
+
+    def instruments(self, instr):
+        arr = (SkgInstrument * len(instr))()
+        for i, d in enumerate(instr):
+            a = arr[i]
+            a.kind = int(d["kind"]); a.distance = float(d["distance"]); a.inclination = float(d["inclination"])
+            a.azimuth = float(d.get("azimuth", 0.0)); a.positionAngle = float(d.get("positionAngle", 0.0))
+            a.Nxp = int(d.get("Nxp", 0)); a.Nyp = int(d.get("Nyp", 0))
+            a.fovxp = float(d.get("fovxp", 0.0)); a.fovyp = float(d.get("fovyp", 0.0))
+            a.xpc = float(d.get("xpc", 0.0)); a.ypc = float(d.get("ypc", 0.0))
+        self._instr = list(instr)
+        self._chk(self._lib.skg_instruments(self.h, len(instr), arr))
+
+    def run_stellar(self, packages, total_packages=None, min_weight_reduction=1e4, min_scatt_events=0.0, scatt_bias=0.5,
+                    store_absorption=False, seed=4357, stream_offset=0, ell_begin=0, ell_end=None):
+        p = SkgMcParams()
+        p.packages = float(packages)
+        p.luminosityScale = float(total_packages if total_packages is not None else packages)
+        p.minWeightReduction = float(min_weight_reduction); p.minScattEvents = float(min_scatt_events)
+        p.scattBias = float(scatt_bias); p.storeAbsorption = int(bool(store_absorption))
+        p.seed = int(seed); p.streamOffset = int(stream_offset)
+        p.ellBegin = int(ell_begin); p.ellEnd = int(self.Nlambda if ell_end is None else ell_end)
+        st = SkgMcStats()
+        self._chk(self._lib.skg_run_stellar(self.h, C.byref(p), C.byref(st)))
+        return dict(packets=st.packets, pathSegments=st.pathSegments, paths=st.paths, scatterings=st.scatterings,
+                    kernel_ms=st.kernel_ms)
+
+    def reset_results(self):
+        self._chk(self._lib.skg_reset_results(self.h))
+
+    def fetch_frame(self, i):
+        d = self._instr[i]
+        a = np.zeros(int(d["Nxp"]) * int(d["Nyp"]) * self.Nlambda)
+        self._chk(self._lib.skg_fetch_frame(self.h, i, _vp(a), 0))
+        return a
+
+    def fetch_sed(self, i):
+        a = np.zeros(self.Nlambda)
+        self._chk(self._lib.skg_fetch_sed(self.h, i, _vp(a), 0))
+        return a
+
+    def fetch_labs(self):
+        a = np.zeros((self.Ncells, self.Nlambda))
+        self._chk(self._lib.skg_fetch_labs(self.h, _vp(a), 0))
+        return a
+
+    def device_accumulator(self, which, part=0):
+        p = C.c_void_p(); n = C.c_int64()
+        self._chk(self._lib.skg_device_accumulators(self.h, int(which), int(part), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    # ---- multi-GPU -----------------------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = np.zeros(128, np.uint8)
+        self._chk(self._lib.skg_comm_unique_id(_vp(buf)))
+        return buf
+
+    def comm_init(self, rank, nranks, unique_id):
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        self._chk(self._lib.skg_comm_init(self.h, int(rank), int(nranks), _vp(uid)))
+
+    def allreduce_results(self):
+        self._chk(self._lib.skg_allreduce_results(self.h))

@@ -1,0 +1,385 @@
+// Engine object + C ABI (include/skirtgpu.h).  Product path: fails loudly without a CUDA device; there is
+// no CPU fallback and nothing here touches oracle/.
+#include <cmath>
+#include <cstring>
+#include <string>
+#include "engine.h"
+
+namespace skg
+{
+
+static thread_local std::string g_lastError;
+
+Engine::Engine(int dev) : device(dev)
+{
+    int count = 0;
+    cudaError_t err = cudaGetDeviceCount(&count);
+    if (err != cudaSuccess || count == 0)
+        throw Error(std::string("no CUDA device available (") + cudaGetErrorString(err) + "); the engine has no CPU fallback");
+    if (dev < 0 || dev >= count) throw Error("invalid CUDA device index " + std::to_string(dev));
+    SKG_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop; SKG_CUDA(cudaGetDeviceProperties(&prop, dev));
+    smCount = prop.multiProcessorCount;
+    SKG_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    counters.ensure(sizeof(Counters));
+    SKG_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(Counters), stream));
+    sync();
+}
+
+Engine::~Engine()
+{
+    cudaSetDevice(device);
+    freeGrid();
+    for (DevBuf* b : sourceBufs) delete b;
+    for (DevBuf* b : instrBufs) delete b;
+    if (stream) cudaStreamDestroy(stream);
+}
+
+void Engine::freeGrid()
+{
+    for (DevBuf* b : gridBufs) delete b;
+    gridBufs.clear();
+    gridKind = GRID_NONE; Ncells = 0;
+}
+
+Counters Engine::readCounters()
+{
+    Counters c;
+    SKG_CUDA(cudaMemcpyAsync(&c, counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
+    sync();
+    return c;
+}
+
+template<class T> static const T* up(Engine& e, const T* host, size_t n)
+{
+    DevBuf* b = new DevBuf(); e.gridBufs.push_back(b);
+    b->upload(host, n * sizeof(T), e.stream);
+    return b->as<T>();
+}
+
+// eps = 1e-12 * extent.widths().norm(), TreeDustGrid.cpp:76 / VoronoiMesh.cpp:234 / AdaptiveMesh.cpp:52
+static double epsFor(double wx, double wy, double wz)
+{
+    volatile double a = wx * wx, b = wy * wy, c = wz * wz;   // no contraction
+    volatile double sum = a + b; sum = sum + c;
+    return 1e-12 * std::sqrt(sum);
+}
+
+}   // namespace skg
+
+using namespace skg;
+
+template<class F> static int guarded(F f)
+{
+    try { f(); return 0; }
+    catch (std::exception& ex) { g_lastError = ex.what(); }
+    catch (...) { g_lastError = "unknown error"; }
+    return 1;
+}
+
+static Engine& E(skg_engine* e)
+{
+    if (!e) throw Error("null engine");
+    Engine& en = *reinterpret_cast<Engine*>(e);
+    SKG_CUDA(cudaSetDevice(en.device));
+    return en;
+}
+
+extern "C"
+{
+
+const char* skg_last_error(void) { return g_lastError.c_str(); }
+int skg_version(void) { return 1; }
+
+int skg_engine_create(int device, skg_engine** out)
+{
+    return guarded([&]{ if (!out) throw Error("null out pointer"); *out = reinterpret_cast<skg_engine*>(new Engine(device)); });
+}
+
+void skg_engine_destroy(skg_engine* e) { delete reinterpret_cast<Engine*>(e); }
+
+int skg_num_cells(skg_engine* e) { return e ? reinterpret_cast<Engine*>(e)->Ncells : 0; }
+
+int skg_grid_cartesian(skg_engine* eh, const double* xv, int Nx, const double* yv, int Ny, const double* zv, int Nz)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (Nx < 1 || Ny < 1 || Nz < 1 || !xv || !yv || !zv) throw Error("cartesian grid needs at least one bin per axis");
+        if ((int64_t)Nx * Ny * Nz > 2147483647LL) throw Error("too many cells for int32 cell numbers");
+        for (int i = 0; i < Nx; i++) if (!(xv[i] < xv[i+1])) throw Error("x borders must be strictly ascending");
+        for (int i = 0; i < Ny; i++) if (!(yv[i] < yv[i+1])) throw Error("y borders must be strictly ascending");
+        for (int i = 0; i < Nz; i++) if (!(zv[i] < zv[i+1])) throw Error("z borders must be strictly ascending");
+        e.freeGrid();
+        e.cart.xv = up(e, xv, Nx + 1); e.cart.yv = up(e, yv, Ny + 1); e.cart.zv = up(e, zv, Nz + 1);
+        e.cart.Nx = Nx; e.cart.Ny = Ny; e.cart.Nz = Nz;
+        // BoxDustGrid extent: for every Mesh of the reference mesh[0]=0 and mesh[N]=1, so that the borders'
+        // end points equal the extent (CartesianDustGrid.cpp:34-36)
+        e.cart.ext[0] = xv[0]; e.cart.ext[1] = xv[Nx]; e.cart.ext[2] = yv[0]; e.cart.ext[3] = yv[Ny]; e.cart.ext[4] = zv[0]; e.cart.ext[5] = zv[Nz];
+        e.gridKind = GRID_CART; e.Ncells = Nx * Ny * Nz;
+        e.sync();
+    });
+}
+
+int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box, const int* child0,
+                  const int* parent, const int* cell, const int* dir, const int* nbrStart, const int* nbrIds)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (N < 1 || !box || !child0 || !parent || !cell) throw Error("tree grid tables missing");
+        if (kind != 0 && kind != 1) throw Error("tree kind must be 0 (octree) or 1 (binary tree)");
+        if (search < 0 || search > 2) throw Error("invalid search method");
+        if (search == 2 && kind != 0) throw Error("Bookkeeping method is not compatible with binary tree");   // BinTreeDustGrid.cpp:19-25
+        if (search == 1 && (!nbrStart || !nbrIds)) throw Error("Neighbor search needs the neighbour lists");
+        if (kind == 1 && !dir) throw Error("binary tree needs the split directions");
+        int nchild = kind == 0 ? 8 : 2; int ncells = 0;
+        for (int l = 0; l < N; l++)
+        {
+            if (child0[l] >= 0 && (child0[l] <= l || child0[l] + nchild > N)) throw Error("invalid child index in tree tables");
+            if (cell[l] >= 0) ncells++;
+            if ((child0[l] < 0) != (cell[l] >= 0)) throw Error("leaf/cell tables are inconsistent");
+        }
+        e.freeGrid();
+        e.tree.box = up(e, box, 6 * (size_t)N); e.tree.child0 = up(e, child0, N); e.tree.parent = up(e, parent, N);
+        e.tree.cell = up(e, cell, N);
+        std::vector<int> zeros; if (!dir) { zeros.assign(N, 0); dir = zeros.data(); }
+        e.tree.dir = up(e, dir, N);
+        if (search == 1) { e.tree.nbrStart = up(e, nbrStart, 6 * (size_t)N + 1); e.tree.nbrIds = up(e, nbrIds, (size_t)std::max(1, nbrStart[6 * (size_t)N])); }
+        else { e.tree.nbrStart = nullptr; e.tree.nbrIds = nullptr; }
+        e.tree.N = N; e.tree.kind = kind; e.tree.search = search;
+        e.tree.eps = epsFor(box[3] - box[0], box[4] - box[1], box[5] - box[2]);
+        e.gridKind = GRID_TREE; e.Ncells = ncells;
+        e.sync();
+    });
+}
+
+int skg_grid_amesh(skg_engine* eh, int N, const double* box, const int* nxyz, const int* child0, const int* cell, const int* wallNbr)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (N < 1 || !box || !nxyz || !child0 || !cell || !wallNbr) throw Error("adaptive mesh tables missing");
+        int ncells = 0;
+        for (int l = 0; l < N; l++)
+        {
+            if (cell[l] >= 0) ncells++;
+            if (child0[l] >= 0)
+            {
+                int64_t nc = (int64_t)nxyz[3*l] * nxyz[3*l+1] * nxyz[3*l+2];
+                if (nc < 1 || child0[l] <= l || child0[l] + nc > N) throw Error("invalid child index in adaptive mesh tables");
+            }
+        }
+        e.freeGrid();
+        e.amesh.box = up(e, box, 6 * (size_t)N); e.amesh.nxyz = up(e, nxyz, 3 * (size_t)N); e.amesh.child0 = up(e, child0, N);
+        e.amesh.cell = up(e, cell, N); e.amesh.wallNbr = up(e, wallNbr, 6 * (size_t)N);
+        e.amesh.N = N;
+        e.amesh.eps = epsFor(box[3] - box[0], box[4] - box[1], box[5] - box[2]);
+        e.gridKind = GRID_AMESH; e.Ncells = ncells;
+        e.sync();
+    });
+}
+
+int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* nbrStart, const int* nbrIds,
+                     const double* extent, int nb, const int* blkStart, const int* blkIds, const int* blkTree,
+                     int Nkd, const int* kdM, const int* kdAxis, const int* kdUp, const int* kdLeft,
+                     const int* kdRight, const double* cellBox)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (N < 1 || !particles || !nbrStart || !nbrIds || !extent || nb < 1 || !blkStart || !blkIds || !blkTree)
+            throw Error("voronoi tables missing");
+        size_t nb3 = (size_t)nb * nb * nb;
+        e.freeGrid();
+        e.voro.particles = up(e, particles, 3 * (size_t)N);
+        e.voro.nbrStart = up(e, nbrStart, (size_t)N + 1); e.voro.nbrIds = up(e, nbrIds, (size_t)std::max(1, nbrStart[N]));
+        e.voro.blkStart = up(e, blkStart, nb3 + 1); e.voro.blkIds = up(e, blkIds, (size_t)std::max(1, blkStart[nb3]));
+        e.voro.blkTree = up(e, blkTree, nb3);
+        int one = -1; size_t nk = (size_t)std::max(1, Nkd);
+        e.voro.kdM = up(e, Nkd ? kdM : &one, nk); e.voro.kdAxis = up(e, Nkd ? kdAxis : &one, nk); e.voro.kdUp = up(e, Nkd ? kdUp : &one, nk);
+        e.voro.kdLeft = up(e, Nkd ? kdLeft : &one, nk); e.voro.kdRight = up(e, Nkd ? kdRight : &one, nk);
+        e.voro.cellBox = cellBox ? up(e, cellBox, 6 * (size_t)N) : nullptr;
+        // extent arrives as xmin,xmax,ymin,ymax,zmin,zmax (Box setters order); stored as min corner, max corner
+        e.voro.ext[0] = extent[0]; e.voro.ext[1] = extent[2]; e.voro.ext[2] = extent[4];
+        e.voro.ext[3] = extent[1]; e.voro.ext[4] = extent[3]; e.voro.ext[5] = extent[5];
+        e.voro.eps = epsFor(extent[1] - extent[0], extent[3] - extent[2], extent[5] - extent[4]);
+        e.voro.N = N; e.voro.nb = nb;
+        e.gridKind = GRID_VORO; e.Ncells = N;
+        e.sync();
+    });
+}
+
+int skg_medium(skg_engine* eh, int Ncells, int Ncomp, int Nlambda, const double* rho, const double* kext, const double* ksca, const double* g)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (Ncells < 1 || Ncomp < 1 || Nlambda < 1 || !rho || !kext) throw Error("medium tables missing");
+        if (e.gridKind != GRID_NONE && Ncells != e.Ncells) throw Error("medium has " + std::to_string(Ncells) + " cells but the grid has " + std::to_string(e.Ncells));
+        e.rho.upload(rho, sizeof(double) * (size_t)Ncells * Ncomp, e.stream);
+        e.kext.upload(kext, sizeof(double) * (size_t)Ncomp * Nlambda, e.stream);
+        std::vector<double> zeros((size_t)Ncomp * Nlambda, 0.0);
+        e.ksca.upload(ksca ? ksca : zeros.data(), sizeof(double) * (size_t)Ncomp * Nlambda, e.stream);
+        e.gasym.upload(g ? g : zeros.data(), sizeof(double) * (size_t)Ncomp * Nlambda, e.stream);
+        e.med.rho = e.rho.as<double>(); e.med.kext = e.kext.as<double>(); e.med.ksca = e.ksca.as<double>(); e.med.g = e.gasym.as<double>();
+        e.med.Ncells = Ncells; e.med.Ncomp = Ncomp; e.med.Nlambda = Nlambda;
+        e.sync();
+    });
+}
+
+// ---- deterministic geometry ---------------------------------------------------------------------------
+int skg_path_count(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, int64_t* offsets, int64_t* total)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (n < 0 || (n > 0 && (!r || !k)) || !offsets) throw Error("skg_path_count: bad arguments");
+        const double* d_r = r; const double* d_k = k; int64_t* d_off = offsets;
+        if (mem == SKG_HOST)
+        {
+            e.scratchR.upload(r, sizeof(double) * 3 * (size_t)n, e.stream); e.scratchK.upload(k, sizeof(double) * 3 * (size_t)n, e.stream);
+            e.scratchOffsets.ensure(sizeof(int64_t) * ((size_t)n + 1));
+            d_r = e.scratchR.as<double>(); d_k = e.scratchK.as<double>(); d_off = e.scratchOffsets.as<int64_t>();
+        }
+        e.scratchCounts.ensure(sizeof(int) * (size_t)std::max<int64_t>(n, 1));
+        launchPathCount(e, n, d_r, d_k, e.scratchCounts.as<int>());
+        exclusiveScan(e, n, e.scratchCounts.as<int>(), d_off);
+        int64_t tot = 0;
+        if (mem == SKG_HOST) SKG_CUDA(cudaMemcpyAsync(offsets, d_off, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, e.stream));
+        if (total || mem == SKG_HOST) SKG_CUDA(cudaMemcpyAsync(&tot, d_off + n, sizeof(int64_t), cudaMemcpyDeviceToHost, e.stream));
+        e.sync();
+        if (total) *total = tot;
+    });
+}
+
+int skg_path_fill(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
+                  const int64_t* offsets, int* m, double* ds, double* s, double* dtau, double* tau)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (n < 0 || (n > 0 && (!r || !k)) || !offsets) throw Error("skg_path_fill: bad arguments");
+        if (ellStride != 0 && ellStride != 1) throw Error("ell_stride must be 0 or 1");
+        if (mem == SKG_DEVICE)
+        {
+            if (!m || !ds || !s || !dtau || !tau) throw Error("skg_path_fill: null output");
+            launchPathFill(e, n, r, k, ell, ellStride, offsets, m, ds, s, dtau, tau);
+            e.sync();
+            return;
+        }
+        int64_t total = n > 0 ? offsets[n] : 0;
+        if (total > 0 && (!m || !ds || !s || !dtau || !tau)) throw Error("skg_path_fill: null output");
+        e.scratchR.upload(r, sizeof(double) * 3 * (size_t)n, e.stream); e.scratchK.upload(k, sizeof(double) * 3 * (size_t)n, e.stream);
+        e.scratchOffsets.upload(offsets, sizeof(int64_t) * ((size_t)n + 1), e.stream);
+        const int* d_ell = nullptr;
+        if (ell) { e.scratchEll.upload(ell, sizeof(int) * (size_t)(ellStride ? n : 1), e.stream); d_ell = e.scratchEll.as<int>(); }
+        if (ell) for (int64_t i = 0; i < (ellStride ? n : 1); i++) if (ell[i] < 0 || ell[i] >= e.med.Nlambda) throw Error("wavelength index out of range");
+        size_t t = (size_t)std::max<int64_t>(total, 1);
+        e.scratchM.ensure(sizeof(int) * t);
+        for (int j = 0; j < 4; j++) e.scratchOut[j].ensure(sizeof(double) * t);
+        launchPathFill(e, n, e.scratchR.as<double>(), e.scratchK.as<double>(), d_ell, ellStride, e.scratchOffsets.as<int64_t>(),
+                       e.scratchM.as<int>(), e.scratchOut[0].as<double>(), e.scratchOut[1].as<double>(), e.scratchOut[2].as<double>(), e.scratchOut[3].as<double>());
+        if (total > 0)
+        {
+            SKG_CUDA(cudaMemcpyAsync(m, e.scratchM.p, sizeof(int) * total, cudaMemcpyDeviceToHost, e.stream));
+            double* outs[4] = {ds, s, dtau, tau};
+            for (int j = 0; j < 4; j++) SKG_CUDA(cudaMemcpyAsync(outs[j], e.scratchOut[j].p, sizeof(double) * total, cudaMemcpyDeviceToHost, e.stream));
+        }
+        e.sync();
+    });
+}
+
+int skg_opticaldepth(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
+                     const double* distance, double* tau)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (n < 0 || (n > 0 && (!r || !k || !tau || !ell))) throw Error("skg_opticaldepth: bad arguments");
+        if (ellStride != 0 && ellStride != 1) throw Error("ell_stride must be 0 or 1");
+        if (mem == SKG_DEVICE) { launchOpticalDepth(e, n, r, k, ell, ellStride, distance, tau); e.sync(); return; }
+        for (int64_t i = 0; i < (ellStride ? n : 1); i++) if (ell[i] < 0 || ell[i] >= e.med.Nlambda) throw Error("wavelength index out of range");
+        e.scratchR.upload(r, sizeof(double) * 3 * (size_t)n, e.stream); e.scratchK.upload(k, sizeof(double) * 3 * (size_t)n, e.stream);
+        e.scratchEll.upload(ell, sizeof(int) * (size_t)(ellStride ? n : 1), e.stream);
+        const double* d_dist = nullptr;
+        if (distance) { e.scratchDist.upload(distance, sizeof(double) * (size_t)n, e.stream); d_dist = e.scratchDist.as<double>(); }
+        e.scratchTau.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
+        launchOpticalDepth(e, n, e.scratchR.as<double>(), e.scratchK.as<double>(), e.scratchEll.as<int>(), ellStride, d_dist, e.scratchTau.as<double>());
+        if (n > 0) SKG_CUDA(cudaMemcpyAsync(tau, e.scratchTau.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+        e.sync();
+    });
+}
+
+int skg_whichcell(skg_engine* eh, int mem, int64_t n, const double* r, int* m)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (n < 0 || (n > 0 && (!r || !m))) throw Error("skg_whichcell: bad arguments");
+        if (mem == SKG_DEVICE) { launchWhichCell(e, n, r, m); e.sync(); return; }
+        e.scratchR.upload(r, sizeof(double) * 3 * (size_t)n, e.stream);
+        e.scratchM.ensure(sizeof(int) * (size_t)std::max<int64_t>(n, 1));
+        launchWhichCell(e, n, e.scratchR.as<double>(), e.scratchM.as<int>());
+        if (n > 0) SKG_CUDA(cudaMemcpyAsync(m, e.scratchM.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+        e.sync();
+    });
+}
+
+int skg_stuck_counts(skg_engine* eh, int64_t* escaped, int64_t* terminated)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        Counters c = e.readCounters();
+        if (escaped) *escaped = (int64_t)c.stuckEscaped;
+        if (terminated) *terminated = (int64_t)c.stuckTerminated;
+    });
+}
+
+// ---- Monte Carlo -----------------------------------------------------------------------------------------
+int skg_sources(skg_engine* eh, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias)
+{ return guarded([&]{ mcSetSources(E(eh), Ncomp, comps, Nlambda, L, emissionBias); }); }
+int skg_instruments(skg_engine* eh, int n, const skg_instrument* instr)
+{ return guarded([&]{ mcSetInstruments(E(eh), n, instr); }); }
+int skg_run_stellar(skg_engine* eh, const skg_mc_params* p, skg_mc_stats* stats)
+{ return guarded([&]{ if (!p) throw Error("null parameters"); mcRunStellar(E(eh), *p, stats); }); }
+int skg_reset_results(skg_engine* eh) { return guarded([&]{ mcResetResults(E(eh)); }); }
+
+static void fetchArray(Engine& e, const double* d_src, int64_t count, double* host, int add)
+{
+    if (!host) throw Error("null host array");
+    if (!add) { SKG_CUDA(cudaMemcpyAsync(host, d_src, sizeof(double) * count, cudaMemcpyDeviceToHost, e.stream)); e.sync(); return; }
+    std::vector<double> tmp(count);
+    SKG_CUDA(cudaMemcpyAsync(tmp.data(), d_src, sizeof(double) * count, cudaMemcpyDeviceToHost, e.stream)); e.sync();
+    for (int64_t i = 0; i < count; i++) host[i] += tmp[i];
+}
+
+int skg_fetch_frame(skg_engine* eh, int i, double* frame, int add)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].frame) throw Error("instrument has no frame");
+        fetchArray(e, e.instr[i].frame, (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.med.Nlambda, frame, add);
+    });
+}
+int skg_fetch_sed(skg_engine* eh, int i, double* sed, int add)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].sed) throw Error("instrument has no SED");
+        fetchArray(e, e.instr[i].sed, e.med.Nlambda, sed, add);
+    });
+}
+int skg_fetch_labs(skg_engine* eh, double* labs, int add)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (!e.labs.p || e.labsCount == 0) throw Error("absorption rates were not stored");
+        fetchArray(e, e.labs.as<double>(), e.labsCount, labs, add);
+    });
+}
+int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr, int64_t* count)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (!d_ptr || !count) throw Error("null output");
+        if (which == 0) { *d_ptr = e.labs.as<double>(); *count = e.labsCount; return; }
+        int i = which - 1;
+        if (i < 0 || i >= (int)e.instr.size()) throw Error("instrument index out of range");
+        if (part == 0) { *d_ptr = e.instr[i].frame; *count = e.instr[i].frame ? (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.med.Nlambda : 0; }
+        else { *d_ptr = e.instr[i].sed; *count = e.instr[i].sed ? e.med.Nlambda : 0; }
+    });
+}
+
+}   // extern "C"

@@ -1,0 +1,97 @@
+// Host-side engine object behind the C ABI of include/skirtgpu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/skirtgpu.h"
+#include "tables.h"
+
+namespace skg
+{
+
+struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
+
+#define SKG_CUDA(call) do { cudaError_t err__ = (call); if (err__ != cudaSuccess) \
+    throw skg::Error(std::string(#call) + ": " + cudaGetErrorString(err__)); } while (0)
+
+// owning device allocation
+struct DevBuf
+{
+    void* p = nullptr; size_t bytes = 0;
+    DevBuf() {}
+    DevBuf(const DevBuf&) = delete; DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+    void ensure(size_t n) { if (n > bytes) { release(); SKG_CUDA(cudaMalloc(&p, n ? n : 1)); bytes = n; } }
+    void upload(const void* host, size_t n, cudaStream_t st)
+    { ensure(n); if (n) SKG_CUDA(cudaMemcpyAsync(p, host, n, cudaMemcpyHostToDevice, st)); }
+    template<class T> T* as() const { return static_cast<T*>(p); }
+};
+
+// sampler tables for one stellar component on the device
+struct SourceDev
+{
+    int geometry; double p[8];
+    int spiral_arms, spiral_index; double spiral_pitch, spiral_radius, spiral_phase, spiral_weight;
+    double spiral_c, spiral_tanp, spiral_cn;    // derived constants (SpiralStructureGeometryDecorator.cpp:24-45)
+    int ntab; const double* rv; const double* Xv;
+};
+
+struct InstrDev
+{
+    int kind;
+    double costheta, sintheta, cosphi, sinphi, cospa, sinpa;
+    double kobsx, kobsy, kobsz;
+    int Nxp, Nyp; double xpmin, ypmin, xpsiz, ypsiz;
+    double* frame; double* sed;     // device accumulators (frame: Nxp*Nyp*Nlambda, sed: Nlambda)
+};
+
+struct Engine
+{
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int smCount = 148;
+
+    int gridKind = GRID_NONE;
+    CartGrid cart{}; TreeGrid tree{}; AMeshGrid amesh{}; VoroGrid voro{};
+    int Ncells = 0;
+    std::vector<DevBuf*> gridBufs;
+    Medium med{};
+    DevBuf rho, kext, ksca, gasym;
+    DevBuf counters;                    // Counters
+    DevBuf scratchR, scratchK, scratchEll, scratchDist, scratchCounts, scratchOffsets, scratchCub, scratchOut[5], scratchTau, scratchM;
+
+    // Monte Carlo state
+    int Nsources = 0; int NlambdaSrc = 0; double emissionBias = 0.5;
+    std::vector<SourceDev> sources; DevBuf sourcesDev, lumDev, lumCdfDev, lumTotDev; std::vector<DevBuf*> sourceBufs;
+    std::vector<double> lumHost, lumTotHost;
+    std::vector<InstrDev> instr; DevBuf instrDev; std::vector<DevBuf*> instrBufs;
+    DevBuf labs; int64_t labsCount = 0;
+    void* nccl = nullptr; int rank = 0, nranks = 1;
+
+    explicit Engine(int dev);
+    ~Engine();
+    void freeGrid();
+    Counters* ctr() { return counters.as<Counters>(); }
+    Counters readCounters();
+    void sync() { SKG_CUDA(cudaStreamSynchronize(stream)); }
+};
+
+// kernels launchers (path_kernels.cu)
+void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k, int* d_counts);
+void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
+                    const int64_t* d_offsets, int* d_m, double* d_ds, double* d_s, double* d_dtau, double* d_tau);
+void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
+                        const double* d_dist, double* d_tau);
+void launchWhichCell(Engine& e, int64_t n, const double* d_r, int* d_m);
+void exclusiveScan(Engine& e, int64_t n, const int* d_counts, int64_t* d_offsets);   // writes n+1 offsets
+
+// Monte Carlo (mc_kernels.cu)
+void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias);
+void mcSetInstruments(Engine& e, int n, const skg_instrument* instr);
+void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats);
+void mcResetResults(Engine& e);
+
+}   // namespace skg

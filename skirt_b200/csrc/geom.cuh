@@ -1,0 +1,696 @@
+// Grid traversal device functions: one "walk" per grid type, each a restructured-for-GPU rendition of
+// the reference's DustGrid::path() that feeds segments to a Sink instead of a std::vector.
+//
+// Bit-exactness contract: compiled with -fmad=false, IEEE division, the reference's
+// operand order, comparison asymmetries and eps conventions, so that cell sequences are identical and
+// ds/s/dtau/tau agree to the last bit with the reference built without FMA contraction.
+//
+//   Cartesian      CartesianDustGrid.cpp:136-283 (+ NR::locate_clip, NR.hpp:99-112,146-151)
+//   Tree           TreeDustGrid.cpp:390-662 (+ DustGridPath::moveInside DustGridPath.cpp:57-150,
+//                  TreeNode::whichnode TreeNode.cpp:70-93, OctTreeNode::child OctTreeNode.cpp:184-189,
+//                  BinTreeNode::child BinTreeNode.cpp:326-335)
+//   AdaptiveMesh   AdaptiveMesh.cpp:297-367 (+ AdaptiveMeshNode.cpp:109-151, Box::cellindices Box.hpp:134-139)
+//   Voronoi        VoronoiMesh.cpp:749-844 (+ cellIndex :512-541, kd Node::nearest :180-225)
+//
+// A Sink provides `bool add(int m, double ds)` with DustGridPath::addSegment semantics handled by the
+// caller-side helper sinkAdd(): segments with ds<=0 are dropped (DustGridPath.cpp:46-53).  add()
+// returns false to stop the walk early (propagation target reached / distance exceeded).
+#pragma once
+#include <cfloat>
+#include <cmath>
+#include "tables.h"
+
+namespace skg
+{
+
+#define SKG_DBL_MAX 1.7976931348623157e308
+
+// ---------------------------------------------------------------------------------------------------
+// pending "outside" segments: the reference adds up to three m=-1 segments while moving a ray into
+// the grid and clears them again if the ray turns out to miss the grid; we hold them back until the
+// entry is confirmed.
+struct Entry
+{
+    double ds[3];
+    int n;
+};
+
+template<class Sink> __device__ __forceinline__ bool flushEntry(const Entry& en, Sink& sink)
+{
+    for (int i = 0; i < en.n; i++)
+        if (en.ds[i] > 0) { if (!sink.add(-1, en.ds[i])) return false; }
+    return true;
+}
+
+__device__ __forceinline__ bool finite3(double a, double b, double c)
+{
+    return isfinite(a) && isfinite(b) && isfinite(c);
+}
+
+// NR::locate_basic_impl, NR.hpp:99-112
+__device__ __forceinline__ int locateBasic(const double* xv, double x, int n)
+{
+    int jl = -1, ju = n;
+    while (ju - jl > 1)
+    {
+        int jm = (ju + jl) >> 1;
+        if (x < xv[jm]) ju = jm; else jl = jm;
+    }
+    return jl;
+}
+// NR::locate_clip over an array of n values, NR.hpp:146-151
+__device__ __forceinline__ int locateClip(const double* xv, double x, int n)
+{
+    if (x < xv[0]) return 0;
+    return locateBasic(xv, x, n - 1);
+}
+// NR::locate_fail, NR.hpp:155-160
+__device__ __forceinline__ int locateFail(const double* xv, double x, int n)
+{
+    if (x > xv[n - 1]) return -1;
+    return locateBasic(xv, x, n - 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Cartesian
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cartWhichCell(const CartGrid& g, double x, double y, double z)
+{
+    // CartesianDustGrid::whichcell, CartesianDustGrid.cpp:109-118
+    int i = locateFail(g.xv, x, g.Nx + 1);
+    int j = locateFail(g.yv, y, g.Ny + 1);
+    int k = locateFail(g.zv, z, g.Nz + 1);
+    if (i < 0 || j < 0 || k < 0) return -1;
+    return k + g.Nz * j + g.Nz * g.Ny * i;
+}
+
+template<class Sink>
+__device__ void walkCart(const CartGrid& g, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
+    const double* xv = g.xv; const double* yv = g.yv; const double* zv = g.zv;
+    const int Nx = g.Nx, Ny = g.Ny, Nz = g.Nz;
+    const double xmin = g.ext[0], xmax = g.ext[1], ymin = g.ext[2], ymax = g.ext[3], zmin = g.ext[4], zmax = g.ext[5];
+    Entry en; en.n = 0;
+    double ds;
+
+    // CartesianDustGrid.cpp:151-222
+    if (x < xmin)
+    {
+        if (kx <= 0.0) return;
+        ds = (xmin - x) / kx; en.ds[en.n++] = ds;
+        x = xmin + 1e-8 * (xv[1] - xv[0]); y += ky * ds; z += kz * ds;
+    }
+    else if (x > xmax)
+    {
+        if (kx >= 0.0) return;
+        ds = (xmax - x) / kx; en.ds[en.n++] = ds;
+        x = xmax - 1e-8 * (xv[Nx] - xv[Nx - 1]); y += ky * ds; z += kz * ds;
+    }
+    if (y < ymin)
+    {
+        if (ky <= 0.0) return;
+        ds = (ymin - y) / ky; en.ds[en.n++] = ds;
+        x += kx * ds; y = ymin + 1e-8 * (yv[1] - yv[0]); z += kz * ds;
+    }
+    else if (y > ymax)
+    {
+        if (ky >= 0.0) return;
+        ds = (ymax - y) / ky; en.ds[en.n++] = ds;
+        x += kx * ds; y = ymax - 1e-8 * (yv[Ny] - yv[Ny - 1]); z += kz * ds;
+    }
+    if (z < zmin)
+    {
+        if (kz <= 0.0) return;
+        ds = (zmin - z) / kz; en.ds[en.n++] = ds;
+        x += kx * ds; y += ky * ds; z = zmin + 1e-8 * (zv[1] - zv[0]);
+    }
+    else if (z > zmax)
+    {
+        if (kz >= 0.0) return;
+        ds = (zmax - z) / kz; en.ds[en.n++] = ds;
+        x += kx * ds; y += ky * ds; z = zmax - 1e-8 * (zv[Nz] - zv[Nz - 1]);
+    }
+    // :224
+    if (x < xmin || x > xmax || y < ymin || y > ymax || z < zmin || z > zmax) return;
+    if (!flushEntry(en, sink)) return;
+
+    // :228-230
+    int i = locateClip(xv, x, Nx + 1);
+    int j = locateClip(yv, y, Ny + 1);
+    int k = locateClip(zv, z, Nz + 1);
+
+    // direction-dependent constants hoisted out of the loop (pure selections, no arithmetic change)
+    const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
+    const bool ax = fabs(kx) > 1e-15, ay = fabs(ky) > 1e-15, az = fabs(kz) > 1e-15;
+    const int di = nx ? -1 : 1, dj = ny ? -1 : 1, dk = nz ? -1 : 1;
+    const int ox = nx ? 0 : 1, oy = ny ? 0 : 1, oz = nz ? 0 : 1;
+    const int NyNz = Ny * Nz;
+    int m = k + Nz * j + NyNz * i;
+
+    // :234-282
+    while (true)
+    {
+        double xE = xv[i + ox];
+        double yE = yv[j + oy];
+        double zE = zv[k + oz];
+        double dsx = ax ? (xE - x) / kx : SKG_DBL_MAX;
+        double dsy = ay ? (yE - y) / ky : SKG_DBL_MAX;
+        double dsz = az ? (zE - z) / kz : SKG_DBL_MAX;
+        if (dsx <= dsy && dsx <= dsz)
+        {
+            ds = dsx;
+            if (ds > 0) { if (!sink.add(m, ds)) return; }
+            i += di; m += di * NyNz;
+            if (i >= Nx || i < 0) return;
+            x = xE; y += ky * ds; z += kz * ds;
+        }
+        else if (dsy < dsx && dsy <= dsz)
+        {
+            ds = dsy;
+            if (ds > 0) { if (!sink.add(m, ds)) return; }
+            j += dj; m += dj * Nz;
+            if (j >= Ny || j < 0) return;
+            x += kx * ds; y = yE; z += kz * ds;
+        }
+        else if (dsz < dsx && dsz < dsy)
+        {
+            ds = dsz;
+            if (ds > 0) { if (!sink.add(m, ds)) return; }
+            k += dk; m += dk;
+            if (k >= Nz || k < 0) return;
+            x += kx * ds; y += ky * ds; z = zE;
+        }
+        else return;    // unreachable for finite input (the reference would spin forever)
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// DustGridPath::moveInside, DustGridPath.cpp:57-150.  box = xmin,ymin,zmin,xmax,ymax,zmax.
+// Returns false for the reference's OUTSIDE position.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool moveInside(const double* box, double eps, double& rx, double& ry, double& rz,
+                                           double kx, double ky, double kz, Entry& en)
+{
+    const double xmin = box[0], ymin = box[1], zmin = box[2], xmax = box[3], ymax = box[4], zmax = box[5];
+    en.n = 0;
+    if (rx <= xmin)
+    {
+        if (kx <= 0.0) return false;
+        double ds = (xmin - rx) / kx; en.ds[en.n++] = ds;
+        rx = xmin + eps; ry += ky * ds; rz += kz * ds;
+    }
+    else if (rx >= xmax)
+    {
+        if (kx >= 0.0) return false;
+        double ds = (xmax - rx) / kx; en.ds[en.n++] = ds;
+        rx = xmax - eps; ry += ky * ds; rz += kz * ds;
+    }
+    if (ry <= ymin)
+    {
+        if (ky <= 0.0) return false;
+        double ds = (ymin - ry) / ky; en.ds[en.n++] = ds;
+        rx += kx * ds; ry = ymin + eps; rz += kz * ds;
+    }
+    else if (ry >= ymax)
+    {
+        if (ky >= 0.0) return false;
+        double ds = (ymax - ry) / ky; en.ds[en.n++] = ds;
+        rx += kx * ds; ry = ymax - eps; rz += kz * ds;
+    }
+    if (rz <= zmin)
+    {
+        if (kz <= 0.0) return false;
+        double ds = (zmin - rz) / kz; en.ds[en.n++] = ds;
+        rx += kx * ds; ry += ky * ds; rz = zmin + eps;
+    }
+    else if (rz >= zmax)
+    {
+        if (kz >= 0.0) return false;
+        double ds = (zmax - rz) / kz; en.ds[en.n++] = ds;
+        rx += kx * ds; ry += ky * ds; rz = zmax - eps;
+    }
+    return true;
+}
+
+// Box::contains (closed on all faces), Box.hpp:94-95
+__device__ __forceinline__ bool boxContains(const double* b, double x, double y, double z)
+{
+    return x >= b[0] && x <= b[3] && y >= b[1] && y <= b[4] && z >= b[2] && z <= b[5];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Tree (octree / binary tree)
+// ---------------------------------------------------------------------------------------------------
+// TreeNode::whichnode(Vec), TreeNode.cpp:70-80, starting from the root
+__device__ __forceinline__ int treeWhichNode(const TreeGrid& g, double x, double y, double z)
+{
+    if (!boxContains(g.box, x, y, z)) return -1;
+    int node = 0;
+    int c0;
+    while ((c0 = __ldg(g.child0 + node)) >= 0)
+    {
+        const double* cb = g.box + 6 * (size_t)c0;
+        if (g.kind == 0)
+        {
+            // OctTreeNode::child, OctTreeNode.cpp:184-189
+            int l = (x < cb[3] ? 0 : 1) + (y < cb[4] ? 0 : 2) + (z < cb[5] ? 0 : 4);
+            node = c0 + l;
+        }
+        else
+        {
+            // BinTreeNode::child, BinTreeNode.cpp:326-335
+            int d = __ldg(g.dir + node);
+            double v = d == 0 ? x : (d == 1 ? y : z);
+            node = (v < cb[3 + d]) ? c0 : c0 + 1;
+        }
+    }
+    return node;
+}
+
+__device__ __forceinline__ double nextAfterAlong(double v, double k)
+{
+    return nextafter(v, (k < 0.0) ? -SKG_DBL_MAX : SKG_DBL_MAX);
+}
+
+template<class Sink>
+__device__ void walkTree(const TreeGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
+    Entry en;
+    if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return;
+    int node = treeWhichNode(g, x, y, z);
+    if (node < 0) return;
+    if (!flushEntry(en, sink)) return;
+    const double eps = g.eps;
+    const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
+    const bool ax = fabs(kx) > 1e-15, ay = fabs(ky) > 1e-15, az = fabs(kz) > 1e-15;
+
+    if (g.search != 2)
+    {
+        // TopDown (TreeDustGrid.cpp:412-456) and Neighbor (:460-521)
+        while (node >= 0)
+        {
+            const double* b = g.box + 6 * (size_t)node;
+            double xnext = nx ? b[0] : b[3];
+            double ynext = ny ? b[1] : b[4];
+            double znext = nz ? b[2] : b[5];
+            double dsx = ax ? (xnext - x) / kx : SKG_DBL_MAX;
+            double dsy = ay ? (ynext - y) / ky : SKG_DBL_MAX;
+            double dsz = az ? (znext - z) / kz : SKG_DBL_MAX;
+            double ds; int wall;
+            if (dsx <= dsy && dsx <= dsz) { ds = dsx; wall = nx ? 0 : 1; }
+            else if (dsy <= dsx && dsy <= dsz) { ds = dsy; wall = ny ? 2 : 3; }
+            else { ds = dsz; wall = nz ? 4 : 5; }
+            if (ds > 0) { if (!sink.add(__ldg(g.cell + node), ds)) return; }
+            x += (ds + eps) * kx;
+            y += (ds + eps) * ky;
+            z += (ds + eps) * kz;
+
+            int oldnode = node;
+            if (g.search == 1)
+            {
+                // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first neighbour whose closed box contains r
+                int beg = __ldg(g.nbrStart + 6 * (size_t)node + wall), end = __ldg(g.nbrStart + 6 * (size_t)node + wall + 1);
+                node = -1;
+                for (int q = beg; q < end; q++)
+                {
+                    int cand = __ldg(g.nbrIds + q);
+                    if (boxContains(g.box + 6 * (size_t)cand, x, y, z)) { node = cand; break; }
+                }
+                if (node < 0) node = treeWhichNode(g, x, y, z);
+            }
+            else node = treeWhichNode(g, x, y, z);
+
+            if (node == oldnode)
+            {
+                atomicAdd(&ctr->stuckEscaped, 1ull);
+                x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
+                node = treeWhichNode(g, x, y, z);
+                if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); break; }
+            }
+        }
+    }
+    else
+    {
+        // Bookkeeping (octree only), TreeDustGrid.cpp:527-659
+        int l = node;
+        while (true)
+        {
+            const double* b = g.box + 6 * (size_t)l;
+            double xnext = nx ? b[0] : b[3];
+            double ynext = ny ? b[1] : b[4];
+            double znext = nz ? b[2] : b[5];
+            double dsx = ax ? (xnext - x) / kx : SKG_DBL_MAX;
+            double dsy = ay ? (ynext - y) / ky : SKG_DBL_MAX;
+            double dsz = az ? (znext - z) / kz : SKG_DBL_MAX;
+            if (dsx <= dsy && dsx <= dsz)
+            {
+                if (dsx > 0) { if (!sink.add(__ldg(g.cell + l), dsx)) return; }
+                x = xnext; y += ky * dsx; z += kz * dsx;
+                while (true)
+                {
+                    int oct = ((l - 1) % 8) + 1;
+                    bool place = nx ? (oct % 2 == 1) : (oct % 2 == 0);
+                    if (!place) break;
+                    l = __ldg(g.parent + l);
+                    if (l == 0) return;
+                }
+                l += nx ? -1 : 1;
+                while (__ldg(g.cell + l) == -1)
+                {
+                    int c0 = __ldg(g.child0 + l);
+                    const double* cb = g.box + 6 * (size_t)c0;
+                    double yM = cb[4], zM = cb[5];
+                    if (nx) l = (y <= yM) ? ((z <= zM) ? c0 + 1 : c0 + 5) : ((z <= zM) ? c0 + 3 : c0 + 7);
+                    else    l = (y <= yM) ? ((z <= zM) ? c0 + 0 : c0 + 4) : ((z <= zM) ? c0 + 2 : c0 + 6);
+                }
+            }
+            else if (dsy < dsx && dsy <= dsz)
+            {
+                if (dsy > 0) { if (!sink.add(__ldg(g.cell + l), dsy)) return; }
+                x += kx * dsy; y = ynext; z += kz * dsy;
+                while (true)
+                {
+                    bool place = ny ? ((l - 1) % 4 < 2) : ((l - 1) % 4 > 1);
+                    if (!place) break;
+                    l = __ldg(g.parent + l);
+                    if (l == 0) return;
+                }
+                l += ny ? -2 : 2;
+                while (__ldg(g.cell + l) == -1)
+                {
+                    int c0 = __ldg(g.child0 + l);
+                    const double* cb = g.box + 6 * (size_t)c0;
+                    double xM = cb[3], zM = cb[5];
+                    if (ny) l = (x <= xM) ? ((z <= zM) ? c0 + 2 : c0 + 6) : ((z <= zM) ? c0 + 3 : c0 + 7);
+                    else    l = (x <= xM) ? ((z <= zM) ? c0 + 0 : c0 + 4) : ((z <= zM) ? c0 + 1 : c0 + 5);
+                }
+            }
+            else if (dsz < dsx && dsz < dsy)
+            {
+                if (dsz > 0) { if (!sink.add(__ldg(g.cell + l), dsz)) return; }
+                x += kx * dsz; y += ky * dsz; z = znext;
+                while (true)
+                {
+                    int oct = ((l - 1) % 8) + 1;
+                    bool place = nz ? (oct < 5) : (oct > 4);
+                    if (!place) break;
+                    l = __ldg(g.parent + l);
+                    if (l == 0) return;
+                }
+                l += nz ? -4 : 4;
+                while (__ldg(g.cell + l) == -1)
+                {
+                    int c0 = __ldg(g.child0 + l);
+                    const double* cb = g.box + 6 * (size_t)c0;
+                    double xM = cb[3], yM = cb[4];
+                    if (nz) l = (x <= xM) ? ((y <= yM) ? c0 + 4 : c0 + 6) : ((y <= yM) ? c0 + 5 : c0 + 7);
+                    else    l = (x <= xM) ? ((y <= yM) ? c0 + 0 : c0 + 2) : ((y <= yM) ? c0 + 1 : c0 + 3);
+                }
+            }
+            else return;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Adaptive mesh
+// ---------------------------------------------------------------------------------------------------
+// Box::cellindices for one axis, Box.hpp:134-139
+__device__ __forceinline__ int cellIndex1(double v, double vmin, double vmax, int n)
+{
+    double q = n * (v - vmin) / (vmax - vmin);
+    int i = (q >= 2147483648.0 || q <= -2147483649.0 || q != q) ? INT_MIN : (int)q;   // x86 cvttsd2si behaviour
+    return max(0, min(n - 1, i));
+}
+
+// AdaptiveMeshNode::whichnode(Vec) from the root, AdaptiveMeshNode.cpp:132-142 (+ child :109-128).
+// Returns -1 when outside, -2 when the reference would throw "Can't locate the appropriate child node".
+__device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, double y, double z)
+{
+    if (!boxContains(g.box, x, y, z)) return -1;
+    int node = 0;
+    int c0;
+    while ((c0 = __ldg(g.child0 + node)) >= 0)
+    {
+        const double* b = g.box + 6 * (size_t)node;
+        int Nx = __ldg(g.nxyz + 3 * (size_t)node), Ny = __ldg(g.nxyz + 3 * (size_t)node + 1), Nz = __ldg(g.nxyz + 3 * (size_t)node + 2);
+        int i = cellIndex1(x, b[0], b[3], Nx);
+        int j = cellIndex1(y, b[1], b[4], Ny);
+        int k = cellIndex1(z, b[2], b[5], Nz);
+        int child = c0 + (k * Ny + j) * Nx + i;
+        const double* cb = g.box + 6 * (size_t)child;
+        if (!boxContains(cb, x, y, z))
+        {
+            if (x < cb[0]) i--; else if (x > cb[3]) i++;
+            if (y < cb[1]) j--; else if (y > cb[4]) j++;
+            if (z < cb[2]) k--; else if (z > cb[5]) k++;
+            if (i < 0 || i >= Nx || j < 0 || j >= Ny || k < 0 || k >= Nz) return -2;
+            child = c0 + (k * Ny + j) * Nx + i;
+            if (!boxContains(g.box + 6 * (size_t)child, x, y, z)) return -2;
+        }
+        node = child;
+    }
+    return node;
+}
+
+template<class Sink>
+__device__ void walkAMesh(const AMeshGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
+    Entry en;
+    if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return;
+    int node = ameshWhichNode(g, x, y, z);
+    if (node < 0) { if (node == -2) atomicAdd(&ctr->errors, 1ull); return; }
+    if (!flushEntry(en, sink)) return;
+    const double eps = g.eps;
+    const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
+    const bool ax = fabs(kx) > 1e-15, ay = fabs(ky) > 1e-15, az = fabs(kz) > 1e-15;
+
+    // AdaptiveMesh.cpp:312-366
+    while (node >= 0)
+    {
+        const double* b = g.box + 6 * (size_t)node;
+        double xnext = nx ? b[0] : b[3];
+        double ynext = ny ? b[1] : b[4];
+        double znext = nz ? b[2] : b[5];
+        double dsx = ax ? (xnext - x) / kx : SKG_DBL_MAX;
+        double dsy = ay ? (ynext - y) / ky : SKG_DBL_MAX;
+        double dsz = az ? (znext - z) / kz : SKG_DBL_MAX;
+        double ds; int wall;
+        if (dsx <= dsy && dsx <= dsz) { ds = dsx; wall = nx ? 0 : 1; }
+        else if (dsy <= dsx && dsy <= dsz) { ds = dsy; wall = ny ? 2 : 3; }
+        else { ds = dsz; wall = nz ? 4 : 5; }
+        if (ds > 0) { if (!sink.add(__ldg(g.cell + node), ds)) return; }
+        // r += (ds+eps)*k   (Vec operator*(double,Vec), Vec.hpp)
+        x += (ds + eps) * kx;
+        y += (ds + eps) * ky;
+        z += (ds + eps) * kz;
+
+        int oldnode = node;
+        int cand = __ldg(g.wallNbr + 6 * (size_t)node + wall);
+        if (cand >= 0 && boxContains(g.box + 6 * (size_t)cand, x, y, z)) node = cand;
+        else node = ameshWhichNode(g, x, y, z);
+        if (node == -2) { atomicAdd(&ctr->errors, 1ull); return; }
+
+        if (node == oldnode)
+        {
+            atomicAdd(&ctr->stuckEscaped, 1ull);
+            x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
+            node = ameshWhichNode(g, x, y, z);
+            if (node == -2) { atomicAdd(&ctr->errors, 1ull); return; }
+            if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); break; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Voronoi
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double voroSD(const VoroGrid& g, int m, double x, double y, double z)
+{
+    // VoronoiCell::squaredDistanceTo: (r-_r).norm2(), Vec.hpp
+    const double* p = g.particles + 3 * (size_t)m;
+    double dx = x - p[0], dy = y - p[1], dz = z - p[2];
+    return dx * dx + dy * dy + dz * dz;
+}
+
+// lessthan(p1, p2, axis), VoronoiMesh.cpp:77-105
+__device__ __forceinline__ bool voroLess(double x1, double y1, double z1, const double* p2, int axis)
+{
+    double a1, a2, b1, b2, c1, c2;
+    if (axis == 0) { a1 = x1; a2 = p2[0]; b1 = y1; b2 = p2[1]; c1 = z1; c2 = p2[2]; }
+    else if (axis == 1) { a1 = y1; a2 = p2[1]; b1 = z1; b2 = p2[2]; c1 = x1; c2 = p2[0]; }
+    else if (axis == 2) { a1 = z1; a2 = p2[2]; b1 = x1; b2 = p2[0]; c1 = y1; c2 = p2[1]; }
+    else return false;
+    if (a1 < a2) return true;
+    if (a1 > a2) return false;
+    if (b1 < b2) return true;
+    if (b1 > b2) return false;
+    if (c1 < c2) return true;
+    return false;
+}
+
+// Node::nearest (VoronoiMesh.cpp:180-225) made iterative: an explicit stack holds the frames of the
+// reference's recursion (each frame = one nearest() invocation on a subtree).
+#define SKG_KD_STACK 40
+__device__ int voroKdNearest(const VoroGrid& g, int root, double x, double y, double z)
+{
+    int fRoot[SKG_KD_STACK], fCur[SKG_KD_STACK], fBest[SKG_KD_STACK];
+    double fBestSD[SKG_KD_STACK];
+    int sp = 0;
+    int result = -1;            // value "returned" by the most recently finished frame
+    bool entering = true;       // true: start a new frame on `root`; false: resume frame sp-1 after a return
+    while (true)
+    {
+        int cur, best; double bestSD; int froot;
+        if (entering)
+        {
+            if (sp >= SKG_KD_STACK) return -1;
+            froot = root;
+            cur = root;
+            while (true)
+            {
+                int mm = __ldg(g.kdM + cur), axis = __ldg(g.kdAxis + cur);
+                bool less = voroLess(x, y, z, g.particles + 3 * (size_t)mm, axis % 3);
+                int child = less ? __ldg(g.kdLeft + cur) : __ldg(g.kdRight + cur);
+                if (child < 0) break;
+                cur = child;
+            }
+            best = cur; bestSD = voroSD(g, __ldg(g.kdM + best), x, y, z);
+        }
+        else
+        {
+            sp--;
+            froot = fRoot[sp]; cur = fCur[sp]; best = fBest[sp]; bestSD = fBestSD[sp];
+            // combine with the result of the recursive call on the other child
+            double oSD = voroSD(g, __ldg(g.kdM + result), x, y, z);
+            if (oSD < bestSD) { best = result; bestSD = oSD; }
+            // move up
+            if (cur == froot) { result = best; if (sp == 0) return __ldg(g.kdM + result); entering = false; continue; }
+            cur = __ldg(g.kdUp + cur);
+        }
+        // climbing loop
+        bool pushed = false;
+        while (true)
+        {
+            int mm = __ldg(g.kdM + cur), axis = __ldg(g.kdAxis + cur) % 3;
+            double curSD = voroSD(g, mm, x, y, z);
+            if (curSD < bestSD) { best = cur; bestSD = curSD; }
+            const double* p = g.particles + 3 * (size_t)mm;
+            double d = (axis == 0) ? (p[0] - x) : (axis == 1 ? (p[1] - y) : (p[2] - z));
+            double splitSD = d * d;
+            if (splitSD < bestSD)
+            {
+                bool less = voroLess(x, y, z, p, axis);
+                int other = less ? __ldg(g.kdRight + cur) : __ldg(g.kdLeft + cur);
+                if (other >= 0)
+                {
+                    fRoot[sp] = froot; fCur[sp] = cur; fBest[sp] = best; fBestSD[sp] = bestSD; sp++;
+                    root = other; entering = true; pushed = true;
+                    break;
+                }
+            }
+            if (cur == froot) break;
+            cur = __ldg(g.kdUp + cur);
+        }
+        if (pushed) continue;
+        result = best;
+        if (sp == 0) return __ldg(g.kdM + result);
+        entering = false;
+    }
+}
+
+// VoronoiMesh::cellIndex, VoronoiMesh.cpp:512-541
+__device__ __forceinline__ int voroCellIndex(const VoroGrid& g, double x, double y, double z)
+{
+    if (!boxContains(g.ext, x, y, z)) return -1;
+    int nb = g.nb;
+    int i = cellIndex1(x, g.ext[0], g.ext[3], nb);
+    int j = cellIndex1(y, g.ext[1], g.ext[4], nb);
+    int k = cellIndex1(z, g.ext[2], g.ext[5], nb);
+    size_t b = (size_t)i * nb * nb + (size_t)j * nb + k;
+    int tree = __ldg(g.blkTree + b);
+    if (tree >= 0) return voroKdNearest(g, tree, x, y, z);
+    int beg = __ldg(g.blkStart + b), end = __ldg(g.blkStart + b + 1);
+    int m = -1;
+    double mdist = SKG_DBL_MAX;
+    for (int q = beg; q < end; q++)
+    {
+        int id = __ldg(g.blkIds + q);
+        double idist = voroSD(g, id, x, y, z);
+        if (idist < mdist) { m = id; mdist = idist; }
+    }
+    return m;
+}
+
+template<class Sink>
+__device__ void walkVoro(const VoroGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
+    Entry en;
+    if (!moveInside(g.ext, g.eps, x, y, z, kx, ky, kz, en)) return;
+    int mr = voroCellIndex(g, x, y, z);
+    if (mr < 0) return;
+    if (!flushEntry(en, sink)) return;
+    const double eps = g.eps;
+    long guard = 0;
+
+    // VoronoiMesh.cpp:764-843
+    while (mr >= 0)
+    {
+        const double* pr = g.particles + 3 * (size_t)mr;
+        double prx = pr[0], pry = pr[1], prz = pr[2];
+        double sq = SKG_DBL_MAX;
+        const int NO_INDEX = -99;
+        int mq = NO_INDEX;
+        int beg = __ldg(g.nbrStart + mr), end = __ldg(g.nbrStart + mr + 1);
+        for (int q = beg; q < end; q++)
+        {
+            int mi = __ldg(g.nbrIds + q);
+            double si = 0;
+            if (mi >= 0)
+            {
+                const double* pi = g.particles + 3 * (size_t)mi;
+                double pix = pi[0], piy = pi[1], piz = pi[2];
+                double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;        // n = pi - pr
+                double ndotk = nxv * kx + nyv * ky + nzv * kz;                   // Vec::dot(n,bfk)
+                if (ndotk > 0)
+                {
+                    double px = 0.5 * (pix + prx), py = 0.5 * (piy + pry), pz = 0.5 * (piz + prz);   // p = 0.5*(pi+pr)
+                    si = (nxv * (px - x) + nyv * (py - y) + nzv * (pz - z)) / ndotk;                // dot(n,p-r)/ndotk
+                }
+            }
+            else
+            {
+                switch (mi)
+                {
+                case -1: si = (g.ext[0] - x) / kx; break;
+                case -2: si = (g.ext[3] - x) / kx; break;
+                case -3: si = (g.ext[1] - y) / ky; break;
+                case -4: si = (g.ext[4] - y) / ky; break;
+                case -5: si = (g.ext[2] - z) / kz; break;
+                case -6: si = (g.ext[5] - z) / kz; break;
+                default: atomicAdd(&ctr->errors, 1ull); return;
+                }
+            }
+            if (si > 0 && si < sq) { sq = si; mq = mi; }
+        }
+        if (mq == NO_INDEX)
+        {
+            // r += bfk*_eps  (Vec operator*(Vec,double))
+            x += kx * eps; y += ky * eps; z += kz * eps;
+            mr = voroCellIndex(g, x, y, z);
+            if (++guard > 1000000) { atomicAdd(&ctr->errors, 1ull); return; }
+        }
+        else
+        {
+            if (!sink.add(mr, sq)) return;      // sq > 0 by construction
+            x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
+            mr = mq;
+        }
+    }
+}
+
+}   // namespace skg

@@ -1,0 +1,66 @@
+// Device-resident table views consumed by the traversal / Monte Carlo kernels.
+// Layouts are those documented in include/skirtgpu.h (flattened state of the reference's grids).
+#pragma once
+#include <cstdint>
+
+namespace skg
+{
+
+enum GridKind { GRID_NONE = -1, GRID_CART = 0, GRID_TREE = 1, GRID_AMESH = 2, GRID_VORO = 3 };
+
+struct CartGrid
+{
+    const double* xv; const double* yv; const double* zv;   // borders, Nx+1 / Ny+1 / Nz+1 values
+    int Nx, Ny, Nz;
+    double ext[6];      // xmin,xmax,ymin,ymax,zmin,zmax of the BoxDustGrid extent
+};
+
+struct TreeGrid
+{
+    const double* box;              // [6N] xmin,ymin,zmin,xmax,ymax,zmax
+    const int* child0; const int* parent; const int* cell; const int* dir;
+    const int* nbrStart; const int* nbrIds;
+    int N, kind, search;
+    double eps;
+};
+
+struct AMeshGrid
+{
+    const double* box; const int* nxyz; const int* child0; const int* cell; const int* wallNbr;
+    int N;
+    double eps;
+};
+
+struct VoroGrid
+{
+    const double* particles;        // [3N]
+    const int* nbrStart; const int* nbrIds;
+    const int* blkStart; const int* blkIds; const int* blkTree;
+    const int* kdM; const int* kdAxis; const int* kdUp; const int* kdLeft; const int* kdRight;
+    const double* cellBox;          // [6N] xmin,ymin,zmin,xmax,ymax,zmax
+    double ext[6];                  // xmin,ymin,zmin,xmax,ymax,zmax
+    double eps;
+    int N, nb;
+};
+
+struct Medium
+{
+    const double* rho;              // [Ncells*Ncomp]
+    const double* kext; const double* ksca; const double* g;    // [Ncomp*Nlambda]
+    int Ncells, Ncomp, Nlambda;
+};
+
+// counters updated by the kernels (device memory, one instance per engine)
+struct Counters
+{
+    unsigned long long stuckEscaped;        // "seems stuck -- escaping" (TreeDustGrid.cpp:437-446)
+    unsigned long long stuckTerminated;     // "is stuck -- terminating this path" (:449-454)
+    unsigned long long errors;              // conditions on which the reference throws FATALERROR
+    unsigned long long segments;            // packet-steps (addSegment with ds>0)
+    unsigned long long paths;               // traversals
+    unsigned long long scatterings;
+    unsigned long long packets;
+    unsigned long long pad;
+};
+
+}   // namespace skg

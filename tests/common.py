@@ -1,0 +1,183 @@
+"""Shared helpers for the test-suite: synthetic configurations, seeded ray batches,
+and the reference harness (oracle/_ref) specs that describe them."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+PC = 3.08567758e16          # Units.cpp:17-30
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+# InterstellarDustMix at 0.55 micron on an OligoWavelengthGrid, evaluated by the reference itself
+# (oracle/_ref, skr_interstellar_mix); regenerate with tests/golden/make_golden.py
+MIX_V = dict(kabs=848.25415325, ksca=1751.62943942, g=0.53723952)
+
+C1_BOX = np.array([-25000., 25000., -25000., 25000., -5000., 5000.]) * PC
+
+
+def box_line(box):
+    return "box " + " ".join(repr(float(v)) for v in box)
+
+
+def rays(n, box, seed, scale=1.2):
+    """SURVEY.md 8d synthetic rays: r uniform in `scale` x bounding box, k isotropic."""
+    rng = np.random.default_rng(seed)
+    box = np.asarray(box, dtype=np.float64)
+    c = 0.5 * (box[0::2] + box[1::2]); w = (box[1::2] - box[0::2])
+    r = c + (rng.random((n, 3)) - 0.5) * w * scale
+    k = rng.normal(size=(n, 3)); k /= np.linalg.norm(k, axis=1)[:, None]
+    return np.ascontiguousarray(r), np.ascontiguousarray(k)
+
+
+def adversarial_rays(box, axes=None, seed=7):
+    """axis-aligned, |k_i|<1e-15, starts on faces/edges/corners, grazing, outside & pointing away."""
+    box = np.asarray(box, dtype=np.float64)
+    lo = box[0::2]; hi = box[1::2]; c = 0.5 * (lo + hi); w = hi - lo
+    rs, ks = [], []
+    e = np.eye(3)
+    for a in range(3):
+        for sgn in (1.0, -1.0):
+            for start in (c, lo - 0.1 * w, hi + 0.1 * w, lo, hi, c + 0.25 * w):
+                rs.append(np.array(start, dtype=np.float64)); ks.append(sgn * e[a])
+    # tiny components
+    for a in range(3):
+        k = np.array([0.6, 0.8, 0.0]); k = np.roll(k, a); k[(a + 2) % 3] = 5e-16
+        rs.append(c + 0.01 * w); ks.append(k / np.linalg.norm(k))
+        rs.append(lo - 0.2 * w); ks.append(np.abs(k) / np.linalg.norm(k))
+    # corners and edges, diagonal directions
+    for sx in (0, 1):
+        for sy in (0, 1):
+            for sz in (0, 1):
+                corner = np.where([sx, sy, sz], hi, lo)
+                d = c - corner
+                rs.append(corner); ks.append(d / np.linalg.norm(d))
+                rs.append(corner - 0.05 * d); ks.append(d / np.linalg.norm(d))
+                rs.append(corner); ks.append(-d / np.linalg.norm(d))
+    # grazing along a face
+    for a in range(3):
+        k = np.zeros(3); k[(a + 1) % 3] = 1.0
+        p = c.copy(); p[a] = hi[a]; p[(a + 1) % 3] = lo[(a + 1) % 3] - 0.1 * w[(a + 1) % 3]
+        rs.append(p); ks.append(k)
+        p2 = p.copy(); p2[a] = lo[a]
+        rs.append(p2); ks.append(k)
+    if axes is not None:
+        # starts exactly on interior cell borders
+        rng = np.random.default_rng(seed)
+        xv, yv, zv = axes
+        for _ in range(24):
+            p = np.array([rng.choice(xv), rng.choice(yv), rng.choice(zv)])
+            k = rng.normal(size=3); k /= np.linalg.norm(k)
+            rs.append(p); ks.append(k)
+    return np.ascontiguousarray(np.array(rs)), np.ascontiguousarray(np.array(ks))
+
+
+def spec_c1(packages=1e5, n=40, threads=1, seed=4357, mesh="lin", grid=None, dustsamples=20, storeabs=0, instruments=None,
+            tau=1.0, box=C1_BOX):
+    """C1: oligochromatic edge-on ExpDisk stars+dust (Tutorial 1.txt:241-245,352-372), 1 wavelength."""
+    if grid is None:
+        grid = f"grid cartesian {n} {n} {n} {mesh} {mesh} {mesh}"
+    if instruments is None:
+        instruments = [f"instrument frame i88 {1e7*PC!r} {float(np.radians(88))!r} 0 0 200 {50000*PC!r} 50 {12500*PC!r}",
+                       f"instrument sed s88 {1e7*PC!r} {float(np.radians(88))!r} 0 0"]
+    lines = ["sim oligo", f"threads {threads}", f"seed {seed}", f"packages {packages!r}", "wavelengths 0.55e-6",
+             box_line(box), grid, f"dustsamples {dustsamples}", f"storeabs {storeabs}",
+             f"stellar expdisk {4000*PC!r} {350*PC!r} 0 0",
+             f"dust {tau!r} 0.55e-6 expdisk {4000*PC!r} {140*PC!r} 0 0"] + list(instruments)
+    return "\n".join(lines) + "\n"
+
+
+def mix_v():
+    return [([MIX_V["kabs"]], [MIX_V["ksca"]], [MIX_V["g"]])]
+
+
+def assert_paths_equal(a, b, rtol=1e-12, label=""):
+    """bit-exact cell sequences + counts; ds/s/dtau/tau to rtol relative (north_star: 1e-12)."""
+    assert np.array_equal(a["offsets"], b["offsets"]), f"{label}: segment counts differ"
+    assert np.array_equal(a["m"], b["m"]), f"{label}: cell index sequences differ"
+    for key in ("ds", "s", "dtau", "tau"):
+        x, y = a[key], b[key]
+        denom = np.maximum(np.abs(y), 1e-300)
+        err = np.max(np.abs(x - y) / denom) if len(x) else 0.0
+        assert err <= rtol, f"{label}: {key} relative error {err:g} > {rtol:g}"
+
+
+def paths_bit_identical(a, b):
+    return all(np.array_equal(a[k], b[k]) for k in ("offsets", "m", "ds", "s", "dtau", "tau"))
+
+
+# ---- synthetic adaptive mesh: refine 2x2x2 where rho*V exceeds a threshold ----------
+def expdisk_density(x, y, z, hR=4000 * PC, hz=140 * PC):
+    R = np.hypot(x, y)
+    return np.exp(-R / hR) * np.exp(-np.abs(z) / hz)
+
+
+def make_amesh(box=C1_BOX, root=(4, 4, 4), max_depth=4, frac=2e-3):
+    """Returns (nxyz[N,3], value[N]) in the reference's file order (AdaptiveMeshAsciiFile.cpp:43-100:
+    depth-first, children looped k -> j -> i)."""
+    box = np.asarray(box, dtype=np.float64)
+    lo = box[0::2]; hi = box[1::2]
+    total = 2 * np.pi * (4000 * PC) ** 2 * 2 * 140 * PC      # integral of the un-normalised density
+    nxyz, val = [], []
+
+    def visit(lo, hi, depth, n):
+        nxyz.append(n); val.append(0.0)
+        for k in range(n[2]):
+            for j in range(n[1]):
+                for i in range(n[0]):
+                    idx = np.array([i, j, k]); nn = np.array(n)
+                    clo = lo + idx * (hi - lo) / nn
+                    chi = lo + (idx + 1) * (hi - lo) / nn
+                    c = 0.5 * (clo + chi)
+                    rho = float(expdisk_density(*c))
+                    # refinement criterion: largest density over a 3x3x3 probe lattice times the cell volume
+                    g3 = [clo + f * (chi - clo) for f in (0.0, 0.5, 1.0)]
+                    peak = max(float(expdisk_density(gx[0], gy[1], gz[2])) for gx in g3 for gy in g3 for gz in g3)
+                    mass = peak * np.prod(chi - clo)
+                    if depth < max_depth and mass > frac * total:
+                        visit(clo, chi, depth + 1, (2, 2, 2))
+                    else:
+                        nxyz.append((0, 0, 0)); val.append(rho)
+
+    visit(lo, hi, 0, tuple(root))
+    return np.array(nxyz, dtype=np.int32), np.array(val, dtype=np.float64)
+
+
+def spec_grid(kind, search=1, box=C1_BOX, minlevel=2, maxlevel=5, massfrac=2e-4, packages=1e4, threads=1, extra=()):
+    """Specs for the non-Cartesian grids; dust = C1's ExpDisk (or the mesh's own densities for amesh)."""
+    head = ["sim oligo", f"threads {threads}", "seed 4357", f"packages {packages!r}", "wavelengths 0.55e-6", box_line(box)]
+    stellar = f"stellar expdisk {4000*PC!r} {350*PC!r} 0 0"
+    dust = f"dust 1.0 0.55e-6 expdisk {4000*PC!r} {140*PC!r} 0 0"
+    instr = f"instrument sed s88 {1e7*PC!r} {float(np.radians(88))!r} 0 0"
+    if kind in ("octtree", "bintree"):
+        grid = f"grid {kind} {minlevel} {maxlevel} {search} {massfrac!r} 0 50"
+        lines = head + [grid, "dustsamples 10", stellar, dust, instr]
+    elif kind == "voronoi":
+        lines = head + ["grid voronoi file", "dustsamples 10", stellar, dust, instr]
+    elif kind == "amesh":
+        lines = head + ["grid amesh", "ameshdust 1e-24", stellar, instr]
+    else:
+        raise ValueError(kind)
+    return "\n".join(lines + list(extra)) + "\n"
+
+
+def voronoi_particles(n, box=C1_BOX, seed=11):
+    """particles drawn from the ExpDisk density (clipped to the box) plus a uniform background."""
+    rng = np.random.default_rng(seed)
+    box = np.asarray(box, dtype=np.float64); lo = box[0::2]; hi = box[1::2]
+    out = []
+    while len(out) < n:
+        m = n
+        R = rng.gamma(2.0, 4000 * PC, m); phi = rng.random(m) * 2 * np.pi
+        z = rng.laplace(0.0, 350 * PC, m)
+        p = np.stack([R * np.cos(phi), R * np.sin(phi), z], axis=1)
+        u = lo + rng.random((m // 4, 3)) * (hi - lo)
+        p = np.concatenate([p, u])
+        ok = np.all((p > lo) & (p < hi), axis=1)
+        out.extend(p[ok].tolist())
+    out = np.array(out[:n])
+    rng.shuffle(out)
+    return np.ascontiguousarray(out)
