@@ -9,6 +9,8 @@ namespace skg
 {
 
 static thread_local std::string g_lastError;
+void setLastError(const std::string& msg) { g_lastError = msg; }
+const char* lastErrorCStr() { return g_lastError.c_str(); }
 
 Engine::Engine(int dev) : device(dev)
 {
@@ -72,8 +74,8 @@ using namespace skg;
 template<class F> static int guarded(F f)
 {
     try { f(); return 0; }
-    catch (std::exception& ex) { g_lastError = ex.what(); }
-    catch (...) { g_lastError = "unknown error"; }
+    catch (std::exception& ex) { setLastError(ex.what()); }
+    catch (...) { setLastError("unknown error"); }
     return 1;
 }
 
@@ -88,7 +90,7 @@ static Engine& E(skg_engine* e)
 extern "C"
 {
 
-const char* skg_last_error(void) { return g_lastError.c_str(); }
+const char* skg_last_error(void) { return skg::lastErrorCStr(); }
 int skg_version(void) { return 1; }
 
 int skg_engine_create(int device, skg_engine** out)

@@ -535,7 +535,7 @@ __device__ __forceinline__ bool voroLess(double x1, double y1, double z1, const 
 // Node::nearest (VoronoiMesh.cpp:180-225) made iterative: an explicit stack holds the frames of the
 // reference's recursion (each frame = one nearest() invocation on a subtree).
 #define SKG_KD_STACK 40
-__device__ int voroKdNearest(const VoroGrid& g, int root, double x, double y, double z)
+static __device__ int voroKdNearest(const VoroGrid& g, int root, double x, double y, double z)
 {
     int fRoot[SKG_KD_STACK], fCur[SKG_KD_STACK], fBest[SKG_KD_STACK];
     double fBestSD[SKG_KD_STACK];

@@ -181,3 +181,70 @@ def voronoi_particles(n, box=C1_BOX, seed=11):
     out = np.array(out[:n])
     rng.shuffle(out)
     return np.ascontiguousarray(out)
+
+
+# ---- configuration dictionaries shared by the reference harness spec and the engine set-up -----------------
+def cfg_c1(n=40, packages=1e5, instruments=None, storeabs=0, tau=1.0, grid=None, seed=4357, threads=1, dustsamples=20):
+    """C1 (BASELINE.json configs[0]): oligochromatic edge-on ExpDisk stars + dust, 1 wavelength, FrameInstrument."""
+    if instruments is None:
+        instruments = [dict(kind=1, name="i88", distance=1e7 * PC, inclination=float(np.radians(88)), azimuth=0.0, positionAngle=0.0,
+                            Nxp=200, fovxp=50000 * PC, Nyp=50, fovyp=12500 * PC),
+                       dict(kind=2, name="s88", distance=1e7 * PC, inclination=float(np.radians(88)), azimuth=0.0, positionAngle=0.0)]
+    return dict(sim="oligo", wavelengths=[0.55e-6], box=C1_BOX, packages=packages, seed=seed, threads=threads,
+                grid=grid or f"grid cartesian {n} {n} {n} lin lin lin", dustsamples=dustsamples, storeabs=storeabs,
+                sources=[dict(geometry=1, p=[4000 * PC, 350 * PC, 0.0, 0.0, 0.0], L=[1.0])],
+                dust=[dict(tau=tau, lam=0.55e-6, geometry=1, p=[4000 * PC, 140 * PC, 0.0, 0.0, 0.0], mix=mix_v()[0])],
+                instruments=instruments, mwr=1e4, minscatt=0.0, xi=0.5, ebias=0.5)
+
+
+def _geom_words(g):
+    if g["geometry"] == 1:
+        p = g["p"]; w = f"expdisk {p[0]!r} {p[1]!r} {p[2]!r} {p[3]!r}"
+    else:
+        p = g["p"]; w = f"sersic {g['n']!r} {p[0]!r} {p[1]!r}"
+    sp = g.get("spiral")
+    if sp:
+        w += f" spiral {sp['arms']} {sp['pitch']!r} {sp['radius']!r} {sp['phase']!r} {sp['weight']!r} {sp['index']}"
+    return w
+
+
+def ref_spec(cfg):
+    lines = [f"sim {cfg['sim']}", f"threads {cfg.get('threads', 1)}", f"seed {cfg.get('seed', 4357)}", f"packages {float(cfg['packages'])!r}",
+             f"minweightreduction {cfg.get('mwr', 1e4)!r}", f"minscatt {cfg.get('minscatt', 0.0)!r}", f"scattbias {cfg.get('xi', 0.5)!r}",
+             f"emissionbias {cfg.get('ebias', 0.5)!r}"]
+    if cfg["sim"] == "oligo":
+        lines.append("wavelengths " + " ".join(repr(float(v)) for v in cfg["wavelengths"]))
+    else:
+        lg = cfg["loggrid"]; lines.append(f"loggrid {lg[0]!r} {lg[1]!r} {lg[2]}")
+    lines += [box_line(cfg["box"]), cfg["grid"], f"dustsamples {cfg.get('dustsamples', 20)}", f"storeabs {cfg.get('storeabs', 0)}"]
+    for s in cfg["sources"]:
+        lines.append("stellar " + _geom_words(s))
+    for d in cfg.get("dust", []):
+        lines.append(f"dust {d['tau']!r} {d['lam']!r} " + _geom_words(d))
+    if cfg.get("ameshdust"):
+        lines.append(f"ameshdust {cfg['ameshdust']!r}")
+    for ins in cfg["instruments"]:
+        kind = {1: "frame", 2: "sed", 3: "simple"}[ins["kind"]]
+        w = f"instrument {kind} {ins['name']} {ins['distance']!r} {ins['inclination']!r} {ins.get('azimuth', 0.0)!r} {ins.get('positionAngle', 0.0)!r}"
+        if ins["kind"] != 2:
+            w += f" {ins['Nxp']} {ins['fovxp']!r} {ins['Nyp']} {ins['fovyp']!r}"
+        lines.append(w)
+    return "\n".join(lines) + "\n"
+
+
+def make_ref(cfg, **kw):
+    from oracle import skirtref as sr
+    return sr.RefSim(ref_spec(cfg), luminosities=[s["L"] for s in cfg["sources"]],
+                     mixes=[d["mix"] for d in cfg.get("dust", [])] + list(cfg.get("extra_mixes", [])), **kw)
+
+
+def setup_engine(e, cfg, tables, medium, L=None):
+    """feeds one engine with the flattened state (tables/medium as produced by the reference harness or
+    by the host-side builders) plus sources and instruments of cfg"""
+    e.set_grid(tables)
+    e.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    if L is None:
+        L = np.array([s["L"] for s in cfg["sources"]], dtype=np.float64)
+    e.sources(cfg["sources"], L, cfg.get("ebias", 0.5))
+    e.instruments(cfg["instruments"])
+    return e
