@@ -29,6 +29,10 @@ int skg_engine_create(int device, skg_engine** out);
 void skg_engine_destroy(skg_engine* e);
 const char* skg_last_error(void);
 int skg_version(void);
+/* the engine's CUDA stream (cudaStream_t) -- every kernel and copy of the engine is issued on it, so host code can
+ * record its own events on it or order other work after it; and the number of kernels launched so far */
+int skg_stream(skg_engine* e, void** stream);
+int skg_launch_count(skg_engine* e, uint64_t* launches);
 
 /* ---- dust grids: replace DustGrid::path / whichcell / randomPositionInCell (DustGrid.hpp:89-106) -- */
 
@@ -139,6 +143,8 @@ typedef struct skg_mc_stats
     uint64_t paths;             /* traversals (full, propagation and peel-off) */
     uint64_t scatterings;
     double kernel_ms;           /* device time of the shooting kernels (CUDA events) */
+    uint64_t absorbSegments;    /* segments that added into the absorption table (one fp64 atomic each) */
+    uint64_t detections;        /* detector updates: frame pixel or SED bin (one fp64 atomic each) */
 } skg_mc_stats;
 int skg_run_stellar(skg_engine* e, const skg_mc_params* p, skg_mc_stats* stats);
 

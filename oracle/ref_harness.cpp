@@ -48,6 +48,8 @@
 #include "FatalError.hpp"
 #include "FrameInstrument.hpp"
 #include "GeometricStellarComp.hpp"
+#include "GreyBodyDustEmissivity.hpp"
+#include "AllCellsDustLib.hpp"
 #include "InstrumentSystem.hpp"
 #include "InterstellarDustMix.hpp"
 #include "LinMesh.hpp"
@@ -367,6 +369,9 @@ namespace
                 ds->setDustDistribution(S->dd); ds->setDustGrid(S->grid); ds->setSampleCount(dustsamples);
                 ds->setWriteConvergence(false); ds->setWriteDensity(false); ds->setWriteDepthMap(false);
                 ds->setWriteQuality(false); ds->setWriteCellProperties(false); ds->setWriteCellsCrossed(false);
+                // storeabs: PanDustSystem::storeabsorptionrates() == dustemission() (PanDustSystem.cpp:290-299), so the
+                // absorption tables only exist with a dust emissivity + library attached
+                if (storeabs) { ds->setDustEmissivity(new GreyBodyDustEmissivity()); ds->setDustLib(new AllCellsDustLib()); }
                 ds->setSelfAbsorption(false); ds->setWriteEmissivity(false); ds->setWriteTemperature(false); ds->setWriteISRF(false);
                 S->ds = ds; p->setDustSystem(ds);
             }

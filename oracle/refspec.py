@@ -1,0 +1,36 @@
+"""TEST INFRASTRUCTURE ONLY: describes a skirt_b200.configs parameter dict in the small description language of the
+reference harness (oracle/ref_harness.cpp).  Imported by tests/ and bench.py's CPU legs only."""
+from skirt_b200 import configs, simulation as sim
+
+
+def reference_spec(p, threads=1, seed=4357, dustsamples=100, storeabs=None, packages=None):
+    """The same configuration in the small description language of the reference harness (oracle/ref_harness.cpp),
+    plus the per-component luminosities and dust-mix tables that go with it.  Used only by tests/ and by
+    bench.py's CPU legs."""
+    lg = configs.wavelength_grid(p)
+    mix = sim.InterstellarDustMix(lg)
+    if storeabs is None:
+        storeabs = 1 if p["sim"] == "pan" else 0
+    n = p["n"]
+    lines = [f"sim {p['sim']}", f"threads {threads}", f"seed {seed}", f"packages {float(packages if packages is not None else p['packages'])!r}"]
+    if p["sim"] == "oligo":
+        lines.append("wavelengths " + " ".join(repr(float(v)) for v in p["wavelengths"]))
+    else:
+        a, b, k = p["loggrid"]; lines.append(f"loggrid {a!r} {b!r} {k}")
+    lines += ["box " + " ".join(repr(float(v)) for v in p["box"]), f"grid cartesian {n} {n} {n} lin lin lin",
+              f"dustsamples {dustsamples}", f"storeabs {int(storeabs)}"]
+
+    def words(g):
+        if g["geometry"] == "expdisk":
+            return f"expdisk {g['hR']!r} {g['hz']!r} {g.get('Rmax', 0.0)!r} {g.get('zmax', 0.0)!r}"
+        return f"sersic {g['index']!r} {g['Re']!r} {g.get('q', 1.0)!r}"
+    for s in p["stellar"]:
+        lines.append("stellar " + words(s))
+    for d in p["dust"]:
+        lines.append(f"dust {d['tau']!r} {d['lam']!r} " + words(d))
+    for i in p["instruments"]:
+        w = f"instrument {i['kind']} {i['name']} {i['distance']!r} {i['inclination']!r} {i.get('azimuth', 0.0)!r} {i.get('positionAngle', 0.0)!r}"
+        if i["kind"] != "sed":
+            w += f" {i['Nxp']} {i['fovxp']!r} {i['Nyp']} {i['fovyp']!r}"
+        lines.append(w)
+    return "\n".join(lines) + "\n", configs.luminosities(p, lg), [(mix.kappaabs, mix.kappasca, mix.asymmpar) for _ in p["dust"]]

@@ -42,7 +42,8 @@ class SkgMcParams(C.Structure):
 
 class SkgMcStats(C.Structure):
     _fields_ = [("packets", C.c_uint64), ("pathSegments", C.c_uint64), ("paths", C.c_uint64),
-                ("scatterings", C.c_uint64), ("kernel_ms", C.c_double)]
+                ("scatterings", C.c_uint64), ("kernel_ms", C.c_double),
+                ("absorbSegments", C.c_uint64), ("detections", C.c_uint64)]
 
 
 def lib_available():
@@ -105,6 +106,19 @@ class Engine:
             self.close()
         except Exception:
             pass
+
+    @property
+    def stream(self):
+        """cudaStream_t of the engine as an integer (wrap with torch.cuda.ExternalStream to record events on it)"""
+        p = C.c_void_p()
+        self._chk(self._lib.skg_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    @property
+    def launch_count(self):
+        n = C.c_uint64()
+        self._chk(self._lib.skg_launch_count(self.h, C.byref(n)))
+        return n.value
 
     # ---- grids ---------------------------------------------------------------------------------
     def grid_cartesian(self, xv, yv, zv):
@@ -255,7 +269,7 @@ class Engine:
         st = SkgMcStats()
         self._chk(self._lib.skg_run_stellar(self.h, C.byref(p), C.byref(st)))
         return dict(packets=st.packets, pathSegments=st.pathSegments, paths=st.paths, scatterings=st.scatterings,
-                    kernel_ms=st.kernel_ms)
+                    kernel_ms=st.kernel_ms, absorbSegments=st.absorbSegments, detections=st.detections)
 
     def reset_results(self):
         self._chk(self._lib.skg_reset_results(self.h))

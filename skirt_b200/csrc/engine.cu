@@ -1,5 +1,5 @@
 // Engine object + C ABI (include/skirtgpu.h).  Product path: fails loudly without a CUDA device; there is
-// no CPU fallback and nothing here touches oracle/.
+// no CPU fallback and nothing here touches the test oracles.
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -99,6 +99,11 @@ int skg_engine_create(int device, skg_engine** out)
 }
 
 void skg_engine_destroy(skg_engine* e) { delete reinterpret_cast<Engine*>(e); }
+
+int skg_stream(skg_engine* eh, void** stream)
+{ return guarded([&]{ if (!stream) throw Error("null output"); *stream = (void*)E(eh).stream; }); }
+int skg_launch_count(skg_engine* eh, uint64_t* launches)
+{ return guarded([&]{ if (!launches) throw Error("null output"); *launches = E(eh).launches; }); }
 
 int skg_num_cells(skg_engine* e) { return e ? reinterpret_cast<Engine*>(e)->Ncells : 0; }
 

@@ -71,6 +71,7 @@ struct Engine
     std::vector<InstrDev> instr; DevBuf instrDev; std::vector<DevBuf*> instrBufs;
     DevBuf labs; int64_t labsCount = 0;
     void* nccl = nullptr; int rank = 0, nranks = 1;
+    uint64_t launches = 0;              // kernels launched by this engine (skg_launch_count)
 
     explicit Engine(int dev);
     ~Engine();

@@ -201,11 +201,12 @@ struct AbsorbSink
     double albedo;          // Ncomp==1: DustMix::albedo(ell)
     double* labs;           // Labs + ell (stride Nlambda) or null
     double tau = 0, Lsca = 0;
-    int n = 0;
+    int n = 0, nAbs = 0;
     __device__ __forceinline__ bool add(int m, double ds)
     {
         n++;
         if (m < 0) return true;             // rho(-1,h) = 0: dtau = 0, nothing absorbed
+        nAbs++;
         int Ncomp = med->Ncomp;
         if (Ncomp == 1)
         {
@@ -286,7 +287,7 @@ __device__ __forceinline__ int whichCellMC(const GridSetMC& G, const CartGrid& c
 // Instrument::detect for the peel-off packet (r, kobs, L): returns the number of segments walked
 template<int KIND>
 __device__ __forceinline__ int detect(const GridSetMC& G, const CartGrid& cart, Counters* ctr, const McDev& P, const InstrDev& I,
-                                      int ell, double x, double y, double z, double L)
+                                      int ell, double x, double y, double z, double L, unsigned long long& nDet)
 {
     int l = -1;
     if (I.kind != SKG_INSTR_SED)
@@ -306,8 +307,8 @@ __device__ __forceinline__ int detect(const GridSetMC& G, const CartGrid& cart, 
     sink.distance = SKG_DBL_MAX;
     if (P.med.rho) walkMC<KIND>(G, cart, ctr, x, y, z, I.kobsx, I.kobsy, I.kobsz, sink);     // Instrument::opticalDepth: 0 without dust
     double Lextf = L * exp(-sink.tau);
-    if (I.kind != SKG_INSTR_FRAME) atomicAdd(I.sed + ell, Lextf);
-    if (I.kind != SKG_INSTR_SED && l >= 0) atomicAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf);
+    if (I.kind != SKG_INSTR_FRAME) { atomicAdd(I.sed + ell, Lextf); nDet++; }
+    if (I.kind != SKG_INSTR_SED && l >= 0) { atomicAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
     return sink.n;
 }
 
@@ -327,7 +328,7 @@ __global__ void __launch_bounds__(128) stellarKernel(const __grid_constant__ Gri
         cart.xv = smem; cart.yv = smem + nx; cart.zv = smem + nx + ny;
     }
 
-    unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nPackets = 0;
+    unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nPackets = 0, nAbs = 0, nDet = 0;
     const unsigned long long total = P.NppInt * (unsigned long long)(P.ellEnd - P.ellBegin);
     const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
 
@@ -369,7 +370,7 @@ __global__ void __launch_bounds__(128) stellarKernel(const __grid_constant__ Gri
         // ---- peeloffemission, MonteCarloSimulation.cpp:305-315 (isotropic emitter: probabilityForDirection = 1) ----
         for (int q = 0; q < P.Ninstr; q++)
         {
-            int ns = detect<KIND>(G, cart, ctr, P, P.instr[q], ell, x, y, z, L);
+            int ns = detect<KIND>(G, cart, ctr, P, P.instr[q], ell, x, y, z, L, nDet);
             nSeg += ns; nPaths++;
         }
 
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(128) stellarKernel(const __grid_constant__ Gri
             double kext0 = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
             ab.albedo = kext0 > 0 ? ksca0 / kext0 : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
             walkMC<KIND>(G, cart, ctr, x, y, z, kx, ky, kz, ab);
-            nSeg += ab.n; nPaths++;
+            nSeg += ab.n; nPaths++; if (ab.labs) nAbs += ab.nAbs;
             const double taupath = ab.tau;
             if (Ncomp == 1) L = L * ab.albedo * (-expm1(-taupath));
             else L = ab.Lsca;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(128) stellarKernel(const __grid_constant__ Gri
                     double t = 1.0 + g * g - 2 * g * cosalpha;
                     w += wv[c] * ((1.0 - g) * (1.0 + g) / sqrt(t * t * t));
                 }
-                int ns = detect<KIND>(G, cart, ctr, P, I, ell, x, y, z, L * w);      // launchScatteringPeelOff, PhotonPackage.cpp:51-62
+                int ns = detect<KIND>(G, cart, ctr, P, I, ell, x, y, z, L * w, nDet);      // launchScatteringPeelOff, PhotonPackage.cpp:51-62
                 nSeg += ns; nPaths++;
             }
 
@@ -485,11 +486,13 @@ __global__ void __launch_bounds__(128) stellarKernel(const __grid_constant__ Gri
     {
         nSeg += __shfl_down_sync(0xffffffffu, nSeg, o); nPaths += __shfl_down_sync(0xffffffffu, nPaths, o);
         nScatt += __shfl_down_sync(0xffffffffu, nScatt, o); nPackets += __shfl_down_sync(0xffffffffu, nPackets, o);
+        nAbs += __shfl_down_sync(0xffffffffu, nAbs, o); nDet += __shfl_down_sync(0xffffffffu, nDet, o);
     }
     if ((threadIdx.x & 31) == 0)
     {
         atomicAdd(&ctr->segments, nSeg); atomicAdd(&ctr->paths, nPaths);
         atomicAdd(&ctr->scatterings, nScatt); atomicAdd(&ctr->packets, nPackets);
+        atomicAdd(&ctr->absorbSegments, nAbs); atomicAdd(&ctr->detections, nDet);
     }
 }
 
@@ -669,7 +672,7 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
         case GRID_VORO: stellarKernel<GRID_VORO><<<blocks, 128, 0, e.stream>>>(G, P, e.ctr(), false); break;
         default: throw Error("no dust grid has been set");
         }
-        SKG_CUDA(cudaGetLastError());
+        e.launches++; SKG_CUDA(cudaGetLastError());
     }
     SKG_CUDA(cudaEventRecord(ev1, e.stream));
     e.sync();
@@ -681,6 +684,7 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
         stats->packets = after.packets - before.packets; stats->pathSegments = after.segments - before.segments;
         stats->paths = after.paths - before.paths; stats->scatterings = after.scatterings - before.scatterings;
         stats->kernel_ms = ms;
+        stats->absorbSegments = after.absorbSegments - before.absorbSegments; stats->detections = after.detections - before.detections;
     }
 }
 

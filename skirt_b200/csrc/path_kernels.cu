@@ -143,7 +143,7 @@ void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k,
     if (n <= 0) return;
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     SKG_DISPATCH(e, (pathCountKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.ctr(), c.cartSmem, n, d_r, d_k, d_counts)));
-    SKG_CUDA(cudaGetLastError());
+    e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
 void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
@@ -154,7 +154,7 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, n, d_r, d_k, d_ell, ellStride,
                                                                                 d_offsets, d_m, d_ds, d_s, d_dtau, d_tau)));
-    SKG_CUDA(cudaGetLastError());
+    e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
 void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
@@ -165,7 +165,7 @@ void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     SKG_DISPATCH(e, (opticalDepthKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, n, d_r, d_k, d_ell, ellStride,
                                                                                     d_dist, d_tau)));
-    SKG_CUDA(cudaGetLastError());
+    e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
 void launchWhichCell(Engine& e, int64_t n, const double* d_r, int* d_m)
@@ -173,7 +173,7 @@ void launchWhichCell(Engine& e, int64_t n, const double* d_r, int* d_m)
     if (n <= 0) return;
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     SKG_DISPATCH(e, (whichCellKernel<K><<<c.blocks, 128, 0, e.stream>>>(G, e.ctr(), n, d_r, d_m)));
-    SKG_CUDA(cudaGetLastError());
+    e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
 __global__ void setLastOffset(const int* counts, int64_t* offsets, int64_t n)
@@ -188,9 +188,10 @@ void exclusiveScan(Engine& e, int64_t n, const int* d_counts, int64_t* d_offsets
     // int32 counts -> int64 offsets
     cub::DeviceScan::ExclusiveScan(nullptr, tmp, d_counts, d_offsets, cub::Sum(), (int64_t)0, n, e.stream);
     e.scratchCub.ensure(tmp);
+    e.launches += 2;   // cub's scan is two kernels
     SKG_CUDA(cub::DeviceScan::ExclusiveScan(e.scratchCub.p, tmp, d_counts, d_offsets, cub::Sum(), (int64_t)0, n, e.stream));
     setLastOffset<<<1, 1, 0, e.stream>>>(d_counts, d_offsets, n);
-    SKG_CUDA(cudaGetLastError());
+    e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
 }   // namespace skg

@@ -60,6 +60,8 @@ struct Counters
     unsigned long long paths;               // traversals
     unsigned long long scatterings;
     unsigned long long packets;
+    unsigned long long absorbSegments;      // segments that updated the absorption table (one fp64 atomic each)
+    unsigned long long detections;          // detector updates (one fp64 atomic each)
     unsigned long long pad;
 };
 

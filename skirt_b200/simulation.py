@@ -1,0 +1,436 @@
+"""Host-side mirror of the reference's simulation items for the propagation hot path.
+
+Class names, attribute names, defaults and error messages follow the reference's SimulationItem classes
+so that a ski file maps one-to-one (MonteCarloSimulation, DustSystem, DustGrid, StellarSystem,
+Instrument -- BASELINE.json north_star).  Each class only carries what the hot path needs: it flattens
+its state into the POD tables of include/skirtgpu.h and hands them to the engine.  All per-packet work
+runs in libskirtgpu.so on the GPU; nothing here walks a grid or shoots a packet, and there is no CPU
+fallback.  Set-up arithmetic (meshes, densities, tables) is numpy.
+"""
+import json
+import math
+import os
+
+import numpy as np
+
+from .binding import Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE
+
+PC = 3.08567758e16          # Units.cpp:17-30
+LSUN = 3.839e26
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+class FatalError(EngineError):
+    """FATALERROR of the reference (FatalError.hpp:47)"""
+
+
+# ---- wavelength grids -----------------------------------------------------------------------------------
+class OligoWavelengthGrid:
+    """OligoWavelengthGrid.cpp:25-26: nominal bin width 0.001*lambda"""
+    def __init__(self, wavelengths):
+        self.lambdav = np.array(wavelengths, dtype=np.float64)
+        if len(self.lambdav) < 1:
+            raise FatalError("There must be at least one wavelength in the grid")
+        self.dlambdav = 0.001 * self.lambdav
+
+    @property
+    def Nlambda(self):
+        return len(self.lambdav)
+
+
+class LogWavelengthGrid:
+    """LogWavelengthGrid.cpp:18-28 (NR::loggrid, NR.hpp:269-275) + PanWavelengthGrid bin widths (:25-37)"""
+    def __init__(self, minWavelength, maxWavelength, points):
+        if minWavelength <= 0:
+            raise FatalError("the shortest wavelength should be positive")
+        if maxWavelength <= minWavelength:
+            raise FatalError("the longest wavelength should be larger than the shortest")
+        if points < 3:
+            raise FatalError("There must be at least three bins in a panchromatic wavelength grid")
+        n = points - 1
+        logxmin = math.log10(minWavelength); dlogx = math.log10(maxWavelength / minWavelength) / n
+        self.lambdav = np.array([10.0 ** (logxmin + i * dlogx) for i in range(n + 1)])
+        lo = np.concatenate([[self.lambdav[0]], np.sqrt(self.lambdav[:-1] * self.lambdav[1:])])
+        hi = np.concatenate([np.sqrt(self.lambdav[:-1] * self.lambdav[1:]), [self.lambdav[-1]]])
+        self.dlambdav = hi - lo
+
+    @property
+    def Nlambda(self):
+        return len(self.lambdav)
+
+
+# ---- 1-D meshes (Mesh / MoveableMesh subclasses; NR.hpp:171-261) ------------------------------------------
+class LinMesh:
+    def __init__(self, numBins):
+        self.numBins = int(numBins)
+
+    def mesh(self):
+        n = self.numBins
+        return np.array([0.0 + i * ((1.0 - 0.0) / n) for i in range(n + 1)])
+
+
+class SymPowMesh:
+    def __init__(self, numBins, ratio):
+        self.numBins = int(numBins); self.ratio = float(ratio)
+
+    def mesh(self):
+        n, ratio = self.numBins, self.ratio
+        if abs(ratio - 1.) < 1e-3:
+            return LinMesh(n).mesh()
+        xv = np.zeros(n + 1); xmin, xmax = 0.0, 1.0; xc = 0.5 * (xmin + xmax)
+        if n % 2 == 0:
+            M = n // 2; q = ratio ** (1.0 / (M - 1.0)); qM = q ** M
+            xv[M] = xc
+            for i in range(1, M + 1):
+                dxi = (1.0 - q ** i) / (1.0 - qM) * 0.5 * (xmax - xmin)
+                xv[M + i] = xc + dxi; xv[M - i] = xc - dxi
+        else:
+            M = (n + 1) // 2; q = ratio ** (1.0 / (M - 1.0)); qM = q ** M        # NR.hpp:248-259
+            for i in range(1, M + 1):
+                dxi = (0.5 + 0.5 * q - q ** i) / (0.5 + 0.5 * q - qM) * 0.5 * (xmax - xmin)
+                xv[M - 1 + i] = xc + dxi; xv[M - i] = xc - dxi
+        return xv
+
+
+# ---- geometries ---------------------------------------------------------------------------------------------
+class ExpDiskGeometry:
+    """ExpDiskGeometry.cpp:22-43 (normalisation), :117-129 (density), :177-187 (SigmaZ)"""
+    def __init__(self, radialScale, axialScale, radialTrunc=0.0, axialTrunc=0.0, innerRadius=0.0):
+        self.hR, self.hz, self.Rmax, self.zmax, self.Rmin = map(float, (radialScale, axialScale, radialTrunc, axialTrunc, innerRadius))
+        if self.hR <= 0:
+            raise FatalError("The radial scale length hR should be positive")
+        if self.hz <= 0:
+            raise FatalError("The axial scale height hz should be positive")
+        intphi = 2.0 * math.pi
+        intz = -2.0 * self.hz * math.expm1(-self.zmax / self.hz) if self.zmax > 0 else 2.0 * self.hz
+        tmin = math.exp(-self.Rmin / self.hR) * (1.0 + self.Rmin / self.hR) if self.Rmin > 0 else 1.0
+        tmax = math.exp(-self.Rmax / self.hR) * (1.0 + self.Rmax / self.hR) if self.Rmax > 0 else 0.0
+        self.rho0 = 1.0 / (self.hR * self.hR * (tmin - tmax) * intphi * intz)
+
+    def density(self, x, y, z):
+        R = np.hypot(x, y); absz = np.abs(z)
+        rho = self.rho0 * np.exp(-R / self.hR) * np.exp(-absz / self.hz)
+        if self.Rmax > 0:
+            rho = np.where(R > self.Rmax, 0.0, rho)
+        if self.zmax > 0:
+            rho = np.where(absz > self.zmax, 0.0, rho)
+        return np.where(R < self.Rmin, 0.0, rho)
+
+    def SigmaZ(self):
+        if self.Rmin > 0:
+            return 0.0
+        return 2.0 * self.rho0 * self.hz * (-math.expm1(-self.zmax / self.hz) if self.zmax > 0 else 1.0)
+
+    def sampler(self):
+        return dict(geometry=GEOM_EXPDISK, p=[self.hR, self.hz, self.Rmax, self.zmax, self.Rmin])
+
+
+class SersicFunction:
+    """SersicFunction.cpp:18-78: tabulated Sersic profile S(s) and cumulative mass M(s) on 101 log-spaced radii"""
+    def __init__(self, n):
+        if n < 0.5 or n > 10.0:
+            raise FatalError(f"The Sersic parameter should be between 0.5 and 10 (n = {n})")
+        b = 2.0 * n - 1.0 / 3.0 + 4.0 / 405.0 / n + 46.0 / 25515.0 / (n * n) + 131.0 / 1148175.0 / (n * n * n)
+        I0 = b ** (2.0 * n) / (math.pi * math.gamma(2.0 * n + 1))
+        Ns = 101; logsmin, logsmax = -6.0, 4.0; dlogs = (logsmax - logsmin) / (Ns - 1.0)
+        sv = 10.0 ** (logsmin + np.arange(Ns) * dlogs)
+        Nu = 10000; tmax = 100.0; umax = math.sqrt((tmax + 1.0) * (tmax - 1.0)); du = umax / Nu
+        u = np.arange(Nu + 1) * du; u2 = u * u
+        with np.errstate(divide="ignore", invalid="ignore"):
+            w = np.where(u > 1e-3, ((1.0 + u2) ** (2.0 * n) - 1.0) / np.where(u2 > 0, u2, 1.0),
+                         2.0 * n + n * (2.0 * n - 1.0) * u2 + 2.0 / 3.0 * n * (2.0 * n - 1.0) * (n - 1.0) * u2 * u2)
+        weight = np.ones(Nu + 1); weight[0] = weight[-1] = 0.5
+        Sv = np.zeros(Ns)
+        for i in range(Ns):
+            alpha = b * sv[i] ** (1.0 / n)
+            integrand = 2.0 * np.exp(-alpha * (1.0 + u2)) / np.sqrt(w)
+            Sv[i] = I0 * b ** n * alpha ** (1.0 - n) / math.pi * du * float(np.sum(weight * integrand))
+        self.sv, self.Sv = sv, Sv
+        Mv = np.zeros(Ns)
+        wj = np.ones(33); wj[0] = wj[-1] = 0.5
+        for i in range(1, Ns):
+            ds = (sv[i] - sv[i - 1]) / 32.0
+            s = sv[i - 1] + np.arange(33) * ds
+            S = self(s)
+            Mv[i] = Mv[i - 1] + 4.0 * math.pi * float(np.sum(wj * S * s * s * ds))
+        self.Mv = Mv / Mv[-1]
+
+    def __call__(self, s):
+        s = np.atleast_1d(np.asarray(s, dtype=np.float64))
+        i = np.clip(np.searchsorted(self.sv, s, side="right") - 1, 0, len(self.sv) - 2)
+        x = np.log10(np.clip(s, self.sv[0], self.sv[-1])); x1 = np.log10(self.sv[i]); x2 = np.log10(self.sv[i + 1])
+        f1 = np.log10(self.Sv[i]); f2 = np.log10(self.Sv[i + 1])
+        return 10.0 ** (f1 + (x - x1) / (x2 - x1) * (f2 - f1))
+
+
+class SersicGeometry:
+    """SersicGeometry.cpp:30-91 (+ SpheroidalGeometryDecorator.cpp:78-85 when flattening != 1)"""
+    def __init__(self, index, radius, flattening=1.0):
+        if index <= 0.5 or index > 10:
+            raise FatalError("the Sersic index n should be between 0.5 and 10")
+        if radius <= 0:
+            raise FatalError("the effective radius should be positive")
+        self.n, self.reff, self.q = float(index), float(radius), float(flattening)
+        self.fn = SersicFunction(self.n)
+        self.rho0 = 1.0 / self.reff ** 3
+
+    def density(self, x, y, z):
+        r = np.sqrt(x * x + y * y + (z / self.q) ** 2)
+        return self.rho0 / self.q * self.fn(r / self.reff).reshape(np.shape(r))
+
+    def sampler(self):
+        return dict(geometry=GEOM_SERSIC, n=self.n, p=[self.reff, self.q], rv=self.fn.sv, Xv=self.fn.Mv)
+
+
+class SpiralStructureGeometryDecorator:
+    """SpiralStructureGeometryDecorator.cpp:24-45,177-229"""
+    def __init__(self, geometry, arms, pitch, radius, phase, perturbWeight, index):
+        self.geometry = geometry
+        self.m, self.p, self.R0, self.phi0, self.w, self.N = int(arms), float(pitch), float(radius), float(phase), float(perturbWeight), int(index)
+        if self.m <= 0:
+            raise FatalError("The number of spiral arms should be positive")
+        if self.p <= 0 or self.p >= math.pi / 2.:
+            raise FatalError("The pitch angle should be between 0 and 90 degrees")
+        self.tanp = math.tan(self.p)
+        self.CN = math.sqrt(math.pi) * math.gamma(self.N + 1.0) / math.gamma(self.N + 0.5)
+
+    def density(self, x, y, z):
+        R = np.hypot(x, y); phi = np.arctan2(y, x)
+        with np.errstate(divide="ignore"):
+            gamma = np.log(R / self.R0) / self.tanp + self.phi0 + 0.5 * math.pi / self.m
+        pert = (1.0 - self.w) + self.w * self.CN * np.sin(0.5 * self.m * (gamma - phi)) ** (2 * self.N)
+        return self.geometry.density(x, y, z) * np.where(R > 0, pert, 1.0)
+
+    def SigmaZ(self):
+        return self.geometry.SigmaZ()
+
+    def sampler(self):
+        s = self.geometry.sampler()
+        s["spiral"] = dict(arms=self.m, pitch=self.p, radius=self.R0, phase=self.phi0, weight=self.w, index=self.N)
+        return s
+
+
+# ---- dust mix ---------------------------------------------------------------------------------------------------
+class InterstellarDustMix:
+    """kappa_abs, kappa_sca, g on the simulation's wavelength grid.  The reference reads
+    dat/DustMix/InterstellarDustMix.dat and resamples log-log / log-lin (InterstellarDustMix.cpp:21-58,
+    DustMix.cpp:300-321); here the same resampling is applied to the 256-point table in skirt_b200/data
+    (derived from that file by tools/make_dustmix_table.py)."""
+    def __init__(self, lambdagrid):
+        t = json.load(open(os.path.join(_DATA, "interstellar_dustmix.json")))
+        lam = np.array(t["lambda_m"]); lg = np.asarray(lambdagrid.lambdav)
+        eps = 0.5e-5
+        if lg[0] < lam[0] * (1 - eps) or lg[-1] > lam[-1] * (1 + eps):
+            raise FatalError("Properties for this dust population are only defined for wavelengths between "
+                             f"{lam[0]*1e6:g} and {lam[-1]*1e6:g} micron")
+        ll = np.log10(lam); x = np.log10(lg)
+        tiny = 1e-300
+        self.kappaabs = 10.0 ** np.interp(x, ll, np.log10(np.maximum(t["kappa_abs"], tiny)))
+        self.kappasca = 10.0 ** np.interp(x, ll, np.log10(np.maximum(t["kappa_sca"], tiny)))
+        self.asymmpar = np.interp(x, ll, np.array(t["asymmpar"]))
+        self.kappaext = self.kappaabs + self.kappasca
+
+    def kappaext_at(self, lambdagrid, lam):
+        return float(10.0 ** np.interp(math.log10(lam), np.log10(lambdagrid.lambdav), np.log10(self.kappaext)))
+
+
+class TableDustMix:
+    def __init__(self, kappaabs, kappasca, asymmpar):
+        self.kappaabs = np.atleast_1d(np.asarray(kappaabs, dtype=np.float64)); self.kappasca = np.atleast_1d(np.asarray(kappasca, dtype=np.float64))
+        self.asymmpar = np.atleast_1d(np.asarray(asymmpar, dtype=np.float64)); self.kappaext = self.kappaabs + self.kappasca
+
+
+# ---- dust grids ---------------------------------------------------------------------------------------------------
+class CartesianDustGrid:
+    """CartesianDustGrid.cpp:28-43: borders = mesh*(max-min)+min; cell m = k + Nz*j + Nz*Ny*i (:326-329)"""
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, meshX, meshY, meshZ):
+        if maxX <= minX:
+            raise FatalError("The extent of the box should be positive in the X direction")
+        if maxY <= minY:
+            raise FatalError("The extent of the box should be positive in the Y direction")
+        if maxZ <= minZ:
+            raise FatalError("The extent of the box should be positive in the Z direction")
+        self.extent = (minX, maxX, minY, maxY, minZ, maxZ)
+        self.xv = meshX.mesh() * (maxX - minX) + minX
+        self.yv = meshY.mesh() * (maxY - minY) + minY
+        self.zv = meshZ.mesh() * (maxZ - minZ) + minZ
+
+    def numCells(self):
+        return (len(self.xv) - 1) * (len(self.yv) - 1) * (len(self.zv) - 1)
+
+    def tables(self):
+        return dict(kind="cartesian", xv=self.xv, yv=self.yv, zv=self.zv)
+
+    def cell_samples(self, nsub=2):
+        """stratified sub-cell sample positions [nsub^3, Ncells, 3] and volumes [Ncells] in cell-number order"""
+        cx = [(a[:-1], a[1:]) for a in (self.xv, self.yv, self.zv)]
+        fr = (np.arange(nsub) + 0.5) / nsub
+        lo = np.stack(np.meshgrid(cx[0][0], cx[1][0], cx[2][0], indexing="ij"), axis=-1).reshape(-1, 3)
+        hi = np.stack(np.meshgrid(cx[0][1], cx[1][1], cx[2][1], indexing="ij"), axis=-1).reshape(-1, 3)
+        vol = np.prod(hi - lo, axis=1)
+        pts = [lo + np.array([fx, fy, fz]) * (hi - lo) for fx in fr for fy in fr for fz in fr]
+        return np.array(pts), vol
+
+
+class TreeTablesDustGrid:
+    """A tree / adaptive mesh / Voronoi grid given by its flattened tables (see include/skirtgpu.h)."""
+    def __init__(self, tables):
+        self._t = tables
+
+    def tables(self):
+        return self._t
+
+
+# ---- dust system --------------------------------------------------------------------------------------------------
+class DustComp:
+    """DustComp + FaceOnDustCompNormalization (FaceOnDustCompNormalization.cpp:67-74): rho scaled so that the
+    face-on optical depth at `wavelength` equals `opticalDepth`"""
+    def __init__(self, geometry, mix, opticalDepth, wavelength):
+        self.geometry, self.mix, self.tau, self.lam = geometry, mix, float(opticalDepth), float(wavelength)
+
+
+class DustSystem:
+    """DustSystem: density table _rhovv(m,h) (DustSystem.hpp:434) + per-component kappa tables.
+    The reference averages 100 random density samples per cell (DustSystem.cpp:152-177); here a
+    deterministic stratified nsub^3 lattice per cell is used (set-up only; the hot path only sees the table)."""
+    def __init__(self, grid, components, lambdagrid, sampleLattice=2, rho=None):
+        self.grid, self.comps, self.lambdagrid = grid, list(components), lambdagrid
+        if not self.comps:
+            raise FatalError("There are no dust components")
+        self.kext = np.array([c.mix.kappaext for c in self.comps])
+        self.ksca = np.array([c.mix.kappasca for c in self.comps])
+        self.g = np.array([c.mix.asymmpar for c in self.comps])
+        if rho is not None:
+            self.rho = np.asarray(rho, dtype=np.float64)
+            return
+        pts, _ = grid.cell_samples(sampleLattice)
+        cols = []
+        for c in self.comps:
+            kv = float(10.0 ** np.interp(math.log10(c.lam), np.log10(lambdagrid.lambdav), np.log10(c.mix.kappaext))) \
+                if lambdagrid.Nlambda > 1 else float(c.mix.kappaext[0])
+            scale = c.tau / (c.geometry.SigmaZ() * kv)
+            dens = np.zeros(pts.shape[1])
+            for p in pts:
+                dens += c.geometry.density(p[:, 0], p[:, 1], p[:, 2])
+            cols.append(scale * dens / len(pts))
+        self.rho = np.stack(cols, axis=1)
+
+    def medium(self):
+        return dict(rho=self.rho, kext=self.kext, ksca=self.ksca, g=self.g)
+
+
+# ---- stellar system ---------------------------------------------------------------------------------------------------
+def planck_lambda(lam, T):
+    h, c, k = 6.62606957e-34, 2.99792458e8, 1.3806488e-23
+    x = h * c / (lam * k * T)
+    return 2.0 * h * c * c / lam ** 5 / np.expm1(x)
+
+
+class StellarComp:
+    """GeometricStellarComp with per-wavelength luminosities L[ell] (W); `blackbody` builds them like a
+    PanStellarComp with BlackBodySED + bolometric normalisation (luminosities = SED(lambda)*dlambda)."""
+    def __init__(self, geometry, luminosities):
+        self.geometry = geometry; self.Lv = np.asarray(luminosities, dtype=np.float64)
+
+    @staticmethod
+    def blackbody(geometry, lambdagrid, temperature, Lbol):
+        B = planck_lambda(lambdagrid.lambdav, temperature) * lambdagrid.dlambdav
+        return StellarComp(geometry, Lbol * B / B.sum())
+
+
+class StellarSystem:
+    def __init__(self, components, emissionBias=0.5):
+        self.comps = list(components); self.emissionBias = float(emissionBias)
+
+    def luminosities(self):
+        return np.array([c.Lv for c in self.comps])
+
+
+# ---- instruments ----------------------------------------------------------------------------------------------------------
+class _DistantInstrument:
+    kind = 0
+
+    def __init__(self, instrumentName, distance, inclination, azimuth=0.0, positionAngle=0.0, pixelsX=0, fieldOfViewX=0.0,
+                 pixelsY=0, fieldOfViewY=0.0, centerX=0.0, centerY=0.0):
+        if distance <= 0:
+            raise FatalError("Distance was not set")
+        self.name = instrumentName
+        self.d = dict(kind=self.kind, name=instrumentName, distance=float(distance), inclination=float(inclination),
+                      azimuth=float(azimuth), positionAngle=float(positionAngle), Nxp=int(pixelsX), Nyp=int(pixelsY),
+                      fovxp=float(fieldOfViewX), fovyp=float(fieldOfViewY), xpc=float(centerX), ypc=float(centerY))
+        if self.kind != INSTR_SED and (pixelsX <= 0 or pixelsY <= 0):
+            raise FatalError("Number of pixels was not set")
+
+
+class FrameInstrument(_DistantInstrument):
+    kind = INSTR_FRAME
+
+
+class SEDInstrument(_DistantInstrument):
+    kind = INSTR_SED
+
+
+class SimpleInstrument(_DistantInstrument):
+    kind = INSTR_SIMPLE
+
+
+class InstrumentSystem:
+    def __init__(self, instruments):
+        self.instruments = list(instruments)
+
+
+# ---- the simulation -------------------------------------------------------------------------------------------------------------
+class MonteCarloSimulation:
+    """MonteCarloSimulation (MonteCarloSimulation.cpp:31-36 defaults): owns the engine(s) and drives the
+    photon shooting phases.  `packages` is the number of packets per wavelength, like the ski property."""
+    def __init__(self, wavelengthGrid, stellarSystem, dustSystem, instrumentSystem, packages=1e6, minWeightReduction=1e4,
+                 minScattEvents=0.0, scattBias=0.5, seed=4357, storeAbsorption=False, device=0, rank=0, nranks=1):
+        self.lambdagrid, self.ss, self.ds, self.isys = wavelengthGrid, stellarSystem, dustSystem, instrumentSystem
+        self.packages = float(packages); self.mwr = float(minWeightReduction); self.minfs = float(minScattEvents)
+        self.xi = float(scattBias); self.seed = int(seed); self.storeabs = bool(storeAbsorption)
+        if self.packages < 0:
+            raise FatalError("Number of photon packages is negative")
+        if self.packages > 1e15:
+            raise FatalError("Number of photon packages is larger than implementation limit of 1e15")     # MonteCarloSimulation.cpp:62-63
+        self.rank, self.nranks = int(rank), int(nranks)
+        self.engine = Engine(device)
+        self._setup = False
+
+    def setup(self):
+        """uploads every table (the engine-side equivalent of Simulation::setup)"""
+        e = self.engine
+        e.set_grid(self.ds.grid.tables())
+        m = self.ds.medium()
+        e.medium(m["rho"], m["kext"], m["ksca"], m["g"])
+        e.sources([c.geometry.sampler() for c in self.ss.comps], self.ss.luminosities(), self.ss.emissionBias)
+        e.instruments([i.d for i in self.isys.instruments])
+        self._setup = True
+        return self
+
+    def packets_per_rank(self):
+        """IdenticalAssigner/SequentialAssigner block split of the packet budget over processes
+        (IdenticalAssigner.cpp:37-58): every rank shoots ceil(packages/nranks) packets per wavelength"""
+        return math.ceil(self.packages / self.nranks)
+
+    def runstellaremission(self):
+        """MonteCarloSimulation::runstellaremission (MonteCarloSimulation.cpp:251-261)"""
+        if not self._setup:
+            raise FatalError("Simulation has not been setup before being run")
+        npr = self.packets_per_rank()
+        st = self.engine.run_stellar(npr, total_packages=npr * self.nranks, min_weight_reduction=self.mwr,
+                                     min_scatt_events=self.minfs, scatt_bias=self.xi, store_absorption=self.storeabs,
+                                     seed=self.seed, stream_offset=self.rank * npr)
+        if self.nranks > 1:
+            self.engine.allreduce_results()      # Instrument::sumResults / PanDustSystem::sumResults
+        return st
+
+    def results(self):
+        out = {}
+        for i, ins in enumerate(self.isys.instruments):
+            if ins.kind != INSTR_SED:
+                out[ins.name + "_frame"] = self.engine.fetch_frame(i).reshape(self.lambdagrid.Nlambda, ins.d["Nyp"], ins.d["Nxp"])
+            if ins.kind != INSTR_FRAME:
+                out[ins.name + "_sed"] = self.engine.fetch_sed(i)
+        if self.storeabs:
+            out["Labs"] = self.engine.fetch_labs()
+        return out

@@ -248,3 +248,42 @@ def setup_engine(e, cfg, tables, medium, L=None):
     e.sources(cfg["sources"], L, cfg.get("ebias", 0.5))
     e.instruments(cfg["instruments"])
     return e
+
+
+# ---- golden fixtures (tests/golden/*.npz, generated from the reference by tests/golden/make_golden.py) ---------
+GEOM_CASES = ["cart_lin", "cart_sympow", "octtree_s0", "octtree_s1", "octtree_s2", "bintree_s0", "bintree_s1", "amesh", "voronoi"]
+
+
+def load_golden(name):
+    """-> (tables, medium, data) of one geometry fixture; data holds rays and the reference's answers"""
+    z = np.load(os.path.join(GOLDEN, f"geom_{name}.npz"))
+    tables, medium, data = {}, {}, {}
+    for key in z.files:
+        v = z[key]
+        if key.startswith("grid_"):
+            k2 = key[5:]
+            if k2 == "kind":
+                v = str(v)
+            elif v.ndim == 0:
+                v = v.item()
+            tables[k2] = v
+        elif key.startswith("med_"):
+            medium[key[4:]] = v
+        else:
+            data[key] = v
+    data["paths"] = {k[5:]: data.pop(k) for k in list(data) if k.startswith("path_")}
+    return tables, medium, data
+
+
+def load_golden_mc():
+    z = np.load(os.path.join(GOLDEN, "mc_c1.npz"))
+    tables = {k[5:]: (str(z[k]) if k == "grid_kind" else z[k]) for k in z.files if k.startswith("grid_")}
+    medium = {k[4:]: z[k] for k in z.files if k.startswith("med_")}
+    data = {k: z[k] for k in z.files if not k.startswith(("grid_", "med_"))}
+    return tables, medium, data
+
+
+def zscores(mean_a, sem_a, mean_b, sem_b):
+    sig = np.sqrt(sem_a ** 2 + sem_b ** 2)
+    ok = sig > 0
+    return (mean_a - mean_b)[ok] / sig[ok]

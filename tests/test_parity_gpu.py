@@ -1,0 +1,94 @@
+"""GPU parity of the deterministic geometry (north_star gate 1): for fixed rays the engine's batched
+DustGrid::path()+fillOpticalDepth() must reproduce the reference's cell-index sequences bit-exactly and
+ds/s/dtau/tau to 1e-12 relative; whichcell() and opticaldepth() likewise.  Checked against the golden vectors
+generated from the reference's own code, through the C ABI (skirt_b200.binding -> libskirtgpu.so)."""
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-12        # north_star: segment lengths and optical depths to 1e-12 relative in fp64
+
+
+def _setup(engine, name):
+    tables, medium, data = common.load_golden(name)
+    engine.set_grid(tables)
+    engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    return tables, medium, data
+
+
+@pytest.mark.parametrize("name", common.GEOM_CASES)
+def test_paths_match_reference(engine, name):
+    _, _, d = _setup(engine, name)
+    got = engine.path_batch(d["r"], d["k"], ell=0)
+    common.assert_paths_equal(got, d["paths"], rtol=RTOL, label=name)
+    # the engine is built without FMA contraction so that it is in fact bit-identical
+    assert common.paths_bit_identical(got, d["paths"]), f"{name}: not bit-identical"
+
+
+@pytest.mark.parametrize("name", common.GEOM_CASES)
+def test_geometry_only_paths(engine, name):
+    _, _, d = _setup(engine, name)
+    got = engine.path_batch(d["r"], d["k"], ell=None)
+    assert np.array_equal(got["offsets"], d["paths"]["offsets"]) and np.array_equal(got["m"], d["paths"]["m"])
+    assert np.array_equal(got["ds"], d["paths"]["ds"]) and np.array_equal(got["s"], d["paths"]["s"])
+    assert not got["tau"].any() and not got["dtau"].any()
+
+
+@pytest.mark.parametrize("name", common.GEOM_CASES)
+def test_whichcell_and_opticaldepth(engine, name):
+    _, _, d = _setup(engine, name)
+    assert np.array_equal(engine.whichcell(d["r"]), d["whichcell"])
+    tau = engine.opticaldepth(d["r"], d["k"], 0)
+    np.testing.assert_allclose(tau, d["tau_inf"], rtol=RTOL, atol=0)
+    tau_d = engine.opticaldepth(d["r"], d["k"], 0, d["distance"])
+    np.testing.assert_allclose(tau_d, d["tau_dist"], rtol=RTOL, atol=0)
+
+
+def test_empty_and_error_paths(engine):
+    import skirt_b200 as sk
+    _setup(engine, "cart_lin")
+    got = engine.path_batch(np.zeros((0, 3)), np.zeros((0, 3)), ell=0)
+    assert got["offsets"].tolist() == [0] and len(got["m"]) == 0
+    # rays that miss the grid produce empty paths (the reference clears the path, CartesianDustGrid.cpp:151-224)
+    r = np.array([[1e30, 0, 0], [0, 0, 1e30]]); k = np.array([[1.0, 0, 0], [0, 0, 1.0]])
+    got = engine.path_batch(r, k, ell=0)
+    assert got["offsets"].tolist() == [0, 0, 0]
+    with pytest.raises(sk.EngineError, match="wavelength index"):
+        engine.path_batch(r, k, ell=5)
+    with pytest.raises(sk.EngineError):
+        engine.grid_cartesian([0.0, 1.0, 0.5], [0.0, 1.0], [0.0, 1.0])
+
+
+def test_full_size_properties(engine):
+    """C1/C2's full 100^3 grid with 2^18 rays: size-independent properties of a correct traversal --
+    the segment lengths of every path add up to the chord through the box, s is the running sum of ds,
+    tau is the running sum of dtau, dtau = kext*rho[m]*ds, cells along a path change by exactly one index step."""
+    from skirt_b200 import configs, simulation as sim
+    p = configs.c2_params()
+    lg = configs.wavelength_grid(p); b = p["box"]; n = p["n"]
+    grid = sim.CartesianDustGrid(b[0], b[1], b[2], b[3], b[4], b[5], sim.LinMesh(n), sim.LinMesh(n), sim.LinMesh(n))
+    rng = np.random.default_rng(5)
+    rho = rng.random(n ** 3) * 1e-22
+    kext = np.linspace(100.0, 3000.0, lg.Nlambda)
+    engine.set_grid(grid.tables()); engine.medium(rho, kext[None, :])
+    nr = 1 << 18
+    r, k = common.rays(nr, np.array(b), 77, scale=0.999)          # all starting inside
+    ell = rng.integers(0, lg.Nlambda, nr).astype(np.int32)
+    got = engine.path_batch(r, k, ell=ell)
+    off = got["offsets"]; cnt = np.diff(off)
+    assert cnt.min() >= 1 and got["m"].min() >= 0 and got["m"].max() < n ** 3
+    # chord length from the start to the exit face of the box
+    lo = np.array(b[0::2]); hi = np.array(b[1::2])
+    with np.errstate(divide="ignore"):
+        t = np.where(k > 0, (hi - r) / k, np.where(k < 0, (lo - r) / k, np.inf)).min(axis=1)
+    last = off[1:] - 1
+    np.testing.assert_allclose(got["s"][last], t, rtol=1e-9)
+    seg_ray = np.repeat(np.arange(nr), cnt)
+    np.testing.assert_allclose(np.add.reduceat(got["ds"], off[:-1]), got["s"][last], rtol=1e-12)
+    np.testing.assert_allclose(np.add.reduceat(got["dtau"], off[:-1]), got["tau"][last], rtol=1e-10, atol=1e-300)
+    assert np.array_equal(got["dtau"], (kext[ell[seg_ray]] * rho[got["m"]]) * got["ds"])
+    # consecutive cells differ by one step along exactly one axis
+    m = got["m"].astype(np.int64); dm = np.abs(np.diff(m)); inner = np.ones(len(m) - 1, bool); inner[last[:-1]] = False
+    assert np.isin(dm[inner], [1, n, n * n]).all()
