@@ -1,0 +1,826 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY (see skirt_oracle.hpp for the rules and the parity pinning).
+//
+// CPU restatement of the reference's DustGrid::path() family, DustGridPath and the optical-depth
+// integration, working on the flattened tables of include/skirtgpu.h.  Plain scalar C++, one ray at
+// a time, written from the reference text cited at every function; the product (skirt_b200/) never
+// links or calls this file.
+#include "skirt_oracle.hpp"
+
+#include <cfloat>
+#include <climits>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <thread>
+
+namespace orc
+{
+
+// =====================================================================================================
+// DustGridPath
+// =====================================================================================================
+
+// DustGridPath::moveInside, DustGridPath.cpp:57-150.  box = xmin,ymin,zmin,xmax,ymax,zmax.
+// The three axes are treated one after the other; each may add its own "outside" segment (m = -1).
+bool Path::moveInside(const double box[6], double eps, double& x, double& y, double& z)
+{
+    x = rx; y = ry; z = rz;
+    for (int a = 0; a < 3; a++)
+    {
+        double& c = (a == 0) ? x : (a == 1) ? y : z;
+        const double kc = (a == 0) ? kx : (a == 1) ? ky : kz;
+        const double lo = box[a], hi = box[3 + a];
+        double target, edge;
+        if (c <= lo) { if (kc <= 0.0) return false; edge = lo; target = lo + eps; }
+        else if (c >= hi) { if (kc >= 0.0) return false; edge = hi; target = hi - eps; }
+        else continue;
+        double ds = (edge - c) / kc;
+        add(-1, ds);
+        // the coordinate that crossed is put just inside; the other two advance along the ray
+        if (a != 0) x += kx * ds;
+        if (a != 1) y += ky * ds;
+        if (a != 2) z += kz * ds;
+        c = target;
+    }
+    return true;
+}
+
+// DustGridPath::pathlength, DustGridPath.cpp:162-173 with NR::locate<Segment> (NR.hpp:76-95) and
+// NR::interpolate_linlin (NR.hpp:296-299); Segment ordering is by tau (DustGridPath.hpp:165)
+double Path::pathlength(double tau) const
+{
+    int N = (int)v.size();
+    if (N > 0 && tau > 0)
+    {
+        int i;
+        if (tau < v[0].tau) i = -1;
+        else if (v[N - 1].tau < tau) i = N - 1;
+        else
+        {
+            int jl = -1, ju = N;
+            while (ju - jl > 1) { int jm = (ju + jl) >> 1; if (tau < v[jm].tau) ju = jm; else jl = jm; }
+            i = jl <= 0 ? 0 : (jl >= N - 2 ? N - 2 : jl);
+        }
+        auto linlin = [](double x, double x1, double x2, double f1, double f2) { return f1 + ((x - x1) / (x2 - x1)) * (f2 - f1); };
+        if (i < 0) return linlin(tau, 0, v[0].tau, 0, v[0].s);
+        if (i < N - 1) return linlin(tau, v[i].tau, v[i + 1].tau, v[i].s, v[i + 1].s);
+        return v[N - 1].s;
+    }
+    return 0;
+}
+
+// DustGridPath::fillOpticalDepth, DustGridPath.hpp:117-129
+void fillOpticalDepth(Path& p, const Medium& med, int ell)
+{
+    double tau = 0;
+    for (Seg& sg : p.v)
+    {
+        sg.dtau = med.kapparho(sg.m, ell) * sg.ds;
+        tau += sg.dtau;
+        sg.tau = tau;
+    }
+}
+
+// DustGridPath::opticalDepth(kapparho, distance), DustGridPath.hpp:97-108: the segment that overshoots
+// the distance is still counted in full
+double opticalDepth(const Path& p, const Medium& med, int ell, double distance)
+{
+    double tau = 0;
+    for (const Seg& sg : p.v)
+    {
+        tau += med.kapparho(sg.m, ell) * sg.ds;
+        if (sg.s > distance) break;
+    }
+    return tau;
+}
+
+namespace
+{
+
+// NR::locate_basic_impl, NR.hpp:99-112
+int locateBasic(const double* xv, double x, int n)
+{
+    int jl = -1, ju = n;
+    while (ju - jl > 1) { int jm = (ju + jl) >> 1; if (x < xv[jm]) ju = jm; else jl = jm; }
+    return jl;
+}
+int locateClip(const double* xv, int n, double x) { return x < xv[0] ? 0 : locateBasic(xv, x, n - 1); }     // NR.hpp:146-151
+int locateFail(const double* xv, int n, double x) { return x > xv[n - 1] ? -1 : locateBasic(xv, x, n - 1); } // NR.hpp:155-160
+
+// Box::contains, closed on every face (Box.hpp:94-95); b = xmin,ymin,zmin,xmax,ymax,zmax
+bool inBox(const double* b, double x, double y, double z)
+{
+    return x >= b[0] && x <= b[3] && y >= b[1] && y <= b[4] && z >= b[2] && z <= b[5];
+}
+
+// one axis of Box::cellindices, Box.hpp:134-139.  static_cast<int> of an out-of-range double is what
+// x86-64's cvttsd2si makes of it (INT_MIN), which the clamp then turns into 0.
+int boxIndex(double v, double vmin, double vmax, int n)
+{
+    double q = n * (v - vmin) / (vmax - vmin);
+    int i = (q >= 2147483648.0 || q <= -2147483649.0 || q != q) ? INT_MIN : static_cast<int>(q);
+    return std::max(0, std::min(n - 1, i));
+}
+
+double nextAlong(double v, double k) { return std::nextafter(v, (k < 0.0) ? -DBL_MAX : DBL_MAX); }
+
+double epsOf(const double* b)   // 1e-12 * extent.widths().norm(): TreeDustGrid.cpp:76, VoronoiMesh.cpp:234, AdaptiveMesh.cpp:52
+{
+    double wx = b[3] - b[0], wy = b[4] - b[1], wz = b[5] - b[2];
+    return 1e-12 * std::sqrt(wx * wx + wy * wy + wz * wz);
+}
+
+// exit distances towards the walls of a box along k (TreeDustGrid.cpp:416-421, AdaptiveMesh.cpp:317-322)
+struct Exit { double dsx, dsy, dsz, xnext, ynext, znext; };
+Exit exits(const double* b, double x, double y, double z, double kx, double ky, double kz)
+{
+    Exit e;
+    e.xnext = (kx < 0.0) ? b[0] : b[3];
+    e.ynext = (ky < 0.0) ? b[1] : b[4];
+    e.znext = (kz < 0.0) ? b[2] : b[5];
+    e.dsx = (std::fabs(kx) > 1e-15) ? (e.xnext - x) / kx : DBL_MAX;
+    e.dsy = (std::fabs(ky) > 1e-15) ? (e.ynext - y) / ky : DBL_MAX;
+    e.dsz = (std::fabs(kz) > 1e-15) ? (e.znext - z) / kz : DBL_MAX;
+    return e;
+}
+
+// =====================================================================================================
+// CartesianDustGrid
+// =====================================================================================================
+struct Cartesian : Grid
+{
+    std::vector<double> xv, yv, zv; int Nx, Ny, Nz;
+    double xmin, xmax, ymin, ymax, zmin, zmax;
+    int numCells() const override { return Nx * Ny * Nz; }
+    int index(int i, int j, int k) const { return k + Nz * j + Nz * Ny * i; }       // CartesianDustGrid.cpp:326-329
+
+    // CartesianDustGrid::whichcell, CartesianDustGrid.cpp:109-118
+    int whichcell(double x, double y, double z) const override
+    {
+        int i = locateFail(xv.data(), Nx + 1, x), j = locateFail(yv.data(), Ny + 1, y), k = locateFail(zv.data(), Nz + 1, z);
+        if (i < 0 || j < 0 || k < 0) return -1;
+        return index(i, j, k);
+    }
+
+    // CartesianDustGrid::path, CartesianDustGrid.cpp:136-283
+    void path(Path& p) const override
+    {
+        p.clear();
+        double x = p.rx, y = p.ry, z = p.rz; const double kx = p.kx, ky = p.ky, kz = p.kz;
+        double ds;
+        // entry from outside, :151-222 (strict comparisons, 1e-8 of the outermost bin width as nudge)
+        if (x < xmin) { if (kx <= 0.0) return p.clear(); ds = (xmin - x) / kx; p.add(-1, ds); x = xmin + 1e-8 * (xv[1] - xv[0]); y += ky * ds; z += kz * ds; }
+        else if (x > xmax) { if (kx >= 0.0) return p.clear(); ds = (xmax - x) / kx; p.add(-1, ds); x = xmax - 1e-8 * (xv[Nx] - xv[Nx - 1]); y += ky * ds; z += kz * ds; }
+        if (y < ymin) { if (ky <= 0.0) return p.clear(); ds = (ymin - y) / ky; p.add(-1, ds); x += kx * ds; y = ymin + 1e-8 * (yv[1] - yv[0]); z += kz * ds; }
+        else if (y > ymax) { if (ky >= 0.0) return p.clear(); ds = (ymax - y) / ky; p.add(-1, ds); x += kx * ds; y = ymax - 1e-8 * (yv[Ny] - yv[Ny - 1]); z += kz * ds; }
+        if (z < zmin) { if (kz <= 0.0) return p.clear(); ds = (zmin - z) / kz; p.add(-1, ds); x += kx * ds; y += ky * ds; z = zmin + 1e-8 * (zv[1] - zv[0]); }
+        else if (z > zmax) { if (kz >= 0.0) return p.clear(); ds = (zmax - z) / kz; p.add(-1, ds); x += kx * ds; y += ky * ds; z = zmax - 1e-8 * (zv[Nz] - zv[Nz - 1]); }
+        if (x < xmin || x > xmax || y < ymin || y > ymax || z < zmin || z > zmax) return p.clear();      // :224
+
+        int i = locateClip(xv.data(), Nx + 1, x), j = locateClip(yv.data(), Ny + 1, y), k = locateClip(zv.data(), Nz + 1, z);
+        if (!std::isfinite(x + y + z + kx + ky + kz)) return p.clear();     // the reference would loop forever on NaN input
+        while (true)    // :234-282
+        {
+            int m = index(i, j, k);
+            double xE = (kx < 0.0) ? xv[i] : xv[i + 1];
+            double yE = (ky < 0.0) ? yv[j] : yv[j + 1];
+            double zE = (kz < 0.0) ? zv[k] : zv[k + 1];
+            double dsx = (std::fabs(kx) > 1e-15) ? (xE - x) / kx : DBL_MAX;
+            double dsy = (std::fabs(ky) > 1e-15) ? (yE - y) / ky : DBL_MAX;
+            double dsz = (std::fabs(kz) > 1e-15) ? (zE - z) / kz : DBL_MAX;
+            if (dsx <= dsy && dsx <= dsz)
+            {
+                p.add(m, dsx);
+                i += (kx < 0.0) ? -1 : 1;
+                if (i >= Nx || i < 0) return;
+                x = xE; y += ky * dsx; z += kz * dsx;
+            }
+            else if (dsy < dsx && dsy <= dsz)
+            {
+                p.add(m, dsy);
+                j += (ky < 0.0) ? -1 : 1;
+                if (j >= Ny || j < 0) return;
+                x += kx * dsy; y = yE; z += kz * dsy;
+            }
+            else if (dsz < dsx && dsz < dsy)
+            {
+                p.add(m, dsz);
+                k += (kz < 0.0) ? -1 : 1;
+                if (k >= Nz || k < 0) return;
+                x += kx * dsz; y += ky * dsz; z = zE;
+            }
+            else return;
+        }
+    }
+
+    // CartesianDustGrid::randomPositionInCell, CartesianDustGrid.cpp:129-132 -> Random::position(Box), Random.cpp:226-234
+    void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
+};
+
+// =====================================================================================================
+// TreeDustGrid (octree / binary tree), nodes flattened in id order
+// =====================================================================================================
+struct Tree : Grid
+{
+    int kind, search, N, ncells = 0;
+    std::vector<double> box; std::vector<int> child0, parent, cell, dir, nbrStart, nbrIds;
+    double eps;
+    int numCells() const override { return ncells; }
+    const double* b(int l) const { return box.data() + 6 * (size_t)l; }
+
+    // TreeNode::whichnode(Vec) from the root, TreeNode.cpp:70-80; OctTreeNode::child (OctTreeNode.cpp:184-189)
+    // compares with the max corner of child 0, BinTreeNode::child (BinTreeNode.cpp:326-335) with its max along _dir
+    int whichnode(double x, double y, double z) const
+    {
+        if (!inBox(b(0), x, y, z)) return -1;
+        int node = 0;
+        while (child0[node] >= 0)
+        {
+            int c0 = child0[node]; const double* cb = b(c0);
+            if (kind == 0) node = c0 + ((x < cb[3]) ? 0 : 1) + ((y < cb[4]) ? 0 : 2) + ((z < cb[5]) ? 0 : 4);
+            else
+            {
+                int d = dir[node];
+                double v = d == 0 ? x : (d == 1 ? y : z);
+                node = (v < cb[3 + d]) ? c0 : c0 + 1;
+            }
+        }
+        return node;
+    }
+    int whichcell(double x, double y, double z) const override { int n = whichnode(x, y, z); return n >= 0 ? cell[n] : -1; }
+
+    // TreeDustGrid::path, TreeDustGrid.cpp:390-662
+    void path(Path& p) const override
+    {
+        p.clear();
+        double x, y, z;
+        const double kx = p.kx, ky = p.ky, kz = p.kz;
+        if (!std::isfinite(p.rx + p.ry + p.rz + kx + ky + kz)) return;
+        if (!p.moveInside(b(0), eps, x, y, z)) return p.clear();
+        int node = whichnode(x, y, z);
+        if (node < 0) return p.clear();
+
+        if (search == 0 || search == 1)
+        {
+            // TopDown :412-456 and Neighbor :460-521 differ only in how the next node is looked up
+            while (node >= 0)
+            {
+                Exit e = exits(b(node), x, y, z, kx, ky, kz);
+                double ds; int wall;    // walls BACK,FRONT,LEFT,RIGHT,BOTTOM,TOP = 0..5 (TreeNode.hpp:100)
+                if (e.dsx <= e.dsy && e.dsx <= e.dsz) { ds = e.dsx; wall = (kx < 0.0) ? 0 : 1; }
+                else if (e.dsy <= e.dsx && e.dsy <= e.dsz) { ds = e.dsy; wall = (ky < 0.0) ? 2 : 3; }
+                else { ds = e.dsz; wall = (kz < 0.0) ? 4 : 5; }
+                p.add(cell[node], ds);
+                x += (ds + eps) * kx; y += (ds + eps) * ky; z += (ds + eps) * kz;
+
+                int old = node;
+                if (search == 1)
+                {
+                    // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first listed neighbour whose closed box holds r
+                    node = -1;
+                    for (int q = nbrStart[6 * (size_t)old + wall]; q < nbrStart[6 * (size_t)old + wall + 1]; q++)
+                        if (inBox(b(nbrIds[q]), x, y, z)) { node = nbrIds[q]; break; }
+                    if (node < 0) node = whichnode(x, y, z);
+                }
+                else node = whichnode(x, y, z);
+
+                if (node == old)    // :437-454 / :502-519
+                {
+                    stuck++;
+                    x = nextAlong(x, kx); y = nextAlong(y, ky); z = nextAlong(z, kz);
+                    node = whichnode(x, y, z);
+                    if (node == old) { stuck++; break; }
+                }
+            }
+            return;
+        }
+
+        // Bookkeeping (octree only), :527-659: children of a node have ids 8q+1 .. 8q+8 relative order, so the
+        // octant of node l within its father is ((l-1)%8)
+        int l = node;
+        while (true)
+        {
+            Exit e = exits(b(l), x, y, z, kx, ky, kz);
+            if (e.dsx <= e.dsy && e.dsx <= e.dsz)
+            {
+                p.add(cell[l], e.dsx);
+                x = e.xnext; y += ky * e.dsx; z += kz * e.dsx;
+                while (true)
+                {
+                    int oct = ((l - 1) % 8) + 1;
+                    bool place = (kx < 0.0) ? (oct % 2 == 1) : (oct % 2 == 0);
+                    if (!place) break;
+                    l = parent[l];
+                    if (l == 0) return;
+                }
+                l += (kx < 0.0) ? -1 : 1;
+                while (cell[l] == -1)
+                {
+                    int c0 = child0[l]; double yM = b(c0)[4], zM = b(c0)[5];
+                    int base = (kx < 0.0) ? 1 : 0;
+                    l = c0 + base + ((y <= yM) ? 0 : 2) + ((z <= zM) ? 0 : 4);
+                }
+            }
+            else if (e.dsy < e.dsx && e.dsy <= e.dsz)
+            {
+                p.add(cell[l], e.dsy);
+                x += kx * e.dsy; y = e.ynext; z += kz * e.dsy;
+                while (true)
+                {
+                    bool place = (ky < 0.0) ? ((l - 1) % 4 < 2) : ((l - 1) % 4 > 1);
+                    if (!place) break;
+                    l = parent[l];
+                    if (l == 0) return;
+                }
+                l += (ky < 0.0) ? -2 : 2;
+                while (cell[l] == -1)
+                {
+                    int c0 = child0[l]; double xM = b(c0)[3], zM = b(c0)[5];
+                    int base = (ky < 0.0) ? 2 : 0;
+                    l = c0 + base + ((x <= xM) ? 0 : 1) + ((z <= zM) ? 0 : 4);
+                }
+            }
+            else if (e.dsz < e.dsx && e.dsz < e.dsy)
+            {
+                p.add(cell[l], e.dsz);
+                x += kx * e.dsz; y += ky * e.dsz; z = e.znext;
+                while (true)
+                {
+                    int oct = ((l - 1) % 8) + 1;
+                    bool place = (kz < 0.0) ? (oct < 5) : (oct > 4);
+                    if (!place) break;
+                    l = parent[l];
+                    if (l == 0) return;
+                }
+                l += (kz < 0.0) ? -4 : 4;
+                while (cell[l] == -1)
+                {
+                    int c0 = child0[l]; double xM = b(c0)[3], yM = b(c0)[4];
+                    int base = (kz < 0.0) ? 4 : 0;
+                    l = c0 + base + ((x <= xM) ? 0 : 1) + ((y <= yM) ? 0 : 2);
+                }
+            }
+            else return;
+        }
+    }
+    void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
+    std::vector<int> leafOfCell;
+};
+
+// =====================================================================================================
+// AdaptiveMesh
+// =====================================================================================================
+struct AMesh : Grid
+{
+    int N, ncells = 0;
+    std::vector<double> box; std::vector<int> nxyz, child0, cell, wallNbr;
+    double eps;
+    mutable long errors = 0;
+    int numCells() const override { return ncells; }
+    const double* b(int l) const { return box.data() + 6 * (size_t)l; }
+
+    // AdaptiveMeshNode::whichnode(Vec) :132-142 with child() :109-128; -2 stands for the FATALERROR
+    int whichnode(double x, double y, double z) const
+    {
+        if (!inBox(b(0), x, y, z)) return -1;
+        int node = 0;
+        while (child0[node] >= 0)
+        {
+            const double* nb = b(node);
+            int Nx = nxyz[3 * node], Ny = nxyz[3 * node + 1], Nz = nxyz[3 * node + 2];
+            int i = boxIndex(x, nb[0], nb[3], Nx), j = boxIndex(y, nb[1], nb[4], Ny), k = boxIndex(z, nb[2], nb[5], Nz);
+            int c = child0[node] + (k * Ny + j) * Nx + i;
+            if (!inBox(b(c), x, y, z))
+            {
+                const double* cb = b(c);
+                if (x < cb[0]) i--; else if (x > cb[3]) i++;
+                if (y < cb[1]) j--; else if (y > cb[4]) j++;
+                if (z < cb[2]) k--; else if (z > cb[5]) k++;
+                if (i < 0 || i >= Nx || j < 0 || j >= Ny || k < 0 || k >= Nz) return -2;
+                c = child0[node] + (k * Ny + j) * Nx + i;
+                if (!inBox(b(c), x, y, z)) return -2;
+            }
+            node = c;
+        }
+        return node;
+    }
+    int whichcell(double x, double y, double z) const override { int n = whichnode(x, y, z); return n >= 0 ? cell[n] : -1; }
+
+    // AdaptiveMesh::path, AdaptiveMesh.cpp:297-367
+    void path(Path& p) const override
+    {
+        p.clear();
+        double x, y, z;
+        const double kx = p.kx, ky = p.ky, kz = p.kz;
+        if (!std::isfinite(p.rx + p.ry + p.rz + kx + ky + kz)) return;
+        if (!p.moveInside(b(0), eps, x, y, z)) return p.clear();
+        int node = whichnode(x, y, z);
+        if (node < 0) { if (node == -2) errors++; return p.clear(); }
+        while (node >= 0)
+        {
+            Exit e = exits(b(node), x, y, z, kx, ky, kz);
+            double ds; int wall;
+            if (e.dsx <= e.dsy && e.dsx <= e.dsz) { ds = e.dsx; wall = (kx < 0.0) ? 0 : 1; }
+            else if (e.dsy <= e.dsx && e.dsy <= e.dsz) { ds = e.dsy; wall = (ky < 0.0) ? 2 : 3; }
+            else { ds = e.dsz; wall = (kz < 0.0) ? 4 : 5; }
+            p.add(cell[node], ds);
+            x += (ds + eps) * kx; y += (ds + eps) * ky; z += (ds + eps) * kz;      // r += (ds+_eps)*k
+
+            // AdaptiveMeshNode::whichnode(wall, r) :146-151: the single stored neighbour if its box holds r
+            int old = node;
+            int cand = wallNbr[6 * (size_t)old + wall];
+            node = (cand >= 0 && inBox(b(cand), x, y, z)) ? cand : whichnode(x, y, z);
+            if (node == -2) { errors++; return; }
+            if (node == old)
+            {
+                stuck++;
+                x = nextAlong(x, kx); y = nextAlong(y, ky); z = nextAlong(z, kz);
+                node = whichnode(x, y, z);
+                if (node == -2) { errors++; return; }
+                if (node == old) { stuck++; break; }
+            }
+        }
+    }
+    void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
+    std::vector<int> leafOfCell;
+};
+
+// =====================================================================================================
+// VoronoiMesh
+// =====================================================================================================
+struct Voronoi : Grid
+{
+    int N, nb;
+    std::vector<double> part, cellBox; std::vector<int> nbrStart, nbrIds, blkStart, blkIds, blkTree, kdM, kdAxis, kdUp, kdLeft, kdRight;
+    double ext[6];      // xmin,ymin,zmin,xmax,ymax,zmax
+    double eps;
+    mutable long errors = 0;
+    int numCells() const override { return N; }
+    const double* pt(int m) const { return part.data() + 3 * (size_t)m; }
+    double sd(int m, double x, double y, double z) const    // VoronoiCell::squaredDistanceTo, VoronoiMesh.cpp:63-64
+    { const double* q = pt(m); double dx = x - q[0], dy = y - q[1], dz = z - q[2]; return dx * dx + dy * dy + dz * dz; }
+
+    // lessthan(p1,p2,axis), VoronoiMesh.cpp:77-105: lexicographic with the split axis first, cyclic order after it
+    static bool lessthan(const double* p1, const double* p2, int axis)
+    {
+        for (int t = 0; t < 3; t++)
+        {
+            int a = (axis + t) % 3;
+            if (p1[a] < p2[a]) return true;
+            if (t < 2 && p1[a] > p2[a]) return false;
+        }
+        return false;
+    }
+
+    // Node::nearest, VoronoiMesh.cpp:180-225 (recursive like the reference)
+    int nearest(int top, const double* r) const
+    {
+        int current = top;
+        while (true)
+        {
+            int child = lessthan(r, pt(kdM[current]), kdAxis[current]) ? kdLeft[current] : kdRight[current];
+            if (child < 0) break;
+            current = child;
+        }
+        int best = current;
+        double bestSD = sd(kdM[best], r[0], r[1], r[2]);
+        while (true)
+        {
+            double currentSD = sd(kdM[current], r[0], r[1], r[2]);
+            if (currentSD < bestSD) { best = current; bestSD = currentSD; }
+            double d = pt(kdM[current])[kdAxis[current]] - r[kdAxis[current]];
+            double splitSD = d * d;
+            if (splitSD < bestSD)
+            {
+                int other = lessthan(r, pt(kdM[current]), kdAxis[current]) ? kdRight[current] : kdLeft[current];
+                if (other >= 0)
+                {
+                    int otherBest = nearest(other, r);
+                    double otherSD = sd(kdM[otherBest], r[0], r[1], r[2]);
+                    if (otherSD < bestSD) { best = otherBest; bestSD = otherSD; }
+                }
+            }
+            if (current == top) break;
+            current = kdUp[current];
+        }
+        return best;
+    }
+
+    // VoronoiMesh::cellIndex, VoronoiMesh.cpp:512-541
+    int whichcell(double x, double y, double z) const override
+    {
+        if (!inBox(ext, x, y, z)) return -1;
+        int i = boxIndex(x, ext[0], ext[3], nb), j = boxIndex(y, ext[1], ext[4], nb), k = boxIndex(z, ext[2], ext[5], nb);
+        size_t blk = ((size_t)i * nb + j) * nb + k;
+        if (blkTree[blk] >= 0) { double r[3] = {x, y, z}; return kdM[nearest(blkTree[blk], r)]; }
+        int m = -1; double mdist = DBL_MAX;
+        for (int q = blkStart[blk]; q < blkStart[blk + 1]; q++)
+        {
+            double idist = sd(blkIds[q], x, y, z);
+            if (idist < mdist) { m = blkIds[q]; mdist = idist; }
+        }
+        return m;
+    }
+
+    // VoronoiMesh::path, VoronoiMesh.cpp:749-844
+    void path(Path& p) const override
+    {
+        p.clear();
+        double x, y, z;
+        const double kx = p.kx, ky = p.ky, kz = p.kz;
+        if (!std::isfinite(p.rx + p.ry + p.rz + kx + ky + kz)) return;
+        if (!p.moveInside(ext, eps, x, y, z)) return p.clear();
+        int mr = whichcell(x, y, z);
+        if (mr < 0) return p.clear();
+        long guard = 0;
+        while (mr >= 0)
+        {
+            const double* pr = pt(mr);
+            double sq = DBL_MAX; const int NO_INDEX = -99; int mq = NO_INDEX;
+            for (int q = nbrStart[mr]; q < nbrStart[mr + 1]; q++)
+            {
+                int mi = nbrIds[q];
+                double si = 0;
+                if (mi >= 0)
+                {
+                    const double* pi = pt(mi);
+                    double nx = pi[0] - pr[0], ny = pi[1] - pr[1], nz = pi[2] - pr[2];
+                    double ndotk = nx * kx + ny * ky + nz * kz;
+                    if (ndotk > 0)
+                    {
+                        double px = 0.5 * (pi[0] + pr[0]), py = 0.5 * (pi[1] + pr[1]), pz = 0.5 * (pi[2] + pr[2]);
+                        si = (nx * (px - x) + ny * (py - y) + nz * (pz - z)) / ndotk;
+                    }
+                }
+                else if (mi >= -6)
+                {
+                    // walls -1..-6 = xmin,xmax,ymin,ymax,zmin,zmax (:810-817)
+                    int a = (-mi - 1) / 2; bool upper = ((-mi - 1) % 2) == 1;
+                    double c = a == 0 ? x : (a == 1 ? y : z), kc = a == 0 ? kx : (a == 1 ? ky : kz);
+                    si = (ext[a + (upper ? 3 : 0)] - c) / kc;
+                }
+                else { errors++; return; }
+                if (si > 0 && si < sq) { sq = si; mq = mi; }
+            }
+            if (mq == NO_INDEX)
+            {
+                x += kx * eps; y += ky * eps; z += kz * eps;
+                mr = whichcell(x, y, z);
+                if (++guard > 1000000) { errors++; return; }
+            }
+            else
+            {
+                p.add(mr, sq);
+                x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
+                mr = mq;
+            }
+        }
+    }
+    void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
+};
+
+}   // anonymous namespace
+
+// =====================================================================================================
+// MT19937 stream, Random.cpp:41-126 (the reference keeps one per thread; seed + thread index)
+// =====================================================================================================
+struct Rng
+{
+    unsigned long mt[624]; int mti;
+    explicit Rng(unsigned long seed)
+    {
+        // Random::initialize, Random.cpp:60-85: Knuth's LCG 69069 seeding of the state vector
+        mt[0] = seed & 0xffffffffUL;
+        for (mti = 1; mti < 624; mti++) mt[mti] = (69069 * mt[mti - 1]) & 0xffffffffUL;
+    }
+    double uniform()    // Random::uniform, Random.cpp:89-126: (0,1) open interval
+    {
+        const unsigned long UPPER = 0x80000000UL, LOWER = 0x7fffffffUL, A = 0x9908b0dfUL;
+        double ans = 0.0;
+        do
+        {
+            unsigned long y;
+            if (mti >= 624)
+            {
+                int kk;
+                for (kk = 0; kk < 624 - 397; kk++) { y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER); mt[kk] = mt[kk + 397] ^ (y >> 1) ^ ((y & 1) ? A : 0); }
+                for (; kk < 623; kk++) { y = (mt[kk] & UPPER) | (mt[kk + 1] & LOWER); mt[kk] = mt[kk + (397 - 624)] ^ (y >> 1) ^ ((y & 1) ? A : 0); }
+                y = (mt[623] & UPPER) | (mt[0] & LOWER); mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1) ? A : 0);
+                mti = 0;
+            }
+            y = mt[mti++];
+            y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680UL; y ^= (y << 15) & 0xefc60000UL; y ^= (y >> 18);
+            ans = ((double)y) / ((unsigned long)0xffffffff);
+        }
+        while (ans <= 0.0 || ans >= 1.0);
+        return ans;
+    }
+};
+
+namespace
+{
+// Random::position(Box), Random.cpp:226-234: x, y, z drawn in this order through Box::fracpos (Box.hpp:125-126)
+void randomInBox(const double* b, Rng& rng, double& x, double& y, double& z)
+{
+    double fx = rng.uniform(), fy = rng.uniform(), fz = rng.uniform();
+    x = b[0] + fx * (b[3] - b[0]); y = b[1] + fy * (b[4] - b[1]); z = b[2] + fz * (b[5] - b[2]);
+}
+void Cartesian::randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const
+{
+    int i = m / (Nz * Ny), j = (m / Nz) % Ny, k = m % Nz;       // CartesianDustGrid::invertindex, :333-343
+    double bb[6] = {xv[i], yv[j], zv[k], xv[i + 1], yv[j + 1], zv[k + 1]};
+    randomInBox(bb, rng, x, y, z);
+}
+void Tree::randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const { randomInBox(b(leafOfCell[m]), rng, x, y, z); }     // TreeDustGrid.cpp:383-386
+void AMesh::randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const { randomInBox(b(leafOfCell[m]), rng, x, y, z); }    // AdaptiveMesh.cpp:163-167
+void Voronoi::randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const
+{
+    // VoronoiMesh::randomPosition, VoronoiMesh.cpp:591-618: rejection in the cell's enclosing box
+    for (int i = 0; i < 10000; i++)
+    {
+        randomInBox(cellBox.data() + 6 * (size_t)m, rng, x, y, z);
+        double target = sd(m, x, y, z); bool closest = true;
+        for (int q = nbrStart[m]; q < nbrStart[m + 1] && closest; q++)
+            if (nbrIds[q] >= 0 && sd(nbrIds[q], x, y, z) < target) closest = false;
+        if (closest) return;
+    }
+    errors++;
+}
+}   // anonymous namespace
+
+// =====================================================================================================
+// factories
+// =====================================================================================================
+Grid* makeCartesian(const double* xv, int Nx, const double* yv, int Ny, const double* zv, int Nz)
+{
+    Cartesian* g = new Cartesian();
+    g->xv.assign(xv, xv + Nx + 1); g->yv.assign(yv, yv + Ny + 1); g->zv.assign(zv, zv + Nz + 1);
+    g->Nx = Nx; g->Ny = Ny; g->Nz = Nz;
+    // for every Mesh of the reference mesh[0]=0 and mesh[N]=1, so the outer borders are the extent (CartesianDustGrid.cpp:34-36)
+    g->xmin = xv[0]; g->xmax = xv[Nx]; g->ymin = yv[0]; g->ymax = yv[Ny]; g->zmin = zv[0]; g->zmax = zv[Nz];
+    return g;
+}
+
+Grid* makeTree(int kind, int search, int N, const double* box, const int* child0, const int* parent, const int* cell,
+               const int* dir, const int* nbrStart, const int* nbrIds)
+{
+    Tree* g = new Tree();
+    g->kind = kind; g->search = search; g->N = N;
+    g->box.assign(box, box + 6 * (size_t)N); g->child0.assign(child0, child0 + N); g->parent.assign(parent, parent + N);
+    g->cell.assign(cell, cell + N);
+    if (dir) g->dir.assign(dir, dir + N); else g->dir.assign(N, 0);
+    if (nbrStart) { g->nbrStart.assign(nbrStart, nbrStart + 6 * (size_t)N + 1); g->nbrIds.assign(nbrIds, nbrIds + nbrStart[6 * (size_t)N]); }
+    for (int l = 0; l < N; l++) if (cell[l] >= 0) g->ncells++;
+    g->leafOfCell.assign(g->ncells, -1);
+    for (int l = 0; l < N; l++) if (cell[l] >= 0) g->leafOfCell[cell[l]] = l;
+    g->eps = epsOf(box);
+    return g;
+}
+
+Grid* makeAdaptiveMesh(int N, const double* box, const int* nxyz, const int* child0, const int* cell, const int* wallNbr)
+{
+    AMesh* g = new AMesh();
+    g->N = N;
+    g->box.assign(box, box + 6 * (size_t)N); g->nxyz.assign(nxyz, nxyz + 3 * (size_t)N); g->child0.assign(child0, child0 + N);
+    g->cell.assign(cell, cell + N); g->wallNbr.assign(wallNbr, wallNbr + 6 * (size_t)N);
+    for (int l = 0; l < N; l++) if (cell[l] >= 0) g->ncells++;
+    g->leafOfCell.assign(g->ncells, -1);
+    for (int l = 0; l < N; l++) if (cell[l] >= 0) g->leafOfCell[cell[l]] = l;
+    g->eps = epsOf(box);
+    return g;
+}
+
+Grid* makeVoronoi(int N, const double* particles, const int* nbrStart, const int* nbrIds, const double extent[6], int nb,
+                  const int* blkStart, const int* blkIds, const int* blkTree, int Nkd, const int* kdM, const int* kdAxis,
+                  const int* kdUp, const int* kdLeft, const int* kdRight, const double* cellBox)
+{
+    Voronoi* g = new Voronoi();
+    g->N = N; g->nb = nb;
+    size_t nb3 = (size_t)nb * nb * nb;
+    g->part.assign(particles, particles + 3 * (size_t)N);
+    g->nbrStart.assign(nbrStart, nbrStart + N + 1); g->nbrIds.assign(nbrIds, nbrIds + nbrStart[N]);
+    g->blkStart.assign(blkStart, blkStart + nb3 + 1); g->blkIds.assign(blkIds, blkIds + blkStart[nb3]);
+    g->blkTree.assign(blkTree, blkTree + nb3);
+    if (Nkd > 0)
+    {
+        g->kdM.assign(kdM, kdM + Nkd); g->kdAxis.assign(kdAxis, kdAxis + Nkd); g->kdUp.assign(kdUp, kdUp + Nkd);
+        g->kdLeft.assign(kdLeft, kdLeft + Nkd); g->kdRight.assign(kdRight, kdRight + Nkd);
+        for (int& a : g->kdAxis) a %= 3;
+    }
+    if (cellBox) g->cellBox.assign(cellBox, cellBox + 6 * (size_t)N);
+    // extent arrives as xmin,xmax,ymin,ymax,zmin,zmax (the order of the ski properties)
+    g->ext[0] = extent[0]; g->ext[1] = extent[2]; g->ext[2] = extent[4]; g->ext[3] = extent[1]; g->ext[4] = extent[3]; g->ext[5] = extent[5];
+    g->eps = epsOf(g->ext);
+    return g;
+}
+
+}   // namespace orc
+
+// =====================================================================================================
+// C interface for ctypes (oracle/oracle_py.py)
+// =====================================================================================================
+using namespace orc;
+
+extern "C"
+{
+void* orc_grid_cartesian(const double* xv, int Nx, const double* yv, int Ny, const double* zv, int Nz) { return makeCartesian(xv, Nx, yv, Ny, zv, Nz); }
+void* orc_grid_tree(int kind, int search, int N, const double* box, const int* child0, const int* parent, const int* cell,
+                    const int* dir, const int* nbrStart, const int* nbrIds)
+{ return makeTree(kind, search, N, box, child0, parent, cell, dir, nbrStart, nbrIds); }
+void* orc_grid_amesh(int N, const double* box, const int* nxyz, const int* child0, const int* cell, const int* wallNbr)
+{ return makeAdaptiveMesh(N, box, nxyz, child0, cell, wallNbr); }
+void* orc_grid_voronoi(int N, const double* particles, const int* nbrStart, const int* nbrIds, const double* extent, int nb,
+                       const int* blkStart, const int* blkIds, const int* blkTree, int Nkd, const int* kdM, const int* kdAxis,
+                       const int* kdUp, const int* kdLeft, const int* kdRight, const double* cellBox)
+{ return makeVoronoi(N, particles, nbrStart, nbrIds, extent, nb, blkStart, blkIds, blkTree, Nkd, kdM, kdAxis, kdUp, kdLeft, kdRight, cellBox); }
+void orc_grid_destroy(void* g) { delete (Grid*)g; }
+int orc_num_cells(void* g) { return ((Grid*)g)->numCells(); }
+long orc_stuck(void* g) { return ((Grid*)g)->stuck; }
+
+void* orc_medium(int Ncells, int Ncomp, int Nlambda, const double* rho, const double* kext, const double* ksca, const double* g)
+{
+    Medium* m = new Medium();
+    m->Ncells = Ncells; m->Ncomp = Ncomp; m->Nlambda = Nlambda;
+    m->rho.assign(rho, rho + (size_t)Ncells * Ncomp); m->kext.assign(kext, kext + (size_t)Ncomp * Nlambda);
+    if (ksca) m->ksca.assign(ksca, ksca + (size_t)Ncomp * Nlambda); else m->ksca.assign((size_t)Ncomp * Nlambda, 0.0);
+    if (g) m->g.assign(g, g + (size_t)Ncomp * Nlambda); else m->g.assign((size_t)Ncomp * Nlambda, 0.0);
+    return m;
+}
+void orc_medium_destroy(void* m) { delete (Medium*)m; }
+
+// batched path(): pass cap = 0 to obtain the counts/offsets, then again with arrays of offsets[n] entries.
+// ell: NULL (geometry only), one value (ellStride 0) or one per ray (ellStride 1)
+long orc_path_batch(void* gh, void* mh, const double* r, const double* k, long n, const int* ell, int ellStride, long cap,
+                    long* offsets, int* m, double* ds, double* s, double* dtau, double* tau, int nthreads)
+{
+    const Grid* g = (const Grid*)gh; const Medium* med = (const Medium*)mh;
+    std::vector<int> counts(n);
+    auto work = [&](int pass, int tid, int nt)
+    {
+        Path p;
+        for (long i = tid; i < n; i += nt)
+        {
+            p.rx = r[3 * i]; p.ry = r[3 * i + 1]; p.rz = r[3 * i + 2]; p.kx = k[3 * i]; p.ky = k[3 * i + 1]; p.kz = k[3 * i + 2];
+            g->path(p);
+            if (pass == 0) { counts[i] = (int)p.v.size(); continue; }
+            if (ell && med) fillOpticalDepth(p, *med, ell[i * ellStride]);
+            long o = offsets[i];
+            if (o + (long)p.v.size() > cap) continue;
+            for (size_t j = 0; j < p.v.size(); j++)
+            { m[o + j] = p.v[j].m; ds[o + j] = p.v[j].ds; s[o + j] = p.v[j].s; dtau[o + j] = p.v[j].dtau; tau[o + j] = p.v[j].tau; }
+        }
+    };
+    auto run = [&](int pass)
+    {
+        int nt = std::max(1, nthreads);
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(work, pass, t, nt);
+        work(pass, 0, nt);
+        for (auto& t : th) t.join();
+    };
+    if (cap <= 0)
+    {
+        run(0);
+        long total = 0;
+        for (long i = 0; i < n; i++) { offsets[i] = total; total += counts[i]; }
+        offsets[n] = total;
+        return total;
+    }
+    run(1);
+    return offsets[n];
+}
+
+void orc_whichcell(void* gh, const double* r, long n, int* m)
+{ const Grid* g = (const Grid*)gh; for (long i = 0; i < n; i++) m[i] = g->whichcell(r[3 * i], r[3 * i + 1], r[3 * i + 2]); }
+
+// DustSystem::opticaldepth(pp, distance), DustSystem.cpp:984-1000
+void orc_opticaldepth(void* gh, void* mh, const double* r, const double* k, long n, const int* ell, int ellStride,
+                      const double* distance, double* tau)
+{
+    const Grid* g = (const Grid*)gh; const Medium* med = (const Medium*)mh;
+    Path p;
+    for (long i = 0; i < n; i++)
+    {
+        p.rx = r[3 * i]; p.ry = r[3 * i + 1]; p.rz = r[3 * i + 2]; p.kx = k[3 * i]; p.ky = k[3 * i + 1]; p.kz = k[3 * i + 2];
+        g->path(p);
+        tau[i] = opticalDepth(p, *med, ell[i * ellStride], distance ? distance[i] : DBL_MAX);
+    }
+}
+
+// DustGridPath::pathlength on the path of one ray (for the propagation check)
+double orc_pathlength(void* gh, void* mh, const double* r, const double* k, int ell, double tau)
+{
+    const Grid* g = (const Grid*)gh; const Medium* med = (const Medium*)mh;
+    Path p; p.rx = r[0]; p.ry = r[1]; p.rz = r[2]; p.kx = k[0]; p.ky = k[1]; p.kz = k[2];
+    g->path(p); fillOpticalDepth(p, *med, ell);
+    return p.pathlength(tau);
+}
+
+void orc_random_positions(void* gh, int m, unsigned long seed, long n, double* xyz)
+{
+    const Grid* g = (const Grid*)gh; Rng rng(seed);
+    for (long i = 0; i < n; i++) g->randomPositionInCell(m, rng, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+}
+void orc_uniforms(unsigned long seed, long n, double* u) { Rng rng(seed); for (long i = 0; i < n; i++) u[i] = rng.uniform(); }
+}

@@ -75,6 +75,7 @@ def sampler_case():
     spec, L, mixes = refspec.reference_spec(p, threads=1, dustsamples=1)
     S = sr.RefSim(spec, luminosities=L, mixes=mixes).setup()
     out = {}
+    S.reset(4357); out["uniforms_4357"] = S.uniforms(2000)      # raw MT19937 stream of thread 0 (Random.cpp:89-126)
     for ell in (0, 4):
         r, k, Lw = S.sample_launch(ell, 200000)
         out[f"r_mean_{ell}"] = r.mean(0); out[f"r_absmean_{ell}"] = np.abs(r).mean(0); out[f"r_sq_{ell}"] = (r * r).mean(0)

@@ -1,0 +1,54 @@
+"""Pins the restated CPU oracle (oracle/liboracle.so) against the reference: every golden vector under
+tests/golden/ (generated from the reference's own translation units) must be reproduced bit for bit, and --
+in the build container, where oracle/_ref/libskirtref.so exists -- so must fresh seeded rays at larger sizes."""
+import numpy as np
+import pytest
+
+import common
+from oracle import oracle_py, skirtref
+
+pytestmark = pytest.mark.skipif(not oracle_py.available(), reason="oracle/liboracle.so not built")
+
+
+@pytest.mark.parametrize("name", common.GEOM_CASES)
+def test_oracle_reproduces_golden_paths(name):
+    tables, medium, d = common.load_golden(name)
+    o = oracle_py.Oracle(tables, medium)
+    got = o.path_batch(d["r"], d["k"], ell=0)
+    assert common.paths_bit_identical(got, d["paths"]), name
+    assert np.array_equal(o.whichcell(d["r"]), d["whichcell"])
+    assert np.array_equal(o.opticaldepth(d["r"], d["k"], 0), d["tau_inf"])
+    assert np.array_equal(o.opticaldepth(d["r"], d["k"], 0, d["distance"]), d["tau_dist"])
+    geo = o.path_batch(d["r"], d["k"], ell=None)
+    assert np.array_equal(geo["m"], d["paths"]["m"]) and np.array_equal(geo["s"], d["paths"]["s"]) and not geo["tau"].any()
+
+
+def test_mt19937_stream_matches_reference_golden():
+    z = np.load(common.GOLDEN + "/launch_c2.npz")
+    if "uniforms_4357" in z.files:
+        assert np.array_equal(oracle_py.uniforms(4357, len(z["uniforms_4357"])), z["uniforms_4357"])
+    u = oracle_py.uniforms(4357, 100000)
+    assert 0 < u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.005
+
+
+@pytest.mark.skipif(not skirtref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("kind", ["cart", "octtree1", "octtree2", "bintree0", "amesh", "voronoi"])
+def test_oracle_matches_reference_on_fresh_rays(kind):
+    mk = lambda spec, **kw: skirtref.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw)
+    if kind == "cart":
+        S = mk(common.spec_c1(n=50, mesh="sympow 20"))
+    elif kind.startswith("octtree"):
+        S = mk(common.spec_grid("octtree", search=int(kind[-1]), maxlevel=5))
+    elif kind.startswith("bintree"):
+        S = mk(common.spec_grid("bintree", search=int(kind[-1]), maxlevel=12))
+    elif kind == "amesh":
+        S = mk(common.spec_grid("amesh"), amesh=common.make_amesh())
+    else:
+        S = mk(common.spec_grid("voronoi"), particles=common.voronoi_particles(4000))
+    S.setup()
+    tables, medium = S.grid_tables(), S.medium()
+    r, k = common.rays(20000, common.C1_BOX, 31)
+    ref = S.path_batch(r, k, ell=0, nthreads=8)
+    got = oracle_py.Oracle(tables, medium).path_batch(r, k, ell=0)
+    assert common.paths_bit_identical(got, ref), kind
+    assert np.array_equal(oracle_py.Oracle(tables, medium).whichcell(r[:4000]), S.whichcell(r[:4000]))
