@@ -6,7 +6,7 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -lineinfo -fmad=false --expt-relaxed-constexpr \
            -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function -Xptxas -v
 CSRC := skirt_b200/csrc
-OBJS := $(CSRC)/build/engine.o $(CSRC)/build/path_kernels.o $(CSRC)/build/mc_kernels.o
+OBJS := $(CSRC)/build/engine.o $(CSRC)/build/path_kernels.o $(CSRC)/build/mc_kernels.o $(CSRC)/build/comm.o
 HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/skirtgpu.h
 NCCL_INC ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'include'))" 2>/dev/null)
 NCCL_LIB ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'lib'))" 2>/dev/null)

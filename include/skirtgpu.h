@@ -135,6 +135,7 @@ typedef struct skg_mc_params
     uint64_t seed;              /* Philox key; replaces Random's seed (Random.cpp:21) */
     uint64_t streamOffset;      /* first global packet index of this engine (disjoint Philox counters per GPU) */
     int ellBegin, ellEnd;       /* wavelength range [ellBegin, ellEnd) to shoot */
+    int poolPackets;            /* packets in flight on the device at a time (0: default 2^22) */
 } skg_mc_params;
 typedef struct skg_mc_stats
 {
@@ -155,7 +156,8 @@ int skg_reset_results(skg_engine* e);
 int skg_fetch_frame(skg_engine* e, int instrument, double* frame, int add);
 int skg_fetch_sed(skg_engine* e, int instrument, double* sed, int add);
 int skg_fetch_labs(skg_engine* e, double* labs /* [Ncells*Nlambda] */, int add);
-/* device views of the accumulators, for collectives issued by the host (NCCL through torch.distributed) */
+/* device views of the accumulators, for collectives issued by the host (NCCL through torch.distributed);
+ * note that the absorption table is wavelength-major on the device: labs[ell*Ncells + m] */
 int skg_device_accumulators(skg_engine* e, int which /*0 labs, 1.. instruments*/, int part /*0 frame,1 sed*/,
                             double** d_ptr, int64_t* count);
 

@@ -34,6 +34,7 @@ Engine::~Engine()
     freeGrid();
     for (DevBuf* b : sourceBufs) delete b;
     for (DevBuf* b : instrBufs) delete b;
+    if (mcHostCounts) cudaFreeHost(mcHostCounts);
     if (stream) cudaStreamDestroy(stream);
 }
 
@@ -372,8 +373,8 @@ int skg_fetch_labs(skg_engine* eh, double* labs, int add)
 {
     return guarded([&]{
         Engine& e = E(eh);
-        if (!e.labs.p || e.labsCount == 0) throw Error("absorption rates were not stored");
-        fetchArray(e, e.labs.as<double>(), e.labsCount, labs, add);
+        if (!labs) throw Error("null host array");
+        mcFetchLabs(e, labs, add);
     });
 }
 int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr, int64_t* count)

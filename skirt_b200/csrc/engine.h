@@ -69,7 +69,10 @@ struct Engine
     std::vector<SourceDev> sources; DevBuf sourcesDev, lumDev, lumCdfDev, lumTotDev; std::vector<DevBuf*> sourceBufs;
     std::vector<double> lumHost, lumTotHost;
     std::vector<InstrDev> instr; DevBuf instrDev; std::vector<DevBuf*> instrBufs;
-    DevBuf labs; int64_t labsCount = 0;
+    DevBuf labs; int64_t labsCount = 0;    // absorbed luminosity, wavelength-major on the device: labs[ell*Ncells+m]
+    DevBuf labsT;                           // scratch for the (m,ell) row-major copy handed to the host
+    DevBuf instrGroupedDev, groupsDev; int Ngroups = 0;    // instruments ordered by line of sight + the groups
+    DevBuf mcPool, mcLists, mcCounts, mcEllList; int* mcHostCounts = nullptr;   // packet pool of the wavefront shooter
     void* nccl = nullptr; int rank = 0, nranks = 1;
     uint64_t launches = 0;              // kernels launched by this engine (skg_launch_count)
 
@@ -95,5 +98,6 @@ void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, co
 void mcSetInstruments(Engine& e, int n, const skg_instrument* instr);
 void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats);
 void mcResetResults(Engine& e);
+void mcFetchLabs(Engine& e, double* host, int add);
 
 }   // namespace skg

@@ -1,0 +1,334 @@
+// Device-side pieces of the photon-packet life cycle shared by the stage kernels (mc_kernels.cu):
+// packet pool layout, launch samplers, life-cycle sinks and warp-aggregated accumulation.
+//   launch                StellarSystem::launch (StellarSystem.cpp:116-158) + geometry samplers
+//   escape + absorption   MonteCarloSimulation.cpp:438-515 (DustSystem::absorb -> atomicAdd, replaces LockFree::add)
+//   forced propagation    :519-537 (+ DustGridPath::pathlength, DustGridPath.cpp:162-173)
+//   scattering            :541-549 (DustMix.cpp:607-614, Random::direction Random.cpp:188-222)
+#pragma once
+#include <cmath>
+#include "engine.h"
+#include "geom.cuh"
+#include "sinks.cuh"
+#include "philox.cuh"
+
+namespace skg
+{
+
+struct GridSetMC { CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro; };
+
+// Packet pool: structure of arrays, one slot per in-flight photon packet (PhotonPackage, PhotonPackage.hpp:28,134-138;
+// unpolarised: position, direction, luminosity, wavelength index, number of scatterings) plus the engine's own
+// bookkeeping (Philox stream position, interaction optical depth sampled by the absorb stage).
+struct PacketPool
+{
+    double* x; double* y; double* z; double* kx; double* ky; double* kz;
+    double* L; double* target;
+    unsigned long long* id;     // Philox stream id of the packet
+    int* ell; int* nscatt; unsigned* rngCtr; int* fresh;
+};
+
+// instruments that look along the same direction share one peel-off traversal
+struct ObsGroup { double kx, ky, kz; int first, count; };
+
+struct McDev
+{
+    Medium med;
+    const SourceDev* sources; int Nsources;
+    const double* L;        // [Nsources*Nlambda]
+    const double* Ltot;     // [Nlambda]
+    const double* Lcdf;     // [Nlambda*(Nsources+1)]
+    double emissionBias;
+    const InstrDev* instr; int Ninstr;      // sorted by observer group
+    const ObsGroup* groups; int Ngroups;
+    double* labs;           // [Nlambda*Ncells] (wavelength-major on the device) or null
+    double Lscale;          // total packets per wavelength over all engines
+    double minWeightReduction, minfs, xi;
+    uint64_t seed, streamOffset;
+    const int* ellList;     // wavelength indices with nonzero luminosity, in shooting order
+    unsigned long long NppInt;
+    PacketPool pool;
+};
+
+// ---- accumulation ----------------------------------------------------------------------------------------
+// LockFree::add (LockFree.hpp:25-37) on the device: lanes of a warp that target the same address are summed
+// first and issue ONE fp64 atomicAdd (SED bins are a single address per wavelength, edge-on frames concentrate
+// flux in few pixels).
+__device__ __forceinline__ void warpAggregatedAdd(double* addr, double v)
+{
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, (unsigned long long)addr);
+    const int lane = threadIdx.x & 31;
+    if (peers == 0xffffffffu)
+    {
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(addr, v);
+        return;
+    }
+    const int leader = __ffs(peers) - 1;
+    double sum = 0;
+    for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, v, __ffs(rem) - 1);
+    if (lane == leader) atomicAdd(addr, sum);
+}
+
+// appends the slots of the lanes with `take` set to a list: one atomicAdd per warp
+__device__ __forceinline__ void warpAppend(bool take, int slot, int* list, int* count)
+{
+    const unsigned active = __activemask();
+    const unsigned mask = __ballot_sync(active, take);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == __ffs(mask) - 1) base = atomicAdd(count, __popc(mask));
+    base = __shfl_sync(active, base, __ffs(mask) - 1);
+    if (take) list[base + __popc(mask & ((1u << lane) - 1))] = slot;
+}
+
+// ---- samplers ------------------------------------------------------------------------------------------
+
+// SpecialFunctions::LambertW1, SpecialFunctions.cpp:579-627 (branch W_-1 for -1/e <= z < 0)
+static __device__ double lambertW1(double z)
+{
+    const double eps = 1.0e-12;
+    const double em1 = 0.3678794411714423215955237701614608;
+    if (z == 0.0) return -SKG_DBL_MAX;
+    double q = z + em1;
+    if (q < 0) q = 0;
+    double r = -sqrt(q);
+    double t8 = -8.401032217523977370984161688514 + r * (12.250753501314460424 + r * (-18.100697012472442755 + r * 27.029044799010561650));
+    double t5 = 3.066858901050631912893148922704 + r * (-4.175335600258177138854984177460 + r * (5.858023729874774148815053846119 + r * t8));
+    double t1 = 2.331643981597124203363536062168 + r * (-1.812187885639363490240191647568 + r * (1.936631114492359755363277457668
+              + r * (-2.353551201881614516821543561516 + r * t5)));
+    double w0 = -1.0 + r * t1;
+    if (q < 3.0e-3) return w0;
+    double w;
+    if (z < -1e-6) w = w0;
+    else { double l1 = log(-z); double l2 = log(-l1); w = l1 - l2 + l2 / l1; }
+    for (int i = 0; i < 10; i++)
+    {
+        double e = exp(w);
+        double t = w * e - z;
+        double p = w + 1.0;
+        t /= e * p - 0.5 * (p + 1.0) * t / p;
+        w -= t;
+        if (fabs(t) < eps * (1.0 + fabs(w))) return w;
+    }
+    return w;
+}
+
+// Direction(theta, phi), Direction.cpp:12-38
+__device__ __forceinline__ void directionFromAngles(double theta, double phi, double& kx, double& ky, double& kz)
+{
+    const double eps = 1e-8;
+    if (theta <= eps) { kx = 0; ky = 0; kz = 1; }
+    else if (theta >= M_PI - eps) { kx = 0; ky = 0; kz = -1; }
+    else { double st = sin(theta); kx = st * cos(phi); ky = st * sin(phi); kz = cos(theta); }
+}
+
+// Random::direction(), Random.cpp:179-184
+__device__ __forceinline__ void randomDirection(Philox& rng, double& kx, double& ky, double& kz)
+{
+    double theta = acos(2.0 * rng.uniform() - 1.0);
+    double phi = 2.0 * M_PI * rng.uniform();
+    directionFromAngles(theta, phi, kx, ky, kz);
+}
+
+// Random::direction(bfk, costheta), Random.cpp:188-222
+__device__ __forceinline__ void scatterDirection(Philox& rng, double costheta, double& kx, double& ky, double& kz)
+{
+    double phi = 2.0 * M_PI * rng.uniform();
+    double cosphi = cos(phi), sinphi = sin(phi);
+    double sintheta = sqrt(fabs((1.0 - costheta) * (1.0 + costheta)));
+    double kxn, kyn, kzn;
+    if (kz > 0.99999) { kxn = cosphi * sintheta; kyn = sinphi * sintheta; kzn = costheta; }
+    else if (kz < -0.99999) { kxn = cosphi * sintheta; kyn = sinphi * sintheta; kzn = -costheta; }
+    else
+    {
+        double root = sqrt((1.0 - kz) * (1.0 + kz));
+        kxn = sintheta / root * (-kx * kz * cosphi + ky * sinphi) + kx * costheta;
+        kyn = -sintheta / root * (ky * kz * cosphi + kx * sinphi) + ky * costheta;
+        kzn = root * sintheta * cosphi + kz * costheta;
+    }
+    kx = kxn; ky = kyn; kz = kzn;
+}
+
+// Random::exponcutoff, Random.cpp:162-175
+__device__ __forceinline__ double exponCutoff(Philox& rng, double xmax)
+{
+    if (xmax == 0.0) return 0.0;
+    else if (xmax < 1e-10) return rng.uniform() * xmax;
+    double x = -log(1.0 - rng.uniform() * (1.0 - exp(-xmax)));
+    while (x > xmax) x = -log(1.0 - rng.uniform() * (1.0 - exp(-xmax)));
+    return x;
+}
+
+// NR::interpolate_loglog, NR.hpp:321-345
+__device__ __forceinline__ double interpLogLog(double x, double x1, double x2, double f1, double f2)
+{
+    x = log10(x); x1 = log10(x1); x2 = log10(x2);
+    bool logf = f1 > 0 && f2 > 0;
+    if (logf) { f1 = log10(f1); f2 = log10(f2); }
+    double fx = f1 + ((x - x1) / (x2 - x1)) * (f2 - f1);
+    if (logf) fx = pow(10.0, fx);
+    return fx;
+}
+
+// Geometry::generatePosition for the supported geometries
+static __device__ void generatePosition(const SourceDev& s, Philox& rng, double& x, double& y, double& z)
+{
+    if (s.geometry == SKG_GEOM_EXPDISK)
+    {
+        // SepAxGeometry::generatePosition (SepAxGeometry.cpp:21-30) + ExpDiskGeometry::randomR/randomz (:134-161)
+        const double hR = s.p[0], hz = s.p[1], Rmax = s.p[2], zmax = s.p[3], Rmin = s.p[4];
+        double R, zz;
+        do
+        {
+            double X = rng.uniform();
+            R = hR * (-1.0 - lambertW1((X - 1.0) / M_E));
+        }
+        while ((Rmax > 0.0 && R >= Rmax) || R <= Rmin);
+        double phi = 2.0 * M_PI * rng.uniform();
+        do
+        {
+            double X = rng.uniform();
+            zz = (X <= 0.5) ? hz * log(2.0 * X) : -hz * log(2.0 * (1.0 - X));
+        }
+        while (zmax > 0.0 && fabs(zz) >= zmax);
+        x = R * cos(phi); y = R * sin(phi); z = zz;     // Position(R,phi,z,CYLINDRICAL), Position.cpp:23-31
+    }
+    else
+    {
+        // SpheGeometry::generatePosition (SpheGeometry.cpp:36-44) with SersicGeometry::randomradius (:85-91),
+        // SersicFunction::inversemass (SersicFunction.cpp:112-124); SpheroidalGeometryDecorator (:78-85)
+        const double reff = s.p[0], q = s.p[1];
+        double X = rng.uniform();
+        int Ns = s.ntab; double sval;
+        if (X <= s.Xv[0]) sval = s.rv[0];
+        else if (X >= s.Xv[Ns - 1]) sval = s.rv[Ns - 1];
+        else
+        {
+            int i = locateClip(s.Xv, X, Ns);
+            sval = interpLogLog(X, s.Xv[i], s.Xv[i + 1], s.rv[i], s.rv[i + 1]);
+        }
+        double r = reff * sval;
+        double kx, ky, kz; randomDirection(rng, kx, ky, kz);
+        x = r * kx; y = r * ky; z = r * kz;             // Position(r,bfk), Position.cpp:51-54
+        z = q * z;
+    }
+    if (s.spiral_arms > 0)
+    {
+        // SpiralStructureGeometryDecorator::generatePosition, SpiralStructureGeometryDecorator.cpp:177-192
+        double R = sqrt(x * x + y * y);
+        double c = s.spiral_c;
+        double phi, t;
+        do
+        {
+            phi = 2.0 * M_PI * rng.uniform();
+            // perturbation(R,phi), :224-229
+            double gamma = log(R / s.spiral_radius) / s.spiral_tanp + s.spiral_phase + 0.5 * M_PI / s.spiral_arms;
+            double pert = (1.0 - s.spiral_weight) + s.spiral_weight * s.spiral_cn * pow(sin(0.5 * s.spiral_arms * (gamma - phi)), 2 * s.spiral_index);
+            t = rng.uniform() * c / pert;
+        }
+        while (t > 1);
+        x = R * cos(phi); y = R * sin(phi);
+    }
+}
+
+// ---- sinks for the life cycle --------------------------------------------------------------------------
+
+// pass 1: DustSystem::fillOpticalDepth + simulateescapeandabsorption (MonteCarloSimulation.cpp:438-515) streamed per
+// segment.  The reference evaluates L*exp(-tau_start)*(-expm1(-dtau)) per segment; here the attenuation factor
+// E = exp(-tau_start) is carried along multiplicatively, E += E*expm1(-dtau), which needs one transcendental per
+// segment instead of two (the two forms agree to a few ulp over a path).
+struct AbsorbSink
+{
+    KappaRho kr; const Medium* med; int ell;
+    double L;               // packet luminosity at the start of the path
+    double albedo;          // Ncomp==1: DustMix::albedo(ell)
+    double* labs;           // Labs + ell*Ncells (wavelength-major) or null
+    double tau = 0, E = 1.0, Lsca = 0;
+    int n = 0, nAbs = 0;
+    __device__ __forceinline__ bool add(int m, double ds)
+    {
+        n++;
+        if (m < 0) return true;             // rho(-1,h) = 0: dtau = 0, nothing absorbed
+        int Ncomp = med->Ncomp;
+        if (Ncomp == 1)
+        {
+            double dtau = kr(m) * ds;
+            if (labs)
+            {
+                double x = expm1(-dtau);
+                atomicAdd(labs + m, (1.0 - albedo) * (L * E * (-x)));
+                E += E * x;
+                nAbs++;
+            }
+            tau += dtau;
+        }
+        else
+        {
+            double ksca = 0.0, kext = 0.0, krr = 0.0;
+            for (int h = 0; h < Ncomp; h++)
+            {
+                double rho = __ldg(med->rho + (size_t)m * Ncomp + h);
+                ksca += rho * __ldg(med->ksca + (size_t)h * med->Nlambda + ell);
+                double ke = __ldg(med->kext + (size_t)h * med->Nlambda + ell);
+                kext += rho * ke;
+                krr += ke * rho;
+            }
+            double alb = (kext > 0.0) ? ksca / kext : 0.0;
+            double dtau = krr * ds;
+            double x = expm1(-dtau);
+            double Lintm = L * E * (-x);
+            E += E * x;
+            Lsca += alb * Lintm;
+            if (labs) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
+            tau += dtau;
+        }
+        return true;
+    }
+};
+
+// pass 2: DustGridPath::pathlength(tau) evaluated on the fly (DustGridPath.cpp:162-173)
+struct PropagateSink
+{
+    KappaRho kr; double target;
+    double sPrev = 0, tauPrev = 0, result = 0;
+    bool found = false;
+    int n = 0;
+    __device__ __forceinline__ bool add(int m, double ds)
+    {
+        n++;
+        double sNew = sPrev + ds;
+        double tauNew = tauPrev + kr(m) * ds;
+        if (target < tauNew)
+        {
+            result = sPrev + ((target - tauPrev) / (tauNew - tauPrev)) * (sNew - sPrev);     // NR::interpolate_linlin
+            found = true;
+            return false;
+        }
+        sPrev = sNew; tauPrev = tauNew;
+        return true;
+    }
+    __device__ __forceinline__ double s() const { return found ? result : sPrev; }
+};
+
+template<int KIND, class Sink>
+__device__ __forceinline__ void walkMC(const GridSetMC& G, const CartGrid& cart, Counters* ctr,
+                                       double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    if (KIND == GRID_CART) walkCart(cart, x, y, z, kx, ky, kz, sink);
+    else if (KIND == GRID_TREE) walkTree(G.tree, ctr, x, y, z, kx, ky, kz, sink);
+    else if (KIND == GRID_AMESH) walkAMesh(G.amesh, ctr, x, y, z, kx, ky, kz, sink);
+    else walkVoro(G.voro, ctr, x, y, z, kx, ky, kz, sink);
+}
+
+template<int KIND>
+__device__ __forceinline__ int whichCellMC(const GridSetMC& G, const CartGrid& cart, double x, double y, double z)
+{
+    if (KIND == GRID_CART) return cartWhichCell(cart, x, y, z);
+    else if (KIND == GRID_TREE) { int node = treeWhichNode(G.tree, x, y, z); return node >= 0 ? G.tree.cell[node] : -1; }
+    else if (KIND == GRID_AMESH) { int node = ameshWhichNode(G.amesh, x, y, z); return node >= 0 ? G.amesh.cell[node] : -1; }
+    else return voroCellIndex(G.voro, x, y, z);
+}
+
+}   // namespace skg

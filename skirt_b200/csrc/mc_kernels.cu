@@ -1,347 +1,74 @@
-// Photon-packet life cycle on the device: the stellar emission phase of
-// MonteCarloSimulation::dostellaremissionchunk (MonteCarloSimulation.cpp:265-301) with
-//   launch                StellarSystem::launch (StellarSystem.cpp:116-158) + geometry samplers
-//   peel-off emission     MonteCarloSimulation.cpp:305-315
-//   escape + absorption   :438-515 (DustSystem::absorb -> atomicAdd on Labs[m,ell], replaces LockFree::add)
-//   forced propagation    :519-537 (+ DustGridPath::pathlength, DustGridPath.cpp:162-173)
-//   peel-off scattering   :319-363 (HG phase function DustMix.cpp:665-668)
-//   scattering            :541-549 (DustMix.cpp:607-614, Random::direction Random.cpp:188-222)
-//   detection             FrameInstrument.cpp:32-47, SEDInstrument.cpp:32-42, SimpleInstrument.cpp:33-49
-// The reference stores every path (DustGridPath) and then loops over it; here the walkers stream the
-// segments straight into sinks, so no path is ever written to memory: pass 1 accumulates tau_path and
-// the per-cell absorption, pass 2 re-walks up to the sampled interaction optical depth.
-#include <cmath>
-#include <dlfcn.h>
+// Photon shooting as a wavefront of converged stage kernels over a pool of in-flight packets:
+//
+//   launch     fills free pool slots with new packets            StellarSystem::launch, StellarSystem.cpp:116-158
+//   peel       one traversal per (packet, observer direction)    peeloffemission / peeloffscattering,
+//                                                                MonteCarloSimulation.cpp:305-363 + Instrument::detect
+//   absorb     scatter (old packets), walk + absorb, terminate   simulatescattering :541-549, fillOpticalDepth +
+//              or sample the interaction optical depth           simulateescapeandabsorption :438-515, :289, :519-533
+//   propagate  re-walk to the sampled optical depth and move     DustGridPath::pathlength, PhotonPackage::propagate
+//
+// which is MonteCarloSimulation::dostellaremissionchunk (MonteCarloSimulation.cpp:265-301) turned inside out: the
+// reference runs one packet through its whole life on one thread; here all packets of the pool advance one stage
+// at a time, so that the 32 lanes of a warp always execute the same walker loop.  Survivors and free slots are
+// compacted into index lists by warp-aggregated appends; packets are launched in wavelength order so that the
+// pool holds few wavelengths at a time (the absorption table is wavelength-major on the device).
+#include <algorithm>
 #include <vector>
-#include "engine.h"
-#include "geom.cuh"
-#include "sinks.cuh"
-#include "philox.cuh"
+#include "mc_device.cuh"
 
 namespace skg
 {
 
-struct GridSetMC { CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro; };
-
-struct McDev
+__device__ __forceinline__ CartGrid stageCartMC(const CartGrid& g, double* smem, bool useSmem)
 {
-    Medium med;
-    const SourceDev* sources; int Nsources;
-    const double* L;        // [Nsources*Nlambda]
-    const double* Ltot;     // [Nlambda]
-    const double* Lcdf;     // [Nlambda*(Nsources+1)]
-    double emissionBias;
-    const InstrDev* instr; int Ninstr;
-    double* labs;           // [Ncells*Nlambda] or null
-    double Npp;             // packets per wavelength shot by this engine
-    double Lscale;          // total packets per wavelength over all engines
-    double minWeightReduction, minfs, xi;
-    uint64_t seed, streamOffset;
-    int ellBegin, ellEnd;
-    unsigned long long NppInt;
-};
+    if (!useSmem) return g;
+    CartGrid s = g;
+    int nx = g.Nx + 1, ny = g.Ny + 1, nz = g.Nz + 1;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) smem[i] = g.xv[i];
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) smem[nx + i] = g.yv[i];
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) smem[nx + ny + i] = g.zv[i];
+    __syncthreads();
+    s.xv = smem; s.yv = smem + nx; s.zv = smem + nx + ny;
+    return s;
+}
 
-// ---- samplers ------------------------------------------------------------------------------------------
-
-// SpecialFunctions::LambertW1, SpecialFunctions.cpp:579-627 (branch W_-1 for -1/e <= z < 0)
-static __device__ double lambertW1(double z)
+// per-kernel statistics: warp-reduced, one atomic per warp and counter
+__device__ __forceinline__ void flushStats(Counters* ctr, unsigned long long nSeg, unsigned long long nPaths, unsigned long long nScatt,
+                                           unsigned long long nPackets, unsigned long long nAbs, unsigned long long nDet)
 {
-    const double eps = 1.0e-12;
-    const double em1 = 0.3678794411714423215955237701614608;
-    if (z == 0.0) return -SKG_DBL_MAX;
-    double q = z + em1;
-    if (q < 0) q = 0;
-    double r = -sqrt(q);
-    double t8 = -8.401032217523977370984161688514 + r * (12.250753501314460424 + r * (-18.100697012472442755 + r * 27.029044799010561650));
-    double t5 = 3.066858901050631912893148922704 + r * (-4.175335600258177138854984177460 + r * (5.858023729874774148815053846119 + r * t8));
-    double t1 = 2.331643981597124203363536062168 + r * (-1.812187885639363490240191647568 + r * (1.936631114492359755363277457668
-              + r * (-2.353551201881614516821543561516 + r * t5)));
-    double w0 = -1.0 + r * t1;
-    if (q < 3.0e-3) return w0;
-    double w;
-    if (z < -1e-6) w = w0;
-    else { double l1 = log(-z); double l2 = log(-l1); w = l1 - l2 + l2 / l1; }
-    for (int i = 0; i < 10; i++)
+    for (int o = 16; o > 0; o >>= 1)
     {
-        double e = exp(w);
-        double t = w * e - z;
-        double p = w + 1.0;
-        t /= e * p - 0.5 * (p + 1.0) * t / p;
-        w -= t;
-        if (fabs(t) < eps * (1.0 + fabs(w))) return w;
+        nSeg += __shfl_down_sync(0xffffffffu, nSeg, o); nPaths += __shfl_down_sync(0xffffffffu, nPaths, o);
+        nScatt += __shfl_down_sync(0xffffffffu, nScatt, o); nPackets += __shfl_down_sync(0xffffffffu, nPackets, o);
+        nAbs += __shfl_down_sync(0xffffffffu, nAbs, o); nDet += __shfl_down_sync(0xffffffffu, nDet, o);
     }
-    return w;
-}
-
-// Direction(theta, phi), Direction.cpp:12-38
-__device__ __forceinline__ void directionFromAngles(double theta, double phi, double& kx, double& ky, double& kz)
-{
-    const double eps = 1e-8;
-    if (theta <= eps) { kx = 0; ky = 0; kz = 1; }
-    else if (theta >= M_PI - eps) { kx = 0; ky = 0; kz = -1; }
-    else { double st = sin(theta); kx = st * cos(phi); ky = st * sin(phi); kz = cos(theta); }
-}
-
-// Random::direction(), Random.cpp:179-184
-__device__ __forceinline__ void randomDirection(Philox& rng, double& kx, double& ky, double& kz)
-{
-    double theta = acos(2.0 * rng.uniform() - 1.0);
-    double phi = 2.0 * M_PI * rng.uniform();
-    directionFromAngles(theta, phi, kx, ky, kz);
-}
-
-// Random::direction(bfk, costheta), Random.cpp:188-222
-__device__ __forceinline__ void scatterDirection(Philox& rng, double costheta, double& kx, double& ky, double& kz)
-{
-    double phi = 2.0 * M_PI * rng.uniform();
-    double cosphi = cos(phi), sinphi = sin(phi);
-    double sintheta = sqrt(fabs((1.0 - costheta) * (1.0 + costheta)));
-    double kxn, kyn, kzn;
-    if (kz > 0.99999) { kxn = cosphi * sintheta; kyn = sinphi * sintheta; kzn = costheta; }
-    else if (kz < -0.99999) { kxn = cosphi * sintheta; kyn = sinphi * sintheta; kzn = -costheta; }
-    else
+    if ((threadIdx.x & 31) == 0)
     {
-        double root = sqrt((1.0 - kz) * (1.0 + kz));
-        kxn = sintheta / root * (-kx * kz * cosphi + ky * sinphi) + kx * costheta;
-        kyn = -sintheta / root * (ky * kz * cosphi + kx * sinphi) + ky * costheta;
-        kzn = root * sintheta * cosphi + kz * costheta;
-    }
-    kx = kxn; ky = kyn; kz = kzn;
-}
-
-// Random::exponcutoff, Random.cpp:162-175
-__device__ __forceinline__ double exponCutoff(Philox& rng, double xmax)
-{
-    if (xmax == 0.0) return 0.0;
-    else if (xmax < 1e-10) return rng.uniform() * xmax;
-    double x = -log(1.0 - rng.uniform() * (1.0 - exp(-xmax)));
-    while (x > xmax) x = -log(1.0 - rng.uniform() * (1.0 - exp(-xmax)));
-    return x;
-}
-
-// NR::interpolate_loglog, NR.hpp:321-345
-__device__ __forceinline__ double interpLogLog(double x, double x1, double x2, double f1, double f2)
-{
-    x = log10(x); x1 = log10(x1); x2 = log10(x2);
-    bool logf = f1 > 0 && f2 > 0;
-    if (logf) { f1 = log10(f1); f2 = log10(f2); }
-    double fx = f1 + ((x - x1) / (x2 - x1)) * (f2 - f1);
-    if (logf) fx = pow(10.0, fx);
-    return fx;
-}
-
-// Geometry::generatePosition for the supported geometries
-static __device__ void generatePosition(const SourceDev& s, Philox& rng, double& x, double& y, double& z)
-{
-    if (s.geometry == SKG_GEOM_EXPDISK)
-    {
-        // SepAxGeometry::generatePosition (SepAxGeometry.cpp:21-30) + ExpDiskGeometry::randomR/randomz (:134-161)
-        const double hR = s.p[0], hz = s.p[1], Rmax = s.p[2], zmax = s.p[3], Rmin = s.p[4];
-        double R, zz;
-        do
-        {
-            double X = rng.uniform();
-            R = hR * (-1.0 - lambertW1((X - 1.0) / M_E));
-        }
-        while ((Rmax > 0.0 && R >= Rmax) || R <= Rmin);
-        double phi = 2.0 * M_PI * rng.uniform();
-        do
-        {
-            double X = rng.uniform();
-            zz = (X <= 0.5) ? hz * log(2.0 * X) : -hz * log(2.0 * (1.0 - X));
-        }
-        while (zmax > 0.0 && fabs(zz) >= zmax);
-        x = R * cos(phi); y = R * sin(phi); z = zz;     // Position(R,phi,z,CYLINDRICAL), Position.cpp:23-31
-    }
-    else
-    {
-        // SpheGeometry::generatePosition (SpheGeometry.cpp:36-44) with SersicGeometry::randomradius (:85-91),
-        // SersicFunction::inversemass (SersicFunction.cpp:112-124); SpheroidalGeometryDecorator (:78-85)
-        const double reff = s.p[0], q = s.p[1];
-        double X = rng.uniform();
-        int Ns = s.ntab; double sval;
-        if (X <= s.Xv[0]) sval = s.rv[0];
-        else if (X >= s.Xv[Ns - 1]) sval = s.rv[Ns - 1];
-        else
-        {
-            int i = locateClip(s.Xv, X, Ns);
-            sval = interpLogLog(X, s.Xv[i], s.Xv[i + 1], s.rv[i], s.rv[i + 1]);
-        }
-        double r = reff * sval;
-        double kx, ky, kz; randomDirection(rng, kx, ky, kz);
-        x = r * kx; y = r * ky; z = r * kz;             // Position(r,bfk), Position.cpp:51-54
-        z = q * z;
-    }
-    if (s.spiral_arms > 0)
-    {
-        // SpiralStructureGeometryDecorator::generatePosition, SpiralStructureGeometryDecorator.cpp:177-192
-        double R = sqrt(x * x + y * y);
-        double c = s.spiral_c;
-        double phi, t;
-        do
-        {
-            phi = 2.0 * M_PI * rng.uniform();
-            // perturbation(R,phi), :224-229
-            double gamma = log(R / s.spiral_radius) / s.spiral_tanp + s.spiral_phase + 0.5 * M_PI / s.spiral_arms;
-            double pert = (1.0 - s.spiral_weight) + s.spiral_weight * s.spiral_cn * pow(sin(0.5 * s.spiral_arms * (gamma - phi)), 2 * s.spiral_index);
-            t = rng.uniform() * c / pert;
-        }
-        while (t > 1);
-        x = R * cos(phi); y = R * sin(phi);
+        if (nSeg) atomicAdd(&ctr->segments, nSeg);
+        if (nPaths) atomicAdd(&ctr->paths, nPaths);
+        if (nScatt) atomicAdd(&ctr->scatterings, nScatt);
+        if (nPackets) atomicAdd(&ctr->packets, nPackets);
+        if (nAbs) atomicAdd(&ctr->absorbSegments, nAbs);
+        if (nDet) atomicAdd(&ctr->detections, nDet);
     }
 }
 
-// ---- sinks for the life cycle --------------------------------------------------------------------------
-
-// pass 1: DustSystem::fillOpticalDepth + simulateescapeandabsorption streamed per segment
-struct AbsorbSink
+// ---- launch ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev P, Counters* ctr, int nLaunch, unsigned long long firstPacket,
+                                                   const int* __restrict__ freeList, int* __restrict__ aliveList, int aliveBase)
 {
-    KappaRho kr; const Medium* med; int ell;
-    double L;               // packet luminosity at the start of the path
-    double albedo;          // Ncomp==1: DustMix::albedo(ell)
-    double* labs;           // Labs + ell (stride Nlambda) or null
-    double tau = 0, Lsca = 0;
-    int n = 0, nAbs = 0;
-    __device__ __forceinline__ bool add(int m, double ds)
+    unsigned long long nPackets = 0;
+    const int Nlambda = P.med.Nlambda;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nLaunch; j += gridDim.x * blockDim.x)
     {
-        n++;
-        if (m < 0) return true;             // rho(-1,h) = 0: dtau = 0, nothing absorbed
-        nAbs++;
-        int Ncomp = med->Ncomp;
-        if (Ncomp == 1)
-        {
-            double dtau = kr(m) * ds;
-            if (labs)
-            {
-                double Lintm = L * exp(-tau) * (-expm1(-dtau));
-                double Labsm = (1.0 - albedo) * Lintm;
-                atomicAdd(labs + (size_t)m * med->Nlambda, Labsm);
-            }
-            tau += dtau;
-        }
-        else
-        {
-            double ksca = 0.0, kext = 0.0, krr = 0.0;
-            for (int h = 0; h < Ncomp; h++)
-            {
-                double rho = __ldg(med->rho + (size_t)m * Ncomp + h);
-                ksca += rho * __ldg(med->ksca + (size_t)h * med->Nlambda + ell);
-                double ke = __ldg(med->kext + (size_t)h * med->Nlambda + ell);
-                kext += rho * ke;
-                krr += ke * rho;
-            }
-            double alb = (kext > 0.0) ? ksca / kext : 0.0;
-            double dtau = krr * ds;
-            double Lintm = L * exp(-tau) * (-expm1(-dtau));
-            Lsca += alb * Lintm;
-            if (labs) atomicAdd(labs + (size_t)m * med->Nlambda, (1.0 - alb) * Lintm);
-            tau += dtau;
-        }
-        return true;
-    }
-};
-
-// pass 2: DustGridPath::pathlength(tau) evaluated on the fly (DustGridPath.cpp:162-173)
-struct PropagateSink
-{
-    KappaRho kr; double target;
-    double sPrev = 0, tauPrev = 0, result = 0;
-    bool found = false;
-    int n = 0;
-    __device__ __forceinline__ bool add(int m, double ds)
-    {
-        n++;
-        double sNew = sPrev + ds;
-        double tauNew = tauPrev + kr(m) * ds;
-        if (target < tauNew)
-        {
-            result = sPrev + ((target - tauPrev) / (tauNew - tauPrev)) * (sNew - sPrev);     // NR::interpolate_linlin
-            found = true;
-            return false;
-        }
-        sPrev = sNew; tauPrev = tauNew;
-        return true;
-    }
-    __device__ __forceinline__ double s() const { return found ? result : sPrev; }
-};
-
-template<int KIND, class Sink>
-__device__ __forceinline__ void walkMC(const GridSetMC& G, const CartGrid& cart, Counters* ctr,
-                                       double x, double y, double z, double kx, double ky, double kz, Sink& sink)
-{
-    if (KIND == GRID_CART) walkCart(cart, x, y, z, kx, ky, kz, sink);
-    else if (KIND == GRID_TREE) walkTree(G.tree, ctr, x, y, z, kx, ky, kz, sink);
-    else if (KIND == GRID_AMESH) walkAMesh(G.amesh, ctr, x, y, z, kx, ky, kz, sink);
-    else walkVoro(G.voro, ctr, x, y, z, kx, ky, kz, sink);
-}
-
-template<int KIND>
-__device__ __forceinline__ int whichCellMC(const GridSetMC& G, const CartGrid& cart, double x, double y, double z)
-{
-    if (KIND == GRID_CART) return cartWhichCell(cart, x, y, z);
-    else if (KIND == GRID_TREE) { int node = treeWhichNode(G.tree, x, y, z); return node >= 0 ? G.tree.cell[node] : -1; }
-    else if (KIND == GRID_AMESH) { int node = ameshWhichNode(G.amesh, x, y, z); return node >= 0 ? G.amesh.cell[node] : -1; }
-    else return voroCellIndex(G.voro, x, y, z);
-}
-
-// Instrument::detect for the peel-off packet (r, kobs, L): returns the number of segments walked
-template<int KIND>
-__device__ __forceinline__ int detect(const GridSetMC& G, const CartGrid& cart, Counters* ctr, const McDev& P, const InstrDev& I,
-                                      int ell, double x, double y, double z, double L, unsigned long long& nDet)
-{
-    int l = -1;
-    if (I.kind != SKG_INSTR_SED)
-    {
-        // SingleFrameInstrument::pixelondetector, SingleFrameInstrument.cpp:130-147
-        double xpp = -I.sinphi * x + I.cosphi * y;
-        double ypp = -I.cosphi * I.costheta * x - I.sinphi * I.costheta * y + I.sintheta * z;
-        double xp = I.cospa * xpp - I.sinpa * ypp;
-        double yp = I.sinpa * xpp + I.cospa * ypp;
-        int i = (int)floor((xp - I.xpmin) / I.xpsiz);
-        int j = (int)floor((yp - I.ypmin) / I.ypsiz);
-        if (!(i < 0 || i >= I.Nxp || j < 0 || j >= I.Nyp)) l = i + I.Nxp * j;
-        if (I.kind == SKG_INSTR_FRAME && l < 0) return 0;       // FrameInstrument.cpp:36: no path for off-frame packets
-    }
-    TauSink sink;
-    sink.kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
-    sink.distance = SKG_DBL_MAX;
-    if (P.med.rho) walkMC<KIND>(G, cart, ctr, x, y, z, I.kobsx, I.kobsy, I.kobsz, sink);     // Instrument::opticalDepth: 0 without dust
-    double Lextf = L * exp(-sink.tau);
-    if (I.kind != SKG_INSTR_FRAME) { atomicAdd(I.sed + ell, Lextf); nDet++; }
-    if (I.kind != SKG_INSTR_SED && l >= 0) { atomicAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
-    return sink.n;
-}
-
-template<int KIND>
-__global__ void __launch_bounds__(128) stellarKernel(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P,
-                                                     Counters* ctr, bool cartSmem)
-{
-    extern __shared__ double smem[];
-    CartGrid cart = G.cart;
-    if (KIND == GRID_CART && cartSmem)
-    {
-        int nx = cart.Nx + 1, ny = cart.Ny + 1, nz = cart.Nz + 1;
-        for (int i = threadIdx.x; i < nx; i += blockDim.x) smem[i] = cart.xv[i];
-        for (int i = threadIdx.x; i < ny; i += blockDim.x) smem[nx + i] = cart.yv[i];
-        for (int i = threadIdx.x; i < nz; i += blockDim.x) smem[nx + ny + i] = cart.zv[i];
-        __syncthreads();
-        cart.xv = smem; cart.yv = smem + nx; cart.zv = smem + nx + ny;
-    }
-
-    unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nPackets = 0, nAbs = 0, nDet = 0;
-    const unsigned long long total = P.NppInt * (unsigned long long)(P.ellEnd - P.ellBegin);
-    const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
-
-    for (unsigned long long gidx = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; gidx < total;
-         gidx += (unsigned long long)gridDim.x * blockDim.x)
-    {
-        const int ell = P.ellBegin + (int)(gidx / P.NppInt);
+        const int slot = freeList[j];
+        const unsigned long long gidx = firstPacket + j;
+        const int ell = P.ellList[gidx / P.NppInt];
         const unsigned long long ipkt = gidx % P.NppInt;
-        // MonteCarloSimulation.cpp:267-271
+        // MonteCarloSimulation.cpp:267-268
         double L = __ldg(P.Ltot + ell) / P.Lscale;
-        if (!(L > 0)) continue;
-        const double Lthreshold = L / P.minWeightReduction;
-        Philox rng; rng.init(P.seed, (P.streamOffset + ipkt) * (unsigned long long)Nlambda + ell);
+        const unsigned long long id = (P.streamOffset + ipkt) * (unsigned long long)Nlambda + ell;
+        Philox rng; rng.init(P.seed, id);
         nPackets++;
 
         // ---- StellarSystem::launch, StellarSystem.cpp:116-158 ----
@@ -361,139 +88,258 @@ __global__ void __launch_bounds__(128) stellarKernel(const __grid_constant__ Gri
             }
             else L = 0;
         }
-        if (!(L > 0)) continue;
-        double x, y, z, kx, ky, kz;
-        generatePosition(P.sources[h], rng, x, y, z);        // GeometricStellarComp::launch, GeometricStellarComp.cpp:75-81
-        randomDirection(rng, kx, ky, kz);                    // Geometry::generateDirection, Geometry.cpp:33
-        int nscatt = 0;
-
-        // ---- peeloffemission, MonteCarloSimulation.cpp:305-315 (isotropic emitter: probabilityForDirection = 1) ----
-        for (int q = 0; q < P.Ninstr; q++)
+        double x = 0, y = 0, z = 0, kx = 0, ky = 0, kz = 1;
+        if (L > 0)
         {
-            int ns = detect<KIND>(G, cart, ctr, P, P.instr[q], ell, x, y, z, L, nDet);
-            nSeg += ns; nPaths++;
+            generatePosition(P.sources[h], rng, x, y, z);        // GeometricStellarComp::launch, GeometricStellarComp.cpp:75-81
+            randomDirection(rng, kx, ky, kz);                    // Geometry::generateDirection, Geometry.cpp:33
         }
+        const PacketPool& q = P.pool;
+        q.x[slot] = x; q.y[slot] = y; q.z[slot] = z; q.kx[slot] = kx; q.ky[slot] = ky; q.kz[slot] = kz;
+        q.L[slot] = L; q.target[slot] = 0; q.id[slot] = id; q.ell[slot] = ell; q.nscatt[slot] = 0; q.rngCtr[slot] = rng.c2; q.fresh[slot] = 1;
+        aliveList[aliveBase + j] = slot;
+    }
+    flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
+}
 
-        if (P.med.rho) while (true)
+// ---- peel-off + detection ------------------------------------------------------------------------------------
+// SingleFrameInstrument::pixelondetector, SingleFrameInstrument.cpp:130-147; -1 when the position maps off the frame
+__device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, double y, double z)
+{
+    double xpp = -I.sinphi * x + I.cosphi * y;
+    double ypp = -I.cosphi * I.costheta * x - I.sinphi * I.costheta * y + I.sintheta * z;
+    double xp = I.cospa * xpp - I.sinpa * ypp;
+    double yp = I.sinpa * xpp + I.cospa * ypp;
+    int i = (int)floor((xp - I.xpmin) / I.xpsiz);
+    int j = (int)floor((yp - I.ypmin) / I.ypsiz);
+    if (i < 0 || i >= I.Nxp || j < 0 || j >= I.Nyp) return -1;
+    return i + I.Nxp * j;
+}
+
+template<int KIND>
+__global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+                                                 const int* __restrict__ aliveList, int nAlive)
+{
+    extern __shared__ double smem[];
+    CartGrid cart = G.cart;
+    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    unsigned long long nSeg = 0, nPaths = 0, nDet = 0;
+    const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
+    const PacketPool& q = P.pool;
+    const long long total = (long long)nAlive * P.Ngroups;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
+    {
+        const int slot = aliveList[t / P.Ngroups];
+        const ObsGroup& grp = P.groups[t % P.Ngroups];
+        double L = q.L[slot];
+        if (!(L > 0)) continue;                                 // MonteCarloSimulation.cpp:281
+        const double x = q.x[slot], y = q.y[slot], z = q.z[slot];
+        const int ell = q.ell[slot];
+
+        // which instruments of this direction record the packet?  FrameInstrument ignores packets that map outside
+        // its frame before any optical depth is computed (FrameInstrument.cpp:36); SED/Simple always need tau
+        bool need = false;
+        for (int c = 0; c < grp.count; c++)
         {
-            // ---- fillOpticalDepth + simulateescapeandabsorption, :286-288, :438-515 ----
-            AbsorbSink ab;
-            ab.kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
-            ab.med = &P.med; ab.ell = ell; ab.L = L;
-            ab.labs = P.labs ? P.labs + ell : nullptr;
-            double kext0 = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
-            ab.albedo = kext0 > 0 ? ksca0 / kext0 : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
-            walkMC<KIND>(G, cart, ctr, x, y, z, kx, ky, kz, ab);
-            nSeg += ab.n; nPaths++; if (ab.labs) nAbs += ab.nAbs;
-            const double taupath = ab.tau;
-            if (Ncomp == 1) L = L * ab.albedo * (-expm1(-taupath));
-            else L = ab.Lsca;
+            const InstrDev& I = P.instr[grp.first + c];
+            if (I.kind != SKG_INSTR_FRAME || pixelOnDetector(I, x, y, z) >= 0) { need = true; break; }
+        }
+        if (!need) continue;
 
-            // ---- termination test, :289 ----
-            if (L <= 0 || (L <= Lthreshold && nscatt >= P.minfs)) break;
-
-            // ---- simulatepropagation, :519-537 ----
-            if (taupath != 0.0)
-            {
-                double tau;
-                if (P.xi == 0.0) tau = exponCutoff(rng, taupath);
-                else
-                {
-                    double X = rng.uniform();
-                    tau = (X < P.xi) ? rng.uniform() * taupath : exponCutoff(rng, taupath);
-                    double p = -exp(-tau) / expm1(-taupath);
-                    double q = (1.0 - P.xi) * p + P.xi / taupath;
-                    L = L * (p / q);
-                }
-                double s = 0;
-                if (tau > 0)
-                {
-                    PropagateSink pr;
-                    pr.kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
-                    pr.target = tau;
-                    walkMC<KIND>(G, cart, ctr, x, y, z, kx, ky, kz, pr);
-                    nSeg += pr.n; nPaths++;
-                    s = pr.s();
-                }
-                x += s * kx; y += s * ky; z += s * kz;      // PhotonPackage::propagate, PhotonPackage.cpp:93-96
-            }
-
-            // ---- peeloffscattering, :319-363 ----
-            double wv[8]; bool peel = true; int mcell = -2;
+        if (!q.fresh[slot])
+        {
+            // ---- peeloffscattering, MonteCarloSimulation.cpp:319-363: weight by the phase function towards the observer ----
+            const double kx = q.kx[slot], ky = q.ky[slot], kz = q.kz[slot];
+            double wv[8];
             if (Ncomp == 1) wv[0] = 1.0;
             else
             {
-                mcell = whichCellMC<KIND>(G, cart, x, y, z);
-                if (mcell == -1) peel = false;
-                else
-                {
-                    double sum = 0;
-                    for (int c = 0; c < Ncomp && c < 8; c++)
-                    { wv[c] = __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c); sum += wv[c]; }
-                    if (sum <= 0) peel = false;
-                    else for (int c = 0; c < Ncomp && c < 8; c++) wv[c] /= sum;
-                }
-            }
-            if (peel) for (int q = 0; q < P.Ninstr; q++)
-            {
-                const InstrDev& I = P.instr[q];
-                double cosalpha = kx * I.kobsx + ky * I.kobsy + kz * I.kobsz;       // Direction::dot
-                double w = 0;
+                int mcell = whichCellMC<KIND>(G, cart, x, y, z);
+                if (mcell == -1) continue;
+                double sum = 0;
                 for (int c = 0; c < Ncomp && c < 8; c++)
-                {
-                    // DustMix::phaseFunctionValue (HG), DustMix.cpp:665-668
-                    double g = __ldg(P.med.g + (size_t)c * Nlambda + ell);
-                    double t = 1.0 + g * g - 2 * g * cosalpha;
-                    w += wv[c] * ((1.0 - g) * (1.0 + g) / sqrt(t * t * t));
-                }
-                int ns = detect<KIND>(G, cart, ctr, P, I, ell, x, y, z, L * w, nDet);      // launchScatteringPeelOff, PhotonPackage.cpp:51-62
-                nSeg += ns; nPaths++;
+                { wv[c] = __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c); sum += wv[c]; }
+                if (sum <= 0) continue;
+                for (int c = 0; c < Ncomp && c < 8; c++) wv[c] /= sum;
             }
+            double cosalpha = kx * grp.kx + ky * grp.ky + kz * grp.kz;          // Direction::dot
+            double w = 0;
+            for (int c = 0; c < Ncomp && c < 8; c++)
+            {
+                // DustMix::phaseFunctionValue (HG), DustMix.cpp:665-668
+                double g = __ldg(P.med.g + (size_t)c * Nlambda + ell);
+                double tt = 1.0 + g * g - 2 * g * cosalpha;
+                w += wv[c] * ((1.0 - g) * (1.0 + g) / sqrt(tt * tt * tt));
+            }
+            L = L * w;                                              // launchScatteringPeelOff, PhotonPackage.cpp:51-62
+        }
 
-            // ---- simulatescattering, :541-549 ----
-            int hmix = 0;
-            if (Ncomp > 1)
+        // Instrument::opticalDepth (Instrument.cpp:69-72) once per direction; 0 without dust
+        TauSink sink;
+        sink.kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
+        sink.distance = SKG_DBL_MAX;
+        if (P.med.rho) { walkMC<KIND>(G, cart, ctr, x, y, z, grp.kx, grp.ky, grp.kz, sink); nSeg += sink.n; nPaths++; }
+        const double Lextf = L * exp(-sink.tau);
+        for (int c = 0; c < grp.count; c++)
+        {
+            const InstrDev& I = P.instr[grp.first + c];
+            // SEDInstrument::detect SEDInstrument.cpp:32-42, FrameInstrument::detect FrameInstrument.cpp:32-47, SimpleInstrument.cpp:33-49
+            if (I.kind != SKG_INSTR_FRAME) { warpAggregatedAdd(I.sed + ell, Lextf); nDet++; }
+            if (I.kind != SKG_INSTR_SED)
             {
-                // DustSystem::randomMixForPosition, DustSystem.cpp:879-893
-                if (mcell == -2) mcell = whichCellMC<KIND>(G, cart, x, y, z);
-                if (mcell >= 0)
-                {
-                    double Xv[9]; Xv[0] = 0;
-                    for (int c = 0; c < Ncomp && c < 8; c++)
-                        Xv[c + 1] = Xv[c] + __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c);
-                    double tot = Xv[Ncomp];
-                    for (int c = 0; c <= Ncomp; c++) Xv[c] /= tot;
-                    hmix = locateClip(Xv, rng.uniform(), Ncomp + 1);
-                }
+                int l = pixelOnDetector(I, x, y, z);
+                if (l >= 0) { warpAggregatedAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
             }
-            {
-                // DustMix::scatteringDirectionAndPolarization (HG branch), DustMix.cpp:607-614
-                double g = __ldg(P.med.g + (size_t)hmix * Nlambda + ell);
-                if (fabs(g) < 1e-6) randomDirection(rng, kx, ky, kz);
-                else
-                {
-                    double f = ((1.0 - g) * (1.0 + g)) / (1.0 - g + 2.0 * g * rng.uniform());
-                    double costheta = (1.0 + g * g - f * f) / (2.0 * g);
-                    scatterDirection(rng, costheta, kx, ky, kz);
-                }
-            }
-            nscatt++; nScatt++;
         }
     }
+    flushStats(ctr, nSeg, nPaths, 0, 0, 0, nDet);
+}
 
-    // statistics: warp-aggregated, one atomic per warp and counter
-    for (int o = 16; o > 0; o >>= 1)
+// ---- scatter (old packets) + escape/absorption + termination + interaction sampling ---------------------------------
+template<int KIND>
+__global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+                                                   const int* __restrict__ aliveList, int nAlive, int* __restrict__ survivors,
+                                                   int* __restrict__ freeList, int* __restrict__ counts)
+{
+    extern __shared__ double smem[];
+    CartGrid cart = G.cart;
+    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
+    const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
+    const PacketPool& q = P.pool;
+    const int nIter = (nAlive + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
+    for (int it = 0; it < nIter; it++)
     {
-        nSeg += __shfl_down_sync(0xffffffffu, nSeg, o); nPaths += __shfl_down_sync(0xffffffffu, nPaths, o);
-        nScatt += __shfl_down_sync(0xffffffffu, nScatt, o); nPackets += __shfl_down_sync(0xffffffffu, nPackets, o);
-        nAbs += __shfl_down_sync(0xffffffffu, nAbs, o); nDet += __shfl_down_sync(0xffffffffu, nDet, o);
+        const int idx = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = idx < nAlive;
+        int slot = 0; bool survive = false;
+        if (valid)
+        {
+            slot = aliveList[idx];
+            double L = q.L[slot];
+            if (L > 0 && P.med.rho)
+            {
+                const int ell = q.ell[slot];
+                const double x = q.x[slot], y = q.y[slot], z = q.z[slot];
+                double kx = q.kx[slot], ky = q.ky[slot], kz = q.kz[slot];
+                int nscatt = q.nscatt[slot];
+                Philox rng; rng.init(P.seed, q.id[slot]); rng.c2 = q.rngCtr[slot];
+                if (!q.fresh[slot])
+                {
+                    // ---- simulatescattering, MonteCarloSimulation.cpp:541-549 ----
+                    int hmix = 0;
+                    if (Ncomp > 1)
+                    {
+                        // DustSystem::randomMixForPosition, DustSystem.cpp:879-893
+                        int mcell = whichCellMC<KIND>(G, cart, x, y, z);
+                        if (mcell >= 0)
+                        {
+                            double Xv[9]; Xv[0] = 0;
+                            for (int c = 0; c < Ncomp && c < 8; c++)
+                                Xv[c + 1] = Xv[c] + __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c);
+                            double tot = Xv[Ncomp];
+                            for (int c = 0; c <= Ncomp; c++) Xv[c] /= tot;
+                            hmix = locateClip(Xv, rng.uniform(), Ncomp + 1);
+                        }
+                    }
+                    // DustMix::scatteringDirectionAndPolarization (HG branch), DustMix.cpp:607-614
+                    double g = __ldg(P.med.g + (size_t)hmix * Nlambda + ell);
+                    if (fabs(g) < 1e-6) randomDirection(rng, kx, ky, kz);
+                    else
+                    {
+                        double f = ((1.0 - g) * (1.0 + g)) / (1.0 - g + 2.0 * g * rng.uniform());
+                        double costheta = (1.0 + g * g - f * f) / (2.0 * g);
+                        scatterDirection(rng, costheta, kx, ky, kz);
+                    }
+                    nscatt++; nScatt++;
+                    q.kx[slot] = kx; q.ky[slot] = ky; q.kz[slot] = kz; q.nscatt[slot] = nscatt;
+                }
+
+                // ---- fillOpticalDepth + simulateescapeandabsorption, :286-288, :438-515 ----
+                AbsorbSink ab;
+                ab.kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
+                ab.med = &P.med; ab.ell = ell; ab.L = L;
+                ab.labs = P.labs ? P.labs + (size_t)ell * P.med.Ncells : nullptr;
+                double kext0 = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
+                ab.albedo = kext0 > 0 ? ksca0 / kext0 : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
+                walkMC<KIND>(G, cart, ctr, x, y, z, kx, ky, kz, ab);
+                nSeg += ab.n; nPaths++; nAbs += ab.nAbs;
+                const double taupath = ab.tau;
+                if (Ncomp == 1) L = L * ab.albedo * (-expm1(-taupath));
+                else L = ab.Lsca;
+
+                // ---- termination test, :289 ----
+                const double Lthreshold = __ldg(P.Ltot + ell) / P.Lscale / P.minWeightReduction;
+                survive = !(L <= 0 || (L <= Lthreshold && nscatt >= P.minfs));
+                if (survive)
+                {
+                    // ---- simulatepropagation, :519-533: sample the interaction optical depth, weight for the bias ----
+                    double tau = 0;
+                    if (taupath != 0.0)
+                    {
+                        if (P.xi == 0.0) tau = exponCutoff(rng, taupath);
+                        else
+                        {
+                            double X = rng.uniform();
+                            tau = (X < P.xi) ? rng.uniform() * taupath : exponCutoff(rng, taupath);
+                            double p = -exp(-tau) / expm1(-taupath);
+                            double qq = (1.0 - P.xi) * p + P.xi / taupath;
+                            L = L * (p / qq);
+                        }
+                    }
+                    q.target[slot] = tau;
+                }
+                q.L[slot] = L; q.rngCtr[slot] = rng.c2;
+            }
+        }
+        warpAppend(valid && survive, slot, survivors, counts);
+        warpAppend(valid && !survive, slot, freeList, counts + 1);
     }
-    if ((threadIdx.x & 31) == 0)
+    flushStats(ctr, nSeg, nPaths, nScatt, 0, nAbs, 0);
+}
+
+// ---- propagate to the interaction point ---------------------------------------------------------------------
+template<int KIND>
+__global__ void __launch_bounds__(128) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+                                                      const int* __restrict__ survivors, int nSurv)
+{
+    extern __shared__ double smem[];
+    CartGrid cart = G.cart;
+    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    unsigned long long nSeg = 0, nPaths = 0;
+    const PacketPool& q = P.pool;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nSurv; idx += gridDim.x * blockDim.x)
     {
-        atomicAdd(&ctr->segments, nSeg); atomicAdd(&ctr->paths, nPaths);
-        atomicAdd(&ctr->scatterings, nScatt); atomicAdd(&ctr->packets, nPackets);
-        atomicAdd(&ctr->absorbSegments, nAbs); atomicAdd(&ctr->detections, nDet);
+        const int slot = survivors[idx];
+        const double tau = q.target[slot];
+        q.fresh[slot] = 0;
+        if (!(tau > 0)) continue;
+        const int ell = q.ell[slot];
+        double x = q.x[slot], y = q.y[slot], z = q.z[slot];
+        const double kx = q.kx[slot], ky = q.ky[slot], kz = q.kz[slot];
+        PropagateSink pr;
+        pr.kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
+        pr.target = tau;
+        walkMC<KIND>(G, cart, ctr, x, y, z, kx, ky, kz, pr);
+        nSeg += pr.n; nPaths++;
+        const double s = pr.s();
+        q.x[slot] = x + s * kx; q.y[slot] = y + s * ky; q.z[slot] = z + s * kz;      // PhotonPackage::propagate, PhotonPackage.cpp:93-96
     }
+    flushStats(ctr, nSeg, nPaths, 0, 0, 0, 0);
+}
+
+__global__ void iotaKernel(int* list, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) list[i] = i; }
+
+// Labs is wavelength-major on the device; the host interface is DustSystem's (m, ell) row-major table
+__global__ void transposeLabs(const double* __restrict__ src, double* __restrict__ dst, int Ncells, int Nlambda)
+{
+    __shared__ double tile[32][33];
+    int m0 = blockIdx.x * 32, l0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    { int l = l0 + r, m = m0 + threadIdx.x; if (l < Nlambda && m < Ncells) tile[r][threadIdx.x] = src[(size_t)l * Ncells + m]; }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y)
+    { int m = m0 + r, l = l0 + threadIdx.x; if (l < Nlambda && m < Ncells) dst[(size_t)m * Nlambda + l] = tile[threadIdx.x][r]; }
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
@@ -605,6 +451,20 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
         e.instr.push_back(d);
     }
     e.instrDev.upload(e.instr.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
+    // observer groups: instruments with the same line of sight share one peel-off traversal per event
+    std::vector<InstrDev> grouped; std::vector<ObsGroup> groups; std::vector<char> used(n, 0);
+    for (int i = 0; i < n; i++)
+    {
+        if (used[i]) continue;
+        ObsGroup g; g.kx = e.instr[i].kobsx; g.ky = e.instr[i].kobsy; g.kz = e.instr[i].kobsz; g.first = (int)grouped.size(); g.count = 0;
+        for (int j = i; j < n; j++)
+            if (!used[j] && e.instr[j].kobsx == g.kx && e.instr[j].kobsy == g.ky && e.instr[j].kobsz == g.kz)
+            { used[j] = 1; grouped.push_back(e.instr[j]); g.count++; }
+        groups.push_back(g);
+    }
+    e.Ngroups = (int)groups.size();
+    e.instrGroupedDev.upload(grouped.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
+    e.groupsDev.upload(groups.data(), sizeof(ObsGroup) * std::max<size_t>(groups.size(), 1), e.stream);
     e.sync();
 }
 
@@ -619,6 +479,54 @@ void mcResetResults(Engine& e)
     e.sync();
 }
 
+void mcFetchLabs(Engine& e, double* host, int add)
+{
+    if (!e.labs.p || e.labsCount == 0) throw Error("absorption rates were not stored");
+    int Nl = e.NlambdaSrc ? e.NlambdaSrc : e.med.Nlambda, Nc = e.Ncells;
+    e.labsT.ensure(sizeof(double) * e.labsCount);
+    dim3 grid((Nc + 31) / 32, (Nl + 31) / 32), block(32, 8);
+    transposeLabs<<<grid, block, 0, e.stream>>>(e.labs.as<double>(), e.labsT.as<double>(), Nc, Nl);
+    e.launches++; SKG_CUDA(cudaGetLastError());
+    if (!add) { SKG_CUDA(cudaMemcpyAsync(host, e.labsT.p, sizeof(double) * e.labsCount, cudaMemcpyDeviceToHost, e.stream)); e.sync(); return; }
+    std::vector<double> tmp(e.labsCount);
+    SKG_CUDA(cudaMemcpyAsync(tmp.data(), e.labsT.p, sizeof(double) * e.labsCount, cudaMemcpyDeviceToHost, e.stream)); e.sync();
+    for (int64_t i = 0; i < e.labsCount; i++) host[i] += tmp[i];
+}
+
+template<int KIND>
+static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned long long total, int pool, size_t smem, bool cartSmem)
+{
+    int* listA = e.mcLists.as<int>(); int* listB = listA + pool; int* freeList = listB + pool;
+    int* counts = e.mcCounts.as<int>();
+    auto blocksFor = [&](long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, (long long)e.smCount * 16)); };
+    iotaKernel<<<blocksFor(pool), 128, 0, e.stream>>>(freeList, pool); e.launches++;
+    unsigned long long launched = 0;
+    int nAlive = 0, nFree = pool;
+    int* hostCounts = e.mcHostCounts;
+    while (true)
+    {
+        int nLaunch = (int)std::min<unsigned long long>((unsigned long long)nFree, total - launched);
+        if (nLaunch > 0)
+        {
+            launchStage<<<blocksFor(nLaunch), 128, 0, e.stream>>>(P, e.ctr(), nLaunch, launched, freeList, listA, nAlive); e.launches++;
+            nAlive += nLaunch; launched += nLaunch;
+        }
+        if (nAlive == 0) break;
+        if (P.Ngroups > 0)
+        { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive); e.launches++; }
+        SKG_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), e.stream));
+        absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, listB, freeList, counts); e.launches++;
+        SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+        SKG_CUDA(cudaGetLastError());
+        e.sync();
+        int nSurv = hostCounts[0]; nFree = hostCounts[1];
+        if (nSurv > 0) { propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listB, nSurv); e.launches++; }
+        std::swap(listA, listB);
+        nAlive = nSurv;
+    }
+    SKG_CUDA(cudaGetLastError());
+}
+
 void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
 {
     if (e.gridKind == GRID_NONE && e.med.rho) throw Error("no dust grid has been set");
@@ -628,8 +536,10 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
     if (p.ellBegin < 0 || p.ellEnd > Nlambda || p.ellBegin > p.ellEnd) throw Error("wavelength range out of bounds");
     if (p.scattBias < 0 || p.scattBias > 1) throw Error("scattBias should be between 0 and 1");
     if (e.med.Ncomp > 8) throw Error("at most 8 dust components are supported");
+    if (!(p.packages >= 0) || p.packages > 1e15) throw Error("Number of photon packages is negative or larger than implementation limit of 1e15");
     if (p.storeAbsorption)
     {
+        if (!e.med.rho) throw Error("absorption rates can only be stored with a dust system");
         int64_t count = (int64_t)e.Ncells * Nlambda;
         if (e.labsCount != count)
         {
@@ -642,37 +552,61 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
     P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
     P.L = e.lumDev.as<double>(); P.Ltot = e.lumTotDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>();
     P.emissionBias = e.emissionBias;
-    P.instr = e.instrDev.as<InstrDev>(); P.Ninstr = (int)e.instr.size();
+    P.instr = e.instrGroupedDev.as<InstrDev>(); P.Ninstr = (int)e.instr.size();
+    P.groups = e.groupsDev.as<ObsGroup>(); P.Ngroups = e.Ngroups;
     P.labs = p.storeAbsorption ? e.labs.as<double>() : nullptr;
     P.NppInt = (unsigned long long)std::ceil(p.packages);
-    P.Npp = (double)P.NppInt; P.Lscale = p.luminosityScale > 0 ? p.luminosityScale : P.Npp;
+    P.Lscale = p.luminosityScale > 0 ? p.luminosityScale : (double)P.NppInt;
     P.minWeightReduction = p.minWeightReduction; P.minfs = p.minScattEvents; P.xi = p.scattBias;
-    P.seed = p.seed; P.streamOffset = p.streamOffset; P.ellBegin = p.ellBegin; P.ellEnd = p.ellEnd;
+    P.seed = p.seed; P.streamOffset = p.streamOffset;
 
-    GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro;
-    unsigned long long total = P.NppInt * (unsigned long long)(p.ellEnd - p.ellBegin);
+    // wavelengths with luminosity, in shooting order (the reference skips the others, MonteCarloSimulation.cpp:269,298)
+    std::vector<int> ells;
+    for (int ell = p.ellBegin; ell < p.ellEnd; ell++) if (e.lumTotHost[ell] > 0) ells.push_back(ell);
+    unsigned long long total = P.NppInt * (unsigned long long)ells.size();
+
     Counters before = e.readCounters();
     cudaEvent_t ev0, ev1; SKG_CUDA(cudaEventCreate(&ev0)); SKG_CUDA(cudaEventCreate(&ev1));
     SKG_CUDA(cudaEventRecord(ev0, e.stream));
     if (total > 0)
     {
-        long long want = (long long)((total + 127) / 128);
-        int blocks = (int)std::max<long long>(1, std::min<long long>(want, (long long)e.smCount * 16));
+        e.mcEllList.upload(ells.data(), sizeof(int) * ells.size(), e.stream);
+        P.ellList = e.mcEllList.as<int>();
+        // the pool of in-flight packets
+        int pool = p.poolPackets > 0 ? p.poolPackets : (1 << 22);
+        pool = (int)std::min<unsigned long long>((unsigned long long)pool, total);
+        pool = std::max(pool, 1);
+        size_t per = 8 * sizeof(double) + sizeof(unsigned long long) + 4 * sizeof(int);
+        e.mcPool.ensure(per * (size_t)pool + 256);
+        char* base = e.mcPool.as<char>();
+        double* d = reinterpret_cast<double*>(base);
+        PacketPool& q = P.pool;
+        q.x = d; q.y = d + (size_t)pool; q.z = d + 2 * (size_t)pool; q.kx = d + 3 * (size_t)pool; q.ky = d + 4 * (size_t)pool; q.kz = d + 5 * (size_t)pool;
+        q.L = d + 6 * (size_t)pool; q.target = d + 7 * (size_t)pool;
+        q.id = reinterpret_cast<unsigned long long*>(d + 8 * (size_t)pool);
+        int* ip = reinterpret_cast<int*>(q.id + (size_t)pool);
+        q.ell = ip; q.nscatt = ip + (size_t)pool; q.rngCtr = reinterpret_cast<unsigned*>(ip + 2 * (size_t)pool); q.fresh = ip + 3 * (size_t)pool;
+        e.mcLists.ensure(sizeof(int) * 3 * (size_t)pool);
+        e.mcCounts.ensure(sizeof(int) * 2);
+        if (!e.mcHostCounts) SKG_CUDA(cudaMallocHost(&e.mcHostCounts, 2 * sizeof(int)));
+
         size_t smem = 0; bool cartSmem = false;
         if (e.gridKind == GRID_CART)
         {
             size_t need = sizeof(double) * (size_t)(e.cart.Nx + e.cart.Ny + e.cart.Nz + 3);
             if (need <= 40 * 1024) { smem = need; cartSmem = true; }
         }
+        GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro;
         switch (e.gridKind)
         {
-        case GRID_CART: stellarKernel<GRID_CART><<<blocks, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem); break;
-        case GRID_TREE: stellarKernel<GRID_TREE><<<blocks, 128, 0, e.stream>>>(G, P, e.ctr(), false); break;
-        case GRID_AMESH: stellarKernel<GRID_AMESH><<<blocks, 128, 0, e.stream>>>(G, P, e.ctr(), false); break;
-        case GRID_VORO: stellarKernel<GRID_VORO><<<blocks, 128, 0, e.stream>>>(G, P, e.ctr(), false); break;
-        default: throw Error("no dust grid has been set");
+        case GRID_CART: shootWavefront<GRID_CART>(e, G, P, total, pool, smem, cartSmem); break;
+        case GRID_TREE: shootWavefront<GRID_TREE>(e, G, P, total, pool, 0, false); break;
+        case GRID_AMESH: shootWavefront<GRID_AMESH>(e, G, P, total, pool, 0, false); break;
+        case GRID_VORO: shootWavefront<GRID_VORO>(e, G, P, total, pool, 0, false); break;
+        default:
+            if (e.med.rho) throw Error("no dust grid has been set");
+            shootWavefront<GRID_CART>(e, G, P, total, pool, 0, false);      // no dust: only launch + emission peel-off run
         }
-        e.launches++; SKG_CUDA(cudaGetLastError());
     }
     SKG_CUDA(cudaEventRecord(ev1, e.stream));
     e.sync();
@@ -688,78 +622,4 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
     }
 }
 
-// ---- NCCL (loaded at run time: libnccl.so.2 is already in the process when torch.distributed is) ---------
-typedef struct ncclComm* ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-typedef int (*fnGetUniqueId)(ncclUniqueId*);
-typedef int (*fnCommInitRank)(ncclComm_t*, int, ncclUniqueId, int);
-typedef int (*fnAllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t);
-typedef int (*fnGroup)(void);
-typedef const char* (*fnErr)(int);
-static struct { void* lib = nullptr; fnGetUniqueId getUniqueId; fnCommInitRank commInitRank; fnAllReduce allReduce; fnGroup groupStart, groupEnd; fnErr errString; } nccl;
-
-static void loadNccl()
-{
-    if (nccl.lib) return;
-    const char* names[] = {"libnccl.so.2", "libnccl.so"};
-    for (const char* nm : names) { nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (nccl.lib) break; }
-    if (!nccl.lib) throw Error(std::string("cannot load NCCL: ") + dlerror());
-    nccl.getUniqueId = (fnGetUniqueId)dlsym(nccl.lib, "ncclGetUniqueId");
-    nccl.commInitRank = (fnCommInitRank)dlsym(nccl.lib, "ncclCommInitRank");
-    nccl.allReduce = (fnAllReduce)dlsym(nccl.lib, "ncclAllReduce");
-    nccl.groupStart = (fnGroup)dlsym(nccl.lib, "ncclGroupStart");
-    nccl.groupEnd = (fnGroup)dlsym(nccl.lib, "ncclGroupEnd");
-    nccl.errString = (fnErr)dlsym(nccl.lib, "ncclGetErrorString");
-    if (!nccl.getUniqueId || !nccl.commInitRank || !nccl.allReduce || !nccl.groupStart || !nccl.groupEnd) throw Error("NCCL symbols missing");
-}
-#define SKG_NCCL(call) do { int rc__ = (call); if (rc__ != 0) throw skg::Error(std::string(#call) + ": " + (nccl.errString ? nccl.errString(rc__) : "NCCL error")); } while (0)
-
 }   // namespace skg
-
-using namespace skg;
-extern "C"
-{
-int skg_comm_unique_id(void* out)
-{
-    try { loadNccl(); ncclUniqueId id; SKG_NCCL(nccl.getUniqueId(&id)); memcpy(out, &id, 128); return 0; }
-    catch (std::exception& ex) { setLastError(ex.what()); return 1; }
-}
-int skg_comm_init(skg_engine* eh, int rank, int nranks, const void* uid)
-{
-    try
-    {
-        Engine& e = *reinterpret_cast<Engine*>(eh);
-        SKG_CUDA(cudaSetDevice(e.device));
-        loadNccl();
-        ncclUniqueId id; memcpy(&id, uid, 128);
-        ncclComm_t comm; SKG_NCCL(nccl.commInitRank(&comm, nranks, id, rank));
-        e.nccl = comm; e.rank = rank; e.nranks = nranks;
-        return 0;
-    }
-    catch (std::exception& ex) { setLastError(ex.what()); return 1; }
-}
-// replaces Instrument::sumResults (Instrument.cpp:57-65) and PanDustSystem::sumResults (PanDustSystem.cpp:394-404):
-// one grouped in-place ncclAllReduce(double, sum) over Labs and every detector array
-int skg_allreduce_results(skg_engine* eh)
-{
-    try
-    {
-        Engine& e = *reinterpret_cast<Engine*>(eh);
-        SKG_CUDA(cudaSetDevice(e.device));
-        if (!e.nccl || e.nranks <= 1) return 0;
-        const int ncclDouble = 8, ncclSum = 0;       // nccl.h: ncclFloat64 = 8, ncclSum = 0
-        ncclComm_t comm = (ncclComm_t)e.nccl;
-        SKG_NCCL(nccl.groupStart());
-        if (e.labs.p && e.labsCount) SKG_NCCL(nccl.allReduce(e.labs.p, e.labs.p, (size_t)e.labsCount, ncclDouble, ncclSum, comm, e.stream));
-        for (const InstrDev& d : e.instr)
-        {
-            if (d.frame) SKG_NCCL(nccl.allReduce(d.frame, d.frame, (size_t)d.Nxp * d.Nyp * e.med.Nlambda, ncclDouble, ncclSum, comm, e.stream));
-            if (d.sed) SKG_NCCL(nccl.allReduce(d.sed, d.sed, (size_t)e.med.Nlambda, ncclDouble, ncclSum, comm, e.stream));
-        }
-        SKG_NCCL(nccl.groupEnd());
-        e.sync();
-        return 0;
-    }
-    catch (std::exception& ex) { setLastError(ex.what()); return 1; }
-}
-}
