@@ -84,104 +84,120 @@ __device__ __forceinline__ int cartWhichCell(const CartGrid& g, double x, double
     return k + g.Nz * j + g.Nz * g.Ny * i;
 }
 
-template<class Sink>
-__device__ void walkCart(const CartGrid& g, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+// One crossing at a time: CartesianDustGrid::path (CartesianDustGrid.cpp:136-283) as a state machine, so that a
+// warp can refill finished lanes with new rays instead of waiting for its longest path.
+struct CartWalker
 {
-    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
-    const double* xv = g.xv; const double* yv = g.yv; const double* zv = g.zv;
-    const int Nx = g.Nx, Ny = g.Ny, Nz = g.Nz;
-    const double xmin = g.ext[0], xmax = g.ext[1], ymin = g.ext[2], ymax = g.ext[3], zmin = g.ext[4], zmax = g.ext[5];
-    Entry en; en.n = 0;
-    double ds;
+    double x, y, z, kx, ky, kz;
+    int i, j, k, m;
+    bool alive;
 
-    // CartesianDustGrid.cpp:151-222
-    if (x < xmin)
+    // entry part, :151-230.  Returns false when the ray misses the grid (the reference clears the path);
+    // otherwise `en` holds the up to three "outside" segments (m = -1) that precede the first cell.
+    __device__ __forceinline__ bool start(const CartGrid& g, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
     {
-        if (kx <= 0.0) return;
-        ds = (xmin - x) / kx; en.ds[en.n++] = ds;
-        x = xmin + 1e-8 * (xv[1] - xv[0]); y += ky * ds; z += kz * ds;
+        alive = false; en.n = 0;
+        x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
+        if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
+        const double* xv = g.xv; const double* yv = g.yv; const double* zv = g.zv;
+        const int Nx = g.Nx, Ny = g.Ny, Nz = g.Nz;
+        const double xmin = g.ext[0], xmax = g.ext[1], ymin = g.ext[2], ymax = g.ext[3], zmin = g.ext[4], zmax = g.ext[5];
+        double ds;
+        if (x < xmin)
+        {
+            if (kx <= 0.0) return false;
+            ds = (xmin - x) / kx; en.ds[en.n++] = ds;
+            x = xmin + 1e-8 * (xv[1] - xv[0]); y += ky * ds; z += kz * ds;
+        }
+        else if (x > xmax)
+        {
+            if (kx >= 0.0) return false;
+            ds = (xmax - x) / kx; en.ds[en.n++] = ds;
+            x = xmax - 1e-8 * (xv[Nx] - xv[Nx - 1]); y += ky * ds; z += kz * ds;
+        }
+        if (y < ymin)
+        {
+            if (ky <= 0.0) return false;
+            ds = (ymin - y) / ky; en.ds[en.n++] = ds;
+            x += kx * ds; y = ymin + 1e-8 * (yv[1] - yv[0]); z += kz * ds;
+        }
+        else if (y > ymax)
+        {
+            if (ky >= 0.0) return false;
+            ds = (ymax - y) / ky; en.ds[en.n++] = ds;
+            x += kx * ds; y = ymax - 1e-8 * (yv[Ny] - yv[Ny - 1]); z += kz * ds;
+        }
+        if (z < zmin)
+        {
+            if (kz <= 0.0) return false;
+            ds = (zmin - z) / kz; en.ds[en.n++] = ds;
+            x += kx * ds; y += ky * ds; z = zmin + 1e-8 * (zv[1] - zv[0]);
+        }
+        else if (z > zmax)
+        {
+            if (kz >= 0.0) return false;
+            ds = (zmax - z) / kz; en.ds[en.n++] = ds;
+            x += kx * ds; y += ky * ds; z = zmax - 1e-8 * (zv[Nz] - zv[Nz - 1]);
+        }
+        if (x < xmin || x > xmax || y < ymin || y > ymax || z < zmin || z > zmax) return false;     // :224
+        i = locateClip(xv, x, Nx + 1);
+        j = locateClip(yv, y, Ny + 1);
+        k = locateClip(zv, z, Nz + 1);
+        m = k + Nz * j + Nz * Ny * i;
+        alive = true;
+        return true;
     }
-    else if (x > xmax)
-    {
-        if (kx >= 0.0) return;
-        ds = (xmax - x) / kx; en.ds[en.n++] = ds;
-        x = xmax - 1e-8 * (xv[Nx] - xv[Nx - 1]); y += ky * ds; z += kz * ds;
-    }
-    if (y < ymin)
-    {
-        if (ky <= 0.0) return;
-        ds = (ymin - y) / ky; en.ds[en.n++] = ds;
-        x += kx * ds; y = ymin + 1e-8 * (yv[1] - yv[0]); z += kz * ds;
-    }
-    else if (y > ymax)
-    {
-        if (ky >= 0.0) return;
-        ds = (ymax - y) / ky; en.ds[en.n++] = ds;
-        x += kx * ds; y = ymax - 1e-8 * (yv[Ny] - yv[Ny - 1]); z += kz * ds;
-    }
-    if (z < zmin)
-    {
-        if (kz <= 0.0) return;
-        ds = (zmin - z) / kz; en.ds[en.n++] = ds;
-        x += kx * ds; y += ky * ds; z = zmin + 1e-8 * (zv[1] - zv[0]);
-    }
-    else if (z > zmax)
-    {
-        if (kz >= 0.0) return;
-        ds = (zmax - z) / kz; en.ds[en.n++] = ds;
-        x += kx * ds; y += ky * ds; z = zmax - 1e-8 * (zv[Nz] - zv[Nz - 1]);
-    }
-    // :224
-    if (x < xmin || x > xmax || y < ymin || y > ymax || z < zmin || z > zmax) return;
-    if (!flushEntry(en, sink)) return;
 
-    // :228-230
-    int i = locateClip(xv, x, Nx + 1);
-    int j = locateClip(yv, y, Ny + 1);
-    int k = locateClip(zv, z, Nz + 1);
-
-    // direction-dependent constants hoisted out of the loop (pure selections, no arithmetic change)
-    const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
-    const bool ax = fabs(kx) > 1e-15, ay = fabs(ky) > 1e-15, az = fabs(kz) > 1e-15;
-    const int di = nx ? -1 : 1, dj = ny ? -1 : 1, dk = nz ? -1 : 1;
-    const int ox = nx ? 0 : 1, oy = ny ? 0 : 1, oz = nz ? 0 : 1;
-    const int NyNz = Ny * Nz;
-    int m = k + Nz * j + NyNz * i;
-
-    // :234-282
-    while (true)
+    // one pass of the loop :234-282.  Returns true when segment (mseg, ds) is to be added (addSegment drops ds <= 0).
+    __device__ __forceinline__ bool step(const CartGrid& g, int& mseg, double& ds)
     {
-        double xE = xv[i + ox];
-        double yE = yv[j + oy];
-        double zE = zv[k + oz];
-        double dsx = ax ? (xE - x) / kx : SKG_DBL_MAX;
-        double dsy = ay ? (yE - y) / ky : SKG_DBL_MAX;
-        double dsz = az ? (zE - z) / kz : SKG_DBL_MAX;
+        const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
+        const double xE = g.xv[i + (nx ? 0 : 1)];
+        const double yE = g.yv[j + (ny ? 0 : 1)];
+        const double zE = g.zv[k + (nz ? 0 : 1)];
+        const double dsx = (fabs(kx) > 1e-15) ? (xE - x) / kx : SKG_DBL_MAX;
+        const double dsy = (fabs(ky) > 1e-15) ? (yE - y) / ky : SKG_DBL_MAX;
+        const double dsz = (fabs(kz) > 1e-15) ? (zE - z) / kz : SKG_DBL_MAX;
+        mseg = m;
         if (dsx <= dsy && dsx <= dsz)
         {
             ds = dsx;
-            if (ds > 0) { if (!sink.add(m, ds)) return; }
-            i += di; m += di * NyNz;
-            if (i >= Nx || i < 0) return;
+            const int di = nx ? -1 : 1;
+            i += di; m += di * g.Ny * g.Nz;
+            if (i >= g.Nx || i < 0) alive = false;
             x = xE; y += ky * ds; z += kz * ds;
         }
         else if (dsy < dsx && dsy <= dsz)
         {
             ds = dsy;
-            if (ds > 0) { if (!sink.add(m, ds)) return; }
-            j += dj; m += dj * Nz;
-            if (j >= Ny || j < 0) return;
+            const int dj = ny ? -1 : 1;
+            j += dj; m += dj * g.Nz;
+            if (j >= g.Ny || j < 0) alive = false;
             x += kx * ds; y = yE; z += kz * ds;
         }
         else if (dsz < dsx && dsz < dsy)
         {
             ds = dsz;
-            if (ds > 0) { if (!sink.add(m, ds)) return; }
+            const int dk = nz ? -1 : 1;
             k += dk; m += dk;
-            if (k >= Nz || k < 0) return;
+            if (k >= g.Nz || k < 0) alive = false;
             x += kx * ds; y += ky * ds; z = zE;
         }
-        else return;    // unreachable for finite input (the reference would spin forever)
+        else { alive = false; return false; }   // unreachable for finite input (the reference would spin forever)
+        return ds > 0;
+    }
+};
+
+template<class Sink>
+__device__ void walkCart(const CartGrid& g, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    CartWalker w; Entry en;
+    if (!w.start(g, x, y, z, kx, ky, kz, en)) return;
+    if (!flushEntry(en, sink)) return;
+    while (w.alive)
+    {
+        int m; double ds;
+        if (w.step(g, m, ds)) { if (!sink.add(m, ds)) return; }
     }
 }
 

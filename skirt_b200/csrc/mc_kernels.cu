@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <vector>
 #include "mc_device.cuh"
+#include "wavefront.cuh"
 
 namespace skg
 {
@@ -116,36 +117,35 @@ __device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, doub
     return i + I.Nxp * j;
 }
 
-template<int KIND>
-__global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
-                                                 const int* __restrict__ aliveList, int nAlive)
+// One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
+template<int KIND> struct PeelJob
 {
-    extern __shared__ double smem[];
-    CartGrid cart = G.cart;
-    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    const GridSetMC& G; const CartGrid& cart; const McDev& P; const int* aliveList;
+    double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
+    double Lw, tau; KappaRho kr; int ell, grp;
     unsigned long long nSeg = 0, nPaths = 0, nDet = 0;
-    const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
-    const PacketPool& q = P.pool;
-    const long long total = (long long)nAlive * P.Ngroups;
-    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x)
-    {
-        const int slot = aliveList[t / P.Ngroups];
-        const ObsGroup& grp = P.groups[t % P.Ngroups];
-        double L = q.L[slot];
-        if (!(L > 0)) continue;                                 // MonteCarloSimulation.cpp:281
-        const double x = q.x[slot], y = q.y[slot], z = q.z[slot];
-        const int ell = q.ell[slot];
+    __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, const int* l_) : G(G_), cart(c_), P(P_), aliveList(l_) {}
 
+    __device__ __forceinline__ int begin(int item)
+    {
+        const PacketPool& q = P.pool;
+        const int slot = aliveList[item / P.Ngroups];
+        grp = item % P.Ngroups;
+        const ObsGroup& g = P.groups[grp];
+        double L = q.L[slot];
+        if (!(L > 0)) return 0;                                 // MonteCarloSimulation.cpp:281
+        rx = q.x[slot]; ry = q.y[slot]; rz = q.z[slot];
+        ell = q.ell[slot];
         // which instruments of this direction record the packet?  FrameInstrument ignores packets that map outside
         // its frame before any optical depth is computed (FrameInstrument.cpp:36); SED/Simple always need tau
         bool need = false;
-        for (int c = 0; c < grp.count; c++)
+        for (int c = 0; c < g.count; c++)
         {
-            const InstrDev& I = P.instr[grp.first + c];
-            if (I.kind != SKG_INSTR_FRAME || pixelOnDetector(I, x, y, z) >= 0) { need = true; break; }
+            const InstrDev& I = P.instr[g.first + c];
+            if (I.kind != SKG_INSTR_FRAME || pixelOnDetector(I, rx, ry, rz) >= 0) { need = true; break; }
         }
-        if (!need) continue;
-
+        if (!need) return 0;
+        const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
         if (!q.fresh[slot])
         {
             // ---- peeloffscattering, MonteCarloSimulation.cpp:319-363: weight by the phase function towards the observer ----
@@ -154,178 +154,280 @@ __global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSet
             if (Ncomp == 1) wv[0] = 1.0;
             else
             {
-                int mcell = whichCellMC<KIND>(G, cart, x, y, z);
-                if (mcell == -1) continue;
+                int mcell = whichCellMC<KIND>(G, cart, rx, ry, rz);
+                if (mcell == -1) return 0;
                 double sum = 0;
                 for (int c = 0; c < Ncomp && c < 8; c++)
                 { wv[c] = __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c); sum += wv[c]; }
-                if (sum <= 0) continue;
+                if (sum <= 0) return 0;
                 for (int c = 0; c < Ncomp && c < 8; c++) wv[c] /= sum;
             }
-            double cosalpha = kx * grp.kx + ky * grp.ky + kz * grp.kz;          // Direction::dot
+            double cosalpha = kx * g.kx + ky * g.ky + kz * g.kz;            // Direction::dot
             double w = 0;
             for (int c = 0; c < Ncomp && c < 8; c++)
             {
                 // DustMix::phaseFunctionValue (HG), DustMix.cpp:665-668
-                double g = __ldg(P.med.g + (size_t)c * Nlambda + ell);
-                double tt = 1.0 + g * g - 2 * g * cosalpha;
-                w += wv[c] * ((1.0 - g) * (1.0 + g) / sqrt(tt * tt * tt));
+                double gg = __ldg(P.med.g + (size_t)c * Nlambda + ell);
+                double tt = 1.0 + gg * gg - 2 * gg * cosalpha;
+                w += wv[c] * ((1.0 - gg) * (1.0 + gg) / sqrt(tt * tt * tt));
             }
             L = L * w;                                              // launchScatteringPeelOff, PhotonPackage.cpp:51-62
         }
-
-        // Instrument::opticalDepth (Instrument.cpp:69-72) once per direction; 0 without dust
-        TauSink sink;
-        sink.kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
-        sink.distance = SKG_DBL_MAX;
-        if (P.med.rho) { walkMC<KIND>(G, cart, ctr, x, y, z, grp.kx, grp.ky, grp.kz, sink); nSeg += sink.n; nPaths++; }
-        const double Lextf = L * exp(-sink.tau);
-        for (int c = 0; c < grp.count; c++)
+        Lw = L; tau = 0;
+        dx = g.kx; dy = g.ky; dz = g.kz;
+        kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
+        if (!P.med.rho) return 2;                                   // Instrument::opticalDepth: 0 without dust
+        nPaths++;
+        return 1;
+    }
+    __device__ __forceinline__ bool outside(double) { nSeg++; return true; }
+    __device__ __forceinline__ bool segment(int m, double ds) { nSeg++; tau += kr(m) * ds; return true; }
+    __device__ __forceinline__ void finish()
+    {
+        const ObsGroup& g = P.groups[grp];
+        const double Lextf = Lw * exp(-tau);
+        for (int c = 0; c < g.count; c++)
         {
-            const InstrDev& I = P.instr[grp.first + c];
+            const InstrDev& I = P.instr[g.first + c];
             // SEDInstrument::detect SEDInstrument.cpp:32-42, FrameInstrument::detect FrameInstrument.cpp:32-47, SimpleInstrument.cpp:33-49
             if (I.kind != SKG_INSTR_FRAME) { warpAggregatedAdd(I.sed + ell, Lextf); nDet++; }
             if (I.kind != SKG_INSTR_SED)
             {
-                int l = pixelOnDetector(I, x, y, z);
+                int l = pixelOnDetector(I, rx, ry, rz);
                 if (l >= 0) { warpAggregatedAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
             }
         }
     }
-    flushStats(ctr, nSeg, nPaths, 0, 0, 0, nDet);
+    __device__ __forceinline__ void collective(bool) {}
+};
+
+template<int KIND>
+__global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+                                                 const int* __restrict__ aliveList, int nAlive, int* work)
+{
+    extern __shared__ double smem[];
+    CartGrid cart = G.cart;
+    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    PeelJob<KIND> job(G, cart, P, aliveList);
+    runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work);
+    flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
 }
 
-// ---- scatter (old packets) + escape/absorption + termination + interaction sampling ---------------------------------
+// scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
+template<int KIND> struct AbsorbJob
+{
+    const GridSetMC& G; const CartGrid& cart; const McDev& P; const int* aliveList;
+    int* survivors; int* freeList; int* counts;
+    double rx, ry, rz, dx, dy, dz;
+    // AbsorbSink state (see mc_device.cuh): one expm1 per segment, E = exp(-tau) carried multiplicatively
+    KappaRho kr; double L, albedo, tau, E, Lsca; double* labs;
+    int slot, ell, nscatt; unsigned rngCtr; bool survive;
+    unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
+    __device__ AbsorbJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, const int* l_, int* s_, int* f_, int* c2_)
+        : G(G_), cart(c_), P(P_), aliveList(l_), survivors(s_), freeList(f_), counts(c2_) {}
+
+    __device__ __forceinline__ int begin(int item)
+    {
+        const PacketPool& q = P.pool;
+        slot = aliveList[item];
+        survive = false;
+        L = q.L[slot];
+        if (!(L > 0) || !P.med.rho) return 2;       // nothing to propagate: the slot is recycled in finish()/collective()
+        const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
+        ell = q.ell[slot];
+        rx = q.x[slot]; ry = q.y[slot]; rz = q.z[slot];
+        dx = q.kx[slot]; dy = q.ky[slot]; dz = q.kz[slot];
+        nscatt = q.nscatt[slot];
+        rngCtr = q.rngCtr[slot];
+        if (!q.fresh[slot])
+        {
+            // ---- simulatescattering, MonteCarloSimulation.cpp:541-549 ----
+            Philox rng; rng.init(P.seed, q.id[slot]); rng.c2 = rngCtr;
+            int hmix = 0;
+            if (Ncomp > 1)
+            {
+                // DustSystem::randomMixForPosition, DustSystem.cpp:879-893
+                int mcell = whichCellMC<KIND>(G, cart, rx, ry, rz);
+                if (mcell >= 0)
+                {
+                    double Xv[9]; Xv[0] = 0;
+                    for (int c = 0; c < Ncomp && c < 8; c++)
+                        Xv[c + 1] = Xv[c] + __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c);
+                    double tot = Xv[Ncomp];
+                    for (int c = 0; c <= Ncomp; c++) Xv[c] /= tot;
+                    hmix = locateClip(Xv, rng.uniform(), Ncomp + 1);
+                }
+            }
+            // DustMix::scatteringDirectionAndPolarization (HG branch), DustMix.cpp:607-614
+            double g = __ldg(P.med.g + (size_t)hmix * Nlambda + ell);
+            if (fabs(g) < 1e-6) randomDirection(rng, dx, dy, dz);
+            else
+            {
+                double f = ((1.0 - g) * (1.0 + g)) / (1.0 - g + 2.0 * g * rng.uniform());
+                double costheta = (1.0 + g * g - f * f) / (2.0 * g);
+                scatterDirection(rng, costheta, dx, dy, dz);
+            }
+            nscatt++; nScatt++;
+            q.kx[slot] = dx; q.ky[slot] = dy; q.kz[slot] = dz; q.nscatt[slot] = nscatt;
+            rngCtr = rng.c2;
+        }
+        // ---- fillOpticalDepth + simulateescapeandabsorption, :286-288, :438-515 ----
+        kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
+        labs = P.labs ? P.labs + (size_t)ell * P.med.Ncells : nullptr;
+        double kext0 = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
+        albedo = kext0 > 0 ? ksca0 / kext0 : 0.0;          // DustMix::albedo(ell) (DustMix.cpp:55-90)
+        tau = 0; E = 1.0; Lsca = 0;
+        nPaths++;
+        return 1;
+    }
+    __device__ __forceinline__ bool outside(double) { nSeg++; return true; }   // rho(-1,h) = 0: dtau = 0, nothing absorbed
+    __device__ __forceinline__ bool segment(int m, double ds)
+    {
+        nSeg++;
+        const int Ncomp = P.med.Ncomp;
+        if (Ncomp == 1)
+        {
+            double dtau = kr(m) * ds;
+            if (labs)
+            {
+                double x = expm1(-dtau);
+                atomicAdd(labs + m, (1.0 - albedo) * (L * E * (-x)));
+                E += E * x;
+                nAbs++;
+            }
+            tau += dtau;
+        }
+        else
+        {
+            double ksca = 0.0, kext = 0.0, krr = 0.0;
+            for (int h = 0; h < Ncomp; h++)
+            {
+                double rho = __ldg(P.med.rho + (size_t)m * Ncomp + h);
+                ksca += rho * __ldg(P.med.ksca + (size_t)h * P.med.Nlambda + ell);
+                double ke = __ldg(P.med.kext + (size_t)h * P.med.Nlambda + ell);
+                kext += rho * ke;
+                krr += ke * rho;
+            }
+            double alb = (kext > 0.0) ? ksca / kext : 0.0;
+            double dtau = krr * ds;
+            double x = expm1(-dtau);
+            double Lintm = L * E * (-x);
+            E += E * x;
+            Lsca += alb * Lintm;
+            if (labs) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
+            tau += dtau;
+        }
+        return true;
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (!(L > 0) || !P.med.rho) return;
+        const PacketPool& q = P.pool;
+        const double taupath = tau;
+        if (P.med.Ncomp == 1) L = L * albedo * (-expm1(-taupath));
+        else L = Lsca;
+        // ---- termination test, :289 ----
+        const double Lthreshold = __ldg(P.Ltot + ell) / P.Lscale / P.minWeightReduction;
+        survive = !(L <= 0 || (L <= Lthreshold && nscatt >= P.minfs));
+        if (survive)
+        {
+            // ---- simulatepropagation, :519-533: sample the interaction optical depth, weight for the bias ----
+            Philox rng; rng.init(P.seed, q.id[slot]); rng.c2 = rngCtr;
+            double t = 0;
+            if (taupath != 0.0)
+            {
+                if (P.xi == 0.0) t = exponCutoff(rng, taupath);
+                else
+                {
+                    double X = rng.uniform();
+                    t = (X < P.xi) ? rng.uniform() * taupath : exponCutoff(rng, taupath);
+                    double p = -exp(-t) / expm1(-taupath);
+                    double qq = (1.0 - P.xi) * p + P.xi / taupath;
+                    L = L * (p / qq);
+                }
+            }
+            q.target[slot] = t;
+            rngCtr = rng.c2;
+        }
+        q.L[slot] = L; q.rngCtr[slot] = rngCtr;
+    }
+    __device__ __forceinline__ void collective(bool fin)
+    {
+        warpAppend(fin && survive, slot, survivors, counts);
+        warpAppend(fin && !survive, slot, freeList, counts + 1);
+    }
+};
+
 template<int KIND>
 __global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                    const int* __restrict__ aliveList, int nAlive, int* __restrict__ survivors,
-                                                   int* __restrict__ freeList, int* __restrict__ counts)
+                                                   int* __restrict__ freeList, int* __restrict__ counts, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
-    const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
-    const PacketPool& q = P.pool;
-    const int nIter = (nAlive + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);
-    for (int it = 0; it < nIter; it++)
-    {
-        const int idx = it * gridDim.x * blockDim.x + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = idx < nAlive;
-        int slot = 0; bool survive = false;
-        if (valid)
-        {
-            slot = aliveList[idx];
-            double L = q.L[slot];
-            if (L > 0 && P.med.rho)
-            {
-                const int ell = q.ell[slot];
-                const double x = q.x[slot], y = q.y[slot], z = q.z[slot];
-                double kx = q.kx[slot], ky = q.ky[slot], kz = q.kz[slot];
-                int nscatt = q.nscatt[slot];
-                Philox rng; rng.init(P.seed, q.id[slot]); rng.c2 = q.rngCtr[slot];
-                if (!q.fresh[slot])
-                {
-                    // ---- simulatescattering, MonteCarloSimulation.cpp:541-549 ----
-                    int hmix = 0;
-                    if (Ncomp > 1)
-                    {
-                        // DustSystem::randomMixForPosition, DustSystem.cpp:879-893
-                        int mcell = whichCellMC<KIND>(G, cart, x, y, z);
-                        if (mcell >= 0)
-                        {
-                            double Xv[9]; Xv[0] = 0;
-                            for (int c = 0; c < Ncomp && c < 8; c++)
-                                Xv[c + 1] = Xv[c] + __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c);
-                            double tot = Xv[Ncomp];
-                            for (int c = 0; c <= Ncomp; c++) Xv[c] /= tot;
-                            hmix = locateClip(Xv, rng.uniform(), Ncomp + 1);
-                        }
-                    }
-                    // DustMix::scatteringDirectionAndPolarization (HG branch), DustMix.cpp:607-614
-                    double g = __ldg(P.med.g + (size_t)hmix * Nlambda + ell);
-                    if (fabs(g) < 1e-6) randomDirection(rng, kx, ky, kz);
-                    else
-                    {
-                        double f = ((1.0 - g) * (1.0 + g)) / (1.0 - g + 2.0 * g * rng.uniform());
-                        double costheta = (1.0 + g * g - f * f) / (2.0 * g);
-                        scatterDirection(rng, costheta, kx, ky, kz);
-                    }
-                    nscatt++; nScatt++;
-                    q.kx[slot] = kx; q.ky[slot] = ky; q.kz[slot] = kz; q.nscatt[slot] = nscatt;
-                }
-
-                // ---- fillOpticalDepth + simulateescapeandabsorption, :286-288, :438-515 ----
-                AbsorbSink ab;
-                ab.kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
-                ab.med = &P.med; ab.ell = ell; ab.L = L;
-                ab.labs = P.labs ? P.labs + (size_t)ell * P.med.Ncells : nullptr;
-                double kext0 = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
-                ab.albedo = kext0 > 0 ? ksca0 / kext0 : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
-                walkMC<KIND>(G, cart, ctr, x, y, z, kx, ky, kz, ab);
-                nSeg += ab.n; nPaths++; nAbs += ab.nAbs;
-                const double taupath = ab.tau;
-                if (Ncomp == 1) L = L * ab.albedo * (-expm1(-taupath));
-                else L = ab.Lsca;
-
-                // ---- termination test, :289 ----
-                const double Lthreshold = __ldg(P.Ltot + ell) / P.Lscale / P.minWeightReduction;
-                survive = !(L <= 0 || (L <= Lthreshold && nscatt >= P.minfs));
-                if (survive)
-                {
-                    // ---- simulatepropagation, :519-533: sample the interaction optical depth, weight for the bias ----
-                    double tau = 0;
-                    if (taupath != 0.0)
-                    {
-                        if (P.xi == 0.0) tau = exponCutoff(rng, taupath);
-                        else
-                        {
-                            double X = rng.uniform();
-                            tau = (X < P.xi) ? rng.uniform() * taupath : exponCutoff(rng, taupath);
-                            double p = -exp(-tau) / expm1(-taupath);
-                            double qq = (1.0 - P.xi) * p + P.xi / taupath;
-                            L = L * (p / qq);
-                        }
-                    }
-                    q.target[slot] = tau;
-                }
-                q.L[slot] = L; q.rngCtr[slot] = rng.c2;
-            }
-        }
-        warpAppend(valid && survive, slot, survivors, counts);
-        warpAppend(valid && !survive, slot, freeList, counts + 1);
-    }
-    flushStats(ctr, nSeg, nPaths, nScatt, 0, nAbs, 0);
+    AbsorbJob<KIND> job(G, cart, P, aliveList, survivors, freeList, counts);
+    runJobs<KIND>(G, cart, ctr, job, nAlive, work);
+    flushStats(ctr, job.nSeg, job.nPaths, job.nScatt, 0, job.nAbs, 0);
 }
 
-// ---- propagate to the interaction point ---------------------------------------------------------------------
+// re-walk to the sampled interaction optical depth and move the packet there:
+// DustGridPath::pathlength (DustGridPath.cpp:162-173) evaluated on the fly + PhotonPackage::propagate (PhotonPackage.cpp:93-96)
+template<int KIND> struct PropagateJob
+{
+    const McDev& P; const int* list;
+    double rx, ry, rz, dx, dy, dz;
+    KappaRho kr; double target, sPrev, tauPrev, result; bool found; int slot;
+    unsigned long long nSeg = 0, nPaths = 0;
+    __device__ PropagateJob(const McDev& P_, const int* l_) : P(P_), list(l_) {}
+    __device__ __forceinline__ int begin(int item)
+    {
+        const PacketPool& q = P.pool;
+        slot = list[item];
+        q.fresh[slot] = 0;
+        target = q.target[slot];
+        if (!(target > 0)) return 0;
+        const int ell = q.ell[slot];
+        rx = q.x[slot]; ry = q.y[slot]; rz = q.z[slot]; dx = q.kx[slot]; dy = q.ky[slot]; dz = q.kz[slot];
+        kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
+        sPrev = 0; tauPrev = 0; result = 0; found = false;
+        nPaths++;
+        return 1;
+    }
+    __device__ __forceinline__ bool outside(double ds) { nSeg++; sPrev += ds; return true; }
+    __device__ __forceinline__ bool segment(int m, double ds)
+    {
+        nSeg++;
+        double sNew = sPrev + ds;
+        double tauNew = tauPrev + kr(m) * ds;
+        if (target < tauNew)
+        {
+            result = sPrev + ((target - tauPrev) / (tauNew - tauPrev)) * (sNew - sPrev);     // NR::interpolate_linlin
+            found = true;
+            return false;
+        }
+        sPrev = sNew; tauPrev = tauNew;
+        return true;
+    }
+    __device__ __forceinline__ void finish()
+    {
+        const PacketPool& q = P.pool;
+        const double s = found ? result : sPrev;
+        q.x[slot] = rx + s * dx; q.y[slot] = ry + s * dy; q.z[slot] = rz + s * dz;
+    }
+    __device__ __forceinline__ void collective(bool) {}
+};
+
 template<int KIND>
 __global__ void __launch_bounds__(128) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
-                                                      const int* __restrict__ survivors, int nSurv)
+                                                      const int* __restrict__ survivors, int nSurv, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    unsigned long long nSeg = 0, nPaths = 0;
-    const PacketPool& q = P.pool;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nSurv; idx += gridDim.x * blockDim.x)
-    {
-        const int slot = survivors[idx];
-        const double tau = q.target[slot];
-        q.fresh[slot] = 0;
-        if (!(tau > 0)) continue;
-        const int ell = q.ell[slot];
-        double x = q.x[slot], y = q.y[slot], z = q.z[slot];
-        const double kx = q.kx[slot], ky = q.ky[slot], kz = q.kz[slot];
-        PropagateSink pr;
-        pr.kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
-        pr.target = tau;
-        walkMC<KIND>(G, cart, ctr, x, y, z, kx, ky, kz, pr);
-        nSeg += pr.n; nPaths++;
-        const double s = pr.s();
-        q.x[slot] = x + s * kx; q.y[slot] = y + s * ky; q.z[slot] = z + s * kz;      // PhotonPackage::propagate, PhotonPackage.cpp:93-96
-    }
-    flushStats(ctr, nSeg, nPaths, 0, 0, 0, 0);
+    PropagateJob<KIND> job(P, survivors);
+    runJobs<KIND>(G, cart, ctr, job, nSurv, work);
+    flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
 }
 
 __global__ void iotaKernel(int* list, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) list[i] = i; }
@@ -497,7 +599,7 @@ template<int KIND>
 static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned long long total, int pool, size_t smem, bool cartSmem)
 {
     int* listA = e.mcLists.as<int>(); int* listB = listA + pool; int* freeList = listB + pool;
-    int* counts = e.mcCounts.as<int>();
+    int* counts = e.mcCounts.as<int>();      // [0] survivors, [1] freed slots, [2..4] work counters of the three traversal stages
     auto blocksFor = [&](long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, (long long)e.smCount * 16)); };
     iotaKernel<<<blocksFor(pool), 128, 0, e.stream>>>(freeList, pool); e.launches++;
     unsigned long long launched = 0;
@@ -512,15 +614,15 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
             nAlive += nLaunch; launched += nLaunch;
         }
         if (nAlive == 0) break;
+        SKG_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), e.stream));
         if (P.Ngroups > 0)
-        { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive); e.launches++; }
-        SKG_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), e.stream));
-        absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, listB, freeList, counts); e.launches++;
+        { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, counts + 2); e.launches++; }
+        absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, listB, freeList, counts, counts + 3); e.launches++;
         SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
         SKG_CUDA(cudaGetLastError());
         e.sync();
         int nSurv = hostCounts[0]; nFree = hostCounts[1];
-        if (nSurv > 0) { propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listB, nSurv); e.launches++; }
+        if (nSurv > 0) { propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listB, nSurv, counts + 4); e.launches++; }
         std::swap(listA, listB);
         nAlive = nSurv;
     }
@@ -587,7 +689,7 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
         int* ip = reinterpret_cast<int*>(q.id + (size_t)pool);
         q.ell = ip; q.nscatt = ip + (size_t)pool; q.rngCtr = reinterpret_cast<unsigned*>(ip + 2 * (size_t)pool); q.fresh = ip + 3 * (size_t)pool;
         e.mcLists.ensure(sizeof(int) * 3 * (size_t)pool);
-        e.mcCounts.ensure(sizeof(int) * 2);
+        e.mcCounts.ensure(sizeof(int) * 8);
         if (!e.mcHostCounts) SKG_CUDA(cudaMallocHost(&e.mcHostCounts, 2 * sizeof(int)));
 
         size_t smem = 0; bool cartSmem = false;

@@ -1,0 +1,128 @@
+// Warp-level scheduling of ray jobs.
+//
+// Every traversal kernel of the engine (batched DustGrid::path(), optical depth, and the peel-off / absorb /
+// propagate stages of the photon shooter) is "for each item: set up a ray, walk it through the grid feeding
+// segments to a sink, finish".  Path lengths vary from 1 to a few hundred crossings, so a plain
+// one-item-per-thread loop leaves most lanes of a warp idle while the longest path finishes.  runJobs() keeps
+// the lanes busy instead: a lane whose path has ended parks until REFILL lanes of its warp are parked, then the
+// parked lanes finish their items together and draw new ones from a global work counter.  The crossing step
+// itself is executed by all walking lanes in lock step.
+//
+// A Job provides (per lane, state in registers):
+//   int  begin(int item)         set rx..dz for the item; 0 = nothing to do, 1 = walk the ray, 2 = no walk but finish()
+//   bool outside(double ds)      segment outside the grid (m = -1); false stops the walk
+//   bool segment(int m, double ds)
+//   void finish()                called once per item that returned 1 or 2 from begin()
+//   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
+#pragma once
+#include "geom.cuh"
+
+namespace skg
+{
+
+#ifndef SKG_REFILL
+#define SKG_REFILL 8
+#endif
+
+template<class Job>
+__device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int n, int* workCounter)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    int state = 0;              // 0 idle, 1 walking, 2 walk ended (finish pending)
+    bool more = true;
+    CartWalker w; w.alive = false;
+    while (true)
+    {
+        unsigned walking = __ballot_sync(FULL, state == 1);
+        if (__popc(~walking) >= SKG_REFILL || walking == 0)
+        {
+            if (state == 2) job.finish();
+            job.collective(state == 2);
+            if (state == 2) state = 0;
+            if (more)
+            {
+                const unsigned idle = __ballot_sync(FULL, state == 0);
+                int base = 0;
+                if (lane == 0) base = atomicAdd(workCounter, __popc(idle));
+                base = __shfl_sync(FULL, base, 0);
+                if (base >= n) more = false;
+                else if (state == 0)
+                {
+                    const int idx = base + __popc(idle & ((1u << lane) - 1));
+                    if (idx < n)
+                    {
+                        const int b = job.begin(idx);
+                        if (b == 1)
+                        {
+                            Entry en;
+                            state = 2;
+                            if (w.start(cart, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, en))
+                            {
+                                bool cont = true;
+                                for (int q = 0; q < en.n && cont; q++) if (en.ds[q] > 0) cont = job.outside(en.ds[q]);
+                                if (cont) state = 1;
+                            }
+                        }
+                        else if (b == 2) state = 2;
+                    }
+                }
+            }
+            walking = __ballot_sync(FULL, state == 1);
+            if (walking == 0)
+            {
+                if (!more && __ballot_sync(FULL, state == 2) == 0) break;
+                continue;
+            }
+        }
+        if (state == 1)
+        {
+            int m; double ds;
+            const bool seg = w.step(cart, m, ds);
+            const bool cont = seg ? job.segment(m, ds) : true;
+            if (!cont || !w.alive) state = 2;
+        }
+    }
+}
+
+// adapter that lets the loop walkers of geom.cuh drive a Job (grids without a stepping walker yet)
+template<class Job> struct JobSink
+{
+    Job& job;
+    __device__ __forceinline__ bool add(int m, double ds) { return m < 0 ? job.outside(ds) : job.segment(m, ds); }
+};
+
+template<int KIND, class Job, class Grids>
+__device__ __forceinline__ void runJobsLoop(const Grids& G, Counters* ctr, Job& job, int n)
+{
+    const int stride = gridDim.x * blockDim.x;
+    const int nIter = (n + stride - 1) / stride;
+    for (int it = 0; it < nIter; it++)
+    {
+        const int idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        int b = 0;
+        if (idx < n)
+        {
+            b = job.begin(idx);
+            if (b == 1)
+            {
+                JobSink<Job> sink{job};
+                if (KIND == GRID_TREE) walkTree(G.tree, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
+                else if (KIND == GRID_AMESH) walkAMesh(G.amesh, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
+                else if (KIND == GRID_VORO) walkVoro(G.voro, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
+                else walkCart(G.cart, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
+            }
+            if (b >= 1) job.finish();
+        }
+        job.collective(b >= 1);
+    }
+}
+
+template<int KIND, class Job, class Grids>
+__device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Counters* ctr, Job& job, int n, int* workCounter)
+{
+    if (KIND == GRID_CART) runJobsCart(cart, job, n, workCounter);
+    else runJobsLoop<KIND>(G, ctr, job, n);
+}
+
+}   // namespace skg
