@@ -62,7 +62,7 @@ struct Engine
     Medium med{};
     DevBuf rho, kext, ksca, gasym;
     DevBuf counters;                    // Counters
-    DevBuf scratchR, scratchK, scratchEll, scratchDist, scratchCounts, scratchOffsets, scratchCub, scratchOut[5], scratchTau, scratchM;
+    DevBuf scratchR, scratchK, scratchEll, scratchDist, scratchCounts, scratchOffsets, scratchCub, scratchOut[5], scratchTau, scratchM, scratchWork;
 
     // Monte Carlo state
     int Nsources = 0; int NlambdaSrc = 0; double emissionBias = 0.5;

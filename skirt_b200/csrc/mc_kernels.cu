@@ -199,6 +199,7 @@ template<int KIND> struct PeelJob
         }
     }
     __device__ __forceinline__ void collective(bool) {}
+    __device__ __forceinline__ void periodic() {}
 };
 
 template<int KIND>
@@ -356,6 +357,7 @@ template<int KIND> struct AbsorbJob
         warpAppend(fin && survive, slot, survivors, counts);
         warpAppend(fin && !survive, slot, freeList, counts + 1);
     }
+    __device__ __forceinline__ void periodic() {}
 };
 
 template<int KIND>
@@ -416,6 +418,7 @@ template<int KIND> struct PropagateJob
         q.x[slot] = rx + s * dx; q.y[slot] = ry + s * dy; q.z[slot] = rz + s * dz;
     }
     __device__ __forceinline__ void collective(bool) {}
+    __device__ __forceinline__ void periodic() {}
 };
 
 template<int KIND>

@@ -14,6 +14,7 @@
 //   bool segment(int m, double ds)
 //   void finish()                called once per item that returned 1 or 2 from begin()
 //   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
+//   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps (stepping walkers only)
 #pragma once
 #include "geom.cuh"
 
@@ -23,6 +24,7 @@ namespace skg
 #ifndef SKG_REFILL
 #define SKG_REFILL 8
 #endif
+#define SKG_PERIOD 4
 
 template<class Job>
 __device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int n, int* workCounter)
@@ -32,6 +34,7 @@ __device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int 
     int state = 0;              // 0 idle, 1 walking, 2 walk ended (finish pending)
     bool more = true;
     CartWalker w; w.alive = false;
+    int sincePeriodic = 0;
     while (true)
     {
         unsigned walking = __ballot_sync(FULL, state == 1);
@@ -82,6 +85,7 @@ __device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int 
             const bool cont = seg ? job.segment(m, ds) : true;
             if (!cont || !w.alive) state = 2;
         }
+        if (++sincePeriodic == SKG_PERIOD) { job.periodic(); sincePeriodic = 0; }
     }
 }
 
