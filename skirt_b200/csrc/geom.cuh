@@ -94,7 +94,7 @@ struct CartWalker
 
     // entry part, :151-230.  Returns false when the ray misses the grid (the reference clears the path);
     // otherwise `en` holds the up to three "outside" segments (m = -1) that precede the first cell.
-    __device__ __forceinline__ bool start(const CartGrid& g, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
+    __device__ __forceinline__ bool start(const CartGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
     {
         alive = false; en.n = 0;
         x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
@@ -149,7 +149,7 @@ struct CartWalker
     }
 
     // one pass of the loop :234-282.  Returns true when segment (mseg, ds) is to be added (addSegment drops ds <= 0).
-    __device__ __forceinline__ bool step(const CartGrid& g, int& mseg, double& ds)
+    __device__ __forceinline__ bool step(const CartGrid& g, Counters*, int& mseg, double& ds)
     {
         const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
         const double xE = g.xv[i + (nx ? 0 : 1)];
@@ -191,13 +191,14 @@ struct CartWalker
 template<class Sink>
 __device__ void walkCart(const CartGrid& g, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
 {
+    Counters* ctr = nullptr;
     CartWalker w; Entry en;
-    if (!w.start(g, x, y, z, kx, ky, kz, en)) return;
+    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
     if (!flushEntry(en, sink)) return;
     while (w.alive)
     {
         int m; double ds;
-        if (w.step(g, m, ds)) { if (!sink.add(m, ds)) return; }
+        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
     }
 }
 
@@ -289,41 +290,49 @@ __device__ __forceinline__ double nextAfterAlong(double v, double k)
     return nextafter(v, (k < 0.0) ? -SKG_DBL_MAX : SKG_DBL_MAX);
 }
 
-template<class Sink>
-__device__ void walkTree(const TreeGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+// TreeDustGrid::path (TreeDustGrid.cpp:390-662) one crossing at a time
+struct TreeWalker
 {
-    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
-    Entry en;
-    if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return;
-    int node = treeWhichNode(g, x, y, z);
-    if (node < 0) return;
-    if (!flushEntry(en, sink)) return;
-    const double eps = g.eps;
-    const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
-    const bool ax = fabs(kx) > 1e-15, ay = fabs(ky) > 1e-15, az = fabs(kz) > 1e-15;
+    double x, y, z, kx, ky, kz;
+    int node;
+    bool alive;
 
-    if (g.search != 2)
+    __device__ __forceinline__ bool start(const TreeGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
     {
-        // TopDown (TreeDustGrid.cpp:412-456) and Neighbor (:460-521)
-        while (node >= 0)
+        alive = false; en.n = 0;
+        x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
+        if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
+        if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
+        node = treeWhichNode(g, x, y, z);
+        if (node < 0) return false;
+        alive = true;
+        return true;
+    }
+
+    __device__ __forceinline__ bool step(const TreeGrid& g, Counters* ctr, int& mseg, double& ds)
+    {
+        const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
+        const double* b = g.box + 6 * (size_t)node;
+        const double xnext = nx ? b[0] : b[3];
+        const double ynext = ny ? b[1] : b[4];
+        const double znext = nz ? b[2] : b[5];
+        const double dsx = (fabs(kx) > 1e-15) ? (xnext - x) / kx : SKG_DBL_MAX;
+        const double dsy = (fabs(ky) > 1e-15) ? (ynext - y) / ky : SKG_DBL_MAX;
+        const double dsz = (fabs(kz) > 1e-15) ? (znext - z) / kz : SKG_DBL_MAX;
+        mseg = __ldg(g.cell + node);
+        if (g.search != 2)
         {
-            const double* b = g.box + 6 * (size_t)node;
-            double xnext = nx ? b[0] : b[3];
-            double ynext = ny ? b[1] : b[4];
-            double znext = nz ? b[2] : b[5];
-            double dsx = ax ? (xnext - x) / kx : SKG_DBL_MAX;
-            double dsy = ay ? (ynext - y) / ky : SKG_DBL_MAX;
-            double dsz = az ? (znext - z) / kz : SKG_DBL_MAX;
-            double ds; int wall;
+            // TopDown (TreeDustGrid.cpp:412-456) and Neighbor (:460-521)
+            const double eps = g.eps;
+            int wall;
             if (dsx <= dsy && dsx <= dsz) { ds = dsx; wall = nx ? 0 : 1; }
             else if (dsy <= dsx && dsy <= dsz) { ds = dsy; wall = ny ? 2 : 3; }
             else { ds = dsz; wall = nz ? 4 : 5; }
-            if (ds > 0) { if (!sink.add(__ldg(g.cell + node), ds)) return; }
             x += (ds + eps) * kx;
             y += (ds + eps) * ky;
             z += (ds + eps) * kz;
 
-            int oldnode = node;
+            const int oldnode = node;
             if (g.search == 1)
             {
                 // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first neighbour whose closed box contains r
@@ -343,90 +352,95 @@ __device__ void walkTree(const TreeGrid& g, Counters* ctr, double x, double y, d
                 atomicAdd(&ctr->stuckEscaped, 1ull);
                 x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
                 node = treeWhichNode(g, x, y, z);
-                if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); break; }
+                if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
             }
+            if (node < 0) alive = false;
+            return ds > 0;
         }
-    }
-    else
-    {
+
         // Bookkeeping (octree only), TreeDustGrid.cpp:527-659
         int l = node;
-        while (true)
+        if (dsx <= dsy && dsx <= dsz)
         {
-            const double* b = g.box + 6 * (size_t)l;
-            double xnext = nx ? b[0] : b[3];
-            double ynext = ny ? b[1] : b[4];
-            double znext = nz ? b[2] : b[5];
-            double dsx = ax ? (xnext - x) / kx : SKG_DBL_MAX;
-            double dsy = ay ? (ynext - y) / ky : SKG_DBL_MAX;
-            double dsz = az ? (znext - z) / kz : SKG_DBL_MAX;
-            if (dsx <= dsy && dsx <= dsz)
+            ds = dsx;
+            x = xnext; y += ky * dsx; z += kz * dsx;
+            while (true)
             {
-                if (dsx > 0) { if (!sink.add(__ldg(g.cell + l), dsx)) return; }
-                x = xnext; y += ky * dsx; z += kz * dsx;
-                while (true)
-                {
-                    int oct = ((l - 1) % 8) + 1;
-                    bool place = nx ? (oct % 2 == 1) : (oct % 2 == 0);
-                    if (!place) break;
-                    l = __ldg(g.parent + l);
-                    if (l == 0) return;
-                }
-                l += nx ? -1 : 1;
-                while (__ldg(g.cell + l) == -1)
-                {
-                    int c0 = __ldg(g.child0 + l);
-                    const double* cb = g.box + 6 * (size_t)c0;
-                    double yM = cb[4], zM = cb[5];
-                    if (nx) l = (y <= yM) ? ((z <= zM) ? c0 + 1 : c0 + 5) : ((z <= zM) ? c0 + 3 : c0 + 7);
-                    else    l = (y <= yM) ? ((z <= zM) ? c0 + 0 : c0 + 4) : ((z <= zM) ? c0 + 2 : c0 + 6);
-                }
+                int oct = ((l - 1) % 8) + 1;
+                bool place = nx ? (oct % 2 == 1) : (oct % 2 == 0);
+                if (!place) break;
+                l = __ldg(g.parent + l);
+                if (l == 0) { alive = false; return ds > 0; }
             }
-            else if (dsy < dsx && dsy <= dsz)
+            l += nx ? -1 : 1;
+            while (__ldg(g.cell + l) == -1)
             {
-                if (dsy > 0) { if (!sink.add(__ldg(g.cell + l), dsy)) return; }
-                x += kx * dsy; y = ynext; z += kz * dsy;
-                while (true)
-                {
-                    bool place = ny ? ((l - 1) % 4 < 2) : ((l - 1) % 4 > 1);
-                    if (!place) break;
-                    l = __ldg(g.parent + l);
-                    if (l == 0) return;
-                }
-                l += ny ? -2 : 2;
-                while (__ldg(g.cell + l) == -1)
-                {
-                    int c0 = __ldg(g.child0 + l);
-                    const double* cb = g.box + 6 * (size_t)c0;
-                    double xM = cb[3], zM = cb[5];
-                    if (ny) l = (x <= xM) ? ((z <= zM) ? c0 + 2 : c0 + 6) : ((z <= zM) ? c0 + 3 : c0 + 7);
-                    else    l = (x <= xM) ? ((z <= zM) ? c0 + 0 : c0 + 4) : ((z <= zM) ? c0 + 1 : c0 + 5);
-                }
+                int c0 = __ldg(g.child0 + l);
+                const double* cb = g.box + 6 * (size_t)c0;
+                double yM = cb[4], zM = cb[5];
+                if (nx) l = (y <= yM) ? ((z <= zM) ? c0 + 1 : c0 + 5) : ((z <= zM) ? c0 + 3 : c0 + 7);
+                else    l = (y <= yM) ? ((z <= zM) ? c0 + 0 : c0 + 4) : ((z <= zM) ? c0 + 2 : c0 + 6);
             }
-            else if (dsz < dsx && dsz < dsy)
-            {
-                if (dsz > 0) { if (!sink.add(__ldg(g.cell + l), dsz)) return; }
-                x += kx * dsz; y += ky * dsz; z = znext;
-                while (true)
-                {
-                    int oct = ((l - 1) % 8) + 1;
-                    bool place = nz ? (oct < 5) : (oct > 4);
-                    if (!place) break;
-                    l = __ldg(g.parent + l);
-                    if (l == 0) return;
-                }
-                l += nz ? -4 : 4;
-                while (__ldg(g.cell + l) == -1)
-                {
-                    int c0 = __ldg(g.child0 + l);
-                    const double* cb = g.box + 6 * (size_t)c0;
-                    double xM = cb[3], yM = cb[4];
-                    if (nz) l = (x <= xM) ? ((y <= yM) ? c0 + 4 : c0 + 6) : ((y <= yM) ? c0 + 5 : c0 + 7);
-                    else    l = (x <= xM) ? ((y <= yM) ? c0 + 0 : c0 + 2) : ((y <= yM) ? c0 + 1 : c0 + 3);
-                }
-            }
-            else return;
         }
+        else if (dsy < dsx && dsy <= dsz)
+        {
+            ds = dsy;
+            x += kx * dsy; y = ynext; z += kz * dsy;
+            while (true)
+            {
+                bool place = ny ? ((l - 1) % 4 < 2) : ((l - 1) % 4 > 1);
+                if (!place) break;
+                l = __ldg(g.parent + l);
+                if (l == 0) { alive = false; return ds > 0; }
+            }
+            l += ny ? -2 : 2;
+            while (__ldg(g.cell + l) == -1)
+            {
+                int c0 = __ldg(g.child0 + l);
+                const double* cb = g.box + 6 * (size_t)c0;
+                double xM = cb[3], zM = cb[5];
+                if (ny) l = (x <= xM) ? ((z <= zM) ? c0 + 2 : c0 + 6) : ((z <= zM) ? c0 + 3 : c0 + 7);
+                else    l = (x <= xM) ? ((z <= zM) ? c0 + 0 : c0 + 4) : ((z <= zM) ? c0 + 1 : c0 + 5);
+            }
+        }
+        else if (dsz < dsx && dsz < dsy)
+        {
+            ds = dsz;
+            x += kx * dsz; y += ky * dsz; z = znext;
+            while (true)
+            {
+                int oct = ((l - 1) % 8) + 1;
+                bool place = nz ? (oct < 5) : (oct > 4);
+                if (!place) break;
+                l = __ldg(g.parent + l);
+                if (l == 0) { alive = false; return ds > 0; }
+            }
+            l += nz ? -4 : 4;
+            while (__ldg(g.cell + l) == -1)
+            {
+                int c0 = __ldg(g.child0 + l);
+                const double* cb = g.box + 6 * (size_t)c0;
+                double xM = cb[3], yM = cb[4];
+                if (nz) l = (x <= xM) ? ((y <= yM) ? c0 + 4 : c0 + 6) : ((y <= yM) ? c0 + 5 : c0 + 7);
+                else    l = (x <= xM) ? ((y <= yM) ? c0 + 0 : c0 + 2) : ((y <= yM) ? c0 + 1 : c0 + 3);
+            }
+        }
+        else { alive = false; return false; }
+        node = l;
+        return ds > 0;
+    }
+};
+
+template<class Sink>
+__device__ void walkTree(const TreeGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    TreeWalker w; Entry en;
+    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
+    if (!flushEntry(en, sink)) return;
+    while (w.alive)
+    {
+        int m; double ds;
+        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
     }
 }
 
@@ -471,53 +485,75 @@ __device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, doub
     return node;
 }
 
-template<class Sink>
-__device__ void walkAMesh(const AMeshGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+// AdaptiveMesh::path (AdaptiveMesh.cpp:297-367) one crossing at a time
+struct AMeshWalker
 {
-    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
-    Entry en;
-    if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return;
-    int node = ameshWhichNode(g, x, y, z);
-    if (node < 0) { if (node == -2) atomicAdd(&ctr->errors, 1ull); return; }
-    if (!flushEntry(en, sink)) return;
-    const double eps = g.eps;
-    const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
-    const bool ax = fabs(kx) > 1e-15, ay = fabs(ky) > 1e-15, az = fabs(kz) > 1e-15;
+    double x, y, z, kx, ky, kz;
+    int node;
+    bool alive;
 
-    // AdaptiveMesh.cpp:312-366
-    while (node >= 0)
+    __device__ __forceinline__ bool start(const AMeshGrid& g, Counters* ctr, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
     {
+        alive = false; en.n = 0;
+        x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
+        if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
+        if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
+        node = ameshWhichNode(g, x, y, z);
+        if (node < 0) { if (node == -2) atomicAdd(&ctr->errors, 1ull); return false; }
+        alive = true;
+        return true;
+    }
+
+    __device__ __forceinline__ bool step(const AMeshGrid& g, Counters* ctr, int& mseg, double& ds)
+    {
+        const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
+        const double eps = g.eps;
         const double* b = g.box + 6 * (size_t)node;
-        double xnext = nx ? b[0] : b[3];
-        double ynext = ny ? b[1] : b[4];
-        double znext = nz ? b[2] : b[5];
-        double dsx = ax ? (xnext - x) / kx : SKG_DBL_MAX;
-        double dsy = ay ? (ynext - y) / ky : SKG_DBL_MAX;
-        double dsz = az ? (znext - z) / kz : SKG_DBL_MAX;
-        double ds; int wall;
+        const double xnext = nx ? b[0] : b[3];
+        const double ynext = ny ? b[1] : b[4];
+        const double znext = nz ? b[2] : b[5];
+        const double dsx = (fabs(kx) > 1e-15) ? (xnext - x) / kx : SKG_DBL_MAX;
+        const double dsy = (fabs(ky) > 1e-15) ? (ynext - y) / ky : SKG_DBL_MAX;
+        const double dsz = (fabs(kz) > 1e-15) ? (znext - z) / kz : SKG_DBL_MAX;
+        int wall;
         if (dsx <= dsy && dsx <= dsz) { ds = dsx; wall = nx ? 0 : 1; }
         else if (dsy <= dsx && dsy <= dsz) { ds = dsy; wall = ny ? 2 : 3; }
         else { ds = dsz; wall = nz ? 4 : 5; }
-        if (ds > 0) { if (!sink.add(__ldg(g.cell + node), ds)) return; }
+        mseg = __ldg(g.cell + node);
         // r += (ds+eps)*k   (Vec operator*(double,Vec), Vec.hpp)
         x += (ds + eps) * kx;
         y += (ds + eps) * ky;
         z += (ds + eps) * kz;
 
-        int oldnode = node;
+        const int oldnode = node;
         int cand = __ldg(g.wallNbr + 6 * (size_t)node + wall);
         if (cand >= 0 && boxContains(g.box + 6 * (size_t)cand, x, y, z)) node = cand;
         else node = ameshWhichNode(g, x, y, z);
-        if (node == -2) { atomicAdd(&ctr->errors, 1ull); return; }
+        if (node == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
 
         if (node == oldnode)
         {
             atomicAdd(&ctr->stuckEscaped, 1ull);
             x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
             node = ameshWhichNode(g, x, y, z);
-            if (node == -2) { atomicAdd(&ctr->errors, 1ull); return; }
-            if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); break; }
+            if (node == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
+            if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
         }
+        if (node < 0) alive = false;
+        return ds > 0;
+    }
+};
+
+template<class Sink>
+__device__ void walkAMesh(const AMeshGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    AMeshWalker w; Entry en;
+    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
+    if (!flushEntry(en, sink)) return;
+    while (w.alive)
+    {
+        int m; double ds;
+        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
     }
 }
 
@@ -641,27 +677,35 @@ __device__ __forceinline__ int voroCellIndex(const VoroGrid& g, double x, double
     return m;
 }
 
-template<class Sink>
-__device__ void walkVoro(const VoroGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+// VoronoiMesh::path (VoronoiMesh.cpp:749-844) one crossing at a time
+struct VoroWalker
 {
-    if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return;
-    Entry en;
-    if (!moveInside(g.ext, g.eps, x, y, z, kx, ky, kz, en)) return;
-    int mr = voroCellIndex(g, x, y, z);
-    if (mr < 0) return;
-    if (!flushEntry(en, sink)) return;
-    const double eps = g.eps;
-    long guard = 0;
+    double x, y, z, kx, ky, kz;
+    int mr;
+    int guard;
+    bool alive;
 
-    // VoronoiMesh.cpp:764-843
-    while (mr >= 0)
+    __device__ __forceinline__ bool start(const VoroGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
     {
+        alive = false; en.n = 0; guard = 0;
+        x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
+        if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
+        if (!moveInside(g.ext, g.eps, x, y, z, kx, ky, kz, en)) return false;
+        mr = voroCellIndex(g, x, y, z);
+        if (mr < 0) return false;
+        alive = true;
+        return true;
+    }
+
+    __device__ __forceinline__ bool step(const VoroGrid& g, Counters* ctr, int& mseg, double& ds)
+    {
+        const double eps = g.eps;
         const double* pr = g.particles + 3 * (size_t)mr;
-        double prx = pr[0], pry = pr[1], prz = pr[2];
+        const double prx = pr[0], pry = pr[1], prz = pr[2];
         double sq = SKG_DBL_MAX;
         const int NO_INDEX = -99;
         int mq = NO_INDEX;
-        int beg = __ldg(g.nbrStart + mr), end = __ldg(g.nbrStart + mr + 1);
+        const int beg = __ldg(g.nbrStart + mr), end = __ldg(g.nbrStart + mr + 1);
         for (int q = beg; q < end; q++)
         {
             int mi = __ldg(g.nbrIds + q);
@@ -688,7 +732,7 @@ __device__ void walkVoro(const VoroGrid& g, Counters* ctr, double x, double y, d
                 case -4: si = (g.ext[4] - y) / ky; break;
                 case -5: si = (g.ext[2] - z) / kz; break;
                 case -6: si = (g.ext[5] - z) / kz; break;
-                default: atomicAdd(&ctr->errors, 1ull); return;
+                default: atomicAdd(&ctr->errors, 1ull); alive = false; return false;
                 }
             }
             if (si > 0 && si < sq) { sq = si; mq = mi; }
@@ -698,14 +742,28 @@ __device__ void walkVoro(const VoroGrid& g, Counters* ctr, double x, double y, d
             // r += bfk*_eps  (Vec operator*(Vec,double))
             x += kx * eps; y += ky * eps; z += kz * eps;
             mr = voroCellIndex(g, x, y, z);
-            if (++guard > 1000000) { atomicAdd(&ctr->errors, 1ull); return; }
+            if (++guard > 1000000) { atomicAdd(&ctr->errors, 1ull); mr = -1; }
+            if (mr < 0) alive = false;
+            return false;
         }
-        else
-        {
-            if (!sink.add(mr, sq)) return;      // sq > 0 by construction
-            x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
-            mr = mq;
-        }
+        mseg = mr; ds = sq;                     // sq > 0 by construction
+        x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
+        mr = mq;
+        if (mr < 0) alive = false;
+        return true;
+    }
+};
+
+template<class Sink>
+__device__ void walkVoro(const VoroGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
+{
+    VoroWalker w; Entry en;
+    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
+    if (!flushEntry(en, sink)) return;
+    while (w.alive)
+    {
+        int m; double ds;
+        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
     }
 }
 

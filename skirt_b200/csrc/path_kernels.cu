@@ -50,33 +50,6 @@ struct CountJob : RayJobBase
     __device__ __forceinline__ void finish() { counts[item] = n; }
 };
 
-// second pass: Segment{m, ds, s, dtau, tau} records = DustGridPath::addSegment (DustGridPath.cpp:46-53, running
-// length s) + DustGridPath::fillOpticalDepth (DustGridPath.hpp:117-129, running tau)
-struct RecordJob : RayJobBase
-{
-    const int64_t* offsets; const int* ell; int ellStride; Medium med;
-    int* m; double* ds; double* s; double* dtau; double* tau;
-    KappaRho kr; int64_t o; double sacc, tacc;
-    __device__ __forceinline__ int begin(int i)
-    {
-        loadRay(i);
-        o = offsets[i]; sacc = 0; tacc = 0;
-        int l = ell ? ell[(size_t)i * ellStride] : 0;
-        kr = KappaRho{med.rho, med.kext + l, med.Ncomp, med.Nlambda};
-        return 1;
-    }
-    __device__ __forceinline__ bool put(int mm, double d, double dt)
-    {
-        sacc += d; tacc += dt;
-        m[o] = mm; ds[o] = d; s[o] = sacc; dtau[o] = dt; tau[o] = tacc;
-        o++;
-        return true;
-    }
-    __device__ __forceinline__ bool outside(double d) { return put(-1, d, ell ? 0.0 * d : 0.0); }     // kapparho(-1) = 0
-    __device__ __forceinline__ bool segment(int mm, double d) { return put(mm, d, ell ? kr(mm) * d : 0.0); }
-    __device__ __forceinline__ void finish() {}
-};
-
 // DustSystem::opticaldepth(pp, distance), DustSystem.cpp:984-1000 + DustGridPath::opticalDepth, DustGridPath.hpp:97-108:
 // the overshooting segment is counted in full, then the walk stops
 struct TauJob : RayJobBase
@@ -107,7 +80,9 @@ __global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ G
     runJobs<KIND>(G, cart, ctr, job, n, work);
 }
 
-// The same records through a per-warp shared-memory stage (stepping walkers only).  A crossing step only parks
+// second pass: Segment{m, ds, s, dtau, tau} records = DustGridPath::addSegment (DustGridPath.cpp:46-53, running
+// length s) + DustGridPath::fillOpticalDepth (DustGridPath.hpp:117-129, running tau), through a per-warp
+// shared-memory stage.  A crossing step only parks
 // (m, ds) in a ring of 8 entries per lane; every SKG_PERIOD steps each lane (1) gathers rho for all its parked
 // entries at once (several independent loads in flight instead of one per step) and extends its running s and tau
 // in path order, and (2) the warp writes the finished entries out together: 8 lanes per source lane, only whole
@@ -224,21 +199,12 @@ __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ Gr
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
-    if (KIND == GRID_CART)
-    {
-        cart = stageCart(G.cart, smem, cartSmem);
-        size_t skip = cartSmem ? (size_t)(G.cart.Nx + G.cart.Ny + G.cart.Nz + 3) : 0;
-        RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
-        job.m = m; job.ds = ds; job.s = s; job.dtau = dtau; job.tau = tau;
-        job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarp());
-        runJobsCart(cart, job, n, work);
-    }
-    else
-    {
-        RecordJob job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
-        job.m = m; job.ds = ds; job.s = s; job.dtau = dtau; job.tau = tau;
-        runJobsLoop<KIND>(G, ctr, job, n);
-    }
+    if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
+    size_t skip = (KIND == GRID_CART && cartSmem) ? (size_t)(G.cart.Nx + G.cart.Ny + G.cart.Nz + 3) : 0;
+    RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
+    job.m = m; job.ds = ds; job.s = s; job.dtau = dtau; job.tau = tau;
+    job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarp());
+    runJobs<KIND>(G, cart, ctr, job, n, work);
 }
 
 template<int KIND>
@@ -314,11 +280,15 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
     if (n <= 0) return;
     if (d_ell && !e.med.rho) throw Error("skg_path_fill with wavelength indices needs skg_medium first");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
-    if (e.gridKind == GRID_CART)
+    c.smem += 4 * RecordJobStaged::bytesPerWarp();
+    static bool attr = false;
+    if (!attr)
     {
-        c.smem += 4 * RecordJobStaged::bytesPerWarp();
-        static bool attr = false;
-        if (!attr) { SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+        SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_AMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_VORO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        attr = true;
     }
     SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, (int)n, d_r, d_k, d_ell, ellStride,
                                                                                 d_offsets, d_m, d_ds, d_s, d_dtau, d_tau, c.work)));

@@ -6,7 +6,7 @@
 // one-item-per-thread loop leaves most lanes of a warp idle while the longest path finishes.  runJobs() keeps
 // the lanes busy instead: a lane whose path has ended parks until REFILL lanes of its warp are parked, then the
 // parked lanes finish their items together and draw new ones from a global work counter.  The crossing step
-// itself is executed by all walking lanes in lock step.
+// itself is executed by all walking lanes in lock step.  Every grid type provides a stepping walker (geom.cuh).
 //
 // A Job provides (per lane, state in registers):
 //   int  begin(int item)         set rx..dz for the item; 0 = nothing to do, 1 = walk the ray, 2 = no walk but finish()
@@ -14,7 +14,7 @@
 //   bool segment(int m, double ds)
 //   void finish()                called once per item that returned 1 or 2 from begin()
 //   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
-//   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps (stepping walkers only)
+//   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps 
 #pragma once
 #include "geom.cuh"
 
@@ -26,14 +26,14 @@ namespace skg
 #endif
 #define SKG_PERIOD 4
 
-template<class Job>
-__device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int n, int* workCounter)
+template<class Walker, class GridT, class Job>
+__device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Job& job, int n, int* workCounter)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     int state = 0;              // 0 idle, 1 walking, 2 walk ended (finish pending)
     bool more = true;
-    CartWalker w; w.alive = false;
+    Walker w; w.alive = false;
     int sincePeriodic = 0;
     while (true)
     {
@@ -60,7 +60,7 @@ __device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int 
                         {
                             Entry en;
                             state = 2;
-                            if (w.start(cart, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, en))
+                            if (w.start(grid, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, en))
                             {
                                 bool cont = true;
                                 for (int q = 0; q < en.n && cont; q++) if (en.ds[q] > 0) cont = job.outside(en.ds[q]);
@@ -81,7 +81,7 @@ __device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int 
         if (state == 1)
         {
             int m; double ds;
-            const bool seg = w.step(cart, m, ds);
+            const bool seg = w.step(grid, ctr, m, ds);
             const bool cont = seg ? job.segment(m, ds) : true;
             if (!cont || !w.alive) state = 2;
         }
@@ -89,44 +89,13 @@ __device__ __forceinline__ void runJobsCart(const CartGrid& cart, Job& job, int 
     }
 }
 
-// adapter that lets the loop walkers of geom.cuh drive a Job (grids without a stepping walker yet)
-template<class Job> struct JobSink
-{
-    Job& job;
-    __device__ __forceinline__ bool add(int m, double ds) { return m < 0 ? job.outside(ds) : job.segment(m, ds); }
-};
-
-template<int KIND, class Job, class Grids>
-__device__ __forceinline__ void runJobsLoop(const Grids& G, Counters* ctr, Job& job, int n)
-{
-    const int stride = gridDim.x * blockDim.x;
-    const int nIter = (n + stride - 1) / stride;
-    for (int it = 0; it < nIter; it++)
-    {
-        const int idx = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        int b = 0;
-        if (idx < n)
-        {
-            b = job.begin(idx);
-            if (b == 1)
-            {
-                JobSink<Job> sink{job};
-                if (KIND == GRID_TREE) walkTree(G.tree, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
-                else if (KIND == GRID_AMESH) walkAMesh(G.amesh, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
-                else if (KIND == GRID_VORO) walkVoro(G.voro, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
-                else walkCart(G.cart, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, sink);
-            }
-            if (b >= 1) job.finish();
-        }
-        job.collective(b >= 1);
-    }
-}
-
 template<int KIND, class Job, class Grids>
 __device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Counters* ctr, Job& job, int n, int* workCounter)
 {
-    if (KIND == GRID_CART) runJobsCart(cart, job, n, workCounter);
-    else runJobsLoop<KIND>(G, ctr, job, n);
+    if (KIND == GRID_CART) runJobsStep<CartWalker>(cart, ctr, job, n, workCounter);
+    else if (KIND == GRID_TREE) runJobsStep<TreeWalker>(G.tree, ctr, job, n, workCounter);
+    else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter);
+    else runJobsStep<VoroWalker>(G.voro, ctr, job, n, workCounter);
 }
 
 }   // namespace skg
