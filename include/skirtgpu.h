@@ -149,6 +149,27 @@ typedef struct skg_mc_stats
 } skg_mc_stats;
 int skg_run_stellar(skg_engine* e, const skg_mc_params* p, skg_mc_stats* stats);
 
+/* ---- dust emission phases: PanMonteCarloSimulation::dodustselfabsorptionchunk / dodustemissionchunk
+ *      (PanMonteCarloSimulation.cpp:187-238, 269-342) for all wavelengths at once ------------------------------- */
+enum { SKG_PHASE_STELLAR = 0, SKG_PHASE_DUST_SELFABS = 1, SKG_PHASE_DUST_EMISSION = 2 };
+/* Lcell[ell*Ncells + m] = Labsbol[m] * dustluminosity(m, ell)  (the vector Lv of :193-198 / :275-280 for every ell;
+ * host memory when mem == SKG_HOST, device memory when SKG_DEVICE).  The engine builds the per-wavelength CDFs
+ * (NR::cdf, NR.hpp:388-394), picks the emitting cell (self-absorption: natural distribution, :217-218; emission:
+ * composite biasing with emissionBias, :296-312), draws the position with DustGrid::randomPositionInCell and an
+ * isotropic direction, and runs the packet life cycle:
+ *   SKG_PHASE_DUST_SELFABS   no peel-off; absorbed luminosity is added to the DUST absorption table
+ *                            (PanDustSystem::absorb(..., ynstellar=false), PanDustSystem.cpp:304-316)
+ *   SKG_PHASE_DUST_EMISSION  peel-off of emission and scattering towards every instrument; nothing is absorbed
+ * p->storeAbsorption is ignored; p->packages is the number of packets per wavelength for this engine
+ * (the caller applies the stage factor / emissionBoost, :142, :258). */
+int skg_run_dust(skg_engine* e, const skg_mc_params* p, int phase, double emissionBias, int mem, const double* Lcell,
+                 skg_mc_stats* stats);
+/* PanDustSystem::rebootLabsdust (PanDustSystem.cpp:330-333), the dust absorption table, and
+ * PanDustSystem::Labs(m) (PanDustSystem.cpp:337-348): bolometric absorbed luminosity per cell, stellar + dust */
+int skg_reset_labs_dust(skg_engine* e);
+int skg_fetch_labs_dust(skg_engine* e, double* labs /* [Ncells*Nlambda] */, int add);
+int skg_labs_bolometric(skg_engine* e, double* Labsbol /* [Ncells] */);
+
 /* accumulators (replace LockFree::add targets: Instrument _ftotv/_Ftotv, DustSystem _Labsvv) */
 int skg_reset_results(skg_engine* e);
 /* frame cube [Nxp*Nyp*Nlambda] (index l + ell*Nframep, FrameInstrument.cpp:38-39), sed [Nlambda];
@@ -158,7 +179,7 @@ int skg_fetch_sed(skg_engine* e, int instrument, double* sed, int add);
 int skg_fetch_labs(skg_engine* e, double* labs /* [Ncells*Nlambda] */, int add);
 /* device views of the accumulators, for collectives issued by the host (NCCL through torch.distributed);
  * note that the absorption table is wavelength-major on the device: labs[ell*Ncells + m] */
-int skg_device_accumulators(skg_engine* e, int which /*0 labs, 1.. instruments*/, int part /*0 frame,1 sed*/,
+int skg_device_accumulators(skg_engine* e, int which /*0 labs, -1 dust labs, 1.. instruments*/, int part /*0 frame,1 sed*/,
                             double** d_ptr, int64_t* count);
 
 /* ---- multi-GPU: replaces ProcessManager::sum / sum_all (ProcessManager.cpp:122-140) ------------------- */

@@ -62,6 +62,7 @@
 #include "PanDustSystem.hpp"
 #include "PanMonteCarloSimulation.hpp"
 #include "PanStellarComp.hpp"
+#include "Parallel.hpp"
 #include "ParallelFactory.hpp"
 #include "PhotonPackage.hpp"
 #include "PowMesh.hpp"
@@ -228,7 +229,7 @@ namespace
         std::istringstream all(spec);
         std::string line;
         double packages = 1e6, mwr = 1e4, minscatt = 0, xi = 0.5, ebias = 0.5;
-        int threads = 1, seed = 4357, dustsamples = 100, storeabs = 0;
+        int threads = 1, seed = 4357, dustsamples = 100, storeabs = 0, selfabs = 0;
         std::vector<std::string> lines;
         while (std::getline(all, line)) if (!line.empty() && line[0] != '#') lines.push_back(line);
 
@@ -254,6 +255,7 @@ namespace
             else if (key == "emissionbias") in >> ebias;
             else if (key == "dustsamples") in >> dustsamples;
             else if (key == "storeabs") in >> storeabs;
+            else if (key == "selfabs") in >> selfabs;
             else if (key == "wavelengths")
             {
                 QList<double> lv; double v; while (in >> v) lv << v;
@@ -372,7 +374,7 @@ namespace
                 // storeabs: PanDustSystem::storeabsorptionrates() == dustemission() (PanDustSystem.cpp:290-299), so the
                 // absorption tables only exist with a dust emissivity + library attached
                 if (storeabs) { ds->setDustEmissivity(new GreyBodyDustEmissivity()); ds->setDustLib(new AllCellsDustLib()); }
-                ds->setSelfAbsorption(false); ds->setWriteEmissivity(false); ds->setWriteTemperature(false); ds->setWriteISRF(false);
+                ds->setSelfAbsorption(storeabs && selfabs); ds->setWriteEmissivity(false); ds->setWriteTemperature(false); ds->setWriteISRF(false);
                 S->ds = ds; p->setDustSystem(ds);
             }
         }
@@ -727,6 +729,66 @@ int skr_get_labs(void* h, double* labs)   // [Ncells*Nlambda], stellar absorptio
     int N = S->ds->Ncells(), L = numLambda(S);
     for (int m = 0; m < N; m++) for (int l = 0; l < L; l++) labs[(size_t)m*L+l] = S->ds->Labs(m, l);
     return 0;
+}
+
+// ---- dust emission phases (PanMonteCarloSimulation.cpp:105-342) ---------------------------------------------
+// PanDustSystem::calculatedustemission (sumResults + DustLib::calculate) and the bolometric absorbed luminosities,
+// exactly as rundustselfabsorption :131-136 / rundustemission :250-255 prepare a shooting phase; returns the
+// vectors Lv of dodust*chunk (:193-198, :275-280) for all wavelengths: Lv[ell*Ncells + m]
+int skr_prepare_dust(void* h, int ynstellar, double* Lv)
+{
+    Sim* S = (Sim*)h;
+    return guarded([&]{
+        PanMonteCarloSimulation* p = dynamic_cast<PanMonteCarloSimulation*>(S->mc);
+        if (!p || !p->_pds || !p->_pds->dustemission()) throw std::runtime_error("not a panchromatic simulation with dust emission");
+        p->_pds->calculatedustemission(ynstellar != 0);
+        int N = p->_Ncells, L = numLambda(S);
+        for (int m = 0; m < N; m++) p->_Labsbolv[m] = p->_pds->Labs(m);
+        if (Lv) for (int ell = 0; ell < L; ell++) for (int m = 0; m < N; m++)
+        {
+            double Labsbol = p->_Labsbolv[m];
+            Lv[(size_t)ell*N + m] = Labsbol > 0.0 ? Labsbol * p->_pds->dustluminosity(m, ell) : 0.0;
+        }
+    });
+}
+// one dust self-absorption cycle (selfabs != 0; :139-148) or the dust emission phase (:258-264) with
+// packages*factor packets per wavelength; skr_prepare_dust must have been called
+int skr_run_dust(void* h, int selfabs, double factor, double* seconds)
+{
+    Sim* S = (Sim*)h;
+    return guarded([&]{
+        PanMonteCarloSimulation* p = dynamic_cast<PanMonteCarloSimulation*>(S->mc);
+        if (!p || !p->_pds || !p->_pds->dustemission()) throw std::runtime_error("not a panchromatic simulation with dust emission");
+        auto t0 = std::chrono::steady_clock::now();
+        if (selfabs) p->_pds->rebootLabsdust();
+        p->setChunkParams(p->packages() * factor);
+        p->initprogress(selfabs ? "dust self-absorption cycle" : "dust emission");
+        Parallel* parallel = p->find<ParallelFactory>()->parallel();
+        if (selfabs) parallel->call(p, &PanMonteCarloSimulation::dodustselfabsorptionchunk, p->assigner());
+        else parallel->call(p, &PanMonteCarloSimulation::dodustemissionchunk, p->assigner());
+        *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    });
+}
+int skr_get_labs_dust(void* h, double* labs)   // [Ncells*Nlambda], absorbed dust emission
+{
+    Sim* S = (Sim*)h; PanDustSystem* p = dynamic_cast<PanDustSystem*>(S->ds);
+    if (!p || !p->_haveLabsdust) return 1;
+    int N = p->Ncells(), L = numLambda(S);
+    for (int m = 0; m < N; m++) for (int l = 0; l < L; l++) labs[(size_t)m*L+l] = p->_Labsdustvv(m, l);
+    return 0;
+}
+int skr_get_labs_bol(void* h, double* out)     // PanDustSystem::Labs(m)
+{
+    Sim* S = (Sim*)h; PanDustSystem* p = dynamic_cast<PanDustSystem*>(S->ds);
+    if (!p) return 1;
+    for (int m = 0; m < p->Ncells(); m++) out[m] = p->Labs(m);
+    return 0;
+}
+// DustGrid::randomPositionInCell driven by the simulation's Random (thread 0)
+int skr_random_positions(void* h, int m, long n, double* xyz)
+{
+    Sim* S = (Sim*)h;
+    return guarded([&]{ for (long i = 0; i < n; i++) { Position r = S->grid->randomPositionInCell(m); xyz[3*i] = r.x(); xyz[3*i+1] = r.y(); xyz[3*i+2] = r.z(); } });
 }
 
 // ---- samplers exposed for distribution-level checks ------------------------------------------------

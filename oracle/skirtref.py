@@ -262,6 +262,33 @@ class RefSim:
         self._chk(lib().skr_get_labs(self.h, a.ctypes.data_as(C.c_void_p)))
         return a
 
+    # ---- dust emission phases -------------------------------------------------------------------
+    def prepare_dust(self, ynstellar=True):
+        """calculatedustemission + bolometric absorbed luminosities; returns Lv[Nlambda, Ncells]"""
+        Lv = np.zeros((self.Nlambda, self.Ncells))
+        self._chk(lib().skr_prepare_dust(self.h, int(bool(ynstellar)), Lv.ctypes.data_as(C.c_void_p)))
+        return Lv
+
+    def run_dust(self, selfabs, factor=1.0):
+        sec = C.c_double()
+        self._chk(lib().skr_run_dust(self.h, int(bool(selfabs)), C.c_double(factor), C.byref(sec)))
+        return sec.value
+
+    def labs_dust(self):
+        a = np.zeros((self.Ncells, self.Nlambda))
+        self._chk(lib().skr_get_labs_dust(self.h, a.ctypes.data_as(C.c_void_p)))
+        return a
+
+    def labs_bol(self):
+        a = np.zeros(self.Ncells)
+        self._chk(lib().skr_get_labs_bol(self.h, a.ctypes.data_as(C.c_void_p)))
+        return a
+
+    def random_positions(self, m, n):
+        xyz = np.zeros((n, 3))
+        self._chk(lib().skr_random_positions(self.h, int(m), C.c_long(n), xyz.ctypes.data_as(C.c_void_p)))
+        return xyz
+
     def sample_launch(self, ell, n):
         r = np.zeros((n, 3)); k = np.zeros((n, 3)); Lw = np.zeros(n)
         self._chk(lib().skr_sample_launch(self.h, ell, C.c_long(n), r.ctypes.data_as(C.c_void_p), k.ctypes.data_as(C.c_void_p),

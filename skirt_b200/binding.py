@@ -13,6 +13,7 @@ _lib = None
 SKG_HOST, SKG_DEVICE = 0, 1
 GEOM_EXPDISK, GEOM_SERSIC = 1, 2
 INSTR_FRAME, INSTR_SED, INSTR_SIMPLE = 1, 2, 3
+PHASE_STELLAR, PHASE_DUST_SELFABS, PHASE_DUST_EMISSION = 0, 1, 2
 
 
 class EngineError(RuntimeError):
@@ -272,6 +273,44 @@ class Engine:
         self._chk(self._lib.skg_run_stellar(self.h, C.byref(p), C.byref(st)))
         return dict(packets=st.packets, pathSegments=st.pathSegments, paths=st.paths, scatterings=st.scatterings,
                     kernel_ms=st.kernel_ms, absorbSegments=st.absorbSegments, detections=st.detections)
+
+    def _params(self, packages, total_packages, min_weight_reduction, min_scatt_events, scatt_bias, store_absorption, seed,
+                stream_offset, ell_begin, ell_end, pool_packets):
+        p = SkgMcParams()
+        p.packages = float(packages)
+        p.luminosityScale = float(total_packages if total_packages is not None else packages)
+        p.minWeightReduction = float(min_weight_reduction); p.minScattEvents = float(min_scatt_events)
+        p.scattBias = float(scatt_bias); p.storeAbsorption = int(bool(store_absorption))
+        p.seed = int(seed); p.streamOffset = int(stream_offset); p.poolPackets = int(pool_packets)
+        p.ellBegin = int(ell_begin); p.ellEnd = int(self.Nlambda if ell_end is None else ell_end)
+        return p
+
+    def run_dust(self, phase, Lcell, packages, total_packages=None, emission_bias=0.5, min_weight_reduction=1e4,
+                 min_scatt_events=0.0, scatt_bias=0.5, seed=4357, stream_offset=0, ell_begin=0, ell_end=None, pool_packets=0):
+        """PanMonteCarloSimulation::dodustselfabsorptionchunk / dodustemissionchunk for all wavelengths;
+        Lcell[Nlambda, Ncells] = Labsbol[m] * dustluminosity(m, ell)"""
+        Lc = _f64(Lcell)
+        if Lc.shape != (self.Nlambda, self.Ncells):
+            raise EngineError(f"Lcell must have shape (Nlambda, Ncells) = ({self.Nlambda}, {self.Ncells})")
+        p = self._params(packages, total_packages, min_weight_reduction, min_scatt_events, scatt_bias, False, seed,
+                         stream_offset, ell_begin, ell_end, pool_packets)
+        st = SkgMcStats()
+        self._chk(self._lib.skg_run_dust(self.h, C.byref(p), int(phase), C.c_double(emission_bias), SKG_HOST, _vp(Lc), C.byref(st)))
+        return dict(packets=st.packets, pathSegments=st.pathSegments, paths=st.paths, scatterings=st.scatterings,
+                    kernel_ms=st.kernel_ms, absorbSegments=st.absorbSegments, detections=st.detections)
+
+    def reset_labs_dust(self):
+        self._chk(self._lib.skg_reset_labs_dust(self.h))
+
+    def fetch_labs_dust(self):
+        a = np.zeros((self.Ncells, self.Nlambda))
+        self._chk(self._lib.skg_fetch_labs_dust(self.h, _vp(a), 0))
+        return a
+
+    def labs_bolometric(self):
+        a = np.zeros(self.Ncells)
+        self._chk(self._lib.skg_labs_bolometric(self.h, _vp(a)))
+        return a
 
     def reset_results(self):
         self._chk(self._lib.skg_reset_results(self.h))

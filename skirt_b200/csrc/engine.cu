@@ -153,6 +153,7 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
         e.tree.dir = up(e, dir, N);
         if (search == 1) { e.tree.nbrStart = up(e, nbrStart, 6 * (size_t)N + 1); e.tree.nbrIds = up(e, nbrIds, (size_t)std::max(1, nbrStart[6 * (size_t)N])); }
         else { e.tree.nbrStart = nullptr; e.tree.nbrIds = nullptr; }
+        { std::vector<int> cn(std::max(ncells, 1), 0); for (int l = 0; l < N; l++) if (cell[l] >= 0 && cell[l] < ncells) cn[cell[l]] = l; e.tree.cellNode = up(e, cn.data(), cn.size()); }
         e.tree.N = N; e.tree.kind = kind; e.tree.search = search;
         e.tree.eps = epsFor(box[3] - box[0], box[4] - box[1], box[5] - box[2]);
         e.gridKind = GRID_TREE; e.Ncells = ncells;
@@ -178,6 +179,7 @@ int skg_grid_amesh(skg_engine* eh, int N, const double* box, const int* nxyz, co
         e.freeGrid();
         e.amesh.box = up(e, box, 6 * (size_t)N); e.amesh.nxyz = up(e, nxyz, 3 * (size_t)N); e.amesh.child0 = up(e, child0, N);
         e.amesh.cell = up(e, cell, N); e.amesh.wallNbr = up(e, wallNbr, 6 * (size_t)N);
+        { std::vector<int> cn(std::max(ncells, 1), 0); for (int l = 0; l < N; l++) if (cell[l] >= 0 && cell[l] < ncells) cn[cell[l]] = l; e.amesh.cellNode = up(e, cn.data(), cn.size()); }
         e.amesh.N = N;
         e.amesh.eps = epsFor(box[3] - box[0], box[4] - box[1], box[5] - box[2]);
         e.gridKind = GRID_AMESH; e.Ncells = ncells;
@@ -342,7 +344,15 @@ int skg_instruments(skg_engine* eh, int n, const skg_instrument* instr)
 { return guarded([&]{ mcSetInstruments(E(eh), n, instr); }); }
 int skg_run_stellar(skg_engine* eh, const skg_mc_params* p, skg_mc_stats* stats)
 { return guarded([&]{ if (!p) throw Error("null parameters"); mcRunStellar(E(eh), *p, stats); }); }
+int skg_run_dust(skg_engine* eh, const skg_mc_params* p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats)
+{ return guarded([&]{ if (!p) throw Error("null parameters"); mcRunDust(E(eh), *p, phase, emissionBias, mem, Lcell, stats); }); }
 int skg_reset_results(skg_engine* eh) { return guarded([&]{ mcResetResults(E(eh)); }); }
+int skg_reset_labs_dust(skg_engine* eh)
+{ return guarded([&]{ Engine& e = E(eh); if (e.labsDust.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labsDust.p, 0, sizeof(double) * e.labsCount, e.stream)); e.sync(); }); }
+int skg_fetch_labs_dust(skg_engine* eh, double* labs, int add)
+{ return guarded([&]{ if (!labs) throw Error("null host array"); mcFetchLabs(E(eh), labs, add, 1); }); }
+int skg_labs_bolometric(skg_engine* eh, double* Labsbol)
+{ return guarded([&]{ if (!Labsbol) throw Error("null host array"); mcLabsBolometric(E(eh), Labsbol); }); }
 
 static void fetchArray(Engine& e, const double* d_src, int64_t count, double* host, int add)
 {
@@ -374,7 +384,7 @@ int skg_fetch_labs(skg_engine* eh, double* labs, int add)
     return guarded([&]{
         Engine& e = E(eh);
         if (!labs) throw Error("null host array");
-        mcFetchLabs(e, labs, add);
+        mcFetchLabs(e, labs, add, 0);
     });
 }
 int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr, int64_t* count)
@@ -383,6 +393,7 @@ int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr,
         Engine& e = E(eh);
         if (!d_ptr || !count) throw Error("null output");
         if (which == 0) { *d_ptr = e.labs.as<double>(); *count = e.labsCount; return; }
+        if (which == -1) { *d_ptr = e.labsDust.as<double>(); *count = e.labsDust.p ? e.labsCount : 0; return; }
         int i = which - 1;
         if (i < 0 || i >= (int)e.instr.size()) throw Error("instrument index out of range");
         if (part == 0) { *d_ptr = e.instr[i].frame; *count = e.instr[i].frame ? (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.med.Nlambda : 0; }

@@ -70,6 +70,8 @@ struct Engine
     std::vector<double> lumHost, lumTotHost;
     std::vector<InstrDev> instr; DevBuf instrDev; std::vector<DevBuf*> instrBufs;
     DevBuf labs; int64_t labsCount = 0;    // absorbed luminosity, wavelength-major on the device: labs[ell*Ncells+m]
+    DevBuf labsDust;                        // absorbed dust emission (self-absorption cycles), same layout
+    DevBuf dustLv, dustCdf, dustLtot;       // per-wavelength cell luminosities of a dust phase, their CDFs and totals
     DevBuf labsT;                           // scratch for the (m,ell) row-major copy handed to the host
     DevBuf instrGroupedDev, groupsDev; int Ngroups = 0;    // instruments ordered by line of sight + the groups
     DevBuf mcPool, mcLists, mcCounts, mcEllList; int* mcHostCounts = nullptr;   // packet pool of the wavefront shooter
@@ -98,6 +100,8 @@ void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, co
 void mcSetInstruments(Engine& e, int n, const skg_instrument* instr);
 void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats);
 void mcResetResults(Engine& e);
-void mcFetchLabs(Engine& e, double* host, int add);
+void mcFetchLabs(Engine& e, double* host, int add, int which);
+void mcLabsBolometric(Engine& e, double* host);
+void mcRunDust(Engine& e, const skg_mc_params& p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats);
 
 }   // namespace skg

@@ -47,6 +47,12 @@ struct McDev
     const int* ellList;     // wavelength indices with nonzero luminosity, in shooting order
     unsigned long long NppInt;
     PacketPool pool;
+    // dust emission phases (PanMonteCarloSimulation.cpp:187-342)
+    int phase;              // SKG_PHASE_*
+    unsigned rngKind;       // Philox stream kind, so that the phases of one simulation never share deviates
+    const double* dustLv;   // [Nlambda*Ncells] luminosity per cell, wavelength-major
+    const double* dustCdf;  // [Nlambda*(Ncells+1)] normalised cumulative distributions
+    double dustBias;        // PanDustSystem::emissionBias
 };
 
 // ---- accumulation ----------------------------------------------------------------------------------------

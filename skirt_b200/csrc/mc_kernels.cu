@@ -14,6 +14,7 @@
 // pool holds few wavelengths at a time (the absorption table is wavelength-major on the device).
 #include <algorithm>
 #include <vector>
+#include <cub/device/device_scan.cuh>
 #include "mc_device.cuh"
 #include "wavefront.cuh"
 
@@ -69,7 +70,7 @@ __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev
         // MonteCarloSimulation.cpp:267-268
         double L = __ldg(P.Ltot + ell) / P.Lscale;
         const unsigned long long id = (P.streamOffset + ipkt) * (unsigned long long)Nlambda + ell;
-        Philox rng; rng.init(P.seed, id);
+        Philox rng; rng.init(P.seed, id, P.rngKind);
         nPackets++;
 
         // ---- StellarSystem::launch, StellarSystem.cpp:116-158 ----
@@ -101,6 +102,99 @@ __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev
         aliveList[aliveBase + j] = slot;
     }
     flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
+}
+
+// DustGrid::randomPositionInCell: Cartesian CartesianDustGrid.cpp:129-132 (+ box(m) :333-343), tree TreeDustGrid.cpp:383-386,
+// adaptive mesh AdaptiveMesh.cpp:163-167 -- Random::position(Box) draws x, y, z in this order (Random.cpp:226-234,
+// Box::fracpos Box.hpp:125-126); Voronoi: rejection in the cell's enclosing box (VoronoiMesh.cpp:591-618)
+template<int KIND>
+__device__ __forceinline__ bool randomPositionInCell(const GridSetMC& G, int m, Philox& rng, double& x, double& y, double& z)
+{
+    double b[6];
+    if (KIND == GRID_CART)
+    {
+        const CartGrid& g = G.cart;
+        int i = m / (g.Nz * g.Ny), j = (m / g.Nz) % g.Ny, k = m % g.Nz;
+        b[0] = g.xv[i]; b[1] = g.yv[j]; b[2] = g.zv[k]; b[3] = g.xv[i + 1]; b[4] = g.yv[j + 1]; b[5] = g.zv[k + 1];
+    }
+    else if (KIND == GRID_TREE) { const double* nb = G.tree.box + 6 * (size_t)__ldg(G.tree.cellNode + m); for (int c = 0; c < 6; c++) b[c] = nb[c]; }
+    else if (KIND == GRID_AMESH) { const double* nb = G.amesh.box + 6 * (size_t)__ldg(G.amesh.cellNode + m); for (int c = 0; c < 6; c++) b[c] = nb[c]; }
+    else { const double* nb = G.voro.cellBox + 6 * (size_t)m; for (int c = 0; c < 6; c++) b[c] = nb[c]; }
+    for (int attempt = 0; attempt < 10000; attempt++)
+    {
+        double fx = rng.uniform(), fy = rng.uniform(), fz = rng.uniform();
+        x = b[0] + fx * (b[3] - b[0]); y = b[1] + fy * (b[4] - b[1]); z = b[2] + fz * (b[5] - b[2]);
+        if (KIND != GRID_VORO) return true;
+        // VoronoiMesh::isPointClosestTo, VoronoiMesh.cpp:610-618
+        const VoroGrid& g = G.voro;
+        double target = voroSD(g, m, x, y, z); bool closest = true;
+        for (int q = __ldg(g.nbrStart + m); q < __ldg(g.nbrStart + m + 1) && closest; q++)
+        { int id = __ldg(g.nbrIds + q); if (id >= 0 && voroSD(g, id, x, y, z) < target) closest = false; }
+        if (closest) return true;
+    }
+    return false;       // the reference throws "Can't find random position in cell"
+}
+
+// launch of dust emission: dodustselfabsorptionchunk :208-221 / dodustemissionchunk :296-316
+template<int KIND>
+__global__ void __launch_bounds__(128) launchDustStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, int nLaunch,
+                                                       unsigned long long firstPacket, const int* __restrict__ freeList, int* __restrict__ aliveList, int aliveBase)
+{
+    unsigned long long nPackets = 0;
+    const int Nlambda = P.med.Nlambda, Ncells = P.med.Ncells;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nLaunch; j += gridDim.x * blockDim.x)
+    {
+        const int slot = freeList[j];
+        const unsigned long long gidx = firstPacket + j;
+        const int ell = P.ellList[gidx / P.NppInt];
+        const unsigned long long ipkt = gidx % P.NppInt;
+        const double Ltot = __ldg(P.Ltot + ell);
+        double L = Ltot / P.Lscale;
+        const unsigned long long id = (P.streamOffset + ipkt) * (unsigned long long)Nlambda + ell;
+        Philox rng; rng.init(P.seed, id, P.rngKind);
+        nPackets++;
+        const double* cdf = P.dustCdf + (size_t)ell * (Ncells + 1);
+        int m;
+        double X = rng.uniform();
+        if (P.phase == SKG_PHASE_DUST_SELFABS) m = locateClip(cdf, X, Ncells + 1);
+        else
+        {
+            const double xi = P.dustBias;
+            if (X < xi) m = max(0, min(Ncells - 1, (int)(Ncells * X / xi)));
+            else m = locateClip(cdf, (X - xi) / (1 - xi), Ncells + 1);
+            double Lmean = Ltot / Ncells;
+            double weight = 1.0 / (1 - xi + xi * Lmean / __ldg(P.dustLv + (size_t)ell * Ncells + m));
+            L = L * weight;
+        }
+        double x = 0, y = 0, z = 0, kx = 0, ky = 0, kz = 1;
+        if (!randomPositionInCell<KIND>(G, m, rng, x, y, z)) { atomicAdd(&ctr->errors, 1ull); L = 0; }
+        randomDirection(rng, kx, ky, kz);
+        const PacketPool& q = P.pool;
+        q.x[slot] = x; q.y[slot] = y; q.z[slot] = z; q.kx[slot] = kx; q.ky[slot] = ky; q.kz[slot] = kz;
+        q.L[slot] = L; q.target[slot] = 0; q.id[slot] = id; q.ell[slot] = ell; q.nscatt[slot] = 0; q.rngCtr[slot] = rng.c2; q.fresh[slot] = 1;
+        aliveList[aliveBase + j] = slot;
+    }
+    flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
+}
+
+// NR::cdf (NR.hpp:388-394): Pv[0] = 0, Pv /= Pv[n]; the running sums Pv[1..n] come from the scan
+__global__ void captureTotal(double* cdf, double* Ltot, int Ncells) { *Ltot = cdf[Ncells]; cdf[0] = 0.0; }
+__global__ void normalizeCdf(double* cdf, const double* Ltot, int Ncells)
+{
+    const double total = *Ltot;
+    for (int i = 1 + blockIdx.x * blockDim.x + threadIdx.x; i <= Ncells; i += gridDim.x * blockDim.x) cdf[i] = cdf[i] / total;
+}
+
+__global__ void sumOverWavelengths(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, int Ncells, int Nlambda)
+{
+    // PanDustSystem::Labs(m), PanDustSystem.cpp:337-348: stellar table first, then the dust table, each in wavelength order
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < Ncells; m += gridDim.x * blockDim.x)
+    {
+        double sum = 0;
+        if (a) for (int ell = 0; ell < Nlambda; ell++) sum += a[(size_t)ell * Ncells + m];
+        if (b) for (int ell = 0; ell < Nlambda; ell++) sum += b[(size_t)ell * Ncells + m];
+        out[m] = sum;
+    }
 }
 
 // ---- peel-off + detection ------------------------------------------------------------------------------------
@@ -243,7 +337,7 @@ template<int KIND> struct AbsorbJob
         if (!q.fresh[slot])
         {
             // ---- simulatescattering, MonteCarloSimulation.cpp:541-549 ----
-            Philox rng; rng.init(P.seed, q.id[slot]); rng.c2 = rngCtr;
+            Philox rng; rng.init(P.seed, q.id[slot], P.rngKind); rng.c2 = rngCtr;
             int hmix = 0;
             if (Ncomp > 1)
             {
@@ -333,7 +427,7 @@ template<int KIND> struct AbsorbJob
         if (survive)
         {
             // ---- simulatepropagation, :519-533: sample the interaction optical depth, weight for the bias ----
-            Philox rng; rng.init(P.seed, q.id[slot]); rng.c2 = rngCtr;
+            Philox rng; rng.init(P.seed, q.id[slot], P.rngKind); rng.c2 = rngCtr;
             double t = 0;
             if (taupath != 0.0)
             {
@@ -584,18 +678,29 @@ void mcResetResults(Engine& e)
     e.sync();
 }
 
-void mcFetchLabs(Engine& e, double* host, int add)
+void mcFetchLabs(Engine& e, double* host, int add, int which)
 {
-    if (!e.labs.p || e.labsCount == 0) throw Error("absorption rates were not stored");
+    DevBuf& src = which ? e.labsDust : e.labs;
+    if (!src.p || e.labsCount == 0) throw Error(which ? "absorption of dust emission was not stored" : "absorption rates were not stored");
     int Nl = e.NlambdaSrc ? e.NlambdaSrc : e.med.Nlambda, Nc = e.Ncells;
     e.labsT.ensure(sizeof(double) * e.labsCount);
     dim3 grid((Nc + 31) / 32, (Nl + 31) / 32), block(32, 8);
-    transposeLabs<<<grid, block, 0, e.stream>>>(e.labs.as<double>(), e.labsT.as<double>(), Nc, Nl);
+    transposeLabs<<<grid, block, 0, e.stream>>>(src.as<double>(), e.labsT.as<double>(), Nc, Nl);
     e.launches++; SKG_CUDA(cudaGetLastError());
     if (!add) { SKG_CUDA(cudaMemcpyAsync(host, e.labsT.p, sizeof(double) * e.labsCount, cudaMemcpyDeviceToHost, e.stream)); e.sync(); return; }
     std::vector<double> tmp(e.labsCount);
     SKG_CUDA(cudaMemcpyAsync(tmp.data(), e.labsT.p, sizeof(double) * e.labsCount, cudaMemcpyDeviceToHost, e.stream)); e.sync();
     for (int64_t i = 0; i < e.labsCount; i++) host[i] += tmp[i];
+}
+
+void mcLabsBolometric(Engine& e, double* host)
+{
+    if ((!e.labs.p && !e.labsDust.p) || e.labsCount == 0) throw Error("absorption rates were not stored");
+    int Nl = (int)(e.labsCount / e.Ncells);
+    e.scratchTau.ensure(sizeof(double) * e.Ncells);
+    sumOverWavelengths<<<(e.Ncells + 127) / 128, 128, 0, e.stream>>>(e.labs.as<double>(), e.labsDust.as<double>(), e.scratchTau.as<double>(), e.Ncells, Nl);
+    e.launches++; SKG_CUDA(cudaGetLastError());
+    SKG_CUDA(cudaMemcpyAsync(host, e.scratchTau.p, sizeof(double) * e.Ncells, cudaMemcpyDeviceToHost, e.stream)); e.sync();
 }
 
 template<int KIND>
@@ -613,12 +718,14 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         int nLaunch = (int)std::min<unsigned long long>((unsigned long long)nFree, total - launched);
         if (nLaunch > 0)
         {
-            launchStage<<<blocksFor(nLaunch), 128, 0, e.stream>>>(P, e.ctr(), nLaunch, launched, freeList, listA, nAlive); e.launches++;
+            if (P.phase == SKG_PHASE_STELLAR) launchStage<<<blocksFor(nLaunch), 128, 0, e.stream>>>(P, e.ctr(), nLaunch, launched, freeList, listA, nAlive);
+            else launchDustStage<KIND><<<blocksFor(nLaunch), 128, 0, e.stream>>>(G, P, e.ctr(), nLaunch, launched, freeList, listA, nAlive);
+            e.launches++;
             nAlive += nLaunch; launched += nLaunch;
         }
         if (nAlive == 0) break;
         SKG_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), e.stream));
-        if (P.Ngroups > 0)
+        if (P.Ngroups > 0 && P.phase != SKG_PHASE_DUST_SELFABS)
         { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, counts + 2); e.launches++; }
         absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, listB, freeList, counts, counts + 3); e.launches++;
         SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
@@ -632,34 +739,55 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
     SKG_CUDA(cudaGetLastError());
 }
 
-void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
+// the per-wavelength cumulative distributions of the cell luminosities (NR::cdf) and their totals
+static void mcBuildCdfs(Engine& e, int Nlambda, int Ncells)
 {
-    if (e.gridKind == GRID_NONE && e.med.rho) throw Error("no dust grid has been set");
-    if (!e.Nsources) throw Error("no sources have been set");
-    if (e.med.Nlambda && e.NlambdaSrc != e.med.Nlambda) throw Error("sources and medium disagree on the number of wavelengths");
-    int Nlambda = e.NlambdaSrc;
+    size_t tmp = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, tmp, e.dustLv.as<double>(), e.dustCdf.as<double>() + 1, Ncells, e.stream);
+    e.scratchCub.ensure(tmp);
+    for (int ell = 0; ell < Nlambda; ell++)
+    {
+        double* cdf = e.dustCdf.as<double>() + (size_t)ell * (Ncells + 1);
+        SKG_CUDA(cub::DeviceScan::InclusiveSum(e.scratchCub.p, tmp, e.dustLv.as<double>() + (size_t)ell * Ncells, cdf + 1, Ncells, e.stream));
+        captureTotal<<<1, 1, 0, e.stream>>>(cdf, e.dustLtot.as<double>() + ell, Ncells);
+        normalizeCdf<<<std::min(148 * 8, (Ncells + 255) / 256), 256, 0, e.stream>>>(cdf, e.dustLtot.as<double>() + ell, Ncells);
+        e.launches += 4;
+    }
+    SKG_CUDA(cudaGetLastError());
+}
+
+// common driver of the three shooting phases
+static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBias, const std::vector<double>& LtotHost, skg_mc_stats* stats)
+{
+    int Nlambda = e.med.Nlambda ? e.med.Nlambda : e.NlambdaSrc;
     if (p.ellBegin < 0 || p.ellEnd > Nlambda || p.ellBegin > p.ellEnd) throw Error("wavelength range out of bounds");
     if (p.scattBias < 0 || p.scattBias > 1) throw Error("scattBias should be between 0 and 1");
     if (e.med.Ncomp > 8) throw Error("at most 8 dust components are supported");
     if (!(p.packages >= 0) || p.packages > 1e15) throw Error("Number of photon packages is negative or larger than implementation limit of 1e15");
-    if (p.storeAbsorption)
+    McDev P{};
+    P.med = e.med; if (!e.med.rho) { P.med.Nlambda = Nlambda; P.med.Ncomp = 0; }
+    P.phase = phase; P.rngKind = (unsigned)phase;
+    P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
+    P.L = e.lumDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>();
+    P.Ltot = phase == SKG_PHASE_STELLAR ? e.lumTotDev.as<double>() : e.dustLtot.as<double>();
+    P.emissionBias = e.emissionBias;
+    P.instr = e.instrGroupedDev.as<InstrDev>(); P.Ninstr = (int)e.instr.size();
+    P.groups = e.groupsDev.as<ObsGroup>(); P.Ngroups = e.Ngroups;
+    P.dustLv = e.dustLv.as<double>(); P.dustCdf = e.dustCdf.as<double>(); P.dustBias = dustBias;
+    const bool store = phase == SKG_PHASE_STELLAR ? p.storeAbsorption != 0 : phase == SKG_PHASE_DUST_SELFABS;
+    if (store)
     {
         if (!e.med.rho) throw Error("absorption rates can only be stored with a dust system");
         int64_t count = (int64_t)e.Ncells * Nlambda;
         if (e.labsCount != count)
         {
-            e.labs.ensure(sizeof(double) * count); e.labsCount = count;
-            SKG_CUDA(cudaMemsetAsync(e.labs.p, 0, sizeof(double) * count, e.stream));
+            // (re)allocate both tables consistently
+            e.labs.release(); e.labsDust.release(); e.labsCount = count;
         }
+        DevBuf& tab = phase == SKG_PHASE_STELLAR ? e.labs : e.labsDust;
+        if (!tab.p) { tab.ensure(sizeof(double) * count); SKG_CUDA(cudaMemsetAsync(tab.p, 0, sizeof(double) * count, e.stream)); }
+        P.labs = tab.as<double>();
     }
-    McDev P{};
-    P.med = e.med; if (!e.med.rho) { P.med.Nlambda = Nlambda; P.med.Ncomp = 0; }
-    P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
-    P.L = e.lumDev.as<double>(); P.Ltot = e.lumTotDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>();
-    P.emissionBias = e.emissionBias;
-    P.instr = e.instrGroupedDev.as<InstrDev>(); P.Ninstr = (int)e.instr.size();
-    P.groups = e.groupsDev.as<ObsGroup>(); P.Ngroups = e.Ngroups;
-    P.labs = p.storeAbsorption ? e.labs.as<double>() : nullptr;
     P.NppInt = (unsigned long long)std::ceil(p.packages);
     P.Lscale = p.luminosityScale > 0 ? p.luminosityScale : (double)P.NppInt;
     P.minWeightReduction = p.minWeightReduction; P.minfs = p.minScattEvents; P.xi = p.scattBias;
@@ -667,7 +795,7 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
 
     // wavelengths with luminosity, in shooting order (the reference skips the others, MonteCarloSimulation.cpp:269,298)
     std::vector<int> ells;
-    for (int ell = p.ellBegin; ell < p.ellEnd; ell++) if (e.lumTotHost[ell] > 0) ells.push_back(ell);
+    for (int ell = p.ellBegin; ell < p.ellEnd; ell++) if (LtotHost[ell] > 0) ells.push_back(ell);
     unsigned long long total = P.NppInt * (unsigned long long)ells.size();
 
     Counters before = e.readCounters();
@@ -709,7 +837,7 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
         case GRID_AMESH: shootWavefront<GRID_AMESH>(e, G, P, total, pool, 0, false); break;
         case GRID_VORO: shootWavefront<GRID_VORO>(e, G, P, total, pool, 0, false); break;
         default:
-            if (e.med.rho) throw Error("no dust grid has been set");
+            if (e.med.rho || phase != SKG_PHASE_STELLAR) throw Error("no dust grid has been set");
             shootWavefront<GRID_CART>(e, G, P, total, pool, 0, false);      // no dust: only launch + emission peel-off run
         }
     }
@@ -718,6 +846,7 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
     float ms = 0; SKG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
     cudaEventDestroy(ev0); cudaEventDestroy(ev1);
     Counters after = e.readCounters();
+    if (after.errors != before.errors) throw Error("the shooting kernels met a condition on which the reference throws a fatal error (" + std::to_string(after.errors - before.errors) + " times)");
     if (stats)
     {
         stats->packets = after.packets - before.packets; stats->pathSegments = after.segments - before.segments;
@@ -725,6 +854,36 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
         stats->kernel_ms = ms;
         stats->absorbSegments = after.absorbSegments - before.absorbSegments; stats->detections = after.detections - before.detections;
     }
+}
+
+void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
+{
+    if (e.gridKind == GRID_NONE && e.med.rho) throw Error("no dust grid has been set");
+    if (!e.Nsources) throw Error("no sources have been set");
+    if (e.med.Nlambda && e.NlambdaSrc != e.med.Nlambda) throw Error("sources and medium disagree on the number of wavelengths");
+    runPhase(e, p, SKG_PHASE_STELLAR, 0.0, e.lumTotHost, stats);
+}
+
+// PanMonteCarloSimulation::dodustselfabsorptionchunk / dodustemissionchunk for every wavelength
+void mcRunDust(Engine& e, const skg_mc_params& p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats)
+{
+    if (phase != SKG_PHASE_DUST_SELFABS && phase != SKG_PHASE_DUST_EMISSION) throw Error("skg_run_dust: phase must be SKG_PHASE_DUST_SELFABS or SKG_PHASE_DUST_EMISSION");
+    if (e.gridKind == GRID_NONE || !e.med.rho) throw Error("dust emission needs a dust grid and a medium");
+    if (!Lcell) throw Error("skg_run_dust: null cell luminosities");
+    if (!(emissionBias >= 0 && emissionBias < 1)) throw Error("emissionBias should be between 0 and 1");
+    if (e.gridKind == GRID_VORO && !e.voro.cellBox) throw Error("the Voronoi grid was given without cell boxes (needed by randomPositionInCell)");
+    const int Nlambda = e.med.Nlambda, Ncells = e.Ncells;
+    const size_t count = (size_t)Nlambda * Ncells;
+    if (mem == SKG_HOST) e.dustLv.upload(Lcell, sizeof(double) * count, e.stream);
+    else { e.dustLv.ensure(sizeof(double) * count); SKG_CUDA(cudaMemcpyAsync(e.dustLv.p, Lcell, sizeof(double) * count, cudaMemcpyDeviceToDevice, e.stream)); }
+    e.dustCdf.ensure(sizeof(double) * (size_t)Nlambda * (Ncells + 1));
+    e.dustLtot.ensure(sizeof(double) * Nlambda);
+    mcBuildCdfs(e, Nlambda, Ncells);
+    std::vector<double> Ltot(Nlambda);
+    SKG_CUDA(cudaMemcpyAsync(Ltot.data(), e.dustLtot.p, sizeof(double) * Nlambda, cudaMemcpyDeviceToHost, e.stream));
+    e.sync();
+    for (double& v : Ltot) if (!(v > 0) || !std::isfinite(v)) v = 0;
+    runPhase(e, p, phase, emissionBias, Ltot, stats);
 }
 
 }   // namespace skg

@@ -20,6 +20,7 @@ struct TreeGrid
     const double* box;              // [6N] xmin,ymin,zmin,xmax,ymax,zmax
     const int* child0; const int* parent; const int* cell; const int* dir;
     const int* nbrStart; const int* nbrIds;
+    const int* cellNode;            // leaf node of every cell (TreeDustGrid::getnode, for randomPositionInCell)
     int N, kind, search;
     double eps;
 };
@@ -27,6 +28,7 @@ struct TreeGrid
 struct AMeshGrid
 {
     const double* box; const int* nxyz; const int* child0; const int* cell; const int* wallNbr;
+    const int* cellNode;            // leaf node of every cell
     int N;
     double eps;
 };

@@ -1,0 +1,98 @@
+"""GPU parity of the dust emission phases: PanMonteCarloSimulation::dodustselfabsorptionchunk
+and dodustemissionchunk.  The reference side runs its own code (oracle/_ref, which travels to the GPU box as a
+prebuilt library): stellar phase -> DustLib -> cell luminosities Lv; both sides then shoot the same Lv."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref_pan(n=16, nlambda=25, packages=2e4, grid=None):
+    from oracle import skirtref as sr, refspec
+    from skirt_b200 import configs
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    p = configs.c2_params(n=n, nlambda=nlambda, packages=packages)
+    spec, L, mixes = refspec.reference_spec(p, threads=os.cpu_count() or 1, dustsamples=5)
+    spec += "selfabs 1\n"
+    if grid:
+        spec = "\n".join(grid if l.startswith("grid ") else l for l in spec.splitlines()) + "\n"
+    S = sr.RefSim(spec, luminosities=L, mixes=mixes).setup()
+    S.reset(4357); S.run_stellar()
+    return S, p
+
+
+def _engine_for(engine, S, p):
+    tables, medium, L = S.grid_tables(), S.medium(), S.luminosities()
+    engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    ins = [dict(kind=1, distance=1e7 * common.PC, inclination=float(np.radians(88)), Nxp=800, fovxp=50000 * common.PC, Nyp=200, fovyp=12500 * common.PC),
+           dict(kind=2, distance=1e7 * common.PC, inclination=float(np.radians(88)))]
+    engine.instruments(ins)
+    return tables
+
+
+def _compare(name, a, r, B, frac=0.97):
+    a = np.array(a).reshape(B, -1); r = np.array(r).reshape(B, -1)
+    ta, tr = a.sum(1), r.sum(1)
+    zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / B + tr.var(ddof=1) / B)
+    assert abs(zt) < 3.5, f"{name}: total differs by {zt:.2f} sigma ({ta.mean():.6g} vs {tr.mean():.6g})"
+    ma, mr = a.mean(0), r.mean(0); sa, sr_ = a.std(0, ddof=1) / np.sqrt(B), r.std(0, ddof=1) / np.sqrt(B)
+    ok = (sa < 0.3 * ma) & (sr_ < 0.3 * mr) & (sa > 0) & (sr_ > 0)
+    if ok.sum() > 20:
+        z = common.zscores(ma[ok], sa[ok], mr[ok], sr_[ok])
+        assert np.mean(np.abs(z) < 3) > frac and abs(z.mean()) < 0.2, f"{name}: {np.mean(np.abs(z) < 3):.4f} within 3 sigma, mean z {z.mean():.3f}"
+
+
+@pytest.mark.parametrize("grid", [None, "grid octtree 2 4 1 0.0005 0 30"])
+def test_dust_selfabsorption_and_emission(engine, grid):
+    S, p = _ref_pan(grid=grid)
+    _engine_for(engine, S, p)
+    Npp = S.packages_per_lambda()
+    Lv = S.prepare_dust(True)
+    assert Lv.sum() > 0
+    B = 10
+    # ---- one self-absorption cycle with a tenth of the packets (first stage, PanMonteCarloSimulation.cpp:116-118)
+    ref, gpu = [], []
+    for b in range(B):
+        S.reset(100 + 1000 * b); S.run_dust(True, 0.1); ref.append(S.labs_dust().ravel().copy())
+        NppStage = S.packages_per_lambda()      # set by setChunkParams(packages*factor)
+        engine.reset_labs_dust()
+        st = engine.run_dust(1, Lv, NppStage, seed=70 + b)
+        gpu.append(engine.fetch_labs_dust().ravel())
+        assert st["detections"] == 0
+    _compare("Labsdust", gpu, ref, B)
+    # ---- the dust emission phase
+    ref_f, ref_s, gpu_f, gpu_s = [], [], [], []
+    for b in range(B):
+        S.reset(5000 + 1000 * b); S.run_dust(False, 1.0); ins = S.instruments()
+        ref_f.append(ins[0]["frame"].copy()); ref_s.append(ins[1]["sed"].copy())
+        NppEm = S.packages_per_lambda()
+        engine.reset_results()
+        st = engine.run_dust(2, Lv, NppEm, emission_bias=0.5, seed=170 + b)
+        gpu_f.append(engine.fetch_frame(0)); gpu_s.append(engine.fetch_sed(1))
+        assert st["absorbSegments"] == 0
+    _compare("dust SED", gpu_s, ref_s, B)
+    _compare("dust frame", gpu_f, ref_f, B)
+
+
+def test_labs_bolometric_and_random_positions(engine):
+    S, p = _ref_pan(packages=5e3)
+    tables = _engine_for(engine, S, p)
+    L = S.luminosities()
+    engine.sources([dict(geometry=2, p=[1600 * common.PC, 0.7], rv=np.ones(2), Xv=np.array([0.0, 1.0])),
+                    dict(geometry=1, p=[4000 * common.PC, 350 * common.PC, 0, 0, 0])], L, 0.5)
+    engine.reset_results()
+    engine.run_stellar(2e3, store_absorption=True, seed=5)
+    bol = engine.labs_bolometric()
+    np.testing.assert_allclose(bol, engine.fetch_labs().sum(1), rtol=1e-12)
+    # uniform positions inside the emitting cell: all luminosity in one cell, no dust interaction needed to see it
+    Lv = np.zeros((engine.Nlambda, engine.Ncells)); m = 1234; Lv[3, m] = 1.0
+    engine.reset_results()
+    st = engine.run_dust(2, Lv, 2e4, emission_bias=0.0, seed=9)
+    assert st["packets"] == 20000
+    sed = engine.fetch_sed(1)
+    assert sed[3] > 0 and np.count_nonzero(sed) == 1
