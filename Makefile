@@ -11,7 +11,7 @@ HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/skirtgpu.h
 NCCL_INC ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'include'))" 2>/dev/null)
 NCCL_LIB ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'lib'))" 2>/dev/null)
 
-all: skirt_b200/libskirtgpu.so oracle
+all: skirt_b200/libskirtgpu.so skirt_b200/skirt_b200_run oracle
 
 $(CSRC)/build/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(CSRC)/build
@@ -20,10 +20,15 @@ $(CSRC)/build/%.o: $(CSRC)/%.cu $(HDRS)
 skirt_b200/libskirtgpu.so: $(OBJS)
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJS) -ldl
 
+# C++ host layer (simulation items with the reference's names) + command-line driver, linked against the C ABI only
+HOST := skirt_b200/host
+skirt_b200/skirt_b200_run: $(HOST)/skirt_b200_run.cpp $(HOST)/SimulationItems.cpp $(HOST)/SimulationItems.hpp include/skirtgpu.h skirt_b200/libskirtgpu.so
+	$(HOSTCXX) -std=c++17 -O2 -Wall -o $@ $(HOST)/skirt_b200_run.cpp $(HOST)/SimulationItems.cpp -Lskirt_b200 -lskirtgpu -Wl,-rpath,'$$ORIGIN' -Wl,-rpath-link,/usr/local/cuda/lib64
+
 oracle:
 	$(MAKE) -C oracle all
 
 clean:
-	rm -rf $(CSRC)/build skirt_b200/libskirtgpu.so
+	rm -rf $(CSRC)/build skirt_b200/libskirtgpu.so skirt_b200/skirt_b200_run
 	$(MAKE) -C oracle clean
 .PHONY: all oracle clean

@@ -146,6 +146,8 @@ typedef struct skg_mc_stats
     double kernel_ms;           /* device time of the shooting kernels (CUDA events) */
     uint64_t absorbSegments;    /* segments that added into the absorption table (one fp64 atomic each) */
     uint64_t detections;        /* detector updates: frame pixel or SED bin (one fp64 atomic each) */
+    double launch_ms, peel_ms, absorb_ms, propagate_ms;     /* device time per stage kernel family (CUDA events) */
+    uint64_t iterations;        /* wavefront iterations (one launch of every stage each) */
 } skg_mc_stats;
 int skg_run_stellar(skg_engine* e, const skg_mc_params* p, skg_mc_stats* stats);
 

@@ -45,7 +45,13 @@ class SkgMcParams(C.Structure):
 class SkgMcStats(C.Structure):
     _fields_ = [("packets", C.c_uint64), ("pathSegments", C.c_uint64), ("paths", C.c_uint64),
                 ("scatterings", C.c_uint64), ("kernel_ms", C.c_double),
-                ("absorbSegments", C.c_uint64), ("detections", C.c_uint64)]
+                ("absorbSegments", C.c_uint64), ("detections", C.c_uint64),
+                ("launch_ms", C.c_double), ("peel_ms", C.c_double), ("absorb_ms", C.c_double), ("propagate_ms", C.c_double),
+                ("iterations", C.c_uint64)]
+
+
+def _stats(st):
+    return {name: getattr(st, name) for name, _ in SkgMcStats._fields_}
 
 
 def lib_available():
@@ -271,8 +277,7 @@ class Engine:
         p.ellBegin = int(ell_begin); p.ellEnd = int(self.Nlambda if ell_end is None else ell_end)
         st = SkgMcStats()
         self._chk(self._lib.skg_run_stellar(self.h, C.byref(p), C.byref(st)))
-        return dict(packets=st.packets, pathSegments=st.pathSegments, paths=st.paths, scatterings=st.scatterings,
-                    kernel_ms=st.kernel_ms, absorbSegments=st.absorbSegments, detections=st.detections)
+        return _stats(st)
 
     def _params(self, packages, total_packages, min_weight_reduction, min_scatt_events, scatt_bias, store_absorption, seed,
                 stream_offset, ell_begin, ell_end, pool_packets):
@@ -296,8 +301,7 @@ class Engine:
                          stream_offset, ell_begin, ell_end, pool_packets)
         st = SkgMcStats()
         self._chk(self._lib.skg_run_dust(self.h, C.byref(p), int(phase), C.c_double(emission_bias), SKG_HOST, _vp(Lc), C.byref(st)))
-        return dict(packets=st.packets, pathSegments=st.pathSegments, paths=st.paths, scatterings=st.scatterings,
-                    kernel_ms=st.kernel_ms, absorbSegments=st.absorbSegments, detections=st.detections)
+        return _stats(st)
 
     def reset_labs_dust(self):
         self._chk(self._lib.skg_reset_labs_dust(self.h))

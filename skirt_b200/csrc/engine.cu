@@ -35,6 +35,7 @@ Engine::~Engine()
     for (DevBuf* b : sourceBufs) delete b;
     for (DevBuf* b : instrBufs) delete b;
     if (mcHostCounts) cudaFreeHost(mcHostCounts);
+    for (cudaEvent_t ev : mcEvents) if (ev) cudaEventDestroy(ev);
     if (stream) cudaStreamDestroy(stream);
 }
 

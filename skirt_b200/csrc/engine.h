@@ -76,6 +76,8 @@ struct Engine
     DevBuf instrGroupedDev, groupsDev; int Ngroups = 0;    // instruments ordered by line of sight + the groups
     DevBuf mcPool, mcLists, mcCounts, mcEllList; int* mcHostCounts = nullptr;   // packet pool of the wavefront shooter
     void* nccl = nullptr; int rank = 0, nranks = 1;
+    double stageMs[4] = {0, 0, 0, 0}; uint64_t mcIterations = 0;     // launch, peel, absorb, propagate device time of the last phase
+    cudaEvent_t mcEvents[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;              // kernels launched by this engine (skg_launch_count)
 
     explicit Engine(int dev);

@@ -709,13 +709,20 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
     int* listA = e.mcLists.as<int>(); int* listB = listA + pool; int* freeList = listB + pool;
     int* counts = e.mcCounts.as<int>();      // [0] survivors, [1] freed slots, [2..4] work counters of the three traversal stages
     auto blocksFor = [&](long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, (long long)e.smCount * 16)); };
+    for (cudaEvent_t& ev : e.mcEvents) if (!ev) SKG_CUDA(cudaEventCreate(&ev));
+    cudaEvent_t* ev = e.mcEvents;            // 0..3: boundaries launch | peel | absorb | end; 4..5: around propagate
+    for (double& t : e.stageMs) t = 0;
+    e.mcIterations = 0;
     iotaKernel<<<blocksFor(pool), 128, 0, e.stream>>>(freeList, pool); e.launches++;
     unsigned long long launched = 0;
     int nAlive = 0, nFree = pool;
     int* hostCounts = e.mcHostCounts;
+    bool propagatePending = false;
+    auto addMs = [&](int stage, cudaEvent_t a, cudaEvent_t b) { float ms = 0; SKG_CUDA(cudaEventElapsedTime(&ms, a, b)); e.stageMs[stage] += ms; };
     while (true)
     {
         int nLaunch = (int)std::min<unsigned long long>((unsigned long long)nFree, total - launched);
+        SKG_CUDA(cudaEventRecord(ev[0], e.stream));
         if (nLaunch > 0)
         {
             if (P.phase == SKG_PHASE_STELLAR) launchStage<<<blocksFor(nLaunch), 128, 0, e.stream>>>(P, e.ctr(), nLaunch, launched, freeList, listA, nAlive);
@@ -725,18 +732,32 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         }
         if (nAlive == 0) break;
         SKG_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), e.stream));
+        SKG_CUDA(cudaEventRecord(ev[1], e.stream));
         if (P.Ngroups > 0 && P.phase != SKG_PHASE_DUST_SELFABS)
         { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, counts + 2); e.launches++; }
+        SKG_CUDA(cudaEventRecord(ev[2], e.stream));
         absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, listB, freeList, counts, counts + 3); e.launches++;
+        SKG_CUDA(cudaEventRecord(ev[3], e.stream));
         SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
         SKG_CUDA(cudaGetLastError());
         e.sync();
+        if (propagatePending) { addMs(3, ev[4], ev[5]); propagatePending = false; }
+        addMs(0, ev[0], ev[1]); addMs(1, ev[1], ev[2]); addMs(2, ev[2], ev[3]);
+        e.mcIterations++;
         int nSurv = hostCounts[0]; nFree = hostCounts[1];
-        if (nSurv > 0) { propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listB, nSurv, counts + 4); e.launches++; }
+        if (nSurv > 0)
+        {
+            SKG_CUDA(cudaEventRecord(ev[4], e.stream));
+            propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listB, nSurv, counts + 4); e.launches++;
+            SKG_CUDA(cudaEventRecord(ev[5], e.stream));
+            propagatePending = true;
+        }
         std::swap(listA, listB);
         nAlive = nSurv;
     }
     SKG_CUDA(cudaGetLastError());
+    e.sync();
+    if (propagatePending) addMs(3, ev[4], ev[5]);
 }
 
 // the per-wavelength cumulative distributions of the cell luminosities (NR::cdf) and their totals
@@ -853,6 +874,8 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         stats->paths = after.paths - before.paths; stats->scatterings = after.scatterings - before.scatterings;
         stats->kernel_ms = ms;
         stats->absorbSegments = after.absorbSegments - before.absorbSegments; stats->detections = after.detections - before.detections;
+        stats->launch_ms = e.stageMs[0]; stats->peel_ms = e.stageMs[1]; stats->absorb_ms = e.stageMs[2]; stats->propagate_ms = e.stageMs[3];
+        stats->iterations = e.mcIterations;
     }
 }
 

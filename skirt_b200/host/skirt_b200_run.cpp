@@ -1,0 +1,140 @@
+// Command-line driver of the C++ host layer: builds a simulation hierarchy from a small parameter file (one item
+// per line, the same vocabulary as the ski properties it stands for), runs the stellar emission phase on the GPU
+// and writes the raw detector arrays.  ski/XML parsing and FITS output stay in the reference (out of scope).
+//
+//   sim oligo|pan ; packages N ; seed S ; minweightreduction f ; minscatt n ; scattbias xi ; emissionbias xi
+//   wavelengths l1 l2 ...          | loggrid min max points
+//   box xmin xmax ymin ymax zmin zmax
+//   grid cartesian nx ny nz lin|pow r|sympow r  (x3)
+//   dustmix interstellar <file> | dustmix table kabs ksca g      (one wavelength)
+//   dust tau lambda expdisk hR hz Rmax zmax
+//   stellar L1[,L2,...]|bb:T:Lbol expdisk hR hz Rmax zmax | sersic n Reff q
+//   instrument frame|sed|simple name distance inclination azimuth pa [nx fovx ny fovy]
+//   storeabs 0|1 ; device d ; lattice n
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include "SimulationItems.hpp"
+
+using namespace skirt;
+
+static Mesh* makeMesh(std::istringstream& in, int n)
+{
+    std::string kind; in >> kind; Mesh* m = nullptr;
+    if (kind == "lin") m = new LinMesh();
+    else if (kind == "pow") { auto* p = new PowMesh(); double r; in >> r; p->setRatio(r); m = p; }
+    else if (kind == "sympow") { auto* p = new SymPowMesh(); double r; in >> r; p->setRatio(r); m = p; }
+    else SKIRT_FATAL("unknown mesh " + kind);
+    m->setNumBins(n);
+    return m;
+}
+
+static Geometry* makeGeometry(std::istringstream& in)
+{
+    std::string kind; in >> kind;
+    if (kind == "expdisk")
+    {
+        double hR, hz, Rmax, zmax; in >> hR >> hz >> Rmax >> zmax;
+        auto* g = new ExpDiskGeometry(); g->setRadialScale(hR); g->setAxialScale(hz); g->setRadialTrunc(Rmax); g->setAxialTrunc(zmax);
+        return g;
+    }
+    if (kind == "sersic")
+    {
+        double n, Re, q; in >> n >> Re >> q;
+        auto* g = new SersicGeometry(); g->setIndex(n); g->setRadius(Re); g->setFlattening(q);
+        return g;
+    }
+    SKIRT_FATAL("unknown geometry " + kind);
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 3) { std::fprintf(stderr, "usage: %s <parameter file> <output prefix>\n", argv[0]); return 2; }
+    try
+    {
+        std::ifstream file(argv[1]);
+        if (!file) SKIRT_FATAL(std::string("cannot open ") + argv[1]);
+        MonteCarloSimulation sim;
+        auto* ss = new StellarSystem(); auto* ds = new DustSystem(); auto* is = new InstrumentSystem();
+        double box[6] = {0, 0, 0, 0, 0, 0};
+        std::string mixKind = "table", mixFile; double mixv[3] = {0, 0, 0};
+        bool pan = false;
+        std::string line;
+        while (std::getline(file, line))
+        {
+            if (line.empty() || line[0] == '#') continue;
+            std::istringstream in(line); std::string key; in >> key;
+            if (key == "sim") { std::string t; in >> t; pan = t == "pan"; }
+            else if (key == "packages") { double v; in >> v; sim.setPackages(v); }
+            else if (key == "seed") { int v; in >> v; sim.setSeed(v); }
+            else if (key == "device") { int v; in >> v; sim.setDevice(v); }
+            else if (key == "minweightreduction") { double v; in >> v; sim.setMinWeightReduction(v); }
+            else if (key == "minscatt") { double v; in >> v; sim.setMinScattEvents(v); }
+            else if (key == "scattbias") { double v; in >> v; sim.setScattBias(v); }
+            else if (key == "emissionbias") { double v; in >> v; ss->setEmissionBias(v); }
+            else if (key == "storeabs") { int v; in >> v; ds->setStoreAbsorptionRates(v != 0); }
+            else if (key == "lattice") { int v; in >> v; ds->setSampleLattice(v); }
+            else if (key == "wavelengths") { std::vector<double> lv; double v; while (in >> v) lv.push_back(v); auto* g = new OligoWavelengthGrid(); g->setWavelengths(lv); sim.setWavelengthGrid(g); }
+            else if (key == "loggrid") { double a, b; int n; in >> a >> b >> n; auto* g = new LogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n); sim.setWavelengthGrid(g); }
+            else if (key == "box") { for (double& v : box) in >> v; }
+            else if (key == "grid")
+            {
+                std::string kind; in >> kind;
+                if (kind != "cartesian") SKIRT_FATAL("this driver builds Cartesian grids; tree, Voronoi and adaptive-mesh grids are handed to the engine as flattened tables");
+                int nx, ny, nz; in >> nx >> ny >> nz;
+                auto* g = new CartesianDustGrid();
+                g->setMinX(box[0]); g->setMaxX(box[1]); g->setMinY(box[2]); g->setMaxY(box[3]); g->setMinZ(box[4]); g->setMaxZ(box[5]);
+                g->setMeshX(makeMesh(in, nx)); g->setMeshY(makeMesh(in, ny)); g->setMeshZ(makeMesh(in, nz));
+                ds->setDustGrid(g);
+            }
+            else if (key == "dustmix") { in >> mixKind; if (mixKind == "interstellar") in >> mixFile; else in >> mixv[0] >> mixv[1] >> mixv[2]; }
+            else if (key == "dust")
+            {
+                double tau, lam; in >> tau >> lam;
+                auto* c = new DustComp(); c->setGeometry(makeGeometry(in));
+                if (mixKind == "interstellar") c->setMix(new InterstellarDustMix(mixFile));
+                else { auto* m = new TableDustMix(); m->setTable({lam}, {mixv[0]}, {mixv[1]}, {mixv[2]}); c->setMix(m); }
+                auto* n = new FaceOnDustCompNormalization(); n->setWavelength(lam); n->setOpticalDepth(tau); c->setNormalization(n);
+                ds->addComponent(c);
+            }
+            else if (key == "stellar")
+            {
+                std::string lum; in >> lum;
+                auto* c = new StellarComp();
+                if (lum.rfind("bb:", 0) == 0) { double T, Lbol; if (std::sscanf(lum.c_str(), "bb:%lf:%lf", &T, &Lbol) != 2) SKIRT_FATAL("bad black body " + lum); c->setBlackBody(T, Lbol); }
+                else { std::vector<double> L; std::istringstream ls(lum); std::string tok; while (std::getline(ls, tok, ',')) L.push_back(std::stod(tok)); c->setLuminosities(L); }
+                c->setGeometry(makeGeometry(in));
+                ss->addComponent(c);
+            }
+            else if (key == "instrument")
+            {
+                std::string kind, name; double d, inc, az, pa; in >> kind >> name >> d >> inc >> az >> pa;
+                Instrument* i = kind == "sed" ? (Instrument*)new SEDInstrument() : kind == "frame" ? (Instrument*)new FrameInstrument() : (Instrument*)new SimpleInstrument();
+                i->setInstrumentName(name); i->setDistance(d); i->setInclination(inc); i->setAzimuth(az); i->setPositionAngle(pa);
+                if (kind != "sed") { int nx, ny; double fx, fy; in >> nx >> fx >> ny >> fy; i->setPixelsX(nx); i->setFieldOfViewX(fx); i->setPixelsY(ny); i->setFieldOfViewY(fy); }
+                is->addInstrument(i);
+            }
+            else SKIRT_FATAL("unknown key " + key);
+        }
+        (void)pan;
+        sim.setStellarSystem(ss); sim.setDustSystem(ds); sim.setInstrumentSystem(is);
+        sim.setup();
+        skg_mc_stats st = sim.runstellaremission();
+        sim.fetchResults();
+        std::string prefix = argv[2];
+        auto dump = [&](const std::string& name, const std::vector<double>& v)
+        { std::ofstream out(prefix + "_" + name + ".f64", std::ios::binary); out.write(reinterpret_cast<const char*>(v.data()), sizeof(double) * v.size()); };
+        for (auto& i : sim.instrumentSystem()->instruments())
+        {
+            if (!i->ftotv.empty()) dump(i->name + "_frame", i->ftotv);
+            if (!i->Ftotv.empty()) dump(i->name + "_sed", i->Ftotv);
+        }
+        if (!sim.Labs().empty()) dump("Labs", sim.Labs());
+        dump("rho", sim.dustSystem()->rho());
+        std::printf("{\"packets\": %llu, \"pathSegments\": %llu, \"scatterings\": %llu, \"kernel_ms\": %.3f, \"cells\": %d, \"wavelengths\": %d}\n",
+                    (unsigned long long)st.packets, (unsigned long long)st.pathSegments, (unsigned long long)st.scatterings, st.kernel_ms,
+                    sim.dustSystem()->Ncells(), sim.wavelengthGrid()->Nlambda());
+        return 0;
+    }
+    catch (std::exception& ex) { std::fprintf(stderr, "*** Error: %s\n", ex.what()); return 1; }
+}

@@ -1,0 +1,80 @@
+"""The C++ host layer (skirt_b200/host: simulation items with the reference's names over the C ABI) through its
+command-line driver.  CPU part: argument/property validation with the reference's error messages and the
+no-fallback rule; GPU part: a C1 run end to end, compared with the Python mirror and the reference's golden run."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import common
+
+RUN = os.path.join(common.ROOT, "skirt_b200", "skirt_b200_run")
+PC = common.PC
+
+
+def params(packages=2e5, n=24, extra=()):
+    lines = ["sim oligo", f"packages {packages!r}", "seed 4357", "wavelengths 0.55e-6", common.box_line(common.C1_BOX),
+             f"grid cartesian {n} {n} {n} lin lin lin", "storeabs 1",
+             f"dustmix table {common.MIX_V['kabs']!r} {common.MIX_V['ksca']!r} {common.MIX_V['g']!r}",
+             f"dust 1.0 0.55e-6 expdisk {4000*PC!r} {140*PC!r} 0 0",
+             f"stellar 1.0 expdisk {4000*PC!r} {350*PC!r} 0 0",
+             f"instrument frame i88 {1e7*PC!r} {float(np.radians(88))!r} 0 0 200 {50000*PC!r} 50 {12500*PC!r}",
+             f"instrument sed s88 {1e7*PC!r} {float(np.radians(88))!r} 0 0"] + list(extra)
+    return "\n".join(lines) + "\n"
+
+
+def run(tmp_path, text):
+    f = tmp_path / "sim.txt"; f.write_text(text)
+    return subprocess.run([RUN, str(f), str(tmp_path / "out")], capture_output=True, text=True, timeout=600)
+
+
+@pytest.mark.skipif(not os.path.exists(RUN), reason="skirt_b200_run not built")
+def test_property_validation_messages(tmp_path):
+    r = run(tmp_path, params(extra=["packages -5"]))
+    assert r.returncode == 1 and "Number of photon packages is negative" in r.stderr
+    r = run(tmp_path, params().replace("expdisk %r %r 0 0" % (4000 * PC, 140 * PC), "expdisk -1 %r 0 0" % (140 * PC)))
+    assert r.returncode == 1 and "radial scale length hR should be positive" in r.stderr
+    r = run(tmp_path, params().replace(common.box_line(common.C1_BOX), "box 1 0 0 1 0 1"))
+    assert r.returncode == 1 and "extent of the box should be positive in the X direction" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.exists(RUN), reason="skirt_b200_run not built")
+def test_no_cpu_fallback(tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    r = run(tmp_path, params(packages=100.0, n=4))
+    assert r.returncode == 1 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c1_through_the_cpp_host(tmp_path, engine):
+    r = run(tmp_path, params())
+    assert r.returncode == 0, r.stderr
+    st = json.loads(r.stdout.strip().splitlines()[-1])
+    assert st["packets"] == 200000 and st["cells"] == 24 ** 3
+    load = lambda name: np.fromfile(tmp_path / f"out_{name}.f64")
+    sed, frame, labs, rho = load("s88_sed"), load("i88_frame"), load("Labs"), load("rho")
+    assert frame.size == 200 * 50 and labs.size == 24 ** 3
+    # the same configuration through the Python mirror: identical density table, statistically identical results
+    from skirt_b200 import simulation as sim
+    lg = sim.OligoWavelengthGrid([0.55e-6])
+    b = common.C1_BOX
+    grid = sim.CartesianDustGrid(b[0], b[1], b[2], b[3], b[4], b[5], sim.LinMesh(24), sim.LinMesh(24), sim.LinMesh(24))
+    mix = sim.TableDustMix(common.MIX_V["kabs"], common.MIX_V["ksca"], common.MIX_V["g"])
+    ds = sim.DustSystem(grid, [sim.DustComp(sim.ExpDiskGeometry(4000 * PC, 140 * PC), mix, 1.0, 0.55e-6)], lg)
+    np.testing.assert_allclose(rho, ds.rho.ravel(), rtol=1e-12)
+    cfg = common.cfg_c1(n=24, packages=2e5, storeabs=1)
+    common.setup_engine(engine, cfg, grid.tables(), ds.medium(), np.array([[1.0]]))
+    engine.reset_results(); engine.run_stellar(2e5, store_absorption=True, seed=99)
+    for name, a, b_ in (("sed", sed.sum(), engine.fetch_sed(1).sum()), ("frame", frame.sum(), engine.fetch_frame(0).sum()),
+                        ("labs", labs.sum(), engine.fetch_labs().sum())):
+        assert abs(a / b_ - 1) < 0.01, f"{name}: C++ host {a} vs Python mirror {b_}"
+    # against the reference's own 16 runs of this configuration (golden), whose density table comes from 20 random
+    # samples per cell instead of the lattice (a coarse 24^3 grid, so the tables differ at the few-percent level)
+    _, _, g = common.load_golden_mc()
+    assert abs(sed[0] / g["sed_total_mean"][0] - 1) < 0.06
+    assert abs(frame.sum() / g["frame_total_mean"][0] - 1) < 0.06
+    assert abs(labs.sum() / g["labs_total_mean"][0] - 1) < 0.12
