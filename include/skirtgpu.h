@@ -92,6 +92,9 @@ int skg_whichcell(skg_engine* e, int mem, int64_t n, const double* r, int* m);
 /* number of "stuck packet" escapes / terminations since engine creation (the reference logs warnings,
  * TreeDustGrid.cpp:437-454, AdaptiveMesh.cpp:348-365) */
 int skg_stuck_counts(skg_engine* e, int64_t* escaped, int64_t* terminated);
+/* self test of the engine's invariant-divisor fp64 division against the IEEE division on n pseudo-random operand
+ * pairs (the walkers divide by the direction cosines, which are constant along a path); *mismatches must be 0 */
+int skg_selftest_division(skg_engine* e, uint64_t n, uint64_t seed, uint64_t* mismatches);
 
 /* ---- sources: StellarSystem::launch (StellarSystem.cpp:116-158) -------------------------------------- */
 enum { SKG_GEOM_EXPDISK = 1, SKG_GEOM_SERSIC = 2 };

@@ -227,6 +227,11 @@ class Engine:
         self._chk(self._lib.skg_whichcell(self.h, SKG_HOST, C.c_int64(len(r)), _vp(r), _vp(m)))
         return m
 
+    def selftest_division(self, n, seed=1):
+        bad = C.c_uint64()
+        self._chk(self._lib.skg_selftest_division(self.h, C.c_uint64(int(n)), C.c_uint64(int(seed)), C.byref(bad)))
+        return bad.value
+
     def stuck_counts(self):
         a = C.c_int64(); b = C.c_int64()
         self._chk(self._lib.skg_stuck_counts(self.h, C.byref(a), C.byref(b)))

@@ -328,6 +328,9 @@ int skg_whichcell(skg_engine* eh, int mem, int64_t n, const double* r, int* m)
     });
 }
 
+int skg_selftest_division(skg_engine* eh, uint64_t n, uint64_t seed, uint64_t* mismatches)
+{ return guarded([&]{ if (!mismatches) throw Error("null output"); *mismatches = runDivisionSelfTest(E(eh), n, seed); }); }
+
 int skg_stuck_counts(skg_engine* eh, int64_t* escaped, int64_t* terminated)
 {
     return guarded([&]{

@@ -47,6 +47,21 @@ __device__ __forceinline__ bool finite3(double a, double b, double c)
     return isfinite(a) && isfinite(b) && isfinite(c);
 }
 
+// a / b for a divisor that stays the same over a whole path (the direction cosines), given rb = 1.0 / b computed
+// once with an IEEE division.  q0 = a*rb is within 2 ulp of a/b; one Newton correction with the exactly computed
+// residual (FMA) makes it a faithful rounding, and by Markstein's theorem (Markstein 1990; Muller et al., Handbook of
+// Floating-Point Arithmetic, 2nd ed., section 4.7) a second one with rb = RN(1/b) yields the correctly rounded
+// quotient RN(a/b) -- bit for bit what the reference's `/` gives, at 5 fp64 operations instead of the ~14-instruction
+// general division sequence with its slow-path branch.  Verified against `/` on the device by skg_selftest_division.
+__device__ __forceinline__ double divInvariant(double a, double b, double rb)
+{
+    double q = a * rb;
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, rb, q);
+    r = __fma_rn(-b, q, a);
+    return __fma_rn(r, rb, q);
+}
+
 // NR::locate_basic_impl, NR.hpp:99-112
 __device__ __forceinline__ int locateBasic(const double* xv, double x, int n)
 {
@@ -89,6 +104,7 @@ __device__ __forceinline__ int cartWhichCell(const CartGrid& g, double x, double
 struct CartWalker
 {
     double x, y, z, kx, ky, kz;
+    double rkx, rky, rkz;       // 1/k per axis (see divInvariant)
     int i, j, k, m;
     bool alive;
 
@@ -144,6 +160,7 @@ struct CartWalker
         j = locateClip(yv, y, Ny + 1);
         k = locateClip(zv, z, Nz + 1);
         m = k + Nz * j + Nz * Ny * i;
+        rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
     }
@@ -155,9 +172,9 @@ struct CartWalker
         const double xE = g.xv[i + (nx ? 0 : 1)];
         const double yE = g.yv[j + (ny ? 0 : 1)];
         const double zE = g.zv[k + (nz ? 0 : 1)];
-        const double dsx = (fabs(kx) > 1e-15) ? (xE - x) / kx : SKG_DBL_MAX;
-        const double dsy = (fabs(ky) > 1e-15) ? (yE - y) / ky : SKG_DBL_MAX;
-        const double dsz = (fabs(kz) > 1e-15) ? (zE - z) / kz : SKG_DBL_MAX;
+        const double dsx = (fabs(kx) > 1e-15) ? divInvariant(xE - x, kx, rkx) : SKG_DBL_MAX;
+        const double dsy = (fabs(ky) > 1e-15) ? divInvariant(yE - y, ky, rky) : SKG_DBL_MAX;
+        const double dsz = (fabs(kz) > 1e-15) ? divInvariant(zE - z, kz, rkz) : SKG_DBL_MAX;
         mseg = m;
         if (dsx <= dsy && dsx <= dsz)
         {
@@ -294,6 +311,7 @@ __device__ __forceinline__ double nextAfterAlong(double v, double k)
 struct TreeWalker
 {
     double x, y, z, kx, ky, kz;
+    double rkx, rky, rkz;
     int node;
     bool alive;
 
@@ -305,6 +323,7 @@ struct TreeWalker
         if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
         node = treeWhichNode(g, x, y, z);
         if (node < 0) return false;
+        rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
     }
@@ -316,9 +335,9 @@ struct TreeWalker
         const double xnext = nx ? b[0] : b[3];
         const double ynext = ny ? b[1] : b[4];
         const double znext = nz ? b[2] : b[5];
-        const double dsx = (fabs(kx) > 1e-15) ? (xnext - x) / kx : SKG_DBL_MAX;
-        const double dsy = (fabs(ky) > 1e-15) ? (ynext - y) / ky : SKG_DBL_MAX;
-        const double dsz = (fabs(kz) > 1e-15) ? (znext - z) / kz : SKG_DBL_MAX;
+        const double dsx = (fabs(kx) > 1e-15) ? divInvariant(xnext - x, kx, rkx) : SKG_DBL_MAX;
+        const double dsy = (fabs(ky) > 1e-15) ? divInvariant(ynext - y, ky, rky) : SKG_DBL_MAX;
+        const double dsz = (fabs(kz) > 1e-15) ? divInvariant(znext - z, kz, rkz) : SKG_DBL_MAX;
         mseg = __ldg(g.cell + node);
         if (g.search != 2)
         {
@@ -489,6 +508,7 @@ __device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, doub
 struct AMeshWalker
 {
     double x, y, z, kx, ky, kz;
+    double rkx, rky, rkz;
     int node;
     bool alive;
 
@@ -500,6 +520,7 @@ struct AMeshWalker
         if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
         node = ameshWhichNode(g, x, y, z);
         if (node < 0) { if (node == -2) atomicAdd(&ctr->errors, 1ull); return false; }
+        rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
     }
@@ -512,9 +533,9 @@ struct AMeshWalker
         const double xnext = nx ? b[0] : b[3];
         const double ynext = ny ? b[1] : b[4];
         const double znext = nz ? b[2] : b[5];
-        const double dsx = (fabs(kx) > 1e-15) ? (xnext - x) / kx : SKG_DBL_MAX;
-        const double dsy = (fabs(ky) > 1e-15) ? (ynext - y) / ky : SKG_DBL_MAX;
-        const double dsz = (fabs(kz) > 1e-15) ? (znext - z) / kz : SKG_DBL_MAX;
+        const double dsx = (fabs(kx) > 1e-15) ? divInvariant(xnext - x, kx, rkx) : SKG_DBL_MAX;
+        const double dsy = (fabs(ky) > 1e-15) ? divInvariant(ynext - y, ky, rky) : SKG_DBL_MAX;
+        const double dsz = (fabs(kz) > 1e-15) ? divInvariant(znext - z, kz, rkz) : SKG_DBL_MAX;
         int wall;
         if (dsx <= dsy && dsx <= dsz) { ds = dsx; wall = nx ? 0 : 1; }
         else if (dsy <= dsx && dsy <= dsz) { ds = dsy; wall = ny ? 2 : 3; }

@@ -81,113 +81,101 @@ __global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ G
 }
 
 // second pass: Segment{m, ds, s, dtau, tau} records = DustGridPath::addSegment (DustGridPath.cpp:46-53, running
-// length s) + DustGridPath::fillOpticalDepth (DustGridPath.hpp:117-129, running tau), through a per-warp
-// shared-memory stage.  A crossing step only parks
-// (m, ds) in a ring of 8 entries per lane; every SKG_PERIOD steps each lane (1) gathers rho for all its parked
-// entries at once (several independent loads in flight instead of one per step) and extends its running s and tau
-// in path order, and (2) the warp writes the finished entries out together: 8 lanes per source lane, only whole
-// 32-byte sectors (4 aligned doubles) except at the two ends of a path, so that L2 never has to merge partial
-// sectors and DRAM sees each byte once.
-#define SKG_RING 8
-#define SKG_RSTRIDE 9       // doubles per lane in a ring (8 + 1 pad against bank conflicts)
+// length s) + DustGridPath::fillOpticalDepth (DustGridPath.hpp:117-129, running tau).
+// A crossing step only parks (m, ds) in a small per-lane ring in shared memory and starts an asynchronous copy of
+// the cell's density into the same ring slot.  Every SKG_PERIOD (= 4) steps the lane turns the entries parked one
+// period earlier (whose densities have landed meanwhile) into records four at a time: s and tau are extended in path order, and each
+// array receives ONE 256-bit store (st.global.v4.f64, a whole 32-byte sector; 128-bit for m) at a 4-aligned
+// record index -- so L2 never merges partial sectors and DRAM sees every byte once.  Only the first and last
+// few records of a path (unaligned ends) are written one by one.
+#define SKG_RING 16
+#define SKG_RSTRIDE 17      // entries per lane in a ring (16 + 1 pad against bank conflicts)
+__device__ __forceinline__ void store4(double* p, double a, double b, double c, double d)
+{ asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory"); }
+__device__ __forceinline__ void store4(int* p, int a, int b, int c, int d)
+{ asm volatile("st.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory"); }
+// asynchronous 8-byte copy global -> shared (LDGSTS): the density of a crossed cell goes straight into the lane's
+// ring without occupying a register or stalling the walker; it is consumed one period later
+__device__ __forceinline__ void asyncCopy8(double* smemDst, const double* src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void asyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void asyncWaitAllButLatest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void asyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 struct RecordJobStaged : RayJobBase
 {
     const int64_t* offsets; const int* ell; int ellStride; Medium med;
     int* m; double* ds; double* s; double* dtau; double* tau;
-    // this lane's rings in shared memory
-    double* rDs; double* rS; double* rDtau; double* rTau; int* rM;
-    // the warp's rings (lane 0), for the cooperative write
-    double* wDs; double* wS; double* wDtau; double* wTau; int* wM;
-    KappaRho kr; int64_t o, f, c; double sacc, tacc; bool optical;
+    double* rDs; double* rRho; int* rM;     // this lane's rings in shared memory
+    KappaRho kr; double kext0; int64_t o, f, ready; double sacc, tacc; bool optical, async;
 
     __device__ __forceinline__ void bind(char* warpBase)
     {
         const int lane = threadIdx.x & 31;
-        wDs = reinterpret_cast<double*>(warpBase); wS = wDs + 32 * SKG_RSTRIDE; wDtau = wS + 32 * SKG_RSTRIDE; wTau = wDtau + 32 * SKG_RSTRIDE;
-        wM = reinterpret_cast<int*>(wTau + 32 * SKG_RSTRIDE);
-        rDs = wDs + lane * SKG_RSTRIDE; rS = wS + lane * SKG_RSTRIDE; rDtau = wDtau + lane * SKG_RSTRIDE; rTau = wTau + lane * SKG_RSTRIDE;
-        rM = wM + lane * SKG_RSTRIDE;
-        o = f = c = 0; sacc = tacc = 0;
+        double* d = reinterpret_cast<double*>(warpBase);
+        rDs = d + lane * SKG_RSTRIDE; rRho = d + (32 + lane) * SKG_RSTRIDE;
+        rM = reinterpret_cast<int*>(d + 64 * SKG_RSTRIDE) + lane * SKG_RSTRIDE;
+        o = f = ready = 0; sacc = tacc = 0; optical = async = false; kext0 = 0;
     }
-    static constexpr size_t bytesPerWarp() { return (4 * sizeof(double) + sizeof(int)) * 32 * SKG_RSTRIDE; }
+    static constexpr size_t bytesPerWarp() { return (2 * sizeof(double) + sizeof(int)) * 32 * SKG_RSTRIDE + 8; }
 
     __device__ __forceinline__ int begin(int i)
     {
         loadRay(i);
-        o = f = c = offsets[i]; sacc = 0; tacc = 0;
+        o = f = ready = offsets[i]; sacc = 0; tacc = 0;
         optical = ell != nullptr;
         int l = optical ? ell[(size_t)i * ellStride] : 0;
         kr = KappaRho{med.rho, med.kext + l, med.Ncomp, med.Nlambda};
+        async = optical && med.Ncomp == 1;
+        kext0 = async ? __ldg(med.kext + l) : 0.0;
         return 1;
     }
-    __device__ __forceinline__ bool outside(double d) { int q = (int)(o & (SKG_RING - 1)); rM[q] = -1; rDs[q] = d; o++; return true; }
-    __device__ __forceinline__ bool segment(int mm, double d) { int q = (int)(o & (SKG_RING - 1)); rM[q] = mm; rDs[q] = d; o++; return true; }
-
-    // running s (DustGridPath::addSegment) and dtau/tau (fillOpticalDepth) for the parked entries [c, o), in path order
-    __device__ __forceinline__ void compute()
+    __device__ __forceinline__ bool outside(double d)
+    { int q = (int)(o & (SKG_RING - 1)); rM[q] = -1; rDs[q] = d; rRho[q] = 0.0; o++; return true; }     // rho(-1,h) = 0 (DustSystem.cpp:918-921)
+    __device__ __forceinline__ bool segment(int mm, double d)
     {
-        while (c < o)
+        int q = (int)(o & (SKG_RING - 1)); rM[q] = mm; rDs[q] = d;
+        if (async) asyncCopy8(rRho + q, med.rho + mm);
+        o++;
+        return true;
+    }
+    // KappaRho (DustSystem.cpp:465-491) of ring entry q: one component -> 0 + kext*rho == kext*rho exactly
+    __device__ __forceinline__ double kapparho(int q, int mm) const { return async ? kext0 * rRho[q] : (optical ? kr(mm) : 0.0); }
+
+    // turns the parked entries [f, upto) into records, in path order
+    __device__ __forceinline__ void emit(int64_t upto)
+    {
+        while (f < upto)
         {
-            double krv[4], dv[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++)
+            const int q = (int)(f & (SKG_RING - 1));
+            if ((f & 3) == 0 && f + 4 <= upto)
             {
-                const bool valid = c + u < o;
-                const int q = (int)((c + u) & (SKG_RING - 1));
-                const int mm = valid ? rM[q] : -1;
-                dv[u] = valid ? rDs[q] : 0.0;
-                krv[u] = (optical && valid) ? kr(mm) : 0.0;         // kapparho(-1) = 0 (DustSystem.cpp:918-921)
+                const int m0 = rM[q], m1 = rM[q + 1], m2 = rM[q + 2], m3 = rM[q + 3];       // q is a multiple of 4: no wrap inside a group
+                const double d0 = rDs[q], d1 = rDs[q + 1], d2 = rDs[q + 2], d3 = rDs[q + 3];
+                const double k0 = kapparho(q, m0), k1 = kapparho(q + 1, m1), k2 = kapparho(q + 2, m2), k3 = kapparho(q + 3, m3);
+                const double s0 = sacc + d0, s1 = s0 + d1, s2 = s1 + d2, s3 = s2 + d3;
+                const double t0 = k0 * d0, t1 = k1 * d1, t2 = k2 * d2, t3 = k3 * d3;
+                const double a0 = tacc + t0, a1 = a0 + t1, a2 = a1 + t2, a3 = a2 + t3;
+                sacc = s3; tacc = a3;
+                store4(m + f, m0, m1, m2, m3);
+                store4(ds + f, d0, d1, d2, d3); store4(s + f, s0, s1, s2, s3);
+                store4(dtau + f, t0, t1, t2, t3); store4(tau + f, a0, a1, a2, a3);
+                f += 4;
             }
-#pragma unroll
-            for (int u = 0; u < 4; u++)
+            else
             {
-                if (c + u < o)
-                {
-                    const int q = (int)((c + u) & (SKG_RING - 1));
-                    sacc += dv[u];
-                    const double dt = krv[u] * dv[u];
-                    tacc += dt;
-                    rS[q] = sacc; rDtau[q] = dt; rTau[q] = tacc;
-                }
+                const int mm = rM[q]; const double d = rDs[q];
+                const double dt = kapparho(q, mm) * d;
+                sacc += d; tacc += dt;
+                m[f] = mm; ds[f] = d; s[f] = sacc; dtau[f] = dt; tau[f] = tacc;
+                f++;
             }
-            c = (o - c > 4) ? c + 4 : o;
         }
     }
-
-    // the warp writes entries [f, e) of every lane that has some: 8 writer lanes per source lane
-    __device__ __forceinline__ void writeOut(int64_t e)
-    {
-        const unsigned FULL = 0xffffffffu;
-        const int lane = threadIdx.x & 31;
-        __syncwarp();
-        unsigned mask = __ballot_sync(FULL, e > f);
-        const int sub = lane >> 3, j = lane & 7;
-        while (mask)
-        {
-            // the next (up to) four source lanes
-            int src = -1; unsigned rem = mask;
-            for (int t = 0; t < 4; t++)
-            {
-                int bit = rem ? __ffs(rem) - 1 : -1;
-                if (t == sub) src = bit;
-                if (rem) rem &= rem - 1;
-            }
-            mask = rem;
-            const int sl = src < 0 ? 0 : src;
-            const int64_t fs = __shfl_sync(FULL, f, sl), es = __shfl_sync(FULL, e, sl);
-            const int64_t idx = fs + j;
-            if (src >= 0 && idx < es)
-            {
-                const int q = (int)(idx & (SKG_RING - 1)) + src * SKG_RSTRIDE;
-                m[idx] = wM[q]; ds[idx] = wDs[q]; s[idx] = wS[q]; dtau[idx] = wDtau[q]; tau[idx] = wTau[q];
-            }
-        }
-        if (e > f) f = e;
-        __syncwarp();
-    }
-    __device__ __forceinline__ void periodic() { compute(); writeOut(o & ~(int64_t)3); }
-    __device__ __forceinline__ void finish() { compute(); }
-    __device__ __forceinline__ void collective(bool fin) { writeOut(fin ? o : f); }
+    // entries parked before the previous call have their density in the ring by now
+    __device__ __forceinline__ void periodic() { asyncCommit(); asyncWaitAllButLatest(); emit(ready & ~(int64_t)3); ready = o; }
+    __device__ __forceinline__ void finish() { asyncCommit(); asyncWaitAll(); emit(o); ready = o; }
+    __device__ __forceinline__ void collective(bool) {}
 };
 
 template<int KIND>
@@ -312,6 +300,46 @@ void launchWhichCell(Engine& e, int64_t n, const double* d_r, int* d_m)
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     SKG_DISPATCH(e, (whichCellKernel<K><<<c.blocks, 128, 0, e.stream>>>(G, e.ctr(), n, d_r, d_m)));
     e.launches++; SKG_CUDA(cudaGetLastError());
+}
+
+// compares divInvariant with the IEEE division on pseudo-random operands spanning the magnitudes the walkers see
+// (numerators: differences of coordinates down to a few ulp, up to the domain size; divisors: direction cosines down
+// to the 1e-15 cut) plus adversarial mantissas; counts the quotients that differ in any bit
+__global__ void divisionSelfTest(unsigned long long n, unsigned long long seed, unsigned long long* mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x)
+    {
+        // splitmix64
+        unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (i + 1);
+        auto next = [&]() { z += 0x9E3779B97F4A7C15ull; unsigned long long t = z; t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull; t = (t ^ (t >> 27)) * 0x94D049BB133111EBull; return t ^ (t >> 31); };
+        unsigned long long ma = next(), mb = next(), ex = next();
+        // mantissas: random, or with long runs of ones / zeros (the hard cases of division rounding)
+        if ((ex & 7) == 0) ma |= 0x000FFFFFFFFFF000ull; if ((ex & 7) == 1) mb |= 0x000FFFFFFFFFFF00ull;
+        if ((ex & 7) == 2) ma &= 0xFFF0000000000FFFull; if ((ex & 7) == 3) mb &= 0xFFF00000000000FFull;
+        int ea = (int)((ex >> 8) % 140) - 70;        // |a| in 2^-70 .. 2^70 times the scale below
+        int eb = -(int)((ex >> 20) % 50);            // |b| in 2^-50 .. 1
+        double a = __longlong_as_double((long long)((ma & 0x800FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+        double b = __longlong_as_double((long long)((mb & 0x800FFFFFFFFFFFFFull) | 0x3FF0000000000000ull));
+        a = ldexp(a, ea) * 3.0e16; b = ldexp(b, eb);
+        if (fabs(b) <= 1e-15) b = b < 0 ? -1e-15 * 1.0000001 : 1e-15 * 1.0000001;
+        double rb = 1.0 / b;
+        double q1 = a / b, q2 = divInvariant(a, b, rb);
+        if (__double_as_longlong(q1) != __double_as_longlong(q2)) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+unsigned long long runDivisionSelfTest(Engine& e, unsigned long long n, unsigned long long seed)
+{
+    e.scratchWork.ensure(sizeof(unsigned long long));
+    SKG_CUDA(cudaMemsetAsync(e.scratchWork.p, 0, sizeof(unsigned long long), e.stream));
+    divisionSelfTest<<<e.smCount * 16, 256, 0, e.stream>>>(n, seed, e.scratchWork.as<unsigned long long>());
+    e.launches++; SKG_CUDA(cudaGetLastError());
+    unsigned long long bad = 0;
+    SKG_CUDA(cudaMemcpyAsync(&bad, e.scratchWork.p, sizeof(bad), cudaMemcpyDeviceToHost, e.stream));
+    e.sync();
+    return bad;
 }
 
 __global__ void setLastOffset(const int* counts, int64_t* offsets, int64_t n)

@@ -92,3 +92,10 @@ def test_full_size_properties(engine):
     # consecutive cells differ by one step along exactly one axis
     m = got["m"].astype(np.int64); dm = np.abs(np.diff(m)); inner = np.ones(len(m) - 1, bool); inner[last[:-1]] = False
     assert np.isin(dm[inner], [1, n, n * n]).all()
+
+
+def test_invariant_divisor_division_is_ieee_exact(engine):
+    """the walkers divide by the (path-constant) direction cosines through a reciprocal + two FMA corrections;
+    the result must equal the IEEE quotient bit for bit -- 2^33 operand pairs including adversarial mantissas"""
+    assert engine.selftest_division(1 << 33, seed=12345) == 0
+    assert engine.selftest_division(1 << 30, seed=777) == 0
