@@ -157,13 +157,11 @@ def traversal_leg(engine, torch, ext, ncomp, nrays, reps=5, warm=3):
     off = torch.zeros(nrays + 1, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()
     total = engine.path_count_device(nrays, r.data_ptr(), k.data_ptr(), off.data_ptr())
-    m = torch.empty(total, dtype=torch.int32, device="cuda")
-    outs = [torch.empty(total, dtype=torch.float64, device="cuda") for _ in range(4)]
+    seg = torch.empty(total * 5, dtype=torch.float64, device="cuda")       # 40-byte DustGridPath::Segment records
     torch.cuda.synchronize()
 
     def fill():
-        engine.path_fill_device(nrays, r.data_ptr(), k.data_ptr(), ell.data_ptr(), 0, off.data_ptr(), m.data_ptr(),
-                                *[o.data_ptr() for o in outs])
+        engine.path_fill_device(nrays, r.data_ptr(), k.data_ptr(), ell.data_ptr(), 0, off.data_ptr(), seg.data_ptr())
     for _ in range(warm):
         fill()
     times = []

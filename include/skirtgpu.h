@@ -77,13 +77,17 @@ int skg_medium(skg_engine* e, int Ncells, int Ncomp, int Nlambda, const double* 
 /* ---- deterministic geometry: batched DustGrid::path() + DustGridPath::fillOpticalDepth() ------------ */
 /* Replaces DustSystem::fillOpticalDepth (DustSystem.cpp:959-980) for n rays at once.
  * Step 1 counts the segments of every ray and returns CSR offsets (offsets[n+1], int64) and the total;
- * step 2 fills m/ds/s/dtau/tau (DustGridPath::Segment, DustGridPath.hpp:161-167) for the same rays.
+ * step 2 fills segments[offsets[i] .. offsets[i+1]) for the same rays (device pointers must be 32-byte aligned).
  * ell[n] may be NULL (geometry only: dtau = tau = 0) or point to ONE value when ell_stride == 0. */
 #define SKG_HOST 0
 #define SKG_DEVICE 1
+/* one path segment: the reference's DustGridPath::Segment { int m; double ds, s, dtau, tau; } (DustGridPath.hpp:161-167),
+ * same 40-byte layout (4 bytes of padding after m), so that a batch of paths can be copied straight into
+ * DustGridPath::_v vectors */
+typedef struct skg_segment { int32_t m; int32_t reserved; double ds, s, dtau, tau; } skg_segment;
 int skg_path_count(skg_engine* e, int mem, int64_t n, const double* r, const double* k, int64_t* offsets, int64_t* total);
 int skg_path_fill(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
-                  const int64_t* offsets, int* m, double* ds, double* s, double* dtau, double* tau);
+                  const int64_t* offsets, skg_segment* segments);
 /* DustSystem::opticaldepth(pp, distance) (DustSystem.cpp:984-1000); distance may be NULL (= DBL_MAX) */
 int skg_opticaldepth(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
                      const double* distance, double* tau);

@@ -14,6 +14,8 @@ SKG_HOST, SKG_DEVICE = 0, 1
 GEOM_EXPDISK, GEOM_SERSIC = 1, 2
 INSTR_FRAME, INSTR_SED, INSTR_SIMPLE = 1, 2, 3
 PHASE_STELLAR, PHASE_DUST_SELFABS, PHASE_DUST_EMISSION = 0, 1, 2
+# skg_segment == DustGridPath::Segment (DustGridPath.hpp:161-167)
+SEGMENT = np.dtype([("m", np.int32), ("reserved", np.int32), ("ds", np.float64), ("s", np.float64), ("dtau", np.float64), ("tau", np.float64)])
 
 
 class EngineError(RuntimeError):
@@ -193,26 +195,25 @@ class Engine:
         r = _f64(r).reshape(-1, 3); k = _f64(k).reshape(-1, 3); n = len(r)
         off = np.zeros(n + 1, np.int64); total = C.c_int64()
         self._chk(self._lib.skg_path_count(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), _vp(off), C.byref(total)))
-        t = max(total.value, 1)
-        m = np.zeros(t, np.int32); ds = np.zeros(t); s = np.zeros(t); dtau = np.zeros(t); tau = np.zeros(t)
+        seg = np.zeros(max(total.value, 1), dtype=SEGMENT)
         ellp, stride = None, 0
         if ell is not None:
             ella = _i32(np.atleast_1d(ell)); ellp = _vp(ella); stride = 1 if len(ella) == n and n > 1 else 0
             if len(ella) not in (1, n):
                 raise EngineError("ell must be a scalar or have one entry per ray")
-        self._chk(self._lib.skg_path_fill(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), ellp, stride, _vp(off),
-                                          _vp(m), _vp(ds), _vp(s), _vp(dtau), _vp(tau)))
-        tt = total.value
-        return dict(offsets=off, m=m[:tt], ds=ds[:tt], s=s[:tt], dtau=dtau[:tt], tau=tau[:tt])
+        self._chk(self._lib.skg_path_fill(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), ellp, stride, _vp(off), _vp(seg)))
+        seg = seg[:total.value]
+        return dict(offsets=off, **{f: np.ascontiguousarray(seg[f]) for f in ("m", "ds", "s", "dtau", "tau")})
 
     def path_count_device(self, n, d_r, d_k, d_offsets):
         total = C.c_int64()
         self._chk(self._lib.skg_path_count(self.h, SKG_DEVICE, C.c_int64(n), _vp(d_r), _vp(d_k), _vp(d_offsets), C.byref(total)))
         return total.value
 
-    def path_fill_device(self, n, d_r, d_k, d_ell, ell_stride, d_offsets, d_m, d_ds, d_s, d_dtau, d_tau):
+    def path_fill_device(self, n, d_r, d_k, d_ell, ell_stride, d_offsets, d_segments):
+        """d_segments: device array of total x 40-byte skg_segment records (32-byte aligned)"""
         self._chk(self._lib.skg_path_fill(self.h, SKG_DEVICE, C.c_int64(n), _vp(d_r), _vp(d_k), _vp(d_ell), int(ell_stride),
-                                          _vp(d_offsets), _vp(d_m), _vp(d_ds), _vp(d_s), _vp(d_dtau), _vp(d_tau)))
+                                          _vp(d_offsets), _vp(d_segments)))
 
     def opticaldepth(self, r, k, ell, distance=None):
         r = _f64(r).reshape(-1, 3); k = _f64(k).reshape(-1, 3); n = len(r)

@@ -259,7 +259,7 @@ int skg_path_count(skg_engine* eh, int mem, int64_t n, const double* r, const do
 }
 
 int skg_path_fill(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
-                  const int64_t* offsets, int* m, double* ds, double* s, double* dtau, double* tau)
+                  const int64_t* offsets, skg_segment* segments)
 {
     return guarded([&]{
         Engine& e = E(eh);
@@ -267,29 +267,24 @@ int skg_path_fill(skg_engine* eh, int mem, int64_t n, const double* r, const dou
         if (ellStride != 0 && ellStride != 1) throw Error("ell_stride must be 0 or 1");
         if (mem == SKG_DEVICE)
         {
-            if (!m || !ds || !s || !dtau || !tau) throw Error("skg_path_fill: null output");
-            launchPathFill(e, n, r, k, ell, ellStride, offsets, m, ds, s, dtau, tau);
+            if (!segments) throw Error("skg_path_fill: null output");
+            if (reinterpret_cast<uintptr_t>(segments) & 31) throw Error("skg_path_fill: the segment array must be 32-byte aligned");
+            launchPathFill(e, n, r, k, ell, ellStride, offsets, segments);
             e.sync();
             return;
         }
         int64_t total = n > 0 ? offsets[n] : 0;
-        if (total > 0 && (!m || !ds || !s || !dtau || !tau)) throw Error("skg_path_fill: null output");
+        if (total > 0 && !segments) throw Error("skg_path_fill: null output");
         e.scratchR.upload(r, sizeof(double) * 3 * (size_t)n, e.stream); e.scratchK.upload(k, sizeof(double) * 3 * (size_t)n, e.stream);
         e.scratchOffsets.upload(offsets, sizeof(int64_t) * ((size_t)n + 1), e.stream);
         const int* d_ell = nullptr;
-        if (ell) { e.scratchEll.upload(ell, sizeof(int) * (size_t)(ellStride ? n : 1), e.stream); d_ell = e.scratchEll.as<int>(); }
         if (ell) for (int64_t i = 0; i < (ellStride ? n : 1); i++) if (ell[i] < 0 || ell[i] >= e.med.Nlambda) throw Error("wavelength index out of range");
+        if (ell) { e.scratchEll.upload(ell, sizeof(int) * (size_t)(ellStride ? n : 1), e.stream); d_ell = e.scratchEll.as<int>(); }
         size_t t = (size_t)std::max<int64_t>(total, 1);
-        e.scratchM.ensure(sizeof(int) * t);
-        for (int j = 0; j < 4; j++) e.scratchOut[j].ensure(sizeof(double) * t);
+        e.scratchOut[0].ensure(sizeof(skg_segment) * t);
         launchPathFill(e, n, e.scratchR.as<double>(), e.scratchK.as<double>(), d_ell, ellStride, e.scratchOffsets.as<int64_t>(),
-                       e.scratchM.as<int>(), e.scratchOut[0].as<double>(), e.scratchOut[1].as<double>(), e.scratchOut[2].as<double>(), e.scratchOut[3].as<double>());
-        if (total > 0)
-        {
-            SKG_CUDA(cudaMemcpyAsync(m, e.scratchM.p, sizeof(int) * total, cudaMemcpyDeviceToHost, e.stream));
-            double* outs[4] = {ds, s, dtau, tau};
-            for (int j = 0; j < 4; j++) SKG_CUDA(cudaMemcpyAsync(outs[j], e.scratchOut[j].p, sizeof(double) * total, cudaMemcpyDeviceToHost, e.stream));
-        }
+                       e.scratchOut[0].as<skg_segment>());
+        if (total > 0) SKG_CUDA(cudaMemcpyAsync(segments, e.scratchOut[0].p, sizeof(skg_segment) * total, cudaMemcpyDeviceToHost, e.stream));
         e.sync();
     });
 }

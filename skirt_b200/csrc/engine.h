@@ -91,7 +91,7 @@ struct Engine
 // kernels launchers (path_kernels.cu)
 void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k, int* d_counts);
 void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
-                    const int64_t* d_offsets, int* d_m, double* d_ds, double* d_s, double* d_dtau, double* d_tau);
+                    const int64_t* d_offsets, skg_segment* d_segments);
 void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
                         const double* d_dist, double* d_tau);
 void launchWhichCell(Engine& e, int64_t n, const double* d_r, int* d_m);

@@ -1,6 +1,7 @@
 // Batched DustGrid::path() kernels: count pass, CSR fill pass, optical depth, whichcell.
 // One ray per thread in a grid-stride loop; the Cartesian borders (3 x (N+1) doubles, 2.4 KB at 100^3)
 // are staged in shared memory once per CTA.
+#include <cstdlib>
 #include <cub/device/device_scan.cuh>
 #include "engine.h"
 #include "geom.cuh"
@@ -88,12 +89,11 @@ __global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ G
 // array receives ONE 256-bit store (st.global.v4.f64, a whole 32-byte sector; 128-bit for m) at a 4-aligned
 // record index -- so L2 never merges partial sectors and DRAM sees every byte once.  Only the first and last
 // few records of a path (unaligned ends) are written one by one.
-#define SKG_RING 16
-#define SKG_RSTRIDE 17      // entries per lane in a ring (16 + 1 pad against bank conflicts)
+#define SKG_RING 12         // three groups of four: at most 11 entries are parked at any time
+#define SKG_RSTRIDE 13      // entries per lane in a ring (12 + 1 pad against bank conflicts)
 __device__ __forceinline__ void store4(double* p, double a, double b, double c, double d)
 { asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory"); }
-__device__ __forceinline__ void store4(int* p, int a, int b, int c, int d)
-{ asm volatile("st.global.v4.s32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory"); }
+__device__ __forceinline__ double cellWord(int m) { return __longlong_as_double((long long)(unsigned)m); }    // {int m; int reserved = 0}
 // asynchronous 8-byte copy global -> shared (LDGSTS): the density of a crossed cell goes straight into the lane's
 // ring without occupying a register or stalling the walker; it is consumed one period later
 __device__ __forceinline__ void asyncCopy8(double* smemDst, const double* src)
@@ -105,9 +105,10 @@ __device__ __forceinline__ void asyncWaitAll() { asm volatile("cp.async.wait_gro
 struct RecordJobStaged : RayJobBase
 {
     const int64_t* offsets; const int* ell; int ellStride; Medium med;
-    int* m; double* ds; double* s; double* dtau; double* tau;
+    skg_segment* seg;
     double* rDs; double* rRho; int* rM;     // this lane's rings in shared memory
     KappaRho kr; double kext0; int64_t o, f, ready; double sacc, tacc; bool optical, async;
+    int qo, qf;                             // ring positions of record indices o and f (index mod 4 is preserved)
 
     __device__ __forceinline__ void bind(char* warpBase)
     {
@@ -115,7 +116,7 @@ struct RecordJobStaged : RayJobBase
         double* d = reinterpret_cast<double*>(warpBase);
         rDs = d + lane * SKG_RSTRIDE; rRho = d + (32 + lane) * SKG_RSTRIDE;
         rM = reinterpret_cast<int*>(d + 64 * SKG_RSTRIDE) + lane * SKG_RSTRIDE;
-        o = f = ready = 0; sacc = tacc = 0; optical = async = false; kext0 = 0;
+        o = f = ready = 0; sacc = tacc = 0; optical = async = false; kext0 = 0; qo = qf = 0;
     }
     static constexpr size_t bytesPerWarp() { return (2 * sizeof(double) + sizeof(int)) * 32 * SKG_RSTRIDE + 8; }
 
@@ -123,6 +124,7 @@ struct RecordJobStaged : RayJobBase
     {
         loadRay(i);
         o = f = ready = offsets[i]; sacc = 0; tacc = 0;
+        qo = qf = (int)(o & 3);
         optical = ell != nullptr;
         int l = optical ? ell[(size_t)i * ellStride] : 0;
         kr = KappaRho{med.rho, med.kext + l, med.Ncomp, med.Nlambda};
@@ -131,12 +133,12 @@ struct RecordJobStaged : RayJobBase
         return 1;
     }
     __device__ __forceinline__ bool outside(double d)
-    { int q = (int)(o & (SKG_RING - 1)); rM[q] = -1; rDs[q] = d; rRho[q] = 0.0; o++; return true; }     // rho(-1,h) = 0 (DustSystem.cpp:918-921)
+    { int q = qo; rM[q] = -1; rDs[q] = d; rRho[q] = 0.0; o++; qo = q + 1 == SKG_RING ? 0 : q + 1; return true; }     // rho(-1,h) = 0 (DustSystem.cpp:918-921)
     __device__ __forceinline__ bool segment(int mm, double d)
     {
-        int q = (int)(o & (SKG_RING - 1)); rM[q] = mm; rDs[q] = d;
+        int q = qo; rM[q] = mm; rDs[q] = d;
         if (async) asyncCopy8(rRho + q, med.rho + mm);
-        o++;
+        o++; qo = q + 1 == SKG_RING ? 0 : q + 1;
         return true;
     }
     // KappaRho (DustSystem.cpp:465-491) of ring entry q: one component -> 0 + kext*rho == kext*rho exactly
@@ -147,7 +149,7 @@ struct RecordJobStaged : RayJobBase
     {
         while (f < upto)
         {
-            const int q = (int)(f & (SKG_RING - 1));
+            const int q = qf;
             if ((f & 3) == 0 && f + 4 <= upto)
             {
                 const int m0 = rM[q], m1 = rM[q + 1], m2 = rM[q + 2], m3 = rM[q + 3];       // q is a multiple of 4: no wrap inside a group
@@ -157,18 +159,22 @@ struct RecordJobStaged : RayJobBase
                 const double t0 = k0 * d0, t1 = k1 * d1, t2 = k2 * d2, t3 = k3 * d3;
                 const double a0 = tacc + t0, a1 = a0 + t1, a2 = a1 + t2, a3 = a2 + t3;
                 sacc = s3; tacc = a3;
-                store4(m + f, m0, m1, m2, m3);
-                store4(ds + f, d0, d1, d2, d3); store4(s + f, s0, s1, s2, s3);
-                store4(dtau + f, t0, t1, t2, t3); store4(tau + f, a0, a1, a2, a3);
-                f += 4;
+                double* out = reinterpret_cast<double*>(seg + f);      // 4 records x 5 words
+                store4(out, cellWord(m0), d0, s0, t0);
+                store4(out + 4, a0, cellWord(m1), d1, s1);
+                store4(out + 8, t1, a1, cellWord(m2), d2);
+                store4(out + 12, s2, t2, a2, cellWord(m3));
+                store4(out + 16, d3, s3, t3, a3);
+                f += 4; qf = q + 4 == SKG_RING ? 0 : q + 4;
             }
             else
             {
                 const int mm = rM[q]; const double d = rDs[q];
                 const double dt = kapparho(q, mm) * d;
                 sacc += d; tacc += dt;
-                m[f] = mm; ds[f] = d; s[f] = sacc; dtau[f] = dt; tau[f] = tacc;
-                f++;
+                double* out = reinterpret_cast<double*>(seg + f);
+                out[0] = cellWord(mm); out[1] = d; out[2] = sacc; out[3] = dt; out[4] = tacc;
+                f++; qf = q + 1 == SKG_RING ? 0 : q + 1;
             }
         }
     }
@@ -182,15 +188,14 @@ template<int KIND>
 __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem,
                                                       int n, const double* __restrict__ r, const double* __restrict__ k,
                                                       const int* __restrict__ ell, int ellStride, const int64_t* __restrict__ offsets,
-                                                      int* __restrict__ m, double* __restrict__ ds, double* __restrict__ s,
-                                                      double* __restrict__ dtau, double* __restrict__ tau, int* work)
+                                                      skg_segment* __restrict__ segments, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     size_t skip = (KIND == GRID_CART && cartSmem) ? (size_t)(G.cart.Nx + G.cart.Ny + G.cart.Nz + 3) : 0;
     RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
-    job.m = m; job.ds = ds; job.s = s; job.dtau = dtau; job.tau = tau;
+    job.seg = segments;
     job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarp());
     runJobs<KIND>(G, cart, ctr, job, n, work);
 }
@@ -263,12 +268,13 @@ void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k,
 }
 
 void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
-                    const int64_t* d_offsets, int* d_m, double* d_ds, double* d_s, double* d_dtau, double* d_tau)
+                    const int64_t* d_offsets, skg_segment* d_segments)
 {
     if (n <= 0) return;
     if (d_ell && !e.med.rho) throw Error("skg_path_fill with wavelength indices needs skg_medium first");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     c.smem += 4 * RecordJobStaged::bytesPerWarp();
+    if (const char* pad = getenv("SKG_FILL_SMEM_PAD")) c.smem += (size_t)atoi(pad);      // experiment: limits resident CTAs
     static bool attr = false;
     if (!attr)
     {
@@ -279,7 +285,7 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
         attr = true;
     }
     SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, (int)n, d_r, d_k, d_ell, ellStride,
-                                                                                d_offsets, d_m, d_ds, d_s, d_dtau, d_tau, c.work)));
+                                                                                d_offsets, d_segments, c.work)));
     e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
