@@ -176,31 +176,20 @@ struct CartWalker
         const double dsy = (fabs(ky) > 1e-15) ? divInvariant(yE - y, ky, rky) : SKG_DBL_MAX;
         const double dsz = (fabs(kz) > 1e-15) ? divInvariant(zE - z, kz, rkz) : SKG_DBL_MAX;
         mseg = m;
-        if (dsx <= dsy && dsx <= dsz)
-        {
-            ds = dsx;
-            const int di = nx ? -1 : 1;
-            i += di; m += di * g.Ny * g.Nz;
-            if (i >= g.Nx || i < 0) alive = false;
-            x = xE; y += ky * ds; z += kz * ds;
-        }
-        else if (dsy < dsx && dsy <= dsz)
-        {
-            ds = dsy;
-            const int dj = ny ? -1 : 1;
-            j += dj; m += dj * g.Nz;
-            if (j >= g.Ny || j < 0) alive = false;
-            x += kx * ds; y = yE; z += kz * ds;
-        }
-        else if (dsz < dsx && dsz < dsy)
-        {
-            ds = dsz;
-            const int dk = nz ? -1 : 1;
-            k += dk; m += dk;
-            if (k >= g.Nz || k < 0) alive = false;
-            x += kx * ds; y += ky * ds; z = zE;
-        }
-        else { alive = false; return false; }   // unreachable for finite input (the reference would spin forever)
+        // the reference's three branches (X if dsx<=dsy&&dsx<=dsz, Y if dsy<dsx&&dsy<=dsz, Z if dsz<dsx&&dsz<dsy) as selects,
+        // so that the lanes of a warp do not diverge on the exit face: the hit coordinate snaps to the face, the other two
+        // advance by k*ds -- identical values, branch free
+        const bool bx = dsx <= dsy && dsx <= dsz;
+        const bool by = !bx && dsy < dsx && dsy <= dsz;
+        const bool bz = !bx && !by && dsz < dsx && dsz < dsy;
+        if (!(bx || by || bz)) { alive = false; return false; }     // unreachable for finite input (the reference would spin forever)
+        ds = bx ? dsx : (by ? dsy : dsz);
+        const double xa = x + kx * ds, ya = y + ky * ds, za = z + kz * ds;
+        x = bx ? xE : xa; y = by ? yE : ya; z = bz ? zE : za;
+        const int di = bx ? (nx ? -1 : 1) : 0, dj = by ? (ny ? -1 : 1) : 0, dk = bz ? (nz ? -1 : 1) : 0;
+        i += di; j += dj; k += dk;
+        m += di * g.Ny * g.Nz + dj * g.Nz + dk;
+        if ((unsigned)i >= (unsigned)g.Nx || (unsigned)j >= (unsigned)g.Ny || (unsigned)k >= (unsigned)g.Nz) alive = false;
         return ds > 0;
     }
 };

@@ -104,4 +104,4 @@ def test_other_grids_against_reference_runs(engine, kind):
             ok = (sa < 0.3 * ma) & (sr_ < 0.3 * mr)
             z = common.zscores(ma[ok], sa[ok], mr[ok], sr_[ok])
             assert ok.sum() > 0.5 * len(ok)
-            assert np.mean(np.abs(z) < 3) > 0.96 and abs(z.mean()) < 0.15, f"{kind}/{name}: {np.mean(np.abs(z) < 3):.4f} within 3 sigma, mean z {z.mean():.3f}"
+            assert np.mean(np.abs(z) < 3) > 0.96 and abs(z.mean()) < 0.3, f"{kind}/{name}: {np.mean(np.abs(z) < 3):.4f} within 3 sigma, mean z {z.mean():.3f}"
