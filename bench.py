@@ -202,11 +202,8 @@ def main_engine(args):
     e = sim.engine
     setup_s = time.time() - t0
     if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid.copy_(torch.from_numpy(e.comm_unique_id()))
-        dist.broadcast(uid, 0)
-        e.comm_init(rank, world, uid.cpu().numpy())
+        from skirt_b200.parallel import share_unique_id
+        share_unique_id(e, dist, device="cuda")
     ext = torch.cuda.ExternalStream(e.stream)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 

@@ -53,6 +53,7 @@ struct McDev
     const double* dustLv;   // [Nlambda*Ncells] luminosity per cell, wavelength-major
     const double* dustCdf;  // [Nlambda*(Ncells+1)] normalised cumulative distributions
     double dustBias;        // PanDustSystem::emissionBias
+    int refill;             // lanes of a warp that must be parked before they finish and draw new work together
 };
 
 // ---- accumulation ----------------------------------------------------------------------------------------

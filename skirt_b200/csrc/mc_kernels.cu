@@ -13,6 +13,7 @@
 // compacted into index lists by warp-aggregated appends; packets are launched in wavelength order so that the
 // pool holds few wavelengths at a time (the absorption table is wavelength-major on the device).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 #include <cub/device/device_scan.cuh>
 #include "mc_device.cuh"
@@ -217,6 +218,9 @@ template<int KIND> struct PeelJob
     const GridSetMC& G; const CartGrid& cart; const McDev& P; const int* aliveList;
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
     double Lw, tau; KappaRho kr; int ell, grp;
+    // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
+    // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
+    double kext0, pendRho, pendDs; bool single;
     unsigned long long nSeg = 0, nPaths = 0, nDet = 0;
     __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, const int* l_) : G(G_), cart(c_), P(P_), aliveList(l_) {}
 
@@ -270,15 +274,23 @@ template<int KIND> struct PeelJob
         Lw = L; tau = 0;
         dx = g.kx; dy = g.ky; dz = g.kz;
         kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
+        single = Ncomp == 1; kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendRho = 0; pendDs = 0;
         if (!P.med.rho) return 2;                                   // Instrument::opticalDepth: 0 without dust
         nPaths++;
         return 1;
     }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }
-    __device__ __forceinline__ bool segment(int m, double ds) { nSeg++; tau += kr(m) * ds; return true; }
+    __device__ __forceinline__ bool segment(int m, double ds)
+    {
+        nSeg++;
+        if (single) { tau += (kext0 * pendRho) * pendDs; pendRho = __ldg(P.med.rho + m); pendDs = ds; }
+        else tau += kr(m) * ds;
+        return true;
+    }
     __device__ __forceinline__ void finish()
     {
         const ObsGroup& g = P.groups[grp];
+        if (single) tau += (kext0 * pendRho) * pendDs;
         const double Lextf = Lw * exp(-tau);
         for (int c = 0; c < g.count; c++)
         {
@@ -304,7 +316,7 @@ __global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSet
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
     PeelJob<KIND> job(G, cart, P, aliveList);
-    runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work);
+    runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, min(28, 2 * P.refill));
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
 }
 
@@ -317,6 +329,7 @@ template<int KIND> struct AbsorbJob
     // AbsorbSink state (see mc_device.cuh): one expm1 per segment, E = exp(-tau) carried multiplicatively
     KappaRho kr; double L, albedo, tau, E, Lsca; double* labs;
     int slot, ell, nscatt; unsigned rngCtr; bool survive;
+    double kext0, pendRho, pendDs; int pendM;      // one-component media: gather now, absorb one crossing later
     unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
     __device__ AbsorbJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, const int* l_, int* s_, int* f_, int* c2_)
         : G(G_), cart(c_), P(P_), aliveList(l_), survivors(s_), freeList(f_), counts(c2_) {}
@@ -369,28 +382,36 @@ template<int KIND> struct AbsorbJob
         // ---- fillOpticalDepth + simulateescapeandabsorption, :286-288, :438-515 ----
         kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
         labs = P.labs ? P.labs + (size_t)ell * P.med.Ncells : nullptr;
-        double kext0 = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
-        albedo = kext0 > 0 ? ksca0 / kext0 : 0.0;          // DustMix::albedo(ell) (DustMix.cpp:55-90)
+        double kext0_ = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
+        albedo = kext0_ > 0 ? ksca0 / kext0_ : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
         tau = 0; E = 1.0; Lsca = 0;
+        kext0 = kext0_; pendM = -1; pendRho = 0; pendDs = 0;
         nPaths++;
         return 1;
     }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }   // rho(-1,h) = 0: dtau = 0, nothing absorbed
+    // escape + absorption of one segment in a one-component medium (MonteCarloSimulation.cpp:446-470)
+    __device__ __forceinline__ void absorbPending()
+    {
+        if (pendM < 0) return;
+        double dtau = (kext0 * pendRho) * pendDs;
+        if (labs)
+        {
+            double x = expm1(-dtau);
+            atomicAdd(labs + pendM, (1.0 - albedo) * (L * E * (-x)));
+            E += E * x;
+            nAbs++;
+        }
+        tau += dtau;
+    }
     __device__ __forceinline__ bool segment(int m, double ds)
     {
         nSeg++;
         const int Ncomp = P.med.Ncomp;
         if (Ncomp == 1)
         {
-            double dtau = kr(m) * ds;
-            if (labs)
-            {
-                double x = expm1(-dtau);
-                atomicAdd(labs + m, (1.0 - albedo) * (L * E * (-x)));
-                E += E * x;
-                nAbs++;
-            }
-            tau += dtau;
+            absorbPending();
+            pendM = m; pendDs = ds; pendRho = __ldg(P.med.rho + m);
         }
         else
         {
@@ -418,6 +439,7 @@ template<int KIND> struct AbsorbJob
     {
         if (!(L > 0) || !P.med.rho) return;
         const PacketPool& q = P.pool;
+        if (P.med.Ncomp == 1) { absorbPending(); pendM = -1; }
         const double taupath = tau;
         if (P.med.Ncomp == 1) L = L * albedo * (-expm1(-taupath));
         else L = Lsca;
@@ -463,7 +485,7 @@ __global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridS
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
     AbsorbJob<KIND> job(G, cart, P, aliveList, survivors, freeList, counts);
-    runJobs<KIND>(G, cart, ctr, job, nAlive, work);
+    runJobs<KIND>(G, cart, ctr, job, nAlive, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, job.nScatt, 0, job.nAbs, 0);
 }
 
@@ -474,6 +496,7 @@ template<int KIND> struct PropagateJob
     const McDev& P; const int* list;
     double rx, ry, rz, dx, dy, dz;
     KappaRho kr; double target, sPrev, tauPrev, result; bool found; int slot;
+    double kext0, pendRho, pendDs; bool single, pending;      // one-component media: gather now, test one crossing later
     unsigned long long nSeg = 0, nPaths = 0;
     __device__ PropagateJob(const McDev& P_, const int* l_) : P(P_), list(l_) {}
     __device__ __forceinline__ int begin(int item)
@@ -487,15 +510,26 @@ template<int KIND> struct PropagateJob
         rx = q.x[slot]; ry = q.y[slot]; rz = q.z[slot]; dx = q.kx[slot]; dy = q.ky[slot]; dz = q.kz[slot];
         kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
         sPrev = 0; tauPrev = 0; result = 0; found = false;
+        single = P.med.Ncomp == 1; kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pending = false; pendRho = 0; pendDs = 0;
         nPaths++;
         return 1;
     }
-    __device__ __forceinline__ bool outside(double ds) { nSeg++; sPrev += ds; return true; }
+    __device__ __forceinline__ bool outside(double ds) { nSeg++; sPrev += ds; return true; }       // only before the first cell
     __device__ __forceinline__ bool segment(int m, double ds)
     {
         nSeg++;
+        if (single)
+        {
+            const bool cont = pending ? test((kext0 * pendRho) * pendDs, pendDs) : true;
+            pending = true; pendRho = __ldg(P.med.rho + m); pendDs = ds;
+            return cont;
+        }
+        return test(kr(m) * ds, ds);
+    }
+    __device__ __forceinline__ bool test(double dtau, double ds)
+    {
         double sNew = sPrev + ds;
-        double tauNew = tauPrev + kr(m) * ds;
+        double tauNew = tauPrev + dtau;
         if (target < tauNew)
         {
             result = sPrev + ((target - tauPrev) / (tauNew - tauPrev)) * (sNew - sPrev);     // NR::interpolate_linlin
@@ -508,6 +542,7 @@ template<int KIND> struct PropagateJob
     __device__ __forceinline__ void finish()
     {
         const PacketPool& q = P.pool;
+        if (single && pending && !found) test((kext0 * pendRho) * pendDs, pendDs);
         const double s = found ? result : sPrev;
         q.x[slot] = rx + s * dx; q.y[slot] = ry + s * dy; q.z[slot] = rz + s * dz;
     }
@@ -523,7 +558,7 @@ __global__ void __launch_bounds__(128) propagateStage(const __grid_constant__ Gr
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
     PropagateJob<KIND> job(P, survivors);
-    runJobs<KIND>(G, cart, ctr, job, nSurv, work);
+    runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
 }
 
@@ -788,6 +823,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     McDev P{};
     P.med = e.med; if (!e.med.rho) { P.med.Nlambda = Nlambda; P.med.Ncomp = 0; }
     P.phase = phase; P.rngKind = (unsigned)phase;
+    P.refill = 12; if (const char* v = getenv("SKG_REFILL")) P.refill = std::max(1, std::min(32, atoi(v)));
     P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
     P.L = e.lumDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>();
     P.Ltot = phase == SKG_PHASE_STELLAR ? e.lumTotDev.as<double>() : e.dustLtot.as<double>();

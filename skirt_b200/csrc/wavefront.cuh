@@ -4,7 +4,7 @@
 // propagate stages of the photon shooter) is "for each item: set up a ray, walk it through the grid feeding
 // segments to a sink, finish".  Path lengths vary from 1 to a few hundred crossings, so a plain
 // one-item-per-thread loop leaves most lanes of a warp idle while the longest path finishes.  runJobs() keeps
-// the lanes busy instead: a lane whose path has ended parks until REFILL lanes of its warp are parked, then the
+// the lanes busy instead: a lane whose path has ended parks until `refill` lanes of its warp are parked, then the
 // parked lanes finish their items together and draw new ones from a global work counter.  The crossing step
 // itself is executed by all walking lanes in lock step.  Every grid type provides a stepping walker (geom.cuh).
 //
@@ -21,13 +21,10 @@
 namespace skg
 {
 
-#ifndef SKG_REFILL
-#define SKG_REFILL 8
-#endif
 #define SKG_PERIOD 4
 
 template<class Walker, class GridT, class Job>
-__device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Job& job, int n, int* workCounter)
+__device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Job& job, int n, int* workCounter, int refill)
 {
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -38,7 +35,7 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
     while (true)
     {
         unsigned walking = __ballot_sync(FULL, state == 1);
-        if (__popc(~walking) >= SKG_REFILL || walking == 0)
+        if (__popc(~walking) >= refill || walking == 0)
         {
             if (state == 2) job.finish();
             job.collective(state == 2);
@@ -90,12 +87,12 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
 }
 
 template<int KIND, class Job, class Grids>
-__device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Counters* ctr, Job& job, int n, int* workCounter)
+__device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Counters* ctr, Job& job, int n, int* workCounter, int refill = 8)
 {
-    if (KIND == GRID_CART) runJobsStep<CartWalker>(cart, ctr, job, n, workCounter);
-    else if (KIND == GRID_TREE) runJobsStep<TreeWalker>(G.tree, ctr, job, n, workCounter);
-    else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter);
-    else runJobsStep<VoroWalker>(G.voro, ctr, job, n, workCounter);
+    if (KIND == GRID_CART) runJobsStep<CartWalker>(cart, ctr, job, n, workCounter, refill);
+    else if (KIND == GRID_TREE) runJobsStep<TreeWalker>(G.tree, ctr, job, n, workCounter, refill);
+    else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter, refill);
+    else runJobsStep<VoroWalker>(G.voro, ctr, job, n, workCounter, refill);
 }
 
 }   // namespace skg

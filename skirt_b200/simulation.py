@@ -13,6 +13,7 @@ import os
 
 import numpy as np
 
+from .parallel import shard_packets
 from .binding import Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE
 
 PC = 3.08567758e16          # Units.cpp:17-30
@@ -410,16 +411,16 @@ class MonteCarloSimulation:
     def packets_per_rank(self):
         """IdenticalAssigner/SequentialAssigner block split of the packet budget over processes
         (IdenticalAssigner.cpp:37-58): every rank shoots ceil(packages/nranks) packets per wavelength"""
-        return math.ceil(self.packages / self.nranks)
+        return shard_packets(self.packages, self.rank, self.nranks)[0]
 
     def runstellaremission(self):
         """MonteCarloSimulation::runstellaremission (MonteCarloSimulation.cpp:251-261)"""
         if not self._setup:
             raise FatalError("Simulation has not been setup before being run")
-        npr = self.packets_per_rank()
-        st = self.engine.run_stellar(npr, total_packages=npr * self.nranks, min_weight_reduction=self.mwr,
+        npr, offset, total = shard_packets(self.packages, self.rank, self.nranks)
+        st = self.engine.run_stellar(npr, total_packages=total, min_weight_reduction=self.mwr,
                                      min_scatt_events=self.minfs, scatt_bias=self.xi, store_absorption=self.storeabs,
-                                     seed=self.seed, stream_offset=self.rank * npr)
+                                     seed=self.seed, stream_offset=offset)
         if self.nranks > 1:
             self.engine.allreduce_results()      # Instrument::sumResults / PanDustSystem::sumResults
         return st

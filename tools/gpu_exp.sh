@@ -1,4 +1,4 @@
 #!/bin/bash
-for pad in 0 12000 24000 40000 70000; do
-  echo "pad=$pad"; SKG_FILL_SMEM_PAD=$pad python bench.py --steps 1 --warmup 1 --packages 20000 --skip-cpu 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); t=d['traversal_roofline']; print(t['ms'], t['frac'])"
+for v in 2 4 8 12 16 24; do
+  echo "refill=$v"; SKG_REFILL=$v python bench.py --steps 1 --warmup 1 --skip-cpu --skip-traversal 2>/dev/null | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['value'], d['stage_ms_per_step'])"
 done
