@@ -16,6 +16,7 @@
 #ifndef SKIRTGPU_H
 #define SKIRTGPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -33,6 +34,11 @@ int skg_version(void);
  * record its own events on it or order other work after it; and the number of kernels launched so far */
 int skg_stream(skg_engine* e, void** stream);
 int skg_launch_count(skg_engine* e, uint64_t* launches);
+
+/* page-locked host memory for result arrays: skg_fetch_* into such a buffer is a single DMA transfer (pageable
+ * destinations are staged by the driver at a fraction of the PCIe rate) */
+int skg_host_alloc(size_t bytes, void** ptr);
+int skg_host_free(void* ptr);
 
 /* ---- dust grids: replace DustGrid::path / whichcell / randomPositionInCell (DustGrid.hpp:89-106) -- */
 

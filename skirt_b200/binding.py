@@ -322,22 +322,34 @@ class Engine:
         self._chk(self._lib.skg_labs_bolometric(self.h, _vp(a)))
         return a
 
+    def pinned_empty(self, shape, dtype=np.float64):
+        """numpy array in page-locked host memory (skg_host_alloc); freed when the array is garbage collected"""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._chk(self._lib.skg_host_alloc(C.c_size_t(n), C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        lib = self._lib
+        import weakref
+        weakref.finalize(buf, lambda ptr=p.value: lib.skg_host_free(C.c_void_p(ptr)))
+        return arr
+
     def reset_results(self):
         self._chk(self._lib.skg_reset_results(self.h))
 
-    def fetch_frame(self, i):
+    def fetch_frame(self, i, out=None):
         d = self._instr[i]
-        a = np.zeros(int(d["Nxp"]) * int(d["Nyp"]) * self.Nlambda)
+        a = np.zeros(int(d["Nxp"]) * int(d["Nyp"]) * self.Nlambda) if out is None else out
         self._chk(self._lib.skg_fetch_frame(self.h, i, _vp(a), 0))
         return a
 
-    def fetch_sed(self, i):
-        a = np.zeros(self.Nlambda)
+    def fetch_sed(self, i, out=None):
+        a = np.zeros(self.Nlambda) if out is None else out
         self._chk(self._lib.skg_fetch_sed(self.h, i, _vp(a), 0))
         return a
 
-    def fetch_labs(self):
-        a = np.zeros((self.Ncells, self.Nlambda))
+    def fetch_labs(self, out=None):
+        a = np.zeros((self.Ncells, self.Nlambda)) if out is None else out
         self._chk(self._lib.skg_fetch_labs(self.h, _vp(a), 0))
         return a
 

@@ -107,6 +107,10 @@ int skg_stream(skg_engine* eh, void** stream)
 int skg_launch_count(skg_engine* eh, uint64_t* launches)
 { return guarded([&]{ if (!launches) throw Error("null output"); *launches = E(eh).launches; }); }
 
+int skg_host_alloc(size_t bytes, void** ptr)
+{ return guarded([&]{ if (!ptr) throw Error("null output"); SKG_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault)); }); }
+int skg_host_free(void* ptr) { return guarded([&]{ if (ptr) SKG_CUDA(cudaFreeHost(ptr)); }); }
+
 int skg_num_cells(skg_engine* e) { return e ? reinterpret_cast<Engine*>(e)->Ncells : 0; }
 
 int skg_grid_cartesian(skg_engine* eh, const double* xv, int Nx, const double* yv, int Ny, const double* zv, int Nz)

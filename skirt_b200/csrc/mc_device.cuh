@@ -56,6 +56,23 @@ struct McDev
     int refill;             // lanes of a warp that must be parked before they finish and draw new work together
 };
 
+// expm1 for the per-segment absorbed fraction -expm1(-dtau) (MonteCarloSimulation.cpp:452): most segments have a small
+// optical depth, where the Taylor polynomial up to x^8/8! is accurate to better than one ulp (remainder < 3e-18
+// relative for |x| <= 2^-5) and costs 8 FMAs; larger arguments use the library function
+__device__ __forceinline__ double expm1Small(double x)
+{
+    if (fabs(x) > 0.03125) return expm1(x);
+    double p = 1.0 / 40320.0;
+    p = __fma_rn(p, x, 1.0 / 5040.0);
+    p = __fma_rn(p, x, 1.0 / 720.0);
+    p = __fma_rn(p, x, 1.0 / 120.0);
+    p = __fma_rn(p, x, 1.0 / 24.0);
+    p = __fma_rn(p, x, 1.0 / 6.0);
+    p = __fma_rn(p, x, 0.5);
+    p = __fma_rn(p, x, 1.0);
+    return p * x;
+}
+
 // ---- accumulation ----------------------------------------------------------------------------------------
 // LockFree::add (LockFree.hpp:25-37) on the device: lanes of a warp that target the same address are summed
 // first and issue ONE fp64 atomicAdd (SED bins are a single address per wavelength, edge-on frames concentrate

@@ -397,7 +397,7 @@ template<int KIND> struct AbsorbJob
         double dtau = (kext0 * pendRho) * pendDs;
         if (labs)
         {
-            double x = expm1(-dtau);
+            double x = expm1Small(-dtau);
             atomicAdd(labs + pendM, (1.0 - albedo) * (L * E * (-x)));
             E += E * x;
             nAbs++;
@@ -426,7 +426,7 @@ template<int KIND> struct AbsorbJob
             }
             double alb = (kext > 0.0) ? ksca / kext : 0.0;
             double dtau = krr * ds;
-            double x = expm1(-dtau);
+            double x = expm1Small(-dtau);
             double Lintm = L * E * (-x);
             E += E * x;
             Lsca += alb * Lintm;

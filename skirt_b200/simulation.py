@@ -425,13 +425,24 @@ class MonteCarloSimulation:
             self.engine.allreduce_results()      # Instrument::sumResults / PanDustSystem::sumResults
         return st
 
-    def results(self):
+    def results(self, pinned=False):
+        """detector arrays and absorption table on the host; pinned=True keeps page-locked result buffers alive across
+        calls so that every fetch is a single DMA transfer"""
         out = {}
+        buf = self.__dict__.setdefault("_pinned", {}) if pinned else None
+        def dest(key, shape):
+            if buf is None:
+                return None
+            if key not in buf:
+                buf[key] = self.engine.pinned_empty(shape)
+            return buf[key]
+        Nl = self.lambdagrid.Nlambda
         for i, ins in enumerate(self.isys.instruments):
             if ins.kind != INSTR_SED:
-                out[ins.name + "_frame"] = self.engine.fetch_frame(i).reshape(self.lambdagrid.Nlambda, ins.d["Nyp"], ins.d["Nxp"])
+                n = ins.d["Nxp"] * ins.d["Nyp"] * Nl
+                out[ins.name + "_frame"] = self.engine.fetch_frame(i, dest(("f", i), (n,))).reshape(Nl, ins.d["Nyp"], ins.d["Nxp"])
             if ins.kind != INSTR_FRAME:
-                out[ins.name + "_sed"] = self.engine.fetch_sed(i)
+                out[ins.name + "_sed"] = self.engine.fetch_sed(i, dest(("s", i), (Nl,)))
         if self.storeabs:
-            out["Labs"] = self.engine.fetch_labs()
+            out["Labs"] = self.engine.fetch_labs(dest("labs", (self.engine.Ncells, Nl)))
         return out
