@@ -3,7 +3,7 @@ NVCC ?= /usr/local/cuda/bin/nvcc
 HOSTCXX := /usr/bin/g++
 ARCH := -gencode arch=compute_100a,code=sm_100a
 # -fmad=false: no FMA contraction, so that fp64 geometry matches the reference bit for bit
-NVFLAGS := $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -lineinfo -fmad=false --expt-relaxed-constexpr \
+NVFLAGS := $(EXTRA) $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -lineinfo -fmad=false --expt-relaxed-constexpr \
            -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function -Xptxas -v
 CSRC := skirt_b200/csrc
 OBJS := $(CSRC)/build/engine.o $(CSRC)/build/path_kernels.o $(CSRC)/build/mc_kernels.o $(CSRC)/build/comm.o

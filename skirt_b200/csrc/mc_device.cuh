@@ -16,16 +16,41 @@ namespace skg
 
 struct GridSetMC { CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro; };
 
-// Packet pool: structure of arrays, one slot per in-flight photon packet (PhotonPackage, PhotonPackage.hpp:28,134-138;
+// Packet pool: one 96-byte record per in-flight photon packet (PhotonPackage, PhotonPackage.hpp:28,134-138;
 // unpolarised: position, direction, luminosity, wavelength index, number of scatterings) plus the engine's own
-// bookkeeping (Philox stream position, interaction optical depth sampled by the absorb stage).
-struct PacketPool
+// bookkeeping (Philox stream position, interaction optical depth sampled by the absorb stage).  The packets in flight
+// are kept COMPACT: the absorb stage writes its survivors to consecutive records of a second pool and new packets are
+// appended behind them, so every stage streams through records [0, n) -- consecutive lanes read consecutive 96-byte
+// records (three 32-byte sectors each, moved as a whole), no index indirection and no random DRAM access.
+struct __align__(32) Packet
 {
-    double* x; double* y; double* z; double* kx; double* ky; double* kz;
-    double* L; double* target;
-    unsigned long long* id;     // Philox stream id of the packet
-    int* ell; int* nscatt; unsigned* rngCtr; int* fresh;
+    double x, y, z, kx, ky, kz;
+    double L, target;
+    unsigned long long id;      // Philox stream id of the packet
+    int ell, nscatt; unsigned rngCtr; int fresh;
+    double pad;
 };
+typedef Packet* PacketPool;
+
+// whole-record access: three 256-bit transactions (LDG/STG.E.ENL2.256 on sm_100a)
+__device__ __forceinline__ Packet loadPacket(const Packet* p)
+{
+#ifdef SKG_PLAIN_PACKET_LOAD
+    return *p;
+#endif
+    Packet r; double* w = reinterpret_cast<double*>(&r);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        asm volatile("ld.global.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[4 * i]), "=d"(w[4 * i + 1]), "=d"(w[4 * i + 2]), "=d"(w[4 * i + 3]) : "l"(reinterpret_cast<const double*>(p) + 4 * i));
+    return r;
+}
+__device__ __forceinline__ void storePacket(Packet* p, const Packet& r)
+{
+    const double* w = reinterpret_cast<const double*>(&r);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+        asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(reinterpret_cast<double*>(p) + 4 * i), "d"(w[4 * i]), "d"(w[4 * i + 1]), "d"(w[4 * i + 2]), "d"(w[4 * i + 3]) : "memory");
+}
 
 // instruments that look along the same direction share one peel-off traversal
 struct ObsGroup { double kx, ky, kz; int first, count; };
@@ -46,7 +71,8 @@ struct McDev
     uint64_t seed, streamOffset;
     const int* ellList;     // wavelength indices with nonzero luminosity, in shooting order
     unsigned long long NppInt;
-    PacketPool pool;
+    PacketPool pool;        // packets of this iteration, compact: [0, nAlive)
+    PacketPool poolNext;    // survivors of the absorb stage are written here, compact again
     // dust emission phases (PanMonteCarloSimulation.cpp:187-342)
     int phase;              // SKG_PHASE_*
     unsigned rngKind;       // Philox stream kind, so that the phases of one simulation never share deviates
@@ -94,17 +120,17 @@ __device__ __forceinline__ void warpAggregatedAdd(double* addr, double v)
     if (lane == leader) atomicAdd(addr, sum);
 }
 
-// appends the slots of the lanes with `take` set to a list: one atomicAdd per warp
-__device__ __forceinline__ void warpAppend(bool take, int slot, int* list, int* count)
+// stream compaction: the lanes with `take` set obtain consecutive positions in an output array, one atomicAdd per warp
+__device__ __forceinline__ int warpAppendPosition(bool take, int* count)
 {
     const unsigned active = __activemask();
     const unsigned mask = __ballot_sync(active, take);
-    if (!mask) return;
+    if (!mask) return -1;
     const int lane = threadIdx.x & 31;
     int base = 0;
     if (lane == __ffs(mask) - 1) base = atomicAdd(count, __popc(mask));
     base = __shfl_sync(active, base, __ffs(mask) - 1);
-    if (take) list[base + __popc(mask & ((1u << lane) - 1))] = slot;
+    return take ? base + __popc(mask & ((1u << lane) - 1)) : -1;
 }
 
 // ---- samplers ------------------------------------------------------------------------------------------

@@ -58,13 +58,13 @@ __device__ __forceinline__ void flushStats(Counters* ctr, unsigned long long nSe
 
 // ---- launch ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev P, Counters* ctr, int nLaunch, unsigned long long firstPacket,
-                                                   const int* __restrict__ freeList, int* __restrict__ aliveList, int aliveBase)
+                                                   int aliveBase)
 {
     unsigned long long nPackets = 0;
     const int Nlambda = P.med.Nlambda;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nLaunch; j += gridDim.x * blockDim.x)
     {
-        const int slot = freeList[j];
+        const int slot = aliveBase + j;        // appended behind the survivors
         const unsigned long long gidx = firstPacket + j;
         const int ell = P.ellList[gidx / P.NppInt];
         const unsigned long long ipkt = gidx % P.NppInt;
@@ -97,10 +97,10 @@ __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev
             generatePosition(P.sources[h], rng, x, y, z);        // GeometricStellarComp::launch, GeometricStellarComp.cpp:75-81
             randomDirection(rng, kx, ky, kz);                    // Geometry::generateDirection, Geometry.cpp:33
         }
-        const PacketPool& q = P.pool;
-        q.x[slot] = x; q.y[slot] = y; q.z[slot] = z; q.kx[slot] = kx; q.ky[slot] = ky; q.kz[slot] = kz;
-        q.L[slot] = L; q.target[slot] = 0; q.id[slot] = id; q.ell[slot] = ell; q.nscatt[slot] = 0; q.rngCtr[slot] = rng.c2; q.fresh[slot] = 1;
-        aliveList[aliveBase + j] = slot;
+        Packet* q = P.pool;
+        Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
+        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.pad = 0;
+        storePacket(q + slot, pk);
     }
     flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
 }
@@ -139,13 +139,13 @@ __device__ __forceinline__ bool randomPositionInCell(const GridSetMC& G, int m, 
 // launch of dust emission: dodustselfabsorptionchunk :208-221 / dodustemissionchunk :296-316
 template<int KIND>
 __global__ void __launch_bounds__(128) launchDustStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, int nLaunch,
-                                                       unsigned long long firstPacket, const int* __restrict__ freeList, int* __restrict__ aliveList, int aliveBase)
+                                                       unsigned long long firstPacket, int aliveBase)
 {
     unsigned long long nPackets = 0;
     const int Nlambda = P.med.Nlambda, Ncells = P.med.Ncells;
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nLaunch; j += gridDim.x * blockDim.x)
     {
-        const int slot = freeList[j];
+        const int slot = aliveBase + j;        // appended behind the survivors
         const unsigned long long gidx = firstPacket + j;
         const int ell = P.ellList[gidx / P.NppInt];
         const unsigned long long ipkt = gidx % P.NppInt;
@@ -170,10 +170,10 @@ __global__ void __launch_bounds__(128) launchDustStage(const __grid_constant__ G
         double x = 0, y = 0, z = 0, kx = 0, ky = 0, kz = 1;
         if (!randomPositionInCell<KIND>(G, m, rng, x, y, z)) { atomicAdd(&ctr->errors, 1ull); L = 0; }
         randomDirection(rng, kx, ky, kz);
-        const PacketPool& q = P.pool;
-        q.x[slot] = x; q.y[slot] = y; q.z[slot] = z; q.kx[slot] = kx; q.ky[slot] = ky; q.kz[slot] = kz;
-        q.L[slot] = L; q.target[slot] = 0; q.id[slot] = id; q.ell[slot] = ell; q.nscatt[slot] = 0; q.rngCtr[slot] = rng.c2; q.fresh[slot] = 1;
-        aliveList[aliveBase + j] = slot;
+        Packet* q = P.pool;
+        Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
+        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.pad = 0;
+        storePacket(q + slot, pk);
     }
     flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
 }
@@ -215,25 +215,26 @@ __device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, doub
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
 template<int KIND> struct PeelJob
 {
-    const GridSetMC& G; const CartGrid& cart; const McDev& P; const int* aliveList;
+    const GridSetMC& G; const CartGrid& cart; const McDev& P;
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
     double Lw, tau; KappaRho kr; int ell, grp;
     // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
     // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
     double kext0, pendRho, pendDs; bool single;
     unsigned long long nSeg = 0, nPaths = 0, nDet = 0;
-    __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, const int* l_) : G(G_), cart(c_), P(P_), aliveList(l_) {}
+    __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_) : G(G_), cart(c_), P(P_) {}
 
     __device__ __forceinline__ int begin(int item)
     {
-        const PacketPool& q = P.pool;
-        const int slot = aliveList[item / P.Ngroups];
+        Packet* q = P.pool;
+        const int slot = item / P.Ngroups;
         grp = item % P.Ngroups;
         const ObsGroup& g = P.groups[grp];
-        double L = q.L[slot];
+        const Packet pk = loadPacket(q + slot);
+        double L = pk.L;
         if (!(L > 0)) return 0;                                 // MonteCarloSimulation.cpp:281
-        rx = q.x[slot]; ry = q.y[slot]; rz = q.z[slot];
-        ell = q.ell[slot];
+        rx = pk.x; ry = pk.y; rz = pk.z;
+        ell = pk.ell;
         // which instruments of this direction record the packet?  FrameInstrument ignores packets that map outside
         // its frame before any optical depth is computed (FrameInstrument.cpp:36); SED/Simple always need tau
         bool need = false;
@@ -244,10 +245,10 @@ template<int KIND> struct PeelJob
         }
         if (!need) return 0;
         const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
-        if (!q.fresh[slot])
+        if (!pk.fresh)
         {
             // ---- peeloffscattering, MonteCarloSimulation.cpp:319-363: weight by the phase function towards the observer ----
-            const double kx = q.kx[slot], ky = q.ky[slot], kz = q.kz[slot];
+            const double kx = pk.kx, ky = pk.ky, kz = pk.kz;
             double wv[8];
             if (Ncomp == 1) wv[0] = 1.0;
             else
@@ -310,12 +311,12 @@ template<int KIND> struct PeelJob
 
 template<int KIND>
 __global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
-                                                 const int* __restrict__ aliveList, int nAlive, int* work)
+                                                 int nAlive, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    PeelJob<KIND> job(G, cart, P, aliveList);
+    PeelJob<KIND> job(G, cart, P);
     runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, min(28, 2 * P.refill));
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
 }
@@ -323,34 +324,35 @@ __global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSet
 // scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
 template<int KIND> struct AbsorbJob
 {
-    const GridSetMC& G; const CartGrid& cart; const McDev& P; const int* aliveList;
-    int* survivors; int* freeList; int* counts;
+    const GridSetMC& G; const CartGrid& cart; const McDev& P;
+    int* counts;
     double rx, ry, rz, dx, dy, dz;
     // AbsorbSink state (see mc_device.cuh): one expm1 per segment, E = exp(-tau) carried multiplicatively
     KappaRho kr; double L, albedo, tau, E, Lsca; double* labs;
-    int slot, ell, nscatt; unsigned rngCtr; bool survive;
+    int slot, ell, nscatt; unsigned rngCtr; bool survive; unsigned long long id; double target;
     double kext0, pendRho, pendDs; int pendM;      // one-component media: gather now, absorb one crossing later
     unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
-    __device__ AbsorbJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, const int* l_, int* s_, int* f_, int* c2_)
-        : G(G_), cart(c_), P(P_), aliveList(l_), survivors(s_), freeList(f_), counts(c2_) {}
+    __device__ AbsorbJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, int* c2_) : G(G_), cart(c_), P(P_), counts(c2_) {}
 
     __device__ __forceinline__ int begin(int item)
     {
-        const PacketPool& q = P.pool;
-        slot = aliveList[item];
+        Packet* q = P.pool;
+        slot = item;
         survive = false;
-        L = q.L[slot];
+        const Packet pk = loadPacket(q + slot);
+        L = pk.L;
         if (!(L > 0) || !P.med.rho) return 2;       // nothing to propagate: the slot is recycled in finish()/collective()
         const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
-        ell = q.ell[slot];
-        rx = q.x[slot]; ry = q.y[slot]; rz = q.z[slot];
-        dx = q.kx[slot]; dy = q.ky[slot]; dz = q.kz[slot];
-        nscatt = q.nscatt[slot];
-        rngCtr = q.rngCtr[slot];
-        if (!q.fresh[slot])
+        ell = pk.ell;
+        rx = pk.x; ry = pk.y; rz = pk.z;
+        dx = pk.kx; dy = pk.ky; dz = pk.kz;
+        nscatt = pk.nscatt;
+        rngCtr = pk.rngCtr;
+        id = pk.id;
+        if (!pk.fresh)
         {
             // ---- simulatescattering, MonteCarloSimulation.cpp:541-549 ----
-            Philox rng; rng.init(P.seed, q.id[slot], P.rngKind); rng.c2 = rngCtr;
+            Philox rng; rng.init(P.seed, id, P.rngKind); rng.c2 = rngCtr;
             int hmix = 0;
             if (Ncomp > 1)
             {
@@ -376,7 +378,6 @@ template<int KIND> struct AbsorbJob
                 scatterDirection(rng, costheta, dx, dy, dz);
             }
             nscatt++; nScatt++;
-            q.kx[slot] = dx; q.ky[slot] = dy; q.kz[slot] = dz; q.nscatt[slot] = nscatt;
             rngCtr = rng.c2;
         }
         // ---- fillOpticalDepth + simulateescapeandabsorption, :286-288, :438-515 ----
@@ -438,7 +439,7 @@ template<int KIND> struct AbsorbJob
     __device__ __forceinline__ void finish()
     {
         if (!(L > 0) || !P.med.rho) return;
-        const PacketPool& q = P.pool;
+        Packet* q = P.pool;
         if (P.med.Ncomp == 1) { absorbPending(); pendM = -1; }
         const double taupath = tau;
         if (P.med.Ncomp == 1) L = L * albedo * (-expm1(-taupath));
@@ -449,7 +450,7 @@ template<int KIND> struct AbsorbJob
         if (survive)
         {
             // ---- simulatepropagation, :519-533: sample the interaction optical depth, weight for the bias ----
-            Philox rng; rng.init(P.seed, q.id[slot], P.rngKind); rng.c2 = rngCtr;
+            Philox rng; rng.init(P.seed, id, P.rngKind); rng.c2 = rngCtr;
             double t = 0;
             if (taupath != 0.0)
             {
@@ -463,28 +464,32 @@ template<int KIND> struct AbsorbJob
                     L = L * (p / qq);
                 }
             }
-            q.target[slot] = t;
+            target = t;
             rngCtr = rng.c2;
         }
-        q.L[slot] = L; q.rngCtr[slot] = rngCtr;
     }
     __device__ __forceinline__ void collective(bool fin)
     {
-        warpAppend(fin && survive, slot, survivors, counts);
-        warpAppend(fin && !survive, slot, freeList, counts + 1);
+        // survivors move on to the next pool, compact; packets that ended simply are not copied
+        const int pos = warpAppendPosition(fin && survive, counts);
+        if (pos >= 0)
+        {
+            Packet pk; pk.x = rx; pk.y = ry; pk.z = rz; pk.kx = dx; pk.ky = dy; pk.kz = dz;
+            pk.L = L; pk.target = target; pk.id = id; pk.ell = ell; pk.nscatt = nscatt; pk.rngCtr = rngCtr; pk.fresh = 0; pk.pad = 0;
+            storePacket(P.poolNext + pos, pk);
+        }
     }
     __device__ __forceinline__ void periodic() {}
 };
 
 template<int KIND>
 __global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
-                                                   const int* __restrict__ aliveList, int nAlive, int* __restrict__ survivors,
-                                                   int* __restrict__ freeList, int* __restrict__ counts, int* work)
+                                                   int nAlive, int* __restrict__ counts, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    AbsorbJob<KIND> job(G, cart, P, aliveList, survivors, freeList, counts);
+    AbsorbJob<KIND> job(G, cart, P, counts);
     runJobs<KIND>(G, cart, ctr, job, nAlive, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, job.nScatt, 0, job.nAbs, 0);
 }
@@ -493,21 +498,21 @@ __global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridS
 // DustGridPath::pathlength (DustGridPath.cpp:162-173) evaluated on the fly + PhotonPackage::propagate (PhotonPackage.cpp:93-96)
 template<int KIND> struct PropagateJob
 {
-    const McDev& P; const int* list;
+    const McDev& P;
     double rx, ry, rz, dx, dy, dz;
     KappaRho kr; double target, sPrev, tauPrev, result; bool found; int slot;
     double kext0, pendRho, pendDs; bool single, pending;      // one-component media: gather now, test one crossing later
     unsigned long long nSeg = 0, nPaths = 0;
-    __device__ PropagateJob(const McDev& P_, const int* l_) : P(P_), list(l_) {}
+    __device__ explicit PropagateJob(const McDev& P_) : P(P_) {}
     __device__ __forceinline__ int begin(int item)
     {
-        const PacketPool& q = P.pool;
-        slot = list[item];
-        q.fresh[slot] = 0;
-        target = q.target[slot];
+        Packet* q = P.poolNext;      // the survivors the absorb stage just compacted
+        slot = item;
+        const Packet pk = loadPacket(q + slot);
+        target = pk.target;
         if (!(target > 0)) return 0;
-        const int ell = q.ell[slot];
-        rx = q.x[slot]; ry = q.y[slot]; rz = q.z[slot]; dx = q.kx[slot]; dy = q.ky[slot]; dz = q.kz[slot];
+        const int ell = pk.ell;
+        rx = pk.x; ry = pk.y; rz = pk.z; dx = pk.kx; dy = pk.ky; dz = pk.kz;
         kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
         sPrev = 0; tauPrev = 0; result = 0; found = false;
         single = P.med.Ncomp == 1; kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pending = false; pendRho = 0; pendDs = 0;
@@ -541,10 +546,10 @@ template<int KIND> struct PropagateJob
     }
     __device__ __forceinline__ void finish()
     {
-        const PacketPool& q = P.pool;
+        Packet* q = P.poolNext;      // the survivors the absorb stage just compacted
         if (single && pending && !found) test((kext0 * pendRho) * pendDs, pendDs);
         const double s = found ? result : sPrev;
-        q.x[slot] = rx + s * dx; q.y[slot] = ry + s * dy; q.z[slot] = rz + s * dz;
+        q[slot].x = rx + s * dx; q[slot].y = ry + s * dy; q[slot].z = rz + s * dz;
     }
     __device__ __forceinline__ void collective(bool) {}
     __device__ __forceinline__ void periodic() {}
@@ -552,17 +557,15 @@ template<int KIND> struct PropagateJob
 
 template<int KIND>
 __global__ void __launch_bounds__(128) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
-                                                      const int* __restrict__ survivors, int nSurv, int* work)
+                                                      int nSurv, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    PropagateJob<KIND> job(P, survivors);
+    PropagateJob<KIND> job(P);
     runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
 }
-
-__global__ void iotaKernel(int* list, int n) { for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) list[i] = i; }
 
 // Labs is wavelength-major on the device; the host interface is DustSystem's (m, ell) row-major table
 __global__ void transposeLabs(const double* __restrict__ src, double* __restrict__ dst, int Ncells, int Nlambda)
@@ -741,27 +744,27 @@ void mcLabsBolometric(Engine& e, double* host)
 template<int KIND>
 static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned long long total, int pool, size_t smem, bool cartSmem)
 {
-    int* listA = e.mcLists.as<int>(); int* listB = listA + pool; int* freeList = listB + pool;
-    int* counts = e.mcCounts.as<int>();      // [0] survivors, [1] freed slots, [2..4] work counters of the three traversal stages
+    Packet* poolA = e.mcPool.as<Packet>(); Packet* poolB = poolA + pool;
+    int* counts = e.mcCounts.as<int>();      // [0] survivors, [2..4] work counters of the three traversal stages
     auto blocksFor = [&](long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, (long long)e.smCount * 16)); };
     for (cudaEvent_t& ev : e.mcEvents) if (!ev) SKG_CUDA(cudaEventCreate(&ev));
     cudaEvent_t* ev = e.mcEvents;            // 0..3: boundaries launch | peel | absorb | end; 4..5: around propagate
     for (double& t : e.stageMs) t = 0;
     e.mcIterations = 0;
-    iotaKernel<<<blocksFor(pool), 128, 0, e.stream>>>(freeList, pool); e.launches++;
     unsigned long long launched = 0;
-    int nAlive = 0, nFree = pool;
+    int nAlive = 0;                          // packets in flight: poolA[0, nAlive), survivors first, then the newly launched
     int* hostCounts = e.mcHostCounts;
     bool propagatePending = false;
     auto addMs = [&](int stage, cudaEvent_t a, cudaEvent_t b) { float ms = 0; SKG_CUDA(cudaEventElapsedTime(&ms, a, b)); e.stageMs[stage] += ms; };
     while (true)
     {
-        int nLaunch = (int)std::min<unsigned long long>((unsigned long long)nFree, total - launched);
+        P.pool = poolA; P.poolNext = poolB;
+        int nLaunch = (int)std::min<unsigned long long>((unsigned long long)(pool - nAlive), total - launched);
         SKG_CUDA(cudaEventRecord(ev[0], e.stream));
         if (nLaunch > 0)
         {
-            if (P.phase == SKG_PHASE_STELLAR) launchStage<<<blocksFor(nLaunch), 128, 0, e.stream>>>(P, e.ctr(), nLaunch, launched, freeList, listA, nAlive);
-            else launchDustStage<KIND><<<blocksFor(nLaunch), 128, 0, e.stream>>>(G, P, e.ctr(), nLaunch, launched, freeList, listA, nAlive);
+            if (P.phase == SKG_PHASE_STELLAR) launchStage<<<blocksFor(nLaunch), 128, 0, e.stream>>>(P, e.ctr(), nLaunch, launched, nAlive);
+            else launchDustStage<KIND><<<blocksFor(nLaunch), 128, 0, e.stream>>>(G, P, e.ctr(), nLaunch, launched, nAlive);
             e.launches++;
             nAlive += nLaunch; launched += nLaunch;
         }
@@ -769,9 +772,9 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         SKG_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), e.stream));
         SKG_CUDA(cudaEventRecord(ev[1], e.stream));
         if (P.Ngroups > 0 && P.phase != SKG_PHASE_DUST_SELFABS)
-        { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, counts + 2); e.launches++; }
+        { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2); e.launches++; }
         SKG_CUDA(cudaEventRecord(ev[2], e.stream));
-        absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listA, nAlive, listB, freeList, counts, counts + 3); e.launches++;
+        absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3); e.launches++;
         SKG_CUDA(cudaEventRecord(ev[3], e.stream));
         SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
         SKG_CUDA(cudaGetLastError());
@@ -779,15 +782,15 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         if (propagatePending) { addMs(3, ev[4], ev[5]); propagatePending = false; }
         addMs(0, ev[0], ev[1]); addMs(1, ev[1], ev[2]); addMs(2, ev[2], ev[3]);
         e.mcIterations++;
-        int nSurv = hostCounts[0]; nFree = hostCounts[1];
+        int nSurv = hostCounts[0];
         if (nSurv > 0)
         {
             SKG_CUDA(cudaEventRecord(ev[4], e.stream));
-            propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, listB, nSurv, counts + 4); e.launches++;
+            propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nSurv, counts + 4); e.launches++;
             SKG_CUDA(cudaEventRecord(ev[5], e.stream));
             propagatePending = true;
         }
-        std::swap(listA, listB);
+        std::swap(poolA, poolB);
         nAlive = nSurv;
     }
     SKG_CUDA(cudaGetLastError());
@@ -866,17 +869,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         int pool = p.poolPackets > 0 ? p.poolPackets : (1 << 22);
         pool = (int)std::min<unsigned long long>((unsigned long long)pool, total);
         pool = std::max(pool, 1);
-        size_t per = 8 * sizeof(double) + sizeof(unsigned long long) + 4 * sizeof(int);
-        e.mcPool.ensure(per * (size_t)pool + 256);
-        char* base = e.mcPool.as<char>();
-        double* d = reinterpret_cast<double*>(base);
-        PacketPool& q = P.pool;
-        q.x = d; q.y = d + (size_t)pool; q.z = d + 2 * (size_t)pool; q.kx = d + 3 * (size_t)pool; q.ky = d + 4 * (size_t)pool; q.kz = d + 5 * (size_t)pool;
-        q.L = d + 6 * (size_t)pool; q.target = d + 7 * (size_t)pool;
-        q.id = reinterpret_cast<unsigned long long*>(d + 8 * (size_t)pool);
-        int* ip = reinterpret_cast<int*>(q.id + (size_t)pool);
-        q.ell = ip; q.nscatt = ip + (size_t)pool; q.rngCtr = reinterpret_cast<unsigned*>(ip + 2 * (size_t)pool); q.fresh = ip + 3 * (size_t)pool;
-        e.mcLists.ensure(sizeof(int) * 3 * (size_t)pool);
+        e.mcPool.ensure(2 * sizeof(Packet) * (size_t)pool);       // two pools: the stages ping-pong between them
         e.mcCounts.ensure(sizeof(int) * 8);
         if (!e.mcHostCounts) SKG_CUDA(cudaMallocHost(&e.mcHostCounts, 2 * sizeof(int)));
 
