@@ -826,7 +826,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     McDev P{};
     P.med = e.med; if (!e.med.rho) { P.med.Nlambda = Nlambda; P.med.Ncomp = 0; }
     P.phase = phase; P.rngKind = (unsigned)phase;
-    P.refill = 12; if (const char* v = getenv("SKG_REFILL")) P.refill = std::max(1, std::min(32, atoi(v)));
+    P.refill = 14; if (const char* v = getenv("SKG_REFILL")) P.refill = std::max(1, std::min(32, atoi(v)));
     P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
     P.L = e.lumDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>();
     P.Ltot = phase == SKG_PHASE_STELLAR ? e.lumTotDev.as<double>() : e.dustLtot.as<double>();
