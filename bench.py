@@ -175,10 +175,19 @@ def traversal_leg(engine, torch, ext, ncomp, nrays, reps=5, warm=3):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(ext); engine.path_count_device(nrays, r.data_ptr(), k.data_ptr(), off.data_ptr()); e1.record(ext); e1.synchronize()
         ctimes.append(e0.elapsed_time(e1))
+    # context for the roofline: a pure streaming write (memset of 1 GiB) on this GPU -- the path-record kernel is a
+    # write-only stream, whereas the roofline denominator (MEASURED_PEAKS.json) is a copy, i.e. reads + writes
+    big = torch.empty(1 << 30, dtype=torch.uint8, device="cuda"); wtimes = []
+    for _ in range(4):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); big.zero_(); e1.record(); e1.synchronize(); wtimes.append(e0.elapsed_time(e1))
+    write_only_gbs = (1 << 30) / (min(wtimes[1:]) * 1e-3) / 1e9
+    del big
     ms = float(np.mean(times))
     nbytes = 60.0 * nrays + total * (36.0 + 8.0 * ncomp)
     return dict(rays=nrays, packet_steps=int(total), ms=ms, ms_count_pass=float(np.mean(ctimes)), bytes=nbytes,
-                steps_per_s=total / (ms * 1e-3), gbs=nbytes / (ms * 1e-3) / 1e9)
+                steps_per_s=total / (ms * 1e-3), gbs=nbytes / (ms * 1e-3) / 1e9, written_gbs=40.0 * total / (ms * 1e-3) / 1e9,
+                write_only_memset_gbs=write_only_gbs)
 
 
 def main_engine(args):

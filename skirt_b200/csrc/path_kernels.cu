@@ -282,6 +282,7 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_AMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_VORO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        if (const char* cv = getenv("SKG_FILL_CARVEOUT")) SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_CART>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
         attr = true;
     }
     SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, (int)n, d_r, d_k, d_ell, ellStride,
