@@ -99,3 +99,55 @@ def test_invariant_divisor_division_is_ieee_exact(engine):
     the result must equal the IEEE quotient bit for bit -- 2^33 operand pairs including adversarial mantissas"""
     assert engine.selftest_division(1 << 33, seed=12345) == 0
     assert engine.selftest_division(1 << 30, seed=777) == 0
+
+
+@pytest.mark.parametrize("name", common.GEOM_CASES)
+def test_fresh_rays_against_the_restated_oracle(engine, name):
+    """60 000 fresh seeded rays per grid fixture (and 2 wavelengths chosen per ray) against oracle/liboracle.so, which is
+    itself pinned bit for bit to the reference (tests/test_oracle.py)"""
+    from oracle import oracle_py
+    if not oracle_py.available():
+        pytest.skip("oracle/liboracle.so not built")
+    tables, medium, _ = common.load_golden(name)
+    med2 = dict(medium)
+    for key in ("kext", "ksca", "g"):                     # a second wavelength with different opacities
+        med2[key] = np.concatenate([medium[key], 0.37 * medium[key]], axis=1)
+    engine.set_grid(tables); engine.medium(med2["rho"], med2["kext"], med2["ksca"], med2["g"])
+    r, k = common.rays(60000, common.C1_BOX, 2024)
+    rng = np.random.default_rng(3)
+    ell = rng.integers(0, 2, len(r)).astype(np.int32)
+    got = engine.path_batch(r, k, ell=ell)
+    ref = oracle_py.Oracle(tables, med2).path_batch(r, k, ell=ell)
+    assert common.paths_bit_identical(got, ref), name
+    dist = rng.random(len(r)) * 4e20
+    assert np.array_equal(engine.opticaldepth(r, k, ell, dist), oracle_py.Oracle(tables, med2).opticaldepth(r, k, ell, dist))
+
+
+def test_non_finite_and_degenerate_rays(engine):
+    """rays the reference could not handle (NaN / infinite components make its loops spin forever) yield empty paths;
+    a zero direction vector outside the grid is a miss, inside it terminates after the first cell boundary test"""
+    tables, medium, _ = common.load_golden("cart_lin")
+    engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    c = [0.0, 0.0, 0.0]
+    r = np.array([[np.nan, 0, 0], c, [np.inf, 0, 0], c, [1e30, 1e30, 1e30]])
+    k = np.array([[1.0, 0, 0], [np.nan, 0, 1], [1.0, 0, 0], [0, np.inf, 0], [0.0, 0.0, 0.0]])
+    got = engine.path_batch(r, k, ell=0)
+    assert np.diff(got["offsets"]).tolist() == [0, 0, 0, 0, 0]
+    # whichcell follows the reference's comparisons literally (a NaN coordinate falls through NR::locate_fail into the last bin)
+    from oracle import oracle_py
+    if oracle_py.available():
+        assert np.array_equal(engine.whichcell(r), oracle_py.Oracle(tables, medium).whichcell(r))
+
+
+def test_large_batch_offsets_are_consistent(engine):
+    """2^20 rays: CSR offsets monotone, total equals the sum of counts, every path ends on the grid boundary"""
+    tables, medium, _ = common.load_golden("octtree_s1")
+    engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    r, k = common.rays(1 << 20, common.C1_BOX, 99, scale=0.99)
+    got = engine.path_batch(r, k, ell=0)
+    off = got["offsets"]
+    assert off[0] == 0 and np.all(np.diff(off) >= 1) and off[-1] == len(got["m"])
+    lo = common.C1_BOX[0::2]; hi = common.C1_BOX[1::2]
+    with np.errstate(divide="ignore"):
+        t = np.where(k > 0, (hi - r) / k, np.where(k < 0, (lo - r) / k, np.inf)).min(axis=1)
+    np.testing.assert_allclose(got["s"][off[1:] - 1], t, rtol=1e-8)      # the tree walker adds eps = 1e-12 x diagonal per crossing
