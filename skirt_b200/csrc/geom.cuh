@@ -1,5 +1,5 @@
-// Grid traversal device functions: one "walk" per grid type, each a restructured-for-GPU rendition of
-// the reference's DustGrid::path() that feeds segments to a Sink instead of a std::vector.
+// Grid traversal device functions: one stepping walker per grid type, each a restructured-for-GPU rendition of
+// the reference's DustGrid::path() that yields one segment per step instead of filling a std::vector.
 //
 // Bit-exactness contract: compiled with -fmad=false, IEEE division, the reference's
 // operand order, comparison asymmetries and eps conventions, so that cell sequences are identical and
@@ -12,9 +12,9 @@
 //   AdaptiveMesh   AdaptiveMesh.cpp:297-367 (+ AdaptiveMeshNode.cpp:109-151, Box::cellindices Box.hpp:134-139)
 //   Voronoi        VoronoiMesh.cpp:749-844 (+ cellIndex :512-541, kd Node::nearest :180-225)
 //
-// A Sink provides `bool add(int m, double ds)` with DustGridPath::addSegment semantics handled by the
-// caller-side helper sinkAdd(): segments with ds<=0 are dropped (DustGridPath.cpp:46-53).  add()
-// returns false to stop the walk early (propagation target reached / distance exceeded).
+// Every grid type provides a stepping walker: start() = entry (moveInside) + point location, step() = one
+// crossing, returning whether a segment (m, ds) is to be added (DustGridPath::addSegment drops ds <= 0,
+// DustGridPath.cpp:46-53).  The scheduler in wavefront.cuh drives them and hands the segments to a job.
 #pragma once
 #include <cfloat>
 #include <cmath>
@@ -34,13 +34,6 @@ struct Entry
     double ds[3];
     int n;
 };
-
-template<class Sink> __device__ __forceinline__ bool flushEntry(const Entry& en, Sink& sink)
-{
-    for (int i = 0; i < en.n; i++)
-        if (en.ds[i] > 0) { if (!sink.add(-1, en.ds[i])) return false; }
-    return true;
-}
 
 __device__ __forceinline__ bool finite3(double a, double b, double c)
 {
@@ -193,20 +186,6 @@ struct CartWalker
         return ds > 0;
     }
 };
-
-template<class Sink>
-__device__ void walkCart(const CartGrid& g, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
-{
-    Counters* ctr = nullptr;
-    CartWalker w; Entry en;
-    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
-    if (!flushEntry(en, sink)) return;
-    while (w.alive)
-    {
-        int m; double ds;
-        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // DustGridPath::moveInside, DustGridPath.cpp:57-150.  box = xmin,ymin,zmin,xmax,ymax,zmax.
@@ -439,19 +418,6 @@ struct TreeWalker
     }
 };
 
-template<class Sink>
-__device__ void walkTree(const TreeGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
-{
-    TreeWalker w; Entry en;
-    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
-    if (!flushEntry(en, sink)) return;
-    while (w.alive)
-    {
-        int m; double ds;
-        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Adaptive mesh
 // ---------------------------------------------------------------------------------------------------
@@ -553,19 +519,6 @@ struct AMeshWalker
         return ds > 0;
     }
 };
-
-template<class Sink>
-__device__ void walkAMesh(const AMeshGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
-{
-    AMeshWalker w; Entry en;
-    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
-    if (!flushEntry(en, sink)) return;
-    while (w.alive)
-    {
-        int m; double ds;
-        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
-    }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Voronoi
@@ -763,18 +716,5 @@ struct VoroWalker
         return true;
     }
 };
-
-template<class Sink>
-__device__ void walkVoro(const VoroGrid& g, Counters* ctr, double x, double y, double z, double kx, double ky, double kz, Sink& sink)
-{
-    VoroWalker w; Entry en;
-    if (!w.start(g, ctr, x, y, z, kx, ky, kz, en)) return;
-    if (!flushEntry(en, sink)) return;
-    while (w.alive)
-    {
-        int m; double ds;
-        if (w.step(g, ctr, m, ds)) { if (!sink.add(m, ds)) return; }
-    }
-}
 
 }   // namespace skg

@@ -283,95 +283,6 @@ static __device__ void generatePosition(const SourceDev& s, Philox& rng, double&
     }
 }
 
-// ---- sinks for the life cycle --------------------------------------------------------------------------
-
-// pass 1: DustSystem::fillOpticalDepth + simulateescapeandabsorption (MonteCarloSimulation.cpp:438-515) streamed per
-// segment.  The reference evaluates L*exp(-tau_start)*(-expm1(-dtau)) per segment; here the attenuation factor
-// E = exp(-tau_start) is carried along multiplicatively, E += E*expm1(-dtau), which needs one transcendental per
-// segment instead of two (the two forms agree to a few ulp over a path).
-struct AbsorbSink
-{
-    KappaRho kr; const Medium* med; int ell;
-    double L;               // packet luminosity at the start of the path
-    double albedo;          // Ncomp==1: DustMix::albedo(ell)
-    double* labs;           // Labs + ell*Ncells (wavelength-major) or null
-    double tau = 0, E = 1.0, Lsca = 0;
-    int n = 0, nAbs = 0;
-    __device__ __forceinline__ bool add(int m, double ds)
-    {
-        n++;
-        if (m < 0) return true;             // rho(-1,h) = 0: dtau = 0, nothing absorbed
-        int Ncomp = med->Ncomp;
-        if (Ncomp == 1)
-        {
-            double dtau = kr(m) * ds;
-            if (labs)
-            {
-                double x = expm1(-dtau);
-                atomicAdd(labs + m, (1.0 - albedo) * (L * E * (-x)));
-                E += E * x;
-                nAbs++;
-            }
-            tau += dtau;
-        }
-        else
-        {
-            double ksca = 0.0, kext = 0.0, krr = 0.0;
-            for (int h = 0; h < Ncomp; h++)
-            {
-                double rho = __ldg(med->rho + (size_t)m * Ncomp + h);
-                ksca += rho * __ldg(med->ksca + (size_t)h * med->Nlambda + ell);
-                double ke = __ldg(med->kext + (size_t)h * med->Nlambda + ell);
-                kext += rho * ke;
-                krr += ke * rho;
-            }
-            double alb = (kext > 0.0) ? ksca / kext : 0.0;
-            double dtau = krr * ds;
-            double x = expm1(-dtau);
-            double Lintm = L * E * (-x);
-            E += E * x;
-            Lsca += alb * Lintm;
-            if (labs) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
-            tau += dtau;
-        }
-        return true;
-    }
-};
-
-// pass 2: DustGridPath::pathlength(tau) evaluated on the fly (DustGridPath.cpp:162-173)
-struct PropagateSink
-{
-    KappaRho kr; double target;
-    double sPrev = 0, tauPrev = 0, result = 0;
-    bool found = false;
-    int n = 0;
-    __device__ __forceinline__ bool add(int m, double ds)
-    {
-        n++;
-        double sNew = sPrev + ds;
-        double tauNew = tauPrev + kr(m) * ds;
-        if (target < tauNew)
-        {
-            result = sPrev + ((target - tauPrev) / (tauNew - tauPrev)) * (sNew - sPrev);     // NR::interpolate_linlin
-            found = true;
-            return false;
-        }
-        sPrev = sNew; tauPrev = tauNew;
-        return true;
-    }
-    __device__ __forceinline__ double s() const { return found ? result : sPrev; }
-};
-
-template<int KIND, class Sink>
-__device__ __forceinline__ void walkMC(const GridSetMC& G, const CartGrid& cart, Counters* ctr,
-                                       double x, double y, double z, double kx, double ky, double kz, Sink& sink)
-{
-    if (KIND == GRID_CART) walkCart(cart, x, y, z, kx, ky, kz, sink);
-    else if (KIND == GRID_TREE) walkTree(G.tree, ctr, x, y, z, kx, ky, kz, sink);
-    else if (KIND == GRID_AMESH) walkAMesh(G.amesh, ctr, x, y, z, kx, ky, kz, sink);
-    else walkVoro(G.voro, ctr, x, y, z, kx, ky, kz, sink);
-}
-
 template<int KIND>
 __device__ __forceinline__ int whichCellMC(const GridSetMC& G, const CartGrid& cart, double x, double y, double z)
 {

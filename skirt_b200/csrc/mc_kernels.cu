@@ -327,7 +327,9 @@ template<int KIND> struct AbsorbJob
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     int* counts;
     double rx, ry, rz, dx, dy, dz;
-    // AbsorbSink state (see mc_device.cuh): one expm1 per segment, E = exp(-tau) carried multiplicatively
+    // escape + absorption state.  The reference evaluates L*exp(-tau_start)*(-expm1(-dtau)) per segment
+    // (MonteCarloSimulation.cpp:452); here the attenuation E = exp(-tau_start) is carried along multiplicatively,
+    // E += E*expm1(-dtau): one transcendental per segment instead of two (the forms agree to a few ulp over a path)
     KappaRho kr; double L, albedo, tau, E, Lsca; double* labs;
     int slot, ell, nscatt; unsigned rngCtr; bool survive; unsigned long long id; double target;
     double kext0, pendRho, pendDs; int pendM;      // one-component media: gather now, absorb one crossing later

@@ -1,6 +1,4 @@
-// Segment sinks for the grid walkers (see geom.cuh).  Every sink reproduces
-// DustGridPath::addSegment's running length `_s += ds` (DustGridPath.cpp:46-53); walkers call add()
-// only for ds > 0.
+// The opacity functor shared by every job that turns path segments into optical depth.
 #pragma once
 #include "tables.h"
 
@@ -19,46 +17,6 @@ struct KappaRho
         for (int h = 0; h < Ncomp; h++)
             result += __ldg(kextEll + (size_t)h * Nlambda) * (m >= 0 ? __ldg(rho + (size_t)m * Ncomp + h) : 0.0);
         return result;
-    }
-};
-
-// counts segments (first pass of the batched path())
-struct CountSink
-{
-    int n = 0;
-    __device__ __forceinline__ bool add(int, double) { n++; return true; }
-};
-
-// records Segment{m, ds, s, dtau, tau}: DustGridPath::addSegment + fillOpticalDepth (DustGridPath.hpp:117-129)
-struct RecordSink
-{
-    int* m; double* ds; double* s; double* dtau; double* tau;   // already offset to this ray's first segment
-    KappaRho kr; bool optical;
-    double sacc = 0, tacc = 0;
-    int n = 0;
-    __device__ __forceinline__ bool add(int mm, double d)
-    {
-        sacc += d;
-        double dt = 0;
-        if (optical) { dt = kr(mm) * d; tacc += dt; }
-        m[n] = mm; ds[n] = d; s[n] = sacc; dtau[n] = dt; tau[n] = tacc;
-        n++;
-        return true;
-    }
-};
-
-// DustGridPath::opticalDepth(kapparho, distance), DustGridPath.hpp:97-108: the overshooting segment is
-// counted in full, then the walk stops.
-struct TauSink
-{
-    KappaRho kr; double distance;
-    double sacc = 0, tau = 0;
-    int n = 0;
-    __device__ __forceinline__ bool add(int mm, double d)
-    {
-        sacc += d; n++;
-        tau += kr(mm) * d;
-        return !(sacc > distance);
     }
 };
 

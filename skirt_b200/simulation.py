@@ -347,6 +347,65 @@ class StellarSystem:
         return np.array([c.Lv for c in self.comps])
 
 
+# ---- dust emission spectra (the step between the shooting phases) ----------------------------------------
+class GreyBodyDustLib:
+    """AllCellsDustLib + GreyBodyDustEmissivity for single-population mixes, vectorised over the cells:
+    mean intensity J (DustSystem::meanintensityv, DustSystem.cpp:935-955), equilibrium temperature through the
+    Planck-integrated absorption table (DustMix.cpp:238-262, :689-711), emissivity kappa_abs*B(T)
+    (GreyBodyDustEmissivity.cpp:22-45) and the normalised cell SEDs (DustLib.cpp:126-158).  Host-side numpy: this is
+    set-up between phases, not part of the hot path."""
+    H, C, K = 6.62606957e-34, 2.99792458e8, 1.3806488e-23      # Units.cpp
+
+    def __init__(self, lambdagrid, kappaabs, rho, volumes):
+        self.lam = np.asarray(lambdagrid.lambdav); self.dlam = np.asarray(lambdagrid.dlambdav)
+        self.kabs = np.atleast_2d(np.asarray(kappaabs, dtype=np.float64))          # [Ncomp, Nlambda]
+        self.rho = np.asarray(rho, dtype=np.float64).reshape(len(volumes), -1)       # [Ncells, Ncomp]
+        self.vol = np.asarray(volumes, dtype=np.float64)
+        NT = 1000; q = 500.0 ** (1.0 / (NT - 1)); qn = q ** NT                       # NR::powgrid(_Tv, 0, 5000, 1000, 500)
+        self.Tv = 0.0 + (1.0 - q ** np.arange(NT + 1)) / (1.0 - qn) * 5000.0
+        self.planckabs = np.zeros((self.kabs.shape[0], NT + 1))
+        for p_ in range(1, NT + 1):
+            self.planckabs[:, p_] = (self.kabs * (self.planck(self.Tv[p_]) * self.dlam)).sum(1)
+
+    def planck(self, T):
+        x = self.H * self.C / (self.lam * self.K * T)
+        with np.errstate(over="ignore"):
+            return 2.0 * self.H * self.C * self.C / self.lam ** 5 / (np.exp(x) - 1.0)
+
+    def meanintensity(self, Labs):
+        """Labs[Ncells, Nlambda] -> J[Ncells, Nlambda]"""
+        kabsrho = self.rho @ self.kabs                                               # [Ncells, Nlambda]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            J = Labs / (kabsrho * (4.0 * math.pi * self.vol)[:, None]) / self.dlam[None, :]
+        return np.where(np.isfinite(J), J, 0.0)
+
+    def luminosities(self, Labs):
+        """normalised emission SED of every cell, [Ncells, Nlambda] (DustLib::luminosity(m, ell))"""
+        J = self.meanintensity(Labs)
+        Ncells, Ncomp = self.rho.shape
+        ev = np.zeros((Ncomp, Ncells, len(self.lam)))
+        for h in range(Ncomp):
+            pa = (J * (self.kabs[h] * self.dlam)[None, :]).sum(1)                    # DustMix::equilibrium
+            tab = self.planckabs[h]
+            p_ = np.clip(np.searchsorted(tab, pa, side="right") - 1, 0, len(tab) - 2)   # NR::locate_clip
+            p_ = np.where(pa < tab[0], 0, p_)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                T = self.Tv[p_] + (pa - tab[p_]) / (tab[p_ + 1] - tab[p_]) * (self.Tv[p_ + 1] - self.Tv[p_])
+            x = self.H * self.C / (self.lam[None, :] * self.K * T[:, None])
+            with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+                B = 2.0 * self.H * self.C * self.C / self.lam[None, :] ** 5 / (np.exp(x) - 1.0)
+            ev[h] = self.kabs[h][None, :] * B
+        if Ncomp == 1:
+            Lv = ev[0]
+        else:
+            Lv = np.einsum("hml,mh->ml", ev, self.rho)
+        Lv = Lv * self.dlam[None, :]
+        tot = Lv.sum(1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            Lv = np.where(tot[:, None] > 0, Lv / tot[:, None], Lv)
+        return np.where(np.isfinite(Lv), Lv, 0.0)
+
+
 # ---- instruments ----------------------------------------------------------------------------------------------------------
 class _DistantInstrument:
     kind = 0
@@ -423,6 +482,50 @@ class MonteCarloSimulation:
                                      seed=self.seed, stream_offset=offset)
         if self.nranks > 1:
             self.engine.allreduce_results()      # Instrument::sumResults / PanDustSystem::sumResults
+        return st
+
+    # ---- dust emission phases (PanMonteCarloSimulation.cpp:105-264) --------------------------------------------------
+    def _cell_luminosities(self, dustlib):
+        """Lv[ell, m] = Labsbol[m] * dustluminosity(m, ell) (PanMonteCarloSimulation.cpp:193-198, 275-280)"""
+        Labs = self.engine.fetch_labs()
+        try:
+            Labs = Labs + self.engine.fetch_labs_dust()
+        except EngineError:
+            pass
+        Labsbol = Labs.sum(1)
+        return np.ascontiguousarray((Labsbol[:, None] * dustlib.luminosities(Labs)).T), Labs
+
+    def rundustselfabsorption(self, dustlib, cycles=0):
+        """three stages of self-absorption cycles with 1/10, 1/3 and all of the packets, each until the absorbed dust
+        luminosity changes by less than 1 %, 0.7 %, 0.5 % (PanMonteCarloSimulation.cpp:105-185)"""
+        prev = 0.0; history = []
+        for stage, (factor, epsmax) in enumerate(((1. / 10., 0.010), (1. / 3., 0.007), (1., 0.005))):
+            ncyclesmax = cycles if cycles else 100
+            convergence = False; cycle = 1
+            while cycle <= ncyclesmax and (not convergence or cycles):
+                Lv, _ = self._cell_luminosities(dustlib)
+                self.engine.reset_labs_dust()
+                npr, offset, total = shard_packets(self.packages * factor, self.rank, self.nranks)
+                self.engine.run_dust(1, Lv, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
+                                     scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
+                if self.nranks > 1:
+                    self.engine.allreduce_results()
+                tot = float(self.engine.fetch_labs_dust().sum())
+                eps = abs((tot - prev) / tot) if tot else 0.0
+                prev = tot; history.append((stage, cycle, tot, eps))
+                if (stage < 2 or cycle > 1) and eps < epsmax:
+                    convergence = True
+                cycle += 1
+        return history
+
+    def rundustemission(self, dustlib, emissionBias=0.5, emissionBoost=1.0):
+        """PanMonteCarloSimulation::rundustemission (PanMonteCarloSimulation.cpp:242-264)"""
+        Lv, _ = self._cell_luminosities(dustlib)
+        npr, offset, total = shard_packets(self.packages * emissionBoost, self.rank, self.nranks)
+        st = self.engine.run_dust(2, Lv, npr, total_packages=total, emission_bias=emissionBias, min_weight_reduction=self.mwr,
+                                  min_scatt_events=self.minfs, scatt_bias=self.xi, seed=self.seed + 999983, stream_offset=offset)
+        if self.nranks > 1:
+            self.engine.allreduce_results()
         return st
 
     def results(self, pinned=False):

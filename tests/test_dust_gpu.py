@@ -96,3 +96,43 @@ def test_labs_bolometric_and_random_positions(engine):
     assert st["packets"] == 20000
     sed = engine.fetch_sed(1)
     assert sed[3] > 0 and np.count_nonzero(sed) == 1
+
+
+def test_full_pan_flow_through_the_host_mirror(engine):
+    """stellar emission -> three fixed self-absorption cycles -> dust emission, driven by the Python mirror of
+    PanMonteCarloSimulation with the numpy DustLib, against the same sequence executed by the reference's own classes"""
+    from oracle import skirtref as sr, refspec
+    from skirt_b200 import configs, simulation as sim
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    p = configs.c2_params(n=14, nlambda=25, packages=2e4)
+    spec, L, mixes = refspec.reference_spec(p, threads=os.cpu_count() or 1, dustsamples=5)
+    S = sr.RefSim(spec + "selfabs 1\n", luminosities=L, mixes=mixes).setup()
+    med = S.medium()
+    # engine side: same density table, same mix, same luminosities
+    m = configs.build(p, rho=med["rho"], storeAbsorption=True)
+    m.engine.close(); m.engine = engine
+    m.setup()
+    lib = sim.GreyBodyDustLib(m.lambdagrid, [mixes[0][0]], med["rho"], S.volumes())
+    B = 6
+    ref_sed, gpu_sed = [], []
+    for b in range(B):
+        S.reset(2000 + 1000 * b); S.run_stellar()
+        for stage, factor in enumerate((0.1, 1. / 3., 1.0)):
+            S.prepare_dust(stage == 0); S.run_dust(True, factor)
+        S.prepare_dust(False); S.run_dust(False, 1.0)
+        ref_sed.append(S.instruments()[1]["sed"].copy())
+        engine.reset_results(); engine.reset_labs_dust() if b else None
+        m.seed = 50 + b
+        m.packages = S.packages_per_lambda()
+        m.runstellaremission()
+        m.rundustselfabsorption(lib, cycles=1)
+        m.rundustemission(lib)
+        gpu_sed.append(engine.fetch_sed(1))
+    ref_sed, gpu_sed = np.array(ref_sed), np.array(gpu_sed)
+    # long wavelengths are pure dust emission, short ones pure (attenuated) star light
+    assert gpu_sed.mean(0)[-5:].sum() > 0
+    for sl in (slice(0, 12), slice(15, 25)):
+        a, r = gpu_sed[:, sl].sum(1), ref_sed[:, sl].sum(1)
+        z = (a.mean() - r.mean()) / np.sqrt(a.var(ddof=1) / B + r.var(ddof=1) / B)
+        assert abs(z) < 4 and abs(a.mean() / r.mean() - 1) < 0.02, f"bins {sl}: gpu {a.mean():.6g} ref {r.mean():.6g} z {z:.2f}"
