@@ -125,6 +125,10 @@ typedef struct skg_source
 /* L[h*Nlambda+ell] = StellarComp::luminosity(ell) of component h */
 int skg_sources(skg_engine* e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias);
 
+/* n launches of StellarSystem::launch(pp, ell, 1.0) with the engine's samplers (the kernel the shooting phase uses):
+ * positions r[3n], directions k[3n] and bias-weighted luminosities L[n]; for distribution-level checks */
+int skg_sample_launch(skg_engine* e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
+
 /* ---- instruments: DistantInstrument / SingleFrameInstrument / Frame-, SED-, SimpleInstrument ---------- */
 enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3 };
 typedef struct skg_instrument

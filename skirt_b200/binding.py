@@ -259,6 +259,11 @@ class Engine:
                 s.ntab = len(rv); s.rv = rv.ctypes.data; s.Xv = Xv.ctypes.data
         self._chk(self._lib.skg_sources(self.h, len(comps), arr, L.shape[1], _vp(L), C.c_double(emission_bias)))
 
+    def sample_launch(self, ell, n, seed=1):
+        r = np.zeros((n, 3)); k = np.zeros((n, 3)); L = np.zeros(n)
+        self._chk(self._lib.skg_sample_launch(self.h, int(ell), int(n), C.c_uint64(int(seed)), _vp(r), _vp(k), _vp(L)))
+        return r, k, L
+
     def instruments(self, instr):
         arr = (SkgInstrument * len(instr))()
         for i, d in enumerate(instr):

@@ -349,6 +349,8 @@ int skg_run_stellar(skg_engine* eh, const skg_mc_params* p, skg_mc_stats* stats)
 { return guarded([&]{ if (!p) throw Error("null parameters"); mcRunStellar(E(eh), *p, stats); }); }
 int skg_run_dust(skg_engine* eh, const skg_mc_params* p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats)
 { return guarded([&]{ if (!p) throw Error("null parameters"); mcRunDust(E(eh), *p, phase, emissionBias, mem, Lcell, stats); }); }
+int skg_sample_launch(skg_engine* eh, int ell, int n, uint64_t seed, double* r, double* k, double* L)
+{ return guarded([&]{ mcSampleLaunch(E(eh), ell, n, seed, r, k, L); }); }
 int skg_reset_results(skg_engine* eh) { return guarded([&]{ mcResetResults(E(eh)); }); }
 int skg_reset_labs_dust(skg_engine* eh)
 { return guarded([&]{ Engine& e = E(eh); if (e.labsDust.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labsDust.p, 0, sizeof(double) * e.labsCount, e.stream)); e.sync(); }); }

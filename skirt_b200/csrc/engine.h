@@ -105,6 +105,7 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats);
 void mcResetResults(Engine& e);
 void mcFetchLabs(Engine& e, double* host, int add, int which);
 void mcLabsBolometric(Engine& e, double* host);
+void mcSampleLaunch(Engine& e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
 void mcRunDust(Engine& e, const skg_mc_params& p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats);
 
 }   // namespace skg

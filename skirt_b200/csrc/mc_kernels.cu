@@ -910,6 +910,42 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     }
 }
 
+__global__ void unpackLaunches(const Packet* __restrict__ pool, int n, double* __restrict__ r, double* __restrict__ k, double* __restrict__ L)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const Packet pk = loadPacket(pool + i);
+        r[3 * i] = pk.x; r[3 * i + 1] = pk.y; r[3 * i + 2] = pk.z; k[3 * i] = pk.kx; k[3 * i + 1] = pk.ky; k[3 * i + 2] = pk.kz; L[i] = pk.L;
+    }
+}
+
+// n launches of StellarSystem::launch(pp, ell, L = 1) exactly as the shooting phase performs them (same kernel), for
+// distribution-level checks of the samplers
+void mcSampleLaunch(Engine& e, int ell, int n, uint64_t seed, double* r, double* k, double* L)
+{
+    if (!e.Nsources) throw Error("no sources have been set");
+    if (ell < 0 || ell >= e.NlambdaSrc) throw Error("wavelength index out of range");
+    if (n < 1 || !r || !k || !L) throw Error("skg_sample_launch: bad arguments");
+    McDev P{};
+    P.med.Nlambda = e.NlambdaSrc;
+    P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
+    P.L = e.lumDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>(); P.Ltot = e.lumTotDev.as<double>();
+    P.emissionBias = e.emissionBias; P.phase = SKG_PHASE_STELLAR; P.rngKind = 0;
+    P.NppInt = (unsigned long long)n; P.Lscale = e.lumTotHost[ell];      // unit luminosity per packet before the bias weight
+    P.seed = seed; P.streamOffset = 0;
+    e.mcEllList.upload(&ell, sizeof(int), e.stream); P.ellList = e.mcEllList.as<int>();
+    e.mcPool.ensure(sizeof(Packet) * (size_t)n); P.pool = e.mcPool.as<Packet>(); P.poolNext = P.pool;
+    e.scratchR.ensure(sizeof(double) * 3 * (size_t)n); e.scratchK.ensure(sizeof(double) * 3 * (size_t)n); e.scratchTau.ensure(sizeof(double) * (size_t)n);
+    int blocks = std::max(1, std::min((n + 127) / 128, e.smCount * 16));
+    launchStage<<<blocks, 128, 0, e.stream>>>(P, e.ctr(), n, 0ull, 0);
+    unpackLaunches<<<blocks, 128, 0, e.stream>>>(P.pool, n, e.scratchR.as<double>(), e.scratchK.as<double>(), e.scratchTau.as<double>());
+    e.launches += 2; SKG_CUDA(cudaGetLastError());
+    SKG_CUDA(cudaMemcpyAsync(r, e.scratchR.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+    SKG_CUDA(cudaMemcpyAsync(k, e.scratchK.p, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+    SKG_CUDA(cudaMemcpyAsync(L, e.scratchTau.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+    e.sync();
+}
+
 void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats)
 {
     if (e.gridKind == GRID_NONE && e.med.rho) throw Error("no dust grid has been set");

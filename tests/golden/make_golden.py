@@ -83,6 +83,17 @@ def sampler_case():
         out[f"R_quant_{ell}"] = np.quantile(np.hypot(r[:, 0], r[:, 1]), [0.1, 0.25, 0.5, 0.75, 0.9])
         out[f"z_quant_{ell}"] = np.quantile(np.abs(r[:, 2]), [0.1, 0.25, 0.5, 0.75, 0.9])
     out["L"] = np.array(L)
+    # an exponential disk with two spiral arms (C3's stellar geometry)
+    spiral = dict(arms=2, pitch=float(np.radians(20)), radius=4000 * common.PC, phase=0.0, weight=1.0, index=1)
+    cfg = common.cfg_c1(n=4, packages=10)
+    cfg["sources"][0]["spiral"] = spiral
+    Ssp = common.make_ref(cfg).setup()
+    r, k, Lw = Ssp.sample_launch(0, 400000)
+    phi = np.arctan2(r[:, 1], r[:, 0]); R = np.hypot(r[:, 0], r[:, 1])
+    out["spiral_R_quant"] = np.quantile(R, [0.1, 0.25, 0.5, 0.75, 0.9])
+    ring = (R > 3000 * common.PC) & (R < 5000 * common.PC)
+    out["spiral_phi_hist"] = np.histogram(phi[ring], bins=24, range=(-np.pi, np.pi))[0] / ring.sum()
+    out["spiral_n"] = np.array([ring.sum()])
     np.savez_compressed(os.path.join(HERE, "launch_c2.npz"), **out)
     print("launch_c2 written")
 

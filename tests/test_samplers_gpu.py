@@ -1,0 +1,95 @@
+"""Launch samplers and the multi-component / SimpleInstrument branches of the life cycle."""
+import os
+
+import numpy as np
+import pytest
+
+import common
+
+pytestmark = pytest.mark.gpu
+
+
+def test_c2_launch_distributions_match_the_reference(engine):
+    """Sersic bulge + exponential disk with composite emission bias: moments and quantiles of 4e5 launches against the
+    golden statistics of 2e5 launches of the reference's StellarSystem::launch"""
+    from skirt_b200 import configs
+    z = np.load(os.path.join(common.GOLDEN, "launch_c2.npz"))
+    p = configs.c2_params(n=4, nlambda=8, packages=10)
+    sim = configs.build(p)
+    sim.engine.close(); sim.engine = engine
+    engine.sources([c.geometry.sampler() for c in sim.ss.comps], sim.ss.luminosities(), sim.ss.emissionBias)
+    n, nref = 400000, 200000
+    for ell in (0, 4):
+        r, k, L = engine.sample_launch(ell, n, seed=5 + ell)
+        # isotropic directions, weights average to one (unbiased estimator), second moment as the reference's
+        assert np.all(np.abs(k.mean(0)) < 5 / np.sqrt(n)) and np.allclose(np.linalg.norm(k, axis=1), 1.0, atol=1e-12)
+        assert abs(L.mean() - 1.0) < 5 * L.std() / np.sqrt(n)
+        assert abs(L.mean() - z[f"L_mean_{ell}"][0]) < 5 * L.std() * np.sqrt(1 / n + 1 / nref)
+        assert abs((L * L).mean() / z[f"L_sq_{ell}"][0] - 1) < 0.02
+        # positions: quantiles of the cylinder radius and |z| within the sampling error of a quantile
+        R = np.hypot(r[:, 0], r[:, 1])
+        for q, got, ref in zip([0.1, 0.25, 0.5, 0.75, 0.9], np.quantile(R, [0.1, 0.25, 0.5, 0.75, 0.9]), z[f"R_quant_{ell}"]):
+            assert abs(got / ref - 1) < 0.015, (ell, q, got, ref)
+        for got, ref in zip(np.quantile(np.abs(r[:, 2]), [0.1, 0.25, 0.5, 0.75, 0.9]), z[f"z_quant_{ell}"]):
+            assert abs(got / ref - 1) < 0.02
+        assert np.all(np.abs(r.mean(0)) < 6 * r.std(0) / np.sqrt(n))
+
+
+def test_spiral_arm_sampler(engine):
+    """SpiralStructureGeometryDecorator::generatePosition: radial distribution unchanged, azimuthal distribution in the
+    3-5 kpc ring follows the two-armed perturbation (golden: the reference's own sampler)"""
+    z = np.load(os.path.join(common.GOLDEN, "launch_c2.npz"))
+    spiral = dict(arms=2, pitch=float(np.radians(20)), radius=4000 * common.PC, phase=0.0, weight=1.0, index=1)
+    engine.sources([dict(geometry=1, p=[4000 * common.PC, 350 * common.PC, 0, 0, 0], spiral=spiral)], np.array([[1.0]]), 0.5)
+    r, k, L = engine.sample_launch(0, 800000, seed=3)
+    R = np.hypot(r[:, 0], r[:, 1]); phi = np.arctan2(r[:, 1], r[:, 0])
+    for got, ref in zip(np.quantile(R, [0.1, 0.25, 0.5, 0.75, 0.9]), z["spiral_R_quant"]):
+        assert abs(got / ref - 1) < 0.01
+    ring = (R > 3000 * common.PC) & (R < 5000 * common.PC)
+    h = np.histogram(phi[ring], bins=24, range=(-np.pi, np.pi))[0] / ring.sum()
+    sig = np.sqrt(z["spiral_phi_hist"] * (1 / ring.sum() + 1 / z["spiral_n"][0]))
+    assert np.all(np.abs(h - z["spiral_phi_hist"]) < 5 * sig)
+    assert h.max() / h.min() > 3            # the arms are really there
+
+
+def test_two_dust_components_and_simple_instrument(engine):
+    """two dust components with different mixes (per-cell albedo, component choice at scattering, peel-off weights:
+    MonteCarloSimulation.cpp:474-514, DustSystem.cpp:879-893, :319-340) and a SimpleInstrument (frame + SED), against runs
+    of the reference's own code"""
+    from oracle import skirtref as sr
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    PC = common.PC
+    cfg = common.cfg_c1(n=20, packages=1e5, storeabs=1, threads=os.cpu_count() or 1, dustsamples=10)
+    mixA = ([900.0], [1700.0], [0.55]); mixB = ([2500.0], [400.0], [-0.2])
+    cfg["dust"] = [dict(tau=0.8, lam=0.55e-6, geometry=1, p=[4000 * PC, 140 * PC, 0.0, 0.0, 0.0], mix=mixA),
+                   dict(tau=0.5, lam=0.55e-6, geometry=1, p=[2500 * PC, 500 * PC, 0.0, 0.0, 0.0], mix=mixB)]
+    cfg["instruments"] = [dict(kind=3, name="simple", distance=1e7 * PC, inclination=float(np.radians(70)), azimuth=0.3, positionAngle=0.2,
+                               Nxp=60, fovxp=50000 * PC, Nyp=40, fovyp=30000 * PC),
+                          dict(kind=2, name="sed0", distance=1e7 * PC, inclination=0.0)]
+    S = common.make_ref(cfg).setup()
+    assert S.Ncomp == 2
+    tables, medium, L = S.grid_tables(), S.medium(), S.luminosities()
+    common.setup_engine(engine, cfg, tables, medium, L)
+    Npp = S.packages_per_lambda()
+    B = 12
+    ref = dict(frame=[], sed=[], sed0=[], labs=[]); gpu = dict(frame=[], sed=[], sed0=[], labs=[])
+    for b in range(B):
+        S.reset(10 + 1000 * b); S.run_stellar(); ins = S.instruments()
+        ref["frame"].append(ins[0]["frame"].copy()); ref["sed"].append(ins[0]["sed"].copy()); ref["sed0"].append(ins[1]["sed"].copy())
+        ref["labs"].append(S.labs().ravel().copy())
+        engine.reset_results(); engine.run_stellar(Npp, store_absorption=True, seed=900 + b)
+        gpu["frame"].append(engine.fetch_frame(0)); gpu["sed"].append(engine.fetch_sed(0)); gpu["sed0"].append(engine.fetch_sed(1))
+        gpu["labs"].append(engine.fetch_labs().ravel())
+    for name in ref:
+        a, r = np.array(gpu[name]).reshape(B, -1), np.array(ref[name]).reshape(B, -1)
+        ta, tr = a.sum(1), r.sum(1)
+        zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / B + tr.var(ddof=1) / B)
+        assert abs(zt) < 3.5 and abs(ta.mean() / tr.mean() - 1) < 0.01, f"{name}: gpu {ta.mean():.6g} ref {tr.mean():.6g} z {zt:.2f}"
+        if a.shape[1] > 10:
+            ma, mr = a.mean(0), r.mean(0); sa, sr_ = a.std(0, ddof=1) / np.sqrt(B), r.std(0, ddof=1) / np.sqrt(B)
+            ok = (sa < 0.3 * ma) & (sr_ < 0.3 * mr) & (sa > 0) & (sr_ > 0)
+            zz = common.zscores(ma[ok], sa[ok], mr[ok], sr_[ok])
+            assert np.mean(np.abs(zz) < 3) > 0.96 and abs(zz.mean()) < 0.3, f"{name}: {np.mean(np.abs(zz) < 3):.4f} within 3 sigma, mean z {zz.mean():.3f}"
+    # the SimpleInstrument's SED is the sum of its frame plus the packets that fall outside the frame
+    assert np.array(gpu["sed"]).sum() >= np.array(gpu["frame"]).sum() * (1 - 1e-12)
