@@ -280,8 +280,18 @@ struct TreeWalker
 {
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
-    int node;
+    double bx[6];               // box of the current node, carried over from the neighbour test that selected it
+    int nb[7];                  // neighbour list offsets of the current node's six walls (Neighbor search)
+    int node, cellv;
     bool alive;
+
+    // everything a crossing needs from the node tables, fetched as soon as the node is known
+    __device__ __forceinline__ void loadNode(const TreeGrid& g, bool withBox)
+    {
+        if (withBox) { const double* b = g.box + 6 * (size_t)node; for (int c = 0; c < 6; c++) bx[c] = __ldg(b + c); }
+        cellv = __ldg(g.cell + node);
+        if (g.search == 1) { const int* s = g.nbrStart + 6 * (size_t)node; for (int w = 0; w < 7; w++) nb[w] = __ldg(s + w); }
+    }
 
     __device__ __forceinline__ bool start(const TreeGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
     {
@@ -291,6 +301,7 @@ struct TreeWalker
         if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
         node = treeWhichNode(g, x, y, z);
         if (node < 0) return false;
+        loadNode(g, true);
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
@@ -299,14 +310,13 @@ struct TreeWalker
     __device__ __forceinline__ bool step(const TreeGrid& g, Counters* ctr, int& mseg, double& ds)
     {
         const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
-        const double* b = g.box + 6 * (size_t)node;
-        const double xnext = nx ? b[0] : b[3];
-        const double ynext = ny ? b[1] : b[4];
-        const double znext = nz ? b[2] : b[5];
+        const double xnext = nx ? bx[0] : bx[3];
+        const double ynext = ny ? bx[1] : bx[4];
+        const double znext = nz ? bx[2] : bx[5];
         const double dsx = (fabs(kx) > 1e-15) ? divInvariant(xnext - x, kx, rkx) : SKG_DBL_MAX;
         const double dsy = (fabs(ky) > 1e-15) ? divInvariant(ynext - y, ky, rky) : SKG_DBL_MAX;
         const double dsz = (fabs(kz) > 1e-15) ? divInvariant(znext - z, kz, rkz) : SKG_DBL_MAX;
-        mseg = __ldg(g.cell + node);
+        mseg = cellv;
         if (g.search != 2)
         {
             // TopDown (TreeDustGrid.cpp:412-456) and Neighbor (:460-521)
@@ -320,15 +330,20 @@ struct TreeWalker
             z += (ds + eps) * kz;
 
             const int oldnode = node;
+            bool haveBox = false;
             if (g.search == 1)
             {
                 // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first neighbour whose closed box contains r
-                int beg = __ldg(g.nbrStart + 6 * (size_t)node + wall), end = __ldg(g.nbrStart + 6 * (size_t)node + wall + 1);
+                const int beg = wall == 0 ? nb[0] : wall == 1 ? nb[1] : wall == 2 ? nb[2] : wall == 3 ? nb[3] : wall == 4 ? nb[4] : nb[5];
+                const int end = wall == 0 ? nb[1] : wall == 1 ? nb[2] : wall == 2 ? nb[3] : wall == 3 ? nb[4] : wall == 4 ? nb[5] : nb[6];
                 node = -1;
                 for (int q = beg; q < end; q++)
                 {
-                    int cand = __ldg(g.nbrIds + q);
-                    if (boxContains(g.box + 6 * (size_t)cand, x, y, z)) { node = cand; break; }
+                    const int cand = __ldg(g.nbrIds + q);
+                    const double* cb = g.box + 6 * (size_t)cand;
+                    const double c0 = __ldg(cb), c1 = __ldg(cb + 1), c2 = __ldg(cb + 2), c3 = __ldg(cb + 3), c4 = __ldg(cb + 4), c5 = __ldg(cb + 5);
+                    if (x >= c0 && x <= c3 && y >= c1 && y <= c4 && z >= c2 && z <= c5)
+                    { node = cand; bx[0] = c0; bx[1] = c1; bx[2] = c2; bx[3] = c3; bx[4] = c4; bx[5] = c5; haveBox = true; break; }
                 }
                 if (node < 0) node = treeWhichNode(g, x, y, z);
             }
@@ -339,9 +354,11 @@ struct TreeWalker
                 atomicAdd(&ctr->stuckEscaped, 1ull);
                 x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
                 node = treeWhichNode(g, x, y, z);
+                haveBox = false;
                 if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
             }
             if (node < 0) alive = false;
+            else loadNode(g, !haveBox);
             return ds > 0;
         }
 
@@ -414,6 +431,7 @@ struct TreeWalker
         }
         else { alive = false; return false; }
         node = l;
+        loadNode(g, true);
         return ds > 0;
     }
 };
@@ -464,8 +482,18 @@ struct AMeshWalker
 {
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
-    int node;
+    double bx[6];               // box of the current node (carried over from the neighbour test that selected it)
+    int wn[6];                  // the node beyond each wall of the current leaf
+    int node, cellv;
     bool alive;
+
+    __device__ __forceinline__ void loadNode(const AMeshGrid& g, bool withBox)
+    {
+        if (withBox) { const double* b = g.box + 6 * (size_t)node; for (int c = 0; c < 6; c++) bx[c] = __ldg(b + c); }
+        cellv = __ldg(g.cell + node);
+        const int* w = g.wallNbr + 6 * (size_t)node;
+        for (int c = 0; c < 6; c++) wn[c] = __ldg(w + c);
+    }
 
     __device__ __forceinline__ bool start(const AMeshGrid& g, Counters* ctr, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
     {
@@ -475,6 +503,7 @@ struct AMeshWalker
         if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
         node = ameshWhichNode(g, x, y, z);
         if (node < 0) { if (node == -2) atomicAdd(&ctr->errors, 1ull); return false; }
+        loadNode(g, true);
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
@@ -484,10 +513,9 @@ struct AMeshWalker
     {
         const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
         const double eps = g.eps;
-        const double* b = g.box + 6 * (size_t)node;
-        const double xnext = nx ? b[0] : b[3];
-        const double ynext = ny ? b[1] : b[4];
-        const double znext = nz ? b[2] : b[5];
+        const double xnext = nx ? bx[0] : bx[3];
+        const double ynext = ny ? bx[1] : bx[4];
+        const double znext = nz ? bx[2] : bx[5];
         const double dsx = (fabs(kx) > 1e-15) ? divInvariant(xnext - x, kx, rkx) : SKG_DBL_MAX;
         const double dsy = (fabs(ky) > 1e-15) ? divInvariant(ynext - y, ky, rky) : SKG_DBL_MAX;
         const double dsz = (fabs(kz) > 1e-15) ? divInvariant(znext - z, kz, rkz) : SKG_DBL_MAX;
@@ -495,16 +523,24 @@ struct AMeshWalker
         if (dsx <= dsy && dsx <= dsz) { ds = dsx; wall = nx ? 0 : 1; }
         else if (dsy <= dsx && dsy <= dsz) { ds = dsy; wall = ny ? 2 : 3; }
         else { ds = dsz; wall = nz ? 4 : 5; }
-        mseg = __ldg(g.cell + node);
+        mseg = cellv;
         // r += (ds+eps)*k   (Vec operator*(double,Vec), Vec.hpp)
         x += (ds + eps) * kx;
         y += (ds + eps) * ky;
         z += (ds + eps) * kz;
 
         const int oldnode = node;
-        int cand = __ldg(g.wallNbr + 6 * (size_t)node + wall);
-        if (cand >= 0 && boxContains(g.box + 6 * (size_t)cand, x, y, z)) node = cand;
-        else node = ameshWhichNode(g, x, y, z);
+        const int cand = wall == 0 ? wn[0] : wall == 1 ? wn[1] : wall == 2 ? wn[2] : wall == 3 ? wn[3] : wall == 4 ? wn[4] : wn[5];
+        bool haveBox = false;
+        node = -3;
+        if (cand >= 0)
+        {
+            const double* cb = g.box + 6 * (size_t)cand;
+            const double c0 = __ldg(cb), c1 = __ldg(cb + 1), c2 = __ldg(cb + 2), c3 = __ldg(cb + 3), c4 = __ldg(cb + 4), c5 = __ldg(cb + 5);
+            if (x >= c0 && x <= c3 && y >= c1 && y <= c4 && z >= c2 && z <= c5)
+            { node = cand; bx[0] = c0; bx[1] = c1; bx[2] = c2; bx[3] = c3; bx[4] = c4; bx[5] = c5; haveBox = true; }
+        }
+        if (node == -3) node = ameshWhichNode(g, x, y, z);
         if (node == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
 
         if (node == oldnode)
@@ -512,10 +548,12 @@ struct AMeshWalker
             atomicAdd(&ctr->stuckEscaped, 1ull);
             x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
             node = ameshWhichNode(g, x, y, z);
+            haveBox = false;
             if (node == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
             if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
         }
         if (node < 0) alive = false;
+        else loadNode(g, !haveBox);
         return ds > 0;
     }
 };

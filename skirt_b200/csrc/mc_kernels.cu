@@ -586,8 +586,7 @@ __global__ void transposeLabs(const double* __restrict__ src, double* __restrict
 void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias)
 {
     if (Ncomp < 1 || !comps || Nlambda < 1 || !L) throw Error("skg_sources: bad arguments");
-    if (e.med.Nlambda && Nlambda != e.med.Nlambda) throw Error("sources and medium disagree on the number of wavelengths");
-    for (DevBuf* b : e.sourceBufs) delete b;
+    for (DevBuf* b : e.sourceBufs) delete b;       // (the wavelength count is checked against the medium when a phase starts)
     e.sourceBufs.clear(); e.sources.clear();
     for (int h = 0; h < Ncomp; h++)
     {
