@@ -707,36 +707,51 @@ struct VoroWalker
         const int NO_INDEX = -99;
         int mq = NO_INDEX;
         const int beg = __ldg(g.nbrStart + mr), end = __ldg(g.nbrStart + mr + 1);
-        for (int q = beg; q < end; q++)
+        // the neighbour loop of VoronoiMesh.cpp:777-828, four neighbours at a time: ids and particle positions of a
+        // group are fetched together (twelve independent loads in flight), then evaluated in list order so that the
+        // first smallest intersection still wins
+        for (int q0 = beg; q0 < end; q0 += 4)
         {
-            int mi = __ldg(g.nbrIds + q);
-            double si = 0;
-            if (mi >= 0)
+            int mi[4]; double px[4], py[4], pz[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) mi[u] = (q0 + u < end) ? __ldg(g.nbrIds + q0 + u) : -99;
+#pragma unroll
+            for (int u = 0; u < 4; u++)
             {
-                const double* pi = g.particles + 3 * (size_t)mi;
-                double pix = pi[0], piy = pi[1], piz = pi[2];
-                double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;        // n = pi - pr
-                double ndotk = nxv * kx + nyv * ky + nzv * kz;                   // Vec::dot(n,bfk)
-                if (ndotk > 0)
-                {
-                    double px = 0.5 * (pix + prx), py = 0.5 * (piy + pry), pz = 0.5 * (piz + prz);   // p = 0.5*(pi+pr)
-                    si = (nxv * (px - x) + nyv * (py - y) + nzv * (pz - z)) / ndotk;                // dot(n,p-r)/ndotk
-                }
+                const double* pi = g.particles + 3 * (size_t)max(mi[u], 0);
+                px[u] = __ldg(pi); py[u] = __ldg(pi + 1); pz[u] = __ldg(pi + 2);
             }
-            else
+#pragma unroll
+            for (int u = 0; u < 4; u++)
             {
-                switch (mi)
+                if (q0 + u >= end) break;
+                double si = 0;
+                if (mi[u] >= 0)
                 {
-                case -1: si = (g.ext[0] - x) / kx; break;
-                case -2: si = (g.ext[3] - x) / kx; break;
-                case -3: si = (g.ext[1] - y) / ky; break;
-                case -4: si = (g.ext[4] - y) / ky; break;
-                case -5: si = (g.ext[2] - z) / kz; break;
-                case -6: si = (g.ext[5] - z) / kz; break;
-                default: atomicAdd(&ctr->errors, 1ull); alive = false; return false;
+                    const double pix = px[u], piy = py[u], piz = pz[u];
+                    double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;        // n = pi - pr
+                    double ndotk = nxv * kx + nyv * ky + nzv * kz;                   // Vec::dot(n,bfk)
+                    if (ndotk > 0)
+                    {
+                        double qx = 0.5 * (pix + prx), qy = 0.5 * (piy + pry), qz = 0.5 * (piz + prz);   // p = 0.5*(pi+pr)
+                        si = (nxv * (qx - x) + nyv * (qy - y) + nzv * (qz - z)) / ndotk;                // dot(n,p-r)/ndotk
+                    }
                 }
+                else
+                {
+                    switch (mi[u])
+                    {
+                    case -1: si = (g.ext[0] - x) / kx; break;
+                    case -2: si = (g.ext[3] - x) / kx; break;
+                    case -3: si = (g.ext[1] - y) / ky; break;
+                    case -4: si = (g.ext[4] - y) / ky; break;
+                    case -5: si = (g.ext[2] - z) / kz; break;
+                    case -6: si = (g.ext[5] - z) / kz; break;
+                    default: atomicAdd(&ctr->errors, 1ull); alive = false; return false;
+                    }
+                }
+                if (si > 0 && si < sq) { sq = si; mq = mi[u]; }
             }
-            if (si > 0 && si < sq) { sq = si; mq = mi; }
         }
         if (mq == NO_INDEX)
         {
