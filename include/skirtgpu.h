@@ -39,6 +39,8 @@ int skg_launch_count(skg_engine* e, uint64_t* launches);
  * destinations are staged by the driver at a fraction of the PCIe rate) */
 int skg_host_alloc(size_t bytes, void** ptr);
 int skg_host_free(void* ptr);
+/* copy of an engine-owned device array (e.g. the result of skg_dust_cell_luminosities) to the host, on the engine's stream */
+int skg_copy_to_host(skg_engine* e, const void* d_src, void* host, size_t bytes);
 
 /* ---- dust grids: replace DustGrid::path / whichcell / randomPositionInCell (DustGrid.hpp:89-106) -- */
 
@@ -183,6 +185,18 @@ enum { SKG_PHASE_STELLAR = 0, SKG_PHASE_DUST_SELFABS = 1, SKG_PHASE_DUST_EMISSIO
  * (the caller applies the stage factor / emissionBoost, :142, :258). */
 int skg_run_dust(skg_engine* e, const skg_mc_params* p, int phase, double emissionBias, int mem, const double* Lcell,
                  skg_mc_stats* stats);
+/* ---- dust emission spectra between the phases: AllCellsDustLib + GreyBodyDustEmissivity ---------
+ * skg_dust_library sets the tables DustLib::calculate needs (DustLib.cpp:59-193): cell volumes [Ncells], kappa_abs
+ * [Ncomp*Nlambda], wavelengths and bin widths [Nlambda].  skg_dust_cell_luminosities then computes, on the device and
+ * from the device-resident absorption tables,
+ *     Lcell[ell*Ncells + m] = Labs(m) * DustLib::luminosity(m, ell)
+ * i.e. mean intensity (DustSystem::meanintensityv, DustSystem.cpp:935-955) -> equilibrium temperature per component
+ * (DustMix::equilibrium / invplanckabs, DustMix.cpp:689-711, table of :238-262) -> kappa_abs * B(T) (GreyBodyDustEmissivity.cpp:22-45)
+ * -> normalised cell SED (DustLib.cpp:126-158) times the bolometric absorbed luminosity (PanMonteCarloSimulation.cpp:193-198),
+ * and returns the device pointer, ready for skg_run_dust(..., SKG_DEVICE, *d_Lcell, ...). */
+int skg_dust_library(skg_engine* e, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda);
+int skg_dust_cell_luminosities(skg_engine* e, double** d_Lcell);
+
 /* PanDustSystem::rebootLabsdust (PanDustSystem.cpp:330-333), the dust absorption table, and
  * PanDustSystem::Labs(m) (PanDustSystem.cpp:337-348): bolometric absorbed luminosity per cell, stellar + dust */
 int skg_reset_labs_dust(skg_engine* e);

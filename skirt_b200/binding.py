@@ -314,6 +314,29 @@ class Engine:
         self._chk(self._lib.skg_run_dust(self.h, C.byref(p), int(phase), C.c_double(emission_bias), SKG_HOST, _vp(Lc), C.byref(st)))
         return _stats(st)
 
+    def dust_library(self, volumes, kappaabs, lambdav, dlambdav):
+        v = _f64(volumes); k = _f64(np.atleast_2d(kappaabs)); lam = _f64(lambdav); dl = _f64(dlambdav)
+        self._chk(self._lib.skg_dust_library(self.h, _vp(v), _vp(k), _vp(lam), _vp(dl)))
+
+    def dust_cell_luminosities(self):
+        """device pointer of Lcell[Nlambda, Ncells] computed from the device-resident absorption tables"""
+        p = C.c_void_p()
+        self._chk(self._lib.skg_dust_cell_luminosities(self.h, C.byref(p)))
+        return p.value
+
+    def run_dust_device(self, phase, d_Lcell, packages, total_packages=None, emission_bias=0.5, min_weight_reduction=1e4,
+                        min_scatt_events=0.0, scatt_bias=0.5, seed=4357, stream_offset=0, pool_packets=0):
+        p = self._params(packages, total_packages, min_weight_reduction, min_scatt_events, scatt_bias, False, seed,
+                         stream_offset, 0, None, pool_packets)
+        st = SkgMcStats()
+        self._chk(self._lib.skg_run_dust(self.h, C.byref(p), int(phase), C.c_double(emission_bias), SKG_DEVICE, C.c_void_p(int(d_Lcell)), C.byref(st)))
+        return _stats(st)
+
+    def copy_from_device(self, d_ptr, shape):
+        out = np.zeros(shape)
+        self._chk(self._lib.skg_copy_to_host(self.h, C.c_void_p(int(d_ptr)), _vp(out), C.c_size_t(out.nbytes)))
+        return out
+
     def reset_labs_dust(self):
         self._chk(self._lib.skg_reset_labs_dust(self.h))
 

@@ -111,6 +111,9 @@ int skg_host_alloc(size_t bytes, void** ptr)
 { return guarded([&]{ if (!ptr) throw Error("null output"); SKG_CUDA(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault)); }); }
 int skg_host_free(void* ptr) { return guarded([&]{ if (ptr) SKG_CUDA(cudaFreeHost(ptr)); }); }
 
+int skg_copy_to_host(skg_engine* eh, const void* d_src, void* host, size_t bytes)
+{ return guarded([&]{ Engine& e = E(eh); if (!d_src || !host) throw Error("null pointer"); SKG_CUDA(cudaMemcpyAsync(host, d_src, bytes, cudaMemcpyDeviceToHost, e.stream)); e.sync(); }); }
+
 int skg_num_cells(skg_engine* e) { return e ? reinterpret_cast<Engine*>(e)->Ncells : 0; }
 
 int skg_grid_cartesian(skg_engine* eh, const double* xv, int Nx, const double* yv, int Ny, const double* zv, int Nz)
@@ -352,6 +355,10 @@ int skg_run_dust(skg_engine* eh, const skg_mc_params* p, int phase, double emiss
 int skg_sample_launch(skg_engine* eh, int ell, int n, uint64_t seed, double* r, double* k, double* L)
 { return guarded([&]{ mcSampleLaunch(E(eh), ell, n, seed, r, k, L); }); }
 int skg_reset_results(skg_engine* eh) { return guarded([&]{ mcResetResults(E(eh)); }); }
+int skg_dust_library(skg_engine* eh, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda)
+{ return guarded([&]{ if (!volumes || !kappaabs || !lambda || !dlambda) throw Error("skg_dust_library: null table"); mcDustLibrary(E(eh), volumes, kappaabs, lambda, dlambda); }); }
+int skg_dust_cell_luminosities(skg_engine* eh, double** d_Lcell)
+{ return guarded([&]{ if (!d_Lcell) throw Error("null output"); *d_Lcell = mcDustCellLuminosities(E(eh)); }); }
 int skg_reset_labs_dust(skg_engine* eh)
 { return guarded([&]{ Engine& e = E(eh); if (e.labsDust.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labsDust.p, 0, sizeof(double) * e.labsCount, e.stream)); e.sync(); }); }
 int skg_fetch_labs_dust(skg_engine* eh, double* labs, int add)

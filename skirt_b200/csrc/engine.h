@@ -71,6 +71,8 @@ struct Engine
     std::vector<InstrDev> instr; DevBuf instrDev; std::vector<DevBuf*> instrBufs;
     DevBuf labs; int64_t labsCount = 0;    // absorbed luminosity, wavelength-major on the device: labs[ell*Ncells+m]
     DevBuf labsDust;                        // absorbed dust emission (self-absorption cycles), same layout
+    DevBuf libVol, libKabs, libLambda, libDlambda, libTv, libPlanckabs; bool haveDustLib = false;     // DustLib tables
+    DevBuf dustLvOut;                       // output of skg_dust_cell_luminosities
     DevBuf dustLv, dustCdf, dustLtot;       // per-wavelength cell luminosities of a dust phase, their CDFs and totals
     DevBuf labsT;                           // scratch for the (m,ell) row-major copy handed to the host
     DevBuf instrGroupedDev, groupsDev; int Ngroups = 0;    // instruments ordered by line of sight + the groups
@@ -105,6 +107,8 @@ void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats);
 void mcResetResults(Engine& e);
 void mcFetchLabs(Engine& e, double* host, int add, int which);
 void mcLabsBolometric(Engine& e, double* host);
+void mcDustLibrary(Engine& e, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda);
+double* mcDustCellLuminosities(Engine& e);
 void mcSampleLaunch(Engine& e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
 void mcRunDust(Engine& e, const skg_mc_params& p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats);
 

@@ -816,6 +816,133 @@ static void mcBuildCdfs(Engine& e, int Nlambda, int Ncells)
     SKG_CUDA(cudaGetLastError());
 }
 
+// ---- dust emission spectra (DustLib::calculate for AllCellsDustLib + GreyBodyDustEmissivity) ----------------------
+struct DustLibDev
+{
+    const double* labsStel; const double* labsDust;     // [Nlambda*Ncells] wavelength-major, either may be null
+    const double* rho; const double* vol; const double* kabs; const double* lambda; const double* dlambda;
+    const double* Tv; const double* planckabs;          // [NT+1], [Ncomp*(NT+1)]
+    double* out;                                        // Lcell [Nlambda*Ncells]
+    int Ncells, Ncomp, Nlambda, NT;
+};
+
+// PlanckFunction::operator(), PlanckFunction.cpp:24-33 (Units.cpp constants)
+__device__ __forceinline__ double planckB(double lambda, double T)
+{
+    const double h = 6.62606957e-34, c = 2.99792458e8, k = 1.3806488e-23;
+    double x = h * c / (lambda * k * T);
+    return 2.0 * h * c * c / pow(lambda, 5) / (exp(x) - 1.0);
+}
+
+// one thread per cell; the absorption tables are wavelength-major, so every pass over ell is coalesced over the cells
+__global__ void __launch_bounds__(128) dustLibraryKernel(const __grid_constant__ DustLibDev D)
+{
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < D.Ncells; m += gridDim.x * blockDim.x)
+    {
+        const size_t N = D.Ncells;
+        const double fac = 4.0 * M_PI * D.vol[m];
+        double T[8]; double Labsbol = 0;
+        for (int h = 0; h < D.Ncomp; h++) T[h] = 0;
+        // mean intensity and the Planck-weighted absorption of every component (DustMix::equilibrium)
+        double pa[8];
+        for (int h = 0; h < D.Ncomp; h++) pa[h] = 0;
+        for (int ell = 0; ell < D.Nlambda; ell++)
+        {
+            double L = 0;
+            if (D.labsStel) L += D.labsStel[ell * N + m];
+            if (D.labsDust) L += D.labsDust[ell * N + m];
+            Labsbol += L;
+        }
+        // PanDustSystem::Labs(m) sums the stellar table first, then the dust table; keep that order for the bolometric value
+        {
+            double a = 0, b = 0;
+            if (D.labsStel) for (int ell = 0; ell < D.Nlambda; ell++) a += D.labsStel[ell * N + m];
+            if (D.labsDust) for (int ell = 0; ell < D.Nlambda; ell++) b += D.labsDust[ell * N + m];
+            Labsbol = a + b;
+        }
+        for (int ell = 0; ell < D.Nlambda; ell++)
+        {
+            double kabsrho = 0.0;
+            for (int h = 0; h < D.Ncomp; h++) kabsrho += D.kabs[h * D.Nlambda + ell] * D.rho[(size_t)m * D.Ncomp + h];
+            double L = 0;
+            if (D.labsStel) L += D.labsStel[ell * N + m];
+            if (D.labsDust) L += D.labsDust[ell * N + m];
+            double J = L / (kabsrho * fac) / D.dlambda[ell];
+            if (!isfinite(J)) J = 0.0;                              // DustSystem.cpp:951-952
+            for (int h = 0; h < D.Ncomp; h++) pa[h] += D.kabs[h * D.Nlambda + ell] * J * D.dlambda[ell];
+        }
+        for (int h = 0; h < D.Ncomp; h++)
+        {
+            // DustMix::invplanckabs: NR::locate_clip on the table + linear interpolation
+            const double* tab = D.planckabs + (size_t)h * (D.NT + 1);
+            int p = locateClip(tab, pa[h], D.NT + 1);
+            T[h] = D.Tv[p] + ((pa[h] - tab[p]) / (tab[p + 1] - tab[p])) * (D.Tv[p + 1] - D.Tv[p]);
+        }
+        // emission spectrum, converted to luminosities and normalised; written straight into the output, then rescaled
+        double total = 0;
+        for (int ell = 0; ell < D.Nlambda; ell++)
+        {
+            double ev = 0;
+            for (int h = 0; h < D.Ncomp; h++)
+            {
+                double e1 = D.kabs[h * D.Nlambda + ell] * planckB(D.lambda[ell], T[h]);
+                ev += D.Ncomp > 1 ? e1 * D.rho[(size_t)m * D.Ncomp + h] : e1;
+            }
+            double Lv = ev * D.dlambda[ell];
+            if (!isfinite(Lv)) Lv = 0.0;
+            D.out[ell * N + m] = Lv;
+            total += Lv;
+        }
+        const bool emit = Labsbol > 0.0 && total > 0;              // PanMonteCarloSimulation.cpp:196-197
+        for (int ell = 0; ell < D.Nlambda; ell++) D.out[ell * N + m] = emit ? Labsbol * (D.out[ell * N + m] / total) : 0.0;
+    }
+}
+
+void mcDustLibrary(Engine& e, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda)
+{
+    if (!e.med.rho) throw Error("skg_dust_library needs skg_medium first");
+    const int Nl = e.med.Nlambda, C = e.med.Ncomp, N = e.Ncells;
+    if (C > 8) throw Error("at most 8 dust components are supported");
+    e.libVol.upload(volumes, sizeof(double) * N, e.stream); e.libKabs.upload(kappaabs, sizeof(double) * C * Nl, e.stream);
+    e.libLambda.upload(lambda, sizeof(double) * Nl, e.stream); e.libDlambda.upload(dlambda, sizeof(double) * Nl, e.stream);
+    // temperature grid and Planck-integrated absorption coefficients, DustMix.cpp:238-262
+    const int NT = 1000;
+    std::vector<double> Tv(NT + 1), pab((size_t)C * (NT + 1), 0.0);
+    { double q = std::pow(500., 1. / (NT - 1)), qn = std::pow(q, NT); for (int i = 0; i <= NT; ++i) Tv[i] = 0. + (1. - std::pow(q, i)) / (1. - qn) * 5000.; }
+    const double hh = 6.62606957e-34, cc = 2.99792458e8, kk = 1.3806488e-23;
+    for (int p = 1; p <= NT; p++) for (int h = 0; h < C; h++)
+    {
+        double planckabs = 0.0;
+        for (int ell = 0; ell < Nl; ell++)
+        {
+            double x = hh * cc / (lambda[ell] * kk * Tv[p]);
+            double B = 2.0 * hh * cc * cc / std::pow(lambda[ell], 5) / (std::exp(x) - 1.0);
+            planckabs += kappaabs[h * Nl + ell] * B * dlambda[ell];
+        }
+        pab[(size_t)h * (NT + 1) + p] = planckabs;
+    }
+    e.libTv.upload(Tv.data(), sizeof(double) * Tv.size(), e.stream); e.libPlanckabs.upload(pab.data(), sizeof(double) * pab.size(), e.stream);
+    e.haveDustLib = true;
+    e.sync();
+}
+
+double* mcDustCellLuminosities(Engine& e)
+{
+    if (!e.haveDustLib) throw Error("skg_dust_library has not been called");
+    if ((!e.labs.p && !e.labsDust.p) || e.labsCount == 0) throw Error("absorption rates were not stored");
+    DustLibDev D{};
+    D.labsStel = e.labs.as<double>(); D.labsDust = e.labsDust.as<double>();
+    D.rho = e.med.rho; D.vol = e.libVol.as<double>(); D.kabs = e.libKabs.as<double>(); D.lambda = e.libLambda.as<double>(); D.dlambda = e.libDlambda.as<double>();
+    D.Tv = e.libTv.as<double>(); D.planckabs = e.libPlanckabs.as<double>();
+    D.Ncells = e.Ncells; D.Ncomp = e.med.Ncomp; D.Nlambda = e.med.Nlambda; D.NT = 1000;
+    e.dustLvOut.ensure(sizeof(double) * (size_t)D.Ncells * D.Nlambda);
+    D.out = e.dustLvOut.as<double>();
+    dustLibraryKernel<<<std::min(e.smCount * 16, (D.Ncells + 127) / 128), 128, 0, e.stream>>>(D);
+    e.launches++; SKG_CUDA(cudaGetLastError());
+    e.sync();
+    return D.out;
+}
+
 // common driver of the three shooting phases
 static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBias, const std::vector<double>& LtotHost, skg_mc_stats* stats)
 {

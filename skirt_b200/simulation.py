@@ -485,6 +485,24 @@ class MonteCarloSimulation:
         return st
 
     # ---- dust emission phases (PanMonteCarloSimulation.cpp:105-264) --------------------------------------------------
+    def setup_dust_library(self, volumes):
+        """hands the DustLib tables to the engine, so that the emission spectra between the phases are computed on the
+        device (skg_dust_library / skg_dust_cell_luminosities) without moving the absorption tables to the host"""
+        kabs = np.array([c.mix.kappaabs for c in self.ds.comps])
+        self.engine.dust_library(volumes, kabs, self.lambdagrid.lambdav, self.lambdagrid.dlambdav)
+        self._devlib = True
+
+    def _shoot_dust(self, phase, dustlib, packages, seed, **kw):
+        npr, offset, total = shard_packets(packages, self.rank, self.nranks)
+        common = dict(total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs, scatt_bias=self.xi,
+                      seed=seed, stream_offset=offset, **kw)
+        if dustlib is None:
+            if not getattr(self, "_devlib", False):
+                raise FatalError("There should be a dust library when dust emission is turned on")     # PanDustSystem.cpp:58
+            return self.engine.run_dust_device(phase, self.engine.dust_cell_luminosities(), npr, **common)
+        Lv, _ = self._cell_luminosities(dustlib)
+        return self.engine.run_dust(phase, Lv, npr, **common)
+
     def _cell_luminosities(self, dustlib):
         """Lv[ell, m] = Labsbol[m] * dustluminosity(m, ell) (PanMonteCarloSimulation.cpp:193-198, 275-280)"""
         Labs = self.engine.fetch_labs()
@@ -495,7 +513,7 @@ class MonteCarloSimulation:
         Labsbol = Labs.sum(1)
         return np.ascontiguousarray((Labsbol[:, None] * dustlib.luminosities(Labs)).T), Labs
 
-    def rundustselfabsorption(self, dustlib, cycles=0):
+    def rundustselfabsorption(self, dustlib=None, cycles=0):
         """three stages of self-absorption cycles with 1/10, 1/3 and all of the packets, each until the absorbed dust
         luminosity changes by less than 1 %, 0.7 %, 0.5 % (PanMonteCarloSimulation.cpp:105-185)"""
         prev = 0.0; history = []
@@ -503,11 +521,21 @@ class MonteCarloSimulation:
             ncyclesmax = cycles if cycles else 100
             convergence = False; cycle = 1
             while cycle <= ncyclesmax and (not convergence or cycles):
-                Lv, _ = self._cell_luminosities(dustlib)
-                self.engine.reset_labs_dust()
-                npr, offset, total = shard_packets(self.packages * factor, self.rank, self.nranks)
-                self.engine.run_dust(1, Lv, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
-                                     scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
+                # the spectra are computed from the absorption of the previous cycle BEFORE the dust table is rebooted
+                if dustlib is None:
+                    if not getattr(self, "_devlib", False):
+                        raise FatalError("There should be a dust library when dust emission is turned on")
+                    d_L = self.engine.dust_cell_luminosities()
+                    self.engine.reset_labs_dust()
+                    npr, offset, total = shard_packets(self.packages * factor, self.rank, self.nranks)
+                    self.engine.run_dust_device(1, d_L, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
+                                                scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
+                else:
+                    Lv, _ = self._cell_luminosities(dustlib)
+                    self.engine.reset_labs_dust()
+                    npr, offset, total = shard_packets(self.packages * factor, self.rank, self.nranks)
+                    self.engine.run_dust(1, Lv, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
+                                         scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
                 if self.nranks > 1:
                     self.engine.allreduce_results()
                 tot = float(self.engine.fetch_labs_dust().sum())
@@ -518,12 +546,9 @@ class MonteCarloSimulation:
                 cycle += 1
         return history
 
-    def rundustemission(self, dustlib, emissionBias=0.5, emissionBoost=1.0):
+    def rundustemission(self, dustlib=None, emissionBias=0.5, emissionBoost=1.0):
         """PanMonteCarloSimulation::rundustemission (PanMonteCarloSimulation.cpp:242-264)"""
-        Lv, _ = self._cell_luminosities(dustlib)
-        npr, offset, total = shard_packets(self.packages * emissionBoost, self.rank, self.nranks)
-        st = self.engine.run_dust(2, Lv, npr, total_packages=total, emission_bias=emissionBias, min_weight_reduction=self.mwr,
-                                  min_scatt_events=self.minfs, scatt_bias=self.xi, seed=self.seed + 999983, stream_offset=offset)
+        st = self._shoot_dust(2, dustlib, self.packages * emissionBoost, self.seed + 999983, emission_bias=emissionBias)
         if self.nranks > 1:
             self.engine.allreduce_results()
         return st

@@ -98,7 +98,8 @@ def test_labs_bolometric_and_random_positions(engine):
     assert sed[3] > 0 and np.count_nonzero(sed) == 1
 
 
-def test_full_pan_flow_through_the_host_mirror(engine):
+@pytest.mark.parametrize("devlib", [False, True])
+def test_full_pan_flow_through_the_host_mirror(engine, devlib):
     """stellar emission -> three fixed self-absorption cycles -> dust emission, driven by the Python mirror of
     PanMonteCarloSimulation with the numpy DustLib, against the same sequence executed by the reference's own classes"""
     from oracle import skirtref as sr, refspec
@@ -114,6 +115,8 @@ def test_full_pan_flow_through_the_host_mirror(engine):
     m.engine.close(); m.engine = engine
     m.setup()
     lib = sim.GreyBodyDustLib(m.lambdagrid, [mixes[0][0]], med["rho"], S.volumes())
+    if devlib:          # dust emission spectra on the device (skg_dust_library) instead of the numpy DustLib
+        m.setup_dust_library(S.volumes()); lib = None
     B = 6
     ref_sed, gpu_sed = [], []
     for b in range(B):
@@ -136,3 +139,35 @@ def test_full_pan_flow_through_the_host_mirror(engine):
         a, r = gpu_sed[:, sl].sum(1), ref_sed[:, sl].sum(1)
         z = (a.mean() - r.mean()) / np.sqrt(a.var(ddof=1) / B + r.var(ddof=1) / B)
         assert abs(z) < 4 and abs(a.mean() / r.mean() - 1) < 0.02, f"bins {sl}: gpu {a.mean():.6g} ref {r.mean():.6g} z {z:.2f}"
+
+
+def test_device_dust_library_matches_the_host_restatement(engine):
+    """skg_dust_cell_luminosities (DustLib on the device, fed by the device-resident absorption tables) against the numpy
+    GreyBodyDustLib, which tests/test_dustlib.py pins to the reference's own DustLib; then a dust emission phase shot
+    straight from the device array equals one shot from the same array passed through the host"""
+    from skirt_b200 import configs, simulation as sim
+    p = configs.c2_params(n=16, nlambda=25, packages=2e4)
+    m = configs.build(p, storeAbsorption=True)
+    m.engine.close(); m.engine = engine
+    m.setup()
+    engine.reset_results(); engine.reset_labs_dust()
+    m.runstellaremission()
+    grid = m.ds.grid
+    dx, dy, dz = np.diff(grid.xv), np.diff(grid.yv), np.diff(grid.zv)
+    vol = (dx[:, None, None] * dy[None, :, None] * dz[None, None, :]).ravel()
+    kabs = np.array([c.mix.kappaabs for c in m.ds.comps])
+    engine.dust_library(vol, kabs, m.lambdagrid.lambdav, m.lambdagrid.dlambdav)
+    d_L = engine.dust_cell_luminosities()
+    got = engine.copy_from_device(d_L, (engine.Nlambda, engine.Ncells))
+    lib = sim.GreyBodyDustLib(m.lambdagrid, kabs, m.ds.rho, vol)
+    labs = engine.fetch_labs()
+    want = (labs.sum(1)[:, None] * lib.luminosities(labs)).T
+    assert want.sum() > 0
+    np.testing.assert_allclose(got.sum(0), want.sum(0), rtol=1e-10)
+    big = want > 1e-12 * want.max()
+    np.testing.assert_allclose(got[big], want[big], rtol=1e-8)
+    # same packets (same seed) from the device array and from its host copy
+    engine.reset_results(); a = engine.run_dust_device(2, d_L, 2e4, seed=5); sed_dev = engine.fetch_sed(1)
+    engine.reset_results(); b = engine.run_dust(2, got, 2e4, seed=5); sed_host = engine.fetch_sed(1)
+    assert a["packets"] == b["packets"] and a["pathSegments"] == b["pathSegments"]
+    np.testing.assert_allclose(sed_dev, sed_host, rtol=1e-9)
