@@ -19,6 +19,7 @@ void DustSystem::setup(const WavelengthGrid& lg)
     _grid->setup();
     _Nlambda = lg.Nlambda();
     const int N = _grid->numCells(), C = (int)_comps.size();
+    _kabs.resize((size_t)C * _Nlambda);
     _rho.assign((size_t)N * C, 0.0); _kext.resize((size_t)C * _Nlambda); _ksca.resize((size_t)C * _Nlambda); _g.resize((size_t)C * _Nlambda);
     for (int h = 0; h < C; h++)
     {
@@ -26,7 +27,7 @@ void DustSystem::setup(const WavelengthGrid& lg)
         if (!c.geometry || !c.mix || !c.norm) SKIRT_FATAL("dust component is incomplete");
         c.geometry->setup(); c.mix->setup(lg);
         for (int ell = 0; ell < _Nlambda; ell++)
-        { _kext[(size_t)h * _Nlambda + ell] = c.mix->kappaext(ell); _ksca[(size_t)h * _Nlambda + ell] = c.mix->kappascav[ell]; _g[(size_t)h * _Nlambda + ell] = c.mix->asymmparv[ell]; }
+        { _kabs[(size_t)h * _Nlambda + ell] = c.mix->kappaabsv[ell]; _kext[(size_t)h * _Nlambda + ell] = c.mix->kappaext(ell); _ksca[(size_t)h * _Nlambda + ell] = c.mix->kappascav[ell]; _g[(size_t)h * _Nlambda + ell] = c.mix->asymmparv[ell]; }
         // FaceOnDustCompNormalization.cpp:67-74: rho scale = tau / (SigmaZ * kappaext(lambda)); kappaext at lambda by
         // log-log interpolation on the simulation grid for panchromatic grids, the grid value itself for oligochromatic ones
         double kv;
@@ -90,6 +91,14 @@ void MonteCarloSimulation::setup()
         SKIRT_FATAL("a simulation without a dust system is not supported by the engine front end");
     }
     _is->upload(_engine);
+    if (_dustemission)
+    {
+        if (!_lambdagrid->issampledrange()) SKIRT_FATAL("dust emission needs a panchromatic wavelength grid");
+        _ds->setStoreAbsorptionRates(true);          // PanDustSystem::storeabsorptionrates() == dustemission()
+        std::vector<double> vol = _ds->volumes(), lam = _lambdagrid->lambdav(), dlam(lam.size());
+        for (size_t i = 0; i < lam.size(); i++) dlam[i] = _lambdagrid->dlambda((int)i);
+        check(skg_dust_library(_engine, vol.data(), _ds->kappaabs().data(), lam.data(), dlam.data()));
+    }
     if (_nranks > 1)
     {
         if (!_uid) SKIRT_FATAL("the NCCL unique id was not set for a multi-process run");
@@ -112,6 +121,55 @@ skg_mc_stats MonteCarloSimulation::runstellaremission()
     check(skg_run_stellar(_engine, &p, &st));
     if (_nranks > 1) check(skg_allreduce_results(_engine));       // Instrument::sumResults / PanDustSystem::sumResults
     return st;
+}
+
+skg_mc_stats MonteCarloSimulation::shootDust(int phase, double packages)
+{
+    skg_mc_params p{};
+    double npr = std::ceil(packages / _nranks);
+    p.packages = npr; p.luminosityScale = npr * _nranks;
+    p.minWeightReduction = _minWeightReduction; p.minScattEvents = _minfs; p.scattBias = _xi;
+    p.seed = (uint64_t)_seed + 7919ull * (uint64_t)(++_phaseCounter); p.streamOffset = (uint64_t)(_rank * npr);
+    p.ellBegin = 0; p.ellEnd = _lambdagrid->Nlambda();
+    double* dL = nullptr;
+    check(skg_dust_cell_luminosities(_engine, &dL));            // PanDustSystem::calculatedustemission + the vectors Lv
+    if (phase == SKG_PHASE_DUST_SELFABS) check(skg_reset_labs_dust(_engine));   // rebootLabsdust, after the spectra were made
+    skg_mc_stats st{};
+    check(skg_run_dust(_engine, &p, phase, _dustBias, SKG_DEVICE, dL, &st));
+    if (_nranks > 1) check(skg_allreduce_results(_engine));
+    return st;
+}
+
+// PanMonteCarloSimulation::rundustselfabsorption, PanMonteCarloSimulation.cpp:105-185
+int MonteCarloSimulation::rundustselfabsorption()
+{
+    if (!_engine || !_dustemission) SKIRT_FATAL("dust self-absorption needs a set-up simulation with dust emission");
+    const double stage_factor[] = {1. / 10., 1. / 3., 1.}; const double stage_epsmax[] = {0.010, 0.007, 0.005};
+    double prev = 0.; int total = 0;
+    std::vector<double> labs((size_t)_ds->Ncells() * _lambdagrid->Nlambda());
+    for (int stage = 0; stage < 3; stage++)
+    {
+        bool fixed = _cycles > 0; const int Ncyclesmax = fixed ? _cycles : 100;
+        bool convergence = false; int cycle = 1;
+        while (cycle <= Ncyclesmax && (!convergence || fixed))
+        {
+            shootDust(SKG_PHASE_DUST_SELFABS, _packages * stage_factor[stage]);
+            check(skg_fetch_labs_dust(_engine, labs.data(), 0));
+            double Labsdusttot = 0; for (double v : labs) Labsdusttot += v;
+            double eps = std::fabs((Labsdusttot - prev) / Labsdusttot);
+            prev = Labsdusttot;
+            if ((stage < 2 || cycle > 1) && eps < stage_epsmax[stage]) convergence = true;
+            cycle++; total++;
+        }
+    }
+    return total;
+}
+
+// PanMonteCarloSimulation::rundustemission, PanMonteCarloSimulation.cpp:242-264
+skg_mc_stats MonteCarloSimulation::rundustemission()
+{
+    if (!_engine || !_dustemission) SKIRT_FATAL("dust emission needs a set-up simulation with dust emission");
+    return shootDust(SKG_PHASE_DUST_EMISSION, _packages * _dustBoost);
 }
 
 void MonteCarloSimulation::fetchResults()

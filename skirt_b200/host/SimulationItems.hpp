@@ -437,10 +437,12 @@ public:
     void setup(const WavelengthGrid& lg);
     void upload(skg_engine* e) const;
     const std::vector<double>& rho() const { return _rho; }
+    const std::vector<double>& kappaabs() const { return _kabs; }       // [Ncomp*Nlambda]
+    std::vector<double> volumes() const { std::vector<double> v(Ncells()); for (int m = 0; m < Ncells(); m++) { double b[6]; _grid->cellBox(m, b); v[m] = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]); } return v; }
 private:
     std::unique_ptr<DustGrid> _grid; std::vector<std::unique_ptr<DustComp>> _comps;
     int _nsub = 2; bool _storeabs = false; int _Nlambda = 0;
-    std::vector<double> _rho, _kext, _ksca, _g;
+    std::vector<double> _rho, _kext, _ksca, _g, _kabs;
 };
 
 // ---- stellar system ------------------------------------------------------------------------------------------------
@@ -542,6 +544,18 @@ public:
 
     void setup();
     skg_mc_stats runstellaremission();
+    // PanMonteCarloSimulation (PanMonteCarloSimulation.cpp:105-264); the emission spectra between the phases come from
+    // the engine's dust library (AllCellsDustLib + GreyBodyDustEmissivity on the device)
+    void setDustEmission(bool v) { _dustemission = v; }
+    void setSelfAbsorption(bool v) { _selfabsorption = v; }
+    void setCycles(int v) { _cycles = v; }
+    void setEmissionBias(double v) { _dustBias = v; }
+    void setEmissionBoost(double v) { _dustBoost = v; }
+    bool dustemission() const { return _dustemission; }
+    int rundustselfabsorption();         // returns the number of cycles performed
+    int rundustselfabsorptionIfEnabled() { return _selfabsorption ? rundustselfabsorption() : 0; }
+    skg_mc_stats rundustemission();
+    void run() { runstellaremission(); if (_dustemission) { if (_selfabsorption) rundustselfabsorption(); rundustemission(); } }
     void fetchResults();                // fills Instrument::ftotv / Ftotv and Labs() on the host (what write() consumes)
     const std::vector<double>& Labs() const { return _Labs; }
     InstrumentSystem* instrumentSystem() const { return _is.get(); }
@@ -551,6 +565,8 @@ private:
     std::unique_ptr<WavelengthGrid> _lambdagrid; std::unique_ptr<StellarSystem> _ss; std::unique_ptr<DustSystem> _ds; std::unique_ptr<InstrumentSystem> _is;
     double _packages = 1e6, _minWeightReduction = 1e4, _minfs = 0, _xi = 0.5; int _seed = 4357, _device = 0;
     int _rank = 0, _nranks = 1; const void* _uid = nullptr;
+    bool _dustemission = false, _selfabsorption = false; int _cycles = 0; double _dustBias = 0.5, _dustBoost = 1.0; int _phaseCounter = 0;
+    skg_mc_stats shootDust(int phase, double packages);
     skg_engine* _engine = nullptr; std::vector<double> _Labs;
 };
 

@@ -10,7 +10,7 @@
 //   dust tau lambda expdisk hR hz Rmax zmax
 //   stellar L1[,L2,...]|bb:T:Lbol expdisk hR hz Rmax zmax | sersic n Reff q
 //   instrument frame|sed|simple name distance inclination azimuth pa [nx fovx ny fovy]
-//   storeabs 0|1 ; device d ; lattice n
+//   storeabs 0|1 ; device d ; lattice n ; dustemission 0|1 ; selfabs 0|1 ; cycles n (0: until convergence)
 #include <cstdio>
 #include <cstring>
 #include <iostream>
@@ -74,6 +74,9 @@ int main(int argc, char** argv)
             else if (key == "emissionbias") { double v; in >> v; ss->setEmissionBias(v); }
             else if (key == "storeabs") { int v; in >> v; ds->setStoreAbsorptionRates(v != 0); }
             else if (key == "lattice") { int v; in >> v; ds->setSampleLattice(v); }
+            else if (key == "dustemission") { int v; in >> v; sim.setDustEmission(v != 0); }
+            else if (key == "selfabs") { int v; in >> v; sim.setSelfAbsorption(v != 0); }
+            else if (key == "cycles") { int v; in >> v; sim.setCycles(v); }
             else if (key == "wavelengths") { std::vector<double> lv; double v; while (in >> v) lv.push_back(v); auto* g = new OligoWavelengthGrid(); g->setWavelengths(lv); sim.setWavelengthGrid(g); }
             else if (key == "loggrid") { double a, b; int n; in >> a >> b >> n; auto* g = new LogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n); sim.setWavelengthGrid(g); }
             else if (key == "box") { for (double& v : box) in >> v; }
@@ -116,10 +119,11 @@ int main(int argc, char** argv)
             }
             else SKIRT_FATAL("unknown key " + key);
         }
-        (void)pan;
         sim.setStellarSystem(ss); sim.setDustSystem(ds); sim.setInstrumentSystem(is);
         sim.setup();
         skg_mc_stats st = sim.runstellaremission();
+        int cycles = 0;
+        if (sim.dustemission()) { if (pan) { cycles = sim.rundustselfabsorptionIfEnabled(); sim.rundustemission(); } else SKIRT_FATAL("dust emission needs a panchromatic simulation"); }
         sim.fetchResults();
         std::string prefix = argv[2];
         auto dump = [&](const std::string& name, const std::vector<double>& v)
@@ -131,9 +135,9 @@ int main(int argc, char** argv)
         }
         if (!sim.Labs().empty()) dump("Labs", sim.Labs());
         dump("rho", sim.dustSystem()->rho());
-        std::printf("{\"packets\": %llu, \"pathSegments\": %llu, \"scatterings\": %llu, \"kernel_ms\": %.3f, \"cells\": %d, \"wavelengths\": %d}\n",
+        std::printf("{\"packets\": %llu, \"pathSegments\": %llu, \"scatterings\": %llu, \"kernel_ms\": %.3f, \"cells\": %d, \"wavelengths\": %d, \"selfabs_cycles\": %d}\n",
                     (unsigned long long)st.packets, (unsigned long long)st.pathSegments, (unsigned long long)st.scatterings, st.kernel_ms,
-                    sim.dustSystem()->Ncells(), sim.wavelengthGrid()->Nlambda());
+                    sim.dustSystem()->Ncells(), sim.wavelengthGrid()->Nlambda(), cycles);
         return 0;
     }
     catch (std::exception& ex) { std::fprintf(stderr, "*** Error: %s\n", ex.what()); return 1; }

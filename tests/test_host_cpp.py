@@ -78,3 +78,26 @@ def test_c1_through_the_cpp_host(tmp_path, engine):
     assert abs(sed[0] / g["sed_total_mean"][0] - 1) < 0.06
     assert abs(frame.sum() / g["frame_total_mean"][0] - 1) < 0.06
     assert abs(labs.sum() / g["labs_total_mean"][0] - 1) < 0.12
+
+
+@pytest.mark.gpu
+def test_pan_flow_through_the_cpp_host(tmp_path):
+    """stellar emission -> self-absorption cycles (until convergence) -> dust emission, all driven by the C++ host layer:
+    energy bookkeeping of the result"""
+    dat = os.path.join(common.ROOT, "skirt_b200", "data", "interstellar_dustmix.dat")
+    text = "\n".join([
+        "sim pan", "packages 20000.0", "loggrid 1e-07 0.001 25", common.box_line(common.C1_BOX), "grid cartesian 16 16 16 lin lin lin",
+        f"dustmix interstellar {dat}", f"dust 1.0 5.5e-07 expdisk {4000*PC!r} {140*PC!r} 0 0",
+        f"stellar bb:3500:1.15e36 sersic 2.0 {1600*PC!r} 0.7", f"stellar bb:10000:1.92e36 expdisk {4000*PC!r} {350*PC!r} 0 0",
+        f"instrument sed s {1e7*PC!r} 0.5 0 0", "dustemission 1", "selfabs 1"]) + "\n"
+    r = run(tmp_path, text)
+    assert r.returncode == 0, r.stderr
+    st = json.loads(r.stdout.strip().splitlines()[-1])
+    assert 4 <= st["selfabs_cycles"] <= 40
+    sed = np.fromfile(tmp_path / "out_s_sed.f64"); labs = np.fromfile(tmp_path / "out_Labs.f64")
+    Lstar = 1.15e36 + 1.92e36
+    # every emitted watt is either seen directly / after scattering, or absorbed and re-emitted by the dust: the SED
+    # integrated over wavelength recovers the stellar luminosity to within the anisotropy of one viewing direction
+    assert 0.7 < sed.sum() / Lstar < 1.3
+    assert 0.02 < labs.sum() / Lstar < 0.6
+    assert sed[-8:].sum() > 0 and sed[:5].sum() > 0
