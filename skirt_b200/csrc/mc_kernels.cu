@@ -213,14 +213,15 @@ __device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, doub
 }
 
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
-template<int KIND> struct PeelJob
+template<int KIND, bool SINGLE> struct PeelJob
 {
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
     double Lw, tau; KappaRho kr; int ell, grp;
     // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
     // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
-    double kext0, pendRho, pendDs; bool single;
+    double kext0, pendRho, pendDs;
+    static constexpr bool single = SINGLE;  // one dust component: compile-time, no branch in the crossing loop
     unsigned long long nSeg = 0, nPaths = 0, nDet = 0;
     __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_) : G(G_), cart(c_), P(P_) {}
 
@@ -275,7 +276,7 @@ template<int KIND> struct PeelJob
         Lw = L; tau = 0;
         dx = g.kx; dy = g.ky; dz = g.kz;
         kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
-        single = Ncomp == 1; kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendRho = 0; pendDs = 0;
+        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendRho = 0; pendDs = 0;
         if (!P.med.rho) return 2;                                   // Instrument::opticalDepth: 0 without dust
         nPaths++;
         return 1;
@@ -309,20 +310,20 @@ template<int KIND> struct PeelJob
     __device__ __forceinline__ void periodic() {}
 };
 
-template<int KIND>
+template<int KIND, bool SINGLE>
 __global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                  int nAlive, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    PeelJob<KIND> job(G, cart, P);
+    PeelJob<KIND, SINGLE> job(G, cart, P);
     runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, min(28, 2 * P.refill));
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
 }
 
 // scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
-template<int KIND> struct AbsorbJob
+template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
 {
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     int* counts;
@@ -398,7 +399,7 @@ template<int KIND> struct AbsorbJob
     {
         if (pendM < 0) return;
         double dtau = (kext0 * pendRho) * pendDs;
-        if (labs)
+        if (STORE)
         {
             double x = expm1Small(-dtau);
             atomicAdd(labs + pendM, (1.0 - albedo) * (L * E * (-x)));
@@ -411,7 +412,7 @@ template<int KIND> struct AbsorbJob
     {
         nSeg++;
         const int Ncomp = P.med.Ncomp;
-        if (Ncomp == 1)
+        if (SINGLE)
         {
             absorbPending();
             pendM = m; pendDs = ds; pendRho = __ldg(P.med.rho + m);
@@ -433,7 +434,7 @@ template<int KIND> struct AbsorbJob
             double Lintm = L * E * (-x);
             E += E * x;
             Lsca += alb * Lintm;
-            if (labs) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
+            if (STORE) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
             tau += dtau;
         }
         return true;
@@ -442,9 +443,9 @@ template<int KIND> struct AbsorbJob
     {
         if (!(L > 0) || !P.med.rho) return;
         Packet* q = P.pool;
-        if (P.med.Ncomp == 1) { absorbPending(); pendM = -1; }
+        if (SINGLE) { absorbPending(); pendM = -1; }
         const double taupath = tau;
-        if (P.med.Ncomp == 1) L = L * albedo * (-expm1(-taupath));
+        if (SINGLE) L = L * albedo * (-expm1(-taupath));
         else L = Lsca;
         // ---- termination test, :289 ----
         const double Lthreshold = __ldg(P.Ltot + ell) / P.Lscale / P.minWeightReduction;
@@ -484,26 +485,26 @@ template<int KIND> struct AbsorbJob
     __device__ __forceinline__ void periodic() {}
 };
 
-template<int KIND>
+template<int KIND, bool SINGLE, bool STORE>
 __global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                    int nAlive, int* __restrict__ counts, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    AbsorbJob<KIND> job(G, cart, P, counts);
+    AbsorbJob<KIND, SINGLE, STORE> job(G, cart, P, counts);
     runJobs<KIND>(G, cart, ctr, job, nAlive, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, job.nScatt, 0, job.nAbs, 0);
 }
 
 // re-walk to the sampled interaction optical depth and move the packet there:
 // DustGridPath::pathlength (DustGridPath.cpp:162-173) evaluated on the fly + PhotonPackage::propagate (PhotonPackage.cpp:93-96)
-template<int KIND> struct PropagateJob
+template<int KIND, bool SINGLE> struct PropagateJob
 {
     const McDev& P;
     double rx, ry, rz, dx, dy, dz;
     KappaRho kr; double target, sPrev, tauPrev, result; bool found; int slot;
-    double kext0, pendRho, pendDs; bool single, pending;      // one-component media: gather now, test one crossing later
+    double kext0, pendRho, pendDs; bool pending; static constexpr bool single = SINGLE;      // one-component media: gather now, test one crossing later
     unsigned long long nSeg = 0, nPaths = 0;
     __device__ explicit PropagateJob(const McDev& P_) : P(P_) {}
     __device__ __forceinline__ int begin(int item)
@@ -517,7 +518,7 @@ template<int KIND> struct PropagateJob
         rx = pk.x; ry = pk.y; rz = pk.z; dx = pk.kx; dy = pk.ky; dz = pk.kz;
         kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
         sPrev = 0; tauPrev = 0; result = 0; found = false;
-        single = P.med.Ncomp == 1; kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pending = false; pendRho = 0; pendDs = 0;
+        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pending = false; pendRho = 0; pendDs = 0;
         nPaths++;
         return 1;
     }
@@ -557,14 +558,14 @@ template<int KIND> struct PropagateJob
     __device__ __forceinline__ void periodic() {}
 };
 
-template<int KIND>
+template<int KIND, bool SINGLE>
 __global__ void __launch_bounds__(128) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                       int nSurv, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
-    PropagateJob<KIND> job(P);
+    PropagateJob<KIND, SINGLE> job(P);
     runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
 }
@@ -746,6 +747,7 @@ template<int KIND>
 static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned long long total, int pool, size_t smem, bool cartSmem)
 {
     Packet* poolA = e.mcPool.as<Packet>(); Packet* poolB = poolA + pool;
+    const bool single = P.med.Ncomp == 1, store = P.labs != nullptr;
     int* counts = e.mcCounts.as<int>();      // [0] survivors, [2..4] work counters of the three traversal stages
     auto blocksFor = [&](long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, (long long)e.smCount * 16)); };
     for (cudaEvent_t& ev : e.mcEvents) if (!ev) SKG_CUDA(cudaEventCreate(&ev));
@@ -773,9 +775,21 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         SKG_CUDA(cudaMemsetAsync(counts, 0, 8 * sizeof(int), e.stream));
         SKG_CUDA(cudaEventRecord(ev[1], e.stream));
         if (P.Ngroups > 0 && P.phase != SKG_PHASE_DUST_SELFABS)
-        { peelStage<KIND><<<blocksFor((long long)nAlive * P.Ngroups), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2); e.launches++; }
+        {
+            const int nb = blocksFor((long long)nAlive * P.Ngroups);
+            if (single) peelStage<KIND, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+            else peelStage<KIND, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+            e.launches++;
+        }
         SKG_CUDA(cudaEventRecord(ev[2], e.stream));
-        absorbStage<KIND><<<blocksFor(nAlive), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3); e.launches++;
+        {
+            const int nb = blocksFor(nAlive);
+            if (single && store) absorbStage<KIND, true, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            else if (single) absorbStage<KIND, true, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            else if (store) absorbStage<KIND, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            else absorbStage<KIND, false, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            e.launches++;
+        }
         SKG_CUDA(cudaEventRecord(ev[3], e.stream));
         SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
         SKG_CUDA(cudaGetLastError());
@@ -787,7 +801,9 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         if (nSurv > 0)
         {
             SKG_CUDA(cudaEventRecord(ev[4], e.stream));
-            propagateStage<KIND><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nSurv, counts + 4); e.launches++;
+            if (single) propagateStage<KIND, true><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nSurv, counts + 4);
+            else propagateStage<KIND, false><<<blocksFor(nSurv), 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nSurv, counts + 4);
+            e.launches++;
             SKG_CUDA(cudaEventRecord(ev[5], e.stream));
             propagatePending = true;
         }
