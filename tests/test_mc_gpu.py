@@ -105,3 +105,35 @@ def test_other_grids_against_reference_runs(engine, kind):
             z = common.zscores(ma[ok], sa[ok], mr[ok], sr_[ok])
             assert ok.sum() > 0.5 * len(ok)
             assert np.mean(np.abs(z) < 3) > 0.96 and abs(z.mean()) < 0.3, f"{kind}/{name}: {np.mean(np.abs(z) < 3):.4f} within 3 sigma, mean z {z.mean():.3f}"
+
+
+def test_c2_benchmark_configuration_against_reference_runs(engine):
+    """the configuration bench.py measures (C2: Sersic bulge + exponential disk, 50 wavelengths, InterstellarDustMix,
+    absorption stored, frame + SED), at a reduced grid / packet count, against the reference's PanMonteCarloSimulation:
+    SED per wavelength, frame and absorbed luminosity per wavelength within the combined Monte Carlo noise"""
+    import os
+    from oracle import skirtref as sr, refspec
+    from skirt_b200 import configs
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    p = configs.c2_params(n=32, nlambda=50, packages=2e4)
+    spec, L, mixes = refspec.reference_spec(p, threads=os.cpu_count() or 1, dustsamples=5)
+    S = sr.RefSim(spec, luminosities=L, mixes=mixes).setup()
+    med = S.medium()
+    m = configs.build(p, rho=med["rho"], storeAbsorption=True)
+    m.engine.close(); m.engine = engine
+    m.setup()
+    np.testing.assert_allclose(m.ds.kext, med["kext"], rtol=1e-9)          # same opacities on both sides
+    m.packages = S.packages_per_lambda()
+    B = 10
+    ref = dict(sed=[], frame=[], labs=[]); gpu = dict(sed=[], frame=[], labs=[])
+    for b in range(B):
+        S.reset(77 + 1000 * b); S.run_stellar(); ins = S.instruments()
+        ref["sed"].append(ins[1]["sed"].copy()); ref["frame"].append(ins[0]["frame"].reshape(50, -1).sum(1)); ref["labs"].append(S.labs().sum(0))
+        engine.reset_results(); m.seed = 400 + b; m.runstellaremission()
+        gpu["sed"].append(engine.fetch_sed(1)); gpu["frame"].append(engine.fetch_frame(0).reshape(50, -1).sum(1)); gpu["labs"].append(engine.fetch_labs().sum(0))
+    for name in ref:
+        a, r = np.array(gpu[name]), np.array(ref[name])
+        z = common.zscores(a.mean(0), a.std(0, ddof=1) / np.sqrt(B), r.mean(0), r.std(0, ddof=1) / np.sqrt(B))
+        assert np.all(np.abs(z) < 4.5) and np.mean(np.abs(z) < 3) > 0.9 and abs(z.mean()) < 0.6, f"{name}: z = {np.round(z, 2)}"
+        assert abs(a.sum() / r.sum() - 1) < 0.01
