@@ -285,6 +285,11 @@ def main_engine(args):
     absorb_paths = st["packets"] + st["scatterings"]
     alg_bytes = (8.0 * ncomp + 16.0) * st["absorbSegments"] + 128.0 * absorb_paths
     achieved = alg_bytes / (absorb_ms * 1e-3) / 1e9
+    # DRAM traffic of the same kernel over one phase of this workload, from the committed ncu pass (profiles/)
+    traffic = None
+    tfile = os.path.join(ROOT, "profiles", "r01_v5_absorbStage_dram_traffic.json")
+    if os.path.exists(tfile) and args.packages == 2e6 and args.nlambda == 50 and args.grid == 100:
+        t_ = json.load(open(tfile)); traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
@@ -293,7 +298,8 @@ def main_engine(args):
                                                  "skg_fetch_frame/sed/labs into page-locked host arrays"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
             "roofline": {"bound": "hbm", "kernel": "absorbStage<GRID_CART> (dominant kernel of the phase: scatter + traverse + absorb + terminate/sample)",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_note": "DRAM bytes of all absorbStage launches of one phase (ncu, profiles/r01_v5_absorbStage_dram_traffic.json): far BELOW the algorithmic bytes because the density table and the wavelength-major Labs slices in flight stay L2-resident",
                          "peak_source": peak_src, "bytes_per_step": alg_bytes, "kernel_ms_per_step": absorb_ms,
                          "launches_per_step": int(st["iterations"]), "share_of_step": absorb_ms / kernel_ms,
                          "absorbing_packet_steps_per_s": st["absorbSegments"] / (absorb_ms * 1e-3),
