@@ -312,6 +312,9 @@ def main_engine(args):
         tr = traversal_leg(e, torch, ext, ncomp, args.rays)
         tr["frac"] = tr["gbs"] / peak; tr["peak"] = peak
         tr["kernel"] = "pathFillKernel<GRID_CART> (batched DustGrid::path + fillOpticalDepth, CSR path records)"
+        # ncu --set full of this kernel on 1 Mi rays (profiles/r01_v3_path_kernels_ncu.txt): 1.987 GB written + 0.112 GB read
+        # for 50 281 330 packet-steps = 41.7 B per step, against 44 B algorithmic (40 B of it written)
+        tr["traffic"] = 41.7 * tr["packet_steps"]
         line["traversal_roofline"] = tr
     if rank == 0 and world == 1 and not args.skip_cpu:
         threads = os.cpu_count() or 1
