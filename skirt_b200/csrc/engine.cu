@@ -159,7 +159,56 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
         e.tree.cell = up(e, cell, N);
         std::vector<int> zeros; if (!dir) { zeros.assign(N, 0); dir = zeros.data(); }
         e.tree.dir = up(e, dir, N);
-        if (search == 1) { e.tree.nbrStart = up(e, nbrStart, 6 * (size_t)N + 1); e.tree.nbrIds = up(e, nbrIds, (size_t)std::max(1, nbrStart[6 * (size_t)N])); }
+        // point-location accelerator: a G^3 lattice over the root box; every lattice cell remembers the deepest node
+        // whose (closed) box contains the whole cell.  TreeNode::whichnode descends from there instead of from the root
+        // when the point lies strictly inside that node's box -- the same leaf, several levels fewer dependent reads.
+        {
+            const int G = N > 4096 ? 32 : (N > 64 ? 8 : 1);
+            std::vector<int> lut((size_t)G * G * G, 0);
+            const double* rb = box;
+            for (int i = 0; i < G; i++) for (int j = 0; j < G; j++) for (int k = 0; k < G; k++)
+            {
+                double lo[3] = {rb[0] + (rb[3] - rb[0]) * i / G, rb[1] + (rb[4] - rb[1]) * j / G, rb[2] + (rb[5] - rb[2]) * k / G};
+                double hi[3] = {rb[0] + (rb[3] - rb[0]) * (i + 1) / G, rb[1] + (rb[4] - rb[1]) * (j + 1) / G, rb[2] + (rb[5] - rb[2]) * (k + 1) / G};
+                int node = 0;
+                while (child0[node] >= 0)
+                {
+                    int next = -1;
+                    for (int c = 0; c < nchild; c++)
+                    {
+                        const double* cb = box + 6 * (size_t)(child0[node] + c);
+                        if (lo[0] >= cb[0] && hi[0] <= cb[3] && lo[1] >= cb[1] && hi[1] <= cb[4] && lo[2] >= cb[2] && hi[2] <= cb[5]) { next = child0[node] + c; break; }
+                    }
+                    if (next < 0) break;
+                    node = next;
+                }
+                lut[((size_t)i * G + j) * G + k] = node;
+            }
+            e.tree.lookup = up(e, lut.data(), lut.size()); e.tree.lookupG = G;
+            for (int c = 0; c < 3; c++) e.tree.lookupInv[c] = G / (rb[3 + c] - rb[c]);
+        }
+        e.tree.nbrRec = nullptr;
+        if (search == 1)
+        {
+            const size_t total = (size_t)std::max(0, nbrStart[6 * (size_t)N]);
+            e.tree.nbrStart = up(e, nbrStart, 6 * (size_t)N + 1); e.tree.nbrIds = up(e, nbrIds, std::max<size_t>(1, total));
+            // expanded neighbour records (96 B each) unless they would take more than 24 GB
+            if (total > 0 && total * sizeof(TreeNbrRec) <= (size_t)24 << 30)
+            {
+                std::vector<TreeNbrRec> rec(total);
+                for (size_t q = 0; q < total; q++)
+                {
+                    const int id = nbrIds[q];
+                    if (id < 0 || id >= N) throw Error("invalid neighbour id in tree tables");
+                    TreeNbrRec& r = rec[q];
+                    for (int c = 0; c < 6; c++) r.box[c] = box[6 * (size_t)id + c];
+                    r.id = id; r.cell = cell[id];
+                    for (int w = 0; w < 7; w++) r.nb[w] = nbrStart[6 * (size_t)id + w];
+                    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                }
+                e.tree.nbrRec = up(e, rec.data(), total);
+            }
+        }
         else { e.tree.nbrStart = nullptr; e.tree.nbrIds = nullptr; }
         { std::vector<int> cn(std::max(ncells, 1), 0); for (int l = 0; l < N; l++) if (cell[l] >= 0 && cell[l] < ncells) cn[cell[l]] = l; e.tree.cellNode = up(e, cn.data(), cn.size()); }
         e.tree.N = N; e.tree.kind = kind; e.tree.search = search;

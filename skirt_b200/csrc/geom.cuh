@@ -249,6 +249,18 @@ __device__ __forceinline__ int treeWhichNode(const TreeGrid& g, double x, double
 {
     if (!boxContains(g.box, x, y, z)) return -1;
     int node = 0;
+    if (g.lookupG > 1)
+    {
+        // start below the root when the lattice cell's node strictly contains the point: the descent from the root
+        // necessarily passes through that node (all comparisons against its ancestors' split planes agree)
+        const int G = g.lookupG;
+        const int i = max(0, min(G - 1, (int)((x - g.box[0]) * g.lookupInv[0])));
+        const int j = max(0, min(G - 1, (int)((y - g.box[1]) * g.lookupInv[1])));
+        const int k = max(0, min(G - 1, (int)((z - g.box[2]) * g.lookupInv[2])));
+        const int cand = __ldg(g.lookup + ((size_t)i * G + j) * G + k);
+        const double* b = g.box + 6 * (size_t)cand;
+        if (x > __ldg(b) && x < __ldg(b + 3) && y > __ldg(b + 1) && y < __ldg(b + 4) && z > __ldg(b + 2) && z < __ldg(b + 5)) node = cand;
+    }
     int c0;
     while ((c0 = __ldg(g.child0 + node)) >= 0)
     {
@@ -330,14 +342,37 @@ struct TreeWalker
             z += (ds + eps) * kz;
 
             const int oldnode = node;
-            bool haveBox = false;
+            bool haveBox = false, haveAll = false;
             if (g.search == 1)
             {
                 // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first neighbour whose closed box contains r
                 const int beg = wall == 0 ? nb[0] : wall == 1 ? nb[1] : wall == 2 ? nb[2] : wall == 3 ? nb[3] : wall == 4 ? nb[4] : nb[5];
                 const int end = wall == 0 ? nb[1] : wall == 1 ? nb[2] : wall == 2 ? nb[3] : wall == 3 ? nb[4] : wall == 4 ? nb[5] : nb[6];
                 node = -1;
-                for (int q = beg; q < end; q++)
+                if (g.nbrRec)
+                {
+                    // expanded records: box, cell and the neighbour offsets of the candidate arrive in one 96-byte read
+                    for (int q = beg; q < end; q++)
+                    {
+                        const double* rp = reinterpret_cast<const double*>(g.nbrRec + q);
+                        double w[12];
+#pragma unroll
+                        for (int u = 0; u < 3; u++)
+                            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[4 * u]), "=d"(w[4 * u + 1]), "=d"(w[4 * u + 2]), "=d"(w[4 * u + 3]) : "l"(rp + 4 * u));
+                        if (x >= w[0] && x <= w[3] && y >= w[1] && y <= w[4] && z >= w[2] && z <= w[5])
+                        {
+                            for (int c = 0; c < 6; c++) bx[c] = w[c];
+                            const long long w6 = __double_as_longlong(w[6]), w7 = __double_as_longlong(w[7]), w8 = __double_as_longlong(w[8]),
+                                            w9 = __double_as_longlong(w[9]), w10 = __double_as_longlong(w[10]);
+                            node = (int)(w6 & 0xffffffffll); cellv = (int)(w6 >> 32);
+                            nb[0] = (int)(w7 & 0xffffffffll); nb[1] = (int)(w7 >> 32); nb[2] = (int)(w8 & 0xffffffffll); nb[3] = (int)(w8 >> 32);
+                            nb[4] = (int)(w9 & 0xffffffffll); nb[5] = (int)(w9 >> 32); nb[6] = (int)(w10 & 0xffffffffll);
+                            haveAll = true;
+                            break;
+                        }
+                    }
+                }
+                else for (int q = beg; q < end; q++)
                 {
                     const int cand = __ldg(g.nbrIds + q);
                     const double* cb = g.box + 6 * (size_t)cand;
@@ -354,11 +389,11 @@ struct TreeWalker
                 atomicAdd(&ctr->stuckEscaped, 1ull);
                 x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
                 node = treeWhichNode(g, x, y, z);
-                haveBox = false;
+                haveBox = false; haveAll = false;
                 if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
             }
             if (node < 0) alive = false;
-            else loadNode(g, !haveBox);
+            else if (!haveAll) loadNode(g, !haveBox);
             return ds > 0;
         }
 

@@ -15,12 +15,26 @@ struct CartGrid
     double ext[6];      // xmin,xmax,ymin,ymax,zmin,zmax of the BoxDustGrid extent
 };
 
+// one entry of a tree node's neighbour list, self-contained: everything the walker needs to continue from that
+// neighbour (its box, cell number and the offsets of ITS six neighbour lists), so that a crossing costs a single
+// dependent memory round trip instead of id -> box -> offsets
+struct __align__(32) TreeNbrRec
+{
+    double box[6];
+    int id, cell;
+    int nb[7];
+    int pad[3];
+};
+
 struct TreeGrid
 {
     const double* box;              // [6N] xmin,ymin,zmin,xmax,ymax,zmax
     const int* child0; const int* parent; const int* cell; const int* dir;
     const int* nbrStart; const int* nbrIds;
     const int* cellNode;            // leaf node of every cell (TreeDustGrid::getnode, for randomPositionInCell)
+    const TreeNbrRec* nbrRec;       // expanded neighbour lists (same order as nbrIds), or null
+    const int* lookup;              // [G^3] deepest node whose box contains the whole lookup cell (entry point of root descents)
+    int lookupG; double lookupInv[3];
     int N, kind, search;
     double eps;
 };
