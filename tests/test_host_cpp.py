@@ -50,6 +50,7 @@ def test_no_cpu_fallback(tmp_path):
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(RUN), reason="skirt_b200_run not built")
 def test_c1_through_the_cpp_host(tmp_path, engine):
     r = run(tmp_path, params())
     assert r.returncode == 0, r.stderr
@@ -81,6 +82,7 @@ def test_c1_through_the_cpp_host(tmp_path, engine):
 
 
 @pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(RUN), reason="skirt_b200_run not built")
 def test_pan_flow_through_the_cpp_host(tmp_path):
     """stellar emission -> self-absorption cycles (until convergence) -> dust emission, all driven by the C++ host layer:
     energy bookkeeping of the result"""
