@@ -286,6 +286,7 @@ int skg_medium(skg_engine* eh, int Ncells, int Ncomp, int Nlambda, const double*
         e.gasym.upload(g ? g : zeros.data(), sizeof(double) * (size_t)Ncomp * Nlambda, e.stream);
         e.med.rho = e.rho.as<double>(); e.med.kext = e.kext.as<double>(); e.med.ksca = e.ksca.as<double>(); e.med.g = e.gasym.as<double>();
         e.med.Ncells = Ncells; e.med.Ncomp = Ncomp; e.med.Nlambda = Nlambda;
+        e.haveDustLib = false;       // the dust library tables belong to the previous medium
         e.sync();
     });
 }

@@ -701,7 +701,7 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             { used[j] = 1; grouped.push_back(e.instr[j]); g.count++; }
         groups.push_back(g);
     }
-    e.Ngroups = (int)groups.size();
+    e.Ngroups = (int)groups.size(); e.instrNlambda = e.med.Nlambda;
     e.instrGroupedDev.upload(grouped.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
     e.groupsDev.upload(groups.data(), sizeof(ObsGroup) * std::max<size_t>(groups.size(), 1), e.stream);
     e.sync();
@@ -966,6 +966,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     if (p.ellBegin < 0 || p.ellEnd > Nlambda || p.ellBegin > p.ellEnd) throw Error("wavelength range out of bounds");
     if (p.scattBias < 0 || p.scattBias > 1) throw Error("scattBias should be between 0 and 1");
     if (e.med.Ncomp > 8) throw Error("at most 8 dust components are supported");
+    if (!e.instr.empty() && e.instrNlambda != Nlambda) throw Error("the instruments were set up for " + std::to_string(e.instrNlambda) + " wavelengths but the medium has " + std::to_string(Nlambda) + ": call skg_instruments again");
     if (!(p.packages >= 0) || p.packages > 1e15) throw Error("Number of photon packages is negative or larger than implementation limit of 1e15");
     McDev P{};
     P.med = e.med; if (!e.med.rho) { P.med.Nlambda = Nlambda; P.med.Ncomp = 0; }
@@ -1013,6 +1014,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         int pool = p.poolPackets > 0 ? p.poolPackets : (1 << 22);
         pool = (int)std::min<unsigned long long>((unsigned long long)pool, total);
         pool = std::max(pool, 1);
+        if ((long long)pool * std::max(1, e.Ngroups) > 2000000000LL) throw Error("packet pool times observer directions exceeds the 32-bit work index: lower poolPackets");
         e.mcPool.ensure(2 * sizeof(Packet) * (size_t)pool);       // two pools: the stages ping-pong between them
         e.mcCounts.ensure(sizeof(int) * 8);
         if (!e.mcHostCounts) SKG_CUDA(cudaMallocHost(&e.mcHostCounts, 2 * sizeof(int)));

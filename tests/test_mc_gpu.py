@@ -137,3 +137,27 @@ def test_c2_benchmark_configuration_against_reference_runs(engine):
         z = common.zscores(a.mean(0), a.std(0, ddof=1) / np.sqrt(B), r.mean(0), r.std(0, ddof=1) / np.sqrt(B))
         assert np.all(np.abs(z) < 4.5) and np.mean(np.abs(z) < 3) > 0.9 and abs(z.mean()) < 0.6, f"{name}: z = {np.round(z, 2)}"
         assert abs(a.sum() / r.sum() - 1) < 0.01
+
+
+def test_configuration_errors_are_reported(engine):
+    """misuse of the C ABI comes back as an error message (the reference-side adapter turns it into FATALERROR)"""
+    import skirt_b200 as sk
+    tables, medium, g = common.load_golden_mc()
+    cfg = common.cfg_c1(n=24, packages=1e3)
+    common.setup_engine(engine, cfg, tables, medium, g["L"])
+    with pytest.raises(sk.EngineError, match="scattBias"):
+        engine.run_stellar(1e3, scatt_bias=1.5)
+    with pytest.raises(sk.EngineError, match="wavelength range"):
+        engine.run_stellar(1e3, ell_end=5)
+    with pytest.raises(sk.EngineError, match="negative|1e15"):
+        engine.run_stellar(-5)
+    # a medium with another number of wavelengths invalidates the detector arrays
+    med2 = {k: (np.concatenate([v, v], axis=1) if k != "rho" else v) for k, v in medium.items()}
+    engine.medium(med2["rho"], med2["kext"], med2["ksca"], med2["g"])
+    engine.sources(cfg["sources"], np.array([[1.0, 1.0]]), 0.5)
+    with pytest.raises(sk.EngineError, match="skg_instruments again"):
+        engine.run_stellar(1e3)
+    with pytest.raises(sk.EngineError, match="unsupported source geometry"):
+        engine.sources([dict(geometry=7, p=[1, 1])], np.array([[1.0, 1.0]]), 0.5)
+    with pytest.raises(sk.EngineError, match="skg_dust_library"):
+        engine.dust_cell_luminosities()
