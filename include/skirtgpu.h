@@ -123,9 +123,20 @@ typedef struct skg_source
     int ntab;
     const double* rv;
     const double* Xv;
+    /* tabulated profile S(s) on the same radii (SersicFunction::_Sv), only needed by skg_sample_density */
+    const double* Sv;
 } skg_source;
 /* L[h*Nlambda+ell] = StellarComp::luminosity(ell) of component h */
 int skg_sources(skg_engine* e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias);
+
+/* ---- set-up side: DustSystem::setSampleDensityBody (DustSystem.cpp:152-177) on the device ----------
+ * rho[m*Ncomp + h] = norm[h] * mean over sampleCount random positions in cell m (DustGrid::randomPositionInCell, the
+ * same position for all components) of the geometry density of component h (ExpDiskGeometry.cpp:117-129,
+ * SersicGeometry.cpp:66-70 + SpheroidalGeometryDecorator.cpp:47-52, SpiralStructureGeometryDecorator.cpp:49-58);
+ * norm[h] is the mass normalisation of the component (e.g. FaceOnDustCompNormalization.cpp:67-74).  The grid must have
+ * been set; geometries are described like the sources of skg_sources.  rho is a host array. */
+int skg_sample_density(skg_engine* e, int Ncomp, const skg_source* geometries, const double* norm, int sampleCount,
+                       uint64_t seed, double* rho);
 
 /* n launches of StellarSystem::launch(pp, ell, 1.0) with the engine's samplers (the kernel the shooting phase uses):
  * positions r[3n], directions k[3n] and bias-weighted luminosities L[n]; for distribution-level checks */

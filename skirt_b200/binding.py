@@ -27,7 +27,7 @@ class SkgSource(C.Structure):
                 ("spiral_arms", C.c_int), ("spiral_index", C.c_int),
                 ("spiral_pitch", C.c_double), ("spiral_radius", C.c_double),
                 ("spiral_phase", C.c_double), ("spiral_weight", C.c_double),
-                ("ntab", C.c_int), ("rv", C.c_void_p), ("Xv", C.c_void_p)]
+                ("ntab", C.c_int), ("rv", C.c_void_p), ("Xv", C.c_void_p), ("Sv", C.c_void_p)]
 
 
 class SkgInstrument(C.Structure):
@@ -239,9 +239,7 @@ class Engine:
         return a.value, b.value
 
     # ---- Monte Carlo -----------------------------------------------------------------------------
-    def sources(self, comps, L, emission_bias=0.5):
-        """comps: list of dicts(geometry=..., p=[...], spiral=dict|None, rv=..., Xv=...); L[Ncomp, Nlambda]."""
-        L = _f64(np.atleast_2d(L))
+    def _source_array(self, comps):
         arr = (SkgSource * len(comps))()
         keep = []
         for i, c in enumerate(comps):
@@ -257,7 +255,23 @@ class Engine:
             if c.get("rv") is not None:
                 rv = _f64(c["rv"]); Xv = _f64(c["Xv"]); keep += [rv, Xv]
                 s.ntab = len(rv); s.rv = rv.ctypes.data; s.Xv = Xv.ctypes.data
+                if c.get("Sv") is not None:
+                    Sv = _f64(c["Sv"]); keep.append(Sv); s.Sv = Sv.ctypes.data
+        return arr, keep
+
+    def sources(self, comps, L, emission_bias=0.5):
+        """comps: list of dicts(geometry=..., p=[...], spiral=dict|None, rv=..., Xv=...); L[Ncomp, Nlambda]."""
+        L = _f64(np.atleast_2d(L))
+        arr, keep = self._source_array(comps)
         self._chk(self._lib.skg_sources(self.h, len(comps), arr, L.shape[1], _vp(L), C.c_double(emission_bias)))
+
+    def sample_density(self, geometries, norm, sample_count=100, seed=4357):
+        """DustSystem::setSampleDensityBody on the device -> rho[Ncells, Ncomp]"""
+        arr, keep = self._source_array(geometries)
+        nrm = _f64(norm)
+        rho = np.zeros((self.Ncells, len(geometries)))
+        self._chk(self._lib.skg_sample_density(self.h, len(geometries), arr, _vp(nrm), int(sample_count), C.c_uint64(int(seed)), _vp(rho)))
+        return rho
 
     def sample_launch(self, ell, n, seed=1):
         r = np.zeros((n, 3)); k = np.zeros((n, 3)); L = np.zeros(n)

@@ -404,6 +404,8 @@ int skg_run_dust(skg_engine* eh, const skg_mc_params* p, int phase, double emiss
 { return guarded([&]{ if (!p) throw Error("null parameters"); mcRunDust(E(eh), *p, phase, emissionBias, mem, Lcell, stats); }); }
 int skg_sample_launch(skg_engine* eh, int ell, int n, uint64_t seed, double* r, double* k, double* L)
 { return guarded([&]{ mcSampleLaunch(E(eh), ell, n, seed, r, k, L); }); }
+int skg_sample_density(skg_engine* eh, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* rho)
+{ return guarded([&]{ mcSampleDensity(E(eh), Ncomp, geoms, norm, sampleCount, seed, rho); }); }
 int skg_reset_results(skg_engine* eh) { return guarded([&]{ mcResetResults(E(eh)); }); }
 int skg_dust_library(skg_engine* eh, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda)
 { return guarded([&]{ if (!volumes || !kappaabs || !lambda || !dlambda) throw Error("skg_dust_library: null table"); mcDustLibrary(E(eh), volumes, kappaabs, lambda, dlambda); }); }

@@ -37,7 +37,8 @@ struct SourceDev
     int geometry; double p[8];
     int spiral_arms, spiral_index; double spiral_pitch, spiral_radius, spiral_phase, spiral_weight;
     double spiral_c, spiral_tanp, spiral_cn;    // derived constants (SpiralStructureGeometryDecorator.cpp:24-45)
-    int ntab; const double* rv; const double* Xv;
+    int ntab; const double* rv; const double* Xv; const double* Sv;
+    double rho0;                                // density normalisation of the bare geometry
 };
 
 struct InstrDev
@@ -110,6 +111,7 @@ void mcFetchLabs(Engine& e, double* host, int add, int which);
 void mcLabsBolometric(Engine& e, double* host);
 void mcDustLibrary(Engine& e, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda);
 double* mcDustCellLuminosities(Engine& e);
+void mcSampleDensity(Engine& e, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* rho);
 void mcSampleLaunch(Engine& e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
 void mcRunDust(Engine& e, const skg_mc_params& p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats);
 

@@ -584,46 +584,57 @@ __global__ void transposeLabs(const double* __restrict__ src, double* __restrict
 
 // ---- host side -------------------------------------------------------------------------------------------
 
+// validates one geometry description and moves its tables to the device
+static SourceDev makeSourceDev(Engine& e, const skg_source& c, std::vector<DevBuf*>& bufs, bool needProfile)
+{
+    SourceDev s{};
+    s.geometry = c.geometry;
+    for (int j = 0; j < 8; j++) s.p[j] = c.p[j];
+    if (c.geometry == SKG_GEOM_EXPDISK)
+    {
+        if (!(c.p[0] > 0) || !(c.p[1] > 0)) throw Error("The radial scale length hR and axial scale height hz should be positive");  // ExpDiskGeometry.cpp:27-28
+        // ExpDiskGeometry::setupSelfBefore, ExpDiskGeometry.cpp:30-42
+        const double hR = c.p[0], hz = c.p[1], Rmax = c.p[2], zmax = c.p[3], Rmin = c.p[4];
+        double intz = zmax > 0 ? -2.0 * hz * std::expm1(-zmax / hz) : 2.0 * hz;
+        double tmin = Rmin > 0 ? std::exp(-Rmin / hR) * (1.0 + Rmin / hR) : 1.0;
+        double tmax = Rmax > 0 ? std::exp(-Rmax / hR) * (1.0 + Rmax / hR) : 0.0;
+        s.rho0 = 1.0 / (hR * hR * (tmin - tmax) * 2.0 * M_PI * intz);
+    }
+    else if (c.geometry == SKG_GEOM_SERSIC)
+    {
+        if (!(c.p[0] > 0)) throw Error("the effective radius should be positive");
+        if (c.ntab < 2 || !c.rv || !c.Xv) throw Error("Sersic geometry needs the tabulated inverse mass function");
+        if (needProfile && !c.Sv) throw Error("Sersic geometry needs the tabulated profile S(s) for density sampling");
+        if (c.p[1] == 0) s.p[1] = 1.0;
+        DevBuf* a = new DevBuf(); DevBuf* b = new DevBuf(); bufs.push_back(a); bufs.push_back(b);
+        a->upload(c.rv, sizeof(double) * c.ntab, e.stream); b->upload(c.Xv, sizeof(double) * c.ntab, e.stream);
+        s.ntab = c.ntab; s.rv = a->as<double>(); s.Xv = b->as<double>();
+        if (c.Sv) { DevBuf* d = new DevBuf(); bufs.push_back(d); d->upload(c.Sv, sizeof(double) * c.ntab, e.stream); s.Sv = d->as<double>(); }
+        s.rho0 = 1.0 / (c.p[0] * c.p[0] * c.p[0]);      // SersicGeometry.cpp:44
+    }
+    else throw Error("unsupported source geometry (no CPU fallback): " + std::to_string(c.geometry));
+    s.spiral_arms = c.spiral_arms; s.spiral_index = c.spiral_index; s.spiral_pitch = c.spiral_pitch;
+    s.spiral_radius = c.spiral_radius; s.spiral_phase = c.spiral_phase; s.spiral_weight = c.spiral_weight;
+    if (c.spiral_arms > 0)
+    {
+        // SpiralStructureGeometryDecorator::setupSelfBefore, SpiralStructureGeometryDecorator.cpp:24-40
+        if (c.spiral_pitch <= 0 || c.spiral_pitch >= M_PI / 2.) throw Error("The pitch angle should be between 0 and 90 degrees");
+        if (c.spiral_radius <= 0) throw Error("The radius zero-point should be positive");
+        if (c.spiral_weight <= 0 || c.spiral_weight > 1.) throw Error("The weight of the spiral perturbation should be between 0 and 1");
+        if (c.spiral_index < 0 || c.spiral_index > 10) throw Error("The arm-interarm size ratio index should be between 0 and 10");
+        s.spiral_tanp = std::tan(c.spiral_pitch);
+        s.spiral_cn = std::sqrt(M_PI) * std::tgamma(c.spiral_index + 1.0) / std::tgamma(c.spiral_index + 0.5);
+        s.spiral_c = 1.0 + (s.spiral_cn - 1.0) * c.spiral_weight;
+    }
+    return s;
+}
+
 void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias)
 {
     if (Ncomp < 1 || !comps || Nlambda < 1 || !L) throw Error("skg_sources: bad arguments");
     for (DevBuf* b : e.sourceBufs) delete b;       // (the wavelength count is checked against the medium when a phase starts)
     e.sourceBufs.clear(); e.sources.clear();
-    for (int h = 0; h < Ncomp; h++)
-    {
-        const skg_source& c = comps[h];
-        SourceDev s{};
-        s.geometry = c.geometry;
-        for (int j = 0; j < 8; j++) s.p[j] = c.p[j];
-        if (c.geometry == SKG_GEOM_EXPDISK)
-        {
-            if (!(c.p[0] > 0) || !(c.p[1] > 0)) throw Error("The radial scale length hR and axial scale height hz should be positive");  // ExpDiskGeometry.cpp:27-28
-        }
-        else if (c.geometry == SKG_GEOM_SERSIC)
-        {
-            if (!(c.p[0] > 0)) throw Error("the effective radius should be positive");
-            if (c.ntab < 2 || !c.rv || !c.Xv) throw Error("Sersic geometry needs the tabulated inverse mass function");
-            if (c.p[1] == 0) s.p[1] = 1.0;
-            DevBuf* a = new DevBuf(); DevBuf* b = new DevBuf(); e.sourceBufs.push_back(a); e.sourceBufs.push_back(b);
-            a->upload(c.rv, sizeof(double) * c.ntab, e.stream); b->upload(c.Xv, sizeof(double) * c.ntab, e.stream);
-            s.ntab = c.ntab; s.rv = a->as<double>(); s.Xv = b->as<double>();
-        }
-        else throw Error("unsupported source geometry (no CPU fallback): " + std::to_string(c.geometry));
-        s.spiral_arms = c.spiral_arms; s.spiral_index = c.spiral_index; s.spiral_pitch = c.spiral_pitch;
-        s.spiral_radius = c.spiral_radius; s.spiral_phase = c.spiral_phase; s.spiral_weight = c.spiral_weight;
-        if (c.spiral_arms > 0)
-        {
-            // SpiralStructureGeometryDecorator::setupSelfBefore, SpiralStructureGeometryDecorator.cpp:24-40
-            if (c.spiral_pitch <= 0 || c.spiral_pitch >= M_PI / 2.) throw Error("The pitch angle should be between 0 and 90 degrees");
-            if (c.spiral_radius <= 0) throw Error("The radius zero-point should be positive");
-            if (c.spiral_weight <= 0 || c.spiral_weight > 1.) throw Error("The weight of the spiral perturbation should be between 0 and 1");
-            if (c.spiral_index < 0 || c.spiral_index > 10) throw Error("The arm-interarm size ratio index should be between 0 and 10");
-            s.spiral_tanp = std::tan(c.spiral_pitch);
-            s.spiral_cn = std::sqrt(M_PI) * std::tgamma(c.spiral_index + 1.0) / std::tgamma(c.spiral_index + 0.5);
-            s.spiral_c = 1.0 + (s.spiral_cn - 1.0) * c.spiral_weight;
-        }
-        e.sources.push_back(s);
-    }
+    for (int h = 0; h < Ncomp; h++) e.sources.push_back(makeSourceDev(e, comps[h], e.sourceBufs, false));
     e.sourcesDev.upload(e.sources.data(), sizeof(SourceDev) * Ncomp, e.stream);
     // StellarSystem::setupSelfAfter, StellarSystem.cpp:35-52: total luminosities and per-wavelength CDFs
     e.lumHost.assign(L, L + (size_t)Ncomp * Nlambda);
@@ -1052,6 +1063,88 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         stats->launch_ms = e.stageMs[0]; stats->peel_ms = e.stageMs[1]; stats->absorb_ms = e.stageMs[2]; stats->propagate_ms = e.stageMs[3];
         stats->iterations = e.mcIterations;
     }
+}
+
+// Geometry::density for the supported geometries
+static __device__ double geometryDensity(const SourceDev& s, double x, double y, double z)
+{
+    double rho;
+    if (s.geometry == SKG_GEOM_EXPDISK)
+    {
+        // ExpDiskGeometry::density, ExpDiskGeometry.cpp:117-129
+        const double hR = s.p[0], hz = s.p[1], Rmax = s.p[2], zmax = s.p[3], Rmin = s.p[4];
+        double R = sqrt(x * x + y * y), absz = fabs(z);
+        if ((Rmax > 0.0 && R > Rmax) || (zmax > 0.0 && absz > zmax) || R < Rmin) rho = 0.0;
+        else rho = s.rho0 * exp(-R / hR) * exp(-absz / hz);
+    }
+    else
+    {
+        // SpheroidalGeometryDecorator::density (:47-52) around SersicGeometry::density (:66-70), SersicFunction::operator() (:82-93)
+        const double reff = s.p[0], q = s.p[1];
+        double zz = z / q;
+        double sr = sqrt(x * x + y * y + zz * zz) / reff;
+        int Ns = s.ntab; double S;
+        if (sr <= s.rv[0]) S = s.Sv[0];
+        else if (sr >= s.rv[Ns - 1]) S = s.Sv[Ns - 1];
+        else { int i = locateClip(s.rv, sr, Ns); S = interpLogLog(sr, s.rv[i], s.rv[i + 1], s.Sv[i], s.Sv[i + 1]); }
+        rho = s.rho0 * S / q;
+    }
+    if (s.spiral_arms > 0)
+    {
+        // SpiralStructureGeometryDecorator::density + perturbation, SpiralStructureGeometryDecorator.cpp:49-58,224-229
+        double R = sqrt(x * x + y * y), phi = atan2(y, x);
+        double gamma = log(R / s.spiral_radius) / s.spiral_tanp + s.spiral_phase + 0.5 * M_PI / s.spiral_arms;
+        rho *= (1.0 - s.spiral_weight) + s.spiral_weight * s.spiral_cn * pow(sin(0.5 * s.spiral_arms * (gamma - phi)), 2 * s.spiral_index);
+    }
+    return rho;
+}
+
+// DustSystem::setSampleDensityBody, DustSystem.cpp:152-177: one thread per cell
+template<int KIND>
+__global__ void __launch_bounds__(128) sampleDensityKernel(const __grid_constant__ GridSetMC G, const SourceDev* __restrict__ geoms, const double* __restrict__ norm,
+                                                           int Ncells, int Ncomp, int sampleCount, unsigned long long seed, double* __restrict__ rho, Counters* ctr)
+{
+    for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < Ncells; m += gridDim.x * blockDim.x)
+    {
+        Philox rng; rng.init(seed, (unsigned long long)m, 7u);
+        double sum[8];
+        for (int h = 0; h < Ncomp; h++) sum[h] = 0;
+        for (int n = 0; n < sampleCount; n++)
+        {
+            double x, y, z;
+            if (!randomPositionInCell<KIND>(G, m, rng, x, y, z)) { atomicAdd(&ctr->errors, 1ull); break; }
+            for (int h = 0; h < Ncomp; h++) sum[h] += norm[h] * geometryDensity(geoms[h], x, y, z);
+        }
+        for (int h = 0; h < Ncomp; h++) rho[(size_t)m * Ncomp + h] = sum[h] / sampleCount;
+    }
+}
+
+void mcSampleDensity(Engine& e, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* rho)
+{
+    if (e.gridKind == GRID_NONE) throw Error("no dust grid has been set");
+    if (Ncomp < 1 || Ncomp > 8 || !geoms || !norm || !rho) throw Error("skg_sample_density: bad arguments");
+    if (sampleCount < 1) throw Error("the number of random density samples should be positive");
+    if (e.gridKind == GRID_VORO && !e.voro.cellBox) throw Error("the Voronoi grid was given without cell boxes (needed by randomPositionInCell)");
+    std::vector<DevBuf*> bufs; std::vector<SourceDev> dev;
+    DevBuf devGeoms, devNorm, devRho;
+    try
+    {
+        for (int h = 0; h < Ncomp; h++) dev.push_back(makeSourceDev(e, geoms[h], bufs, true));
+        devGeoms.upload(dev.data(), sizeof(SourceDev) * Ncomp, e.stream); devNorm.upload(norm, sizeof(double) * Ncomp, e.stream);
+        devRho.ensure(sizeof(double) * (size_t)e.Ncells * Ncomp);
+        GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro;
+        Counters before = e.readCounters();
+        int blocks = std::max(1, std::min((e.Ncells + 127) / 128, e.smCount * 16));
+#define SKG_DENS(K) sampleDensityKernel<K><<<blocks, 128, 0, e.stream>>>(G, devGeoms.as<SourceDev>(), devNorm.as<double>(), e.Ncells, Ncomp, sampleCount, seed, devRho.as<double>(), e.ctr())
+        switch (e.gridKind) { case GRID_CART: SKG_DENS(GRID_CART); break; case GRID_TREE: SKG_DENS(GRID_TREE); break;
+                              case GRID_AMESH: SKG_DENS(GRID_AMESH); break; default: SKG_DENS(GRID_VORO); }
+        e.launches++; SKG_CUDA(cudaGetLastError());
+        SKG_CUDA(cudaMemcpyAsync(rho, devRho.p, sizeof(double) * (size_t)e.Ncells * Ncomp, cudaMemcpyDeviceToHost, e.stream));
+        e.sync();
+        if (e.readCounters().errors != before.errors) throw Error("Can't find random position in cell");      // VoronoiMesh.cpp:606
+    }
+    catch (...) { for (DevBuf* b : bufs) delete b; throw; }
+    for (DevBuf* b : bufs) delete b;
 }
 
 __global__ void unpackLaunches(const Packet* __restrict__ pool, int n, double* __restrict__ r, double* __restrict__ k, double* __restrict__ L)

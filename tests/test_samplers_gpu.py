@@ -93,3 +93,61 @@ def test_two_dust_components_and_simple_instrument(engine):
             assert np.mean(np.abs(zz) < 3) > 0.96 and abs(zz.mean()) < 0.3, f"{name}: {np.mean(np.abs(zz) < 3):.4f} within 3 sigma, mean z {zz.mean():.3f}"
     # the SimpleInstrument's SED is the sum of its frame plus the packets that fall outside the frame
     assert np.array(gpu["sed"]).sum() >= np.array(gpu["frame"]).sum() * (1 - 1e-12)
+
+
+@pytest.mark.parametrize("kind", ["cartesian", "octtree"])
+def test_density_sampling_on_the_device(engine, kind):
+    """DustSystem::setSampleDensityBody on the device (SURVEY.md 8f row 3) against the reference's own density table:
+    same total mass, per-cell differences no larger than the Monte Carlo noise of 100 samples per cell"""
+    from oracle import skirtref as sr
+    from skirt_b200 import simulation as sim
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    PC = common.PC
+    if kind == "cartesian":
+        cfg = common.cfg_c1(n=24, packages=10, dustsamples=100, threads=os.cpu_count() or 1)
+        S = common.make_ref(cfg).setup()
+    else:
+        S = sr.RefSim(common.spec_grid("octtree", search=1, maxlevel=5, packages=10, threads=os.cpu_count() or 1).replace("dustsamples 10", "dustsamples 100"),
+                      luminosities=[[1.0]], mixes=common.mix_v()).setup()
+    tables, medium = S.grid_tables(), S.medium()
+    engine.set_grid(tables)
+    geo = sim.ExpDiskGeometry(4000 * PC, 140 * PC)
+    kext = common.MIX_V["kabs"] + common.MIX_V["ksca"]
+    norm = 1.0 / (geo.SigmaZ() * kext)                      # FaceOnDustCompNormalization.cpp:67-74 with tau = 1
+    g = geo.sampler()
+    ref = medium["rho"][:, 0]
+    vol = S.volumes()
+    if kind == "octtree":
+        # TreeDustGrid implements DustGridDensityInterface through the mass in each node's box (TreeDustGrid.cpp:666-679),
+        # i.e. the reference's table is the exact cell average up to its own sampling: compare the masses only
+        pass
+    r1 = engine.sample_density([g], [norm], 100, seed=1)[:, 0]
+    r2 = engine.sample_density([g], [norm], 100, seed=2)[:, 0]
+    assert abs((r1 * vol).sum() / (ref * vol).sum() - 1) < 0.01
+    big = ref > 1e-3 * ref.max()
+    assert abs(np.median(r1[big] / ref[big]) - 1) < 0.02
+    noise = np.std((r1 - r2)[big] / ref[big])
+    assert np.std((r1 - ref)[big] / ref[big]) < 1.5 * noise + 0.02
+    # a flattened Sersic component and a spiral-armed disk (which the reference's face-on normalisation does not accept,
+    # FaceOnDustCompNormalization.cpp:72) next to it: masses against the host mirror's densities on a fine lattice
+    if kind == "cartesian":
+        ser = sim.SersicGeometry(2.0, 1600 * PC, 0.7)
+        sg = ser.sampler(); sg["Sv"] = ser.fn.Sv
+        spi = sim.SpiralStructureGeometryDecorator(sim.ExpDiskGeometry(4000 * PC, 350 * PC), 2, float(np.radians(20)), 4000 * PC, 0.3, 0.8, 1)
+        r = engine.sample_density([g, sg, spi.sampler()], [norm, 1.0, 1.0], 200, seed=3)
+        assert r.shape == (engine.Ncells, 3) and abs((r[:, 0] * vol).sum() / (ref * vol).sum() - 1) < 0.01
+        grid = sim.CartesianDustGrid(*common.C1_BOX, sim.LinMesh(24), sim.LinMesh(24), sim.LinMesh(24))
+        pts, v = grid.cell_samples(4)
+        wspi = np.mean([spi.density(p_[:, 0], p_[:, 1], p_[:, 2]) for p_ in pts], axis=0)
+        assert abs((r[:, 2] * vol).sum() / (wspi * vol).sum() - 1) < 0.02
+        arm = wspi > 0.2 * wspi.max()
+        assert np.corrcoef(r[arm, 2], wspi[arm])[0, 1] > 0.95
+        want = np.mean([ser.density(p_[:, 0], p_[:, 1], p_[:, 2]) for p_ in pts], axis=0)
+        # the cusp of the Sersic profile sits in the 8 central cells; compare outside them
+        outer = np.ones(len(want), bool); c = 24 // 2
+        for i in (c - 1, c):
+            for j in (c - 1, c):
+                for k in (c - 1, c):
+                    outer[k + 24 * j + 576 * i] = False
+        assert abs((r[outer, 1] * vol[outer]).sum() / (want[outer] * vol[outer]).sum() - 1) < 0.03
