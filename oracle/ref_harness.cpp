@@ -69,6 +69,7 @@
 #include "Random.hpp"
 #include "SEDInstrument.hpp"
 #include "SersicGeometry.hpp"
+#include "SIUnits.hpp"
 #include "SimpleInstrument.hpp"
 #include "SpheroidalGeometryDecorator.hpp"
 #include "SpiralStructureGeometryDecorator.hpp"
@@ -359,6 +360,7 @@ namespace
         S->mc->setPackages(packages); S->mc->setMinWeightReduction(mwr); S->mc->setMinScattEvents(minscatt); S->mc->setScattBias(xi);
         S->ss->setEmissionBias(ebias);
         S->mc->setInstrumentSystem(S->is);
+        S->mc->setUnits(new SIUnits());
         S->dd = S->amdd ? (DustDistribution*)S->amdd : (DustDistribution*)S->cdd;
         if (S->pan)
         {
@@ -406,6 +408,10 @@ namespace
 
     int numLambda(Sim* S) { return S->pan ? S->plg->Nlambda() : S->olg->Nlambda(); }
 }
+
+// captured by the Image / TextOutFile stand-ins (ref_stubs/services.cpp)
+std::map<std::string, std::vector<double>>& skr_saved_images();
+std::map<std::string, std::vector<std::vector<double>>>& skr_saved_rows();
 
 extern "C"
 {
@@ -789,6 +795,29 @@ int skr_random_positions(void* h, int m, long n, double* xyz)
 {
     Sim* S = (Sim*)h;
     return guarded([&]{ for (long i = 0; i < n; i++) { Position r = S->grid->randomPositionInCell(m); xyz[3*i] = r.x(); xyz[3*i+1] = r.y(); xyz[3*i+2] = r.z(); } });
+}
+
+// ---- output: Instrument::write() = sumResults + calibration (SingleFrameInstrument.cpp:151-226, DistantInstrument.cpp:131-183);
+// the calibrated data cubes / SED rows are captured by the Image / TextOutFile stand-ins of ref_stubs
+int skr_write_instruments(void* h)
+{
+    Sim* S = (Sim*)h;
+    return guarded([&]{ for (Instrument* ins : S->is->instruments()) ins->write(); });
+}
+long skr_saved_image(const char* name, double* out, long cap)
+{
+    auto it = skr_saved_images().find(name);
+    if (it == skr_saved_images().end()) return -1;
+    if (out) for (long i = 0; i < cap && i < (long)it->second.size(); i++) out[i] = it->second[i];
+    return (long)it->second.size();
+}
+long skr_saved_table(const char* name, double* out, long cap, int* ncols)
+{
+    auto it = skr_saved_rows().find(name);
+    if (it == skr_saved_rows().end()) return -1;
+    long n = 0; *ncols = it->second.empty() ? 0 : (int)it->second[0].size();
+    for (auto& row : it->second) for (double v : row) { if (out && n < cap) out[n] = v; n++; }
+    return n;
 }
 
 // ---- samplers exposed for distribution-level checks ------------------------------------------------

@@ -13,12 +13,22 @@
 #include "Console.hpp"
 #include "MemoryStatistics.hpp"
 
-// ---- TextOutFile: swallow everything ----
-TextOutFile::TextOutFile(const SimulationItem*, QString, QString, bool) : _log(0), _units(0), _ncolumns(0) {}
-TextOutFile::~TextOutFile() {}
+// ---- TextOutFile: keep the numeric rows in memory, keyed by file name (SED files) ----
+std::map<std::string, std::vector<std::vector<double>>>& skr_saved_rows()
+{ static std::map<std::string, std::vector<std::vector<double>>> m; return m; }
+static std::map<const TextOutFile*, std::string>& openNames() { static std::map<const TextOutFile*, std::string> m; return m; }
+static std::mutex txtMutex;
+TextOutFile::TextOutFile(const SimulationItem*, QString filename, QString, bool) : _log(0), _units(0), _ncolumns(0)
+{ std::lock_guard<std::mutex> lock(txtMutex); openNames()[this] = filename.toStdString(); skr_saved_rows()[filename.toStdString()].clear(); }
+TextOutFile::~TextOutFile() { std::lock_guard<std::mutex> lock(txtMutex); openNames().erase(this); }
 void TextOutFile::writeLine(QString) {}
 void TextOutFile::addColumn(QString, char, int) {}
-void TextOutFile::writeRow(QList<double>) {}
+void TextOutFile::writeRow(QList<double> values)
+{
+    std::lock_guard<std::mutex> lock(txtMutex);
+    std::vector<double> row; for (int i = 0; i < values.size(); i++) row.push_back(values[i]);
+    skr_saved_rows()[openNames()[this]].push_back(row);
+}
 
 // ---- DustGridPlotFile ----
 DustGridPlotFile::DustGridPlotFile(const SimulationItem* item, QString filename) : TextOutFile(item, filename, "") {}

@@ -32,6 +32,8 @@ def lib():
         L.skr_packages_per_lambda.restype = C.c_double
         L.skr_path_batch.restype = C.c_long
         L.skr_warnings.restype = C.c_long
+        L.skr_saved_image.restype = C.c_long
+        L.skr_saved_table.restype = C.c_long
         _lib = L
     return _lib
 
@@ -288,6 +290,29 @@ class RefSim:
         xyz = np.zeros((n, 3))
         self._chk(lib().skr_random_positions(self.h, int(m), C.c_long(n), xyz.ctypes.data_as(C.c_void_p)))
         return xyz
+
+    # ---- output ------------------------------------------------------------------------------------
+    def write_instruments(self):
+        """Instrument::write() for every instrument (calibration included); note that it calibrates the detector
+        arrays IN PLACE, like the reference does at the end of a simulation"""
+        self._chk(lib().skr_write_instruments(self.h))
+
+    def saved_image(self, name):
+        n = lib().skr_saved_image(name.encode(), None, C.c_long(0))
+        if n < 0:
+            raise RefError(f"no image named {name}")
+        a = np.zeros(n)
+        lib().skr_saved_image(name.encode(), a.ctypes.data_as(C.c_void_p), C.c_long(n))
+        return a
+
+    def saved_table(self, name):
+        nc = C.c_int()
+        n = lib().skr_saved_table(name.encode(), None, C.c_long(0), C.byref(nc))
+        if n < 0:
+            raise RefError(f"no table named {name}")
+        a = np.zeros(n)
+        lib().skr_saved_table(name.encode(), a.ctypes.data_as(C.c_void_p), C.c_long(n), C.byref(nc))
+        return a.reshape(-1, max(nc.value, 1))
 
     def sample_launch(self, ell, n):
         r = np.zeros((n, 3)); k = np.zeros((n, 3)); Lw = np.zeros(n)
