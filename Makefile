@@ -6,18 +6,21 @@ ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := $(EXTRA) $(ARCH) -ccbin $(HOSTCXX) -std=c++17 -O3 -lineinfo -fmad=false --expt-relaxed-constexpr \
            -Xcompiler -fPIC,-ffp-contract=off,-Wall,-Wno-unused-function -Xptxas -v
 CSRC := skirt_b200/csrc
-OBJS := $(CSRC)/build/engine.o $(CSRC)/build/path_kernels.o $(CSRC)/build/mc_kernels.o $(CSRC)/build/comm.o
+# BUILD / LIB can be overridden to build experiment variants side by side (tools/gpu_variants.sh)
+BUILD ?= $(CSRC)/build
+LIB ?= skirt_b200/libskirtgpu.so
+OBJS := $(BUILD)/engine.o $(BUILD)/path_kernels.o $(BUILD)/mc_kernels.o $(BUILD)/comm.o
 HDRS := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/skirtgpu.h
 NCCL_INC ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'include'))" 2>/dev/null)
 NCCL_LIB ?= $(shell python -c "import os,nvidia.nccl as n; print(os.path.join(list(n.__path__)[0],'lib'))" 2>/dev/null)
 
-all: skirt_b200/libskirtgpu.so skirt_b200/skirt_b200_run oracle
+all: $(LIB) skirt_b200/skirt_b200_run oracle
 
-$(CSRC)/build/%.o: $(CSRC)/%.cu $(HDRS)
-	@mkdir -p $(CSRC)/build
-	$(NVCC) $(NVFLAGS) -I$(NCCL_INC) -c $< -o $@ 2> $(CSRC)/build/$*.ptxas.log || (cat $(CSRC)/build/$*.ptxas.log; false)
+$(BUILD)/%.o: $(CSRC)/%.cu $(HDRS)
+	@mkdir -p $(BUILD)
+	$(NVCC) $(NVFLAGS) -I$(NCCL_INC) -c $< -o $@ 2> $(BUILD)/$*.ptxas.log || (cat $(BUILD)/$*.ptxas.log; false)
 
-skirt_b200/libskirtgpu.so: $(OBJS)
+$(LIB): $(OBJS)
 	$(NVCC) $(ARCH) -ccbin $(HOSTCXX) -shared -o $@ $(OBJS) -ldl
 
 # C++ host layer (simulation items with the reference's names) + command-line driver, linked against the C ABI only

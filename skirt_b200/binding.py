@@ -7,7 +7,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libskirtgpu.so")
+# SKG_LIBRARY selects another build of the same library (kernel experiments); there is still no fallback
+LIB_PATH = os.environ.get("SKG_LIBRARY") or os.path.join(_HERE, "libskirtgpu.so")
 _lib = None
 
 SKG_HOST, SKG_DEVICE = 0, 1

@@ -14,6 +14,8 @@ namespace skg
 struct Error : std::runtime_error { using std::runtime_error::runtime_error; };
 void setLastError(const std::string& msg);   // message returned by skg_last_error()
 
+#define SKG_CART_SMEM_MAX (64 * 1024)      // shared-memory budget of the staged Cartesian borders (3 arrays of N+1 doubles)
+
 #define SKG_CUDA(call) do { cudaError_t err__ = (call); if (err__ != cudaSuccess) \
     throw skg::Error(std::string(#call) + ": " + cudaGetErrorString(err__)); } while (0)
 

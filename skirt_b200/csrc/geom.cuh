@@ -92,13 +92,35 @@ __device__ __forceinline__ int cartWhichCell(const CartGrid& g, double x, double
     return k + g.Nz * j + g.Nz * g.Ny * i;
 }
 
+// 8-byte load from the shared window (the staged Cartesian borders): an explicit LDS instead of a generic load
+__device__ __forceinline__ double ldsF64(unsigned addr)
+{ double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
+
 // One crossing at a time: CartesianDustGrid::path (CartesianDustGrid.cpp:136-283) as a state machine, so that a
 // warp can refill finished lanes with new rays instead of waiting for its longest path.
-struct CartWalker
+//
+// Per-ray invariants are hoisted out of the crossing: the walker tracks, per axis, the BYTE OFFSET of the border the
+// ray leaves through (xv[i+1] for k >= 0, xv[i] for k < 0, :236-238), the signed offset / cell-number increments
+// of a crossing, and the offset at which the ray leaves the grid.  A crossing is then three shared-memory loads,
+// three invariant-divisor divisions, the reference's three-way exit test as selects, and predicated increments.
+#ifndef SKG_CART_REGBORDERS
+#define SKG_CART_REGBORDERS 0
+#endif
+// REGB: keep the three exit borders in registers and re-read only the axis that was crossed (fewer shared-memory
+// wavefronts: for kernels whose load/store pipe is the bottleneck); otherwise read all three every crossing (the
+// loads are issued first and overlap, shortest dependency chain).
+// TINYSEL: how direction components with |k| <= 1e-15 are handled: as unconditional selects (peel-off rays towards
+// an observer at azimuth 0/90/... have an exactly zero component in EVERY lane) or as a branch that random rays
+// essentially never take.
+template<bool REGB, bool TINYSEL> struct CartWalkerT
 {
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;       // 1/k per axis (see divInvariant)
-    int i, j, k, m;
+    double xE, yE, zE;          // the exit borders themselves: only the axis that was crossed is re-read
+    int ox, oy, oz;             // byte offsets of the exit borders in xv / yv / zv
+    int stx, sty, stz;          // +-8: offset increment of a crossing along each axis
+    int dmx, dmy, dmz;          // cell number increments (m = k + Nz*j + Nz*Ny*i, :326-329)
+    int m, tiny;                // tiny: bit a set when |k_a| <= 1e-15 (that axis is never crossed, :240-242)
     bool alive;
 
     // entry part, :151-230.  Returns false when the ray misses the grid (the reference clears the path);
@@ -149,11 +171,17 @@ struct CartWalker
             x += kx * ds; y += ky * ds; z = zmax - 1e-8 * (zv[Nz] - zv[Nz - 1]);
         }
         if (x < xmin || x > xmax || y < ymin || y > ymax || z < zmin || z > zmax) return false;     // :224
-        i = locateClip(xv, x, Nx + 1);
-        j = locateClip(yv, y, Ny + 1);
-        k = locateClip(zv, z, Nz + 1);
+        const int i = locateClip(xv, x, Nx + 1);
+        const int j = locateClip(yv, y, Ny + 1);
+        const int k = locateClip(zv, z, Nz + 1);
         m = k + Nz * j + Nz * Ny * i;
+        const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
+        ox = 8 * (i + (nx ? 0 : 1)); oy = 8 * (j + (ny ? 0 : 1)); oz = 8 * (k + (nz ? 0 : 1));
+        stx = nx ? -8 : 8; sty = ny ? -8 : 8; stz = nz ? -8 : 8;
+        dmx = nx ? -Ny * Nz : Ny * Nz; dmy = ny ? -Nz : Nz; dmz = nz ? -1 : 1;
+        tiny = (fabs(kx) > 1e-15 ? 0 : 1) | (fabs(ky) > 1e-15 ? 0 : 2) | (fabs(kz) > 1e-15 ? 0 : 4);
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
+        if (REGB) { xE = ldsF64(g.sx + ox); yE = ldsF64(g.sy + oy); zE = ldsF64(g.sz + oz); }
         alive = true;
         return true;
     }
@@ -161,13 +189,27 @@ struct CartWalker
     // one pass of the loop :234-282.  Returns true when segment (mseg, ds) is to be added (addSegment drops ds <= 0).
     __device__ __forceinline__ bool step(const CartGrid& g, Counters*, int& mseg, double& ds)
     {
-        const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
-        const double xE = g.xv[i + (nx ? 0 : 1)];
-        const double yE = g.yv[j + (ny ? 0 : 1)];
-        const double zE = g.zv[k + (nz ? 0 : 1)];
-        const double dsx = (fabs(kx) > 1e-15) ? divInvariant(xE - x, kx, rkx) : SKG_DBL_MAX;
-        const double dsy = (fabs(ky) > 1e-15) ? divInvariant(yE - y, ky, rky) : SKG_DBL_MAX;
-        const double dsz = (fabs(kz) > 1e-15) ? divInvariant(zE - z, kz, rkz) : SKG_DBL_MAX;
+        // the borders are always staged in shared memory by the kernels that walk (stageCart)
+        if (!REGB) { xE = ldsF64(g.sx + ox); yE = ldsF64(g.sy + oy); zE = ldsF64(g.sz + oz); }
+        double dsx = divInvariant(xE - x, kx, rkx);
+        double dsy = divInvariant(yE - y, ky, rky);
+        double dsz = divInvariant(zE - z, kz, rkz);
+        // direction components with |k| <= 1e-15 never cross a border: ds = DBL_MAX (:240-242)
+        if (TINYSEL)
+        {
+            dsx = (tiny & 1) ? SKG_DBL_MAX : dsx; dsy = (tiny & 2) ? SKG_DBL_MAX : dsy; dsz = (tiny & 4) ? SKG_DBL_MAX : dsz;
+        }
+        else if (tiny)
+        {
+            // written as a loop over the set bits so that it stays a branch instead of predicated selects
+            int t = tiny;
+            do
+            {
+                const int bit = t & -t;
+                if (bit == 1) dsx = SKG_DBL_MAX; else if (bit == 2) dsy = SKG_DBL_MAX; else dsz = SKG_DBL_MAX;
+                t ^= bit;
+            } while (t);
+        }
         mseg = m;
         // the reference's three branches (X if dsx<=dsy&&dsx<=dsz, Y if dsy<dsx&&dsy<=dsz, Z if dsz<dsx&&dsz<dsy) as selects,
         // so that the lanes of a warp do not diverge on the exit face: the hit coordinate snaps to the face, the other two
@@ -179,10 +221,14 @@ struct CartWalker
         ds = bx ? dsx : (by ? dsy : dsz);
         const double xa = x + kx * ds, ya = y + ky * ds, za = z + kz * ds;
         x = bx ? xE : xa; y = by ? yE : ya; z = bz ? zE : za;
-        const int di = bx ? (nx ? -1 : 1) : 0, dj = by ? (ny ? -1 : 1) : 0, dk = bz ? (nz ? -1 : 1) : 0;
-        i += di; j += dj; k += dk;
-        m += di * g.Ny * g.Nz + dj * g.Nz + dk;
-        if ((unsigned)i >= (unsigned)g.Nx || (unsigned)j >= (unsigned)g.Ny || (unsigned)k >= (unsigned)g.Nz) alive = false;
+        // only the crossed axis gets a new exit border (one shared-memory read per crossing, a third of the lanes
+        // per table: few bank conflicts); the staged arrays carry one pad element on either side, so that the read
+        // is harmless when the ray has just left the grid
+        if (bx) { ox += stx; m += dmx; if (REGB) xE = ldsF64(g.sx + ox); }
+        if (by) { oy += sty; m += dmy; if (REGB) yE = ldsF64(g.sy + oy); }
+        if (bz) { oz += stz; m += dmz; if (REGB) zE = ldsF64(g.sz + oz); }
+        // left the grid: the offset stepped below 0 (wraps) or beyond the last border
+        alive = (unsigned)ox <= 8u * g.Nx && (unsigned)oy <= 8u * g.Ny && (unsigned)oz <= 8u * g.Nz;
         return ds > 0;
     }
 };

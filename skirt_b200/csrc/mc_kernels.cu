@@ -26,12 +26,17 @@ __device__ __forceinline__ CartGrid stageCartMC(const CartGrid& g, double* smem,
 {
     if (!useSmem) return g;
     CartGrid s = g;
+    // layout: [pad] xv[0..Nx] [pad] [pad] yv[0..Ny] [pad] [pad] zv[0..Nz] [pad]   (SKG_CART_SMEM_DOUBLES)
     int nx = g.Nx + 1, ny = g.Ny + 1, nz = g.Nz + 1;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) smem[i] = g.xv[i];
-    for (int i = threadIdx.x; i < ny; i += blockDim.x) smem[nx + i] = g.yv[i];
-    for (int i = threadIdx.x; i < nz; i += blockDim.x) smem[nx + ny + i] = g.zv[i];
+    double* sxv = smem + 1; double* syv = sxv + nx + 2; double* szv = syv + ny + 2;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) sxv[i] = g.xv[i];
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) syv[i] = g.yv[i];
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) szv[i] = g.zv[i];
+    if (threadIdx.x == 0) { sxv[-1] = sxv[nx] = syv[-1] = syv[ny] = szv[-1] = szv[nz] = 0.0; }
     __syncthreads();
-    s.xv = smem; s.yv = smem + nx; s.zv = smem + nx + ny;
+    s.xv = sxv; s.yv = syv; s.zv = szv;
+    s.sx = (unsigned)__cvta_generic_to_shared(sxv); s.sy = (unsigned)__cvta_generic_to_shared(syv); s.sz = (unsigned)__cvta_generic_to_shared(szv);
+    s.staged = 1;
     return s;
 }
 
@@ -215,6 +220,7 @@ __device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, doub
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
 template<int KIND, bool SINGLE> struct PeelJob
 {
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = true;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
     double Lw, tau; KappaRho kr; int ell, grp;
@@ -325,6 +331,7 @@ __global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSet
 // scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
 template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
 {
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     int* counts;
     double rx, ry, rz, dx, dy, dz;
@@ -501,6 +508,7 @@ __global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridS
 // DustGridPath::pathlength (DustGridPath.cpp:162-173) evaluated on the fly + PhotonPackage::propagate (PhotonPackage.cpp:93-96)
 template<int KIND, bool SINGLE> struct PropagateJob
 {
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false;
     const McDev& P;
     double rx, ry, rz, dx, dy, dz;
     KappaRho kr; double target, sPrev, tauPrev, result; bool found; int slot;
@@ -1033,8 +1041,23 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         size_t smem = 0; bool cartSmem = false;
         if (e.gridKind == GRID_CART)
         {
-            size_t need = sizeof(double) * (size_t)(e.cart.Nx + e.cart.Ny + e.cart.Nz + 3);
-            if (need <= 40 * 1024) { smem = need; cartSmem = true; }
+            size_t need = sizeof(double) * SKG_CART_SMEM_DOUBLES(e.cart);
+            if (need > SKG_CART_SMEM_MAX) throw Error("CartesianDustGrid: more than 8189 mesh borders in total are not supported");
+            smem = need; cartSmem = true;
+            static bool attr = false;
+            if (!attr)
+            {
+                const int cap = 96 * 1024;
+                SKG_CUDA(cudaFuncSetAttribute(peelStage<GRID_CART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                SKG_CUDA(cudaFuncSetAttribute(peelStage<GRID_CART, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                SKG_CUDA(cudaFuncSetAttribute(propagateStage<GRID_CART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                SKG_CUDA(cudaFuncSetAttribute(propagateStage<GRID_CART, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+                attr = true;
+            }
         }
         GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro;
         switch (e.gridKind)

@@ -21,12 +21,17 @@ __device__ __forceinline__ CartGrid stageCart(const CartGrid& g, double* smem, b
 {
     if (!useSmem) return g;
     CartGrid s = g;
+    // layout: [pad] xv[0..Nx] [pad] [pad] yv[0..Ny] [pad] [pad] zv[0..Nz] [pad]   (SKG_CART_SMEM_DOUBLES)
     int nx = g.Nx + 1, ny = g.Ny + 1, nz = g.Nz + 1;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) smem[i] = g.xv[i];
-    for (int i = threadIdx.x; i < ny; i += blockDim.x) smem[nx + i] = g.yv[i];
-    for (int i = threadIdx.x; i < nz; i += blockDim.x) smem[nx + ny + i] = g.zv[i];
+    double* sxv = smem + 1; double* syv = sxv + nx + 2; double* szv = syv + ny + 2;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) sxv[i] = g.xv[i];
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) syv[i] = g.yv[i];
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) szv[i] = g.zv[i];
+    if (threadIdx.x == 0) { sxv[-1] = sxv[nx] = syv[-1] = syv[ny] = szv[-1] = szv[nz] = 0.0; }
     __syncthreads();
-    s.xv = smem; s.yv = smem + nx; s.zv = smem + nx + ny;
+    s.xv = sxv; s.yv = syv; s.zv = szv;
+    s.sx = (unsigned)__cvta_generic_to_shared(sxv); s.sy = (unsigned)__cvta_generic_to_shared(syv); s.sz = (unsigned)__cvta_generic_to_shared(szv);
+    s.staged = 1;
     return s;
 }
 
@@ -35,6 +40,7 @@ struct RayJobBase
 {
     const double* r; const double* k;
     double rx, ry, rz, dx, dy, dz;
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false;
     __device__ __forceinline__ void loadRay(int i)
     { rx = r[3 * (size_t)i]; ry = r[3 * (size_t)i + 1]; rz = r[3 * (size_t)i + 2]; dx = k[3 * (size_t)i]; dy = k[3 * (size_t)i + 1]; dz = k[3 * (size_t)i + 2]; }
     __device__ __forceinline__ void collective(bool) {}
@@ -90,41 +96,54 @@ __global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ G
 // record index -- so L2 never merges partial sectors and DRAM sees every byte once.  Only the first and last
 // few records of a path (unaligned ends) are written one by one.
 #define SKG_RING 12         // three groups of four: at most 11 entries are parked at any time
-#define SKG_RSTRIDE 13      // entries per lane in a ring (12 + 1 pad against bank conflicts)
 __device__ __forceinline__ void store4(double* p, double a, double b, double c, double d)
 { asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory"); }
 __device__ __forceinline__ double cellWord(int m) { return __longlong_as_double((long long)(unsigned)m); }    // {int m; int reserved = 0}
 // asynchronous 8-byte copy global -> shared (LDGSTS): the density of a crossed cell goes straight into the lane's
 // ring without occupying a register or stalling the walker; it is consumed one period later
-__device__ __forceinline__ void asyncCopy8(double* smemDst, const double* src)
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smemDst)), "l"(src) : "memory"); }
+__device__ __forceinline__ void asyncCopy8(unsigned smemDst, const double* src)
+{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smemDst), "l"(src) : "memory"); }
 __device__ __forceinline__ void asyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void asyncWaitAllButLatest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void asyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void stsF64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
+__device__ __forceinline__ void stsI32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ double ldsVF64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
+__device__ __forceinline__ int ldsVI32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 
+// The rings are lane-interleaved in shared memory -- entry q of lane l lives at [q][l] -- so that every access of a
+// warp is bank-conflict free whatever ring positions its lanes are at: per warp ds[12][32], rho[12][32] (f64) and
+// m[12][32] (i32).
 struct RecordJobStaged : RayJobBase
 {
+    static constexpr bool kCartRegBorders = true, kCartTinySelect = false;       // the record kernel is bound by the load/store pipe
+    static constexpr unsigned RHO_OFF = SKG_RING * 32 * 8, M_OFF = 2 * SKG_RING * 32 * 8;
+    static constexpr size_t bytesPerWarp() { return (size_t)SKG_RING * 32 * (8 + 8 + 4); }
+
     const int64_t* offsets; const int* ell; int ellStride; Medium med;
     skg_segment* seg;
-    double* rDs; double* rRho; int* rM;     // this lane's rings in shared memory
-    KappaRho kr; double kext0; int64_t o, f, ready; double sacc, tacc; bool optical, async;
-    int qo, qf;                             // ring positions of record indices o and f (index mod 4 is preserved)
+    unsigned rb, rbM;           // shared-window addresses of this lane's columns: ds entry q at rb + 256 q, rho at + RHO_OFF; m entry q at rbM + 128 q
+    double* out0;               // record with relative index 0: &seg[first record of the path rounded down to a multiple of 4]
+    KappaRho kr; double kext0; double sacc, tacc; bool optical, async;
+    int o, f, ready;            // relative record indices: parked up to o, written up to f, densities landed up to ready
+    int qo, qf;                 // ring positions (256 x slot) of o and f; relative index mod 4 == record index mod 4 == slot mod 4
 
     __device__ __forceinline__ void bind(char* warpBase)
     {
         const int lane = threadIdx.x & 31;
-        double* d = reinterpret_cast<double*>(warpBase);
-        rDs = d + lane * SKG_RSTRIDE; rRho = d + (32 + lane) * SKG_RSTRIDE;
-        rM = reinterpret_cast<int*>(d + 64 * SKG_RSTRIDE) + lane * SKG_RSTRIDE;
-        o = f = ready = 0; sacc = tacc = 0; optical = async = false; kext0 = 0; qo = qf = 0;
+        const unsigned w = (unsigned)__cvta_generic_to_shared(warpBase);
+        rb = w + 8u * lane; rbM = w + M_OFF + 4u * lane;
+        o = f = ready = 0; sacc = tacc = 0; optical = async = false; kext0 = 0; qo = qf = 0; out0 = nullptr;
     }
-    static constexpr size_t bytesPerWarp() { return (2 * sizeof(double) + sizeof(int)) * 32 * SKG_RSTRIDE + 8; }
 
     __device__ __forceinline__ int begin(int i)
     {
         loadRay(i);
-        o = f = ready = offsets[i]; sacc = 0; tacc = 0;
-        qo = qf = (int)(o & 3);
+        const int64_t first = offsets[i];
+        const int a0 = (int)(first & 3);
+        out0 = reinterpret_cast<double*>(seg + (first - a0));
+        o = f = ready = a0; qo = qf = 256 * a0;
+        sacc = 0; tacc = 0;
         optical = ell != nullptr;
         int l = optical ? ell[(size_t)i * ellStride] : 0;
         kr = KappaRho{med.rho, med.kext + l, med.Ncomp, med.Nlambda};
@@ -132,54 +151,58 @@ struct RecordJobStaged : RayJobBase
         kext0 = async ? __ldg(med.kext + l) : 0.0;
         return 1;
     }
+    __device__ __forceinline__ void advance() { o++; qo = qo + 256 == 256 * SKG_RING ? 0 : qo + 256; }
     __device__ __forceinline__ bool outside(double d)
-    { int q = qo; rM[q] = -1; rDs[q] = d; rRho[q] = 0.0; o++; qo = q + 1 == SKG_RING ? 0 : q + 1; return true; }     // rho(-1,h) = 0 (DustSystem.cpp:918-921)
+    { stsI32(rbM + (qo >> 1), -1); stsF64(rb + qo, d); stsF64(rb + RHO_OFF + qo, 0.0); advance(); return true; }     // rho(-1,h) = 0 (DustSystem.cpp:918-921)
     __device__ __forceinline__ bool segment(int mm, double d)
     {
-        int q = qo; rM[q] = mm; rDs[q] = d;
-        if (async) asyncCopy8(rRho + q, med.rho + mm);
-        o++; qo = q + 1 == SKG_RING ? 0 : q + 1;
+        stsI32(rbM + (qo >> 1), mm); stsF64(rb + qo, d);
+        if (async) asyncCopy8(rb + RHO_OFF + qo, med.rho + mm);
+        advance();
         return true;
     }
-    // KappaRho (DustSystem.cpp:465-491) of ring entry q: one component -> 0 + kext*rho == kext*rho exactly
-    __device__ __forceinline__ double kapparho(int q, int mm) const { return async ? kext0 * rRho[q] : (optical ? kr(mm) : 0.0); }
+    // KappaRho (DustSystem.cpp:465-491) of a ring entry: one component -> 0 + kext*rho == kext*rho exactly
+    __device__ __forceinline__ double kapparho(unsigned q, int mm) const { return async ? kext0 * ldsVF64(rb + RHO_OFF + q) : (optical ? kr(mm) : 0.0); }
 
-    // turns the parked entries [f, upto) into records, in path order
-    __device__ __forceinline__ void emit(int64_t upto)
+    __device__ __forceinline__ void emitOne()
     {
-        while (f < upto)
-        {
-            const int q = qf;
-            if ((f & 3) == 0 && f + 4 <= upto)
-            {
-                const int m0 = rM[q], m1 = rM[q + 1], m2 = rM[q + 2], m3 = rM[q + 3];       // q is a multiple of 4: no wrap inside a group
-                const double d0 = rDs[q], d1 = rDs[q + 1], d2 = rDs[q + 2], d3 = rDs[q + 3];
-                const double k0 = kapparho(q, m0), k1 = kapparho(q + 1, m1), k2 = kapparho(q + 2, m2), k3 = kapparho(q + 3, m3);
-                const double s0 = sacc + d0, s1 = s0 + d1, s2 = s1 + d2, s3 = s2 + d3;
-                const double t0 = k0 * d0, t1 = k1 * d1, t2 = k2 * d2, t3 = k3 * d3;
-                const double a0 = tacc + t0, a1 = a0 + t1, a2 = a1 + t2, a3 = a2 + t3;
-                sacc = s3; tacc = a3;
-                double* out = reinterpret_cast<double*>(seg + f);      // 4 records x 5 words
-                store4(out, cellWord(m0), d0, s0, t0);
-                store4(out + 4, a0, cellWord(m1), d1, s1);
-                store4(out + 8, t1, a1, cellWord(m2), d2);
-                store4(out + 12, s2, t2, a2, cellWord(m3));
-                store4(out + 16, d3, s3, t3, a3);
-                f += 4; qf = q + 4 == SKG_RING ? 0 : q + 4;
-            }
-            else
-            {
-                const int mm = rM[q]; const double d = rDs[q];
-                const double dt = kapparho(q, mm) * d;
-                sacc += d; tacc += dt;
-                double* out = reinterpret_cast<double*>(seg + f);
-                out[0] = cellWord(mm); out[1] = d; out[2] = sacc; out[3] = dt; out[4] = tacc;
-                f++; qf = q + 1 == SKG_RING ? 0 : q + 1;
-            }
-        }
+        const unsigned q = qf;
+        const int mm = ldsVI32(rbM + (q >> 1)); const double d = ldsVF64(rb + q);
+        const double dt = kapparho(q, mm) * d;
+        sacc += d; tacc += dt;
+        double* out = out0 + 5 * (size_t)f;
+        out[0] = cellWord(mm); out[1] = d; out[2] = sacc; out[3] = dt; out[4] = tacc;
+        f++; qf = q + 256 == 256 * SKG_RING ? 0 : q + 256;
+    }
+    // four records at a 4-aligned record index: 160 contiguous, 32-byte aligned bytes as five 256-bit stores
+    __device__ __forceinline__ void emitFour()
+    {
+        const unsigned q = qf;              // a multiple of 4 slots: no wrap inside the group
+        const unsigned qm = rbM + (q >> 1), qd = rb + q;
+        const int m0 = ldsVI32(qm), m1 = ldsVI32(qm + 128), m2 = ldsVI32(qm + 256), m3 = ldsVI32(qm + 384);
+        const double d0 = ldsVF64(qd), d1 = ldsVF64(qd + 256), d2 = ldsVF64(qd + 512), d3 = ldsVF64(qd + 768);
+        const double k0 = kapparho(q, m0), k1 = kapparho(q + 256, m1), k2 = kapparho(q + 512, m2), k3 = kapparho(q + 768, m3);
+        const double s0 = sacc + d0, s1 = s0 + d1, s2 = s1 + d2, s3 = s2 + d3;
+        const double t0 = k0 * d0, t1 = k1 * d1, t2 = k2 * d2, t3 = k3 * d3;
+        const double a0 = tacc + t0, a1 = a0 + t1, a2 = a1 + t2, a3 = a2 + t3;
+        sacc = s3; tacc = a3;
+        double* out = out0 + 5 * (size_t)f;      // 4 records x 5 words
+        store4(out, cellWord(m0), d0, s0, t0);
+        store4(out + 4, a0, cellWord(m1), d1, s1);
+        store4(out + 8, t1, a1, cellWord(m2), d2);
+        store4(out + 12, s2, t2, a2, cellWord(m3));
+        store4(out + 16, d3, s3, t3, a3);
+        f += 4; qf = q + 1024 == 256 * SKG_RING ? 0 : q + 1024;
+    }
+    // turns the parked entries [f, upto) into records, in path order
+    __device__ __forceinline__ void emit(int upto)
+    {
+        while (f < upto && (f & 3)) emitOne();          // unaligned head of a path
+        while (f + 4 <= upto) emitFour();
+        while (f < upto) emitOne();                     // tail (finish only)
     }
     // entries parked before the previous call have their density in the ring by now
-    __device__ __forceinline__ void periodic() { asyncCommit(); asyncWaitAllButLatest(); emit(ready & ~(int64_t)3); ready = o; }
+    __device__ __forceinline__ void periodic() { asyncCommit(); asyncWaitAllButLatest(); emit(ready & ~3); ready = o; }
     __device__ __forceinline__ void finish() { asyncCommit(); asyncWaitAll(); emit(o); ready = o; }
     __device__ __forceinline__ void collective(bool) {}
 };
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ Gr
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
-    size_t skip = (KIND == GRID_CART && cartSmem) ? (size_t)(G.cart.Nx + G.cart.Ny + G.cart.Nz + 3) : 0;
+    size_t skip = (KIND == GRID_CART && cartSmem) ? SKG_CART_SMEM_DOUBLES(G.cart) : 0;
     RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
     job.seg = segments;
     job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarp());
@@ -245,8 +268,17 @@ static LaunchCfg cfgFor(Engine& e, int64_t n)
     SKG_CUDA(cudaMemsetAsync(c.work, 0, sizeof(int), e.stream));
     if (e.gridKind == GRID_CART)
     {
-        size_t need = sizeof(double) * (size_t)(e.cart.Nx + e.cart.Ny + e.cart.Nz + 3);
-        if (need <= 40 * 1024) { c.smem = need; c.cartSmem = true; }
+        // the Cartesian walker reads the borders from shared memory only (CartWalker::step)
+        size_t need = sizeof(double) * SKG_CART_SMEM_DOUBLES(e.cart);
+        if (need > SKG_CART_SMEM_MAX) throw Error("CartesianDustGrid: more than 8189 mesh borders in total are not supported");
+        c.smem = need; c.cartSmem = true;
+        static bool attr = false;
+        if (!attr)
+        {
+            SKG_CUDA(cudaFuncSetAttribute(pathCountKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            SKG_CUDA(cudaFuncSetAttribute(opticalDepthKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            attr = true;
+        }
     }
     return c;
 }

@@ -13,7 +13,12 @@ struct CartGrid
     const double* xv; const double* yv; const double* zv;   // borders, Nx+1 / Ny+1 / Nz+1 values
     int Nx, Ny, Nz;
     double ext[6];      // xmin,xmax,ymin,ymax,zmin,zmax of the BoxDustGrid extent
+    unsigned sx, sy, sz;        // shared-window byte addresses of the staged borders (kernel-side view only)
+    int staged;                 // non-zero when xv/yv/zv have been staged in shared memory (stageCart)
 };
+
+// doubles of shared memory taken by the staged borders (three arrays with one pad element on either side)
+#define SKG_CART_SMEM_DOUBLES(c) ((size_t)((c).Nx + (c).Ny + (c).Nz + 9))
 
 // one entry of a tree node's neighbour list, self-contained: everything the walker needs to continue from that
 // neighbour (its box, cell number and the offsets of ITS six neighbour lists), so that a crossing costs a single

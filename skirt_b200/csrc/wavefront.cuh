@@ -14,7 +14,8 @@
 //   bool segment(int m, double ds)
 //   void finish()                called once per item that returned 1 or 2 from begin()
 //   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
-//   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps 
+//   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps
+//   static constexpr bool kCartRegBorders, kCartTinySelect   variant of the Cartesian walker (geom.cuh)
 #pragma once
 #include "geom.cuh"
 
@@ -89,7 +90,7 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
 template<int KIND, class Job, class Grids>
 __device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Counters* ctr, Job& job, int n, int* workCounter, int refill = 8)
 {
-    if (KIND == GRID_CART) runJobsStep<CartWalker>(cart, ctr, job, n, workCounter, refill);
+    if (KIND == GRID_CART) runJobsStep<CartWalkerT<Job::kCartRegBorders, Job::kCartTinySelect>>(cart, ctr, job, n, workCounter, refill);
     else if (KIND == GRID_TREE) runJobsStep<TreeWalker>(G.tree, ctr, job, n, workCounter, refill);
     else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter, refill);
     else runJobsStep<VoroWalker>(G.voro, ctr, job, n, workCounter, refill);
