@@ -70,6 +70,8 @@
 #include "SEDInstrument.hpp"
 #include "SersicGeometry.hpp"
 #include "SIUnits.hpp"
+#include "StellarUnits.hpp"
+#include "ExtragalacticUnits.hpp"
 #include "SimpleInstrument.hpp"
 #include "SpheroidalGeometryDecorator.hpp"
 #include "SpiralStructureGeometryDecorator.hpp"
@@ -230,7 +232,7 @@ namespace
         std::istringstream all(spec);
         std::string line;
         double packages = 1e6, mwr = 1e4, minscatt = 0, xi = 0.5, ebias = 0.5;
-        int threads = 1, seed = 4357, dustsamples = 100, storeabs = 0, selfabs = 0;
+        int threads = 1, seed = 4357, dustsamples = 100, storeabs = 0, selfabs = 0, unitsys = 0, fluxstyle = 0;
         std::vector<std::string> lines;
         while (std::getline(all, line)) if (!line.empty() && line[0] != '#') lines.push_back(line);
 
@@ -256,6 +258,7 @@ namespace
             else if (key == "emissionbias") in >> ebias;
             else if (key == "dustsamples") in >> dustsamples;
             else if (key == "storeabs") in >> storeabs;
+            else if (key == "units") in >> unitsys >> fluxstyle;      // 0 SI / 1 stellar / 2 extragalactic; 0 neutral / 1 wavelength / 2 frequency
             else if (key == "selfabs") in >> selfabs;
             else if (key == "wavelengths")
             {
@@ -360,7 +363,9 @@ namespace
         S->mc->setPackages(packages); S->mc->setMinWeightReduction(mwr); S->mc->setMinScattEvents(minscatt); S->mc->setScattBias(xi);
         S->ss->setEmissionBias(ebias);
         S->mc->setInstrumentSystem(S->is);
-        S->mc->setUnits(new SIUnits());
+        Units* units = unitsys == 1 ? (Units*)new StellarUnits() : unitsys == 2 ? (Units*)new ExtragalacticUnits() : (Units*)new SIUnits();
+        units->setFluxOutputStyle(fluxstyle == 1 ? Units::Wavelength : fluxstyle == 2 ? Units::Frequency : Units::Neutral);
+        S->mc->setUnits(units);
         S->dd = S->amdd ? (DustDistribution*)S->amdd : (DustDistribution*)S->cdd;
         if (S->pan)
         {

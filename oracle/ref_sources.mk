@@ -1,6 +1,6 @@
 # reference translation units compiled in place (paths resolved through vpath in the Makefile)
 REF_CPP := Array.cpp ProcessManager.cpp \
- Simulation.cpp FatalError.cpp Log.cpp TimeLogger.cpp Units.cpp SIUnits.cpp \
+ Simulation.cpp FatalError.cpp Log.cpp TimeLogger.cpp Units.cpp SIUnits.cpp StellarUnits.cpp ExtragalacticUnits.cpp \
  Parallel.cpp ParallelFactory.cpp ParallelTarget.cpp ProcessAssigner.cpp IdenticalAssigner.cpp \
  SequentialAssigner.cpp StaggeredAssigner.cpp RootAssigner.cpp ProcessCommunicator.cpp PeerToPeerCommunicator.cpp \
  Random.cpp Position.cpp Direction.cpp StokesVector.cpp PhotonPackage.cpp DustGridPath.cpp \

@@ -6,6 +6,7 @@
 #include "engine.h"
 #include "geom.cuh"
 #include "sinks.cuh"
+#include "ring.cuh"
 #include "wavefront.cuh"
 
 namespace skg
@@ -95,21 +96,9 @@ __global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ G
 // array receives ONE 256-bit store (st.global.v4.f64, a whole 32-byte sector; 128-bit for m) at a 4-aligned
 // record index -- so L2 never merges partial sectors and DRAM sees every byte once.  Only the first and last
 // few records of a path (unaligned ends) are written one by one.
-#define SKG_RING 12         // three groups of four: at most 11 entries are parked at any time
 __device__ __forceinline__ void store4(double* p, double a, double b, double c, double d)
 { asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory"); }
 __device__ __forceinline__ double cellWord(int m) { return __longlong_as_double((long long)(unsigned)m); }    // {int m; int reserved = 0}
-// asynchronous 8-byte copy global -> shared (LDGSTS): the density of a crossed cell goes straight into the lane's
-// ring without occupying a register or stalling the walker; it is consumed one period later
-__device__ __forceinline__ void asyncCopy8(unsigned smemDst, const double* src)
-{ asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"(smemDst), "l"(src) : "memory"); }
-__device__ __forceinline__ void asyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void asyncWaitAllButLatest() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
-__device__ __forceinline__ void asyncWaitAll() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void stsF64(unsigned a, double v) { asm volatile("st.shared.f64 [%0], %1;" :: "r"(a), "d"(v) : "memory"); }
-__device__ __forceinline__ void stsI32(unsigned a, int v) { asm volatile("st.shared.s32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ double ldsVF64(unsigned a) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a) : "memory"); return v; }
-__device__ __forceinline__ int ldsVI32(unsigned a) { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(a) : "memory"); return v; }
 
 // The rings are lane-interleaved in shared memory -- entry q of lane l lives at [q][l] -- so that every access of a
 // warp is bank-conflict free whatever ring positions its lanes are at: per warp ds[12][32], rho[12][32] (f64) and

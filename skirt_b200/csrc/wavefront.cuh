@@ -32,7 +32,6 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
     int state = 0;              // 0 idle, 1 walking, 2 walk ended (finish pending)
     bool more = true;
     Walker w; w.alive = false;
-    int sincePeriodic = 0;
     while (true)
     {
         unsigned walking = __ballot_sync(FULL, state == 1);
@@ -76,14 +75,21 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
                 continue;
             }
         }
-        if (state == 1)
+        // SKG_PERIOD crossings between two warp-wide votes: a vote is a convergence point at which every outstanding
+        // load of the warp is waited for, so voting once per crossing would expose the latency of each density gather
+        // (lanes whose path ends inside the batch idle for at most SKG_PERIOD - 1 crossings)
+#pragma unroll
+        for (int u = 0; u < SKG_PERIOD; u++)
         {
-            int m; double ds;
-            const bool seg = w.step(grid, ctr, m, ds);
-            const bool cont = seg ? job.segment(m, ds) : true;
-            if (!cont || !w.alive) state = 2;
+            if (state == 1)
+            {
+                int m; double ds;
+                const bool seg = w.step(grid, ctr, m, ds);
+                const bool cont = seg ? job.segment(m, ds) : true;
+                if (!cont || !w.alive) state = 2;
+            }
         }
-        if (++sincePeriodic == SKG_PERIOD) { job.periodic(); sincePeriodic = 0; }
+        job.periodic();
     }
 }
 

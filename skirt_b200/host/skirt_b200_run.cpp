@@ -1,6 +1,9 @@
 // Command-line driver of the C++ host layer: builds a simulation hierarchy from a small parameter file (one item
 // per line, the same vocabulary as the ski properties it stands for), runs the stellar emission phase on the GPU
-// and writes the raw detector arrays.  ski/XML parsing and FITS output stay in the reference (out of scope).
+// and writes the raw detector arrays plus what Instrument::write() produces in the reference: the calibrated FITS data
+// cubes and SED text files (Output.hpp).  ski/XML parsing stays in the reference (out of scope).
+// With --write-only the shooting is skipped: the raw arrays <prefix>_<name>_frame.f64 / _sed.f64 of an earlier run are
+// read back and only the calibration + output step runs (no GPU needed).
 //
 //   sim oligo|pan ; packages N ; seed S ; minweightreduction f ; minscatt n ; scattbias xi ; emissionbias xi
 //   wavelengths l1 l2 ...          | loggrid min max points
@@ -11,10 +14,12 @@
 //   stellar L1[,L2,...]|bb:T:Lbol expdisk hR hz Rmax zmax | sersic n Reff q
 //   instrument frame|sed|simple name distance inclination azimuth pa [nx fovx ny fovy]
 //   storeabs 0|1 ; device d ; lattice n ; dustemission 0|1 ; selfabs 0|1 ; cycles n (0: until convergence)
+//   units si|stellar|extragalactic neutral|wavelength|frequency
 #include <cstdio>
 #include <cstring>
 #include <iostream>
 #include "SimulationItems.hpp"
+#include "Output.hpp"
 
 using namespace skirt;
 
@@ -49,11 +54,14 @@ static Geometry* makeGeometry(std::istringstream& in)
 
 int main(int argc, char** argv)
 {
-    if (argc < 3) { std::fprintf(stderr, "usage: %s <parameter file> <output prefix>\n", argv[0]); return 2; }
+    bool writeOnly = argc > 1 && std::string(argv[1]) == "--write-only";
+    if (writeOnly) { argv++; argc--; }
+    if (argc < 3) { std::fprintf(stderr, "usage: %s [--write-only] <parameter file> <output prefix>\n", argv[0]); return 2; }
     try
     {
         std::ifstream file(argv[1]);
         if (!file) SKIRT_FATAL(std::string("cannot open ") + argv[1]);
+        std::unique_ptr<UnitSystem> units(new SIUnits());
         MonteCarloSimulation sim;
         auto* ss = new StellarSystem(); auto* ds = new DustSystem(); auto* is = new InstrumentSystem();
         double box[6] = {0, 0, 0, 0, 0, 0};
@@ -77,6 +85,14 @@ int main(int argc, char** argv)
             else if (key == "dustemission") { int v; in >> v; sim.setDustEmission(v != 0); }
             else if (key == "selfabs") { int v; in >> v; sim.setSelfAbsorption(v != 0); }
             else if (key == "cycles") { int v; in >> v; sim.setCycles(v); }
+            else if (key == "units")
+            {
+                std::string sys, style; in >> sys >> style;
+                if (sys == "si") units.reset(new SIUnits()); else if (sys == "stellar") units.reset(new StellarUnits());
+                else if (sys == "extragalactic") units.reset(new ExtragalacticUnits()); else SKIRT_FATAL("unknown unit system " + sys);
+                if (style == "wavelength") units->setFluxOutputStyle(UnitSystem::Wavelength); else if (style == "frequency") units->setFluxOutputStyle(UnitSystem::Frequency);
+                else if (style != "neutral" && !style.empty()) SKIRT_FATAL("Unknown flux output style " + style);
+            }
             else if (key == "wavelengths") { std::vector<double> lv; double v; while (in >> v) lv.push_back(v); auto* g = new OligoWavelengthGrid(); g->setWavelengths(lv); sim.setWavelengthGrid(g); }
             else if (key == "loggrid") { double a, b; int n; in >> a >> b >> n; auto* g = new LogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n); sim.setWavelengthGrid(g); }
             else if (key == "box") { for (double& v : box) in >> v; }
@@ -120,18 +136,39 @@ int main(int argc, char** argv)
             else SKIRT_FATAL("unknown key " + key);
         }
         sim.setStellarSystem(ss); sim.setDustSystem(ds); sim.setInstrumentSystem(is);
+        std::string prefix = argv[2];
+        if (writeOnly)
+        {
+            if (!sim.wavelengthGrid()) SKIRT_FATAL("no wavelength grid");
+            sim.wavelengthGrid()->setup();
+            const int Nl = sim.wavelengthGrid()->Nlambda();
+            auto load = [&](const std::string& name, size_t n)
+            {
+                std::vector<double> v(n); std::ifstream f(prefix + "_" + name + ".f64", std::ios::binary);
+                if (!f.read(reinterpret_cast<char*>(v.data()), sizeof(double) * n)) SKIRT_FATAL("cannot read " + prefix + "_" + name + ".f64");
+                return v;
+            };
+            for (auto& i : sim.instrumentSystem()->instruments())
+            {
+                skg_instrument d = i->descriptor();
+                if (d.kind != SKG_INSTR_SED) i->ftotv = load(i->name + "_frame", (size_t)d.Nxp * d.Nyp * Nl);
+                if (d.kind != SKG_INSTR_FRAME) i->Ftotv = load(i->name + "_sed", Nl);
+                writeInstrument(*i, *sim.wavelengthGrid(), *units, prefix);
+            }
+            return 0;
+        }
         sim.setup();
         skg_mc_stats st = sim.runstellaremission();
         int cycles = 0;
         if (sim.dustemission()) { if (pan) { cycles = sim.rundustselfabsorptionIfEnabled(); sim.rundustemission(); } else SKIRT_FATAL("dust emission needs a panchromatic simulation"); }
         sim.fetchResults();
-        std::string prefix = argv[2];
         auto dump = [&](const std::string& name, const std::vector<double>& v)
         { std::ofstream out(prefix + "_" + name + ".f64", std::ios::binary); out.write(reinterpret_cast<const char*>(v.data()), sizeof(double) * v.size()); };
         for (auto& i : sim.instrumentSystem()->instruments())
         {
             if (!i->ftotv.empty()) dump(i->name + "_frame", i->ftotv);
             if (!i->Ftotv.empty()) dump(i->name + "_sed", i->Ftotv);
+            writeInstrument(*i, *sim.wavelengthGrid(), *units, prefix);        // Instrument::write(): calibration + FITS / SED files
         }
         if (!sim.Labs().empty()) dump("Labs", sim.Labs());
         dump("rho", sim.dustSystem()->rho());

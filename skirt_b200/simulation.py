@@ -574,3 +574,12 @@ class MonteCarloSimulation:
         if self.storeabs:
             out["Labs"] = self.engine.fetch_labs(dest("labs", (self.engine.Ncells, Nl)))
         return out
+
+    def write(self, outdir, prefix="", units=None):
+        """InstrumentSystem::write() (MonteCarloSimulation.cpp:553-557): calibrates the reduced detector arrays and
+        writes the FITS data cubes / SED text files of every instrument (skirt_b200/output.py); rank 0 only, like
+        the reference (DistantInstrument.cpp:134, Image.cpp:298)"""
+        from . import output
+        if self.rank != 0:
+            return {}
+        return output.write_instruments(self, self.results(), outdir, prefix, units)

@@ -217,6 +217,8 @@ def ref_spec(cfg):
     else:
         lg = cfg["loggrid"]; lines.append(f"loggrid {lg[0]!r} {lg[1]!r} {lg[2]}")
     lines += [box_line(cfg["box"]), cfg["grid"], f"dustsamples {cfg.get('dustsamples', 20)}", f"storeabs {cfg.get('storeabs', 0)}"]
+    if "units" in cfg:
+        lines.append(f"units {cfg['units'][0]} {cfg['units'][1]}")
     for s in cfg["sources"]:
         lines.append("stellar " + _geom_words(s))
     for d in cfg.get("dust", []):
