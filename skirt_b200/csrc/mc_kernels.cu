@@ -18,7 +18,6 @@
 #include <cub/device/device_scan.cuh>
 #include "mc_device.cuh"
 #include "wavefront.cuh"
-#include "ring.cuh"
 
 namespace skg
 {
@@ -40,10 +39,6 @@ __device__ __forceinline__ CartGrid stageCartMC(const CartGrid& g, double* smem,
     s.staged = 1;
     return s;
 }
-
-// this warp's ring area in dynamic shared memory: after the staged Cartesian borders (if any)
-__device__ __forceinline__ char* ringBase(double* smem, bool afterCart, const CartGrid& c)
-{ return reinterpret_cast<char*>(smem + (afterCart ? SKG_CART_SMEM_DOUBLES(c) : 0)) + (threadIdx.x >> 5) * RhoRing::bytesPerWarp(); }
 
 // per-kernel statistics: warp-reduced, one atomic per warp and counter
 __device__ __forceinline__ void flushStats(Counters* ctr, unsigned long long nSeg, unsigned long long nPaths, unsigned long long nScatt,
@@ -229,9 +224,9 @@ template<int KIND, bool SINGLE> struct PeelJob
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
     double Lw, tau; KappaRho kr; int ell, grp;
-    // one-component media: a crossing parks (m, ds) in the lane's ring and starts the copy of the cell's density; the
-    // entries are consumed one period later (ring.cuh) -- same summation order: tau += (kext*rho[m])*ds per segment
-    double kext0; RhoRing ring;
+    // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
+    // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
+    double kext0, pendRho, pendDs;
     static constexpr bool single = SINGLE;  // one dust component: compile-time, no branch in the crossing loop
     unsigned long long nSeg = 0, nPaths = 0, nDet = 0;
     __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_) : G(G_), cart(c_), P(P_) {}
@@ -287,7 +282,7 @@ template<int KIND, bool SINGLE> struct PeelJob
         Lw = L; tau = 0;
         dx = g.kx; dy = g.ky; dz = g.kz;
         kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
-        kext0 = single ? __ldg(P.med.kext + ell) : 0.0;
+        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendRho = 0; pendDs = 0;
         if (!P.med.rho) return 2;                                   // Instrument::opticalDepth: 0 without dust
         nPaths++;
         return 1;
@@ -296,14 +291,14 @@ template<int KIND, bool SINGLE> struct PeelJob
     __device__ __forceinline__ bool segment(int m, double ds)
     {
         nSeg++;
-        if (single) ring.park(m, ds, P.med.rho + m);
+        if (single) { tau += (kext0 * pendRho) * pendDs; pendRho = __ldg(P.med.rho + m); pendDs = ds; }
         else tau += kr(m) * ds;
         return true;
     }
     __device__ __forceinline__ void finish()
     {
         const ObsGroup& g = P.groups[grp];
-        if (single) ring.finish([&](int, double ds, double rho) { tau += (kext0 * rho) * ds; });
+        if (single) tau += (kext0 * pendRho) * pendDs;
         const double Lextf = Lw * exp(-tau);
         for (int c = 0; c < g.count; c++)
         {
@@ -318,7 +313,7 @@ template<int KIND, bool SINGLE> struct PeelJob
         }
     }
     __device__ __forceinline__ void collective(bool) {}
-    __device__ __forceinline__ void periodic() { if (single) ring.periodic([&](int, double ds, double rho) { tau += (kext0 * rho) * ds; }); }
+    __device__ __forceinline__ void periodic() {}
 };
 
 template<int KIND, bool SINGLE>
@@ -329,7 +324,6 @@ __global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSet
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
     PeelJob<KIND, SINGLE> job(G, cart, P);
-    job.ring.bind(ringBase(smem, KIND == GRID_CART && cartSmem, G.cart));
     runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, min(28, 2 * P.refill));
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
 }
@@ -346,7 +340,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
     // E += E*expm1(-dtau): one transcendental per segment instead of two (the forms agree to a few ulp over a path)
     KappaRho kr; double L, albedo, tau, E, Lsca; double* labs;
     int slot, ell, nscatt; unsigned rngCtr; bool survive; unsigned long long id; double target;
-    double kext0; RhoRing ring;                     // one-component media: park the crossing, absorb one period later (ring.cuh)
+    double kext0, pendRho, pendDs; int pendM;      // one-component media: gather now, absorb one crossing later
     unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
     __device__ AbsorbJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, int* c2_) : G(G_), cart(c_), P(P_), counts(c2_) {}
 
@@ -402,19 +396,20 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
         double kext0_ = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
         albedo = kext0_ > 0 ? ksca0 / kext0_ : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
         tau = 0; E = 1.0; Lsca = 0;
-        kext0 = kext0_;
+        kext0 = kext0_; pendM = -1; pendRho = 0; pendDs = 0;
         nPaths++;
         return 1;
     }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }   // rho(-1,h) = 0: dtau = 0, nothing absorbed
     // escape + absorption of one segment in a one-component medium (MonteCarloSimulation.cpp:446-470)
-    __device__ __forceinline__ void absorbOne(int m, double ds, double rho)
+    __device__ __forceinline__ void absorbPending()
     {
-        double dtau = (kext0 * rho) * ds;
+        if (pendM < 0) return;
+        double dtau = (kext0 * pendRho) * pendDs;
         if (STORE)
         {
             double x = expm1Small(-dtau);
-            atomicAdd(labs + m, (1.0 - albedo) * (L * E * (-x)));
+            atomicAdd(labs + pendM, (1.0 - albedo) * (L * E * (-x)));
             E += E * x;
             nAbs++;
         }
@@ -424,7 +419,11 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
     {
         nSeg++;
         const int Ncomp = P.med.Ncomp;
-        if (SINGLE) ring.park(m, ds, P.med.rho + m);
+        if (SINGLE)
+        {
+            absorbPending();
+            pendM = m; pendDs = ds; pendRho = __ldg(P.med.rho + m);
+        }
         else
         {
             double ksca = 0.0, kext = 0.0, krr = 0.0;
@@ -451,7 +450,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
     {
         if (!(L > 0) || !P.med.rho) return;
         Packet* q = P.pool;
-        if (SINGLE) ring.finish([&](int m, double ds, double rho) { absorbOne(m, ds, rho); });
+        if (SINGLE) { absorbPending(); pendM = -1; }
         const double taupath = tau;
         if (SINGLE) L = L * albedo * (-expm1(-taupath));
         else L = Lsca;
@@ -490,7 +489,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
             storePacket(P.poolNext + pos, pk);
         }
     }
-    __device__ __forceinline__ void periodic() { if (SINGLE) ring.periodic([&](int m, double ds, double rho) { absorbOne(m, ds, rho); }); }
+    __device__ __forceinline__ void periodic() {}
 };
 
 template<int KIND, bool SINGLE, bool STORE>
@@ -501,7 +500,6 @@ __global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridS
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
     AbsorbJob<KIND, SINGLE, STORE> job(G, cart, P, counts);
-    job.ring.bind(ringBase(smem, KIND == GRID_CART && cartSmem, G.cart));
     runJobs<KIND>(G, cart, ctr, job, nAlive, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, job.nScatt, 0, job.nAbs, 0);
 }
@@ -779,7 +777,6 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
     int nAlive = 0;                          // packets in flight: poolA[0, nAlive), survivors first, then the newly launched
     int* hostCounts = e.mcHostCounts;
     bool propagatePending = false;
-    const size_t smemRing = smem + 4 * RhoRing::bytesPerWarp();      // peel / absorb: staged borders + one ring set per warp
     auto addMs = [&](int stage, cudaEvent_t a, cudaEvent_t b) { float ms = 0; SKG_CUDA(cudaEventElapsedTime(&ms, a, b)); e.stageMs[stage] += ms; };
     while (true)
     {
@@ -799,17 +796,17 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         if (P.Ngroups > 0 && P.phase != SKG_PHASE_DUST_SELFABS)
         {
             const int nb = blocksFor((long long)nAlive * P.Ngroups);
-            if (single) peelStage<KIND, true><<<nb, 128, smemRing, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
-            else peelStage<KIND, false><<<nb, 128, smemRing, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+            if (single) peelStage<KIND, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+            else peelStage<KIND, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
             e.launches++;
         }
         SKG_CUDA(cudaEventRecord(ev[2], e.stream));
         {
             const int nb = blocksFor(nAlive);
-            if (single && store) absorbStage<KIND, true, true><<<nb, 128, smemRing, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
-            else if (single) absorbStage<KIND, true, false><<<nb, 128, smemRing, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
-            else if (store) absorbStage<KIND, false, true><<<nb, 128, smemRing, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
-            else absorbStage<KIND, false, false><<<nb, 128, smemRing, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            if (single && store) absorbStage<KIND, true, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            else if (single) absorbStage<KIND, true, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            else if (store) absorbStage<KIND, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+            else absorbStage<KIND, false, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
             e.launches++;
         }
         SKG_CUDA(cudaEventRecord(ev[3], e.stream));
