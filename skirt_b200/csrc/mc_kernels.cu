@@ -19,6 +19,20 @@
 #include "mc_device.cuh"
 #include "wavefront.cuh"
 
+// resident CTAs per SM the stage kernels are compiled for (register budget 65536 / (128 x blocks)): the crossing loop
+// is a chain of dependent fp64 operations, so warps in flight are what hides its latency -- measured on B200:
+// absorb 205 / 176 / 163 / 187 ms per C2 phase at 3 / 4 / 5 / 6 CTAs, peel 109 / 90 / 102 (spills at 5).  The walkers of the
+// hierarchical / unstructured grids carry more state: 4 CTAs (no spills)
+#ifndef SKG_PEEL_MINBLOCKS
+#define SKG_PEEL_MINBLOCKS 4
+#endif
+#ifndef SKG_ABSORB_MINBLOCKS
+#define SKG_ABSORB_MINBLOCKS 5
+#endif
+#ifndef SKG_PROP_MINBLOCKS
+#define SKG_PROP_MINBLOCKS 5
+#endif
+
 namespace skg
 {
 
@@ -317,7 +331,7 @@ template<int KIND, bool SINGLE> struct PeelJob
 };
 
 template<int KIND, bool SINGLE>
-__global__ void __launch_bounds__(128) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128, SKG_PEEL_MINBLOCKS) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                  int nAlive, int* work)
 {
     extern __shared__ double smem[];
@@ -493,7 +507,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
 };
 
 template<int KIND, bool SINGLE, bool STORE>
-__global__ void __launch_bounds__(128) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS : 4) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                    int nAlive, int* __restrict__ counts, int* work)
 {
     extern __shared__ double smem[];
@@ -567,7 +581,7 @@ template<int KIND, bool SINGLE> struct PropagateJob
 };
 
 template<int KIND, bool SINGLE>
-__global__ void __launch_bounds__(128) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PROP_MINBLOCKS : 4) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                       int nSurv, int* work)
 {
     extern __shared__ double smem[];
