@@ -114,6 +114,7 @@ __device__ __forceinline__ double ldsF64(unsigned addr)
 // essentially never take.
 template<bool REGB, bool TINYSEL> struct CartWalkerT
 {
+    static constexpr int kStepUnroll = 4;       // crossings of a batch unrolled in the scheduler (wavefront.cuh): the step is ~100 instructions
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;       // 1/k per axis (see divInvariant)
     double xE, yE, zE;          // the exit borders themselves: only the axis that was crossed is re-read
@@ -336,6 +337,7 @@ __device__ __forceinline__ double nextAfterAlong(double v, double k)
 // TreeDustGrid::path (TreeDustGrid.cpp:390-662) one crossing at a time
 struct TreeWalker
 {
+    static constexpr int kStepUnroll = 1;       // large step body: a plain loop (unrolling it costs more in instruction fetch than it gains)
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
     double bx[6];               // box of the current node, carried over from the neighbour test that selected it
@@ -348,7 +350,28 @@ struct TreeWalker
     {
         if (withBox) { const double* b = g.box + 6 * (size_t)node; for (int c = 0; c < 6; c++) bx[c] = __ldg(b + c); }
         cellv = __ldg(g.cell + node);
-        if (g.search == 1) { const int* s = g.nbrStart + 6 * (size_t)node; for (int w = 0; w < 7; w++) nb[w] = __ldg(s + w); }
+        if (g.search == 1)
+        {
+            const int* s = g.nbrStart + 6 * (size_t)node; for (int w = 0; w < 7; w++) nb[w] = __ldg(s + w);
+        }
+    }
+    // one expanded neighbour record: 96 bytes as three 256-bit reads
+    static __device__ __forceinline__ void loadRec(const TreeNbrRec* rec, double (&w)[12])
+    {
+        const double* rp = reinterpret_cast<const double*>(rec);
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[4 * u]), "=d"(w[4 * u + 1]), "=d"(w[4 * u + 2]), "=d"(w[4 * u + 3]) : "l"(rp + 4 * u));
+    }
+    // continue from the neighbour whose record has been read
+    __device__ __forceinline__ void adopt(const double (&w)[12])
+    {
+        for (int c = 0; c < 6; c++) bx[c] = w[c];
+        const long long w6 = __double_as_longlong(w[6]), w7 = __double_as_longlong(w[7]), w8 = __double_as_longlong(w[8]),
+                        w9 = __double_as_longlong(w[9]), w10 = __double_as_longlong(w[10]);
+        node = (int)(w6 & 0xffffffffll); cellv = (int)(w6 >> 32);
+        nb[0] = (int)(w7 & 0xffffffffll); nb[1] = (int)(w7 >> 32); nb[2] = (int)(w8 & 0xffffffffll); nb[3] = (int)(w8 >> 32);
+        nb[4] = (int)(w9 & 0xffffffffll); nb[5] = (int)(w9 >> 32); nb[6] = (int)(w10 & 0xffffffffll);
     }
 
     __device__ __forceinline__ bool start(const TreeGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
@@ -397,26 +420,14 @@ struct TreeWalker
                 node = -1;
                 if (g.nbrRec)
                 {
-                    // expanded records: box, cell and the neighbour offsets of the candidate arrive in one 96-byte read
-                    for (int q = beg; q < end; q++)
+                    // expanded records: box, cell and the neighbour offsets of the candidate arrive in one 96-byte read.
+                    int q = beg;
+                    for (; q < end; q++)
                     {
-                        const double* rp = reinterpret_cast<const double*>(g.nbrRec + q);
-                        double w[12];
-#pragma unroll
-                        for (int u = 0; u < 3; u++)
-                            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[4 * u]), "=d"(w[4 * u + 1]), "=d"(w[4 * u + 2]), "=d"(w[4 * u + 3]) : "l"(rp + 4 * u));
-                        if (x >= w[0] && x <= w[3] && y >= w[1] && y <= w[4] && z >= w[2] && z <= w[5])
-                        {
-                            for (int c = 0; c < 6; c++) bx[c] = w[c];
-                            const long long w6 = __double_as_longlong(w[6]), w7 = __double_as_longlong(w[7]), w8 = __double_as_longlong(w[8]),
-                                            w9 = __double_as_longlong(w[9]), w10 = __double_as_longlong(w[10]);
-                            node = (int)(w6 & 0xffffffffll); cellv = (int)(w6 >> 32);
-                            nb[0] = (int)(w7 & 0xffffffffll); nb[1] = (int)(w7 >> 32); nb[2] = (int)(w8 & 0xffffffffll); nb[3] = (int)(w8 >> 32);
-                            nb[4] = (int)(w9 & 0xffffffffll); nb[5] = (int)(w9 >> 32); nb[6] = (int)(w10 & 0xffffffffll);
-                            haveAll = true;
-                            break;
-                        }
+                        double w[12]; loadRec(g.nbrRec + q, w);
+                        if (x >= w[0] && x <= w[3] && y >= w[1] && y <= w[4] && z >= w[2] && z <= w[5]) { adopt(w); haveAll = true; break; }
                     }
+                    if (!haveAll) node = -1;
                 }
                 else for (int q = beg; q < end; q++)
                 {
@@ -561,6 +572,7 @@ __device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, doub
 // AdaptiveMesh::path (AdaptiveMesh.cpp:297-367) one crossing at a time
 struct AMeshWalker
 {
+    static constexpr int kStepUnroll = 1;
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
     double bx[6];               // box of the current node (carried over from the neighbour test that selected it)
@@ -762,6 +774,7 @@ __device__ __forceinline__ int voroCellIndex(const VoroGrid& g, double x, double
 // VoronoiMesh::path (VoronoiMesh.cpp:749-844) one crossing at a time
 struct VoroWalker
 {
+    static constexpr int kStepUnroll = 1;
     double x, y, z, kx, ky, kz;
     int mr;
     int guard;

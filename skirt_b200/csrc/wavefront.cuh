@@ -16,6 +16,7 @@
 //   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
 //   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps
 //   static constexpr bool kCartRegBorders, kCartTinySelect   variant of the Cartesian walker (geom.cuh)
+//   static constexpr int kBatches           batches of SKG_PERIOD crossings between two votes / periodic() calls
 #pragma once
 #include "geom.cuh"
 
@@ -27,6 +28,7 @@ namespace skg
 template<class Walker, class GridT, class Job>
 __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Job& job, int n, int* workCounter, int refill)
 {
+    constexpr int kStepUnroll = Walker::kStepUnroll;
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     int state = 0;              // 0 idle, 1 walking, 2 walk ended (finish pending)
@@ -75,18 +77,21 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
                 continue;
             }
         }
-        // SKG_PERIOD crossings between two warp-wide votes: a vote is a convergence point at which every outstanding
+        // kBatches x SKG_PERIOD crossings between two warp-wide votes: a vote is a convergence point at which every outstanding
         // load of the warp is waited for, so voting once per crossing would expose the latency of each density gather
         // (lanes whose path ends inside the batch idle for at most SKG_PERIOD - 1 crossings)
-#pragma unroll
-        for (int u = 0; u < SKG_PERIOD; u++)
+        for (int batch = 0; batch < Job::kBatches; batch++)
         {
-            if (state == 1)
+#pragma unroll kStepUnroll
+            for (int u = 0; u < SKG_PERIOD; u++)
             {
-                int m; double ds;
-                const bool seg = w.step(grid, ctr, m, ds);
-                const bool cont = seg ? job.segment(m, ds) : true;
-                if (!cont || !w.alive) state = 2;
+                if (state == 1)
+                {
+                    int m; double ds;
+                    const bool seg = w.step(grid, ctr, m, ds);
+                    const bool cont = seg ? job.segment(m, ds) : true;
+                    if (!cont || !w.alive) state = 2;
+                }
             }
         }
         job.periodic();
