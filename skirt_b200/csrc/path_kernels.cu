@@ -77,7 +77,7 @@ struct TauJob : RayJobBase
 };
 
 template<int KIND>
-__global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ GridSet G, Counters* ctr, bool cartSmem, int n,
+__global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ GridSet G, Counters* ctr, bool cartSmem, int refill, int n,
                                                        const double* __restrict__ r, const double* __restrict__ k,
                                                        int* __restrict__ counts, int* work)
 {
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(128) pathCountKernel(const __grid_constant__ G
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     CountJob job; job.r = r; job.k = k; job.counts = counts;
-    runJobs<KIND>(G, cart, ctr, job, n, work);
+    runJobs<KIND>(G, cart, ctr, job, n, work, refill);
 }
 
 // second pass: Segment{m, ds, s, dtau, tau} records = DustGridPath::addSegment (DustGridPath.cpp:46-53, running
@@ -198,7 +198,7 @@ struct RecordJobStaged : RayJobBase
 };
 
 template<int KIND>
-__global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem, int refill,
                                                       int n, const double* __restrict__ r, const double* __restrict__ k,
                                                       const int* __restrict__ ell, int ellStride, const int64_t* __restrict__ offsets,
                                                       skg_segment* __restrict__ segments, int* work)
@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ Gr
     RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
     job.seg = segments;
     job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarp());
-    runJobs<KIND>(G, cart, ctr, job, n, work);
+    runJobs<KIND>(G, cart, ctr, job, n, work, refill);
 }
 
 template<int KIND>
-__global__ void __launch_bounds__(128) opticalDepthKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128) opticalDepthKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem, int refill,
                                                           int n, const double* __restrict__ r, const double* __restrict__ k,
                                                           const int* __restrict__ ell, int ellStride,
                                                           const double* __restrict__ dist, double* __restrict__ tau, int* work)
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128) opticalDepthKernel(const __grid_constant_
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     TauJob job; job.r = r; job.k = k; job.ell = ell; job.ellStride = ellStride; job.med = med; job.dist = dist; job.out = tau;
-    runJobs<KIND>(G, cart, ctr, job, n, work);
+    runJobs<KIND>(G, cart, ctr, job, n, work, refill);
 }
 
 template<int KIND>
@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(128) whichCellKernel(const __grid_constant__ G
 // ---------------------------------------------------------------------------------------------------
 static GridSet gridSet(const Engine& e) { GridSet G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro; return G; }
 
-struct LaunchCfg { int blocks; size_t smem; bool cartSmem; int* work; };
+struct LaunchCfg { int blocks; size_t smem; bool cartSmem; int* work; int refill; };
 static LaunchCfg cfgFor(Engine& e, int64_t n)
 {
     LaunchCfg c;
@@ -253,6 +253,9 @@ static LaunchCfg cfgFor(Engine& e, int64_t n)
     int64_t cap = (int64_t)e.smCount * 16;
     c.blocks = (int)std::max<int64_t>(1, std::min(want, cap));
     c.smem = 0; c.cartSmem = false;
+    // idle lanes of a warp at which it draws new rays (runJobs): entry + point location are cheap on the Cartesian grid,
+    // a chain of dependent reads on the hierarchical ones
+    c.refill = 8; if (const char* v = getenv("SKG_PATH_REFILL")) c.refill = std::max(1, std::min(32, atoi(v)));
     if (n > 2147483647LL) throw Error("at most 2^31-1 rays per call");
     e.scratchWork.ensure(sizeof(int)); c.work = e.scratchWork.as<int>();
     SKG_CUDA(cudaMemsetAsync(c.work, 0, sizeof(int), e.stream));
@@ -285,7 +288,7 @@ void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k,
 {
     if (n <= 0) return;
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
-    SKG_DISPATCH(e, (pathCountKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.ctr(), c.cartSmem, (int)n, d_r, d_k, d_counts, c.work)));
+    SKG_DISPATCH(e, (pathCountKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_counts, c.work)));
     e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
@@ -307,7 +310,7 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
         if (const char* cv = getenv("SKG_FILL_CARVEOUT")) SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_CART>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
         attr = true;
     }
-    SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, (int)n, d_r, d_k, d_ell, ellStride,
+    SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride,
                                                                                 d_offsets, d_segments, c.work)));
     e.launches++; SKG_CUDA(cudaGetLastError());
 }
@@ -318,7 +321,7 @@ void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d
     if (n <= 0) return;
     if (!e.med.rho) throw Error("skg_opticaldepth needs skg_medium first");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
-    SKG_DISPATCH(e, (opticalDepthKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, (int)n, d_r, d_k, d_ell, ellStride,
+    SKG_DISPATCH(e, (opticalDepthKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride,
                                                                                     d_dist, d_tau, c.work)));
     e.launches++; SKG_CUDA(cudaGetLastError());
 }
