@@ -143,15 +143,22 @@ int skg_sample_density(skg_engine* e, int Ncomp, const skg_source* geometries, c
 int skg_sample_launch(skg_engine* e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
 
 /* ---- instruments: DistantInstrument / SingleFrameInstrument / Frame-, SED-, SimpleInstrument ---------- */
-enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3 };
+enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3, SKG_INSTR_FULL = 4 };
+/* FullInstrument (FullInstrument.cpp:107-172, unpolarised part): one data cube + SED per channel, in this order */
+enum { SKG_CHAN_TRANSPARENT = 0, SKG_CHAN_STELLAR_DIRECT = 1, SKG_CHAN_STELLAR_SCATTERED = 2, SKG_CHAN_DUST_DIRECT = 3,
+       SKG_CHAN_DUST_SCATTERED = 4, SKG_CHAN_SCATTERING_LEVEL1 = 5 /* + (level - 1), level = 1..scatteringLevels */ };
 typedef struct skg_instrument
 {
     int kind;
     double distance, inclination, azimuth, positionAngle;       /* DistantInstrument.hpp */
     int Nxp, Nyp;                                                /* SingleFrameInstrument */
     double fovxp, fovyp, xpc, ypc;
+    int scatteringLevels;                                        /* FullInstrument::setScatteringLevels (0 for the other kinds) */
 } skg_instrument;
 int skg_instruments(skg_engine* e, int n, const skg_instrument* instr);
+/* detector arrays of one FullInstrument channel (replace FullInstrument's private _f*v / _F*v arrays); add as for skg_fetch_frame */
+int skg_fetch_frame_channel(skg_engine* e, int instrument, int channel, double* frame, int add);
+int skg_fetch_sed_channel(skg_engine* e, int instrument, int channel, double* sed, int add);
 
 /* ---- photon shooting: MonteCarloSimulation::runstellaremission (MonteCarloSimulation.cpp:251-301) ------ */
 typedef struct skg_mc_params

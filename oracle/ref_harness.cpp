@@ -73,6 +73,7 @@
 #include "StellarUnits.hpp"
 #include "ExtragalacticUnits.hpp"
 #include "SimpleInstrument.hpp"
+#include "FullInstrument.hpp"
 #include "SpheroidalGeometryDecorator.hpp"
 #include "SpiralStructureGeometryDecorator.hpp"
 #include "StellarSystem.hpp"
@@ -347,7 +348,9 @@ namespace
                 else
                 {
                     int nx, ny; double fx, fy; in >> nx >> fx >> ny >> fy;
-                    SingleFrameInstrument* fi = (kind == "frame") ? (SingleFrameInstrument*)new FrameInstrument() : (SingleFrameInstrument*)new SimpleInstrument();
+                    SingleFrameInstrument* fi = (kind == "frame") ? (SingleFrameInstrument*)new FrameInstrument()
+                                              : (kind == "full") ? (SingleFrameInstrument*)new FullInstrument() : (SingleFrameInstrument*)new SimpleInstrument();
+                    if (kind == "full") { int nscatt; in >> nscatt; ((FullInstrument*)fi)->setScatteringLevels(nscatt); }
                     fi->setPixelsX(nx); fi->setFieldOfViewX(fx); fi->setPixelsY(ny); fi->setFieldOfViewY(fy); fi->setCenterX(0); fi->setCenterY(0);
                     di = fi;
                 }
@@ -680,6 +683,12 @@ int skr_reset(void* h, int seed)
             if (FrameInstrument* f = dynamic_cast<FrameInstrument*>(ins)) f->_ftotv = 0.0;
             if (SEDInstrument* f = dynamic_cast<SEDInstrument*>(ins)) f->_Ftotv = 0.0;
             if (SimpleInstrument* f = dynamic_cast<SimpleInstrument*>(ins)) { f->_ftotv = 0.0; f->_Ftotv = 0.0; }
+            if (FullInstrument* f = dynamic_cast<FullInstrument*>(ins))
+            {
+                for (Array* a : {&f->_ftrav, &f->_Ftrav, &f->_fstrdirv, &f->_Fstrdirv, &f->_fstrscav, &f->_Fstrscav, &f->_fdusdirv, &f->_Fdusdirv,
+                                 &f->_fdusscav, &f->_Fdusscav}) if (a->size()) *a = 0.0;
+                for (int n = 0; n < f->_Nscatt; n++) { f->_fstrscavv[n] = 0.0; f->_Fstrscavv[n] = 0.0; }
+            }
         }
         if (S->ds)
         {
@@ -721,6 +730,25 @@ void skr_get_instrument(void* h, int i, double* frame, double* sed)
     if (SimpleInstrument* f = dynamic_cast<SimpleInstrument*>(ins)) { fa = &f->_ftotv; sa = &f->_Ftotv; }
     if (fa && frame) for (size_t j = 0; j < fa->size(); j++) frame[j] = (*fa)[j];
     if (sa && sed) for (size_t j = 0; j < sa->size(); j++) sed[j] = (*sa)[j];
+}
+// raw arrays of one FullInstrument channel (0 transparent, 1 direct, 2 scattered, 3 dust direct, 4 dust scattered, 5+n level n+1)
+int skr_get_full_channel(void* h, int i, int c, double* frame, double* sed)
+{
+    FullInstrument* f = dynamic_cast<FullInstrument*>(((Sim*)h)->is->instruments()[i]);
+    if (!f) return 1;
+    const Array* fa = 0; const Array* sa = 0;
+    switch (c)
+    {
+    case 0: fa = &f->_ftrav; sa = &f->_Ftrav; break;
+    case 1: fa = &f->_fstrdirv; sa = &f->_Fstrdirv; break;
+    case 2: fa = &f->_fstrscav; sa = &f->_Fstrscav; break;
+    case 3: fa = &f->_fdusdirv; sa = &f->_Fdusdirv; break;
+    case 4: fa = &f->_fdusscav; sa = &f->_Fdusscav; break;
+    default: if (c - 5 >= f->_Nscatt) return 1; fa = &f->_fstrscavv[c - 5]; sa = &f->_Fstrscavv[c - 5];
+    }
+    if (frame) for (size_t j = 0; j < fa->size(); j++) frame[j] = (*fa)[j];
+    if (sed) for (size_t j = 0; j < sa->size(); j++) sed[j] = (*sa)[j];
+    return 0;
 }
 // instrument geometry as the reference derived it (DistantInstrument.cpp:27-50, SingleFrameInstrument.cpp)
 void skr_get_instrument_geometry(void* h, int i, double* out /*[16]*/)

@@ -53,7 +53,7 @@ public:
             if (item) { if (setup) item->setup(); return item; }
             ancestor = ancestor->parent();
         }
-        throw shimNotFound(typeid(T).name());
+        shimNotFound(typeid(T).name());
     }
     template<class T> T* interface()
     {
@@ -66,9 +66,11 @@ protected:
     enum State { Created = 0, SetupInProgress, SetupDone };
     State _state;
 private:
-    static std::runtime_error shimNotFound(const char* name);
+    // throws FatalError like the reference's find<T>() (SimulationItem.hpp:120-127): callers such as
+    // FullInstrument::setupSelfBefore (FullInstrument.cpp:29-49) catch exactly that type
+    [[noreturn]] static void shimNotFound(const char* name);
 };
-#include <stdexcept>
-inline std::runtime_error SimulationItem::shimNotFound(const char* name)
-{ return std::runtime_error(std::string("No simulation item of type ") + name + " found in hierarchy"); }
+#include "FatalError.hpp"
+inline void SimulationItem::shimNotFound(const char* name)
+{ throw FATALERROR(QString("No simulation item of type ") + name + " found in hierarchy"); }
 #endif

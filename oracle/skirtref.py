@@ -259,6 +259,13 @@ class RefSim:
             out.append(dict(frame=frame, sed=sed, geometry=geo))
         return out
 
+    def full_channel(self, i, c, nframe):
+        """raw (uncalibrated) data cube and SED of one FullInstrument channel"""
+        frame = np.zeros(nframe); sed = np.zeros(self.Nlambda)
+        if lib().skr_get_full_channel(self.h, int(i), int(c), frame.ctypes.data_as(C.c_void_p), sed.ctypes.data_as(C.c_void_p)):
+            raise RefError("not a FullInstrument channel")
+        return frame, sed
+
     def labs(self):
         a = np.zeros((self.Ncells, self.Nlambda))
         self._chk(lib().skr_get_labs(self.h, a.ctypes.data_as(C.c_void_p)))

@@ -13,7 +13,9 @@ _lib = None
 
 SKG_HOST, SKG_DEVICE = 0, 1
 GEOM_EXPDISK, GEOM_SERSIC = 1, 2
-INSTR_FRAME, INSTR_SED, INSTR_SIMPLE = 1, 2, 3
+INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL = 1, 2, 3, 4
+# FullInstrument channels (include/skirtgpu.h SKG_CHAN_*): scattering level n is channel CHAN_LEVEL1 + n - 1
+CHAN_TRANSPARENT, CHAN_STELLAR_DIRECT, CHAN_STELLAR_SCATTERED, CHAN_DUST_DIRECT, CHAN_DUST_SCATTERED, CHAN_LEVEL1 = 0, 1, 2, 3, 4, 5
 PHASE_STELLAR, PHASE_DUST_SELFABS, PHASE_DUST_EMISSION = 0, 1, 2
 # skg_segment == DustGridPath::Segment (DustGridPath.hpp:161-167)
 SEGMENT = np.dtype([("m", np.int32), ("reserved", np.int32), ("ds", np.float64), ("s", np.float64), ("dtau", np.float64), ("tau", np.float64)])
@@ -35,7 +37,8 @@ class SkgInstrument(C.Structure):
     _fields_ = [("kind", C.c_int), ("distance", C.c_double), ("inclination", C.c_double),
                 ("azimuth", C.c_double), ("positionAngle", C.c_double),
                 ("Nxp", C.c_int), ("Nyp", C.c_int),
-                ("fovxp", C.c_double), ("fovyp", C.c_double), ("xpc", C.c_double), ("ypc", C.c_double)]
+                ("fovxp", C.c_double), ("fovyp", C.c_double), ("xpc", C.c_double), ("ypc", C.c_double),
+                ("scatteringLevels", C.c_int)]
 
 
 class SkgMcParams(C.Structure):
@@ -288,6 +291,7 @@ class Engine:
             a.Nxp = int(d.get("Nxp", 0)); a.Nyp = int(d.get("Nyp", 0))
             a.fovxp = float(d.get("fovxp", 0.0)); a.fovyp = float(d.get("fovyp", 0.0))
             a.xpc = float(d.get("xpc", 0.0)); a.ypc = float(d.get("ypc", 0.0))
+            a.scatteringLevels = int(d.get("scatteringLevels", 0))
         self._instr = list(instr)
         self._chk(self._lib.skg_instruments(self.h, len(instr), arr))
 
@@ -389,6 +393,18 @@ class Engine:
     def fetch_sed(self, i, out=None):
         a = np.zeros(self.Nlambda) if out is None else out
         self._chk(self._lib.skg_fetch_sed(self.h, i, _vp(a), 0))
+        return a
+
+    def fetch_frame_channel(self, i, channel, out=None):
+        """data cube of one FullInstrument channel (CHAN_*)"""
+        d = self._instr[i]
+        a = np.zeros(int(d["Nxp"]) * int(d["Nyp"]) * self.Nlambda) if out is None else out
+        self._chk(self._lib.skg_fetch_frame_channel(self.h, i, int(channel), _vp(a), 0))
+        return a
+
+    def fetch_sed_channel(self, i, channel, out=None):
+        a = np.zeros(self.Nlambda) if out is None else out
+        self._chk(self._lib.skg_fetch_sed_channel(self.h, i, int(channel), _vp(a), 0))
         return a
 
     def fetch_labs(self, out=None):

@@ -74,6 +74,8 @@ int skg_allreduce_results(skg_engine* eh)
         {
             if (d.frame) SKG_NCCL(nccl.allReduce(d.frame, d.frame, (size_t)d.Nxp * d.Nyp * e.med.Nlambda, ncclDouble, ncclSum, comm, e.stream));
             if (d.sed) SKG_NCCL(nccl.allReduce(d.sed, d.sed, (size_t)e.med.Nlambda, ncclDouble, ncclSum, comm, e.stream));
+            if (d.chanFrame) SKG_NCCL(nccl.allReduce(d.chanFrame, d.chanFrame, (size_t)d.Nxp * d.Nyp * e.med.Nlambda * d.Nchan, ncclDouble, ncclSum, comm, e.stream));
+            if (d.chanSed) SKG_NCCL(nccl.allReduce(d.chanSed, d.chanSed, (size_t)e.med.Nlambda * d.Nchan, ncclDouble, ncclSum, comm, e.stream));
         }
         SKG_NCCL(nccl.groupEnd());
         e.sync();

@@ -444,6 +444,25 @@ int skg_fetch_sed(skg_engine* eh, int i, double* sed, int add)
         fetchArray(e, e.instr[i].sed, e.med.Nlambda, sed, add);
     });
 }
+int skg_fetch_frame_channel(skg_engine* eh, int i, int c, double* frame, int add)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].chanFrame) throw Error("instrument has no channels");
+        if (c < 0 || c >= e.instr[i].Nchan) throw Error("channel out of range");
+        const int64_t n = (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.med.Nlambda;
+        fetchArray(e, e.instr[i].chanFrame + c * n, n, frame, add);
+    });
+}
+int skg_fetch_sed_channel(skg_engine* eh, int i, int c, double* sed, int add)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].chanSed) throw Error("instrument has no channels");
+        if (c < 0 || c >= e.instr[i].Nchan) throw Error("channel out of range");
+        fetchArray(e, e.instr[i].chanSed + (int64_t)c * e.med.Nlambda, e.med.Nlambda, sed, add);
+    });
+}
 int skg_fetch_labs(skg_engine* eh, double* labs, int add)
 {
     return guarded([&]{
@@ -461,8 +480,15 @@ int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr,
         if (which == -1) { *d_ptr = e.labsDust.as<double>(); *count = e.labsDust.p ? e.labsCount : 0; return; }
         int i = which - 1;
         if (i < 0 || i >= (int)e.instr.size()) throw Error("instrument index out of range");
-        if (part == 0) { *d_ptr = e.instr[i].frame; *count = e.instr[i].frame ? (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.med.Nlambda : 0; }
-        else { *d_ptr = e.instr[i].sed; *count = e.instr[i].sed ? e.med.Nlambda : 0; }
+        const InstrDev& d = e.instr[i];
+        if (d.kind == SKG_INSTR_FULL)
+        {
+            if (part == 0) { *d_ptr = d.chanFrame; *count = (int64_t)d.Nxp * d.Nyp * e.med.Nlambda * d.Nchan; }
+            else { *d_ptr = d.chanSed; *count = (int64_t)e.med.Nlambda * d.Nchan; }
+            return;
+        }
+        if (part == 0) { *d_ptr = d.frame; *count = d.frame ? (int64_t)d.Nxp * d.Nyp * e.med.Nlambda : 0; }
+        else { *d_ptr = d.sed; *count = d.sed ? e.med.Nlambda : 0; }
     });
 }
 

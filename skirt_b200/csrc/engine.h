@@ -50,6 +50,8 @@ struct InstrDev
     double kobsx, kobsy, kobsz;
     int Nxp, Nyp; double xpmin, ypmin, xpsiz, ypsiz;
     double* frame; double* sed;     // device accumulators (frame: Nxp*Nyp*Nlambda, sed: Nlambda)
+    // FullInstrument: Nchan = 5 + Nscatt channels, channel-major: chanFrame[(c*Nlambda + ell)*Nxp*Nyp + l], chanSed[c*Nlambda + ell]
+    int Nchan, Nscatt; double* chanFrame; double* chanSed;
 };
 
 struct Engine

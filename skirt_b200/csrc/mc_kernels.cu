@@ -234,6 +234,29 @@ __device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, doub
     return i + I.Nxp * j;
 }
 
+// FullInstrument::detect (FullInstrument.cpp:107-172, unpolarised part): the flux goes to the channel of its origin --
+// stellar / dust emission, direct / scattered -- plus the transparent channel (unextincted direct stellar light) and
+// the channel of its scattering level.  Kept out of line: it runs once per peel-off ray, outside the crossing loop.
+static __device__ __noinline__ int detectFull(const InstrDev& I, int Nlambda, double x, double y, double z, int ell,
+                                              double L, double Lextf, int nscatt, bool stellar)
+{
+    const int l = pixelOnDetector(I, x, y, z);
+    const size_t Nf = (size_t)I.Nxp * I.Nyp;
+    int n = 0;
+    auto add = [&](int c, double v)
+    {
+        atomicAdd(I.chanSed + (size_t)c * Nlambda + ell, v); n++;
+        if (l >= 0) { atomicAdd(I.chanFrame + ((size_t)c * Nlambda + ell) * Nf + l, v); n++; }
+    };
+    if (stellar)
+    {
+        if (nscatt == 0) { add(SKG_CHAN_TRANSPARENT, L); add(SKG_CHAN_STELLAR_DIRECT, Lextf); }
+        else { add(SKG_CHAN_STELLAR_SCATTERED, Lextf); if (nscatt <= I.Nscatt) add(SKG_CHAN_SCATTERING_LEVEL1 + nscatt - 1, Lextf); }
+    }
+    else add(nscatt == 0 ? SKG_CHAN_DUST_DIRECT : SKG_CHAN_DUST_SCATTERED, Lextf);
+    return n;
+}
+
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
 template<int KIND, bool SINGLE> struct PeelJob
 {
@@ -241,6 +264,7 @@ template<int KIND, bool SINGLE> struct PeelJob
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
     double Lw, tau; KappaRho kr; int ell, grp;
+    int ns;                                 // scattering count of the peel-off packet (0: emission, else previous scatterings + 1)
     // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
     // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
     double kext0, pendRho, pendDs;
@@ -296,7 +320,7 @@ template<int KIND, bool SINGLE> struct PeelJob
             }
             L = L * w;                                              // launchScatteringPeelOff, PhotonPackage.cpp:51-62
         }
-        Lw = L; tau = 0;
+        Lw = L; tau = 0; ns = pk.fresh ? 0 : pk.nscatt + 1;       // launchEmissionPeelOff / launchScatteringPeelOff, PhotonPackage.cpp:34-62
         dx = g.kx; dy = g.ky; dz = g.kz;
         kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
         kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendRho = 0; pendDs = 0;
@@ -320,6 +344,7 @@ template<int KIND, bool SINGLE> struct PeelJob
         for (int c = 0; c < g.count; c++)
         {
             const InstrDev& I = P.instr[g.first + c];
+            if (I.kind == SKG_INSTR_FULL) { nDet += detectFull(I, P.med.Nlambda, rx, ry, rz, ell, Lw, Lextf, ns, P.phase == SKG_PHASE_STELLAR); continue; }
             // SEDInstrument::detect SEDInstrument.cpp:32-42, FrameInstrument::detect FrameInstrument.cpp:32-47, SimpleInstrument.cpp:33-49
             if (I.kind != SKG_INSTR_FRAME) { warpAggregatedAdd(I.sed + ell, Lextf); nDet++; }
             if (I.kind != SKG_INSTR_SED)
@@ -691,7 +716,8 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
         const skg_instrument& s = instr[i];
         InstrDev d{};
         d.kind = s.kind;
-        if (s.kind < SKG_INSTR_FRAME || s.kind > SKG_INSTR_SIMPLE) throw Error("unsupported instrument kind");
+        if (s.kind < SKG_INSTR_FRAME || s.kind > SKG_INSTR_FULL) throw Error("unsupported instrument kind");
+        if (s.kind == SKG_INSTR_FULL && (s.scatteringLevels < 0 || s.scatteringLevels > 1000)) throw Error("invalid number of scattering levels");
         if (s.distance <= 0) throw Error("Distance was not set");                    // DistantInstrument.cpp:32
         // DistantInstrument::setupSelfBefore, DistantInstrument.cpp:27-50
         d.costheta = std::cos(s.inclination); d.sintheta = std::sin(s.inclination);
@@ -712,16 +738,18 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             d.Nxp = s.Nxp; d.Nyp = s.Nyp;
             d.xpmin = s.xpc - 0.5 * s.fovxp; d.xpsiz = s.fovxp / s.Nxp;
             d.ypmin = s.ypc - 0.5 * s.fovyp; d.ypsiz = s.fovyp / s.Nyp;
+            if (s.kind == SKG_INSTR_FULL) { d.Nscatt = s.scatteringLevels; d.Nchan = 5 + d.Nscatt; }
             DevBuf* f = new DevBuf(); e.instrBufs.push_back(f);
-            size_t bytes = sizeof(double) * (size_t)s.Nxp * s.Nyp * e.med.Nlambda;
+            size_t bytes = sizeof(double) * (size_t)s.Nxp * s.Nyp * e.med.Nlambda * (s.kind == SKG_INSTR_FULL ? d.Nchan : 1);
             f->ensure(bytes); SKG_CUDA(cudaMemsetAsync(f->p, 0, bytes, e.stream));
-            d.frame = f->as<double>();
+            if (s.kind == SKG_INSTR_FULL) d.chanFrame = f->as<double>(); else d.frame = f->as<double>();
         }
         if (s.kind != SKG_INSTR_FRAME)
         {
             DevBuf* f = new DevBuf(); e.instrBufs.push_back(f);
-            f->ensure(sizeof(double) * e.med.Nlambda); SKG_CUDA(cudaMemsetAsync(f->p, 0, sizeof(double) * e.med.Nlambda, e.stream));
-            d.sed = f->as<double>();
+            size_t bytes = sizeof(double) * e.med.Nlambda * (s.kind == SKG_INSTR_FULL ? d.Nchan : 1);
+            f->ensure(bytes); SKG_CUDA(cudaMemsetAsync(f->p, 0, bytes, e.stream));
+            if (s.kind == SKG_INSTR_FULL) d.chanSed = f->as<double>(); else d.sed = f->as<double>();
         }
         e.instr.push_back(d);
     }
@@ -749,6 +777,8 @@ void mcResetResults(Engine& e)
     {
         if (d.frame) SKG_CUDA(cudaMemsetAsync(d.frame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * e.med.Nlambda, e.stream));
         if (d.sed) SKG_CUDA(cudaMemsetAsync(d.sed, 0, sizeof(double) * e.med.Nlambda, e.stream));
+        if (d.chanFrame) SKG_CUDA(cudaMemsetAsync(d.chanFrame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * e.med.Nlambda * d.Nchan, e.stream));
+        if (d.chanSed) SKG_CUDA(cudaMemsetAsync(d.chanSed, 0, sizeof(double) * e.med.Nlambda * d.Nchan, e.stream));
     }
     if (e.labs.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labs.p, 0, sizeof(double) * e.labsCount, e.stream));
     e.sync();

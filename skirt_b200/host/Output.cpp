@@ -49,12 +49,12 @@ double UnitSystem::osurfacebrightness(double lambda, double flambda) const  // U
     }
 }
 
-std::vector<double> calibrateDataCube(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units)
+static std::vector<double> calibrateCube(const Instrument& ins, const std::vector<double>& raw, const WavelengthGrid& lg, const UnitSystem& units)
 {
     const skg_instrument d = ins.descriptor();
     const int Nl = lg.Nlambda(); const size_t Nframe = (size_t)d.Nxp * d.Nyp;
-    if (ins.ftotv.size() != Nframe * Nl) SKIRT_FATAL("the data cube of instrument " + ins.name + " has not been fetched");
-    std::vector<double> f = ins.ftotv;
+    if (raw.size() != Nframe * Nl) SKIRT_FATAL("the data cube of instrument " + ins.name + " has not been fetched");
+    std::vector<double> f = raw;
     // step 1: W -> W/m
     for (int ell = 0; ell < Nl; ell++) { const double dl = lg.dlambda(ell); for (size_t l = 0; l < Nframe; l++) f[l + Nframe * ell] /= dl; }
     // step 2: per steradian
@@ -69,18 +69,23 @@ std::vector<double> calibrateDataCube(const Instrument& ins, const WavelengthGri
     return f;
 }
 
-std::vector<double> calibrateSED(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units)
+std::vector<double> calibrateDataCube(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units)
+{ return calibrateCube(ins, ins.ftotv, lg, units); }
+
+static std::vector<double> calibrateFluxes(const Instrument& ins, const std::vector<double>& raw, const WavelengthGrid& lg, const UnitSystem& units)
 {
     const skg_instrument d = ins.descriptor();
     const int Nl = lg.Nlambda();
-    if ((int)ins.Ftotv.size() != Nl) SKIRT_FATAL("the SED of instrument " + ins.name + " has not been fetched");
-    std::vector<double> F = ins.Ftotv;
+    if ((int)raw.size() != Nl) SKIRT_FATAL("the SED of instrument " + ins.name + " has not been fetched");
+    std::vector<double> F = raw;
     for (int ell = 0; ell < Nl; ell++) F[ell] /= lg.dlambda(ell);
     const double fourpid2 = 4.0 * M_PI * d.distance * d.distance;
     for (double& v : F) v /= fourpid2;
     for (int ell = 0; ell < Nl; ell++) F[ell] = units.ofluxdensity(lg.lambda(ell), F[ell]);
     return F;
 }
+std::vector<double> calibrateSED(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units)
+{ return calibrateFluxes(ins, ins.Ftotv, lg, units); }
 
 namespace
 {
@@ -149,23 +154,66 @@ void writeFITS(const std::string& path, const std::vector<double>& data, int nx,
     if (!out) SKIRT_FATAL("Error while writing FITS file " + path);
 }
 
-void writeSED(const std::string& path, const WavelengthGrid& lg, const std::vector<double>& F, const std::string& columnName, const UnitSystem& units)
+void writeSEDs(const std::string& path, const WavelengthGrid& lg, const std::vector<std::vector<double>>& Fs,
+               const std::vector<std::string>& columnNames, const UnitSystem& units)
 {
     std::ofstream out(path, std::ios::trunc);
     if (!out) SKIRT_FATAL("cannot create " + path);
     out << "# column 1: lambda (" << units.uwavelength() << ")\n";
-    out << "# column 2: " << columnName << "; " << units.sfluxdensity() << " (" << units.ufluxdensity() << ")\n";
-    char b[64];
+    for (size_t q = 0; q < Fs.size(); q++)
+        out << "# column " << q + 2 << ": " << columnNames[q] << "; " << units.sfluxdensity() << " (" << units.ufluxdensity() << ")\n";
+    char b[32];
     for (int ell = 0; ell < lg.Nlambda(); ell++)
     {
-        std::snprintf(b, sizeof b, "%.8e %.8e\n", units.owavelength(lg.lambda(ell)), F[ell]);       // QString::number(v, 'e', 8)
-        out << b;
+        std::snprintf(b, sizeof b, "%.8e", units.owavelength(lg.lambda(ell))); out << b;       // QString::number(v, 'e', 8)
+        for (const auto& F : Fs) { std::snprintf(b, sizeof b, " %.8e", F.empty() ? 0.0 : F[ell]); out << b; }
+        out << "\n";
     }
 }
+void writeSED(const std::string& path, const WavelengthGrid& lg, const std::vector<double>& F, const std::string& columnName, const UnitSystem& units)
+{ writeSEDs(path, lg, {F}, {columnName}, units); }
 
-void writeInstrument(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units, const std::string& prefix, const std::string& stamp)
+void writeInstrument(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units, const std::string& prefix, const std::string& stamp,
+                     bool dustsystem, bool dustemission)
 {
     const skg_instrument d = ins.descriptor();
+    if (const FullInstrument* fi = dynamic_cast<const FullInstrument*>(&ins))
+    {
+        // FullInstrument::write, FullInstrument.cpp:176-236: total = direct + scattered (+ dust); empty arrays are skipped as
+        // data cubes (calibrateAndWriteDataCubes, SingleFrameInstrument.cpp:151-226) and written as zero SED columns
+        if ((int)fi->fchanv.size() != fi->channels() || (int)fi->Fchanv.size() != fi->channels())
+            SKIRT_FATAL("the detector arrays of instrument " + ins.name + " have not been fetched");
+        typedef std::vector<double> V;
+        auto sum = [](const V& a, const V& b) { V r(a); for (size_t i = 0; i < r.size(); i++) r[i] += b[i]; return r; };
+        const V none;
+        const V &ftra = fi->fchanv[SKG_CHAN_TRANSPARENT], &Ftra = fi->Fchanv[SKG_CHAN_TRANSPARENT];
+        const V &fdir = fi->fchanv[SKG_CHAN_STELLAR_DIRECT], &Fdir = fi->Fchanv[SKG_CHAN_STELLAR_DIRECT];
+        const V &fsca = fi->fchanv[SKG_CHAN_STELLAR_SCATTERED], &Fsca = fi->Fchanv[SKG_CHAN_STELLAR_SCATTERED];
+        const V &fdd = fi->fchanv[SKG_CHAN_DUST_DIRECT], &Fdd = fi->Fchanv[SKG_CHAN_DUST_DIRECT];
+        const V &fds = fi->fchanv[SKG_CHAN_DUST_SCATTERED], &Fds = fi->Fchanv[SKG_CHAN_DUST_SCATTERED];
+        std::vector<V> f, F; std::vector<std::string> fn, Fn;
+        auto add = [&](const V& fa, const V& Fa, const char* fname, const std::string& Fname) { f.push_back(fa); F.push_back(Fa); fn.push_back(fname); Fn.push_back(Fname); };
+        if (dustemission) add(sum(sum(fdir, fsca), sum(fdd, fds)), sum(sum(Fdir, Fsca), sum(Fdd, Fds)), "total", "total flux");
+        else if (dustsystem) add(sum(fdir, fsca), sum(Fdir, Fsca), "total", "total flux");
+        else add(ftra, Ftra, "total", "total flux");
+        add(dustsystem ? fdir : none, dustsystem ? Fdir : Ftra, "direct", "direct stellar flux");
+        add(dustsystem ? fsca : none, dustsystem ? Fsca : none, "scattered", "scattered stellar flux");
+        add(dustemission ? sum(fdd, fds) : none, dustemission ? sum(Fdd, Fds) : none, "dust", "total dust emission flux");
+        add(dustemission ? fds : none, dustemission ? Fds : none, "dustscattered", "dust emission scattered flux");
+        add(dustsystem ? ftra : none, Ftra, "transparent", "transparent flux");
+        for (int n = 0; n < fi->scatteringLevels(); n++)
+            add(dustsystem ? fi->fchanv[SKG_CHAN_SCATTERING_LEVEL1 + n] : none, dustsystem ? fi->Fchanv[SKG_CHAN_SCATTERING_LEVEL1 + n] : none,
+                ("scatteringlevel" + std::to_string(n + 1)).c_str(), std::to_string(n + 1) + "-times scattered flux");
+        for (size_t q = 0; q < f.size(); q++)
+        {
+            if (!f[q].empty())
+                writeFITS(prefix + "_" + ins.name + "_" + fn[q] + ".fits", calibrateCube(ins, f[q], lg, units), d.Nxp, d.Nyp, lg.Nlambda(),
+                          units.olength(d.fovxp / d.Nxp), units.olength(d.fovyp / d.Nyp), d.xpc, d.ypc, units.usurfacebrightness(), units.ulength(), stamp);
+            if (!F[q].empty()) F[q] = calibrateFluxes(ins, F[q], lg, units);
+        }
+        writeSEDs(prefix + "_" + ins.name + "_sed.dat", lg, F, Fn, units);
+        return;
+    }
     if (d.kind != SKG_INSTR_SED)
         writeFITS(prefix + "_" + ins.name + "_total.fits", calibrateDataCube(ins, lg, units), d.Nxp, d.Nyp, lg.Nlambda(),
                   units.olength(d.fovxp / d.Nxp), units.olength(d.fovyp / d.Nyp), d.xpc, d.ypc, units.usurfacebrightness(), units.ulength(), stamp);

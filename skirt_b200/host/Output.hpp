@@ -47,8 +47,14 @@ std::vector<double> calibrateSED(const Instrument& ins, const WavelengthGrid& lg
 void writeFITS(const std::string& path, const std::vector<double>& data, int nx, int ny, int nz, double incx, double incy,
                double xc, double yc, const std::string& dataUnits, const std::string& xyUnits, const std::string& stamp = "");
 void writeSED(const std::string& path, const WavelengthGrid& lg, const std::vector<double>& F, const std::string& columnName, const UnitSystem& units);
+// several flux columns (DistantInstrument::calibrateAndWriteSEDs, DistantInstrument.cpp:131-183); an empty column is written as zeros
+void writeSEDs(const std::string& path, const WavelengthGrid& lg, const std::vector<std::vector<double>>& Fs,
+               const std::vector<std::string>& columnNames, const UnitSystem& units);
 
-// Instrument::write() of FrameInstrument / SEDInstrument / SimpleInstrument: <prefix>_<name>_total.fits, <prefix>_<name>_sed.dat
-void writeInstrument(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units, const std::string& prefix, const std::string& stamp = "");
+// Instrument::write() of FrameInstrument / SEDInstrument / SimpleInstrument: <prefix>_<name>_total.fits, <prefix>_<name>_sed.dat;
+// of FullInstrument (FullInstrument.cpp:176-236): <prefix>_<name>_{total,direct,scattered,dust,dustscattered,transparent,
+// scatteringlevelN}.fits for the non-empty channels and one SED file with a column per channel
+void writeInstrument(const Instrument& ins, const WavelengthGrid& lg, const UnitSystem& units, const std::string& prefix, const std::string& stamp = "",
+                     bool dustsystem = true, bool dustemission = false);
 
 }   // namespace skirt

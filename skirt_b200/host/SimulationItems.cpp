@@ -179,6 +179,17 @@ void MonteCarloSimulation::fetchResults()
     for (auto& i : _is->instruments())
     {
         skg_instrument d = i->descriptor();
+        if (FullInstrument* f = dynamic_cast<FullInstrument*>(i.get()))
+        {
+            f->fchanv.assign(f->channels(), std::vector<double>((size_t)d.Nxp * d.Nyp * Nl, 0.0));
+            f->Fchanv.assign(f->channels(), std::vector<double>(Nl, 0.0));
+            for (int c = 0; c < f->channels(); c++)
+            {
+                check(skg_fetch_frame_channel(_engine, idx, c, f->fchanv[c].data(), 0));
+                check(skg_fetch_sed_channel(_engine, idx, c, f->Fchanv[c].data(), 0));
+            }
+            idx++; continue;
+        }
         if (d.kind != SKG_INSTR_SED) { i->ftotv.assign((size_t)d.Nxp * d.Nyp * Nl, 0.0); check(skg_fetch_frame(_engine, idx, i->ftotv.data(), 0)); }
         if (d.kind != SKG_INSTR_FRAME) { i->Ftotv.assign(Nl, 0.0); check(skg_fetch_sed(_engine, idx, i->Ftotv.data(), 0)); }
         idx++;

@@ -499,6 +499,7 @@ public:
     void setFieldOfViewX(double v) { d.fovxp = v; } void setFieldOfViewY(double v) { d.fovyp = v; }
     void setCenterX(double v) { d.xpc = v; } void setCenterY(double v) { d.ypc = v; }
     skg_instrument descriptor() const { skg_instrument s = d; s.kind = kind(); return s; }
+    virtual int channels() const { return 0; }     // FullInstrument: 5 + scatteringLevels separate detector arrays
     std::string name;
     std::vector<double> ftotv, Ftotv;      // the detector arrays that Instrument::write() calibrates and saves (filled by fetch)
 protected:
@@ -507,6 +508,17 @@ protected:
 class FrameInstrument : public Instrument { public: int kind() const override { return SKG_INSTR_FRAME; } };
 class SEDInstrument : public Instrument { public: int kind() const override { return SKG_INSTR_SED; } };
 class SimpleInstrument : public Instrument { public: int kind() const override { return SKG_INSTR_SIMPLE; } };
+// FullInstrument (FullInstrument.cpp, unpolarised): transparent / direct / scattered stellar and direct / scattered dust
+// emission flux in separate data cubes and SEDs, plus one per scattering level; channel order = SKG_CHAN_*
+class FullInstrument : public Instrument
+{
+public:
+    int kind() const override { return SKG_INSTR_FULL; }
+    void setScatteringLevels(int v) { if (v < 0) SKIRT_FATAL("the number of scattering levels should be zero or positive"); d.scatteringLevels = v; }
+    int scatteringLevels() const { return d.scatteringLevels; }
+    int channels() const override { return SKG_CHAN_SCATTERING_LEVEL1 + d.scatteringLevels; }
+    std::vector<std::vector<double>> fchanv, Fchanv;     // [channel][...] raw detector arrays (filled by fetch)
+};
 
 class InstrumentSystem
 {

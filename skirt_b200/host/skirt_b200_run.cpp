@@ -128,9 +128,11 @@ int main(int argc, char** argv)
             else if (key == "instrument")
             {
                 std::string kind, name; double d, inc, az, pa; in >> kind >> name >> d >> inc >> az >> pa;
-                Instrument* i = kind == "sed" ? (Instrument*)new SEDInstrument() : kind == "frame" ? (Instrument*)new FrameInstrument() : (Instrument*)new SimpleInstrument();
+                Instrument* i = kind == "sed" ? (Instrument*)new SEDInstrument() : kind == "frame" ? (Instrument*)new FrameInstrument()
+                              : kind == "full" ? (Instrument*)new FullInstrument() : (Instrument*)new SimpleInstrument();
                 i->setInstrumentName(name); i->setDistance(d); i->setInclination(inc); i->setAzimuth(az); i->setPositionAngle(pa);
                 if (kind != "sed") { int nx, ny; double fx, fy; in >> nx >> fx >> ny >> fy; i->setPixelsX(nx); i->setFieldOfViewX(fx); i->setPixelsY(ny); i->setFieldOfViewY(fy); }
+                if (kind == "full") { int nscatt; in >> nscatt; static_cast<FullInstrument*>(i)->setScatteringLevels(nscatt); }
                 is->addInstrument(i);
             }
             else SKIRT_FATAL("unknown key " + key);
@@ -151,6 +153,16 @@ int main(int argc, char** argv)
             for (auto& i : sim.instrumentSystem()->instruments())
             {
                 skg_instrument d = i->descriptor();
+                if (FullInstrument* f = dynamic_cast<FullInstrument*>(i.get()))
+                {
+                    for (int c = 0; c < f->channels(); c++)
+                    {
+                        f->fchanv.push_back(load(i->name + "_frame" + std::to_string(c), (size_t)d.Nxp * d.Nyp * Nl));
+                        f->Fchanv.push_back(load(i->name + "_sed" + std::to_string(c), Nl));
+                    }
+                    writeInstrument(*i, *sim.wavelengthGrid(), *units, prefix, "", true, sim.dustemission());
+                    continue;
+                }
                 if (d.kind != SKG_INSTR_SED) i->ftotv = load(i->name + "_frame", (size_t)d.Nxp * d.Nyp * Nl);
                 if (d.kind != SKG_INSTR_FRAME) i->Ftotv = load(i->name + "_sed", Nl);
                 writeInstrument(*i, *sim.wavelengthGrid(), *units, prefix);
@@ -168,7 +180,9 @@ int main(int argc, char** argv)
         {
             if (!i->ftotv.empty()) dump(i->name + "_frame", i->ftotv);
             if (!i->Ftotv.empty()) dump(i->name + "_sed", i->Ftotv);
-            writeInstrument(*i, *sim.wavelengthGrid(), *units, prefix);        // Instrument::write(): calibration + FITS / SED files
+            if (FullInstrument* f = dynamic_cast<FullInstrument*>(i.get()))
+                for (int c = 0; c < f->channels(); c++) { dump(i->name + "_frame" + std::to_string(c), f->fchanv[c]); dump(i->name + "_sed" + std::to_string(c), f->Fchanv[c]); }
+            writeInstrument(*i, *sim.wavelengthGrid(), *units, prefix, "", true, sim.dustemission());        // Instrument::write(): calibration + FITS / SED files
         }
         if (!sim.Labs().empty()) dump("Labs", sim.Labs());
         dump("rho", sim.dustSystem()->rho());

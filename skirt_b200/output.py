@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from .simulation import FatalError, INSTR_FRAME, INSTR_SED
+from .simulation import FatalError, INSTR_FRAME, INSTR_SED, INSTR_FULL
 
 _C = 2.99792458e8            # Units.cpp:17-22
 _AU = 1.49597871e11
@@ -222,6 +222,38 @@ def _qnum_e(v, prec):
     return f"{v:.{prec}e}"
 
 
+def full_instrument_arrays(ins, results, dustsystem=True, dustemission=False):
+    """the lists FullInstrument::write assembles (FullInstrument.cpp:176-236): [(file name, column name, cube, sed)] with
+    total = direct + scattered (+ dust), empty arrays left out like the reference's `if (farr->size())`"""
+    get = lambda c, k: np.asarray(results[f"{ins.name}_{c}_{k}"], dtype=np.float64)
+    fr = {c: get(c, "frame") for c in ins.channel_names()}; se = {c: get(c, "sed") for c in ins.channel_names()}
+    rows = []
+    if dustemission:
+        rows.append(("total", "total flux", fr["direct"] + fr["scattered"] + fr["dustdirect"] + fr["dustscattered"],
+                     se["direct"] + se["scattered"] + se["dustdirect"] + se["dustscattered"]))
+    elif dustsystem:
+        rows.append(("total", "total flux", fr["direct"] + fr["scattered"], se["direct"] + se["scattered"]))
+    else:
+        rows.append(("total", "total flux", fr["transparent"], se["transparent"]))
+    if dustsystem:
+        rows.append(("direct", "direct stellar flux", fr["direct"], se["direct"]))
+        rows.append(("scattered", "scattered stellar flux", fr["scattered"], se["scattered"]))
+    else:
+        rows.append(("direct", "direct stellar flux", None, se["transparent"]))
+        rows.append(("scattered", "scattered stellar flux", None, None))
+    if dustemission:
+        rows.append(("dust", "total dust emission flux", fr["dustdirect"] + fr["dustscattered"], se["dustdirect"] + se["dustscattered"]))
+        rows.append(("dustscattered", "dust emission scattered flux", fr["dustscattered"], se["dustscattered"]))
+    else:
+        rows.append(("dust", "total dust emission flux", None, None))
+        rows.append(("dustscattered", "dust emission scattered flux", None, None))
+    rows.append(("transparent", "transparent flux", fr["transparent"] if dustsystem else None, se["transparent"]))
+    for n in range(ins.d["scatteringLevels"]):
+        c = f"scatteringlevel{n + 1}"
+        rows.append((c, f"{n + 1}-times scattered flux", fr[c] if dustsystem else None, se[c] if dustsystem else None))
+    return rows
+
+
 def write_sed(path, lambdagrid, columns, names, units):
     """the <instrument>_sed.dat text file (DistantInstrument.cpp:160-182 through TextOutFile.cpp:45-85)"""
     lines = [f"# column 1: lambda ({units.uwavelength()})"]
@@ -245,6 +277,23 @@ def write_instruments(sim, results, outdir, prefix="", units=None, stamp=None):
     lg = sim.lambdagrid
     for ins in sim.isys.instruments:
         d = ins.d
+        if ins.kind == INSTR_FULL:
+            rows = full_instrument_arrays(ins, results, dustsystem=sim.ds is not None, dustemission=bool(getattr(sim, "dustemission", False)))
+            xpsiz = d["fovxp"] / d["Nxp"]; ypsiz = d["fovyp"] / d["Nyp"]
+            cols, names = [], []
+            for fname, cname, cube, sed in rows:
+                if cube is not None:
+                    cal = calibrate_frames(cube, lg, d, units)
+                    name = f"{prefix}{ins.name}_{fname}.fits"
+                    write_fits(os.path.join(outdir, name), cal, d["Nxp"], d["Nyp"], lg.Nlambda, units.out("length", xpsiz),
+                               units.out("length", ypsiz), d["xpc"], d["ypc"], units.unit("surfacebrightness"), units.unit("length"), stamp)
+                    out[name] = cal
+                # an empty F-array still gets a column of zeros (DistantInstrument.cpp:178)
+                cols.append(calibrate_sed(sed, lg, d, units) if sed is not None else np.zeros(lg.Nlambda)); names.append(cname)
+            name = f"{prefix}{ins.name}_sed.dat"
+            write_sed(os.path.join(outdir, name), lg, cols, names, units)
+            out[name] = np.array(cols)
+            continue
         if ins.kind != INSTR_SED:
             cube = calibrate_frames(results[ins.name + "_frame"], lg, d, units)
             xpsiz = d["fovxp"] / d["Nxp"]; ypsiz = d["fovyp"] / d["Nyp"]

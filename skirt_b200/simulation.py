@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from .parallel import shard_packets
-from .binding import Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE
+from .binding import Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, CHAN_LEVEL1
 
 PC = 3.08567758e16          # Units.cpp:17-30
 LSUN = 3.839e26
@@ -434,6 +434,24 @@ class SimpleInstrument(_DistantInstrument):
     kind = INSTR_SIMPLE
 
 
+class FullInstrument(_DistantInstrument):
+    """FullInstrument (FullInstrument.cpp): separate data cubes and SEDs for the transparent, direct / scattered stellar and
+    direct / scattered dust emission flux, plus one per scattering level (unpolarised)"""
+    kind = INSTR_FULL
+    CHANNELS = ("transparent", "direct", "scattered", "dustdirect", "dustscattered")
+
+    def __init__(self, instrumentName, distance, inclination, azimuth=0.0, positionAngle=0.0, pixelsX=0, fieldOfViewX=0.0,
+                 pixelsY=0, fieldOfViewY=0.0, centerX=0.0, centerY=0.0, scatteringLevels=0):
+        super().__init__(instrumentName, distance, inclination, azimuth, positionAngle, pixelsX, fieldOfViewX, pixelsY, fieldOfViewY,
+                         centerX, centerY)
+        if scatteringLevels < 0:
+            raise FatalError("the number of scattering levels should be zero or positive")
+        self.d["scatteringLevels"] = int(scatteringLevels)
+
+    def channel_names(self):
+        return list(self.CHANNELS) + [f"scatteringlevel{n + 1}" for n in range(self.d["scatteringLevels"])]
+
+
 class InstrumentSystem:
     def __init__(self, instruments):
         self.instruments = list(instruments)
@@ -566,6 +584,11 @@ class MonteCarloSimulation:
             return buf[key]
         Nl = self.lambdagrid.Nlambda
         for i, ins in enumerate(self.isys.instruments):
+            if ins.kind == INSTR_FULL:
+                for c, cname in enumerate(ins.channel_names()):
+                    out[f"{ins.name}_{cname}_frame"] = self.engine.fetch_frame_channel(i, c).reshape(Nl, ins.d["Nyp"], ins.d["Nxp"])
+                    out[f"{ins.name}_{cname}_sed"] = self.engine.fetch_sed_channel(i, c)
+                continue
             if ins.kind != INSTR_SED:
                 n = ins.d["Nxp"] * ins.d["Nyp"] * Nl
                 out[ins.name + "_frame"] = self.engine.fetch_frame(i, dest(("f", i), (n,))).reshape(Nl, ins.d["Nyp"], ins.d["Nxp"])

@@ -197,6 +197,18 @@ def cfg_c1(n=40, packages=1e5, instruments=None, storeabs=0, tau=1.0, grid=None,
                 instruments=instruments, mwr=1e4, minscatt=0.0, xi=0.5, ebias=0.5)
 
 
+FULL_NSCATT = 2
+
+
+def cfg_full(threads=1):
+    """C1 geometry at tau_V = 3 seen by a FullInstrument with 2 scattering levels plus an SEDInstrument in the same
+    direction (tests/golden/mc_full.npz, made by tests/golden/make_full_golden.py)"""
+    ins = [dict(kind=4, name="full", distance=1e7 * PC, inclination=float(np.radians(80)), azimuth=0.0, positionAngle=0.0,
+                Nxp=40, fovxp=50000 * PC, Nyp=16, fovyp=20000 * PC, scatteringLevels=FULL_NSCATT),
+           dict(kind=2, name="s80", distance=1e7 * PC, inclination=float(np.radians(80)), azimuth=0.0, positionAngle=0.0)]
+    return cfg_c1(n=24, packages=2e5, instruments=ins, tau=3.0, threads=threads)
+
+
 def _geom_words(g):
     if g["geometry"] == 1:
         p = g["p"]; w = f"expdisk {p[0]!r} {p[1]!r} {p[2]!r} {p[3]!r}"
@@ -226,10 +238,12 @@ def ref_spec(cfg):
     if cfg.get("ameshdust"):
         lines.append(f"ameshdust {cfg['ameshdust']!r}")
     for ins in cfg["instruments"]:
-        kind = {1: "frame", 2: "sed", 3: "simple"}[ins["kind"]]
+        kind = {1: "frame", 2: "sed", 3: "simple", 4: "full"}[ins["kind"]]
         w = f"instrument {kind} {ins['name']} {ins['distance']!r} {ins['inclination']!r} {ins.get('azimuth', 0.0)!r} {ins.get('positionAngle', 0.0)!r}"
         if ins["kind"] != 2:
             w += f" {ins['Nxp']} {ins['fovxp']!r} {ins['Nyp']} {ins['fovyp']!r}"
+        if ins["kind"] == 4:
+            w += f" {ins.get('scatteringLevels', 0)}"
         lines.append(w)
     return "\n".join(lines) + "\n"
 
@@ -277,8 +291,8 @@ def load_golden(name):
     return tables, medium, data
 
 
-def load_golden_mc():
-    z = np.load(os.path.join(GOLDEN, "mc_c1.npz"))
+def load_golden_mc(name="mc_c1"):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
     tables = {k[5:]: (str(z[k]) if k == "grid_kind" else z[k]) for k in z.files if k.startswith("grid_")}
     medium = {k[4:]: z[k] for k in z.files if k.startswith("med_")}
     data = {k: z[k] for k in z.files if not k.startswith(("grid_", "med_"))}

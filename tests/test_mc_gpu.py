@@ -161,3 +161,52 @@ def test_configuration_errors_are_reported(engine):
         engine.sources([dict(geometry=7, p=[1, 1])], np.array([[1.0, 1.0]]), 0.5)
     with pytest.raises(sk.EngineError, match="skg_dust_library"):
         engine.dust_cell_luminosities()
+
+
+def test_full_instrument_channels_against_reference_runs(engine):
+    """FullInstrument::detect (FullInstrument.cpp:107-172, unpolarised): transparent / direct / scattered data cubes and SEDs
+    plus one per scattering level, against 16 runs of the reference's own FullInstrument (tests/golden/mc_full.npz)"""
+    tables, medium, g = common.load_golden_mc("mc_full")
+    cfg = common.cfg_full()
+    common.setup_engine(engine, cfg, tables, medium, g["L"])
+    B = 16; Npp = float(g["Npp"][0])
+    chans = (0, 1, 2, 5, 6)
+    fr = {c: [] for c in range(7)}; se = {c: [] for c in range(7)}; tot = []
+    for b in range(B):
+        engine.reset_results()
+        engine.run_stellar(Npp, seed=900 + b)
+        for c in range(7):
+            fr[c].append(engine.fetch_frame_channel(0, c)); se[c].append(engine.fetch_sed_channel(0, c))
+        tot.append(engine.fetch_sed(1))
+    fr = {c: np.array(v) for c, v in fr.items()}; se = {c: np.array(v) for c, v in se.items()}; tot = np.array(tot)
+    # exact structure of one run: no dust emission channels in the stellar phase; transparent SED = emitted luminosity;
+    # direct + scattered = what the SEDInstrument in the same direction saw; levels 1 and 2 are part of 'scattered'
+    assert not fr[3].any() and not fr[4].any() and not se[3].any() and not se[4].any()
+    np.testing.assert_allclose(se[0][:, 0], g["L"].sum(), rtol=1e-9)
+    np.testing.assert_allclose(se[1] + se[2], tot, rtol=1e-9)
+    assert np.all(se[5] + se[6] < se[2]) and np.all(fr[5] + fr[6] <= fr[2] * (1 + 1e-12))
+    for c in chans:
+        for name, a in (("frame", fr[c]), ("sed", se[c])):
+            mean = a.mean(0); sem = a.std(0, ddof=1) / np.sqrt(B)
+            gm, gs = g[f"{name}{c}_mean"], g[f"{name}{c}_sem"]
+            zt = (a.reshape(B, -1).sum(1).mean() - gm.sum()) / max(np.hypot(a.reshape(B, -1).sum(1).std(ddof=1) / np.sqrt(B), np.sqrt((gs ** 2).sum())), 1e-12 * gm.sum())
+            assert abs(zt) < 3.5, f"channel {c} {name}: total differs by {zt:.2f} sigma"
+            z = common.zscores(mean, sem, gm, gs)
+            if len(z) > 10:
+                assert np.mean(np.abs(z) < 3) > 0.97, f"channel {c} {name}: only {np.mean(np.abs(z) < 3):.4f} of bins within 3 sigma"
+                assert abs(z.mean()) < 0.15, f"channel {c} {name}: systematic offset, mean z = {z.mean():.3f}"
+    z = (tot.mean(0) - g["sedtotal_mean"]) / np.hypot(tot.std(0, ddof=1) / np.sqrt(B), g["sedtotal_sem"])
+    assert np.all(np.abs(z) < 3.5)
+
+
+def test_full_instrument_errors(engine):
+    tables, medium, g = common.load_golden_mc("mc_full")
+    cfg = common.cfg_full()
+    common.setup_engine(engine, cfg, tables, medium, g["L"])
+    with pytest.raises(Exception):
+        engine.fetch_frame_channel(0, 7)                 # 5 + 2 channels
+    with pytest.raises(Exception):
+        engine.fetch_sed_channel(1, 0)                   # an SEDInstrument has no channels
+    bad = [dict(cfg["instruments"][0], scatteringLevels=-1)]
+    with pytest.raises(Exception):
+        engine.instruments(bad)

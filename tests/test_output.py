@@ -127,3 +127,67 @@ def test_cpp_write_matches_reference(tmp_path, simkind, us, style):
         assert lines[1] == f"# column 2: total flux; {units.sfluxdensity()} ({units.ufluxdensity()})"
         rows = np.array([[float(v) for v in ln.split()] for ln in lines[2:]])
         np.testing.assert_allclose(rows, G[key + name + "_cal_sed"], rtol=1e-8)
+
+
+def test_full_instrument_write_matches_reference(tmp_path):
+    """FullInstrument::write (FullInstrument.cpp:176-236): total = direct + scattered, one FITS cube per non-empty channel
+    (total, direct, scattered, transparent, scatteringlevelN -- no dust cubes without dust emission) and one SED column per
+    channel (zeros for the empty dust channels), against the files the reference wrote for the same raw detector arrays"""
+    import types
+    F = np.load(os.path.join(common.GOLDEN, "mc_full.npz"))
+    cfg = common.cfg_full()
+    d = cfg["instruments"][0]
+    ins = sim.FullInstrument("full", d["distance"], d["inclination"], pixelsX=d["Nxp"], fieldOfViewX=d["fovxp"], pixelsY=d["Nyp"],
+                             fieldOfViewY=d["fovyp"], scatteringLevels=d["scatteringLevels"])
+    assert ins.channel_names() == ["transparent", "direct", "scattered", "dustdirect", "dustscattered", "scatteringlevel1", "scatteringlevel2"]
+    lg = sim.OligoWavelengthGrid(cfg["wavelengths"])
+    nf = d["Nxp"] * d["Nyp"]
+    res = {}
+    for c, cname in enumerate(ins.channel_names()):
+        res[f"full_{cname}_frame"] = F[f"last_frame{c}"] if f"last_frame{c}" in F.files else np.zeros(nf)
+        res[f"full_{cname}_sed"] = F[f"last_sed{c}"] if f"last_sed{c}" in F.files else np.zeros(1)
+    fake = types.SimpleNamespace(lambdagrid=lg, isys=types.SimpleNamespace(instruments=[ins]), ds=object(), dustemission=False)
+    out = output.write_instruments(fake, res, str(tmp_path), prefix="t_", units=output.SIUnits(0))
+    cubes = sorted(k for k in out if k.endswith(".fits"))
+    assert cubes == sorted(f"t_full_{n}.fits" for n in ("total", "direct", "scattered", "transparent", "scatteringlevel1", "scatteringlevel2"))
+    for n in ("total", "direct", "scattered", "transparent", "scatteringlevel1", "scatteringlevel2"):
+        ref = F["written_" + n]
+        assert ref.max() > 0
+        np.testing.assert_allclose(out[f"t_full_{n}.fits"].ravel(), ref, rtol=4e-15, atol=0)
+        hdr, data = output.read_fits(str(tmp_path / f"t_full_{n}.fits"))
+        np.testing.assert_array_equal(data.ravel(), ref.astype(np.float32))
+    rows = F["written_sed_rows"]              # lambda + 8 columns: total, direct, scattered, dust, dustscattered, transparent, level 1, level 2
+    assert rows.shape == (1, 9)
+    np.testing.assert_allclose(out["t_full_sed.dat"][:, 0], rows[0, 1:], rtol=4e-15, atol=0)
+    assert rows[0, 4] == 0 and rows[0, 5] == 0
+    lines = open(tmp_path / "t_full_sed.dat").read().splitlines()
+    assert lines[1].startswith("# column 2: total flux;") and lines[8].startswith("# column 9: 2-times scattered flux;")
+    np.testing.assert_allclose([float(v) for v in lines[9].split()], rows[0], rtol=1e-8)
+    with pytest.raises(sim.FatalError):
+        sim.FullInstrument("x", 1.0, 0.0, pixelsX=2, fieldOfViewX=1.0, pixelsY=2, fieldOfViewY=1.0, scatteringLevels=-1)
+
+
+@pytest.mark.skipif(not os.path.exists(RUN), reason="skirt_b200_run not built")
+def test_cpp_full_instrument_write_matches_reference(tmp_path):
+    """the C++ host layer's FullInstrument::write on the reference's raw channel arrays: same cubes, same SED columns"""
+    import subprocess
+    F = np.load(os.path.join(common.GOLDEN, "mc_full.npz"))
+    cfg = common.cfg_full(); d = cfg["instruments"][0]
+    prefix = str(tmp_path / "out")
+    lines = ["sim oligo", f"wavelengths {cfg['wavelengths'][0]!r}", "units si neutral",
+             f"instrument full full {d['distance']!r} {d['inclination']!r} 0 0 {d['Nxp']} {d['fovxp']!r} {d['Nyp']} {d['fovyp']!r} {d['scatteringLevels']}"]
+    nf = d["Nxp"] * d["Nyp"]
+    for c in range(5 + d["scatteringLevels"]):
+        (F[f"last_frame{c}"] if f"last_frame{c}" in F.files else np.zeros(nf)).astype(np.float64).tofile(f"{prefix}_full_frame{c}.f64")
+        (F[f"last_sed{c}"] if f"last_sed{c}" in F.files else np.zeros(1)).astype(np.float64).tofile(f"{prefix}_full_sed{c}.f64")
+    f = tmp_path / "sim.txt"; f.write_text("\n".join(lines) + "\n")
+    r = subprocess.run([RUN, "--write-only", str(f), prefix], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    names = ("total", "direct", "scattered", "transparent", "scatteringlevel1", "scatteringlevel2")
+    assert sorted(p for p in os.listdir(tmp_path) if p.endswith(".fits")) == sorted(f"out_full_{n}.fits" for n in names)
+    for n in names:
+        hdr, cube = output.read_fits(f"{prefix}_full_{n}.fits")
+        np.testing.assert_array_equal(cube.ravel(), F["written_" + n].astype(np.float32))
+    lines = open(f"{prefix}_full_sed.dat").read().splitlines()
+    assert len(lines) == 10 and lines[4] == "# column 5: total dust emission flux; lambda*F_lambda (W/m2)"
+    np.testing.assert_allclose([float(v) for v in lines[9].split()], F["written_sed_rows"][0], rtol=1e-8)

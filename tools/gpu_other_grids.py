@@ -44,5 +44,5 @@ thr = os.cpu_count() or 1
 bench("octtree L7 neighbor", mk(common.spec_grid("octtree", search=1, minlevel=2, maxlevel=7, massfrac=2e-6, threads=thr)))
 #bench("octtree L7 bookkeeping", mk(common.spec_grid("octtree", search=2, minlevel=2, maxlevel=7, massfrac=2e-6, threads=thr)))
 bench("bintree L18 neighbor", mk(common.spec_grid("bintree", search=1, minlevel=6, maxlevel=18, massfrac=4e-6, threads=thr)))
-#bench("amesh depth5", mk(common.spec_grid("amesh", threads=thr), amesh=common.make_amesh(root=(8, 8, 8), max_depth=5, frac=2e-5)))
-#bench("voronoi 1e5", mk(common.spec_grid("voronoi", threads=thr), particles=common.voronoi_particles(100000)))
+bench("amesh depth5", mk(common.spec_grid("amesh", threads=thr), amesh=common.make_amesh(root=(8, 8, 8), max_depth=5, frac=2e-5)))
+bench("voronoi 1e5", mk(common.spec_grid("voronoi", threads=thr), particles=common.voronoi_particles(100000)))
