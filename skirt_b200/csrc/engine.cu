@@ -188,27 +188,58 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
             e.tree.lookup = up(e, lut.data(), lut.size()); e.tree.lookupG = G;
             for (int c = 0; c < 3; c++) e.tree.lookupInv[c] = G / (rb[3 + c] - rb[c]);
         }
-        e.tree.nbrRec = nullptr;
+        e.tree.nodeRec = nullptr; e.tree.nbrHint = nullptr;
         if (search == 1)
         {
             const size_t total = (size_t)std::max(0, nbrStart[6 * (size_t)N]);
+            for (size_t q = 0; q < total; q++) if (nbrIds[q] < 0 || nbrIds[q] >= N) throw Error("invalid neighbour id in tree tables");
             e.tree.nbrStart = up(e, nbrStart, 6 * (size_t)N + 1); e.tree.nbrIds = up(e, nbrIds, std::max<size_t>(1, total));
-            // expanded neighbour records (96 B each) unless they would take more than 24 GB
-            if (total > 0 && total * sizeof(TreeNbrRec) <= (size_t)24 << 30)
+            std::vector<TreeNodeRec> rec(N); std::vector<int> hints;
+            for (int l = 0; l < N; l++)
             {
-                std::vector<TreeNbrRec> rec(total);
-                for (size_t q = 0; q < total; q++)
+                TreeNodeRec& r = rec[l];
+                for (int c = 0; c < 6; c++) r.box[c] = box[6 * (size_t)l + c];
+                r.cell = cell[l]; r.hbase = (int)(hints.size() / 4); r.hmeta = 0; r.pad0 = 0; r.pad1[0] = r.pad1[1] = 0;
+                for (int w = 0; w < 6; w++)
                 {
-                    const int id = nbrIds[q];
-                    if (id < 0 || id >= N) throw Error("invalid neighbour id in tree tables");
-                    TreeNbrRec& r = rec[q];
-                    for (int c = 0; c < 6; c++) r.box[c] = box[6 * (size_t)id + c];
-                    r.id = id; r.cell = cell[id];
-                    for (int w = 0; w < 7; w++) r.nb[w] = nbrStart[6 * (size_t)id + w];
-                    r.pad[0] = r.pad[1] = r.pad[2] = 0;
+                    const int beg = nbrStart[6 * (size_t)l + w], cnt = nbrStart[6 * (size_t)l + w + 1] - beg;
+                    if (cnt < 0) throw Error("neighbour list offsets must not decrease");
+                    r.first[w] = cnt > 0 ? nbrIds[beg] : -1;
+                    if (cnt > 1)
+                    {
+                        // which neighbour covers the centre of each of the G x G bins of this wall (in-plane axes a, b); G = 2, 4, 8
+                        // or 16, fine enough to resolve the smallest neighbour where that is possible
+                        const int a = w < 2 ? 1 : 0, b = w < 4 ? 2 : 1;
+                        const double* nb = box + 6 * (size_t)l;
+                        double ratio = 1;
+                        for (int q = beg; q < beg + cnt; q++)
+                        {
+                            const double* c = box + 6 * (size_t)nbrIds[q];
+                            const double ea = c[a + 3] - c[a], eb = c[b + 3] - c[b];
+                            if (ea > 0) ratio = std::max(ratio, (nb[a + 3] - nb[a]) / ea);
+                            if (eb > 0) ratio = std::max(ratio, (nb[b + 3] - nb[b]) / eb);
+                        }
+                        int lg = 0; while (lg < 3 && (2 << lg) < ratio * 0.99) lg++;
+                        const int G = 2 << lg;
+                        if (hints.size() / 4 >= 2000000000u) throw Error("too many multi-neighbour walls");
+                        r.hmeta |= (1u | ((unsigned)lg << 1)) << (3 * w);
+                        for (int ia = 0; ia < G; ia++) for (int ib = 0; ib < G; ib++)
+                        {
+                            const double ca = nb[a] + (nb[a + 3] - nb[a]) * (ia + 0.5) / G, cb = nb[b] + (nb[b + 3] - nb[b]) * (ib + 0.5) / G;
+                            int pick = nbrIds[beg];
+                            for (int q = beg; q < beg + cnt; q++)
+                            {
+                                const double* c = box + 6 * (size_t)nbrIds[q];
+                                if (ca >= c[a] && ca <= c[a + 3] && cb >= c[b] && cb <= c[b + 3]) { pick = nbrIds[q]; break; }
+                            }
+                            hints.push_back(pick);
+                        }
+                    }
                 }
-                e.tree.nbrRec = up(e, rec.data(), total);
             }
+            e.tree.nodeRec = up(e, rec.data(), (size_t)N);
+            if (hints.empty()) hints.assign(16, 0);
+            e.tree.nbrHint = up(e, hints.data(), hints.size());
         }
         else { e.tree.nbrStart = nullptr; e.tree.nbrIds = nullptr; }
         { std::vector<int> cn(std::max(ncells, 1), 0); for (int l = 0; l < N; l++) if (cell[l] >= 0 && cell[l] < ncells) cn[cell[l]] = l; e.tree.cellNode = up(e, cn.data(), cn.size()); }
@@ -238,6 +269,16 @@ int skg_grid_amesh(skg_engine* eh, int N, const double* box, const int* nxyz, co
         e.amesh.box = up(e, box, 6 * (size_t)N); e.amesh.nxyz = up(e, nxyz, 3 * (size_t)N); e.amesh.child0 = up(e, child0, N);
         e.amesh.cell = up(e, cell, N); e.amesh.wallNbr = up(e, wallNbr, 6 * (size_t)N);
         { std::vector<int> cn(std::max(ncells, 1), 0); for (int l = 0; l < N; l++) if (cell[l] >= 0 && cell[l] < ncells) cn[cell[l]] = l; e.amesh.cellNode = up(e, cn.data(), cn.size()); }
+        {
+            std::vector<AMeshNodeRec> rec(N);
+            for (int l = 0; l < N; l++)
+            {
+                AMeshNodeRec& r = rec[l];
+                for (int c = 0; c < 6; c++) { r.box[c] = box[6 * (size_t)l + c]; r.wallNbr[c] = wallNbr[6 * (size_t)l + c]; }
+                r.cell = cell[l]; r.child0 = child0[l]; r.nx = nxyz[3 * (size_t)l]; r.ny = nxyz[3 * (size_t)l + 1]; r.nz = nxyz[3 * (size_t)l + 2]; r.pad = 0;
+            }
+            e.amesh.nodeRec = up(e, rec.data(), (size_t)N);
+        }
         e.amesh.N = N;
         e.amesh.eps = epsFor(box[3] - box[0], box[4] - box[1], box[5] - box[2]);
         e.gridKind = GRID_AMESH; e.Ncells = ncells;
@@ -264,6 +305,28 @@ int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* 
         e.voro.kdM = up(e, Nkd ? kdM : &one, nk); e.voro.kdAxis = up(e, Nkd ? kdAxis : &one, nk); e.voro.kdUp = up(e, Nkd ? kdUp : &one, nk);
         e.voro.kdLeft = up(e, Nkd ? kdLeft : &one, nk); e.voro.kdRight = up(e, Nkd ? kdRight : &one, nk);
         e.voro.cellBox = cellBox ? up(e, cellBox, 6 * (size_t)N) : nullptr;
+        {
+            const size_t total = (size_t)std::max(0, nbrStart[N]);
+            if (total + N + 8 > 2147483647ull) throw Error("too many Voronoi neighbours for int32 record indices");
+            std::vector<double> rec(4 * (total + N + 8), 0.0);
+            auto pack = [](int lo, int hi) { const long long v = (long long)(unsigned)lo | ((long long)hi << 32); double d; std::memcpy(&d, &v, 8); return d; };
+            for (int m = 0; m < N; m++)
+            {
+                const int beg = nbrStart[m], cnt = nbrStart[m + 1] - beg;
+                if (cnt < 0) throw Error("neighbour list offsets must not decrease");
+                double* h = rec.data() + 4 * ((size_t)beg + m);
+                h[0] = particles[3 * (size_t)m]; h[1] = particles[3 * (size_t)m + 1]; h[2] = particles[3 * (size_t)m + 2]; h[3] = pack(cnt, 0);
+                for (int q = 0; q < cnt; q++)
+                {
+                    const int id = nbrIds[beg + q];
+                    if (id >= N) throw Error("invalid neighbour id in Voronoi tables");
+                    double* s4 = h + 4 * (size_t)(q + 1);
+                    if (id >= 0) { s4[0] = particles[3 * (size_t)id]; s4[1] = particles[3 * (size_t)id + 1]; s4[2] = particles[3 * (size_t)id + 2]; s4[3] = pack(id, nbrStart[id] + id); }
+                    else s4[3] = pack(id, 0);
+                }
+            }
+            e.voro.rec = up(e, rec.data(), rec.size());
+        }
         // extent arrives as xmin,xmax,ymin,ymax,zmin,zmax (Box setters order); stored as min corner, max corner
         e.voro.ext[0] = extent[0]; e.voro.ext[1] = extent[2]; e.voro.ext[2] = extent[4];
         e.voro.ext[3] = extent[1]; e.voro.ext[4] = extent[3]; e.voro.ext[5] = extent[5];

@@ -329,49 +329,58 @@ __device__ __forceinline__ int treeWhichNode(const TreeGrid& g, double x, double
     return node;
 }
 
+// rarely taken parts of a crossing, kept out of line so that the step body the warps loop over stays small
+static __device__ __noinline__ int treeWhichNodeCold(const TreeGrid& g, double x, double y, double z) { return treeWhichNode(g, x, y, z); }
 __device__ __forceinline__ double nextAfterAlong(double v, double k)
 {
     return nextafter(v, (k < 0.0) ? -SKG_DBL_MAX : SKG_DBL_MAX);
 }
 
-// TreeDustGrid::path (TreeDustGrid.cpp:390-662) one crossing at a time
-struct TreeWalker
+// TreeDustGrid::path (TreeDustGrid.cpp:390-662) one crossing at a time.  HINT selects how a wall with several neighbours is
+// searched (see step()): through the wall-bin table, or in list order starting from the neighbour held with the node.
+#ifndef SKG_TREE_HINTS_PATH
+#define SKG_TREE_HINTS_PATH true
+#endif
+#ifndef SKG_TREE_HINTS_MC
+#define SKG_TREE_HINTS_MC false
+#endif
+template<bool HINT> struct TreeWalkerT
 {
     static constexpr int kStepUnroll = 1;       // large step body: a plain loop (unrolling it costs more in instruction fetch than it gains)
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
     double bx[6];               // box of the current node, carried over from the neighbour test that selected it
-    int nb[7];                  // neighbour list offsets of the current node's six walls (Neighbor search)
+    int first[6];               // Neighbor search: first neighbour of each wall of the current node (TreeNodeRec)
+    int hbase; unsigned hmeta;  // where its wall-bin blocks start, and which walls have one
     int node, cellv;
     bool alive;
 
-    // everything a crossing needs from the node tables, fetched as soon as the node is known
-    __device__ __forceinline__ void loadNode(const TreeGrid& g, bool withBox)
-    {
-        if (withBox) { const double* b = g.box + 6 * (size_t)node; for (int c = 0; c < 6; c++) bx[c] = __ldg(b + c); }
-        cellv = __ldg(g.cell + node);
-        if (g.search == 1)
-        {
-            const int* s = g.nbrStart + 6 * (size_t)node; for (int w = 0; w < 7; w++) nb[w] = __ldg(s + w);
-        }
-    }
-    // one expanded neighbour record: 96 bytes as three 256-bit reads
-    static __device__ __forceinline__ void loadRec(const TreeNbrRec* rec, double (&w)[12])
+    // one node record: 96 bytes as three 256-bit reads
+    static __device__ __forceinline__ void loadRec(const TreeNodeRec* rec, double (&w)[12])
     {
         const double* rp = reinterpret_cast<const double*>(rec);
 #pragma unroll
         for (int u = 0; u < 3; u++)
             asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[4 * u]), "=d"(w[4 * u + 1]), "=d"(w[4 * u + 2]), "=d"(w[4 * u + 3]) : "l"(rp + 4 * u));
     }
-    // continue from the neighbour whose record has been read
-    __device__ __forceinline__ void adopt(const double (&w)[12])
+    static __device__ __forceinline__ bool recContains(const double (&w)[12], double x, double y, double z)
+    { return x >= w[0] && x <= w[3] && y >= w[1] && y <= w[4] && z >= w[2] && z <= w[5]; }
+    // continue from the node whose record has been read
+    __device__ __forceinline__ void adopt(int id, const double (&w)[12])
     {
         for (int c = 0; c < 6; c++) bx[c] = w[c];
-        const long long w6 = __double_as_longlong(w[6]), w7 = __double_as_longlong(w[7]), w8 = __double_as_longlong(w[8]),
+        const long long w6 = __double_as_longlong(w[6]), w8 = __double_as_longlong(w[8]),
                         w9 = __double_as_longlong(w[9]), w10 = __double_as_longlong(w[10]);
-        node = (int)(w6 & 0xffffffffll); cellv = (int)(w6 >> 32);
-        nb[0] = (int)(w7 & 0xffffffffll); nb[1] = (int)(w7 >> 32); nb[2] = (int)(w8 & 0xffffffffll); nb[3] = (int)(w8 >> 32);
-        nb[4] = (int)(w9 & 0xffffffffll); nb[5] = (int)(w9 >> 32); nb[6] = (int)(w10 & 0xffffffffll);
+        node = id; cellv = (int)(w6 & 0xffffffffll); hbase = (int)(w6 >> 32); hmeta = (unsigned)(__double_as_longlong(w[7]) & 0xffffffffll);
+        first[0] = (int)(w8 & 0xffffffffll); first[1] = (int)(w8 >> 32); first[2] = (int)(w9 & 0xffffffffll); first[3] = (int)(w9 >> 32);
+        first[4] = (int)(w10 & 0xffffffffll); first[5] = (int)(w10 >> 32);
+    }
+    // everything a crossing needs from the node tables, fetched as soon as the node is known
+    __device__ __forceinline__ void loadNode(const TreeGrid& g, bool withBox)
+    {
+        if (g.search == 1) { double w[12]; loadRec(g.nodeRec + node, w); adopt(node, w); return; }
+        if (withBox) { const double* b = g.box + 6 * (size_t)node; for (int c = 0; c < 6; c++) bx[c] = __ldg(b + c); }
+        cellv = __ldg(g.cell + node);
     }
 
     __device__ __forceinline__ bool start(const TreeGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
@@ -414,30 +423,50 @@ struct TreeWalker
             bool haveBox = false, haveAll = false;
             if (g.search == 1)
             {
-                // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first neighbour whose closed box contains r
-                const int beg = wall == 0 ? nb[0] : wall == 1 ? nb[1] : wall == 2 ? nb[2] : wall == 3 ? nb[3] : wall == 4 ? nb[4] : nb[5];
-                const int end = wall == 0 ? nb[1] : wall == 1 ? nb[2] : wall == 2 ? nb[3] : wall == 3 ? nb[4] : wall == 4 ? nb[5] : nb[6];
+                // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first neighbour whose closed box contains r.
+                // A wall with one neighbour tests that neighbour.  For a wall with several,
+                //  HINT: the wall-bin table says which of them covers the G x G bin r falls in; when r lies strictly inside that
+                //        neighbour's box no other leaf can contain r, so it is the list's first match as well.  Anything else (r
+                //        on a box face, a neighbour finer than the bins resolve) searches the list in order;
+                //  else: the list is searched in order, starting from its first entry which travels with the node's record.
+                // The path kernels (isotropic rays: coarse-to-fine crossings are common) use the table, the photon life cycle
+                // (rays leave the refined regions: almost every wall has a single neighbour) measured faster without it.
+                const int f0 = wall == 0 ? first[0] : wall == 1 ? first[1] : wall == 2 ? first[2] : wall == 3 ? first[3] : wall == 4 ? first[4] : first[5];
+                const unsigned wm = (hmeta >> (3 * wall)) & 7u;
+                int cand = f0;
+                bool strict = false;
+                if (HINT && (wm & 1u))
+                {
+                    const int a = wall < 2 ? 1 : 0, b = wall < 4 ? 2 : 1;
+                    const double pa = a == 1 ? y : x, pb = b == 2 ? z : y;
+                    const double la = a == 1 ? bx[1] : bx[0], ha = a == 1 ? bx[4] : bx[3], lb = b == 2 ? bx[2] : bx[1], hb = b == 2 ? bx[5] : bx[4];
+                    const int G = 2 << (wm >> 1);
+                    int off = 0;            // ids of the multi-neighbour walls before this one
+                    for (int v = 0; v < 5; v++) { const unsigned vm = (hmeta >> (3 * v)) & 7u; off += (v < wall && (vm & 1u)) ? (4 << (vm & 6u)) : 0; }
+                    const int ia = max(0, min(G - 1, (int)((float)G * (float)(pa - la) / (float)(ha - la))));
+                    const int ib = max(0, min(G - 1, (int)((float)G * (float)(pb - lb) / (float)(hb - lb))));
+                    cand = __ldg(g.nbrHint + 4 * (size_t)hbase + off + G * ia + ib);
+                    strict = true;
+                }
                 node = -1;
-                if (g.nbrRec)
+                if (cand >= 0)
                 {
-                    // expanded records: box, cell and the neighbour offsets of the candidate arrive in one 96-byte read.
-                    int q = beg;
-                    for (; q < end; q++)
+                    double w[12]; loadRec(g.nodeRec + cand, w);
+                    const bool ok = strict ? (x > w[0] && x < w[3] && y > w[1] && y < w[4] && z > w[2] && z < w[5]) : recContains(w, x, y, z);
+                    if (ok) { adopt(cand, w); haveAll = true; }
+                    else if (wm & 1u)
                     {
-                        double w[12]; loadRec(g.nbrRec + q, w);
-                        if (x >= w[0] && x <= w[3] && y >= w[1] && y <= w[4] && z >= w[2] && z <= w[5]) { adopt(w); haveAll = true; break; }
+                        // in list order (from the second entry when the first one has just been tested)
+                        const int beg = __ldg(g.nbrStart + 6 * (size_t)oldnode + wall), end = __ldg(g.nbrStart + 6 * (size_t)oldnode + wall + 1);
+                        for (int q = strict ? beg : beg + 1; q < end; q++)
+                        {
+                            const int c2 = __ldg(g.nbrIds + q);
+                            loadRec(g.nodeRec + c2, w);
+                            if (recContains(w, x, y, z)) { adopt(c2, w); haveAll = true; break; }
+                        }
                     }
-                    if (!haveAll) node = -1;
                 }
-                else for (int q = beg; q < end; q++)
-                {
-                    const int cand = __ldg(g.nbrIds + q);
-                    const double* cb = g.box + 6 * (size_t)cand;
-                    const double c0 = __ldg(cb), c1 = __ldg(cb + 1), c2 = __ldg(cb + 2), c3 = __ldg(cb + 3), c4 = __ldg(cb + 4), c5 = __ldg(cb + 5);
-                    if (x >= c0 && x <= c3 && y >= c1 && y <= c4 && z >= c2 && z <= c5)
-                    { node = cand; bx[0] = c0; bx[1] = c1; bx[2] = c2; bx[3] = c3; bx[4] = c4; bx[5] = c5; haveBox = true; break; }
-                }
-                if (node < 0) node = treeWhichNode(g, x, y, z);
+                if (node < 0) node = treeWhichNodeCold(g, x, y, z);
             }
             else node = treeWhichNode(g, x, y, z);
 
@@ -445,7 +474,7 @@ struct TreeWalker
             {
                 atomicAdd(&ctr->stuckEscaped, 1ull);
                 x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
-                node = treeWhichNode(g, x, y, z);
+                node = treeWhichNodeCold(g, x, y, z);
                 haveBox = false; haveAll = false;
                 if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
             }
@@ -539,35 +568,61 @@ __device__ __forceinline__ int cellIndex1(double v, double vmin, double vmax, in
     return max(0, min(n - 1, i));
 }
 
+// one node record: 96 bytes as three 256-bit reads
+struct AMeshRecWords
+{
+    double w[12];
+    __device__ __forceinline__ void load(const AMeshNodeRec* rec)
+    {
+        const double* rp = reinterpret_cast<const double*>(rec);
+#pragma unroll
+        for (int u = 0; u < 3; u++)
+            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[4 * u]), "=d"(w[4 * u + 1]), "=d"(w[4 * u + 2]), "=d"(w[4 * u + 3]) : "l"(rp + 4 * u));
+    }
+    __device__ __forceinline__ bool contains(double x, double y, double z) const { return x >= w[0] && x <= w[3] && y >= w[1] && y <= w[4] && z >= w[2] && z <= w[5]; }
+    __device__ __forceinline__ int lo(int i) const { return (int)(__double_as_longlong(w[i]) & 0xffffffffll); }
+    __device__ __forceinline__ int hi(int i) const { return (int)(__double_as_longlong(w[i]) >> 32); }
+    __device__ __forceinline__ int cell() const { return lo(6); }
+    __device__ __forceinline__ int child0() const { return hi(6); }
+    __device__ __forceinline__ int nx() const { return lo(7); }
+    __device__ __forceinline__ int ny() const { return hi(7); }
+    __device__ __forceinline__ int nz() const { return lo(8); }
+};
+
 // AdaptiveMeshNode::whichnode(Vec) from the root, AdaptiveMeshNode.cpp:132-142 (+ child :109-128).
 // Returns -1 when outside, -2 when the reference would throw "Can't locate the appropriate child node".
-__device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, double y, double z)
+// On success `rec` holds the record of the returned leaf (one dependent read per level: the child's record is both the
+// containment test of this level and the node of the next).
+__device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, double y, double z, AMeshRecWords& rec)
 {
     if (!boxContains(g.box, x, y, z)) return -1;
     int node = 0;
+    rec.load(g.nodeRec);
     int c0;
-    while ((c0 = __ldg(g.child0 + node)) >= 0)
+    while ((c0 = rec.child0()) >= 0)
     {
-        const double* b = g.box + 6 * (size_t)node;
-        int Nx = __ldg(g.nxyz + 3 * (size_t)node), Ny = __ldg(g.nxyz + 3 * (size_t)node + 1), Nz = __ldg(g.nxyz + 3 * (size_t)node + 2);
-        int i = cellIndex1(x, b[0], b[3], Nx);
-        int j = cellIndex1(y, b[1], b[4], Ny);
-        int k = cellIndex1(z, b[2], b[5], Nz);
+        const int Nx = rec.nx(), Ny = rec.ny(), Nz = rec.nz();
+        int i = cellIndex1(x, rec.w[0], rec.w[3], Nx);
+        int j = cellIndex1(y, rec.w[1], rec.w[4], Ny);
+        int k = cellIndex1(z, rec.w[2], rec.w[5], Nz);
         int child = c0 + (k * Ny + j) * Nx + i;
-        const double* cb = g.box + 6 * (size_t)child;
-        if (!boxContains(cb, x, y, z))
+        rec.load(g.nodeRec + child);
+        if (!rec.contains(x, y, z))
         {
-            if (x < cb[0]) i--; else if (x > cb[3]) i++;
-            if (y < cb[1]) j--; else if (y > cb[4]) j++;
-            if (z < cb[2]) k--; else if (z > cb[5]) k++;
+            if (x < rec.w[0]) i--; else if (x > rec.w[3]) i++;
+            if (y < rec.w[1]) j--; else if (y > rec.w[4]) j++;
+            if (z < rec.w[2]) k--; else if (z > rec.w[5]) k++;
             if (i < 0 || i >= Nx || j < 0 || j >= Ny || k < 0 || k >= Nz) return -2;
             child = c0 + (k * Ny + j) * Nx + i;
-            if (!boxContains(g.box + 6 * (size_t)child, x, y, z)) return -2;
+            rec.load(g.nodeRec + child);
+            if (!rec.contains(x, y, z)) return -2;
         }
         node = child;
     }
     return node;
 }
+__device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, double y, double z)
+{ AMeshRecWords rec; return ameshWhichNode(g, x, y, z, rec); }
 
 // AdaptiveMesh::path (AdaptiveMesh.cpp:297-367) one crossing at a time
 struct AMeshWalker
@@ -580,12 +635,12 @@ struct AMeshWalker
     int node, cellv;
     bool alive;
 
-    __device__ __forceinline__ void loadNode(const AMeshGrid& g, bool withBox)
+    // continue from the leaf whose record has been read
+    __device__ __forceinline__ void adopt(int id, const AMeshRecWords& r)
     {
-        if (withBox) { const double* b = g.box + 6 * (size_t)node; for (int c = 0; c < 6; c++) bx[c] = __ldg(b + c); }
-        cellv = __ldg(g.cell + node);
-        const int* w = g.wallNbr + 6 * (size_t)node;
-        for (int c = 0; c < 6; c++) wn[c] = __ldg(w + c);
+        for (int c = 0; c < 6; c++) bx[c] = r.w[c];
+        node = id; cellv = r.cell();
+        wn[0] = r.lo(9); wn[1] = r.hi(9); wn[2] = r.lo(10); wn[3] = r.hi(10); wn[4] = r.lo(11); wn[5] = r.hi(11);
     }
 
     __device__ __forceinline__ bool start(const AMeshGrid& g, Counters* ctr, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
@@ -594,9 +649,10 @@ struct AMeshWalker
         x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
         if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
         if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
-        node = ameshWhichNode(g, x, y, z);
-        if (node < 0) { if (node == -2) atomicAdd(&ctr->errors, 1ull); return false; }
-        loadNode(g, true);
+        AMeshRecWords rec;
+        const int id = ameshWhichNode(g, x, y, z, rec);
+        if (id < 0) { if (id == -2) atomicAdd(&ctr->errors, 1ull); return false; }
+        adopt(id, rec);
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
@@ -624,29 +680,26 @@ struct AMeshWalker
 
         const int oldnode = node;
         const int cand = wall == 0 ? wn[0] : wall == 1 ? wn[1] : wall == 2 ? wn[2] : wall == 3 ? wn[3] : wall == 4 ? wn[4] : wn[5];
-        bool haveBox = false;
-        node = -3;
+        AMeshRecWords rec;
+        int id = -3;
         if (cand >= 0)
         {
-            const double* cb = g.box + 6 * (size_t)cand;
-            const double c0 = __ldg(cb), c1 = __ldg(cb + 1), c2 = __ldg(cb + 2), c3 = __ldg(cb + 3), c4 = __ldg(cb + 4), c5 = __ldg(cb + 5);
-            if (x >= c0 && x <= c3 && y >= c1 && y <= c4 && z >= c2 && z <= c5)
-            { node = cand; bx[0] = c0; bx[1] = c1; bx[2] = c2; bx[3] = c3; bx[4] = c4; bx[5] = c5; haveBox = true; }
+            rec.load(g.nodeRec + cand);
+            if (rec.contains(x, y, z)) id = cand;
         }
-        if (node == -3) node = ameshWhichNode(g, x, y, z);
-        if (node == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
+        if (id == -3) id = ameshWhichNode(g, x, y, z, rec);
+        if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
 
-        if (node == oldnode)
+        if (id == oldnode)
         {
             atomicAdd(&ctr->stuckEscaped, 1ull);
             x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
-            node = ameshWhichNode(g, x, y, z);
-            haveBox = false;
-            if (node == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
-            if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
+            id = ameshWhichNode(g, x, y, z, rec);
+            if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
+            if (id == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); id = -1; }
         }
-        if (node < 0) alive = false;
-        else loadNode(g, !haveBox);
+        if (id < 0) { node = id; alive = false; }
+        else adopt(id, rec);
         return ds > 0;
     }
 };
@@ -776,7 +829,7 @@ struct VoroWalker
 {
     static constexpr int kStepUnroll = 1;
     double x, y, z, kx, ky, kz;
-    int mr;
+    int mr, rr;                 // current cell and the first slot of its crossing record
     int guard;
     bool alive;
 
@@ -788,41 +841,47 @@ struct VoroWalker
         if (!moveInside(g.ext, g.eps, x, y, z, kx, ky, kz, en)) return false;
         mr = voroCellIndex(g, x, y, z);
         if (mr < 0) return false;
+        rr = __ldg(g.nbrStart + mr) + mr;
         alive = true;
         return true;
     }
 
+    static __device__ __forceinline__ void loadSlot(const double* p, double (&w)[4])
+    { asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(p)); }
+
     __device__ __forceinline__ bool step(const VoroGrid& g, Counters* ctr, int& mseg, double& ds)
     {
         const double eps = g.eps;
-        const double* pr = g.particles + 3 * (size_t)mr;
-        const double prx = pr[0], pry = pr[1], prz = pr[2];
         double sq = SKG_DBL_MAX;
         const int NO_INDEX = -99;
-        int mq = NO_INDEX;
-        const int beg = __ldg(g.nbrStart + mr), end = __ldg(g.nbrStart + mr + 1);
-        // the neighbour loop of VoronoiMesh.cpp:777-828, four neighbours at a time: ids and particle positions of a
-        // group are fetched together (twelve independent loads in flight), then evaluated in list order so that the
-        // first smallest intersection still wins
-        for (int q0 = beg; q0 < end; q0 += 4)
+        int mq = NO_INDEX, rq = 0;
+        // the neighbour loop of VoronoiMesh.cpp:777-828 over the cell's crossing record (tables.h), four neighbours at a
+        // time: the header and the first group travel together, every slot is one 256-bit read, and the neighbours are
+        // evaluated in list order so that the first smallest intersection still wins
+        const double* R = g.rec + 4 * (size_t)rr;
+        double h[4], e[4][4];
+        loadSlot(R, h);
+#pragma unroll
+        for (int u = 0; u < 4; u++) loadSlot(R + 4 * (u + 1), e[u]);        // the table ends with 8 spare slots
+        const double prx = h[0], pry = h[1], prz = h[2];
+        const int cnt = (int)(__double_as_longlong(h[3]) & 0xffffffffll);
+        for (int q0 = 0; q0 < cnt; q0 += 4)
         {
-            int mi[4]; double px[4], py[4], pz[4];
-#pragma unroll
-            for (int u = 0; u < 4; u++) mi[u] = (q0 + u < end) ? __ldg(g.nbrIds + q0 + u) : -99;
-#pragma unroll
-            for (int u = 0; u < 4; u++)
+            if (q0)
             {
-                const double* pi = g.particles + 3 * (size_t)max(mi[u], 0);
-                px[u] = __ldg(pi); py[u] = __ldg(pi + 1); pz[u] = __ldg(pi + 2);
+#pragma unroll
+                for (int u = 0; u < 4; u++) loadSlot(R + 4 * (q0 + u + 1), e[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; u++)
             {
-                if (q0 + u >= end) break;
+                if (q0 + u >= cnt) break;
+                const long long tag = __double_as_longlong(e[u][3]);
+                const int mi = (int)(tag & 0xffffffffll);
                 double si = 0;
-                if (mi[u] >= 0)
+                if (mi >= 0)
                 {
-                    const double pix = px[u], piy = py[u], piz = pz[u];
+                    const double pix = e[u][0], piy = e[u][1], piz = e[u][2];
                     double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;        // n = pi - pr
                     double ndotk = nxv * kx + nyv * ky + nzv * kz;                   // Vec::dot(n,bfk)
                     if (ndotk > 0)
@@ -833,7 +892,7 @@ struct VoroWalker
                 }
                 else
                 {
-                    switch (mi[u])
+                    switch (mi)
                     {
                     case -1: si = (g.ext[0] - x) / kx; break;
                     case -2: si = (g.ext[3] - x) / kx; break;
@@ -844,7 +903,7 @@ struct VoroWalker
                     default: atomicAdd(&ctr->errors, 1ull); alive = false; return false;
                     }
                 }
-                if (si > 0 && si < sq) { sq = si; mq = mi[u]; }
+                if (si > 0 && si < sq) { sq = si; mq = mi; rq = (int)(tag >> 32); }
             }
         }
         if (mq == NO_INDEX)
@@ -853,12 +912,12 @@ struct VoroWalker
             x += kx * eps; y += ky * eps; z += kz * eps;
             mr = voroCellIndex(g, x, y, z);
             if (++guard > 1000000) { atomicAdd(&ctr->errors, 1ull); mr = -1; }
-            if (mr < 0) alive = false;
+            if (mr < 0) alive = false; else rr = __ldg(g.nbrStart + mr) + mr;
             return false;
         }
         mseg = mr; ds = sq;                     // sq > 0 by construction
         x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
-        mr = mq;
+        mr = mq; rr = rq;
         if (mr < 0) alive = false;
         return true;
     }

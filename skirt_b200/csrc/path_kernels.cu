@@ -41,7 +41,7 @@ struct RayJobBase
 {
     const double* r; const double* k;
     double rx, ry, rz, dx, dy, dz;
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr int kBatches = 1;
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH; static constexpr int kBatches = 1;
     __device__ __forceinline__ void loadRay(int i)
     { rx = r[3 * (size_t)i]; ry = r[3 * (size_t)i + 1]; rz = r[3 * (size_t)i + 2]; dx = k[3 * (size_t)i]; dy = k[3 * (size_t)i + 1]; dz = k[3 * (size_t)i + 2]; }
     __device__ __forceinline__ void collective(bool) {}
@@ -106,7 +106,7 @@ __device__ __forceinline__ double cellWord(int m) { return __longlong_as_double(
 struct RecordJobStaged : RayJobBase
 {
     static constexpr int kBatches = 1;              // the ring holds three periods
-    static constexpr bool kCartRegBorders = true, kCartTinySelect = false;       // the record kernel is bound by the load/store pipe
+    static constexpr bool kCartRegBorders = true, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH;       // the record kernel is bound by the load/store pipe
     static constexpr unsigned RHO_OFF = SKG_RING * 32 * 8, M_OFF = 2 * SKG_RING * 32 * 8;
     static constexpr size_t bytesPerWarp() { return (size_t)SKG_RING * 32 * (8 + 8 + 4); }
 

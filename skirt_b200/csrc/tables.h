@@ -20,15 +20,18 @@ struct CartGrid
 // doubles of shared memory taken by the staged borders (three arrays with one pad element on either side)
 #define SKG_CART_SMEM_DOUBLES(c) ((size_t)((c).Nx + (c).Ny + (c).Nz + 9))
 
-// one entry of a tree node's neighbour list, self-contained: everything the walker needs to continue from that
-// neighbour (its box, cell number and the offsets of ITS six neighbour lists), so that a crossing costs a single
-// dependent memory round trip instead of id -> box -> offsets
-struct __align__(32) TreeNbrRec
+// everything the walker needs to continue from a tree node, in one 96-byte record per NODE (three 256-bit reads): its box,
+// cell number, the first neighbour of each wall (the common case is a single neighbour per wall) and where the rest of its
+// neighbour lists start.  A node table stays resident in L2 (96 B x N; the lists expanded per neighbour did not), and a
+// crossing into a single-neighbour wall costs one dependent L2 round trip.
+struct __align__(32) TreeNodeRec
 {
     double box[6];
-    int id, cell;
-    int nb[7];
-    int pad[3];
+    int cell;
+    int hbase;                  // nbrHint offset / 4 of the node's first wall-bin block
+    unsigned hmeta; int pad0;   // per wall w, bits 3w..3w+2: bit 0 = the wall has several neighbours, bits 1-2 = lg with G = 2 << lg
+    int first[6];               // first neighbour of each wall, -1 when the list is empty
+    int pad1[2];
 };
 
 struct TreeGrid
@@ -37,16 +40,29 @@ struct TreeGrid
     const int* child0; const int* parent; const int* cell; const int* dir;
     const int* nbrStart; const int* nbrIds;
     const int* cellNode;            // leaf node of every cell (TreeDustGrid::getnode, for randomPositionInCell)
-    const TreeNbrRec* nbrRec;       // expanded neighbour lists (same order as nbrIds), or null
+    const TreeNodeRec* nodeRec;     // per-node records for the Neighbor search, or null
+    const int* nbrHint;             // per multi-neighbour wall, G x G ids: the neighbour covering the centre of each wall bin (a hint: the walker verifies it);
+                                    // the blocks of a node follow each other in wall order from 4 hbase
     const int* lookup;              // [G^3] deepest node whose box contains the whole lookup cell (entry point of root descents)
     int lookupG; double lookupInv[3];
     int N, kind, search;
     double eps;
 };
 
+// one adaptive mesh node in 96 bytes (three 256-bit reads): what a crossing needs from the neighbour beyond a wall (box,
+// cell, its own wall neighbours) and what a descent needs from an internal node (box, child grid, first child)
+struct __align__(32) AMeshNodeRec
+{
+    double box[6];
+    int cell, child0;
+    int nx, ny, nz; int pad;
+    int wallNbr[6];
+};
+
 struct AMeshGrid
 {
     const double* box; const int* nxyz; const int* child0; const int* cell; const int* wallNbr;
+    const AMeshNodeRec* nodeRec;
     const int* cellNode;            // leaf node of every cell
     int N;
     double eps;
@@ -59,6 +75,10 @@ struct VoroGrid
     const int* blkStart; const int* blkIds; const int* blkTree;
     const int* kdM; const int* kdAxis; const int* kdUp; const int* kdLeft; const int* kdRight;
     const double* cellBox;          // [6N] xmin,ymin,zmin,xmax,ymax,zmax
+    // crossing records, 32-byte slots: cell m owns slots [nbrStart[m] + m, nbrStart[m+1] + m + 1): a header {particle of m,
+    // (neighbour count, 0)} followed by one slot per neighbour in list order {particle of the neighbour, (id, first slot of
+    // the neighbour's own block)} -- a crossing reads one contiguous block instead of ids -> particle positions
+    const double* rec;
     double ext[6];                  // xmin,ymin,zmin,xmax,ymax,zmax
     double eps;
     int N, nb;

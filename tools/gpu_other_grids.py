@@ -41,8 +41,14 @@ def bench(name, S, packages=2e6, nrays=1 << 21):
 
 mk = lambda spec, **kw: sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw)
 thr = os.cpu_count() or 1
-bench("octtree L7 neighbor", mk(common.spec_grid("octtree", search=1, minlevel=2, maxlevel=7, massfrac=2e-6, threads=thr)))
-#bench("octtree L7 bookkeeping", mk(common.spec_grid("octtree", search=2, minlevel=2, maxlevel=7, massfrac=2e-6, threads=thr)))
-bench("bintree L18 neighbor", mk(common.spec_grid("bintree", search=1, minlevel=6, maxlevel=18, massfrac=4e-6, threads=thr)))
-bench("amesh depth5", mk(common.spec_grid("amesh", threads=thr), amesh=common.make_amesh(root=(8, 8, 8), max_depth=5, frac=2e-5)))
-bench("voronoi 1e5", mk(common.spec_grid("voronoi", threads=thr), particles=common.voronoi_particles(100000)))
+which = os.environ.get("SKG_GRIDS", "oct,bin,amesh,voronoi").split(",")
+if "oct" in which:
+    bench("octtree L7 neighbor", mk(common.spec_grid("octtree", search=1, minlevel=2, maxlevel=7, massfrac=2e-6, threads=thr)))
+if "oct8" in which:
+    bench("octtree L8 neighbor", mk(common.spec_grid("octtree", search=1, minlevel=2, maxlevel=8, massfrac=2e-7, threads=thr)))
+if "bin" in which:
+    bench("bintree L18 neighbor", mk(common.spec_grid("bintree", search=1, minlevel=6, maxlevel=18, massfrac=4e-6, threads=thr)))
+if "amesh" in which:
+    bench("amesh depth5", mk(common.spec_grid("amesh", threads=thr), amesh=common.make_amesh(root=(8, 8, 8), max_depth=5, frac=2e-5)))
+if "voronoi" in which:
+    bench("voronoi 1e5", mk(common.spec_grid("voronoi", threads=thr), particles=common.voronoi_particles(100000)))
