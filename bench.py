@@ -287,7 +287,7 @@ def main_engine(args):
     achieved = alg_bytes / (absorb_ms * 1e-3) / 1e9
     # DRAM traffic of the same kernel over one phase of this workload, from the committed ncu pass (profiles/)
     traffic = None
-    tfile = os.path.join(ROOT, "profiles", "r01_v5_absorbStage_dram_traffic.json")
+    tfile = os.path.join(ROOT, "profiles", "r01_v6_absorbStage_dram_traffic.json")
     if os.path.exists(tfile) and args.packages == 2e6 and args.nlambda == 50 and args.grid == 100:
         t_ = json.load(open(tfile)); traffic = t_["dram_bytes_read"] + t_["dram_bytes_write"]
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps, "warmup": args.warmup,
@@ -299,7 +299,7 @@ def main_engine(args):
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
             "roofline": {"bound": "hbm", "kernel": "absorbStage<GRID_CART> (dominant kernel of the phase: scatter + traverse + absorb + terminate/sample)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_note": "DRAM bytes of all absorbStage launches of one phase (ncu, profiles/r01_v5_absorbStage_dram_traffic.json): far BELOW the algorithmic bytes because the density table and the wavelength-major Labs slices in flight stay L2-resident",
+                         "traffic_note": "DRAM bytes of all absorbStage launches of one phase (ncu, profiles/r01_v6_absorbStage_dram_traffic.json): far BELOW the algorithmic bytes because the density table and the wavelength-major Labs slices in flight stay L2-resident",
                          "peak_source": peak_src, "bytes_per_step": alg_bytes, "kernel_ms_per_step": absorb_ms,
                          "launches_per_step": int(st["iterations"]), "share_of_step": absorb_ms / kernel_ms,
                          "absorbing_packet_steps_per_s": st["absorbSegments"] / (absorb_ms * 1e-3),
@@ -312,9 +312,9 @@ def main_engine(args):
         tr = traversal_leg(e, torch, ext, ncomp, args.rays)
         tr["frac"] = tr["gbs"] / peak; tr["peak"] = peak
         tr["kernel"] = "pathFillKernel<GRID_CART> (batched DustGrid::path + fillOpticalDepth, CSR path records)"
-        # ncu --set full of this kernel on 1 Mi rays (profiles/r01_v3_path_kernels_ncu.txt): 1.987 GB written + 0.112 GB read
-        # for 50 281 330 packet-steps = 41.7 B per step, against 44 B algorithmic (40 B of it written)
-        tr["traffic"] = 41.7 * tr["packet_steps"]
+        # ncu --set full of this kernel on 1 Mi rays (profiles/r01_v6_path_kernels_ncu.txt): 1.995 GB written + 0.118 GB read
+        # for 50 281 330 packet-steps = 42.0 B per step, against 44 B algorithmic (40 B of it written)
+        tr["traffic"] = 42.0 * tr["packet_steps"]
         line["traversal_roofline"] = tr
     if rank == 0 and world == 1 and not args.skip_cpu:
         threads = os.cpu_count() or 1
