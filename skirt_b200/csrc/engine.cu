@@ -127,7 +127,7 @@ int skg_grid_cartesian(skg_engine* eh, const double* xv, int Nx, const double* y
         for (int i = 0; i < Nz; i++) if (!(zv[i] < zv[i+1])) throw Error("z borders must be strictly ascending");
         e.freeGrid();
         e.cart.xv = up(e, xv, Nx + 1); e.cart.yv = up(e, yv, Ny + 1); e.cart.zv = up(e, zv, Nz + 1);
-        e.cart.Nx = Nx; e.cart.Ny = Ny; e.cart.Nz = Nz; e.cart.sx = e.cart.sy = e.cart.sz = 0; e.cart.staged = 0;
+        e.cart.Nx = Nx; e.cart.Ny = Ny; e.cart.Nz = Nz; e.cart.sx = e.cart.sy = e.cart.sz = 0; e.cart.staged = 0; e.cart.rhoAhead = nullptr; e.cart.rhoAheadStride = 0;
         // BoxDustGrid extent: for every Mesh of the reference mesh[0]=0 and mesh[N]=1, so that the borders'
         // end points equal the extent (CartesianDustGrid.cpp:34-36)
         e.cart.ext[0] = xv[0]; e.cart.ext[1] = xv[Nx]; e.cart.ext[2] = yv[0]; e.cart.ext[3] = yv[Ny]; e.cart.ext[4] = zv[0]; e.cart.ext[5] = zv[Nz];

@@ -93,6 +93,8 @@ __device__ __forceinline__ int cartWhichCell(const CartGrid& g, double x, double
 }
 
 // 8-byte load from the shared window (the staged Cartesian borders): an explicit LDS instead of a generic load
+// pulls the line holding *p into L1 (no register, no scoreboard)
+__device__ __forceinline__ void prefetchL1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 __device__ __forceinline__ double ldsF64(unsigned addr)
 { double v; asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v; }
 
@@ -112,7 +114,7 @@ __device__ __forceinline__ double ldsF64(unsigned addr)
 // TINYSEL: how direction components with |k| <= 1e-15 are handled: as unconditional selects (peel-off rays towards
 // an observer at azimuth 0/90/... have an exactly zero component in EVERY lane) or as a branch that random rays
 // essentially never take.
-template<bool REGB, bool TINYSEL> struct CartWalkerT
+template<bool REGB, bool TINYSEL, bool AHEAD = false> struct CartWalkerT
 {
     static constexpr int kStepUnroll = 4;       // crossings of a batch unrolled in the scheduler (wavefront.cuh): the step is ~100 instructions
     double x, y, z, kx, ky, kz;
@@ -230,6 +232,9 @@ template<bool REGB, bool TINYSEL> struct CartWalkerT
         if (bz) { oz += stz; m += dmz; if (REGB) zE = ldsF64(g.sz + oz); }
         // left the grid: the offset stepped below 0 (wraps) or beyond the last border
         alive = (unsigned)ox <= 8u * g.Nx && (unsigned)oy <= 8u * g.Ny && (unsigned)oz <= 8u * g.Nz;
+        // the cell entered now is the one whose density the NEXT crossing gathers (after its three divisions): start pulling
+        // it into L1 here, half a crossing earlier than the gather itself (no register, no scoreboard)
+        if (AHEAD && g.rhoAhead && alive) prefetchL1(g.rhoAhead + (size_t)m * g.rhoAheadStride);
         return ds > 0;
     }
 };

@@ -41,7 +41,7 @@ struct RayJobBase
 {
     const double* r; const double* k;
     double rx, ry, rz, dx, dy, dz;
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH; static constexpr int kBatches = 1;
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH, kCartRhoAhead = false; static constexpr int kBatches = 1;
     __device__ __forceinline__ void loadRay(int i)
     { rx = r[3 * (size_t)i]; ry = r[3 * (size_t)i + 1]; rz = r[3 * (size_t)i + 2]; dx = k[3 * (size_t)i]; dy = k[3 * (size_t)i + 1]; dz = k[3 * (size_t)i + 2]; }
     __device__ __forceinline__ void collective(bool) {}
@@ -106,7 +106,7 @@ __device__ __forceinline__ double cellWord(int m) { return __longlong_as_double(
 struct RecordJobStaged : RayJobBase
 {
     static constexpr int kBatches = 1;              // the ring holds three periods
-    static constexpr bool kCartRegBorders = true, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH;       // the record kernel is bound by the load/store pipe
+    static constexpr bool kCartRegBorders = true, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH, kCartRhoAhead = true;       // the record kernel is bound by the load/store pipe
     static constexpr unsigned RHO_OFF = SKG_RING * 32 * 8, M_OFF = 2 * SKG_RING * 32 * 8;
     static constexpr size_t bytesPerWarp() { return (size_t)SKG_RING * 32 * (8 + 8 + 4); }
 
@@ -197,6 +197,12 @@ struct RecordJobStaged : RayJobBase
     __device__ __forceinline__ void collective(bool) {}
 };
 
+// 1: the record kernel really pulls the next cell's density into L1 at the end of a crossing.  Measured slower (2.94 ms against
+// 2.80 ms for 4 Mi rays), so the table pointer stays null; the guarded prefetch is still compiled into the walker
+// (kCartRhoAhead) because with that branch in the crossing ptxas allocates the 96 registers without spilling (2.58 ms).
+#ifndef SKG_FILL_RHO_AHEAD
+#define SKG_FILL_RHO_AHEAD 0
+#endif
 template<int KIND>
 __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem, int refill,
                                                       int n, const double* __restrict__ r, const double* __restrict__ k,
@@ -205,7 +211,13 @@ __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ Gr
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
-    if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
+    if (KIND == GRID_CART)
+    {
+        cart = stageCart(G.cart, smem, cartSmem);
+#if SKG_FILL_RHO_AHEAD
+        if (ell && med.Ncomp == 1) { cart.rhoAhead = med.rho; cart.rhoAheadStride = 1; }     // the density the ring's copy fetches a crossing later
+#endif
+    }
     size_t skip = (KIND == GRID_CART && cartSmem) ? SKG_CART_SMEM_DOUBLES(G.cart) : 0;
     RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
     job.seg = segments;
