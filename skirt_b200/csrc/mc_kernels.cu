@@ -23,6 +23,9 @@
 // is a chain of dependent fp64 operations, so warps in flight are what hides its latency -- measured on B200:
 // absorb 205 / 176 / 163 / 187 ms per C2 phase at 3 / 4 / 5 / 6 CTAs, peel 109 / 90 / 102 (spills at 5).  The walkers of the
 // hierarchical / unstructured grids carry more state: 4 CTAs (no spills)
+#ifndef SKG_MC_RHO_AHEAD
+#define SKG_MC_RHO_AHEAD false       // the guarded next-cell prefetch of the Cartesian walker compiled into the stage kernels
+#endif
 #ifndef SKG_MC_BATCHES
 #define SKG_MC_BATCHES 1     // batches of SKG_PERIOD crossings between two warp votes in the stage kernels
 #endif
@@ -260,7 +263,7 @@ static __device__ __noinline__ int detectFull(const InstrDev& I, int Nlambda, do
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
 template<int KIND, bool SINGLE> struct PeelJob
 {
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = true; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = false; static constexpr int kBatches = SKG_MC_BATCHES;
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = true; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
     double Lw, tau; KappaRho kr; int ell, grp;
@@ -373,7 +376,7 @@ __global__ void __launch_bounds__(128, SKG_PEEL_MINBLOCKS) peelStage(const __gri
 // scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
 template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
 {
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = false; static constexpr int kBatches = SKG_MC_BATCHES;
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     int* counts;
     double rx, ry, rz, dx, dy, dz;
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS 
 // DustGridPath::pathlength (DustGridPath.cpp:162-173) evaluated on the fly + PhotonPackage::propagate (PhotonPackage.cpp:93-96)
 template<int KIND, bool SINGLE> struct PropagateJob
 {
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = false; static constexpr int kBatches = SKG_MC_BATCHES;
+    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
     const McDev& P;
     double rx, ry, rz, dx, dy, dz;
     KappaRho kr; double target, sPrev, tauPrev, result; bool found; int slot;
