@@ -151,3 +151,36 @@ def test_large_batch_offsets_are_consistent(engine):
     with np.errstate(divide="ignore"):
         t = np.where(k > 0, (hi - r) / k, np.where(k < 0, (lo - r) / k, np.inf)).min(axis=1)
     np.testing.assert_allclose(got["s"][off[1:] - 1], t, rtol=1e-8)      # the tree walker adds eps = 1e-12 x diagonal per crossing
+
+
+@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi"])
+def test_deep_grids_against_the_reference(engine, kind):
+    """grids deep enough for every part of the per-node crossing records -- walls with up to 16 neighbours, edge-touching ones included (wall-bin
+    tables of several resolutions), root descents through several levels, Voronoi cells with up to 30+ neighbours --
+    built by the reference's own grid classes; 40 000 isotropic rays plus rays along the grid planes, against the
+    reference's DustGrid::path() + fillOpticalDepth bit for bit (oracle/_ref travels to the GPU box)"""
+    from oracle import skirtref as sr
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    import os
+    kw = {}
+    if kind == "amesh":
+        kw["amesh"] = common.make_amesh(root=(4, 4, 4), max_depth=4, frac=1e-4)
+    if kind == "voronoi":
+        kw["particles"] = common.voronoi_particles(20000)
+    spec = common.spec_grid(kind, search=1, minlevel=2, maxlevel=7 if kind == "octtree" else 16, massfrac=2e-5, threads=os.cpu_count() or 1)
+    S = sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw).setup()
+    tables, medium = S.grid_tables(), S.medium()
+    engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    r, k = common.rays(40000, common.C1_BOX, 515)
+    # rays inside the planes x = 0 / z = 0 and along the axes: positions on cell faces, |k_a| <= 1e-15 components
+    rng = np.random.default_rng(8)
+    r2 = (rng.random((2000, 3)) - 0.5) * (np.asarray(common.C1_BOX)[1::2] - np.asarray(common.C1_BOX)[0::2]); k2 = rng.normal(size=(2000, 3))
+    r2[:700, 0] = 0.0; k2[:700, 0] = 0.0; r2[700:1400, 2] = 0.0; k2[700:1400, 2] = 0.0; k2[1400:, 1:] = 0.0
+    k2 /= np.linalg.norm(k2, axis=1, keepdims=True)
+    r = np.concatenate([r, r2]); k = np.concatenate([k, k2])
+    got = engine.path_batch(r, k, ell=0)
+    ref = S.path_batch(r, k, ell=0, nthreads=os.cpu_count() or 1)
+    assert len(ref["m"]) > 4 * len(r)
+    assert common.paths_bit_identical(got, ref), kind
+    assert engine.stuck_counts()[1] == 0
