@@ -222,7 +222,12 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
                         int lg = 0; while (lg < 3 && (2 << lg) < ratio * 0.99) lg++;
                         const int G = 2 << lg;
                         if (hints.size() / 4 >= 2000000000u) throw Error("too many multi-neighbour walls");
-                        r.hmeta |= (1u | ((unsigned)lg << 1)) << (3 * w);
+                        // does the first neighbour (the lists are sorted by decreasing overlap, TreeNode::sortneighbors) cover at
+                        // least half of the wall?  then it is tested first, like a single neighbour
+                        const double* c0 = box + 6 * (size_t)nbrIds[beg];
+                        const double oa = std::min(nb[a + 3], c0[a + 3]) - std::max(nb[a], c0[a]), ob = std::min(nb[b + 3], c0[b + 3]) - std::max(nb[b], c0[b]);
+                        const bool dominant = oa > 0 && ob > 0 && oa * ob >= 0.5 * (nb[a + 3] - nb[a]) * (nb[b + 3] - nb[b]);
+                        r.hmeta |= (1u | ((unsigned)lg << 1) | (dominant ? 8u : 0u)) << (5 * w);
                         for (int ia = 0; ia < G; ia++) for (int ib = 0; ib < G; ib++)
                         {
                             const double ca = nb[a] + (nb[a + 3] - nb[a]) * (ia + 0.5) / G, cb = nb[b] + (nb[b + 3] - nb[b]) * (ib + 0.5) / G;
