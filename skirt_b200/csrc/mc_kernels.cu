@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(128, SKG_PEEL_MINBLOCKS) peelStage(const __gri
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
     PeelJob<KIND, SINGLE> job(G, cart, P);
-    runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, min(28, 2 * P.refill));
+    runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, P.peelRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
 }
 
@@ -1041,6 +1041,11 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     P.med = e.med; if (!e.med.rho) { P.med.Nlambda = Nlambda; P.med.Ncomp = 0; }
     P.phase = phase; P.rngKind = (unsigned)phase;
     P.refill = 14; if (const char* v = getenv("SKG_REFILL")) P.refill = std::max(1, std::min(32, atoi(v)));
+    // measured (profiles/README.md): on the Cartesian grid the peel-off stage is fastest when a warp waits for 28 parked lanes
+    // (its crossings are issue-bound), on the tree / adaptive-mesh grids at 16 and on the Voronoi grid at 8 (long crossings:
+    // more walking lanes per step cost nothing, idle ones do)
+    P.peelRefill = e.gridKind == GRID_CART ? std::min(28, 2 * P.refill) : (e.gridKind == GRID_VORO ? 8 : 16);
+    if (const char* v = getenv("SKG_PEEL_REFILL")) P.peelRefill = std::max(1, std::min(32, atoi(v)));
     P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
     P.L = e.lumDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>();
     P.Ltot = phase == SKG_PHASE_STELLAR ? e.lumTotDev.as<double>() : e.dustLtot.as<double>();
