@@ -343,7 +343,7 @@ def main():
     ap.add_argument("--packages", type=float, default=2e6, help="packets per wavelength per GPU (C2: 2e6 x 50 = 1e8)")
     ap.add_argument("--nlambda", type=int, default=50)
     ap.add_argument("--grid", type=int, default=100)
-    ap.add_argument("--rays", type=int, default=1 << 22, help="rays of the traversal-roofline leg")
+    ap.add_argument("--rays", type=int, default=1 << 24, help="rays of the traversal-roofline leg (SURVEY.md 8d: 2^24; the records take 40 B x ~48 crossings per ray = 32 GB)")
     ap.add_argument("--ref-packages", type=float, default=None, help="packets per wavelength of the bounded CPU sample")
     ap.add_argument("--skip-traversal", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
