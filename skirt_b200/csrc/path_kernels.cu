@@ -263,11 +263,12 @@ static LaunchCfg cfgFor(Engine& e, int64_t n)
     LaunchCfg c;
     int64_t want = (n + 127) / 128;
     int64_t cap = (int64_t)e.smCount * 16;
+    if (const char* v = getenv("SKG_PATH_BLOCKS_PER_SM")) cap = (int64_t)e.smCount * std::max(1, std::min(64, atoi(v)));
     c.blocks = (int)std::max<int64_t>(1, std::min(want, cap));
     c.smem = 0; c.cartSmem = false;
     // idle lanes of a warp at which it draws new rays (runJobs): entry + point location are cheap on the Cartesian grid,
     // a chain of dependent reads on the hierarchical ones
-    c.refill = 8; if (const char* v = getenv("SKG_PATH_REFILL")) c.refill = std::max(1, std::min(32, atoi(v)));
+    c.refill = e.gridKind == GRID_CART ? 12 : 8; if (const char* v = getenv("SKG_PATH_REFILL")) c.refill = std::max(1, std::min(32, atoi(v)));
     if (n > 2147483647LL) throw Error("at most 2^31-1 rays per call");
     e.scratchWork.ensure(sizeof(int)); c.work = e.scratchWork.as<int>();
     SKG_CUDA(cudaMemsetAsync(c.work, 0, sizeof(int), e.stream));
