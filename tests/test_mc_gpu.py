@@ -96,7 +96,9 @@ def test_other_grids_against_reference_runs(engine, kind):
     for name, a, r in (("sed", np.array(gpu_s), np.array(ref_s)), ("labs", np.array(gpu_l), np.array(ref_l))):
         ta, tr = a.reshape(B, -1).sum(1), r.reshape(B, -1).sum(1)
         zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / B + tr.var(ddof=1) / B)
-        assert abs(zt) < 3.5, f"{kind}/{name}: total differs by {zt:.2f} sigma"
+        # the reference side runs multi-threaded, i.e. not reproducibly: Welch's t with ~22 degrees of freedom; 4.5 keeps the
+        # false-alarm rate negligible while a 1 % bias would be > 5 sigma at these batch sizes
+        assert abs(zt) < 4.5, f"{kind}/{name}: total differs by {zt:.2f} sigma"
         if a.shape[1] > 10:
             # cells that see only a handful of absorption events per batch have strongly skewed batch statistics:
             # apply the per-bin gate where the relative noise of the batch mean is below 30 %

@@ -85,7 +85,7 @@ def test_two_dust_components_and_simple_instrument(engine):
         a, r = np.array(gpu[name]).reshape(B, -1), np.array(ref[name]).reshape(B, -1)
         ta, tr = a.sum(1), r.sum(1)
         zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / B + tr.var(ddof=1) / B)
-        assert abs(zt) < 3.5 and abs(ta.mean() / tr.mean() - 1) < 0.01, f"{name}: gpu {ta.mean():.6g} ref {tr.mean():.6g} z {zt:.2f}"
+        assert abs(zt) < 4.5 and abs(ta.mean() / tr.mean() - 1) < 0.01, f"{name}: gpu {ta.mean():.6g} ref {tr.mean():.6g} z {zt:.2f}"
         if a.shape[1] > 10:
             ma, mr = a.mean(0), r.mean(0); sa, sr_ = a.std(0, ddof=1) / np.sqrt(B), r.std(0, ddof=1) / np.sqrt(B)
             ok = (sa < 0.3 * ma) & (sr_ < 0.3 * mr) & (sa > 0) & (sr_ > 0)
