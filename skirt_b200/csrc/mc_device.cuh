@@ -80,6 +80,7 @@ struct McDev
     const double* dustCdf;  // [Nlambda*(Ncells+1)] normalised cumulative distributions
     double dustBias;        // PanDustSystem::emissionBias
     int refill;             // lanes of a warp that must be parked before they finish and draw new work together
+    int propRefill;         // the same for the propagate stage
     int peelRefill;         // the same for the peel-off stage (one item per packet and observer direction: cheap to begin)
 };
 

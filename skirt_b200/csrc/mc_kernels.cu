@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PROP_MINBLOCKS : 
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
     PropagateJob<KIND, SINGLE> job(P);
-    runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.refill);
+    runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.propRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
 }
 
@@ -1043,11 +1043,15 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     McDev P{};
     P.med = e.med; if (!e.med.rho) { P.med.Nlambda = Nlambda; P.med.Ncomp = 0; }
     P.phase = phase; P.rngKind = (unsigned)phase;
-    P.refill = 14; if (const char* v = getenv("SKG_REFILL")) P.refill = std::max(1, std::min(32, atoi(v)));
+    // parked lanes at which a warp refills, measured per stage (profiles/README.md): absorb 24 / propagate 18 / peel 28 on the
+    // Cartesian grid (issue-bound crossings: a refill interrupts every walking lane of the warp), 14 / 14 / 16 on the tree and
+    // adaptive-mesh grids, 14 / 14 / 8 on the Voronoi grid
+    P.refill = e.gridKind == GRID_CART ? 24 : 14; P.propRefill = e.gridKind == GRID_CART ? 18 : 14;
+    if (const char* v = getenv("SKG_REFILL")) P.refill = P.propRefill = std::max(1, std::min(32, atoi(v)));
     // measured (profiles/README.md): on the Cartesian grid the peel-off stage is fastest when a warp waits for 28 parked lanes
     // (its crossings are issue-bound), on the tree / adaptive-mesh grids at 16 and on the Voronoi grid at 8 (long crossings:
     // more walking lanes per step cost nothing, idle ones do)
-    P.peelRefill = e.gridKind == GRID_CART ? std::min(28, 2 * P.refill) : (e.gridKind == GRID_VORO ? 8 : 16);
+    P.peelRefill = e.gridKind == GRID_CART ? 28 : (e.gridKind == GRID_VORO ? 8 : 16);
     if (const char* v = getenv("SKG_PEEL_REFILL")) P.peelRefill = std::max(1, std::min(32, atoi(v)));
     P.sources = e.sourcesDev.as<SourceDev>(); P.Nsources = e.Nsources;
     P.L = e.lumDev.as<double>(); P.Lcdf = e.lumCdfDev.as<double>();
