@@ -264,6 +264,7 @@ int skg_grid_amesh(skg_engine* eh, int N, const double* box, const int* nxyz, co
         for (int l = 0; l < N; l++)
         {
             if (cell[l] >= 0) ncells++;
+            for (int w = 0; w < 6; w++) if (wallNbr[6 * (size_t)l + w] >= N) throw Error("invalid wall neighbour in adaptive mesh tables");
             if (child0[l] >= 0)
             {
                 int64_t nc = (int64_t)nxyz[3*l] * nxyz[3*l+1] * nxyz[3*l+2];
@@ -324,7 +325,7 @@ int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* 
                 for (int q = 0; q < cnt; q++)
                 {
                     const int id = nbrIds[beg + q];
-                    if (id >= N) throw Error("invalid neighbour id in Voronoi tables");
+                    if (id >= N || id < -6) throw Error("invalid neighbour id in Voronoi tables");
                     double* s4 = h + 4 * (size_t)(q + 1);
                     if (id >= 0) { s4[0] = particles[3 * (size_t)id]; s4[1] = particles[3 * (size_t)id + 1]; s4[2] = particles[3 * (size_t)id + 2]; s4[3] = pack(id, nbrStart[id] + id); }
                     else s4[3] = pack(id, 0);

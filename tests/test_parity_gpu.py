@@ -59,6 +59,12 @@ def test_empty_and_error_paths(engine):
         engine.path_batch(r, k, ell=5)
     with pytest.raises(sk.EngineError):
         engine.grid_cartesian([0.0, 1.0, 0.5], [0.0, 1.0], [0.0, 1.0])
+    # corrupt neighbour tables are rejected at set-up instead of being followed out of bounds by the walkers
+    for name, key in (("octtree_s1", "nbrIds"), ("amesh", "wallNbr"), ("voronoi", "nbrIds")):
+        tables, _, _ = common.load_golden(name)
+        bad = dict(tables); a = np.array(bad[key]).copy(); a.flat[a.size // 2] = 2 ** 30; bad[key] = a
+        with pytest.raises(sk.EngineError, match="neighbour"):
+            engine.set_grid(bad)
 
 
 def test_full_size_properties(engine):
