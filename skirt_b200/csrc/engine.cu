@@ -163,7 +163,7 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
         // whose (closed) box contains the whole cell.  TreeNode::whichnode descends from there instead of from the root
         // when the point lies strictly inside that node's box -- the same leaf, several levels fewer dependent reads.
         {
-            int G = N > 4096 ? 32 : (N > 64 ? 8 : 1);
+            int G = N > 4096 ? 64 : (N > 64 ? 8 : 1);
             if (const char* v = getenv("SKG_TREE_LATTICE")) G = std::max(1, std::min(256, atoi(v)));
             std::vector<int> lut((size_t)G * G * G, 0);
             const double* rb = box;
