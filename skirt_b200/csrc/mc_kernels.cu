@@ -32,6 +32,9 @@
 #ifndef SKG_MC_BATCHES
 #define SKG_MC_BATCHES 1     // batches of SKG_PERIOD crossings between two warp votes in the stage kernels
 #endif
+#ifndef SKG_OTHER_MINBLOCKS
+#define SKG_OTHER_MINBLOCKS 4     // resident CTAs per SM the stage kernels are compiled for on the tree / adaptive mesh / Voronoi grids
+#endif
 #ifndef SKG_PEEL_MINBLOCKS
 #define SKG_PEEL_MINBLOCKS 4
 #endif
@@ -365,7 +368,7 @@ template<int KIND, bool SINGLE> struct PeelJob
 };
 
 template<int KIND, bool SINGLE>
-__global__ void __launch_bounds__(128, SKG_PEEL_MINBLOCKS) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PEEL_MINBLOCKS : SKG_OTHER_MINBLOCKS) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                  int nAlive, int* work)
 {
     extern __shared__ double smem[];
@@ -541,7 +544,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
 };
 
 template<int KIND, bool SINGLE, bool STORE>
-__global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS : 4) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS : SKG_OTHER_MINBLOCKS) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                    int nAlive, int* __restrict__ counts, int* work)
 {
     extern __shared__ double smem[];
@@ -615,7 +618,7 @@ template<int KIND, bool SINGLE> struct PropagateJob
 };
 
 template<int KIND, bool SINGLE>
-__global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PROP_MINBLOCKS : 4) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
+__global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PROP_MINBLOCKS : SKG_OTHER_MINBLOCKS) propagateStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                       int nSurv, int* work)
 {
     extern __shared__ double smem[];
