@@ -446,7 +446,17 @@ int skr_set_particles(void* h, const double* xyz, int n)
 int skr_set_amesh(void* h, const int* nxyz, const double* val, int n)
 { Sim* S = (Sim*)h; if (!S->afile) return 1; S->afile->nxyz.assign(nxyz, nxyz+3*(size_t)n); S->afile->val.assign(val, val+n); return 0; }
 
-int skr_setup(void* h) { Sim* S = (Sim*)h; return guarded([&]{ S->mc->setup(); }); }
+int skr_setup(void* h)
+{
+    Sim* S = (Sim*)h;
+    return guarded([&]{
+        S->mc->setup();
+        // The reference never assigns AdaptiveMeshDustGrid::_random (initialised to 0 in AdaptiveMeshDustGrid.cpp:19 and used
+        // by randomPositionInCell, :86-89), so its dust emission phases crash on adaptive mesh grids.  The harness supplies the
+        // simulation's Random instance -- what the class evidently intends -- so that those phases can serve as a reference.
+        if (AdaptiveMeshDustGrid* ag = dynamic_cast<AdaptiveMeshDustGrid*>(S->grid)) if (!ag->_random) ag->_random = S->mc->find<Random>();
+    });
+}
 
 // the reference's InterstellarDustMix evaluated on this simulation's wavelength grid (needs dat/)
 int skr_interstellar_mix(void* h, double* kabs, double* ksca, double* g)

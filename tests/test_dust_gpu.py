@@ -19,9 +19,14 @@ def _ref_pan(n=16, nlambda=25, packages=2e4, grid=None):
     p = configs.c2_params(n=n, nlambda=nlambda, packages=packages)
     spec, L, mixes = refspec.reference_spec(p, threads=os.cpu_count() or 1, dustsamples=5)
     spec += "selfabs 1\n"
+    kw = {}
+    if grid == "grid amesh":
+        # C5's grid type: the dust density comes from the mesh itself (AdaptiveMeshDustDistribution)
+        spec = "\n".join("ameshdust 1e-24" if l.startswith("dust ") else l for l in spec.splitlines()) + "\n"
+        kw["amesh"] = common.make_amesh(max_depth=3)
     if grid:
         spec = "\n".join(grid if l.startswith("grid ") else l for l in spec.splitlines()) + "\n"
-    S = sr.RefSim(spec, luminosities=L, mixes=mixes).setup()
+    S = sr.RefSim(spec, luminosities=L, mixes=mixes, **kw).setup()
     S.reset(4357); S.run_stellar()
     return S, p
 
@@ -50,7 +55,7 @@ def _compare(name, a, r, B, frac=0.97):
         assert nout <= max(2, (1 - frac) * len(z)) and abs(z.mean()) < 0.25, f"{name}: {nout} of {len(z)} bins beyond 3 sigma, mean z {z.mean():.3f}"
 
 
-@pytest.mark.parametrize("grid", [None, "grid octtree 2 4 1 0.0005 0 30"])
+@pytest.mark.parametrize("grid", [None, "grid octtree 2 4 1 0.0005 0 30", "grid amesh"])
 def test_dust_selfabsorption_and_emission(engine, grid):
     S, p = _ref_pan(grid=grid)
     _engine_for(engine, S, p)
