@@ -24,6 +24,8 @@ def _ref_pan(n=16, nlambda=25, packages=2e4, grid=None):
         # C5's grid type: the dust density comes from the mesh itself (AdaptiveMeshDustDistribution)
         spec = "\n".join("ameshdust 1e-24" if l.startswith("dust ") else l for l in spec.splitlines()) + "\n"
         kw["amesh"] = common.make_amesh(max_depth=3)
+    if grid == "grid voronoi file":
+        kw["particles"] = common.voronoi_particles(3000)       # C4's grid type
     if grid:
         spec = "\n".join(grid if l.startswith("grid ") else l for l in spec.splitlines()) + "\n"
     S = sr.RefSim(spec, luminosities=L, mixes=mixes, **kw).setup()
@@ -55,7 +57,7 @@ def _compare(name, a, r, B, frac=0.97):
         assert nout <= max(2, (1 - frac) * len(z)) and abs(z.mean()) < 0.25, f"{name}: {nout} of {len(z)} bins beyond 3 sigma, mean z {z.mean():.3f}"
 
 
-@pytest.mark.parametrize("grid", [None, "grid octtree 2 4 1 0.0005 0 30", "grid amesh"])
+@pytest.mark.parametrize("grid", [None, "grid octtree 2 4 1 0.0005 0 30", "grid amesh", "grid voronoi file"])
 def test_dust_selfabsorption_and_emission(engine, grid):
     S, p = _ref_pan(grid=grid)
     _engine_for(engine, S, p)
