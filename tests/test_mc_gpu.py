@@ -212,3 +212,49 @@ def test_full_instrument_errors(engine):
     bad = [dict(cfg["instruments"][0], scatteringLevels=-1)]
     with pytest.raises(Exception):
         engine.instruments(bad)
+
+
+def test_c3_configuration_against_reference_runs(engine):
+    """C3 at a reduced size: adaptive octree (Neighbor search), stars in a spiral-arm exponential disk
+    (SpiralStructureGeometryDecorator; the dust disk stays axisymmetric, as the reference's face-on normalisation demands), forced scattering, six frame instruments at inclinations 0 ... 90 degrees (five
+    observer directions on the engine, one traversal each per peel-off), against runs of the reference's own classes"""
+    import os
+    from oracle import skirtref as sr
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    PC = common.PC
+    sp = f"spiral 2 {float(np.radians(20))!r} {4000 * PC!r} 0.0 1.0 1"
+    incl = (0, 30, 60, 80, 88, 90)
+    lines = ["sim oligo", f"threads {os.cpu_count() or 1}", "seed 4357", "packages 100000.0", "wavelengths 0.55e-6", common.box_line(common.C1_BOX),
+             "grid octtree 2 6 1 2e-05 0 50", "dustsamples 10", "storeabs 1",
+             f"stellar expdisk {4000 * PC!r} {350 * PC!r} 0 0 {sp}", f"dust 2.0 0.55e-6 expdisk {4000 * PC!r} {140 * PC!r} 0 0"]
+    for i in incl:
+        lines.append(f"instrument frame f{i} {1e7 * PC!r} {float(np.radians(i))!r} 0 0 60 {50000 * PC!r} 60 {50000 * PC!r}")
+    S = sr.RefSim("\n".join(lines) + "\n", luminosities=[[1.0]], mixes=common.mix_v()).setup()
+    tables, medium, L = S.grid_tables(), S.medium(), S.luminosities()
+    Npp = S.packages_per_lambda()
+    engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    spiral = dict(arms=2, pitch=float(np.radians(20)), radius=4000 * PC, phase=0.0, weight=1.0, index=1)
+    engine.sources([dict(geometry=1, p=[4000 * PC, 350 * PC, 0, 0, 0], spiral=spiral)], L, 0.5)
+    engine.instruments([dict(kind=1, distance=1e7 * PC, inclination=float(np.radians(i)), Nxp=60, fovxp=50000 * PC, Nyp=60, fovyp=50000 * PC) for i in incl])
+    B = 10
+    ref = {i: [] for i in incl}; gpu = {i: [] for i in incl}; ref_l, gpu_l = [], []
+    for b in range(B):
+        S.reset(900 + 1000 * b); S.run_stellar(); ins = S.instruments()
+        engine.reset_results(); st = engine.run_stellar(Npp, store_absorption=True, seed=60 + b)
+        for q, i in enumerate(incl):
+            ref[i].append(ins[q]["frame"].copy()); gpu[i].append(engine.fetch_frame(q))
+        ref_l.append(S.labs().sum()); gpu_l.append(engine.fetch_labs().sum())
+    assert st["scatterings"] > 0.5 * st["packets"]                     # forced scattering: tau_V = 2 face-on
+    for i in incl:
+        a, r = np.array(gpu[i]), np.array(ref[i])
+        ta, tr = a.sum(1), r.sum(1)
+        zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / B + tr.var(ddof=1) / B)
+        assert abs(zt) < 4.5 and abs(ta.mean() / tr.mean() - 1) < 0.01, f"i={i}: frame total gpu {ta.mean():.6g} ref {tr.mean():.6g} ({zt:.2f} sigma)"
+        ma, mr = a.mean(0), r.mean(0); sa, sr_ = a.std(0, ddof=1) / np.sqrt(B), r.std(0, ddof=1) / np.sqrt(B)
+        ok = (sa < 0.3 * ma) & (sr_ < 0.3 * mr) & (sa > 0) & (sr_ > 0)
+        z = common.zscores(ma[ok], sa[ok], mr[ok], sr_[ok])
+        assert ok.sum() > 200 and np.mean(np.abs(z) < 3) > 0.95 and abs(z.mean()) < 0.25, f"i={i}: {np.mean(np.abs(z) < 3):.4f} of {ok.sum()} pixels within 3 sigma, mean z {z.mean():.3f}"
+    ta, tr = np.array(gpu_l), np.array(ref_l)
+    zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / B + tr.var(ddof=1) / B)
+    assert abs(zt) < 4.5 and abs(ta.mean() / tr.mean() - 1) < 0.01
