@@ -252,7 +252,12 @@ def main_engine(args):
     Lum = sim.ss.luminosities(); instr = [i.d for i in sim.isys.instruments]
     h2d = sum(np.asarray(v).nbytes for v in (tabs["xv"], tabs["yv"], tabs["zv"], med["rho"], med["kext"], med["ksca"], med["g"], Lum))
     e2e_steps = max(1, min(args.steps, 3))
-    sim.results(pinned=True)            # allocates the page-locked result buffers once (set-up, outside the timed steps)
+    # the job's results are read back once, by the root process, like the reference does (Instrument::sumResults reduces to
+    # the root, which alone writes the output; PeerToPeerCommunicator.cpp:36-50): the other ranks upload their tables, shoot
+    # their share and take part in the all-reduce
+    root = rank == 0
+    if root:
+        sim.results(pinned=True)        # allocates the page-locked result buffers once (set-up, outside the timed steps)
     d2h = 0
     barrier()
     w0 = time.perf_counter()
@@ -260,8 +265,11 @@ def main_engine(args):
         e.set_grid(tabs); e.medium(med["rho"], med["kext"], med["ksca"], med["g"])
         e.sources(comps, Lum, sim.ss.emissionBias); e.instruments(instr)
         sim.runstellaremission()
-        res = sim.results(pinned=True)
-        d2h = sum(v.nbytes for v in res.values())
+        if root:
+            res = sim.results(pinned=True)
+            d2h = sum(v.nbytes for v in res.values())
+        else:
+            torch.cuda.synchronize()
     barrier()
     e2e_s = (time.perf_counter() - w0) / e2e_steps
 
@@ -294,8 +302,8 @@ def main_engine(args):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "steps": e2e_steps, "what": "skg_grid_cartesian+skg_medium+skg_sources+skg_instruments from host arrays, skg_run_stellar, "
-                                                 "skg_fetch_frame/sed/labs into page-locked host arrays"},
+                    "steps": e2e_steps, "what": "skg_grid_cartesian+skg_medium+skg_sources+skg_instruments from host arrays (every rank), skg_run_stellar, "
+                                                 "skg_fetch_frame/sed/labs into page-locked host arrays (on the root rank, after the all-reduce)"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
             "roofline": {"bound": "hbm", "kernel": "absorbStage<GRID_CART> (dominant kernel of the phase: scatter + traverse + absorb + terminate/sample)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
