@@ -360,6 +360,12 @@ def main():
         # about 10-30 s of CPU work per step: ~3e4 packets/s/core measured on this class of host
         cores = os.cpu_count() or 1
         args.ref_packages = float(min(args.packages, max(2e3, round(15.0 * 3.0e4 * cores / args.nlambda, -3))))
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there)
+    # are sent to stderr for the whole run, and the line goes out on the saved descriptor
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(saved, "w", buffering=1)
     if args.impl == "reference":
         return main_reference(args)
     return main_engine(args)
