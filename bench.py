@@ -24,10 +24,6 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# keep stdout to the one JSON line: NCCL prints its version banner there at the VERSION level
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
-
 METRIC = "photon packets/sec"
 UNIT = "packets/s"
 

@@ -235,11 +235,34 @@ int skg_device_accumulators(skg_engine* e, int which /*0 labs, -1 dust labs, 1..
 
 /* ---- multi-GPU: replaces ProcessManager::sum / sum_all (ProcessManager.cpp:122-140) ------------------- */
 /* NCCL communicator over one engine per GPU/process.  unique_id is the 128-byte ncclUniqueId that rank 0
- * obtained from skg_comm_unique_id and distributed by any means (MPI_Bcast, torch.distributed, a file). */
+ * obtained from skg_comm_unique_id and distributed by any means (MPI_Bcast, torch.distributed, a file).
+ * A second skg_comm_init on the same engine destroys the previous communicator first. */
 int skg_comm_unique_id(void* unique_id_128);
 int skg_comm_init(skg_engine* e, int rank, int nranks, const void* unique_id_128);
-/* in-place sum over all ranks of every accumulator (Labs table, frames, SEDs) on the engine's stream */
+
+/* The reference sums each accumulator over the processes at its own moment, and exactly once:
+ *   SKG_REDUCE_LABS_STELLAR  the stellar absorption table, before the first dust emission spectra are made
+ *                            (PanDustSystem::calculatedustemission(true) -> sumResults(true), PanDustSystem.cpp:383-404)
+ *   SKG_REDUCE_LABS_DUST     the dust absorption table, after every self-absorption cycle (sumResults(false), called at
+ *                            the start of the next cycle or of the emission phase, PanMonteCarloSimulation.cpp:131,249)
+ *   SKG_REDUCE_INSTRUMENTS   every detector array, once, in Instrument::write() (Instrument.cpp:57-65)
+ * skg_allreduce sums the selected accumulators in place over all ranks (one grouped ncclAllReduce(double, sum) on the
+ * engine's stream).  The engine tracks per accumulator whether it holds rank-local additions only, the global sum, or
+ * nothing since the last reset: an accumulator that already holds the global sum (or nothing) is skipped, so the call
+ * is idempotent; one that received rank-local additions AFTER it was summed cannot be summed again in place and is an
+ * error ("... already summed over the processes").  elapsed_ms (may be NULL) receives the device time of the collective.
+ * Every rank of the communicator must make the same calls in the same order (as with sum_all). */
+enum { SKG_REDUCE_LABS_STELLAR = 1, SKG_REDUCE_LABS_DUST = 2, SKG_REDUCE_INSTRUMENTS = 4, SKG_REDUCE_ALL = 7 };
+int skg_allreduce(skg_engine* e, int which, double* elapsed_ms);
+/* = skg_allreduce(e, SKG_REDUCE_ALL, NULL) */
 int skg_allreduce_results(skg_engine* e);
+/* PanDustSystem::Labsdusttot() (PanDustSystem.cpp:363-379): the total of the dust absorption table over all cells,
+ * wavelengths AND processes, identical on every rank (the convergence test of the self-absorption cycles,
+ * PanMonteCarloSimulation.cpp:152-167, must take the same decision everywhere).  Summed on the device; a rank-local
+ * table adds a scalar all-reduce, a table that already holds the global sum is totalled as it is (rank 0's value is
+ * broadcast).  skg_labs_stellar_total is PanDustSystem::Labsstellartot() (:351-359) with the same conventions. */
+int skg_labs_dust_total(skg_engine* e, double* total);
+int skg_labs_stellar_total(skg_engine* e, double* total);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,7 @@ INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL = 1, 2, 3, 4
 # FullInstrument channels (include/skirtgpu.h SKG_CHAN_*): scattering level n is channel CHAN_LEVEL1 + n - 1
 CHAN_TRANSPARENT, CHAN_STELLAR_DIRECT, CHAN_STELLAR_SCATTERED, CHAN_DUST_DIRECT, CHAN_DUST_SCATTERED, CHAN_LEVEL1 = 0, 1, 2, 3, 4, 5
 PHASE_STELLAR, PHASE_DUST_SELFABS, PHASE_DUST_EMISSION = 0, 1, 2
+REDUCE_LABS_STELLAR, REDUCE_LABS_DUST, REDUCE_INSTRUMENTS, REDUCE_ALL = 1, 2, 4, 7
 # skg_segment == DustGridPath::Segment (DustGridPath.hpp:161-167)
 SEGMENT = np.dtype([("m", np.int32), ("reserved", np.int32), ("ds", np.float64), ("s", np.float64), ("dtau", np.float64), ("tau", np.float64)])
 
@@ -427,5 +428,23 @@ class Engine:
         uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
         self._chk(self._lib.skg_comm_init(self.h, int(rank), int(nranks), _vp(uid)))
 
+    def allreduce(self, which=REDUCE_ALL):
+        """skg_allreduce: in-place sum over the ranks of the selected accumulators (each at most once, see skirtgpu.h);
+        returns the device time of the collective in ms"""
+        ms = C.c_double()
+        self._chk(self._lib.skg_allreduce(self.h, int(which), C.byref(ms)))
+        return ms.value
+
     def allreduce_results(self):
         self._chk(self._lib.skg_allreduce_results(self.h))
+
+    def labs_dust_total(self):
+        """PanDustSystem::Labsdusttot(): over all cells, wavelengths and processes; identical on every rank"""
+        t = C.c_double()
+        self._chk(self._lib.skg_labs_dust_total(self.h, C.byref(t)))
+        return t.value
+
+    def labs_stellar_total(self):
+        t = C.c_double()
+        self._chk(self._lib.skg_labs_stellar_total(self.h, C.byref(t)))
+        return t.value

@@ -63,7 +63,7 @@ def luminosities(p, lg):
     return out
 
 
-def build(p, device=0, rank=0, nranks=1, seed=4357, storeAbsorption=None, rho=None):
+def build(p, device=0, rank=0, nranks=1, seed=4357, storeAbsorption=None, rho=None, engine=None):
     """MonteCarloSimulation (engine side) for a parameter dict"""
     lg = wavelength_grid(p)
     mix = sim.InterstellarDustMix(lg)
@@ -82,7 +82,7 @@ def build(p, device=0, rank=0, nranks=1, seed=4357, storeAbsorption=None, rho=No
     if storeAbsorption is None:
         storeAbsorption = p["sim"] == "pan"
     return sim.MonteCarloSimulation(lg, ss, ds, sim.InstrumentSystem(ins), packages=p["packages"], seed=seed,
-                                    storeAbsorption=storeAbsorption, device=device, rank=rank, nranks=nranks)
+                                    storeAbsorption=storeAbsorption, device=device, rank=rank, nranks=nranks, engine=engine)
 
 
 def c1_oligo(n=100, packages=1e6, **kw):

@@ -31,6 +31,7 @@ Engine::Engine(int dev) : device(dev)
 Engine::~Engine()
 {
     cudaSetDevice(device);
+    destroyComm(*this);
     freeGrid();
     for (DevBuf* b : sourceBufs) delete b;
     for (DevBuf* b : instrBufs) delete b;
@@ -154,6 +155,13 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
             if (cell[l] >= 0) ncells++;
             if ((child0[l] < 0) != (cell[l] >= 0)) throw Error("leaf/cell tables are inconsistent");
         }
+        if (search == 1)
+        {
+            if (nbrStart[0] != 0) throw Error("neighbour list offsets must start at 0");
+            for (size_t q = 0; q < 6 * (size_t)N; q++) if (nbrStart[q + 1] < nbrStart[q]) throw Error("neighbour list offsets must not decrease");
+            const size_t total = (size_t)nbrStart[6 * (size_t)N];
+            for (size_t q = 0; q < total; q++) if (nbrIds[q] < 0 || nbrIds[q] >= N) throw Error("invalid neighbour id in tree tables");
+        }
         e.freeGrid();
         e.tree.box = up(e, box, 6 * (size_t)N); e.tree.child0 = up(e, child0, N); e.tree.parent = up(e, parent, N);
         e.tree.cell = up(e, cell, N);
@@ -192,7 +200,6 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
         if (search == 1)
         {
             const size_t total = (size_t)std::max(0, nbrStart[6 * (size_t)N]);
-            for (size_t q = 0; q < total; q++) if (nbrIds[q] < 0 || nbrIds[q] >= N) throw Error("invalid neighbour id in tree tables");
             e.tree.nbrStart = up(e, nbrStart, 6 * (size_t)N + 1); e.tree.nbrIds = up(e, nbrIds, std::max<size_t>(1, total));
             std::vector<TreeNodeRec> rec(N); std::vector<int> hints;
             for (int l = 0; l < N; l++)
@@ -203,7 +210,6 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
                 for (int w = 0; w < 6; w++)
                 {
                     const int beg = nbrStart[6 * (size_t)l + w], cnt = nbrStart[6 * (size_t)l + w + 1] - beg;
-                    if (cnt < 0) throw Error("neighbour list offsets must not decrease");
                     r.first[w] = cnt > 0 ? nbrIds[beg] : -1;
                     if (cnt > 1)
                     {
@@ -302,6 +308,13 @@ int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* 
         if (N < 1 || !particles || !nbrStart || !nbrIds || !extent || nb < 1 || !blkStart || !blkIds || !blkTree)
             throw Error("voronoi tables missing");
         size_t nb3 = (size_t)nb * nb * nb;
+        // every table is validated before the previous grid is released
+        if (nbrStart[0] != 0) throw Error("neighbour list offsets must start at 0");
+        for (int m = 0; m < N; m++) if (nbrStart[m + 1] < nbrStart[m]) throw Error("neighbour list offsets must not decrease");
+        for (int q = 0; q < nbrStart[N]; q++) if (nbrIds[q] >= N || nbrIds[q] < -6) throw Error("invalid neighbour id in Voronoi tables");
+        if ((size_t)std::max(0, nbrStart[N]) + N + 8 > 2147483647ull) throw Error("too many Voronoi neighbours for int32 record indices");
+        for (size_t b = 0; b < nb3; b++) if (blkStart[b + 1] < blkStart[b] || blkTree[b] >= Nkd) throw Error("invalid block tables in Voronoi grid");
+        for (int q = 0; q < blkStart[nb3]; q++) if (blkIds[q] < 0 || blkIds[q] >= N) throw Error("invalid cell id in Voronoi block lists");
         e.freeGrid();
         e.voro.particles = up(e, particles, 3 * (size_t)N);
         e.voro.nbrStart = up(e, nbrStart, (size_t)N + 1); e.voro.nbrIds = up(e, nbrIds, (size_t)std::max(1, nbrStart[N]));
@@ -313,19 +326,16 @@ int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* 
         e.voro.cellBox = cellBox ? up(e, cellBox, 6 * (size_t)N) : nullptr;
         {
             const size_t total = (size_t)std::max(0, nbrStart[N]);
-            if (total + N + 8 > 2147483647ull) throw Error("too many Voronoi neighbours for int32 record indices");
             std::vector<double> rec(4 * (total + N + 8), 0.0);
             auto pack = [](int lo, int hi) { const long long v = (long long)(unsigned)lo | ((long long)hi << 32); double d; std::memcpy(&d, &v, 8); return d; };
             for (int m = 0; m < N; m++)
             {
                 const int beg = nbrStart[m], cnt = nbrStart[m + 1] - beg;
-                if (cnt < 0) throw Error("neighbour list offsets must not decrease");
                 double* h = rec.data() + 4 * ((size_t)beg + m);
                 h[0] = particles[3 * (size_t)m]; h[1] = particles[3 * (size_t)m + 1]; h[2] = particles[3 * (size_t)m + 2]; h[3] = pack(cnt, 0);
                 for (int q = 0; q < cnt; q++)
                 {
                     const int id = nbrIds[beg + q];
-                    if (id >= N || id < -6) throw Error("invalid neighbour id in Voronoi tables");
                     double* s4 = h + 4 * (size_t)(q + 1);
                     if (id >= 0) { s4[0] = particles[3 * (size_t)id]; s4[1] = particles[3 * (size_t)id + 1]; s4[2] = particles[3 * (size_t)id + 2]; s4[3] = pack(id, nbrStart[id] + id); }
                     else s4[3] = pack(id, 0);
@@ -482,7 +492,7 @@ int skg_dust_library(skg_engine* eh, const double* volumes, const double* kappaa
 int skg_dust_cell_luminosities(skg_engine* eh, double** d_Lcell)
 { return guarded([&]{ if (!d_Lcell) throw Error("null output"); *d_Lcell = mcDustCellLuminosities(E(eh)); }); }
 int skg_reset_labs_dust(skg_engine* eh)
-{ return guarded([&]{ Engine& e = E(eh); if (e.labsDust.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labsDust.p, 0, sizeof(double) * e.labsCount, e.stream)); e.sync(); }); }
+{ return guarded([&]{ Engine& e = E(eh); if (e.labsDust.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labsDust.p, 0, sizeof(double) * e.labsCount, e.stream)); e.accLabsDust = Engine::ACC_ZERO; e.sync(); }); }
 int skg_fetch_labs_dust(skg_engine* eh, double* labs, int add)
 { return guarded([&]{ if (!labs) throw Error("null host array"); mcFetchLabs(E(eh), labs, add, 1); }); }
 int skg_labs_bolometric(skg_engine* eh, double* Labsbol)
@@ -502,7 +512,7 @@ int skg_fetch_frame(skg_engine* eh, int i, double* frame, int add)
     return guarded([&]{
         Engine& e = E(eh);
         if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].frame) throw Error("instrument has no frame");
-        fetchArray(e, e.instr[i].frame, (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.med.Nlambda, frame, add);
+        fetchArray(e, e.instr[i].frame, (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.instrNlambda, frame, add);
     });
 }
 int skg_fetch_sed(skg_engine* eh, int i, double* sed, int add)
@@ -510,7 +520,7 @@ int skg_fetch_sed(skg_engine* eh, int i, double* sed, int add)
     return guarded([&]{
         Engine& e = E(eh);
         if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].sed) throw Error("instrument has no SED");
-        fetchArray(e, e.instr[i].sed, e.med.Nlambda, sed, add);
+        fetchArray(e, e.instr[i].sed, e.instrNlambda, sed, add);
     });
 }
 int skg_fetch_frame_channel(skg_engine* eh, int i, int c, double* frame, int add)
@@ -519,7 +529,7 @@ int skg_fetch_frame_channel(skg_engine* eh, int i, int c, double* frame, int add
         Engine& e = E(eh);
         if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].chanFrame) throw Error("instrument has no channels");
         if (c < 0 || c >= e.instr[i].Nchan) throw Error("channel out of range");
-        const int64_t n = (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.med.Nlambda;
+        const int64_t n = (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.instrNlambda;
         fetchArray(e, e.instr[i].chanFrame + c * n, n, frame, add);
     });
 }
@@ -529,7 +539,7 @@ int skg_fetch_sed_channel(skg_engine* eh, int i, int c, double* sed, int add)
         Engine& e = E(eh);
         if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].chanSed) throw Error("instrument has no channels");
         if (c < 0 || c >= e.instr[i].Nchan) throw Error("channel out of range");
-        fetchArray(e, e.instr[i].chanSed + (int64_t)c * e.med.Nlambda, e.med.Nlambda, sed, add);
+        fetchArray(e, e.instr[i].chanSed + (int64_t)c * e.instrNlambda, e.instrNlambda, sed, add);
     });
 }
 int skg_fetch_labs(skg_engine* eh, double* labs, int add)
@@ -552,12 +562,12 @@ int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr,
         const InstrDev& d = e.instr[i];
         if (d.kind == SKG_INSTR_FULL)
         {
-            if (part == 0) { *d_ptr = d.chanFrame; *count = (int64_t)d.Nxp * d.Nyp * e.med.Nlambda * d.Nchan; }
-            else { *d_ptr = d.chanSed; *count = (int64_t)e.med.Nlambda * d.Nchan; }
+            if (part == 0) { *d_ptr = d.chanFrame; *count = (int64_t)d.Nxp * d.Nyp * e.instrNlambda * d.Nchan; }
+            else { *d_ptr = d.chanSed; *count = (int64_t)e.instrNlambda * d.Nchan; }
             return;
         }
-        if (part == 0) { *d_ptr = d.frame; *count = d.frame ? (int64_t)d.Nxp * d.Nyp * e.med.Nlambda : 0; }
-        else { *d_ptr = d.sed; *count = d.sed ? e.med.Nlambda : 0; }
+        if (part == 0) { *d_ptr = d.frame; *count = d.frame ? (int64_t)d.Nxp * d.Nyp * e.instrNlambda : 0; }
+        else { *d_ptr = d.sed; *count = d.sed ? e.instrNlambda : 0; }
     });
 }
 

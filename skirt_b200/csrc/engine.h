@@ -84,6 +84,14 @@ struct Engine
     DevBuf instrGroupedDev, groupsDev; int Ngroups = 0;    // instruments ordered by line of sight + the groups
     DevBuf mcPool, mcLists, mcCounts, mcEllList; int* mcHostCounts = nullptr;   // packet pool of the wavefront shooter
     void* nccl = nullptr; int rank = 0, nranks = 1;
+    // what each accumulator holds with respect to the other processes (skg_allreduce): nothing since the last reset,
+    // rank-local additions only, the sum over all ranks, or the sum over all ranks plus later rank-local additions
+    enum AccState { ACC_ZERO = 0, ACC_LOCAL = 1, ACC_GLOBAL = 2, ACC_MIXED = 3 };
+    int accLabs = ACC_ZERO, accLabsDust = ACC_ZERO, accInstr = ACC_ZERO;
+    void touched(int& st) const { st = (nranks > 1 && (st == ACC_GLOBAL || st == ACC_MIXED)) ? ACC_MIXED : ACC_LOCAL; }
+    // opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: set once per engine
+    bool attrPath = false, attrFill = false, attrStages = false;
+    DevBuf scalarDev;                       // one double: device-side totals (skg_labs_dust_total)
     double stageMs[4] = {0, 0, 0, 0}; uint64_t mcIterations = 0;     // launch, peel, absorb, propagate device time of the last phase
     cudaEvent_t mcEvents[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;              // kernels launched by this engine (skg_launch_count)
@@ -111,6 +119,8 @@ void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, co
 void mcSetInstruments(Engine& e, int n, const skg_instrument* instr);
 void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats);
 void mcResetResults(Engine& e);
+double mcLabsTotal(Engine& e, int which);     // sum over the whole (stellar: 0, dust: 1) absorption table, on the device
+void destroyComm(Engine& e);                  // comm.cu
 void mcFetchLabs(Engine& e, double* host, int add, int which);
 void mcLabsBolometric(Engine& e, double* host);
 void mcDustLibrary(Engine& e, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda);

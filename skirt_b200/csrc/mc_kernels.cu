@@ -48,24 +48,6 @@
 namespace skg
 {
 
-__device__ __forceinline__ CartGrid stageCartMC(const CartGrid& g, double* smem, bool useSmem)
-{
-    if (!useSmem) return g;
-    CartGrid s = g;
-    // layout: [pad] xv[0..Nx] [pad] [pad] yv[0..Ny] [pad] [pad] zv[0..Nz] [pad]   (SKG_CART_SMEM_DOUBLES)
-    int nx = g.Nx + 1, ny = g.Ny + 1, nz = g.Nz + 1;
-    double* sxv = smem + 1; double* syv = sxv + nx + 2; double* szv = syv + ny + 2;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) sxv[i] = g.xv[i];
-    for (int i = threadIdx.x; i < ny; i += blockDim.x) syv[i] = g.yv[i];
-    for (int i = threadIdx.x; i < nz; i += blockDim.x) szv[i] = g.zv[i];
-    if (threadIdx.x == 0) { sxv[-1] = sxv[nx] = syv[-1] = syv[ny] = szv[-1] = szv[nz] = 0.0; }
-    __syncthreads();
-    s.xv = sxv; s.yv = syv; s.zv = szv;
-    s.sx = (unsigned)__cvta_generic_to_shared(sxv); s.sy = (unsigned)__cvta_generic_to_shared(syv); s.sz = (unsigned)__cvta_generic_to_shared(szv);
-    s.staged = 1;
-    return s;
-}
-
 // per-kernel statistics: warp-reduced, one atomic per warp and counter
 __device__ __forceinline__ void flushStats(Counters* ctr, unsigned long long nSeg, unsigned long long nPaths, unsigned long long nScatt,
                                            unsigned long long nPackets, unsigned long long nAbs, unsigned long long nDet)
@@ -373,7 +355,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PEEL_MINBLOCKS : 
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
-    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     PeelJob<KIND, SINGLE> job(G, cart, P);
     runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, P.peelRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
@@ -549,7 +531,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS 
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
-    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     AbsorbJob<KIND, SINGLE, STORE> job(G, cart, P, counts);
     runJobs<KIND>(G, cart, ctr, job, nAlive, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, job.nScatt, 0, job.nAbs, 0);
@@ -623,7 +605,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PROP_MINBLOCKS : 
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
-    if (KIND == GRID_CART) cart = stageCartMC(G.cart, smem, cartSmem);
+    if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     PropagateJob<KIND, SINGLE> job(P);
     runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.propRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
@@ -774,23 +756,55 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             { used[j] = 1; grouped.push_back(e.instr[j]); g.count++; }
         groups.push_back(g);
     }
-    e.Ngroups = (int)groups.size(); e.instrNlambda = e.med.Nlambda;
+    e.Ngroups = (int)groups.size(); e.instrNlambda = e.med.Nlambda; e.accInstr = Engine::ACC_ZERO;
     e.instrGroupedDev.upload(grouped.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
     e.groupsDev.upload(groups.data(), sizeof(ObsGroup) * std::max<size_t>(groups.size(), 1), e.stream);
     e.sync();
 }
 
+// every accumulator back to zero: detector arrays, the stellar AND the dust absorption table (the reference starts a
+// simulation with _Labsstelvv = _Labsdustvv = 0, PanDustSystem.cpp:100-118)
 void mcResetResults(Engine& e)
 {
+    const size_t Nl = (size_t)e.instrNlambda;
     for (const InstrDev& d : e.instr)
     {
-        if (d.frame) SKG_CUDA(cudaMemsetAsync(d.frame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * e.med.Nlambda, e.stream));
-        if (d.sed) SKG_CUDA(cudaMemsetAsync(d.sed, 0, sizeof(double) * e.med.Nlambda, e.stream));
-        if (d.chanFrame) SKG_CUDA(cudaMemsetAsync(d.chanFrame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * e.med.Nlambda * d.Nchan, e.stream));
-        if (d.chanSed) SKG_CUDA(cudaMemsetAsync(d.chanSed, 0, sizeof(double) * e.med.Nlambda * d.Nchan, e.stream));
+        if (d.frame) SKG_CUDA(cudaMemsetAsync(d.frame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * Nl, e.stream));
+        if (d.sed) SKG_CUDA(cudaMemsetAsync(d.sed, 0, sizeof(double) * Nl, e.stream));
+        if (d.chanFrame) SKG_CUDA(cudaMemsetAsync(d.chanFrame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * Nl * d.Nchan, e.stream));
+        if (d.chanSed) SKG_CUDA(cudaMemsetAsync(d.chanSed, 0, sizeof(double) * Nl * d.Nchan, e.stream));
     }
     if (e.labs.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labs.p, 0, sizeof(double) * e.labsCount, e.stream));
+    if (e.labsDust.p && e.labsCount) SKG_CUDA(cudaMemsetAsync(e.labsDust.p, 0, sizeof(double) * e.labsCount, e.stream));
+    e.accLabs = e.accLabsDust = e.accInstr = Engine::ACC_ZERO;
     e.sync();
+}
+
+// block-wise sum of an array into *out (fp64 atomicAdd of one partial sum per CTA)
+__global__ void __launch_bounds__(256) sumArray(const double* __restrict__ a, size_t n, double* __restrict__ out)
+{
+    double s = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) s += a[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    __shared__ double part[8];
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int w = 0; w < 8; w++) t += part[w]; atomicAdd(out, t); }
+}
+
+// PanDustSystem::Labsstellartot / Labsdusttot (PanDustSystem.cpp:351-366), the rank-local part
+double mcLabsTotal(Engine& e, int which)
+{
+    DevBuf& src = which ? e.labsDust : e.labs;
+    if (!src.p || e.labsCount == 0) return 0.0;
+    e.scalarDev.ensure(sizeof(double));
+    SKG_CUDA(cudaMemsetAsync(e.scalarDev.p, 0, sizeof(double), e.stream));
+    sumArray<<<e.smCount * 4, 256, 0, e.stream>>>(src.as<double>(), (size_t)e.labsCount, e.scalarDev.as<double>());
+    e.launches++; SKG_CUDA(cudaGetLastError());
+    double total = 0;
+    SKG_CUDA(cudaMemcpyAsync(&total, e.scalarDev.p, sizeof(double), cudaMemcpyDeviceToHost, e.stream));
+    e.sync();
+    return total;
 }
 
 void mcFetchLabs(Engine& e, double* host, int add, int which)
@@ -1041,6 +1055,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     if (p.ellBegin < 0 || p.ellEnd > Nlambda || p.ellBegin > p.ellEnd) throw Error("wavelength range out of bounds");
     if (p.scattBias < 0 || p.scattBias > 1) throw Error("scattBias should be between 0 and 1");
     if (e.med.Ncomp > 8) throw Error("at most 8 dust components are supported");
+    if (e.med.rho && e.med.Ncells != e.Ncells) throw Error("the medium has " + std::to_string(e.med.Ncells) + " cells but the grid has " + std::to_string(e.Ncells) + ": call skg_medium again");
     if (!e.instr.empty() && e.instrNlambda != Nlambda) throw Error("the instruments were set up for " + std::to_string(e.instrNlambda) + " wavelengths but the medium has " + std::to_string(Nlambda) + ": call skg_instruments again");
     if (!(p.packages >= 0) || p.packages > 1e15) throw Error("Number of photon packages is negative or larger than implementation limit of 1e15");
     McDev P{};
@@ -1071,12 +1086,14 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         if (e.labsCount != count)
         {
             // (re)allocate both tables consistently
-            e.labs.release(); e.labsDust.release(); e.labsCount = count;
+            e.labs.release(); e.labsDust.release(); e.labsCount = count; e.accLabs = e.accLabsDust = Engine::ACC_ZERO;
         }
         DevBuf& tab = phase == SKG_PHASE_STELLAR ? e.labs : e.labsDust;
         if (!tab.p) { tab.ensure(sizeof(double) * count); SKG_CUDA(cudaMemsetAsync(tab.p, 0, sizeof(double) * count, e.stream)); }
         P.labs = tab.as<double>();
+        e.touched(phase == SKG_PHASE_STELLAR ? e.accLabs : e.accLabsDust);
     }
+    if (!e.instr.empty() && phase != SKG_PHASE_DUST_SELFABS) e.touched(e.accInstr);
     P.NppInt = (unsigned long long)std::ceil(p.packages);
     P.Lscale = p.luminosityScale > 0 ? p.luminosityScale : (double)P.NppInt;
     P.minWeightReduction = p.minWeightReduction; P.minfs = p.minScattEvents; P.xi = p.scattBias;
@@ -1109,8 +1126,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
             size_t need = sizeof(double) * SKG_CART_SMEM_DOUBLES(e.cart);
             if (need > SKG_CART_SMEM_MAX) throw Error("CartesianDustGrid: more than 8189 mesh borders in total are not supported");
             smem = need; cartSmem = true;
-            static bool attr = false;
-            if (!attr)
+            if (!e.attrStages)
             {
                 const int cap = 96 * 1024;
                 SKG_CUDA(cudaFuncSetAttribute(peelStage<GRID_CART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
@@ -1121,7 +1137,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
                 SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
                 SKG_CUDA(cudaFuncSetAttribute(propagateStage<GRID_CART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
                 SKG_CUDA(cudaFuncSetAttribute(propagateStage<GRID_CART, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-                attr = true;
+                e.attrStages = true;
             }
         }
         GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro;

@@ -17,25 +17,6 @@ struct GridSet
     CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro;
 };
 
-// shared-memory staging of the Cartesian borders; returns a CartGrid view whose xv/yv/zv point to smem
-__device__ __forceinline__ CartGrid stageCart(const CartGrid& g, double* smem, bool useSmem)
-{
-    if (!useSmem) return g;
-    CartGrid s = g;
-    // layout: [pad] xv[0..Nx] [pad] [pad] yv[0..Ny] [pad] [pad] zv[0..Nz] [pad]   (SKG_CART_SMEM_DOUBLES)
-    int nx = g.Nx + 1, ny = g.Ny + 1, nz = g.Nz + 1;
-    double* sxv = smem + 1; double* syv = sxv + nx + 2; double* szv = syv + ny + 2;
-    for (int i = threadIdx.x; i < nx; i += blockDim.x) sxv[i] = g.xv[i];
-    for (int i = threadIdx.x; i < ny; i += blockDim.x) syv[i] = g.yv[i];
-    for (int i = threadIdx.x; i < nz; i += blockDim.x) szv[i] = g.zv[i];
-    if (threadIdx.x == 0) { sxv[-1] = sxv[nx] = syv[-1] = syv[ny] = szv[-1] = szv[nz] = 0.0; }
-    __syncthreads();
-    s.xv = sxv; s.yv = syv; s.zv = szv;
-    s.sx = (unsigned)__cvta_generic_to_shared(sxv); s.sy = (unsigned)__cvta_generic_to_shared(syv); s.sz = (unsigned)__cvta_generic_to_shared(szv);
-    s.staged = 1;
-    return s;
-}
-
 // ---- jobs (see wavefront.cuh) ---------------------------------------------------------------------------
 struct RayJobBase
 {
@@ -278,12 +259,11 @@ static LaunchCfg cfgFor(Engine& e, int64_t n)
         size_t need = sizeof(double) * SKG_CART_SMEM_DOUBLES(e.cart);
         if (need > SKG_CART_SMEM_MAX) throw Error("CartesianDustGrid: more than 8189 mesh borders in total are not supported");
         c.smem = need; c.cartSmem = true;
-        static bool attr = false;
-        if (!attr)
+        if (!e.attrPath)
         {
             SKG_CUDA(cudaFuncSetAttribute(pathCountKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             SKG_CUDA(cudaFuncSetAttribute(opticalDepthKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            attr = true;
+            e.attrPath = true;
         }
     }
     return c;
@@ -310,18 +290,18 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
 {
     if (n <= 0) return;
     if (d_ell && !e.med.rho) throw Error("skg_path_fill with wavelength indices needs skg_medium first");
+    if (d_ell && e.med.Ncells != e.Ncells) throw Error("the medium has " + std::to_string(e.med.Ncells) + " cells but the grid has " + std::to_string(e.Ncells) + ": call skg_medium again");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     c.smem += 4 * RecordJobStaged::bytesPerWarp();
     if (const char* pad = getenv("SKG_FILL_SMEM_PAD")) c.smem += (size_t)atoi(pad);      // experiment: limits resident CTAs
-    static bool attr = false;
-    if (!attr)
+    if (!e.attrFill)
     {
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_AMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_VORO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         if (const char* cv = getenv("SKG_FILL_CARVEOUT")) SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_CART>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
-        attr = true;
+        e.attrFill = true;
     }
     SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride,
                                                                                 d_offsets, d_segments, c.work)));
@@ -333,6 +313,7 @@ void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d
 {
     if (n <= 0) return;
     if (!e.med.rho) throw Error("skg_opticaldepth needs skg_medium first");
+    if (e.med.Ncells != e.Ncells) throw Error("the medium has " + std::to_string(e.med.Ncells) + " cells but the grid has " + std::to_string(e.Ncells) + ": call skg_medium again");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
     SKG_DISPATCH(e, (opticalDepthKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride,
                                                                                     d_dist, d_tau, c.work)));

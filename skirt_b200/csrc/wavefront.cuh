@@ -27,6 +27,26 @@ namespace skg
 
 #define SKG_PERIOD 4
 
+// shared-memory staging of the Cartesian borders; returns a CartGrid view whose xv/yv/zv point to smem
+__device__ __forceinline__ CartGrid stageCart(const CartGrid& g, double* smem, bool useSmem)
+{
+    if (!useSmem) return g;
+    CartGrid s = g;
+    // layout: [pad] xv[0..Nx] [pad] [pad] yv[0..Ny] [pad] [pad] zv[0..Nz] [pad]   (SKG_CART_SMEM_DOUBLES)
+    int nx = g.Nx + 1, ny = g.Ny + 1, nz = g.Nz + 1;
+    double* sxv = smem + 1; double* syv = sxv + nx + 2; double* szv = syv + ny + 2;
+    for (int i = threadIdx.x; i < nx; i += blockDim.x) sxv[i] = g.xv[i];
+    for (int i = threadIdx.x; i < ny; i += blockDim.x) syv[i] = g.yv[i];
+    for (int i = threadIdx.x; i < nz; i += blockDim.x) szv[i] = g.zv[i];
+    if (threadIdx.x == 0) { sxv[-1] = sxv[nx] = syv[-1] = syv[ny] = szv[-1] = szv[nz] = 0.0; }
+    __syncthreads();
+    s.xv = sxv; s.yv = syv; s.zv = szv;
+    s.sx = (unsigned)__cvta_generic_to_shared(sxv); s.sy = (unsigned)__cvta_generic_to_shared(syv); s.sz = (unsigned)__cvta_generic_to_shared(szv);
+    s.staged = 1;
+    return s;
+}
+
+
 template<class Walker, class GridT, class Job>
 __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Job& job, int n, int* workCounter, int refill)
 {

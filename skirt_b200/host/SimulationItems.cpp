@@ -119,7 +119,9 @@ skg_mc_stats MonteCarloSimulation::runstellaremission()
     p.ellBegin = 0; p.ellEnd = _lambdagrid->Nlambda();
     skg_mc_stats st{};
     check(skg_run_stellar(_engine, &p, &st));
-    if (_nranks > 1) check(skg_allreduce_results(_engine));       // Instrument::sumResults / PanDustSystem::sumResults
+    // the stellar absorption table is summed over the processes once (PanDustSystem::sumResults(true), PanDustSystem.cpp:394-404);
+    // the detector arrays once, when they are read (fetchResults; Instrument::sumResults at write(), Instrument.cpp:57-65)
+    if (_nranks > 1 && p.storeAbsorption) check(skg_allreduce(_engine, SKG_REDUCE_LABS_STELLAR, nullptr));
     return st;
 }
 
@@ -136,7 +138,8 @@ skg_mc_stats MonteCarloSimulation::shootDust(int phase, double packages)
     if (phase == SKG_PHASE_DUST_SELFABS) check(skg_reset_labs_dust(_engine));   // rebootLabsdust, after the spectra were made
     skg_mc_stats st{};
     check(skg_run_dust(_engine, &p, phase, _dustBias, SKG_DEVICE, dL, &st));
-    if (_nranks > 1) check(skg_allreduce_results(_engine));
+    // PanDustSystem::sumResults(false): the dust absorption of this cycle, summed before the next spectra are made from it
+    if (_nranks > 1 && phase == SKG_PHASE_DUST_SELFABS) check(skg_allreduce(_engine, SKG_REDUCE_LABS_DUST, nullptr));
     return st;
 }
 
@@ -146,7 +149,6 @@ int MonteCarloSimulation::rundustselfabsorption()
     if (!_engine || !_dustemission) SKIRT_FATAL("dust self-absorption needs a set-up simulation with dust emission");
     const double stage_factor[] = {1. / 10., 1. / 3., 1.}; const double stage_epsmax[] = {0.010, 0.007, 0.005};
     double prev = 0.; int total = 0;
-    std::vector<double> labs((size_t)_ds->Ncells() * _lambdagrid->Nlambda());
     for (int stage = 0; stage < 3; stage++)
     {
         bool fixed = _cycles > 0; const int Ncyclesmax = fixed ? _cycles : 100;
@@ -154,8 +156,8 @@ int MonteCarloSimulation::rundustselfabsorption()
         while (cycle <= Ncyclesmax && (!convergence || fixed))
         {
             shootDust(SKG_PHASE_DUST_SELFABS, _packages * stage_factor[stage]);
-            check(skg_fetch_labs_dust(_engine, labs.data(), 0));
-            double Labsdusttot = 0; for (double v : labs) Labsdusttot += v;
+            double Labsdusttot = 0;                 // PanDustSystem::Labsdusttot(): the same number on every process
+            check(skg_labs_dust_total(_engine, &Labsdusttot));
             double eps = std::fabs((Labsdusttot - prev) / Labsdusttot);
             prev = Labsdusttot;
             if ((stage < 2 || cycle > 1) && eps < stage_epsmax[stage]) convergence = true;
@@ -175,6 +177,7 @@ skg_mc_stats MonteCarloSimulation::rundustemission()
 void MonteCarloSimulation::fetchResults()
 {
     const int Nl = _lambdagrid->Nlambda();
+    if (_nranks > 1) check(skg_allreduce(_engine, SKG_REDUCE_INSTRUMENTS, nullptr));     // Instrument::sumResults; once
     int idx = 0;
     for (auto& i : _is->instruments())
     {

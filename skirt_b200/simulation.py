@@ -14,7 +14,8 @@ import os
 import numpy as np
 
 from .parallel import shard_packets
-from .binding import Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, CHAN_LEVEL1
+from .binding import (Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, CHAN_LEVEL1,
+                      REDUCE_LABS_STELLAR, REDUCE_LABS_DUST, REDUCE_INSTRUMENTS)
 
 PC = 3.08567758e16          # Units.cpp:17-30
 LSUN = 3.839e26
@@ -462,7 +463,7 @@ class MonteCarloSimulation:
     """MonteCarloSimulation (MonteCarloSimulation.cpp:31-36 defaults): owns the engine(s) and drives the
     photon shooting phases.  `packages` is the number of packets per wavelength, like the ski property."""
     def __init__(self, wavelengthGrid, stellarSystem, dustSystem, instrumentSystem, packages=1e6, minWeightReduction=1e4,
-                 minScattEvents=0.0, scattBias=0.5, seed=4357, storeAbsorption=False, device=0, rank=0, nranks=1):
+                 minScattEvents=0.0, scattBias=0.5, seed=4357, storeAbsorption=False, device=0, rank=0, nranks=1, engine=None):
         self.lambdagrid, self.ss, self.ds, self.isys = wavelengthGrid, stellarSystem, dustSystem, instrumentSystem
         self.packages = float(packages); self.mwr = float(minWeightReduction); self.minfs = float(minScattEvents)
         self.xi = float(scattBias); self.seed = int(seed); self.storeabs = bool(storeAbsorption)
@@ -471,8 +472,9 @@ class MonteCarloSimulation:
         if self.packages > 1e15:
             raise FatalError("Number of photon packages is larger than implementation limit of 1e15")     # MonteCarloSimulation.cpp:62-63
         self.rank, self.nranks = int(rank), int(nranks)
-        self.engine = Engine(device)
+        self.engine = engine if engine is not None else Engine(device)      # one engine per process / GPU
         self._setup = False
+        self.comm_ms = {}           # device time of the collectives of the last phases (ms), by accumulator
 
     def setup(self):
         """uploads every table (the engine-side equivalent of Simulation::setup)"""
@@ -498,8 +500,11 @@ class MonteCarloSimulation:
         st = self.engine.run_stellar(npr, total_packages=total, min_weight_reduction=self.mwr,
                                      min_scatt_events=self.minfs, scatt_bias=self.xi, store_absorption=self.storeabs,
                                      seed=self.seed, stream_offset=offset)
-        if self.nranks > 1:
-            self.engine.allreduce_results()      # Instrument::sumResults / PanDustSystem::sumResults
+        # the stellar absorption table is summed over the processes once, here (the reference does it when the first dust
+        # emission spectra are made: PanDustSystem::calculatedustemission(true) -> sumResults(true), PanDustSystem.cpp:383-404);
+        # the detector arrays are summed once, when they are read (Instrument::write -> sumResults, Instrument.cpp:57-65)
+        if self.nranks > 1 and self.storeabs:
+            self.comm_ms["labs_stellar"] = self.engine.allreduce(REDUCE_LABS_STELLAR)
         return st
 
     # ---- dust emission phases (PanMonteCarloSimulation.cpp:105-264) --------------------------------------------------
@@ -554,9 +559,12 @@ class MonteCarloSimulation:
                     npr, offset, total = shard_packets(self.packages * factor, self.rank, self.nranks)
                     self.engine.run_dust(1, Lv, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
                                          scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
+                # PanDustSystem::sumResults(false): the dust table of this cycle, summed over the processes before the next
+                # spectra are made from it; PanDustSystem::Labsdusttot(): the same number on every rank, so that all of
+                # them take the same convergence decision (PanMonteCarloSimulation.cpp:152-167)
                 if self.nranks > 1:
-                    self.engine.allreduce_results()
-                tot = float(self.engine.fetch_labs_dust().sum())
+                    self.comm_ms.setdefault("labs_dust_cycles", []).append(self.engine.allreduce(REDUCE_LABS_DUST))
+                tot = self.engine.labs_dust_total()
                 eps = abs((tot - prev) / tot) if tot else 0.0
                 prev = tot; history.append((stage, cycle, tot, eps))
                 if (stage < 2 or cycle > 1) and eps < epsmax:
@@ -566,15 +574,17 @@ class MonteCarloSimulation:
 
     def rundustemission(self, dustlib=None, emissionBias=0.5, emissionBoost=1.0):
         """PanMonteCarloSimulation::rundustemission (PanMonteCarloSimulation.cpp:242-264)"""
-        st = self._shoot_dust(2, dustlib, self.packages * emissionBoost, self.seed + 999983, emission_bias=emissionBias)
-        if self.nranks > 1:
-            self.engine.allreduce_results()
-        return st
+        return self._shoot_dust(2, dustlib, self.packages * emissionBoost, self.seed + 999983, emission_bias=emissionBias)
 
     def results(self, pinned=False):
         """detector arrays and absorption table on the host; pinned=True keeps page-locked result buffers alive across
         calls so that every fetch is a single DMA transfer"""
         out = {}
+        if self.nranks > 1:
+            # Instrument::sumResults at write() time: once (the engine skips arrays that already hold the sum)
+            ms = self.engine.allreduce(REDUCE_INSTRUMENTS)
+            if ms:
+                self.comm_ms["instruments"] = ms
         buf = self.__dict__.setdefault("_pinned", {}) if pinned else None
         def dest(key, shape):
             if buf is None:
