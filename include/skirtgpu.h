@@ -99,6 +99,12 @@ int skg_path_fill(skg_engine* e, int mem, int64_t n, const double* r, const doub
 /* DustSystem::opticaldepth(pp, distance) (DustSystem.cpp:984-1000); distance may be NULL (= DBL_MAX) */
 int skg_opticaldepth(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
                      const double* distance, double* tau);
+/* the same quantity computed with the walker of the photon SHOOTING stages (skg_run_stellar / skg_run_dust), whose results
+ * are Monte Carlo estimates gated at 3 sigma rather than bit-exact paths: on Cartesian grids that walker carries the
+ * crossing in the path-length parameter (no divisions; csrc/geom.cuh CartFastWalker) and may differ from the exact one by
+ * rounding; on the other grids the two are the same.  Exposed so that the deviation can be measured (tests: <= 1e-10). */
+int skg_opticaldepth_mc(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
+                        const double* distance, double* tau);
 /* DustGrid::whichcell (DustGrid.hpp:89) */
 int skg_whichcell(skg_engine* e, int mem, int64_t n, const double* r, int* m);
 /* number of "stuck packet" escapes / terminations since engine creation (the reference logs warnings,

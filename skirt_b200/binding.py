@@ -220,12 +220,14 @@ class Engine:
         self._chk(self._lib.skg_path_fill(self.h, SKG_DEVICE, C.c_int64(n), _vp(d_r), _vp(d_k), _vp(d_ell), int(ell_stride),
                                           _vp(d_offsets), _vp(d_segments)))
 
-    def opticaldepth(self, r, k, ell, distance=None):
+    def opticaldepth(self, r, k, ell, distance=None, mc_walker=False):
+        """DustSystem::opticaldepth for host rays; mc_walker=True: with the walker of the shooting stages (skg_opticaldepth_mc)"""
         r = _f64(r).reshape(-1, 3); k = _f64(k).reshape(-1, 3); n = len(r)
         ella = _i32(np.atleast_1d(ell)); stride = 1 if len(ella) == n and n > 1 else 0
         d = None if distance is None else _f64(distance)
         tau = np.zeros(n)
-        self._chk(self._lib.skg_opticaldepth(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), _vp(ella), stride, _vp(d), _vp(tau)))
+        fn = self._lib.skg_opticaldepth_mc if mc_walker else self._lib.skg_opticaldepth
+        self._chk(fn(self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), _vp(ella), stride, _vp(d), _vp(tau)))
         return tau
 
     def whichcell(self, r):

@@ -426,25 +426,32 @@ int skg_path_fill(skg_engine* eh, int mem, int64_t n, const double* r, const dou
     });
 }
 
-int skg_opticaldepth(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
-                     const double* distance, double* tau)
+static int opticalDepthImpl(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
+                            const double* distance, double* tau, bool mcWalker)
 {
     return guarded([&]{
         Engine& e = E(eh);
         if (n < 0 || (n > 0 && (!r || !k || !tau || !ell))) throw Error("skg_opticaldepth: bad arguments");
         if (ellStride != 0 && ellStride != 1) throw Error("ell_stride must be 0 or 1");
-        if (mem == SKG_DEVICE) { launchOpticalDepth(e, n, r, k, ell, ellStride, distance, tau); e.sync(); return; }
+        if (mem == SKG_DEVICE) { launchOpticalDepth(e, n, r, k, ell, ellStride, distance, tau, mcWalker); e.sync(); return; }
         for (int64_t i = 0; i < (ellStride ? n : 1); i++) if (ell[i] < 0 || ell[i] >= e.med.Nlambda) throw Error("wavelength index out of range");
         e.scratchR.upload(r, sizeof(double) * 3 * (size_t)n, e.stream); e.scratchK.upload(k, sizeof(double) * 3 * (size_t)n, e.stream);
         e.scratchEll.upload(ell, sizeof(int) * (size_t)(ellStride ? n : 1), e.stream);
         const double* d_dist = nullptr;
         if (distance) { e.scratchDist.upload(distance, sizeof(double) * (size_t)n, e.stream); d_dist = e.scratchDist.as<double>(); }
         e.scratchTau.ensure(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
-        launchOpticalDepth(e, n, e.scratchR.as<double>(), e.scratchK.as<double>(), e.scratchEll.as<int>(), ellStride, d_dist, e.scratchTau.as<double>());
+        launchOpticalDepth(e, n, e.scratchR.as<double>(), e.scratchK.as<double>(), e.scratchEll.as<int>(), ellStride, d_dist, e.scratchTau.as<double>(), mcWalker);
         if (n > 0) SKG_CUDA(cudaMemcpyAsync(tau, e.scratchTau.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
         e.sync();
     });
 }
+
+int skg_opticaldepth(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
+                     const double* distance, double* tau)
+{ return opticalDepthImpl(eh, mem, n, r, k, ell, ellStride, distance, tau, false); }
+int skg_opticaldepth_mc(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
+                        const double* distance, double* tau)
+{ return opticalDepthImpl(eh, mem, n, r, k, ell, ellStride, distance, tau, true); }
 
 int skg_whichcell(skg_engine* eh, int mem, int64_t n, const double* r, int* m)
 {

@@ -109,7 +109,7 @@ void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k,
 void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
                     const int64_t* d_offsets, skg_segment* d_segments);
 void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
-                        const double* d_dist, double* d_tau);
+                        const double* d_dist, double* d_tau, bool mcWalker = false);
 void launchWhichCell(Engine& e, int64_t n, const double* d_r, int* d_m);
 unsigned long long runDivisionSelfTest(Engine& e, unsigned long long n, unsigned long long seed);
 void exclusiveScan(Engine& e, int64_t n, const int* d_counts, int64_t* d_offsets);   // writes n+1 offsets

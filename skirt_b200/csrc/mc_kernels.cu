@@ -32,6 +32,9 @@
 #ifndef SKG_MC_BATCHES
 #define SKG_MC_BATCHES 1     // batches of SKG_PERIOD crossings between two warp votes in the stage kernels
 #endif
+#ifndef SKG_MC_FAST
+#define SKG_MC_FAST true     // the shooting stages walk Cartesian grids with CartFastWalker (geom.cuh); false: the bit-exact walker
+#endif
 #ifndef SKG_OTHER_MINBLOCKS
 #define SKG_OTHER_MINBLOCKS 4     // resident CTAs per SM the stage kernels are compiled for on the tree / adaptive mesh / Voronoi grids
 #endif
@@ -251,25 +254,25 @@ static __device__ __noinline__ int detectFull(const InstrDev& I, int Nlambda, do
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
 template<int KIND, bool SINGLE> struct PeelJob
 {
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = true; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_PEEL_BATCHES;
+    static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = true; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_PEEL_BATCHES;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
-    double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface)
-    double Lw, tau; KappaRho kr; int ell, grp;
-    int ns;                                 // scattering count of the peel-off packet (0: emission, else previous scatterings + 1)
+    double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface): only read by the walker's start(), not kept over the walk
+    // state carried over the walk, kept small (registers are what limits the warps in flight): everything else the
+    // detection needs (position, wavelength, scattering count) is re-read from the packet record in finish()
+    double Lw, tau; int item, ell;
     // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
     // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
     double kext0, pendRho, pendDs;
     static constexpr bool single = SINGLE;  // one dust component: compile-time, no branch in the crossing loop
-    unsigned long long nSeg = 0, nPaths = 0, nDet = 0;
+    unsigned nSeg = 0, nPaths = 0, nDet = 0;
     __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_) : G(G_), cart(c_), P(P_) {}
 
-    __device__ __forceinline__ int begin(int item)
+    __device__ __forceinline__ int begin(int it)
     {
-        Packet* q = P.pool;
-        const int slot = item / P.Ngroups;
-        grp = item % P.Ngroups;
-        const ObsGroup& g = P.groups[grp];
-        const Packet pk = loadPacket(q + slot);
+        item = it;
+        const int slot = it / P.Ngroups;
+        const ObsGroup& g = P.groups[it % P.Ngroups];
+        const Packet pk = loadPacket(P.pool + slot);
         double L = pk.L;
         if (!(L > 0)) return 0;                                 // MonteCarloSimulation.cpp:281
         rx = pk.x; ry = pk.y; rz = pk.z;
@@ -311,9 +314,8 @@ template<int KIND, bool SINGLE> struct PeelJob
             }
             L = L * w;                                              // launchScatteringPeelOff, PhotonPackage.cpp:51-62
         }
-        Lw = L; tau = 0; ns = pk.fresh ? 0 : pk.nscatt + 1;       // launchEmissionPeelOff / launchScatteringPeelOff, PhotonPackage.cpp:34-62
+        Lw = L; tau = 0;
         dx = g.kx; dy = g.ky; dz = g.kz;
-        kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
         kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendRho = 0; pendDs = 0;
         if (!P.med.rho) return 2;                                   // Instrument::opticalDepth: 0 without dust
         nPaths++;
@@ -324,23 +326,31 @@ template<int KIND, bool SINGLE> struct PeelJob
     {
         nSeg++;
         if (single) { tau += (kext0 * pendRho) * pendDs; pendRho = __ldg(P.med.rho + m); pendDs = ds; }
-        else tau += kr(m) * ds;
+        else tau += KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda}(m) * ds;
         return true;
     }
     __device__ __forceinline__ void finish()
     {
-        const ObsGroup& g = P.groups[grp];
+        const ObsGroup& g = P.groups[item % P.Ngroups];
+        // position and scattering count of the peel-off packet (launchEmissionPeelOff / launchScatteringPeelOff,
+        // PhotonPackage.cpp:34-62: 0 for emission, else previous scatterings + 1) from the packet record
+        const Packet* q = P.pool + item / P.Ngroups;
+        const double px = q->x, py = q->y, pz = q->z;
         if (single) tau += (kext0 * pendRho) * pendDs;
         const double Lextf = Lw * exp(-tau);
         for (int c = 0; c < g.count; c++)
         {
             const InstrDev& I = P.instr[g.first + c];
-            if (I.kind == SKG_INSTR_FULL) { nDet += detectFull(I, P.med.Nlambda, rx, ry, rz, ell, Lw, Lextf, ns, P.phase == SKG_PHASE_STELLAR); continue; }
+            if (I.kind == SKG_INSTR_FULL)
+            {
+                const int ns = q->fresh ? 0 : q->nscatt + 1;
+                nDet += detectFull(I, P.med.Nlambda, px, py, pz, ell, Lw, Lextf, ns, P.phase == SKG_PHASE_STELLAR); continue;
+            }
             // SEDInstrument::detect SEDInstrument.cpp:32-42, FrameInstrument::detect FrameInstrument.cpp:32-47, SimpleInstrument.cpp:33-49
             if (I.kind != SKG_INSTR_FRAME) { warpAggregatedAdd(I.sed + ell, Lextf); nDet++; }
             if (I.kind != SKG_INSTR_SED)
             {
-                int l = pixelOnDetector(I, rx, ry, rz);
+                int l = pixelOnDetector(I, px, py, pz);
                 if (l >= 0) { warpAggregatedAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
             }
         }
@@ -364,38 +374,40 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PEEL_MINBLOCKS : 
 // scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
 template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
 {
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
+    static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
     int* counts;
-    double rx, ry, rz, dx, dy, dz;
-    // escape + absorption state.  The reference evaluates L*exp(-tau_start)*(-expm1(-dtau)) per segment
-    // (MonteCarloSimulation.cpp:452); here the attenuation E = exp(-tau_start) is carried along multiplicatively,
-    // E += E*expm1(-dtau): one transcendental per segment instead of two (the forms agree to a few ulp over a path)
-    KappaRho kr; double L, albedo, tau, E, Lsca; double* labs;
-    int slot, ell, nscatt; unsigned rngCtr; bool survive; unsigned long long id; double target;
+    double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface): only read by the walker's start(), not kept over the walk
+    // escape + absorption state carried over the walk, kept small (registers are what limits the warps in flight); the
+    // packet's other fields are re-read from its record when the path has ended.  The reference evaluates
+    // L*exp(-tau_start)*(-expm1(-dtau)) per segment (MonteCarloSimulation.cpp:452); here the attenuation
+    // E = exp(-tau_start) is carried along multiplicatively, E += E*expm1(-dtau): one transcendental per segment instead
+    // of two (the forms agree to a few ulp over a path)
+    double Labs0;                           // (1 - albedo) * L of the packet: what a fully absorbing segment would take (one component)
+    double tau, E, Lsca; double* labs;
+    int slot, ell; bool walked, survive;
     double kext0, pendRho, pendDs; int pendM;      // one-component media: gather now, absorb one crossing later
-    unsigned long long nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
+    // what finish() hands to collective() (alive only during a refill, not over the walk)
+    double Lout, target; unsigned rngOut;
+    unsigned nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
     __device__ AbsorbJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, int* c2_) : G(G_), cart(c_), P(P_), counts(c2_) {}
 
     __device__ __forceinline__ int begin(int item)
     {
-        Packet* q = P.pool;
+        Packet* q = P.pool + item;
         slot = item;
-        survive = false;
-        const Packet pk = loadPacket(q + slot);
-        L = pk.L;
-        if (!(L > 0) || !P.med.rho) return 2;       // nothing to propagate: the slot is recycled in finish()/collective()
+        survive = false; walked = false;
+        Packet pk = loadPacket(q);
+        const double L = pk.L;
+        if (!(L > 0) || !P.med.rho) return 2;       // nothing to propagate: the slot is simply not copied to the next pool
         const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
         ell = pk.ell;
         rx = pk.x; ry = pk.y; rz = pk.z;
         dx = pk.kx; dy = pk.ky; dz = pk.kz;
-        nscatt = pk.nscatt;
-        rngCtr = pk.rngCtr;
-        id = pk.id;
         if (!pk.fresh)
         {
             // ---- simulatescattering, MonteCarloSimulation.cpp:541-549 ----
-            Philox rng; rng.init(P.seed, id, P.rngKind); rng.c2 = rngCtr;
+            Philox rng; rng.init(P.seed, pk.id, P.rngKind); rng.c2 = pk.rngCtr;
             int hmix = 0;
             if (Ncomp > 1)
             {
@@ -420,17 +432,20 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
                 double costheta = (1.0 + g * g - f * f) / (2.0 * g);
                 scatterDirection(rng, costheta, dx, dy, dz);
             }
-            nscatt++; nScatt++;
-            rngCtr = rng.c2;
+            nScatt++;
+            // the scattered packet goes back to its record (new direction, one more scattering, stream position): the walk
+            // keeps none of it in registers
+            pk.kx = dx; pk.ky = dy; pk.kz = dz; pk.nscatt++; pk.rngCtr = rng.c2; pk.fresh = 0;
+            storePacket(q, pk);
         }
         // ---- fillOpticalDepth + simulateescapeandabsorption, :286-288, :438-515 ----
-        kr = KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda};
         labs = P.labs ? P.labs + (size_t)ell * P.med.Ncells : nullptr;
-        double kext0_ = __ldg(P.med.kext + ell), ksca0 = __ldg(P.med.ksca + ell);
-        albedo = kext0_ > 0 ? ksca0 / kext0_ : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
+        kext0 = __ldg(P.med.kext + ell);
+        const double albedo = kext0 > 0 ? __ldg(P.med.ksca + ell) / kext0 : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
+        Labs0 = SINGLE ? (1.0 - albedo) * L : L;
         tau = 0; E = 1.0; Lsca = 0;
-        kext0 = kext0_; pendM = -1; pendRho = 0; pendDs = 0;
-        nPaths++;
+        pendM = -1; pendRho = 0; pendDs = 0;
+        nPaths++; walked = true;
         return 1;
     }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }   // rho(-1,h) = 0: dtau = 0, nothing absorbed
@@ -442,7 +457,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
         if (STORE)
         {
             double x = expm1Small(-dtau);
-            atomicAdd(labs + pendM, (1.0 - albedo) * (L * E * (-x)));
+            atomicAdd(labs + pendM, Labs0 * (E * (-x)));
             E += E * x;
             nAbs++;
         }
@@ -471,7 +486,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
             double alb = (kext > 0.0) ? ksca / kext : 0.0;
             double dtau = krr * ds;
             double x = expm1Small(-dtau);
-            double Lintm = L * E * (-x);
+            double Lintm = Labs0 * E * (-x);        // Labs0 = L for several components
             E += E * x;
             Lsca += alb * Lintm;
             if (STORE) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
@@ -481,19 +496,20 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
     }
     __device__ __forceinline__ void finish()
     {
-        if (!(L > 0) || !P.med.rho) return;
-        Packet* q = P.pool;
+        if (!walked) return;
         if (SINGLE) { absorbPending(); pendM = -1; }
+        const Packet* q = P.pool + slot;
         const double taupath = tau;
-        if (SINGLE) L = L * albedo * (-expm1(-taupath));
+        double L = q->L;
+        if (SINGLE) { const double albedo = kext0 > 0 ? __ldg(P.med.ksca + ell) / kext0 : 0.0; L = L * albedo * (-expm1(-taupath)); }
         else L = Lsca;
         // ---- termination test, :289 ----
         const double Lthreshold = __ldg(P.Ltot + ell) / P.Lscale / P.minWeightReduction;
-        survive = !(L <= 0 || (L <= Lthreshold && nscatt >= P.minfs));
+        survive = !(L <= 0 || (L <= Lthreshold && q->nscatt >= P.minfs));
         if (survive)
         {
             // ---- simulatepropagation, :519-533: sample the interaction optical depth, weight for the bias ----
-            Philox rng; rng.init(P.seed, id, P.rngKind); rng.c2 = rngCtr;
+            Philox rng; rng.init(P.seed, q->id, P.rngKind); rng.c2 = q->rngCtr;
             double t = 0;
             if (taupath != 0.0)
             {
@@ -508,8 +524,9 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
                 }
             }
             target = t;
-            rngCtr = rng.c2;
+            rngOut = rng.c2;
         }
+        Lout = L;
     }
     __device__ __forceinline__ void collective(bool fin)
     {
@@ -517,8 +534,8 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
         const int pos = warpAppendPosition(fin && survive, counts);
         if (pos >= 0)
         {
-            Packet pk; pk.x = rx; pk.y = ry; pk.z = rz; pk.kx = dx; pk.ky = dy; pk.kz = dz;
-            pk.L = L; pk.target = target; pk.id = id; pk.ell = ell; pk.nscatt = nscatt; pk.rngCtr = rngCtr; pk.fresh = 0; pk.pad = 0;
+            Packet pk = loadPacket(P.pool + slot);
+            pk.L = Lout; pk.target = target; pk.rngCtr = rngOut; pk.fresh = 0; pk.pad = 0;
             storePacket(P.poolNext + pos, pk);
         }
     }
@@ -541,12 +558,12 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS 
 // DustGridPath::pathlength (DustGridPath.cpp:162-173) evaluated on the fly + PhotonPackage::propagate (PhotonPackage.cpp:93-96)
 template<int KIND, bool SINGLE> struct PropagateJob
 {
-    static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
+    static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
     const McDev& P;
     double rx, ry, rz, dx, dy, dz;
-    KappaRho kr; double target, sPrev, tauPrev, result; bool found; int slot;
+    double target, sPrev, tauPrev, result; bool found; int slot, ell;
     double kext0, pendRho, pendDs; bool pending; static constexpr bool single = SINGLE;      // one-component media: gather now, test one crossing later
-    unsigned long long nSeg = 0, nPaths = 0;
+    unsigned nSeg = 0, nPaths = 0;
     __device__ explicit PropagateJob(const McDev& P_) : P(P_) {}
     __device__ __forceinline__ int begin(int item)
     {
@@ -555,9 +572,8 @@ template<int KIND, bool SINGLE> struct PropagateJob
         const Packet pk = loadPacket(q + slot);
         target = pk.target;
         if (!(target > 0)) return 0;
-        const int ell = pk.ell;
+        ell = pk.ell;
         rx = pk.x; ry = pk.y; rz = pk.z; dx = pk.kx; dy = pk.ky; dz = pk.kz;
-        kr = KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda};
         sPrev = 0; tauPrev = 0; result = 0; found = false;
         kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pending = false; pendRho = 0; pendDs = 0;
         nPaths++;
@@ -573,7 +589,7 @@ template<int KIND, bool SINGLE> struct PropagateJob
             pending = true; pendRho = __ldg(P.med.rho + m); pendDs = ds;
             return cont;
         }
-        return test(kr(m) * ds, ds);
+        return test(KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda}(m) * ds, ds);
     }
     __device__ __forceinline__ bool test(double dtau, double ds)
     {
@@ -593,7 +609,10 @@ template<int KIND, bool SINGLE> struct PropagateJob
         Packet* q = P.poolNext;      // the survivors the absorb stage just compacted
         if (single && pending && !found) test((kext0 * pendRho) * pendDs, pendDs);
         const double s = found ? result : sPrev;
-        q[slot].x = rx + s * dx; q[slot].y = ry + s * dy; q[slot].z = rz + s * dz;
+        // PhotonPackage::propagate: r += s k, with r and k from the record (not kept in registers over the walk)
+        Packet* w = q + slot;
+        const double px = w->x, py = w->y, pz = w->z, kx = w->kx, ky = w->ky, kz = w->kz;
+        w->x = px + s * kx; w->y = py + s * ky; w->z = pz + s * kz;
     }
     __device__ __forceinline__ void collective(bool) {}
     __device__ __forceinline__ void periodic() {}

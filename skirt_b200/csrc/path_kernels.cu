@@ -23,6 +23,7 @@ struct RayJobBase
     const double* r; const double* k;
     double rx, ry, rz, dx, dy, dz;
     static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH, kCartRhoAhead = false; static constexpr int kBatches = 1;
+    static constexpr bool kCartFast = false;        // the deterministic-geometry entry points are bit-exact
     __device__ __forceinline__ void loadRay(int i)
     { rx = r[3 * (size_t)i]; ry = r[3 * (size_t)i + 1]; rz = r[3 * (size_t)i + 2]; dx = k[3 * (size_t)i]; dy = k[3 * (size_t)i + 1]; dz = k[3 * (size_t)i + 2]; }
     __device__ __forceinline__ void collective(bool) {}
@@ -41,8 +42,9 @@ struct CountJob : RayJobBase
 
 // DustSystem::opticaldepth(pp, distance), DustSystem.cpp:984-1000 + DustGridPath::opticalDepth, DustGridPath.hpp:97-108:
 // the overshooting segment is counted in full, then the walk stops
-struct TauJob : RayJobBase
+template<bool FAST> struct TauJobT : RayJobBase
 {
+    static constexpr bool kCartFast = FAST;         // FAST: the walker of the shooting stages (skg_opticaldepth_mc)
     const int* ell; int ellStride; Medium med; const double* dist; double* out;
     KappaRho kr; double distance, sacc, tau; int item;
     __device__ __forceinline__ int begin(int i)
@@ -206,7 +208,7 @@ __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ Gr
     runJobs<KIND>(G, cart, ctr, job, n, work, refill);
 }
 
-template<int KIND>
+template<int KIND, bool FAST>
 __global__ void __launch_bounds__(128) opticalDepthKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem, int refill,
                                                           int n, const double* __restrict__ r, const double* __restrict__ k,
                                                           const int* __restrict__ ell, int ellStride,
@@ -215,7 +217,7 @@ __global__ void __launch_bounds__(128) opticalDepthKernel(const __grid_constant_
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
-    TauJob job; job.r = r; job.k = k; job.ell = ell; job.ellStride = ellStride; job.med = med; job.dist = dist; job.out = tau;
+    TauJobT<FAST> job; job.r = r; job.k = k; job.ell = ell; job.ellStride = ellStride; job.med = med; job.dist = dist; job.out = tau;
     runJobs<KIND>(G, cart, ctr, job, n, work, refill);
 }
 
@@ -262,7 +264,8 @@ static LaunchCfg cfgFor(Engine& e, int64_t n)
         if (!e.attrPath)
         {
             SKG_CUDA(cudaFuncSetAttribute(pathCountKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            SKG_CUDA(cudaFuncSetAttribute(opticalDepthKernel<GRID_CART>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            SKG_CUDA(cudaFuncSetAttribute(opticalDepthKernel<GRID_CART, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            SKG_CUDA(cudaFuncSetAttribute(opticalDepthKernel<GRID_CART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
             e.attrPath = true;
         }
     }
@@ -309,14 +312,16 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
 }
 
 void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
-                        const double* d_dist, double* d_tau)
+                        const double* d_dist, double* d_tau, bool mcWalker)
 {
     if (n <= 0) return;
     if (!e.med.rho) throw Error("skg_opticaldepth needs skg_medium first");
     if (e.med.Ncells != e.Ncells) throw Error("the medium has " + std::to_string(e.med.Ncells) + " cells but the grid has " + std::to_string(e.Ncells) + ": call skg_medium again");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
-    SKG_DISPATCH(e, (opticalDepthKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride,
-                                                                                    d_dist, d_tau, c.work)));
+    if (mcWalker)
+    { SKG_DISPATCH(e, (opticalDepthKernel<K, true><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride, d_dist, d_tau, c.work))); }
+    else
+    { SKG_DISPATCH(e, (opticalDepthKernel<K, false><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride, d_dist, d_tau, c.work))); }
     e.launches++; SKG_CUDA(cudaGetLastError());
 }
 

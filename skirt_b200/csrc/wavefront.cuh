@@ -16,6 +16,7 @@
 //   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
 //   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps
 //   static constexpr bool kCartRegBorders, kCartTinySelect   variant of the Cartesian walker (geom.cuh)
+//   static constexpr bool kCartFast         the shooting stages' t-parameterised Cartesian walker instead of the bit-exact one
 //   static constexpr bool kCartRhoAhead     Cartesian walker: pull the next cell's density into L1 at the end of a crossing
 //   static constexpr bool kTreeHints        tree walker: wall-bin table for walls with several neighbours (geom.cuh)
 //   static constexpr int kBatches           batches of SKG_PERIOD crossings between two votes / periodic() calls
@@ -123,7 +124,11 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
 template<int KIND, class Job, class Grids>
 __device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Counters* ctr, Job& job, int n, int* workCounter, int refill = 8)
 {
-    if (KIND == GRID_CART) runJobsStep<CartWalkerT<Job::kCartRegBorders, Job::kCartTinySelect, Job::kCartRhoAhead>>(cart, ctr, job, n, workCounter, refill);
+    if (KIND == GRID_CART)
+    {
+        if (Job::kCartFast) runJobsStep<CartFastWalker>(cart, ctr, job, n, workCounter, refill);
+        else runJobsStep<CartWalkerT<Job::kCartRegBorders, Job::kCartTinySelect, Job::kCartRhoAhead>>(cart, ctr, job, n, workCounter, refill);
+    }
     else if (KIND == GRID_TREE) runJobsStep<TreeWalkerT<Job::kTreeHints>>(G.tree, ctr, job, n, workCounter, refill);
     else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter, refill);
     else runJobsStep<VoroWalker>(G.voro, ctr, job, n, workCounter, refill);

@@ -190,3 +190,36 @@ def test_deep_grids_against_the_reference(engine, kind):
     assert len(ref["m"]) > 4 * len(r)
     assert common.paths_bit_identical(got, ref), kind
     assert engine.stuck_counts()[1] == 0
+
+
+@pytest.mark.parametrize("name", common.GEOM_CASES)
+def test_shooting_walker_agrees_with_the_exact_walker(engine, name):
+    """skg_opticaldepth_mc: the walker the photon shooting stages use (on Cartesian grids the division-free,
+    path-length-parameterised CartFastWalker) against the bit-exact one and the reference's golden optical depths --
+    random and adversarial rays (axis-aligned, on faces/edges/corners, |k_a| < 1e-15, grazing).  The Monte Carlo gate is
+    3 sigma (north_star); this bounds the systematic part: 1e-10 relative, with an absolute floor of 1e-13 x the largest
+    optical depth for rays whose whole path is a rounding-sized sliver"""
+    _, _, d = _setup(engine, name)
+    for dist, want in ((None, d["tau_inf"]), (d["distance"], d["tau_dist"])):
+        tau = engine.opticaldepth(d["r"], d["k"], 0, dist, mc_walker=True)
+        if not name.startswith("cart"):
+            assert np.array_equal(tau, engine.opticaldepth(d["r"], d["k"], 0, dist))
+            continue
+        if dist is None:
+            np.testing.assert_allclose(tau, want, rtol=1e-10, atol=1e-13 * float(np.max(want)))
+        else:
+            # a cut-off distance ends the walk with the first segment beyond it: where a segment boundary lies within rounding
+            # of the distance the two walkers may stop one segment apart -- allow that for a handful of rays, no more
+            bad = ~np.isclose(tau, want, rtol=1e-10, atol=1e-13 * float(np.max(want)))
+            assert bad.sum() <= max(2, len(tau) // 500), f"{bad.sum()} of {len(tau)} rays differ"
+
+
+def test_shooting_walker_on_the_full_size_grid(engine):
+    """2^18 rays through the 100^3 grid of C1/C2: exact and shooting walkers agree to 1e-10 on every optical depth"""
+    from skirt_b200 import configs
+    m = configs.build(configs.c2_params(n=100, nlambda=3, packages=10), engine=engine).setup()
+    r, k = common.rays(1 << 18, configs.C1_BOX, seed=77)
+    ell = np.full(len(r), 1, np.int32)
+    a = engine.opticaldepth(r, k, ell); b = engine.opticaldepth(r, k, ell, mc_walker=True)
+    assert a.max() > 0
+    np.testing.assert_allclose(b, a, rtol=1e-10, atol=1e-13 * float(a.max()))
