@@ -1,6 +1,7 @@
 // Engine object + C ABI (include/skirtgpu.h).  Product path: fails loudly without a CUDA device; there is
 // no CPU fallback and nothing here touches the test oracles.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include "engine.h"
@@ -132,6 +133,15 @@ int skg_grid_cartesian(skg_engine* eh, const double* xv, int Nx, const double* y
         // BoxDustGrid extent: for every Mesh of the reference mesh[0]=0 and mesh[N]=1, so that the borders'
         // end points equal the extent (CartesianDustGrid.cpp:34-36)
         e.cart.ext[0] = xv[0]; e.cart.ext[1] = xv[Nx]; e.cart.ext[2] = yv[0]; e.cart.ext[3] = yv[Ny]; e.cart.ext[4] = zv[0]; e.cart.ext[5] = zv[Nz];
+        // uniform meshes (LinMesh on every axis, NR::lingrid NR.hpp:171-176): the shooting stages then step the exit
+        // parameters by a constant per axis instead of reading the borders (CartFastWalker<true>)
+        auto uniformAxis = [](const double* v, int n) {
+            const double w = (v[n] - v[0]) / n;
+            for (int i = 0; i <= n; i++) if (std::fabs(v[i] - (v[0] + i * w)) > 1e-12 * std::fabs(v[n] - v[0])) return false;
+            return true; };
+        e.cart.uniform = uniformAxis(xv, Nx) && uniformAxis(yv, Ny) && uniformAxis(zv, Nz);
+        if (const char* v = getenv("SKG_CART_UNIFORM")) e.cart.uniform = e.cart.uniform && atoi(v) != 0;
+        e.cart.wx = (xv[Nx] - xv[0]) / Nx; e.cart.wy = (yv[Ny] - yv[0]) / Ny; e.cart.wz = (zv[Nz] - zv[0]) / Nz;
         e.gridKind = GRID_CART; e.Ncells = Nx * Ny * Nz;
         e.sync();
     });
@@ -359,6 +369,9 @@ int skg_medium(skg_engine* eh, int Ncells, int Ncomp, int Nlambda, const double*
         Engine& e = E(eh);
         if (Ncells < 1 || Ncomp < 1 || Nlambda < 1 || !rho || !kext) throw Error("medium tables missing");
         if (e.gridKind != GRID_NONE && Ncells != e.Ncells) throw Error("medium has " + std::to_string(Ncells) + " cells but the grid has " + std::to_string(e.Ncells));
+        // the density table is read in aligned 32-byte sectors by the shooting stages (RhoSector): one spare sector at the end
+        e.rho.ensure(sizeof(double) * (size_t)Ncells * Ncomp + 64);
+        SKG_CUDA(cudaMemsetAsync(static_cast<char*>(e.rho.p) + sizeof(double) * (size_t)Ncells * Ncomp, 0, 64, e.stream));
         e.rho.upload(rho, sizeof(double) * (size_t)Ncells * Ncomp, e.stream);
         e.kext.upload(kext, sizeof(double) * (size_t)Ncomp * Nlambda, e.stream);
         std::vector<double> zeros((size_t)Ncomp * Nlambda, 0.0);

@@ -81,7 +81,7 @@ struct Engine
     DevBuf dustLv, dustCdf, dustLtot;       // per-wavelength cell luminosities of a dust phase, their CDFs and totals
     DevBuf labsT;                           // scratch for the (m,ell) row-major copy handed to the host
     int instrNlambda = 0;                   // number of wavelengths the detector arrays were allocated for
-    DevBuf instrGroupedDev, groupsDev; int Ngroups = 0;    // instruments ordered by line of sight + the groups
+    DevBuf instrGroupedDev, groupsDev; int Ngroups = 0, maxGroupCount = 0;    // instruments ordered by line of sight + the groups
     DevBuf mcPool, mcLists, mcCounts, mcEllList; int* mcHostCounts = nullptr;   // packet pool of the wavefront shooter
     void* nccl = nullptr; int rank = 0, nranks = 1;
     // what each accumulator holds with respect to the other processes (skg_allreduce): nothing since the last reset,

@@ -171,6 +171,7 @@ __device__ __forceinline__ bool cartEnter(const CartGrid& g, double& x, double& 
 // essentially never take.
 template<bool REGB, bool TINYSEL, bool AHEAD = false> struct CartWalkerT
 {
+    static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 4;       // crossings of a batch unrolled in the scheduler (wavefront.cuh): the step is ~100 instructions
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;       // 1/k per axis (see divInvariant)
@@ -263,15 +264,21 @@ template<bool REGB, bool TINYSEL, bool AHEAD = false> struct CartWalkerT
 // the order of an ulp of t per segment (they do not accumulate: every t_a is computed from the border itself) and, at a
 // crossing through a cell edge within that rounding, the order of two zero-length neighbours; skg_opticaldepth_mc exposes
 // this walker so that tests can bound the deviation from the exact one.
+// UNIFORM (every axis a LinMesh): consecutive borders of an axis are one bin width apart, so the exit parameter of
+// the crossed axis advances by the constant |width / k_a| -- no shared-memory read at all in the crossing, and the walker
+// only counts the cells left along each axis.  (The additions drift by an ulp of t per crossing, far inside the 1e-10 the
+// walker is held to.)  Otherwise the next border is read from the staged arrays and t_a = fma(border, 1/k_a, -r0_a/k_a).
 #ifndef SKG_FAST_UNROLL
 #define SKG_FAST_UNROLL 4
 #endif
-struct CartFastWalker
+template<bool UNIFORM> struct CartFastWalkerT
 {
     static constexpr int kStepUnroll = SKG_FAST_UNROLL;
+    static constexpr bool kPredicated = true;       // provides stepLive(): the scheduler runs batches of crossings branch-free
     double tx, ty, tz, t;
-    double rkx, rky, rkz, cx, cy, cz;
-    int ox, oy, oz, stx, sty, stz, dmx, dmy, dmz, m;
+    double rkx, rky, rkz, cx, cy, cz;               // UNIFORM: rk* hold the constant steps |w_a / k_a|, c* are unused
+    int ox, oy, oz, stx, sty, stz;                  // UNIFORM: o* count the cells left along each axis (current one included)
+    int dmx, dmy, dmz, m;
     bool alive;
 
     __device__ __forceinline__ bool start(const CartGrid& g, Counters*, double x, double y, double z, double kx, double ky, double kz, Entry& en)
@@ -282,34 +289,61 @@ struct CartFastWalker
         const int Ny = g.Ny, Nz = g.Nz;
         m = k + Nz * j + Nz * Ny * i;
         const bool nx = kx < 0.0, ny = ky < 0.0, nz = kz < 0.0;
-        ox = 8 * (i + (nx ? 0 : 1)); oy = 8 * (j + (ny ? 0 : 1)); oz = 8 * (k + (nz ? 0 : 1));
-        stx = nx ? -8 : 8; sty = ny ? -8 : 8; stz = nz ? -8 : 8;
         dmx = nx ? -Ny * Nz : Ny * Nz; dmy = ny ? -Nz : Nz; dmz = nz ? -1 : 1;
         const bool ax = fabs(kx) > 1e-15, ay = fabs(ky) > 1e-15, az = fabs(kz) > 1e-15;
-        rkx = ax ? 1.0 / kx : 0.0; rky = ay ? 1.0 / ky : 0.0; rkz = az ? 1.0 / kz : 0.0;
-        cx = ax ? -x * rkx : SKG_DBL_MAX; cy = ay ? -y * rky : SKG_DBL_MAX; cz = az ? -z * rkz : SKG_DBL_MAX;
-        tx = __fma_rn(ldsF64(g.sx + ox), rkx, cx); ty = __fma_rn(ldsF64(g.sy + oy), rky, cy); tz = __fma_rn(ldsF64(g.sz + oz), rkz, cz);
+        const double ikx = ax ? 1.0 / kx : 0.0, iky = ay ? 1.0 / ky : 0.0, ikz = az ? 1.0 / kz : 0.0;
+        const double ccx = ax ? -x * ikx : SKG_DBL_MAX, ccy = ay ? -y * iky : SKG_DBL_MAX, ccz = az ? -z * ikz : SKG_DBL_MAX;
+        const int ex = 8 * (i + (nx ? 0 : 1)), ey = 8 * (j + (ny ? 0 : 1)), ez = 8 * (k + (nz ? 0 : 1));      // exit borders of the first cell
+        tx = __fma_rn(ldsF64(g.sx + ex), ikx, ccx); ty = __fma_rn(ldsF64(g.sy + ey), iky, ccy); tz = __fma_rn(ldsF64(g.sz + ez), ikz, ccz);
+        if (UNIFORM)
+        {
+            rkx = fabs(g.wx * ikx); rky = fabs(g.wy * iky); rkz = fabs(g.wz * ikz);
+            ox = nx ? i + 1 : g.Nx - i; oy = ny ? j + 1 : Ny - j; oz = nz ? k + 1 : Nz - k;
+        }
+        else
+        {
+            rkx = ikx; rky = iky; rkz = ikz; cx = ccx; cy = ccy; cz = ccz;
+            ox = ex; oy = ey; oz = ez; stx = nx ? -8 : 8; sty = ny ? -8 : 8; stz = nz ? -8 : 8;
+        }
         t = 0.0;
         alive = true;
         return true;
     }
 
-    __device__ __forceinline__ bool step(const CartGrid& g, Counters*, int& mseg, double& ds)
+    // One crossing, fully predicated: `live` lanes advance, the others keep their state (so that the scheduler can run a
+    // batch of crossings without a branch around each one).  Only the crossed axis is touched -- three small predicated
+    // blocks instead of selects over the per-axis constants.  Returns true when segment (mseg, ds) is to be added; clears
+    // `live` when the ray has left the grid (the staged arrays carry one pad element on either side: the last read is harmless).
+    __device__ __forceinline__ bool stepLive(const CartGrid& g, bool& live, int& mseg, double& ds)
     {
-        const bool bx = tx <= ty && tx <= tz;
-        const bool by = !bx && ty <= tz;
-        const bool bz = !bx && !by;
+        const bool bx = live && tx <= ty && tx <= tz;
+        const bool by = live && !bx && ty <= tz;
+        const bool bz = live && !bx && !by;
         const double tn = bx ? tx : (by ? ty : tz);
         mseg = m;
-        ds = tn - t; t = tn;
-        ox += bx ? stx : 0; oy += by ? sty : 0; oz += bz ? stz : 0;
-        m += bx ? dmx : (by ? dmy : dmz);
-        // the staged arrays carry one pad element on either side: the read is harmless when the ray has just left the grid
-        const double E = ldsF64(bx ? g.sx + ox : (by ? g.sy + oy : g.sz + oz));
-        const double tnew = __fma_rn(E, bx ? rkx : (by ? rky : rkz), bx ? cx : (by ? cy : cz));
-        tx = bx ? tnew : tx; ty = by ? tnew : ty; tz = bz ? tnew : tz;
-        alive = (unsigned)ox <= 8u * g.Nx && (unsigned)oy <= 8u * g.Ny && (unsigned)oz <= 8u * g.Nz;
-        return ds > 0;
+        ds = tn - t;
+        const bool seg = live && ds > 0;
+        if (live) t = tn;
+        if (UNIFORM)
+        {
+            if (bx) { tx += rkx; m += dmx; live = --ox > 0; }
+            if (by) { ty += rky; m += dmy; live = --oy > 0; }
+            if (bz) { tz += rkz; m += dmz; live = --oz > 0; }
+        }
+        else
+        {
+            if (bx) { ox += stx; m += dmx; tx = __fma_rn(ldsF64(g.sx + ox), rkx, cx); live = (unsigned)ox <= 8u * g.Nx; }
+            if (by) { oy += sty; m += dmy; ty = __fma_rn(ldsF64(g.sy + oy), rky, cy); live = (unsigned)oy <= 8u * g.Ny; }
+            if (bz) { oz += stz; m += dmz; tz = __fma_rn(ldsF64(g.sz + oz), rkz, cz); live = (unsigned)oz <= 8u * g.Nz; }
+        }
+        return seg;
+    }
+    __device__ __forceinline__ bool step(const CartGrid& g, Counters*, int& mseg, double& ds)
+    {
+        bool live = true;
+        const bool seg = stepLive(g, live, mseg, ds);
+        alive = live;
+        return seg;
     }
 };
 
@@ -425,6 +459,7 @@ __device__ __forceinline__ double nextAfterAlong(double v, double k)
 #endif
 template<bool HINT> struct TreeWalkerT
 {
+    static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;       // large step body: a plain loop (unrolling it costs more in instruction fetch than it gains)
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
@@ -707,6 +742,7 @@ __device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, doub
 // AdaptiveMesh::path (AdaptiveMesh.cpp:297-367) one crossing at a time
 struct AMeshWalker
 {
+    static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
@@ -907,6 +943,7 @@ __device__ __forceinline__ int voroCellIndex(const VoroGrid& g, double x, double
 // VoronoiMesh::path (VoronoiMesh.cpp:749-844) one crossing at a time
 struct VoroWalker
 {
+    static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;
     double x, y, z, kx, ky, kz;
     int mr, rr;                 // current cell and the first slot of its crossing record

@@ -64,7 +64,7 @@ struct McDev
     const double* Lcdf;     // [Nlambda*(Nsources+1)]
     double emissionBias;
     const InstrDev* instr; int Ninstr;      // sorted by observer group
-    const ObsGroup* groups; int Ngroups;
+    const ObsGroup* groups; int Ngroups; int maxGroupCount;     // largest number of instruments sharing one line of sight
     double* labs;           // [Nlambda*Ncells] (wavelength-major on the device) or null
     double Lscale;          // total packets per wavelength over all engines
     double minWeightReduction, minfs, xi;
@@ -84,12 +84,14 @@ struct McDev
     int peelRefill;         // the same for the peel-off stage (one item per packet and observer direction: cheap to begin)
 };
 
-// expm1 for the per-segment absorbed fraction -expm1(-dtau) (MonteCarloSimulation.cpp:452): most segments have a small
-// optical depth, where the Taylor polynomial up to x^8/8! is accurate to better than one ulp (remainder < 3e-18
-// relative for |x| <= 2^-5) and costs 8 FMAs; larger arguments use the library function
-__device__ __forceinline__ double expm1Small(double x)
+// expm1(x) for x <= 0: the per-segment absorbed fraction -expm1(-dtau) (MonteCarloSimulation.cpp:452).  Two branch-free
+// forms, chosen per WARP (the library function is a long, divergent slow path that segments with a large optical depth
+// would drag the whole warp through): when every lane's argument is small, the Taylor polynomial up to x^8/8! (remainder
+// < 3e-18 relative for |x| <= 2^-5, 8 FMAs); otherwise x = k ln2 + r with |r| <= ln2/2, expm1(r) by its Taylor
+// polynomial up to r^13/13! (remainder < 5e-16 relative) and expm1(x) = 2^k expm1(r) + (2^k - 1) -- exact cancellation-
+// free for k = 0, and correct to ~1 ulp of the result elsewhere.
+__device__ __forceinline__ double expm1Poly8(double x)
 {
-    if (fabs(x) > 0.03125) return expm1(x);
     double p = 1.0 / 40320.0;
     p = __fma_rn(p, x, 1.0 / 5040.0);
     p = __fma_rn(p, x, 1.0 / 720.0);
@@ -100,6 +102,77 @@ __device__ __forceinline__ double expm1Small(double x)
     p = __fma_rn(p, x, 1.0);
     return p * x;
 }
+__device__ __forceinline__ double expm1Reduced(double x)
+{
+    x = fmax(x, -700.0);                                            // exp(-700) ~ 1e-304: expm1 = -1 to the last bit
+    const double kf = rint(x * 1.4426950408889634074);
+    double r = __fma_rn(kf, -6.93147180369123816490e-01, x);        // Cody-Waite: ln2 = hi + lo
+    r = __fma_rn(kf, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = __fma_rn(p, r, 1.0 / 479001600.0);
+    p = __fma_rn(p, r, 1.0 / 39916800.0);
+    p = __fma_rn(p, r, 1.0 / 3628800.0);
+    p = __fma_rn(p, r, 1.0 / 362880.0);
+    p = __fma_rn(p, r, 1.0 / 40320.0);
+    p = __fma_rn(p, r, 1.0 / 5040.0);
+    p = __fma_rn(p, r, 1.0 / 720.0);
+    p = __fma_rn(p, r, 1.0 / 120.0);
+    p = __fma_rn(p, r, 1.0 / 24.0);
+    p = __fma_rn(p, r, 1.0 / 6.0);
+    p = __fma_rn(p, r, 0.5);
+    p = __fma_rn(p, r, 1.0);
+    const double e = p * r;                                         // expm1(r)
+    const double s = __longlong_as_double((long long)((int)kf + 1023) << 52);      // 2^k, k in [-1010, 0]
+    return __fma_rn(s, e, s - 1.0);
+}
+__device__ __forceinline__ double expm1Small(double x)
+{
+    if (__any_sync(__activemask(), x < -0.03125)) return expm1Reduced(x);
+    return expm1Poly8(x);
+}
+
+// One-component media: the density gather of the shooting stages.  A random 8-byte gather costs the SM's load/store unit
+// one wavefront per lane whatever its width, and that -- not arithmetic -- is what bounds the stage kernels.  So a lane
+// reads the whole aligned 32-byte SECTOR that holds its cell (four consecutive cell numbers: on a Cartesian grid four
+// neighbours along z, m = k + Nz*j + Nz*Ny*i) with one 256-bit load and keeps it: the next crossings along z, the most
+// frequent ones in flattened grids, find their density in registers.  touch() starts the load of the sector of cell m
+// unless it is the one held; get() picks a cell of the held sector.  Jobs consume a segment one crossing after it was
+// parked (same summation order as without the cache), so the load has a crossing's worth of time to land.
+// Measured on B200 (profiles/r02_f_sweep.txt): SLOWER than the plain 8-byte gather -- peel 68 -> 85 ms, absorb 130 -> 146 ms
+// per C2 phase (a random 256-bit load occupies the load/store data path four times as long, and the eight extra
+// registers cost occupancy) -- so it is compiled out; kept as a switch for the record.
+#ifndef SKG_RHO_SECTOR
+#define SKG_RHO_SECTOR 0
+#endif
+#if !SKG_RHO_SECTOR
+struct RhoSector        // experiment switch: plain 8-byte gather per crossing
+{
+    double c0; int group;
+    __device__ __forceinline__ void reset() { group = -1; c0 = 0.0; }
+#ifdef SKG_EXP_NOGATHER
+    __device__ __forceinline__ void touch(const double* rho, int m) { group = m; c0 = 1e-24 * (m & 7); }      // experiment: no density gather
+#else
+    __device__ __forceinline__ void touch(const double* rho, int m) { group = m; c0 = __ldg(rho + m); }
+#endif
+    __device__ __forceinline__ double get(int) const { return c0; }
+};
+#else
+struct RhoSector
+{
+    double c0, c1, c2, c3; int group;
+    __device__ __forceinline__ void reset() { group = -1; c0 = c1 = c2 = c3 = 0.0; }
+    __device__ __forceinline__ void touch(const double* rho, int m)
+    {
+        const int g = m >> 2;
+        if (g != group)
+        {
+            group = g;
+            asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(c0), "=d"(c1), "=d"(c2), "=d"(c3) : "l"(rho + 4 * (size_t)g));
+        }
+    }
+    __device__ __forceinline__ double get(int m) const { const int j = m & 3; return j == 0 ? c0 : (j == 1 ? c1 : (j == 2 ? c2 : c3)); }
+};
+#endif
 
 // ---- accumulation ----------------------------------------------------------------------------------------
 // LockFree::add (LockFree.hpp:25-37) on the device: lanes of a warp that target the same address are summed
@@ -120,6 +193,28 @@ __device__ __forceinline__ void warpAggregatedAdd(double* addr, double v)
     double sum = 0;
     for (unsigned rem = peers; rem; rem &= rem - 1) sum += __shfl_sync(peers, v, __ffs(rem) - 1);
     if (lane == leader) atomicAdd(addr, sum);
+}
+
+// The same for a value that (almost) all lanes of a CONVERGED warp add to one address -- SED bins: one address per
+// wavelength, and the pool holds few adjacent wavelengths at a time.  Called by all 32 lanes; lanes without a
+// contribution pass take = false.  When the contributing lanes agree on the address, the values are summed by a
+// butterfly (5 shuffle steps) and lane 0 issues the one atomic; otherwise every group of equal addresses is served as in
+// warpAggregatedAdd.
+__device__ __forceinline__ void warpConvergedAdd(bool take, double* addr, double v)
+{
+    const unsigned FULL = 0xffffffffu;
+    const unsigned takers = __ballot_sync(FULL, take);
+    if (!takers) return;
+    const int first = __ffs(takers) - 1;
+    double* ref = reinterpret_cast<double*>(__shfl_sync(FULL, (unsigned long long)addr, first));
+    if (__all_sync(FULL, !take || addr == ref))
+    {
+        double sum = take ? v : 0.0;
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(ref, sum);
+        return;
+    }
+    if (take) warpAggregatedAdd(addr, v);
 }
 
 // stream compaction: the lanes with `take` set obtain consecutive positions in an output array, one atomicAdd per warp

@@ -35,6 +35,12 @@
 #ifndef SKG_MC_FAST
 #define SKG_MC_FAST true     // the shooting stages walk Cartesian grids with CartFastWalker (geom.cuh); false: the bit-exact walker
 #endif
+#ifndef SKG_PEEL_DEPTH
+#define SKG_PEEL_DEPTH 4     // crossings between a density gather of the peel-off stage and its use (registers: 4 per level);
+#endif                       // measured per C2 phase: 67.4 / 55.4 / 50.5 ms at depth 1 / 2 / 4 (profiles/r02_h_sweep.txt)
+// (the escape + absorption stage consumes a gather at the NEXT crossing: a deeper FIFO of parked segments measured slower,
+// 132.7 / 139.0 / 181.2 ms per C2 phase at depth 1 / 2 / 4, profiles/r02_i_absorb_depth_sweep.txt -- that stage is bound
+// by its fp64 atomics, 53 of its 130 ms with L2 at 74 %, not by the latency of the gather)
 #ifndef SKG_OTHER_MINBLOCKS
 #define SKG_OTHER_MINBLOCKS 4     // resident CTAs per SM the stage kernels are compiled for on the tree / adaptive mesh / Voronoi grids
 #endif
@@ -262,8 +268,12 @@ template<int KIND, bool SINGLE> struct PeelJob
     double Lw, tau; int item, ell;
     // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
     // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
-    double kext0, pendRho, pendDs;
+    // one-component media: the density gather of a crossing is consumed kDepth crossings later (the optical depth is a
+    // plain sum: the order of its terms is free), so that the L2 latency of the gather overlaps that many crossings
+    static constexpr int kDepth = SKG_PEEL_DEPTH;
+    double kext0, pendRho[kDepth], pendDs[kDepth];
     static constexpr bool single = SINGLE;  // one dust component: compile-time, no branch in the crossing loop
+    double sedAdd;                          // what finish() leaves for collective(): the extincted luminosity for the SED bins
     unsigned nSeg = 0, nPaths = 0, nDet = 0;
     __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_) : G(G_), cart(c_), P(P_) {}
 
@@ -291,10 +301,18 @@ template<int KIND, bool SINGLE> struct PeelJob
         {
             // ---- peeloffscattering, MonteCarloSimulation.cpp:319-363: weight by the phase function towards the observer ----
             const double kx = pk.kx, ky = pk.ky, kz = pk.kz;
-            double wv[8];
-            if (Ncomp == 1) wv[0] = 1.0;
+            const double cosalpha = kx * g.kx + ky * g.ky + kz * g.kz;          // Direction::dot
+            double w = 0;
+            if (SINGLE)
+            {
+                // one component: weight 1 (MonteCarloSimulation.cpp:325-326); DustMix::phaseFunctionValue (HG), DustMix.cpp:665-668
+                const double gg = __ldg(P.med.g + ell);
+                const double tt = 1.0 + gg * gg - 2 * gg * cosalpha;
+                w = (1.0 - gg) * (1.0 + gg) / sqrt(tt * tt * tt);
+            }
             else
             {
+                double wv[8];
                 int mcell = whichCellMC<KIND>(G, cart, rx, ry, rz);
                 if (mcell == -1) return 0;
                 double sum = 0;
@@ -302,33 +320,35 @@ template<int KIND, bool SINGLE> struct PeelJob
                 { wv[c] = __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c); sum += wv[c]; }
                 if (sum <= 0) return 0;
                 for (int c = 0; c < Ncomp && c < 8; c++) wv[c] /= sum;
-            }
-            double cosalpha = kx * g.kx + ky * g.ky + kz * g.kz;            // Direction::dot
-            double w = 0;
-            for (int c = 0; c < Ncomp && c < 8; c++)
-            {
-                // DustMix::phaseFunctionValue (HG), DustMix.cpp:665-668
-                double gg = __ldg(P.med.g + (size_t)c * Nlambda + ell);
-                double tt = 1.0 + gg * gg - 2 * gg * cosalpha;
-                w += wv[c] * ((1.0 - gg) * (1.0 + gg) / sqrt(tt * tt * tt));
+                for (int c = 0; c < Ncomp && c < 8; c++)
+                {
+                    double gg = __ldg(P.med.g + (size_t)c * Nlambda + ell);
+                    double tt = 1.0 + gg * gg - 2 * gg * cosalpha;
+                    w += wv[c] * ((1.0 - gg) * (1.0 + gg) / sqrt(tt * tt * tt));
+                }
             }
             L = L * w;                                              // launchScatteringPeelOff, PhotonPackage.cpp:51-62
         }
         Lw = L; tau = 0;
         dx = g.kx; dy = g.ky; dz = g.kz;
-        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendRho = 0; pendDs = 0;
+        kext0 = single ? __ldg(P.med.kext + ell) : 0.0;
+#pragma unroll
+        for (int q = 0; q < kDepth; q++) { pendRho[q] = 0; pendDs[q] = 0; }
         if (!P.med.rho) return 2;                                   // Instrument::opticalDepth: 0 without dust
         nPaths++;
         return 1;
     }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }
-    __device__ __forceinline__ bool segment(int m, double ds)
+    template<int U> __device__ __forceinline__ bool segmentU(int m, double ds)
     {
         nSeg++;
-        if (single) { tau += (kext0 * pendRho) * pendDs; pendRho = __ldg(P.med.rho + m); pendDs = ds; }
+        constexpr int q = U % kDepth;
+        if (single) { tau += (kext0 * pendRho[q]) * pendDs[q]; pendRho[q] = __ldg(P.med.rho + m); pendDs[q] = ds; }
         else tau += KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda}(m) * ds;
         return true;
     }
+    __device__ __forceinline__ bool segment(int m, double ds) { return segmentU<0>(m, ds); }
+    template<int U> __device__ __forceinline__ void idleU() {}
     __device__ __forceinline__ void finish()
     {
         const ObsGroup& g = P.groups[item % P.Ngroups];
@@ -336,8 +356,13 @@ template<int KIND, bool SINGLE> struct PeelJob
         // PhotonPackage.cpp:34-62: 0 for emission, else previous scatterings + 1) from the packet record
         const Packet* q = P.pool + item / P.Ngroups;
         const double px = q->x, py = q->y, pz = q->z;
-        if (single) tau += (kext0 * pendRho) * pendDs;
+        if (single)
+        {
+#pragma unroll
+            for (int q = 0; q < kDepth; q++) tau += (kext0 * pendRho[q]) * pendDs[q];
+        }
         const double Lextf = Lw * exp(-tau);
+        sedAdd = Lextf;
         for (int c = 0; c < g.count; c++)
         {
             const InstrDev& I = P.instr[g.first + c];
@@ -347,15 +372,30 @@ template<int KIND, bool SINGLE> struct PeelJob
                 nDet += detectFull(I, P.med.Nlambda, px, py, pz, ell, Lw, Lextf, ns, P.phase == SKG_PHASE_STELLAR); continue;
             }
             // SEDInstrument::detect SEDInstrument.cpp:32-42, FrameInstrument::detect FrameInstrument.cpp:32-47, SimpleInstrument.cpp:33-49
-            if (I.kind != SKG_INSTR_FRAME) { warpAggregatedAdd(I.sed + ell, Lextf); nDet++; }
+            // (the SED bins are served by collective(): one address per wavelength, summed over the converged warp)
+            if (I.kind != SKG_INSTR_FRAME) nDet++;
             if (I.kind != SKG_INSTR_SED)
             {
                 int l = pixelOnDetector(I, px, py, pz);
-                if (l >= 0) { warpAggregatedAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
+                if (l >= 0) { atomicAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
             }
         }
     }
-    __device__ __forceinline__ void collective(bool) {}
+    // SED bins (SEDInstrument::detect SEDInstrument.cpp:32-42, SimpleInstrument.cpp:33-49), warp-uniformly: up to
+    // maxCount instruments per observer direction, every lane taking part in every round
+    __device__ __forceinline__ void collective(bool fin)
+    {
+        if (!__any_sync(0xffffffffu, fin)) return;
+        const ObsGroup& g = P.groups[fin ? item % P.Ngroups : 0];
+        const int rounds = P.maxGroupCount;
+        for (int c = 0; c < rounds; c++)
+        {
+            const bool has = fin && c < g.count;
+            const InstrDev& I = P.instr[has ? g.first + c : 0];
+            const bool take = has && I.kind != SKG_INSTR_FRAME && I.kind != SKG_INSTR_FULL;
+            warpConvergedAdd(take, take ? I.sed + ell : nullptr, sedAdd);
+        }
+    }
     __device__ __forceinline__ void periodic() {}
 };
 
@@ -386,7 +426,9 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
     double Labs0;                           // (1 - albedo) * L of the packet: what a fully absorbing segment would take (one component)
     double tau, E, Lsca; double* labs;
     int slot, ell; bool walked, survive;
-    double kext0, pendRho, pendDs; int pendM;      // one-component media: gather now, absorb one crossing later
+    // one-component media: a crossing parks (m, ds) and starts the gather of the cell's density; the entry is consumed at
+    // the next crossing, in path order (the attenuation E must be that at the START of each segment)
+    double kext0, pendDs, pendRho; int pendM;
     // what finish() hands to collective() (alive only during a refill, not over the walk)
     double Lout, target; unsigned rngOut;
     unsigned nSeg = 0, nPaths = 0, nScatt = 0, nAbs = 0;
@@ -444,12 +486,12 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
         const double albedo = kext0 > 0 ? __ldg(P.med.ksca + ell) / kext0 : 0.0;        // DustMix::albedo(ell) (DustMix.cpp:55-90)
         Labs0 = SINGLE ? (1.0 - albedo) * L : L;
         tau = 0; E = 1.0; Lsca = 0;
-        pendM = -1; pendRho = 0; pendDs = 0;
+        pendM = -1; pendDs = 0; pendRho = 0;
         nPaths++; walked = true;
         return 1;
     }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }   // rho(-1,h) = 0: dtau = 0, nothing absorbed
-    // escape + absorption of one segment in a one-component medium (MonteCarloSimulation.cpp:446-470)
+    // escape + absorption of the parked segment in a one-component medium (MonteCarloSimulation.cpp:446-470)
     __device__ __forceinline__ void absorbPending()
     {
         if (pendM < 0) return;
@@ -457,47 +499,56 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
         if (STORE)
         {
             double x = expm1Small(-dtau);
+#ifdef SKG_EXP_NOATOMIC
+            Lsca += Labs0 * (E * (-x));         // experiment: no absorption atomics
+#else
             atomicAdd(labs + pendM, Labs0 * (E * (-x)));
+#endif
             E += E * x;
             nAbs++;
         }
         tau += dtau;
+        pendM = -1;
     }
     __device__ __forceinline__ bool segment(int m, double ds)
     {
         nSeg++;
-        const int Ncomp = P.med.Ncomp;
         if (SINGLE)
         {
             absorbPending();
             pendM = m; pendDs = ds; pendRho = __ldg(P.med.rho + m);
+            return true;
         }
-        else
+        return segmentMulti(m, ds);
+    }
+    template<int U> __device__ __forceinline__ bool segmentU(int m, double ds) { return segment(m, ds); }
+    template<int U> __device__ __forceinline__ void idleU() {}
+    __device__ __forceinline__ bool segmentMulti(int m, double ds)
+    {
+        const int Ncomp = P.med.Ncomp;
+        double ksca = 0.0, kext = 0.0, krr = 0.0;
+        for (int h = 0; h < Ncomp; h++)
         {
-            double ksca = 0.0, kext = 0.0, krr = 0.0;
-            for (int h = 0; h < Ncomp; h++)
-            {
-                double rho = __ldg(P.med.rho + (size_t)m * Ncomp + h);
-                ksca += rho * __ldg(P.med.ksca + (size_t)h * P.med.Nlambda + ell);
-                double ke = __ldg(P.med.kext + (size_t)h * P.med.Nlambda + ell);
-                kext += rho * ke;
-                krr += ke * rho;
-            }
-            double alb = (kext > 0.0) ? ksca / kext : 0.0;
-            double dtau = krr * ds;
-            double x = expm1Small(-dtau);
-            double Lintm = Labs0 * E * (-x);        // Labs0 = L for several components
-            E += E * x;
-            Lsca += alb * Lintm;
-            if (STORE) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
-            tau += dtau;
+            double rho = __ldg(P.med.rho + (size_t)m * Ncomp + h);
+            ksca += rho * __ldg(P.med.ksca + (size_t)h * P.med.Nlambda + ell);
+            double ke = __ldg(P.med.kext + (size_t)h * P.med.Nlambda + ell);
+            kext += rho * ke;
+            krr += ke * rho;
         }
+        double alb = (kext > 0.0) ? ksca / kext : 0.0;
+        double dtau = krr * ds;
+        double x = expm1Small(-dtau);
+        double Lintm = Labs0 * E * (-x);        // Labs0 = L for several components
+        E += E * x;
+        Lsca += alb * Lintm;
+        if (STORE) { atomicAdd(labs + m, (1.0 - alb) * Lintm); nAbs++; }
+        tau += dtau;
         return true;
     }
     __device__ __forceinline__ void finish()
     {
         if (!walked) return;
-        if (SINGLE) { absorbPending(); pendM = -1; }
+        if (SINGLE) absorbPending();
         const Packet* q = P.pool + slot;
         const double taupath = tau;
         double L = q->L;
@@ -562,7 +613,7 @@ template<int KIND, bool SINGLE> struct PropagateJob
     const McDev& P;
     double rx, ry, rz, dx, dy, dz;
     double target, sPrev, tauPrev, result; bool found; int slot, ell;
-    double kext0, pendRho, pendDs; bool pending; static constexpr bool single = SINGLE;      // one-component media: gather now, test one crossing later
+    double kext0, pendDs; int pendM; RhoSector sec; static constexpr bool single = SINGLE;      // one-component media: gather now (by sector), test one crossing later
     unsigned nSeg = 0, nPaths = 0;
     __device__ explicit PropagateJob(const McDev& P_) : P(P_) {}
     __device__ __forceinline__ int begin(int item)
@@ -575,7 +626,7 @@ template<int KIND, bool SINGLE> struct PropagateJob
         ell = pk.ell;
         rx = pk.x; ry = pk.y; rz = pk.z; dx = pk.kx; dy = pk.ky; dz = pk.kz;
         sPrev = 0; tauPrev = 0; result = 0; found = false;
-        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pending = false; pendRho = 0; pendDs = 0;
+        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendM = -1; pendDs = 0; sec.reset();
         nPaths++;
         return 1;
     }
@@ -585,12 +636,14 @@ template<int KIND, bool SINGLE> struct PropagateJob
         nSeg++;
         if (single)
         {
-            const bool cont = pending ? test((kext0 * pendRho) * pendDs, pendDs) : true;
-            pending = true; pendRho = __ldg(P.med.rho + m); pendDs = ds;
+            const bool cont = pendM >= 0 ? test((kext0 * sec.get(pendM)) * pendDs, pendDs) : true;
+            sec.touch(P.med.rho, m); pendM = m; pendDs = ds;
             return cont;
         }
         return test(KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda}(m) * ds, ds);
     }
+    template<int U> __device__ __forceinline__ bool segmentU(int m, double ds) { return segment(m, ds); }
+    template<int U> __device__ __forceinline__ void idleU() {}
     __device__ __forceinline__ bool test(double dtau, double ds)
     {
         double sNew = sPrev + ds;
@@ -607,7 +660,7 @@ template<int KIND, bool SINGLE> struct PropagateJob
     __device__ __forceinline__ void finish()
     {
         Packet* q = P.poolNext;      // the survivors the absorb stage just compacted
-        if (single && pending && !found) test((kext0 * pendRho) * pendDs, pendDs);
+        if (single && pendM >= 0 && !found) test((kext0 * sec.get(pendM)) * pendDs, pendDs);
         const double s = found ? result : sPrev;
         // PhotonPackage::propagate: r += s k, with r and k from the record (not kept in registers over the walk)
         Packet* w = q + slot;
@@ -775,6 +828,7 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             { used[j] = 1; grouped.push_back(e.instr[j]); g.count++; }
         groups.push_back(g);
     }
+    e.maxGroupCount = 0; for (const ObsGroup& g : groups) e.maxGroupCount = std::max(e.maxGroupCount, g.count);
     e.Ngroups = (int)groups.size(); e.instrNlambda = e.med.Nlambda; e.accInstr = Engine::ACC_ZERO;
     e.instrGroupedDev.upload(grouped.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
     e.groupsDev.upload(groups.data(), sizeof(ObsGroup) * std::max<size_t>(groups.size(), 1), e.stream);
@@ -1095,7 +1149,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     P.Ltot = phase == SKG_PHASE_STELLAR ? e.lumTotDev.as<double>() : e.dustLtot.as<double>();
     P.emissionBias = e.emissionBias;
     P.instr = e.instrGroupedDev.as<InstrDev>(); P.Ninstr = (int)e.instr.size();
-    P.groups = e.groupsDev.as<ObsGroup>(); P.Ngroups = e.Ngroups;
+    P.groups = e.groupsDev.as<ObsGroup>(); P.Ngroups = e.Ngroups; P.maxGroupCount = e.maxGroupCount;
     P.dustLv = e.dustLv.as<double>(); P.dustCdf = e.dustCdf.as<double>(); P.dustBias = dustBias;
     const bool store = phase == SKG_PHASE_STELLAR ? p.storeAbsorption != 0 : phase == SKG_PHASE_DUST_SELFABS;
     if (store)

@@ -29,6 +29,7 @@ struct RayJobBase
     __device__ __forceinline__ void collective(bool) {}
     __device__ __forceinline__ void periodic() {}
 };
+// (jobs of the deterministic-geometry kernels never run on a predicated walker, except TauJobT<true>, which forwards)
 
 // first pass of the batched path(): number of segments of every ray
 struct CountJob : RayJobBase
@@ -56,6 +57,8 @@ template<bool FAST> struct TauJobT : RayJobBase
     }
     __device__ __forceinline__ bool outside(double d) { sacc += d; return !(sacc > distance); }
     __device__ __forceinline__ bool segment(int mm, double d) { sacc += d; tau += kr(mm) * d; return !(sacc > distance); }
+    template<int U> __device__ __forceinline__ bool segmentU(int mm, double d) { return segment(mm, d); }
+    template<int U> __device__ __forceinline__ void idleU() {}
     __device__ __forceinline__ void finish() { out[item] = tau; }
 };
 

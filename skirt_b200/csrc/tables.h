@@ -15,6 +15,8 @@ struct CartGrid
     double ext[6];      // xmin,xmax,ymin,ymax,zmin,zmax of the BoxDustGrid extent
     unsigned sx, sy, sz;        // shared-window byte addresses of the staged borders (kernel-side view only)
     int staged;                 // non-zero when xv/yv/zv have been staged in shared memory (stageCart)
+    int uniform;                // every axis is a LinMesh: borders = min + i * width (to rounding); then wx, wy, wz are the bin widths
+    double wx, wy, wz;
     const double* rhoAhead;     // kernel-side view only: density table whose row of the NEXT cell a crossing pulls into L1 (or null)
     int rhoAheadStride;         // doubles per cell in that table
 };

@@ -12,6 +12,9 @@
 //   int  begin(int item)         set rx..dz for the item; 0 = nothing to do, 1 = walk the ray, 2 = no walk but finish()
 //   bool outside(double ds)      segment outside the grid (m = -1); false stops the walk
 //   bool segment(int m, double ds)
+//   bool segmentU<U>(int m, double ds)   the same for walkers that step in branch-free batches; U = position of the crossing in its
+//                                batch of SKG_PERIOD (compile time: lets a job keep one pending entry per position in registers)
+//   void idleU<U>()              a walking lane's crossing at position U that produced no segment
 //   void finish()                called once per item that returned 1 or 2 from begin()
 //   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
 //   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps
@@ -21,6 +24,7 @@
 //   static constexpr bool kTreeHints        tree walker: wall-bin table for walls with several neighbours (geom.cuh)
 //   static constexpr int kBatches           batches of SKG_PERIOD crossings between two votes / periodic() calls
 #pragma once
+#include <type_traits>
 #include "geom.cuh"
 
 namespace skg
@@ -105,15 +109,34 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
         // (lanes whose path ends inside the batch idle for at most SKG_PERIOD - 1 crossings)
         for (int batch = 0; batch < Job::kBatches; batch++)
         {
-#pragma unroll kStepUnroll
-            for (int u = 0; u < SKG_PERIOD; u++)
+            if constexpr (Walker::kPredicated)
             {
-                if (state == 1)
+                // branch-free crossings: lanes that are not walking execute the step predicated off
+                auto crossing = [&](auto U)
                 {
+                    bool live = state == 1;
                     int m; double ds;
-                    const bool seg = w.step(grid, ctr, m, ds);
-                    const bool cont = seg ? job.segment(m, ds) : true;
-                    if (!cont || !w.alive) state = 2;
+                    const bool seg = w.stepLive(grid, live, m, ds);
+                    if (seg) { if (!job.template segmentU<decltype(U)::value>(m, ds)) live = false; }
+                    else if (state == 1) job.template idleU<decltype(U)::value>();      // a crossing without a segment (ds <= 0)
+                    if (state == 1 && !live) state = 2;
+                };
+                static_assert(SKG_PERIOD == 4, "the batch of crossings is written out for a period of four");
+                crossing(std::integral_constant<int, 0>{}); crossing(std::integral_constant<int, 1>{});
+                crossing(std::integral_constant<int, 2>{}); crossing(std::integral_constant<int, 3>{});
+            }
+            else
+            {
+#pragma unroll kStepUnroll
+                for (int u = 0; u < SKG_PERIOD; u++)
+                {
+                    if (state == 1)
+                    {
+                        int m; double ds;
+                        const bool seg = w.step(grid, ctr, m, ds);
+                        const bool cont = seg ? job.segment(m, ds) : true;
+                        if (!cont || !w.alive) state = 2;
+                    }
                 }
             }
         }
@@ -126,7 +149,12 @@ __device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Co
 {
     if (KIND == GRID_CART)
     {
-        if (Job::kCartFast) runJobsStep<CartFastWalker>(cart, ctr, job, n, workCounter, refill);
+        if constexpr (Job::kCartFast)
+        {
+            // (warp-uniform: a property of the grid)
+            if (cart.uniform) runJobsStep<CartFastWalkerT<true>>(cart, ctr, job, n, workCounter, refill);
+            else runJobsStep<CartFastWalkerT<false>>(cart, ctr, job, n, workCounter, refill);
+        }
         else runJobsStep<CartWalkerT<Job::kCartRegBorders, Job::kCartTinySelect, Job::kCartRhoAhead>>(cart, ctr, job, n, workCounter, refill);
     }
     else if (KIND == GRID_TREE) runJobsStep<TreeWalkerT<Job::kTreeHints>>(G.tree, ctr, job, n, workCounter, refill);
