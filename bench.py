@@ -171,6 +171,21 @@ def traversal_leg(engine, torch, ext, ncomp, nrays, reps=5, warm=3):
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record(ext); engine.path_count_device(nrays, r.data_ptr(), k.data_ptr(), off.data_ptr()); e1.record(ext); e1.synchronize()
         ctimes.append(e0.elapsed_time(e1))
+    # through the API in ONE traversal per ray (skg_path_batch: closed-form slab capacities + scan + the same record kernel),
+    # next to the two-pass sequence count + scan + fill that the CSR interface needs
+    starts = torch.zeros(nrays + 1, dtype=torch.int64, device="cuda"); lens = torch.zeros(nrays, dtype=torch.int32, device="cuda")
+    need = engine.path_batch_device(nrays, r.data_ptr(), k.data_ptr(), ell.data_ptr(), 0, starts.data_ptr(), lens.data_ptr(), None, 0)
+    del seg
+    slab = torch.empty(need * 5, dtype=torch.float64, device="cuda")
+    otimes = []
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        engine.path_batch_device(nrays, r.data_ptr(), k.data_ptr(), ell.data_ptr(), 0, starts.data_ptr(), lens.data_ptr(), slab.data_ptr(), need)
+        e1.record(ext); e1.synchronize()
+        otimes.append(e0.elapsed_time(e1))
+    assert int(lens.sum().item()) == total, "one-pass and two-pass traversals disagree on the number of packet-steps"
+    del slab
     # context for the roofline: a pure streaming write (memset of 1 GiB) on this GPU -- the path-record kernel is a
     # write-only stream, whereas the roofline denominator (MEASURED_PEAKS.json) is a copy, i.e. reads + writes
     big = torch.empty(1 << 30, dtype=torch.uint8, device="cuda"); wtimes = []
@@ -181,7 +196,11 @@ def traversal_leg(engine, torch, ext, ncomp, nrays, reps=5, warm=3):
     del big
     ms = float(np.mean(times))
     nbytes = 60.0 * nrays + total * (36.0 + 8.0 * ncomp)
+    ms_one = float(np.mean(otimes)); ms_two = ms + float(np.mean(ctimes))
     return dict(rays=nrays, packet_steps=int(total), ms=ms, ms_count_pass=float(np.mean(ctimes)), bytes=nbytes,
+                through_api={"one_pass_ms": ms_one, "one_pass_gbs": nbytes / (ms_one * 1e-3) / 1e9, "slab_records": int(need),
+                             "two_pass_ms": ms_two, "two_pass_gbs": nbytes / (ms_two * 1e-3) / 1e9,
+                             "what": "skg_path_batch (capacity kernel + scan + record kernel, one traversal per ray) vs skg_path_count + skg_path_fill; device-resident rays and records, same algorithmic bytes"},
                 steps_per_s=total / (ms * 1e-3), gbs=nbytes / (ms * 1e-3) / 1e9, written_gbs=40.0 * total / (ms * 1e-3) / 1e9,
                 write_only_memset_gbs=write_only_gbs)
 
@@ -315,6 +334,7 @@ def main_engine(args):
     if rank == 0 and not args.skip_traversal:
         tr = traversal_leg(e, torch, ext, ncomp, args.rays)
         tr["frac"] = tr["gbs"] / peak; tr["peak"] = peak
+        tr["through_api_frac"] = tr["through_api"]["one_pass_gbs"] / peak; tr["through_api_two_pass_frac"] = tr["through_api"]["two_pass_gbs"] / peak
         tr["kernel"] = "pathFillKernel<GRID_CART> (batched DustGrid::path + fillOpticalDepth, CSR path records)"
         # ncu --set full of this kernel on 1 Mi rays (profiles/r01_v6_path_kernels_ncu.txt): 1.995 GB written + 0.118 GB read
         # for 50 281 330 packet-steps = 42.0 B per step, against 44 B algorithmic (40 B of it written)

@@ -96,6 +96,15 @@ typedef struct skg_segment { int32_t m; int32_t reserved; double ds, s, dtau, ta
 int skg_path_count(skg_engine* e, int mem, int64_t n, const double* r, const double* k, int64_t* offsets, int64_t* total);
 int skg_path_fill(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
                   const int64_t* offsets, skg_segment* segments);
+/* The same in ONE traversal per ray (what the reference does: DustGrid::path fills the caller's DustGridPath in a single
+ * pass).  Ray i receives the slab segments[starts[i] .. starts[i+1]) of which the first lengths[i] records are its path;
+ * slabs are sized without walking -- on Cartesian grids from the closed form of the number of crossings plus a few spare
+ * records per ray (about 5 % of the total), on the other grids by the counting pass (then lengths[i] == slab size).
+ * *needed receives the number of records the segment array must hold; when capacity is smaller (or segments is NULL)
+ * nothing is written and the call succeeds only if segments is NULL (a size query).  Device segment arrays must be
+ * 32-byte aligned.  A path that outgrows its slab (never observed) makes the call fail. */
+int skg_path_batch(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
+                   int64_t* starts /*[n+1]*/, int32_t* lengths /*[n]*/, skg_segment* segments, int64_t capacity, int64_t* needed);
 /* DustSystem::opticaldepth(pp, distance) (DustSystem.cpp:984-1000); distance may be NULL (= DBL_MAX) */
 int skg_opticaldepth(skg_engine* e, int mem, int64_t n, const double* r, const double* k, const int* ell, int ell_stride,
                      const double* distance, double* tau);

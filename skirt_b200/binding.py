@@ -210,6 +210,32 @@ class Engine:
         seg = seg[:total.value]
         return dict(offsets=off, **{f: np.ascontiguousarray(seg[f]) for f in ("m", "ds", "s", "dtau", "tau")})
 
+    def path_batch_onepass(self, r, k, ell=None):
+        """skg_path_batch for host rays: one traversal per ray into slabs; returns the same CSR dict as path_batch (the slabs
+        compacted on the host) plus the raw starts / lengths and the number of records the slabs took"""
+        r = _f64(r).reshape(-1, 3); k = _f64(k).reshape(-1, 3); n = len(r)
+        starts = np.zeros(n + 1, np.int64); lengths = np.zeros(max(n, 1), np.int32); needed = C.c_int64()
+        ellp, stride = None, 0
+        if ell is not None:
+            ella = _i32(np.atleast_1d(ell)); ellp = _vp(ella); stride = 1 if len(ella) == n and n > 1 else 0
+        args = (self.h, SKG_HOST, C.c_int64(n), _vp(r), _vp(k), ellp, stride, _vp(starts), _vp(lengths))
+        self._chk(self._lib.skg_path_batch(*args, None, C.c_int64(0), C.byref(needed)))          # size query
+        seg = np.zeros(max(needed.value, 1), dtype=SEGMENT)
+        self._chk(self._lib.skg_path_batch(*args, _vp(seg), C.c_int64(len(seg)), C.byref(needed)))
+        lengths = lengths[:n]
+        off = np.zeros(n + 1, np.int64); np.cumsum(lengths, out=off[1:])
+        idx = np.repeat(starts[:n] - off[:n], lengths) + np.arange(off[n]) if n else np.zeros(0, np.int64)
+        out = seg[idx]
+        return dict(offsets=off, starts=starts, lengths=lengths, slab_records=int(needed.value),
+                    **{f: np.ascontiguousarray(out[f]) for f in ("m", "ds", "s", "dtau", "tau")})
+
+    def path_batch_device(self, n, d_r, d_k, d_ell, ell_stride, d_starts, d_lengths, d_segments, capacity):
+        """skg_path_batch on device arrays; returns the number of records needed (query with d_segments = None)"""
+        needed = C.c_int64()
+        self._chk(self._lib.skg_path_batch(self.h, SKG_DEVICE, C.c_int64(n), _vp(d_r), _vp(d_k), _vp(d_ell), int(ell_stride), _vp(d_starts),
+                                           _vp(d_lengths), _vp(d_segments), C.c_int64(int(capacity)), C.byref(needed)))
+        return needed.value
+
     def path_count_device(self, n, d_r, d_k, d_offsets):
         total = C.c_int64()
         self._chk(self._lib.skg_path_count(self.h, SKG_DEVICE, C.c_int64(n), _vp(d_r), _vp(d_k), _vp(d_offsets), C.byref(total)))

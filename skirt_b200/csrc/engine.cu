@@ -459,6 +459,54 @@ static int opticalDepthImpl(skg_engine* eh, int mem, int64_t n, const double* r,
     });
 }
 
+// one-pass batched path(): slabs from analytic capacities (Cartesian) or exact counts (other grids), then the record kernel
+int skg_path_batch(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
+                   int64_t* starts, int32_t* lengths, skg_segment* segments, int64_t capacity, int64_t* needed)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (n < 0 || (n > 0 && (!r || !k)) || !starts || !lengths || !needed) throw Error("skg_path_batch: bad arguments");
+        if (ellStride != 0 && ellStride != 1) throw Error("ell_stride must be 0 or 1");
+        const bool host = mem == SKG_HOST;
+        const double* d_r = r; const double* d_k = k; const int* d_ell = ell; int64_t* d_starts = starts; int* d_len = lengths;
+        if (host)
+        {
+            e.scratchR.upload(r, sizeof(double) * 3 * (size_t)n, e.stream); e.scratchK.upload(k, sizeof(double) * 3 * (size_t)n, e.stream);
+            d_r = e.scratchR.as<double>(); d_k = e.scratchK.as<double>();
+            if (ell)
+            {
+                for (int64_t i = 0; i < (ellStride ? n : 1); i++) if (ell[i] < 0 || ell[i] >= e.med.Nlambda) throw Error("wavelength index out of range");
+                e.scratchEll.upload(ell, sizeof(int) * (size_t)(ellStride ? n : 1), e.stream); d_ell = e.scratchEll.as<int>();
+            }
+            e.scratchOffsets.ensure(sizeof(int64_t) * ((size_t)n + 1)); d_starts = e.scratchOffsets.as<int64_t>();
+            e.scratchM.ensure(sizeof(int) * (size_t)std::max<int64_t>(n, 1)); d_len = e.scratchM.as<int>();
+        }
+        e.scratchCounts.ensure(sizeof(int) * (size_t)std::max<int64_t>(n, 1));
+        const bool analytic = e.gridKind == GRID_CART;
+        if (analytic) launchPathCapacity(e, n, d_r, d_k, e.scratchCounts.as<int>());
+        else launchPathCount(e, n, d_r, d_k, e.scratchCounts.as<int>());
+        exclusiveScan(e, n, e.scratchCounts.as<int>(), d_starts);
+        int64_t total = 0;
+        SKG_CUDA(cudaMemcpyAsync(&total, d_starts + n, sizeof(int64_t), cudaMemcpyDeviceToHost, e.stream));
+        e.sync();
+        *needed = total + 8;                    // a few spare records behind the last slab
+        if (capacity < *needed || (!segments && total > 0))
+        { if (segments) throw Error("skg_path_batch: the segment array holds " + std::to_string(capacity) + " records, " + std::to_string(*needed) + " are needed"); return; }
+        skg_segment* d_seg = segments;
+        if (host) { e.scratchOut[0].ensure(sizeof(skg_segment) * (size_t)*needed); d_seg = e.scratchOut[0].as<skg_segment>(); }
+        else if (reinterpret_cast<uintptr_t>(segments) & 31) throw Error("skg_path_batch: the segment array must be 32-byte aligned");
+        const unsigned long long errorsBefore = e.readCounters().errors;
+        launchPathFill(e, n, d_r, d_k, d_ell, ellStride, d_starts, d_seg, d_len);
+        if (host)
+        {
+            SKG_CUDA(cudaMemcpyAsync(starts, d_starts, sizeof(int64_t) * ((size_t)n + 1), cudaMemcpyDeviceToHost, e.stream));
+            if (n > 0) SKG_CUDA(cudaMemcpyAsync(lengths, d_len, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+            if (total > 0) SKG_CUDA(cudaMemcpyAsync(segments, d_seg, sizeof(skg_segment) * (size_t)total, cudaMemcpyDeviceToHost, e.stream));
+        }
+        if (e.readCounters().errors != errorsBefore) throw Error("skg_path_batch: a path was longer than its slab (the analytic capacity was too small); use skg_path_count + skg_path_fill");
+    });
+}
+
 int skg_opticaldepth(skg_engine* eh, int mem, int64_t n, const double* r, const double* k, const int* ell, int ellStride,
                      const double* distance, double* tau)
 { return opticalDepthImpl(eh, mem, n, r, k, ell, ellStride, distance, tau, false); }

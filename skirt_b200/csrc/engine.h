@@ -107,7 +107,8 @@ struct Engine
 // kernels launchers (path_kernels.cu)
 void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k, int* d_counts);
 void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
-                    const int64_t* d_offsets, skg_segment* d_segments);
+                    const int64_t* d_offsets, skg_segment* d_segments, int* d_lengths = nullptr);
+void launchPathCapacity(Engine& e, int64_t n, const double* d_r, const double* d_k, int* d_cap);
 void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
                         const double* d_dist, double* d_tau, bool mcWalker = false);
 void launchWhichCell(Engine& e, int64_t n, const double* d_r, int* d_m);

@@ -95,9 +95,12 @@ struct RecordJobStaged : RayJobBase
     static constexpr bool kCartRegBorders = true, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH, kCartRhoAhead = true;       // the record kernel is bound by the load/store pipe
     static constexpr unsigned RHO_OFF = SKG_RING * 32 * 8, M_OFF = 2 * SKG_RING * 32 * 8;
     static constexpr size_t bytesPerWarp() { return (size_t)SKG_RING * 32 * (8 + 8 + 4); }
+    static constexpr size_t bytesPerWarpAll() { return bytesPerWarp() + 32 * 4; }      // + the ray index of every lane
 
     const int64_t* offsets; const int* ell; int ellStride; Medium med;
     skg_segment* seg;
+    int* lengths;               // one-pass mode: the number of records actually written per ray (offsets then hold capacities), or null
+    unsigned rbItem;            // shared-window address of this lane's slot for the ray index (one-pass mode; not a register over the walk)
     unsigned rb, rbM;           // shared-window addresses of this lane's columns: ds entry q at rb + 256 q, rho at + RHO_OFF; m entry q at rbM + 128 q
     double* out0;               // record with relative index 0: &seg[first record of the path rounded down to a multiple of 4]
     KappaRho kr; double kext0; double sacc, tacc; bool optical, async;
@@ -108,7 +111,7 @@ struct RecordJobStaged : RayJobBase
     {
         const int lane = threadIdx.x & 31;
         const unsigned w = (unsigned)__cvta_generic_to_shared(warpBase);
-        rb = w + 8u * lane; rbM = w + M_OFF + 4u * lane;
+        rb = w + 8u * lane; rbM = w + M_OFF + 4u * lane; rbItem = w + (unsigned)bytesPerWarp() + 4u * lane;
         o = f = ready = 0; sacc = tacc = 0; optical = async = false; kext0 = 0; qo = qf = 0; out0 = nullptr;
     }
 
@@ -116,6 +119,7 @@ struct RecordJobStaged : RayJobBase
     {
         loadRay(i);
         const int64_t first = offsets[i];
+        if (lengths) stsI32(rbItem, i);
         const int a0 = (int)(first & 3);
         out0 = reinterpret_cast<double*>(seg + (first - a0));
         o = f = ready = a0; qo = qf = 256 * a0;
@@ -179,7 +183,20 @@ struct RecordJobStaged : RayJobBase
     }
     // entries parked before the previous call have their density in the ring by now
     __device__ __forceinline__ void periodic() { asyncCommit(); asyncWaitAllButLatest(); emit(ready & ~3); ready = o; }
-    __device__ __forceinline__ void finish() { asyncCommit(); asyncWaitAll(); emit(o); ready = o; }
+    __device__ __forceinline__ void finish()
+    {
+        asyncCommit(); asyncWaitAll(); emit(o); ready = o;
+        if (lengths)
+        {
+            // one-pass mode: report the length; the ray's slab [offsets[i], offsets[i+1]) must have held it
+            const int i = ldsVI32(rbItem);
+            const int64_t first = offsets[i], cap = offsets[i + 1] - first;
+            const int len = o - (int)(first & 3);
+            lengths[i] = len;
+            if (len > cap) atomicAdd(overflow, 1ull);
+        }
+    }
+    unsigned long long* overflow;
     __device__ __forceinline__ void collective(bool) {}
 };
 
@@ -193,7 +210,7 @@ template<int KIND>
 __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ GridSet G, const Medium med, Counters* ctr, bool cartSmem, int refill,
                                                       int n, const double* __restrict__ r, const double* __restrict__ k,
                                                       const int* __restrict__ ell, int ellStride, const int64_t* __restrict__ offsets,
-                                                      skg_segment* __restrict__ segments, int* work)
+                                                      skg_segment* __restrict__ segments, int* work, int* __restrict__ lengths)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
@@ -206,8 +223,8 @@ __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ Gr
     }
     size_t skip = (KIND == GRID_CART && cartSmem) ? SKG_CART_SMEM_DOUBLES(G.cart) : 0;
     RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
-    job.seg = segments;
-    job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarp());
+    job.seg = segments; job.lengths = lengths; job.overflow = &ctr->errors;
+    job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarpAll());
     runJobs<KIND>(G, cart, ctr, job, n, work, refill);
 }
 
@@ -222,6 +239,36 @@ __global__ void __launch_bounds__(128) opticalDepthKernel(const __grid_constant_
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     TauJobT<FAST> job; job.r = r; job.k = k; job.ell = ell; job.ellStride = ellStride; job.med = med; job.dist = dist; job.out = tau;
     runJobs<KIND>(G, cart, ctr, job, n, work, refill);
+}
+
+// One-pass batched path() on Cartesian grids: an upper bound of every ray's number of segments WITHOUT walking it.  The
+// path of CartesianDustGrid::path is monotone in the cell indices of every axis and ends when one of them leaves the grid,
+// so it has (number of crossings) = |di| + |dj| + |dk| + 1 segments between its first cell and the cell in which the
+// straight line leaves the grid box, plus the up to three "outside" segments of the entry (cartEnter).  The walk itself
+// rounds differently from this closed form only at the level of an ulp of the coordinates: near a cell corner it may take
+// the crossings in another order or end one cell over in an axis, hence one spare segment per axis.  Segments with
+// ds <= 0 are dropped by addSegment (DustGridPath.cpp:46-53): the bound stays a bound.  The record kernel reports the
+// true length and flags any ray whose slab was too short (never observed; skg_path_batch then returns an error).
+__global__ void __launch_bounds__(128) pathCapacityKernel(const CartGrid g, int64_t n, const double* __restrict__ r, const double* __restrict__ k,
+                                                          int* __restrict__ cap)
+{
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    {
+        double x = r[3 * q], y = r[3 * q + 1], z = r[3 * q + 2];
+        const double kx = k[3 * q], ky = k[3 * q + 1], kz = k[3 * q + 2];
+        Entry en; int i, j, kk;
+        if (!cartEnter(g, x, y, z, kx, ky, kz, en, i, j, kk)) { cap[q] = 0; continue; }
+        int c = 0;
+        for (int u = 0; u < en.n; u++) if (en.ds[u] > 0) c++;
+        // where the straight line leaves the box
+        const double tx = fabs(kx) > 1e-15 ? ((kx < 0 ? g.ext[0] : g.ext[1]) - x) / kx : SKG_DBL_MAX;
+        const double ty = fabs(ky) > 1e-15 ? ((ky < 0 ? g.ext[2] : g.ext[3]) - y) / ky : SKG_DBL_MAX;
+        const double tz = fabs(kz) > 1e-15 ? ((kz < 0 ? g.ext[4] : g.ext[5]) - z) / kz : SKG_DBL_MAX;
+        const double t = fmin(tx, fmin(ty, tz));
+        const int i2 = locateClip(g.xv, x + t * kx, g.Nx + 1), j2 = locateClip(g.yv, y + t * ky, g.Ny + 1), k2 = locateClip(g.zv, z + t * kz, g.Nz + 1);
+        c += abs(i2 - i) + abs(j2 - j) + abs(k2 - kk) + 1 + 3;
+        cap[q] = c;
+    }
 }
 
 template<int KIND>
@@ -292,13 +339,13 @@ void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k,
 }
 
 void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, const int* d_ell, int ellStride,
-                    const int64_t* d_offsets, skg_segment* d_segments)
+                    const int64_t* d_offsets, skg_segment* d_segments, int* d_lengths)
 {
     if (n <= 0) return;
     if (d_ell && !e.med.rho) throw Error("skg_path_fill with wavelength indices needs skg_medium first");
     if (d_ell && e.med.Ncells != e.Ncells) throw Error("the medium has " + std::to_string(e.med.Ncells) + " cells but the grid has " + std::to_string(e.Ncells) + ": call skg_medium again");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
-    c.smem += 4 * RecordJobStaged::bytesPerWarp();
+    c.smem += 4 * RecordJobStaged::bytesPerWarpAll();
     if (const char* pad = getenv("SKG_FILL_SMEM_PAD")) c.smem += (size_t)atoi(pad);      // experiment: limits resident CTAs
     if (!e.attrFill)
     {
@@ -310,7 +357,7 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
         e.attrFill = true;
     }
     SKG_DISPATCH(e, (pathFillKernel<K><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride,
-                                                                                d_offsets, d_segments, c.work)));
+                                                                                d_offsets, d_segments, c.work, d_lengths)));
     e.launches++; SKG_CUDA(cudaGetLastError());
 }
 
@@ -325,6 +372,15 @@ void launchOpticalDepth(Engine& e, int64_t n, const double* d_r, const double* d
     { SKG_DISPATCH(e, (opticalDepthKernel<K, true><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride, d_dist, d_tau, c.work))); }
     else
     { SKG_DISPATCH(e, (opticalDepthKernel<K, false><<<c.blocks, 128, c.smem, e.stream>>>(G, e.med, e.ctr(), c.cartSmem, c.refill, (int)n, d_r, d_k, d_ell, ellStride, d_dist, d_tau, c.work))); }
+    e.launches++; SKG_CUDA(cudaGetLastError());
+}
+
+void launchPathCapacity(Engine& e, int64_t n, const double* d_r, const double* d_k, int* d_cap)
+{
+    if (n <= 0) return;
+    if (e.gridKind != GRID_CART) throw Error("analytic path capacities exist for Cartesian grids only");
+    const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)e.smCount * 16));
+    pathCapacityKernel<<<blocks, 128, 0, e.stream>>>(e.cart, n, d_r, d_k, d_cap);
     e.launches++; SKG_CUDA(cudaGetLastError());
 }
 

@@ -223,3 +223,30 @@ def test_shooting_walker_on_the_full_size_grid(engine):
     a = engine.opticaldepth(r, k, ell); b = engine.opticaldepth(r, k, ell, mc_walker=True)
     assert a.max() > 0
     np.testing.assert_allclose(b, a, rtol=1e-10, atol=1e-13 * float(a.max()))
+
+
+@pytest.mark.parametrize("name", common.GEOM_CASES)
+def test_one_pass_paths_match_reference(engine, name):
+    """skg_path_batch: one traversal per ray into slabs sized without walking (Cartesian: closed-form capacity; other grids:
+    counting pass) -- the records of every ray are bit-identical to the reference's golden paths, adversarial rays included,
+    and the slabs waste only a few records per ray"""
+    _, _, d = _setup(engine, name)
+    got = engine.path_batch_onepass(d["r"], d["k"], ell=0)
+    assert common.paths_bit_identical(got, d["paths"]), f"{name}: one-pass records differ"
+    assert np.all(got["lengths"] <= np.diff(got["starts"]))
+    if not name.startswith("cart"):
+        assert np.array_equal(got["lengths"], np.diff(got["starts"]))
+    # geometry only
+    geo = engine.path_batch_onepass(d["r"], d["k"], ell=None)
+    assert np.array_equal(geo["m"], d["paths"]["m"]) and np.array_equal(geo["s"], d["paths"]["s"]) and not geo["tau"].any()
+
+
+def test_one_pass_on_the_full_size_grid(engine):
+    """2^18 random rays through the 100^3 grid: the one-pass slabs hold every path, the records equal the two-pass ones"""
+    from skirt_b200 import configs
+    configs.build(configs.c2_params(n=100, nlambda=3, packages=10), engine=engine).setup()
+    r, k = common.rays(1 << 18, configs.C1_BOX, seed=78)
+    a = engine.path_batch(r, k, ell=1); b = engine.path_batch_onepass(r, k, ell=1)
+    assert common.paths_bit_identical(a, b)
+    waste = b["slab_records"] / max(len(a["m"]), 1) - 1
+    assert 0 <= waste < 0.12, f"slabs waste {waste:.1%}"
