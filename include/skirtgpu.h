@@ -123,6 +123,10 @@ int skg_stuck_counts(skg_engine* e, int64_t* escaped, int64_t* terminated);
  * pairs (the walkers divide by the direction cosines, which are constant along a path); *mismatches must be 0 */
 int skg_selftest_division(skg_engine* e, uint64_t n, uint64_t seed, uint64_t* mismatches);
 
+/* measurement aid: the rate (per second) at which this GPU retires n fp64 atomicAdds to pseudo-random cells of a table of
+ * `cells` doubles -- the access pattern of the escape + absorption stage (LockFree::add into _Labsvv), whose ceiling it is */
+int skg_selftest_atomics(skg_engine* e, uint64_t n, int cells, double* atomicsPerSecond);
+
 /* ---- sources: StellarSystem::launch (StellarSystem.cpp:116-158) -------------------------------------- */
 enum { SKG_GEOM_EXPDISK = 1, SKG_GEOM_SERSIC = 2 };
 typedef struct skg_source
@@ -152,6 +156,13 @@ int skg_sources(skg_engine* e, int Ncomp, const skg_source* comps, int Nlambda, 
  * been set; geometries are described like the sources of skg_sources.  rho is a host array. */
 int skg_sample_density(skg_engine* e, int Ncomp, const skg_source* geometries, const double* norm, int sampleCount,
                        uint64_t seed, double* rho);
+
+/* Tree subdivision sampling (TreeDustGrid::subdivide, TreeDustGrid.cpp:168-233 -> TreeNodeSampleDensityCalculator.cpp:25-45)
+ * for a batch of node boxes: mass[q] = volume(q) * mean over sampleCount random positions in box q of sum_h norm[h] *
+ * density_h.  box[6*q..] = xmin,ymin,zmin,xmax,ymax,zmax; geometries and norm as for skg_sample_density.  Host arrays.
+ * No grid needs to be set: this is what grows one (include/skirthost.h, skh_tree_*). */
+int skg_sample_boxes(skg_engine* e, int64_t n, const double* box, int Ncomp, const skg_source* geometries, const double* norm,
+                     int sampleCount, uint64_t seed, double* mass);
 
 /* n launches of StellarSystem::launch(pp, ell, 1.0) with the engine's samplers (the kernel the shooting phase uses):
  * positions r[3n], directions k[3n] and bias-weighted luminosities L[n]; for distribution-level checks */
@@ -200,6 +211,7 @@ typedef struct skg_mc_stats
     uint64_t detections;        /* detector updates: frame pixel or SED bin (one fp64 atomic each) */
     double launch_ms, peel_ms, absorb_ms, propagate_ms;     /* device time per stage kernel family (CUDA events) */
     uint64_t iterations;        /* wavefront iterations (one launch of every stage each) */
+    uint64_t peelSegments, propagateSegments;   /* packet-steps of the peel-off and the propagation stage (the rest: escape + absorption) */
 } skg_mc_stats;
 int skg_run_stellar(skg_engine* e, const skg_mc_params* p, skg_mc_stats* stats);
 

@@ -54,7 +54,7 @@ class SkgMcStats(C.Structure):
                 ("scatterings", C.c_uint64), ("kernel_ms", C.c_double),
                 ("absorbSegments", C.c_uint64), ("detections", C.c_uint64),
                 ("launch_ms", C.c_double), ("peel_ms", C.c_double), ("absorb_ms", C.c_double), ("propagate_ms", C.c_double),
-                ("iterations", C.c_uint64)]
+                ("iterations", C.c_uint64), ("peelSegments", C.c_uint64), ("propagateSegments", C.c_uint64)]
 
 
 def _stats(st):
@@ -153,8 +153,8 @@ class Engine:
         self._chk(self._lib.skg_grid_amesh(self.h, len(child0), _vp(box), _vp(nxyz), _vp(child0), _vp(cell), _vp(wallNbr)))
 
     def grid_voronoi(self, t):
-        a = {k: (_f64(v) if k in ("particles", "cellBox", "extent") else _i32(v) if isinstance(v, np.ndarray) else v)
-             for k, v in t.items()}
+        ints = ("nbrStart", "nbrIds", "blkStart", "blkIds", "blkTree", "kdM", "kdAxis", "kdUp", "kdLeft", "kdRight")
+        a = {k: (_f64(v) if k in ("particles", "cellBox", "extent") else _i32(v) if k in ints else v) for k, v in t.items()}
         nkd = len(a["kdM"])
         pad = lambda v: v if len(v) else np.zeros(1, np.int32)
         self._chk(self._lib.skg_grid_voronoi(
@@ -266,6 +266,12 @@ class Engine:
         self._chk(self._lib.skg_selftest_division(self.h, C.c_uint64(int(n)), C.c_uint64(int(seed)), C.byref(bad)))
         return bad.value
 
+    def selftest_atomics(self, n=1 << 30, cells=1000000):
+        """fp64 atomicAdds per second to random cells of a table (skg_selftest_atomics)"""
+        r = C.c_double()
+        self._chk(self._lib.skg_selftest_atomics(self.h, C.c_uint64(int(n)), int(cells), C.byref(r)))
+        return r.value
+
     def stuck_counts(self):
         a = C.c_int64(); b = C.c_int64()
         self._chk(self._lib.skg_stuck_counts(self.h, C.byref(a), C.byref(b)))
@@ -305,6 +311,16 @@ class Engine:
         rho = np.zeros((self.Ncells, len(geometries)))
         self._chk(self._lib.skg_sample_density(self.h, len(geometries), arr, _vp(nrm), int(sample_count), C.c_uint64(int(seed)), _vp(rho)))
         return rho
+
+    def sample_boxes(self, boxes, geometries, norm, sample_count=100, seed=4357):
+        """skg_sample_boxes: dust mass in every box (TreeNodeSampleDensityCalculator on the device); boxes[n, 6] =
+        xmin,ymin,zmin,xmax,ymax,zmax"""
+        arr, keep = self._source_array(geometries)
+        nrm = _f64(norm); b = _f64(boxes).reshape(-1, 6)
+        mass = np.zeros(len(b))
+        self._chk(self._lib.skg_sample_boxes(self.h, C.c_int64(len(b)), _vp(b), len(geometries), arr, _vp(nrm), int(sample_count),
+                                             C.c_uint64(int(seed)), _vp(mass)))
+        return mass
 
     def sample_launch(self, ell, n, seed=1):
         r = np.zeros((n, 3)); k = np.zeros((n, 3)); L = np.zeros(n)

@@ -531,6 +531,9 @@ int skg_whichcell(skg_engine* eh, int mem, int64_t n, const double* r, int* m)
 int skg_selftest_division(skg_engine* eh, uint64_t n, uint64_t seed, uint64_t* mismatches)
 { return guarded([&]{ if (!mismatches) throw Error("null output"); *mismatches = runDivisionSelfTest(E(eh), n, seed); }); }
 
+int skg_selftest_atomics(skg_engine* eh, uint64_t n, int cells, double* atomicsPerSecond)
+{ return guarded([&]{ if (!atomicsPerSecond) throw Error("null output"); *atomicsPerSecond = mcAtomicRate(E(eh), n, cells); }); }
+
 int skg_stuck_counts(skg_engine* eh, int64_t* escaped, int64_t* terminated)
 {
     return guarded([&]{
@@ -554,6 +557,8 @@ int skg_sample_launch(skg_engine* eh, int ell, int n, uint64_t seed, double* r, 
 { return guarded([&]{ mcSampleLaunch(E(eh), ell, n, seed, r, k, L); }); }
 int skg_sample_density(skg_engine* eh, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* rho)
 { return guarded([&]{ mcSampleDensity(E(eh), Ncomp, geoms, norm, sampleCount, seed, rho); }); }
+int skg_sample_boxes(skg_engine* eh, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* mass)
+{ return guarded([&]{ mcSampleBoxes(E(eh), n, box, Ncomp, geoms, norm, sampleCount, seed, mass); }); }
 int skg_reset_results(skg_engine* eh) { return guarded([&]{ mcResetResults(E(eh)); }); }
 int skg_dust_library(skg_engine* eh, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda)
 { return guarded([&]{ if (!volumes || !kappaabs || !lambda || !dlambda) throw Error("skg_dust_library: null table"); mcDustLibrary(E(eh), volumes, kappaabs, lambda, dlambda); }); }

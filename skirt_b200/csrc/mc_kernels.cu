@@ -78,6 +78,12 @@ __device__ __forceinline__ void flushStats(Counters* ctr, unsigned long long nSe
     }
 }
 
+__device__ __forceinline__ void flushStageSegments(unsigned long long* counter, unsigned long long n)
+{
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_down_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0 && n) atomicAdd(counter, n);
+}
+
 // ---- launch ----------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev P, Counters* ctr, int nLaunch, unsigned long long firstPacket,
                                                    int aliveBase)
@@ -409,6 +415,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PEEL_MINBLOCKS : 
     PeelJob<KIND, SINGLE> job(G, cart, P);
     runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, P.peelRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
+    flushStageSegments(&ctr->peelSegments, job.nSeg);
 }
 
 // scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
@@ -681,6 +688,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PROP_MINBLOCKS : 
     PropagateJob<KIND, SINGLE> job(P);
     runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.propRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
+    flushStageSegments(&ctr->propSegments, job.nSeg);
 }
 
 // Labs is wavelength-major on the device; the host interface is DustSystem's (m, ell) row-major table
@@ -1239,6 +1247,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         stats->absorbSegments = after.absorbSegments - before.absorbSegments; stats->detections = after.detections - before.detections;
         stats->launch_ms = e.stageMs[0]; stats->peel_ms = e.stageMs[1]; stats->absorb_ms = e.stageMs[2]; stats->propagate_ms = e.stageMs[3];
         stats->iterations = e.mcIterations;
+        stats->peelSegments = after.peelSegments - before.peelSegments; stats->propagateSegments = after.propSegments - before.propSegments;
     }
 }
 
@@ -1322,6 +1331,79 @@ void mcSampleDensity(Engine& e, int Ncomp, const skg_source* geoms, const double
     }
     catch (...) { for (DevBuf* b : bufs) delete b; throw; }
     for (DevBuf* b : bufs) delete b;
+}
+
+// TreeNodeSampleDensityCalculator (TreeNodeSampleDensityCalculator.cpp:25-45) for a batch of boxes: one thread per box draws
+// sampleCount positions (Random::position(Box): x, y, z in this order) and averages the total density of the components;
+// mass = mean density x volume -- the quantity TreeDustGrid::subdivide compares with maxMassFraction (TreeDustGrid.cpp:197-201)
+__global__ void __launch_bounds__(128) sampleBoxesKernel(const double* __restrict__ box, int64_t n, const SourceDev* __restrict__ geoms,
+                                                         const double* __restrict__ norm, int Ncomp, int sampleCount, unsigned long long seed,
+                                                         double* __restrict__ mass)
+{
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
+    {
+        const double* b = box + 6 * q;
+        const double x0 = b[0], y0 = b[1], z0 = b[2], wx = b[3] - b[0], wy = b[4] - b[1], wz = b[5] - b[2];
+        Philox rng; rng.init(seed, (unsigned long long)q, 9u);
+        double sum = 0;
+        for (int s = 0; s < sampleCount; s++)
+        {
+            const double fx = rng.uniform(), fy = rng.uniform(), fz = rng.uniform();
+            const double x = x0 + fx * wx, y = y0 + fy * wy, z = z0 + fz * wz;
+            for (int h = 0; h < Ncomp; h++) sum += norm[h] * geometryDensity(geoms[h], x, y, z);
+        }
+        mass[q] = sum / sampleCount * (wx * wy * wz);
+    }
+}
+
+void mcSampleBoxes(Engine& e, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* mass)
+{
+    if (n < 0 || (n > 0 && (!box || !mass)) || Ncomp < 1 || Ncomp > 8 || !geoms || !norm) throw Error("skg_sample_boxes: bad arguments");
+    if (sampleCount < 1) throw Error("Number of random samples must be at least 1");       // TreeDustGrid.cpp:60
+    if (n == 0) return;
+    std::vector<DevBuf*> bufs; std::vector<SourceDev> dev;
+    DevBuf devGeoms, devNorm, devBox, devMass;
+    try
+    {
+        for (int h = 0; h < Ncomp; h++) dev.push_back(makeSourceDev(e, geoms[h], bufs, true));
+        devGeoms.upload(dev.data(), sizeof(SourceDev) * Ncomp, e.stream); devNorm.upload(norm, sizeof(double) * Ncomp, e.stream);
+        devBox.upload(box, sizeof(double) * 6 * (size_t)n, e.stream); devMass.ensure(sizeof(double) * (size_t)n);
+        const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)e.smCount * 16));
+        sampleBoxesKernel<<<blocks, 128, 0, e.stream>>>(devBox.as<double>(), n, devGeoms.as<SourceDev>(), devNorm.as<double>(), Ncomp, sampleCount, seed, devMass.as<double>());
+        e.launches++; SKG_CUDA(cudaGetLastError());
+        SKG_CUDA(cudaMemcpyAsync(mass, devMass.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+        e.sync();
+    }
+    catch (...) { for (DevBuf* b : bufs) delete b; throw; }
+    for (DevBuf* b : bufs) delete b;
+}
+
+// fp64 atomic adds to pseudo-random cells of a table, the access pattern of the escape + absorption stage: the rate at which
+// this GPU retires them is the ceiling of that stage (skg_selftest_atomics)
+__global__ void __launch_bounds__(128) atomicRateKernel(double* __restrict__ table, unsigned cells, unsigned long long perThread, unsigned long long seed)
+{
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x + 1);
+    for (unsigned long long i = 0; i < perThread; i++)
+    {
+        z += 0x9E3779B97F4A7C15ull; unsigned long long t = z; t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull; t = (t ^ (t >> 27)) * 0x94D049BB133111EBull; t ^= t >> 31;
+        atomicAdd(table + (unsigned)(t % cells), 1.0);
+    }
+}
+
+double mcAtomicRate(Engine& e, uint64_t n, int cells)
+{
+    if (cells < 1 || n < 1) throw Error("skg_selftest_atomics: bad arguments");
+    DevBuf table; table.ensure(sizeof(double) * (size_t)cells);
+    SKG_CUDA(cudaMemsetAsync(table.p, 0, sizeof(double) * (size_t)cells, e.stream));
+    const int blocks = e.smCount * 16; const unsigned long long per = std::max<unsigned long long>(1, n / ((unsigned long long)blocks * 128));
+    cudaEvent_t ev0, ev1; SKG_CUDA(cudaEventCreate(&ev0)); SKG_CUDA(cudaEventCreate(&ev1));
+    atomicRateKernel<<<blocks, 128, 0, e.stream>>>(table.as<double>(), (unsigned)cells, per / 8 + 1, 1ull);      // warm-up
+    SKG_CUDA(cudaEventRecord(ev0, e.stream));
+    atomicRateKernel<<<blocks, 128, 0, e.stream>>>(table.as<double>(), (unsigned)cells, per, 2ull);
+    SKG_CUDA(cudaEventRecord(ev1, e.stream));
+    e.launches += 2; SKG_CUDA(cudaGetLastError()); e.sync();
+    float ms = 0; SKG_CUDA(cudaEventElapsedTime(&ms, ev0, ev1)); cudaEventDestroy(ev0); cudaEventDestroy(ev1);
+    return (double)per * blocks * 128 / (ms * 1e-3);
 }
 
 __global__ void unpackLaunches(const Packet* __restrict__ pool, int n, double* __restrict__ r, double* __restrict__ k, double* __restrict__ L)

@@ -108,6 +108,8 @@ struct Counters
     unsigned long long packets;
     unsigned long long absorbSegments;      // segments that updated the absorption table (one fp64 atomic each)
     unsigned long long detections;          // detector updates (one fp64 atomic each)
+    unsigned long long peelSegments;        // packet-steps of the peel-off stage
+    unsigned long long propSegments;        // packet-steps of the propagation stage
     unsigned long long pad;
 };
 

@@ -283,6 +283,122 @@ class TreeTablesDustGrid:
         return self._t
 
 
+class _BoxDustGrid:
+    def _set_extent(self, minX, maxX, minY, maxY, minZ, maxZ):
+        if maxX <= minX:
+            raise FatalError("The extent of the box should be positive in the X direction")
+        if maxY <= minY:
+            raise FatalError("The extent of the box should be positive in the Y direction")
+        if maxZ <= minZ:
+            raise FatalError("The extent of the box should be positive in the Z direction")
+        self.extent = (float(minX), float(maxX), float(minY), float(maxY), float(minZ), float(maxZ))
+
+    def tables(self):
+        if self._t is None:
+            raise FatalError("the dust grid has not been built (MonteCarloSimulation.setup does it)")
+        return self._t
+
+    def numCells(self):
+        return int(self.tables()["Ncells"])
+
+
+class OctTreeDustGrid(_BoxDustGrid):
+    """TreeDustGrid / OctTreeDustGrid (TreeDustGrid.cpp:50-233; defaults TreeDustGrid.cpp:20-37): the tree is grown level by
+    level by the native host library (skirt_b200/host/GridBuilders.cpp through hostlib), the dust mass of the candidate
+    nodes of a level is estimated on the GPU (skg_sample_boxes = TreeNodeSampleDensityCalculator), and a node is subdivided
+    when it holds more than maxMassFraction of the dust mass or its mean optical depth exceeds maxOpticalDepth."""
+    kind = 0
+    KAPPA_V = 2600.0            # Units::kappaV(), Units.cpp:30
+
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, minLevel=2, maxLevel=6, searchMethod="Neighbor", sampleCount=100,
+                 maxOpticalDepth=0.0, maxMassFraction=1e-6, maxDensDispFraction=0.0):
+        self._set_extent(minX, maxX, minY, maxY, minZ, maxZ)
+        self.minLevel, self.maxLevel, self.sampleCount = int(minLevel), int(maxLevel), int(sampleCount)
+        self.maxOpticalDepth, self.maxMassFraction = float(maxOpticalDepth), float(maxMassFraction)
+        if maxDensDispFraction:
+            raise FatalError("the density dispersion criterion is not supported by this host (TreeDustGrid.cpp:215-219)")
+        try:
+            self.search = {"TopDown": 0, "Neighbor": 1, "Bookkeeping": 2}[searchMethod]
+        except KeyError:
+            raise FatalError(f"unknown search method {searchMethod}")
+        if self.search == 2 and self.kind != 0:
+            raise FatalError("Bookkeeping method is not compatible with binary tree")
+        if self.sampleCount < 1:
+            raise FatalError("Number of random samples must be at least 1")
+        self._t = None
+
+    def build(self, engine, geometries, norms, seed=4357):
+        """geometries / norms: samplers and mass normalisations of the dust components (CompDustDistribution)"""
+        from . import hostlib
+        tb = hostlib.TreeBuilder(self.kind, self.extent, self.minLevel, self.maxLevel)
+        total = float(np.sum(norms))
+        always = self.maxOpticalDepth == 0 and self.maxMassFraction == 0
+
+        def decide(level, boxes):
+            if always:
+                return np.ones(len(boxes), bool)
+            mass = engine.sample_boxes(boxes, geometries, norms, self.sampleCount, seed + 7919 * level)
+            need = np.zeros(len(boxes), bool)
+            if self.maxMassFraction > 0:
+                need |= mass / total >= self.maxMassFraction
+            if self.maxOpticalDepth > 0:
+                vol = np.prod(boxes[:, 3:] - boxes[:, :3], axis=1)
+                need |= self.KAPPA_V * mass / vol ** (2. / 3.) >= self.maxOpticalDepth
+            return need
+        tb.grow(decide)
+        self._t = tb.finish(self.search)
+        tb.close()
+        return self
+
+    def volumes(self):
+        t = self.tables(); box = t["box"].reshape(-1, 6)[t["cell"] >= 0]
+        return np.prod(box[:, 3:] - box[:, :3], axis=1)
+
+
+class BinTreeDustGrid(OctTreeDustGrid):
+    """BinTreeDustGrid: k-d tree, split direction level % 3 (BinTreeNode.cpp:74-77)"""
+    kind = 1
+
+
+class AdaptiveMeshDustGrid(_BoxDustGrid):
+    """AdaptiveMeshDustGrid + AdaptiveMeshDustDistribution: the mesh comes as the node sequence of an adaptive mesh file
+    (AdaptiveMeshAsciiFile.cpp:43-100: depth first, one (Nx, Ny, Nz) per non-leaf and one density value per leaf); the
+    dust density of a cell is its field value times densityUnits (AdaptiveMeshDustDistribution)."""
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, nxyz, values, densityUnits=1.0):
+        self._set_extent(minX, maxX, minY, maxY, minZ, maxZ)
+        from . import hostlib
+        self._t = hostlib.build_adaptive_mesh(self.extent, nxyz)
+        self.values = np.asarray(values, dtype=np.float64)
+        self.densityUnits = float(densityUnits)
+
+    def build(self, *a, **k):
+        return self
+
+    def volumes(self):
+        return self._t["volume"]
+
+    def density(self):
+        """rho[m] of the mesh's own dust distribution (negative values count as no dust, AdaptiveMesh.cpp:88)"""
+        return np.maximum(self.values[self._t["fileIndex"]], 0.0) * self.densityUnits
+
+
+class VoronoiDustGrid(_BoxDustGrid):
+    """VoronoiDustGrid over given particle positions (VoronoiMesh::buildMesh, VoronoiMesh.cpp:310-393, via Voro++)"""
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, particles):
+        self._set_extent(minX, maxX, minY, maxY, minZ, maxZ)
+        from . import hostlib
+        pts = np.asarray(particles, dtype=np.float64).reshape(-1, 3)
+        e = self.extent
+        inside = ((pts[:, 0] >= e[0]) & (pts[:, 0] <= e[1]) & (pts[:, 1] >= e[2]) & (pts[:, 1] <= e[3]) & (pts[:, 2] >= e[4]) & (pts[:, 2] <= e[5]))
+        self._t = hostlib.build_voronoi_mesh(self.extent, pts[inside])       # VoronoiMesh.cpp:262-263: particles outside are dropped
+
+    def build(self, *a, **k):
+        return self
+
+    def volumes(self):
+        return self._t["volume"]
+
+
 # ---- dust system --------------------------------------------------------------------------------------------------
 class DustComp:
     """DustComp + FaceOnDustCompNormalization (FaceOnDustCompNormalization.cpp:67-74): rho scaled so that the
@@ -302,9 +418,15 @@ class DustSystem:
         self.kext = np.array([c.mix.kappaext for c in self.comps])
         self.ksca = np.array([c.mix.kappasca for c in self.comps])
         self.g = np.array([c.mix.asymmpar for c in self.comps])
+        self.rho = None; self.sampleCount = 100
         if rho is not None:
             self.rho = np.asarray(rho, dtype=np.float64)
             return
+        if isinstance(grid, AdaptiveMeshDustGrid):
+            self.rho = grid.density()[:, None]
+            return
+        if not hasattr(grid, "cell_samples"):
+            return          # tree / Voronoi grids: sampled on the device once the grid is there (sample_on_device)
         pts, _ = grid.cell_samples(sampleLattice)
         cols = []
         for c in self.comps:
@@ -316,6 +438,29 @@ class DustSystem:
                 dens += c.geometry.density(p[:, 0], p[:, 1], p[:, 2])
             cols.append(scale * dens / len(pts))
         self.rho = np.stack(cols, axis=1)
+
+    def norms(self):
+        """mass normalisation of every component: FaceOnDustCompNormalization.cpp:67-74, tau / (SigmaZ * kappaext(lambda))"""
+        lg = self.lambdagrid; out = []
+        for c in self.comps:
+            kv = float(10.0 ** np.interp(math.log10(c.lam), np.log10(lg.lambdav), np.log10(c.mix.kappaext))) \
+                if lg.Nlambda > 1 else float(c.mix.kappaext[0])
+            out.append(c.tau / (c.geometry.SigmaZ() * kv))
+        return np.array(out)
+
+    def geometry_samplers(self):
+        out = []
+        for c in self.comps:
+            s = c.geometry.sampler()
+            if s["geometry"] == GEOM_SERSIC:
+                s["Sv"] = c.geometry.fn.Sv
+            out.append(s)
+        return out
+
+    def sample_on_device(self, engine, seed=4357):
+        """DustSystem::setSampleDensityBody (DustSystem.cpp:152-177) on the device: mean of sampleCount random positions per cell"""
+        if self.rho is None:
+            self.rho = engine.sample_density(self.geometry_samplers(), self.norms(), self.sampleCount, seed)
 
     def medium(self):
         return dict(rho=self.rho, kext=self.kext, ksca=self.ksca, g=self.g)
@@ -475,11 +620,16 @@ class MonteCarloSimulation:
         self.engine = engine if engine is not None else Engine(device)      # one engine per process / GPU
         self._setup = False
         self.comm_ms = {}           # device time of the collectives of the last phases (ms), by accumulator
+        self.stats_log = []         # (phase, engine statistics) of every shooting phase run so far
 
     def setup(self):
         """uploads every table (the engine-side equivalent of Simulation::setup)"""
         e = self.engine
-        e.set_grid(self.ds.grid.tables())
+        grid = self.ds.grid
+        if hasattr(grid, "build") and getattr(grid, "_t", 0) is None:
+            grid.build(e, self.ds.geometry_samplers(), self.ds.norms(), self.seed)     # TreeDustGrid::setupSelfBefore
+        e.set_grid(grid.tables())
+        self.ds.sample_on_device(e, self.seed)
         m = self.ds.medium()
         e.medium(m["rho"], m["kext"], m["ksca"], m["g"])
         e.sources([c.geometry.sampler() for c in self.ss.comps], self.ss.luminosities(), self.ss.emissionBias)
@@ -500,6 +650,7 @@ class MonteCarloSimulation:
         st = self.engine.run_stellar(npr, total_packages=total, min_weight_reduction=self.mwr,
                                      min_scatt_events=self.minfs, scatt_bias=self.xi, store_absorption=self.storeabs,
                                      seed=self.seed, stream_offset=offset)
+        self.stats_log.append(("stellar", st))
         # the stellar absorption table is summed over the processes once, here (the reference does it when the first dust
         # emission spectra are made: PanDustSystem::calculatedustemission(true) -> sumResults(true), PanDustSystem.cpp:383-404);
         # the detector arrays are summed once, when they are read (Instrument::write -> sumResults, Instrument.cpp:57-65)
@@ -551,14 +702,15 @@ class MonteCarloSimulation:
                     d_L = self.engine.dust_cell_luminosities()
                     self.engine.reset_labs_dust()
                     npr, offset, total = shard_packets(self.packages * factor, self.rank, self.nranks)
-                    self.engine.run_dust_device(1, d_L, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
-                                                scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
+                    st = self.engine.run_dust_device(1, d_L, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
+                                                     scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
                 else:
                     Lv, _ = self._cell_luminosities(dustlib)
                     self.engine.reset_labs_dust()
                     npr, offset, total = shard_packets(self.packages * factor, self.rank, self.nranks)
-                    self.engine.run_dust(1, Lv, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
-                                         scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
+                    st = self.engine.run_dust(1, Lv, npr, total_packages=total, min_weight_reduction=self.mwr, min_scatt_events=self.minfs,
+                                              scatt_bias=self.xi, seed=self.seed + 1000 * (len(history) + 1), stream_offset=offset)
+                self.stats_log.append(("selfabs", st))
                 # PanDustSystem::sumResults(false): the dust table of this cycle, summed over the processes before the next
                 # spectra are made from it; PanDustSystem::Labsdusttot(): the same number on every rank, so that all of
                 # them take the same convergence decision (PanMonteCarloSimulation.cpp:152-167)
@@ -574,7 +726,9 @@ class MonteCarloSimulation:
 
     def rundustemission(self, dustlib=None, emissionBias=0.5, emissionBoost=1.0):
         """PanMonteCarloSimulation::rundustemission (PanMonteCarloSimulation.cpp:242-264)"""
-        return self._shoot_dust(2, dustlib, self.packages * emissionBoost, self.seed + 999983, emission_bias=emissionBias)
+        st = self._shoot_dust(2, dustlib, self.packages * emissionBoost, self.seed + 999983, emission_bias=emissionBias)
+        self.stats_log.append(("emission", st))
+        return st
 
     def results(self, pinned=False):
         """detector arrays and absorption table on the host; pinned=True keeps page-locked result buffers alive across

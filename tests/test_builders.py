@@ -1,0 +1,97 @@
+"""Product-side grid builders (skirt_b200/libskirthost.so: include/skirthost.h, skirt_b200/host/GridBuilders.cpp) against
+the reference's own grid classes (oracle/_ref): for the same subdivision decisions / mesh file / particles the flattened
+tables -- node boxes and ids, cell numbers, neighbour lists IN THE REFERENCE'S ORDER, wall neighbours, Voro++ neighbour
+lists, block lists and search trees -- are identical.  CPU only."""
+import numpy as np
+import pytest
+
+import common
+from skirt_b200 import configs, hostlib
+
+pytestmark = pytest.mark.skipif(not hostlib.lib_available(), reason="skirt_b200/libskirthost.so not built")
+
+
+def _ref(spec, **kw):
+    from oracle import skirtref as sr
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    return sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw).setup()
+
+
+@pytest.mark.parametrize("kind,kw", [("octtree", dict(minlevel=2, maxlevel=6, massfrac=2e-5)),
+                                     ("bintree", dict(minlevel=4, maxlevel=14, massfrac=2e-5))])
+@pytest.mark.parametrize("search", [0, 1])
+def test_tree_builder_reproduces_the_reference_tree(kind, kw, search):
+    ref = _ref(common.spec_grid(kind, search=search, **kw)).grid_tables()
+    tb = hostlib.TreeBuilder(0 if kind == "octtree" else 1, common.C1_BOX, kw["minlevel"], kw["maxlevel"])
+    child0 = ref["child0"]; pos = {tuple(b): i for i, b in enumerate(ref["box"].reshape(-1, 6))}
+    levels = []
+
+    def decide(level, boxes):       # the reference's own decisions: a node was subdivided iff it has children
+        levels.append(level)
+        return np.array([child0[pos[tuple(b)]] >= 0 for b in boxes])
+    tb.grow(decide)
+    mine = tb.finish(search)
+    assert min(levels) == kw["minlevel"] + 1 and max(levels) == kw["maxlevel"] - 1
+    keys = ["box", "child0", "parent", "cell"] + (["nbrStart", "nbrIds"] if search == 1 else [])
+    for k in keys:
+        assert np.array_equal(np.asarray(mine[k]).ravel(), np.asarray(ref[k]).ravel()), f"{kind}: {k} differs from the reference"
+    inner = child0 >= 0         # BinTreeNode::_dir is only ever set for nodes that were split
+    assert np.array_equal(mine["dir"][inner], np.asarray(ref["dir"])[inner])
+    assert mine["Ncells"] == int((child0 < 0).sum())
+
+
+def test_tree_builder_validation():
+    with pytest.raises(hostlib.HostError, match="Maximum tree level should be larger"):
+        hostlib.TreeBuilder(0, common.C1_BOX, 3, 3)
+    with pytest.raises(hostlib.HostError, match="maximum tree level should be at least 2"):
+        hostlib.TreeBuilder(0, common.C1_BOX, 0, 1)
+    tb = hostlib.TreeBuilder(1, common.C1_BOX, 1, 3)
+    tb.grow(lambda level, boxes: np.ones(len(boxes), bool))
+    with pytest.raises(hostlib.HostError, match="Bookkeeping method is not compatible with binary tree"):
+        tb.finish(2)
+    t = tb.finish(0)
+    assert t["Ncells"] == 8 and len(t["child0"]) == 15
+
+
+def test_adaptive_mesh_builder_reproduces_the_reference_mesh():
+    am = common.make_amesh(root=(4, 4, 4), max_depth=4, frac=2e-3)
+    S = _ref(common.spec_grid("amesh"), amesh=am)
+    ref = S.grid_tables()
+    mine = hostlib.build_adaptive_mesh(common.C1_BOX, am[0])
+    for k in ("box", "nxyz", "child0", "cell", "wallNbr"):
+        assert np.array_equal(np.asarray(mine[k]).ravel(), np.asarray(ref[k]).ravel()), f"{k} differs from the reference"
+    assert np.array_equal(mine["volume"], S.volumes())
+    # densities: the reference's table is value x units in cell order
+    np.testing.assert_allclose(am[1][mine["fileIndex"]] * 1e-24, S.medium()["rho"].ravel(), rtol=1e-15)
+    # the vectorised generator of the product side writes the same file order as the recursive one of the tests
+    nx, val = configs.synthetic_amesh(root=4, depth=4, frac=2e-3)
+    assert np.array_equal(nx, am[0]) and np.allclose(val, am[1], rtol=1e-14)
+    with pytest.raises(hostlib.HostError, match="Reached end of file"):
+        hostlib.build_adaptive_mesh(common.C1_BOX, am[0][:-3])
+    with pytest.raises(hostlib.HostError, match="Superfluous data"):
+        hostlib.build_adaptive_mesh(common.C1_BOX, np.concatenate([am[0], [[0, 0, 0]]]))
+
+
+def test_voronoi_builder_reproduces_the_reference_mesh():
+    if not hostlib.voronoi_available():
+        pytest.skip("libskirthost.so was built without Voro++")
+    pts = common.voronoi_particles(3000)
+    S = _ref(common.spec_grid("voronoi"), particles=pts)
+    ref = S.grid_tables()
+    mine = hostlib.build_voronoi_mesh(common.C1_BOX, pts)
+    assert mine["nb"] == ref["nb"]
+    for k in ("particles", "nbrStart", "nbrIds", "blkStart", "blkIds", "blkTree", "kdM", "kdAxis", "kdUp", "kdLeft", "kdRight", "cellBox"):
+        assert np.array_equal(np.asarray(mine[k]).ravel(), np.asarray(ref[k]).ravel()), f"{k} differs from the reference"
+    assert np.array_equal(mine["volume"], S.volumes())
+    assert abs(mine["volume"].sum() / np.prod(common.C1_BOX[1::2] - common.C1_BOX[0::2]) - 1) < 1e-9
+
+
+def test_host_library_exports_its_header():
+    import ctypes, os, re
+    hdr = open(os.path.join(common.ROOT, "include", "skirthost.h")).read()
+    names = sorted(set(re.findall(r"\b(skh_[a-z_]+)\s*\(", hdr)))
+    L = ctypes.CDLL(hostlib.LIB_PATH)
+    assert len(names) >= 15
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in skirthost.h but not exported"
