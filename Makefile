@@ -44,8 +44,8 @@ skirt_b200/libskirthost.so: $(HOSTLIB_SRC) skirt_b200/host/GridBuilders.hpp incl
 
 # C++ host layer (simulation items with the reference's names) + command-line driver, linked against the C ABI only
 HOST := skirt_b200/host
-skirt_b200/skirt_b200_run: $(HOST)/skirt_b200_run.cpp $(HOST)/SimulationItems.cpp $(HOST)/Output.cpp $(HOST)/SimulationItems.hpp $(HOST)/Output.hpp include/skirtgpu.h skirt_b200/libskirtgpu.so
-	$(HOSTCXX) -std=c++17 -O2 -Wall -o $@ $(HOST)/skirt_b200_run.cpp $(HOST)/SimulationItems.cpp $(HOST)/Output.cpp -Lskirt_b200 -lskirtgpu -Wl,-rpath,'$$ORIGIN' -Wl,-rpath-link,/usr/local/cuda/lib64
+skirt_b200/skirt_b200_run: $(HOST)/skirt_b200_run.cpp $(HOST)/SimulationItems.cpp $(HOST)/Output.cpp $(HOST)/SimulationItems.hpp $(HOST)/Output.hpp $(HOST)/GridBuilders.hpp include/skirtgpu.h skirt_b200/libskirtgpu.so skirt_b200/libskirthost.so
+	$(HOSTCXX) -std=c++17 -O2 -Wall -o $@ $(HOST)/skirt_b200_run.cpp $(HOST)/SimulationItems.cpp $(HOST)/Output.cpp -Lskirt_b200 -lskirtgpu -lskirthost -Wl,-rpath,'$$ORIGIN' -Wl,-rpath-link,/usr/local/cuda/lib64
 
 oracle:
 	$(MAKE) -C oracle all

@@ -183,7 +183,8 @@ template<bool REGB, bool TINYSEL, bool AHEAD = false> struct CartWalkerT
     bool alive;
 
     // entry part, :151-230 (cartEnter), then the per-ray invariants of the crossing loop
-    __device__ __forceinline__ bool start(const CartGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
+    __device__ __forceinline__ int locator() const { return -1; }       // point location is cheap on this grid: nothing to remember
+    __device__ __forceinline__ bool start(const CartGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en, int = -1)
     {
         alive = false;
         x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
@@ -281,7 +282,8 @@ template<bool UNIFORM> struct CartFastWalkerT
     int dmx, dmy, dmz, m;
     bool alive;
 
-    __device__ __forceinline__ bool start(const CartGrid& g, Counters*, double x, double y, double z, double kx, double ky, double kz, Entry& en)
+    __device__ __forceinline__ int locator() const { return -1; }
+    __device__ __forceinline__ bool start(const CartGrid& g, Counters*, double x, double y, double z, double kx, double ky, double kz, Entry& en, int = -1)
     {
         alive = false;
         int i, j, k;
@@ -497,15 +499,27 @@ template<bool HINT> struct TreeWalkerT
         cellv = __ldg(g.cell + node);
     }
 
-    __device__ __forceinline__ bool start(const TreeGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
+    __device__ __forceinline__ int locator() const { return node; }
+    // hint: the leaf the ray starts in, as remembered from an earlier traversal (the shooting stages: a packet keeps its
+    // node between its peel-off, absorption and propagation walks), verified against the node's box; -1: locate the point
+    __device__ __forceinline__ bool start(const TreeGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en, int hint = -1)
     {
         alive = false; en.n = 0;
         x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
         if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
-        if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
-        node = treeWhichNode(g, x, y, z);
-        if (node < 0) return false;
-        loadNode(g, true);
+        bool located = false;
+        if (hint >= 0)
+        {
+            node = hint; loadNode(g, true);
+            located = cellv >= 0 && x > bx[0] && x < bx[3] && y > bx[1] && y < bx[4] && z > bx[2] && z < bx[5];
+        }
+        if (!located)
+        {
+            if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
+            node = treeWhichNode(g, x, y, z);
+            if (node < 0) return false;
+            loadNode(g, true);
+        }
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
@@ -759,16 +773,28 @@ struct AMeshWalker
         wn[0] = r.lo(9); wn[1] = r.hi(9); wn[2] = r.lo(10); wn[3] = r.hi(10); wn[4] = r.lo(11); wn[5] = r.hi(11);
     }
 
-    __device__ __forceinline__ bool start(const AMeshGrid& g, Counters* ctr, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
+    __device__ __forceinline__ int locator() const { return node; }
+    __device__ __forceinline__ bool start(const AMeshGrid& g, Counters* ctr, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en, int hint = -1)
     {
         alive = false; en.n = 0;
         x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
         if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
-        if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
         AMeshRecWords rec;
-        const int id = ameshWhichNode(g, x, y, z, rec);
-        if (id < 0) { if (id == -2) atomicAdd(&ctr->errors, 1ull); return false; }
-        adopt(id, rec);
+        bool located = false;
+        if (hint >= 0)
+        {
+            // the leaf remembered from an earlier traversal of the same packet (see TreeWalkerT::start), verified against its box
+            rec.load(g.nodeRec + hint);
+            located = rec.cell() >= 0 && x > rec.w[0] && x < rec.w[3] && y > rec.w[1] && y < rec.w[4] && z > rec.w[2] && z < rec.w[5];
+            if (located) adopt(hint, rec);
+        }
+        if (!located)
+        {
+            if (!moveInside(g.box, g.eps, x, y, z, kx, ky, kz, en)) return false;
+            const int id = ameshWhichNode(g, x, y, z, rec);
+            if (id < 0) { if (id == -2) atomicAdd(&ctr->errors, 1ull); return false; }
+            adopt(id, rec);
+        }
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
         alive = true;
         return true;
@@ -940,8 +966,15 @@ __device__ __forceinline__ int voroCellIndex(const VoroGrid& g, double x, double
     return m;
 }
 
-// VoronoiMesh::path (VoronoiMesh.cpp:749-844) one crossing at a time
-struct VoroWalker
+// VoronoiMesh::path (VoronoiMesh.cpp:749-844) one crossing at a time.
+// EXACT: the reference's arithmetic -- every candidate wall distance is the quotient si = n.(p - r) / n.k and the smallest
+// positive one wins, first in list order among equals (the deterministic-geometry entry points: bit-exact paths).
+// !EXACT (the photon shooting stages, whose results are Monte Carlo estimates): the same candidates are compared as
+// fractions, num_i * den_best < num_best * den_i (all denominators positive), in the same list order with the same
+// first-wins rule; only the winner is divided.  That removes the IEEE division (and its divergent slow path) from the
+// neighbour loop -- a third of the instructions of the Voronoi stage kernels -- and makes the loop body branch-free; two
+// candidates whose quotients differ by less than the rounding of the products may swap, which moves a crossing by an ulp.
+template<bool EXACT> struct VoroWalkerT
 {
     static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;
@@ -950,13 +983,20 @@ struct VoroWalker
     int guard;
     bool alive;
 
-    __device__ __forceinline__ bool start(const VoroGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en)
+    __device__ __forceinline__ int locator() const { return mr; }
+    // hint: the cell the ray starts in, as remembered from an earlier traversal of the same packet (taken on trust: a point
+    // that a path placed inside cell m is nearest to particle m up to rounding); -1: VoronoiMesh::cellIndex
+    __device__ __forceinline__ bool start(const VoroGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en, int hint = -1)
     {
         alive = false; en.n = 0; guard = 0;
         x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
         if (!finite3(x, y, z) || !finite3(kx, ky, kz)) return false;
-        if (!moveInside(g.ext, g.eps, x, y, z, kx, ky, kz, en)) return false;
-        mr = voroCellIndex(g, x, y, z);
+        if (hint >= 0 && hint < g.N) mr = hint;
+        else
+        {
+            if (!moveInside(g.ext, g.eps, x, y, z, kx, ky, kz, en)) return false;
+            mr = voroCellIndex(g, x, y, z);
+        }
         if (mr < 0) return false;
         rr = __ldg(g.nbrStart + mr) + mr;
         alive = true;
@@ -969,7 +1009,8 @@ struct VoroWalker
     __device__ __forceinline__ bool step(const VoroGrid& g, Counters* ctr, int& mseg, double& ds)
     {
         const double eps = g.eps;
-        double sq = SKG_DBL_MAX;
+        double sq = SKG_DBL_MAX;                // EXACT: best quotient
+        double nb = 0.0, db = 1.0;              // !EXACT: best fraction nb / db (db > 0); mq == NO_INDEX: none yet
         const int NO_INDEX = -99;
         int mq = NO_INDEX, rq = 0;
         // the neighbour loop of VoronoiMesh.cpp:777-828 over the cell's crossing record (tables.h), four neighbours at a
@@ -982,6 +1023,8 @@ struct VoroWalker
         for (int u = 0; u < 4; u++) loadSlot(R + 4 * (u + 1), e[u]);        // the table ends with 8 spare slots
         const double prx = h[0], pry = h[1], prz = h[2];
         const int cnt = (int)(__double_as_longlong(h[3]) & 0xffffffffll);
+        // the rest of the block (typically 12 more slots = 3 lines): into L1 while the first group is evaluated
+        for (int q0 = 4; q0 < cnt; q0 += 4) prefetchL1(R + 4 * (q0 + 1));
         for (int q0 = 0; q0 < cnt; q0 += 4)
         {
             if (q0)
@@ -995,32 +1038,59 @@ struct VoroWalker
                 if (q0 + u >= cnt) break;
                 const long long tag = __double_as_longlong(e[u][3]);
                 const int mi = (int)(tag & 0xffffffffll);
-                double si = 0;
-                if (mi >= 0)
+                if (EXACT)
                 {
-                    const double pix = e[u][0], piy = e[u][1], piz = e[u][2];
-                    double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;        // n = pi - pr
-                    double ndotk = nxv * kx + nyv * ky + nzv * kz;                   // Vec::dot(n,bfk)
-                    if (ndotk > 0)
+                    double si = 0;
+                    if (mi >= 0)
                     {
-                        double qx = 0.5 * (pix + prx), qy = 0.5 * (piy + pry), qz = 0.5 * (piz + prz);   // p = 0.5*(pi+pr)
-                        si = (nxv * (qx - x) + nyv * (qy - y) + nzv * (qz - z)) / ndotk;                // dot(n,p-r)/ndotk
+                        const double pix = e[u][0], piy = e[u][1], piz = e[u][2];
+                        double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;        // n = pi - pr
+                        double ndotk = nxv * kx + nyv * ky + nzv * kz;                   // Vec::dot(n,bfk)
+                        if (ndotk > 0)
+                        {
+                            double qx = 0.5 * (pix + prx), qy = 0.5 * (piy + pry), qz = 0.5 * (piz + prz);   // p = 0.5*(pi+pr)
+                            si = (nxv * (qx - x) + nyv * (qy - y) + nzv * (qz - z)) / ndotk;                // dot(n,p-r)/ndotk
+                        }
                     }
+                    else
+                    {
+                        switch (mi)
+                        {
+                        case -1: si = (g.ext[0] - x) / kx; break;
+                        case -2: si = (g.ext[3] - x) / kx; break;
+                        case -3: si = (g.ext[1] - y) / ky; break;
+                        case -4: si = (g.ext[4] - y) / ky; break;
+                        case -5: si = (g.ext[2] - z) / kz; break;
+                        case -6: si = (g.ext[5] - z) / kz; break;
+                        default: atomicAdd(&ctr->errors, 1ull); alive = false; return false;
+                        }
+                    }
+                    if (si > 0 && si < sq) { sq = si; mq = mi; rq = (int)(tag >> 32); }
                 }
                 else
                 {
-                    switch (mi)
+                    // the candidate as a fraction num / den, den > 0 (a wall: (border - r_a) / k_a with the sign moved into num)
+                    double num, den;
+                    if (mi >= 0)
                     {
-                    case -1: si = (g.ext[0] - x) / kx; break;
-                    case -2: si = (g.ext[3] - x) / kx; break;
-                    case -3: si = (g.ext[1] - y) / ky; break;
-                    case -4: si = (g.ext[4] - y) / ky; break;
-                    case -5: si = (g.ext[2] - z) / kz; break;
-                    case -6: si = (g.ext[5] - z) / kz; break;
-                    default: atomicAdd(&ctr->errors, 1ull); alive = false; return false;
+                        const double pix = e[u][0], piy = e[u][1], piz = e[u][2];
+                        const double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;
+                        den = nxv * kx + nyv * ky + nzv * kz;
+                        num = nxv * (0.5 * (pix + prx) - x) + nyv * (0.5 * (piy + pry) - y) + nzv * (0.5 * (piz + prz) - z);
                     }
+                    else
+                    {
+                        if (mi < -6) { atomicAdd(&ctr->errors, 1ull); alive = false; return false; }
+                        const int a = (-1 - mi) >> 1;                                   // axis of the wall; odd ids are the lower faces
+                        const double ka = a == 0 ? kx : (a == 1 ? ky : kz), ra = a == 0 ? x : (a == 1 ? y : z);
+                        const double border = g.ext[a + (((-1 - mi) & 1) ? 3 : 0)];
+                        num = border - ra; den = ka;
+                        if (den < 0) { num = -num; den = -den; }
+                    }
+                    // si > 0 && si < sq with si = num / den, sq = nb / db
+                    const bool better = den > 0 && num > 0 && (mq == NO_INDEX || num * db < nb * den);
+                    if (better) { nb = num; db = den; mq = mi; rq = (int)(tag >> 32); }
                 }
-                if (si > 0 && si < sq) { sq = si; mq = mi; rq = (int)(tag >> 32); }
             }
         }
         if (mq == NO_INDEX)
@@ -1032,6 +1102,7 @@ struct VoroWalker
             if (mr < 0) alive = false; else rr = __ldg(g.nbrStart + mr) + mr;
             return false;
         }
+        if (!EXACT) sq = nb / db;
         mseg = mr; ds = sq;                     // sq > 0 by construction
         x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
         mr = mq; rr = rq;

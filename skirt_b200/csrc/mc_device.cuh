@@ -28,7 +28,8 @@ struct __align__(32) Packet
     double L, target;
     unsigned long long id;      // Philox stream id of the packet
     int ell, nscatt; unsigned rngCtr; int fresh;
-    double pad;
+    int hint;                   // the walker's locator of the packet's position (tree / adaptive-mesh leaf node, Voronoi cell) when a
+    int pad;                    // traversal has established it, else -1: the next traversal from this position skips the point location
 };
 typedef Packet* PacketPool;
 

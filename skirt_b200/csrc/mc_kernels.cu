@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev
         }
         Packet* q = P.pool;
         Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
-        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.pad = 0;
+        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.pad = 0;
         storePacket(q + slot, pk);
     }
     flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) launchDustStage(const __grid_constant__ G
         randomDirection(rng, kx, ky, kz);
         Packet* q = P.pool;
         Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
-        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.pad = 0;
+        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.pad = 0;
         storePacket(q + slot, pk);
     }
     flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
@@ -271,7 +271,7 @@ template<int KIND, bool SINGLE> struct PeelJob
     double rx, ry, rz, dx, dy, dz;          // the ray (runJobs interface): only read by the walker's start(), not kept over the walk
     // state carried over the walk, kept small (registers are what limits the warps in flight): everything else the
     // detection needs (position, wavelength, scattering count) is re-read from the packet record in finish()
-    double Lw, tau; int item, ell;
+    double Lw, tau; int item, ell, hint;
     // one-component media: the density gather of a crossing is consumed one crossing later, so that its latency
     // overlaps the next step's arithmetic (same summation order: tau += (kext*rho[m])*ds per segment)
     // one-component media: the density gather of a crossing is consumed kDepth crossings later (the optical depth is a
@@ -292,7 +292,7 @@ template<int KIND, bool SINGLE> struct PeelJob
         double L = pk.L;
         if (!(L > 0)) return 0;                                 // MonteCarloSimulation.cpp:281
         rx = pk.x; ry = pk.y; rz = pk.z;
-        ell = pk.ell;
+        ell = pk.ell; hint = KIND == GRID_CART ? -1 : pk.hint;
         // which instruments of this direction record the packet?  FrameInstrument ignores packets that map outside
         // its frame before any optical depth is computed (FrameInstrument.cpp:36); SED/Simple always need tau
         bool need = false;
@@ -344,6 +344,9 @@ template<int KIND, bool SINGLE> struct PeelJob
         nPaths++;
         return 1;
     }
+    __device__ __forceinline__ int cellHint() const { return hint; }
+    // the first traversal from a position establishes where it lies: remembered in the packet record for the next ones
+    __device__ __forceinline__ void noteStart(int loc) { if (KIND != GRID_CART) P.pool[item / P.Ngroups].hint = loc; }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }
     template<int U> __device__ __forceinline__ bool segmentU(int m, double ds)
     {
@@ -432,7 +435,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
     // of two (the forms agree to a few ulp over a path)
     double Labs0;                           // (1 - albedo) * L of the packet: what a fully absorbing segment would take (one component)
     double tau, E, Lsca; double* labs;
-    int slot, ell; bool walked, survive;
+    int slot, ell, hint; bool walked, survive;
     // one-component media: a crossing parks (m, ds) and starts the gather of the cell's density; the entry is consumed at
     // the next crossing, in path order (the attenuation E must be that at the START of each segment)
     double kext0, pendDs, pendRho; int pendM;
@@ -450,7 +453,7 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
         const double L = pk.L;
         if (!(L > 0) || !P.med.rho) return 2;       // nothing to propagate: the slot is simply not copied to the next pool
         const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
-        ell = pk.ell;
+        ell = pk.ell; hint = KIND == GRID_CART ? -1 : pk.hint;
         rx = pk.x; ry = pk.y; rz = pk.z;
         dx = pk.kx; dy = pk.ky; dz = pk.kz;
         if (!pk.fresh)
@@ -497,6 +500,8 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
         nPaths++; walked = true;
         return 1;
     }
+    __device__ __forceinline__ int cellHint() const { return hint; }
+    __device__ __forceinline__ void noteStart(int loc) { if (KIND != GRID_CART) P.pool[slot].hint = loc; }
     __device__ __forceinline__ bool outside(double) { nSeg++; return true; }   // rho(-1,h) = 0: dtau = 0, nothing absorbed
     // escape + absorption of the parked segment in a one-component medium (MonteCarloSimulation.cpp:446-470)
     __device__ __forceinline__ void absorbPending()
@@ -617,12 +622,13 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS 
 template<int KIND, bool SINGLE> struct PropagateJob
 {
     static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
-    const McDev& P;
+    const GridSetMC& G; const McDev& P;
     double rx, ry, rz, dx, dy, dz;
-    double target, sPrev, tauPrev, result; bool found; int slot, ell;
-    double kext0, pendDs; int pendM; RhoSector sec; static constexpr bool single = SINGLE;      // one-component media: gather now (by sector), test one crossing later
+    double target, sPrev, tauPrev, result; bool found; int slot, ell, hint;
+    int foundM;                                 // the cell in which the interaction takes place (-1: the path ended first)
+    double kext0, pendDs, pendRho; int pendM; static constexpr bool single = SINGLE;      // one-component media: gather now, test one crossing later
     unsigned nSeg = 0, nPaths = 0;
-    __device__ explicit PropagateJob(const McDev& P_) : P(P_) {}
+    __device__ PropagateJob(const GridSetMC& G_, const McDev& P_) : G(G_), P(P_) {}
     __device__ __forceinline__ int begin(int item)
     {
         Packet* q = P.poolNext;      // the survivors the absorb stage just compacted
@@ -630,35 +636,37 @@ template<int KIND, bool SINGLE> struct PropagateJob
         const Packet pk = loadPacket(q + slot);
         target = pk.target;
         if (!(target > 0)) return 0;
-        ell = pk.ell;
+        ell = pk.ell; hint = KIND == GRID_CART ? -1 : pk.hint;
         rx = pk.x; ry = pk.y; rz = pk.z; dx = pk.kx; dy = pk.ky; dz = pk.kz;
-        sPrev = 0; tauPrev = 0; result = 0; found = false;
-        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendM = -1; pendDs = 0; sec.reset();
+        sPrev = 0; tauPrev = 0; result = 0; found = false; foundM = -1;
+        kext0 = single ? __ldg(P.med.kext + ell) : 0.0; pendM = -1; pendDs = 0; pendRho = 0;
         nPaths++;
         return 1;
     }
+    __device__ __forceinline__ int cellHint() const { return hint; }
+    __device__ __forceinline__ void noteStart(int) {}        // the packet is about to move: finish() records where it ends up
     __device__ __forceinline__ bool outside(double ds) { nSeg++; sPrev += ds; return true; }       // only before the first cell
     __device__ __forceinline__ bool segment(int m, double ds)
     {
         nSeg++;
         if (single)
         {
-            const bool cont = pendM >= 0 ? test((kext0 * sec.get(pendM)) * pendDs, pendDs) : true;
-            sec.touch(P.med.rho, m); pendM = m; pendDs = ds;
+            const bool cont = pendM >= 0 ? test((kext0 * pendRho) * pendDs, pendDs, pendM) : true;
+            pendRho = __ldg(P.med.rho + m); pendM = m; pendDs = ds;
             return cont;
         }
-        return test(KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda}(m) * ds, ds);
+        return test(KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda}(m) * ds, ds, m);
     }
     template<int U> __device__ __forceinline__ bool segmentU(int m, double ds) { return segment(m, ds); }
     template<int U> __device__ __forceinline__ void idleU() {}
-    __device__ __forceinline__ bool test(double dtau, double ds)
+    __device__ __forceinline__ bool test(double dtau, double ds, int m)
     {
         double sNew = sPrev + ds;
         double tauNew = tauPrev + dtau;
         if (target < tauNew)
         {
             result = sPrev + ((target - tauPrev) / (tauNew - tauPrev)) * (sNew - sPrev);     // NR::interpolate_linlin
-            found = true;
+            found = true; foundM = m;
             return false;
         }
         sPrev = sNew; tauPrev = tauNew;
@@ -667,12 +675,20 @@ template<int KIND, bool SINGLE> struct PropagateJob
     __device__ __forceinline__ void finish()
     {
         Packet* q = P.poolNext;      // the survivors the absorb stage just compacted
-        if (single && pendM >= 0 && !found) test((kext0 * sec.get(pendM)) * pendDs, pendDs);
+        if (single && pendM >= 0 && !found) test((kext0 * pendRho) * pendDs, pendDs, pendM);
         const double s = found ? result : sPrev;
         // PhotonPackage::propagate: r += s k, with r and k from the record (not kept in registers over the walk)
         Packet* w = q + slot;
         const double px = w->x, py = w->y, pz = w->z, kx = w->kx, ky = w->ky, kz = w->kz;
         w->x = px + s * kx; w->y = py + s * ky; w->z = pz + s * kz;
+        // where the packet now lies, for the traversals that start from there (peel-off, escape + absorption, propagation):
+        // the leaf node of the interaction cell on tree / adaptive-mesh grids, the cell itself on Voronoi grids
+        if (KIND != GRID_CART)
+        {
+            int loc = -1;
+            if (foundM >= 0) loc = KIND == GRID_TREE ? __ldg(G.tree.cellNode + foundM) : (KIND == GRID_AMESH ? __ldg(G.amesh.cellNode + foundM) : foundM);
+            w->hint = loc;
+        }
     }
     __device__ __forceinline__ void collective(bool) {}
     __device__ __forceinline__ void periodic() {}
@@ -685,7 +701,7 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PROP_MINBLOCKS : 
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
-    PropagateJob<KIND, SINGLE> job(P);
+    PropagateJob<KIND, SINGLE> job(G, P);
     runJobs<KIND>(G, cart, ctr, job, nSurv, work, P.propRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, 0);
     flushStageSegments(&ctr->propSegments, job.nSeg);

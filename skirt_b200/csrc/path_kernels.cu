@@ -28,6 +28,8 @@ struct RayJobBase
     { rx = r[3 * (size_t)i]; ry = r[3 * (size_t)i + 1]; rz = r[3 * (size_t)i + 2]; dx = k[3 * (size_t)i]; dy = k[3 * (size_t)i + 1]; dz = k[3 * (size_t)i + 2]; }
     __device__ __forceinline__ void collective(bool) {}
     __device__ __forceinline__ void periodic() {}
+    __device__ __forceinline__ int cellHint() const { return -1; }      // the deterministic entry points always locate the start of a ray
+    __device__ __forceinline__ void noteStart(int) {}
 };
 // (jobs of the deterministic-geometry kernels never run on a predicated walker, except TauJobT<true>, which forwards)
 

@@ -15,6 +15,9 @@
 //   bool segmentU<U>(int m, double ds)   the same for walkers that step in branch-free batches; U = position of the crossing in its
 //                                batch of SKG_PERIOD (compile time: lets a job keep one pending entry per position in registers)
 //   void idleU<U>()              a walking lane's crossing at position U that produced no segment
+//   int  cellHint()              where the ray starts, if known from an earlier traversal (the walker's locator: tree / adaptive-mesh
+//                                node, Voronoi cell), else -1: the walker then skips its point location
+//   void noteStart(int locator)  called after a start without hint: the job may remember the locator for later traversals
 //   void finish()                called once per item that returned 1 or 2 from begin()
 //   void collective(bool fin)    called warp-uniformly after the finish() calls; fin = this lane just finished an item
 //   void periodic()              called warp-uniformly after every SKG_PERIOD crossing steps
@@ -86,8 +89,10 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
                         {
                             Entry en;
                             state = 2;
-                            if (w.start(grid, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, en))
+                            const int hint = job.cellHint();
+                            if (w.start(grid, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, en, hint))
                             {
+                                if (hint < 0) job.noteStart(w.locator());
                                 bool cont = true;
                                 for (int q = 0; q < en.n && cont; q++) if (en.ds[q] > 0) cont = job.outside(en.ds[q]);
                                 if (cont) state = 1;
@@ -159,7 +164,7 @@ __device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Co
     }
     else if (KIND == GRID_TREE) runJobsStep<TreeWalkerT<Job::kTreeHints>>(G.tree, ctr, job, n, workCounter, refill);
     else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter, refill);
-    else runJobsStep<VoroWalker>(G.voro, ctr, job, n, workCounter, refill);
+    else runJobsStep<VoroWalkerT<!Job::kCartFast>>(G.voro, ctr, job, n, workCounter, refill);      // kCartFast marks the shooting stages
 }
 
 }   // namespace skg

@@ -10,17 +10,153 @@ static void check(int rc) { if (rc) SKIRT_FATAL(skg_last_error()); }
 void CartesianDustGrid::upload(skg_engine* e) const
 { check(skg_grid_cartesian(e, _xv.data(), (int)_xv.size() - 1, _yv.data(), (int)_yv.size() - 1, _zv.data(), (int)_zv.size() - 1)); }
 
+// ---- tree grids ------------------------------------------------------------------------------------------------------
+void TreeDustGrid::build(skg_engine* e, const std::vector<skg_source>& geoms, const std::vector<double>& norms, uint64_t seed)
+{
+    BoxDustGrid::setup();
+    if (_Nrandom < 1) SKIRT_FATAL("Number of random samples must be at least 1");
+    if (_maxOpticalDepth < 0.0) SKIRT_FATAL("The maximum mean optical depth should be positive");
+    if (_maxMassFraction < 0.0) SKIRT_FATAL("The maximum mass fraction should be positive");
+    try
+    {
+        skirt::TreeBuilder tb(_kind, _ext, _minlevel, _maxlevel);
+        double total = 0; for (double v : norms) total += v;                        // CompDustDistribution::mass
+        const bool always = _maxOpticalDepth == 0 && _maxMassFraction == 0;         // TreeDustGrid.cpp:192
+        const double kappaV = 2600.0;                                               // Units::kappaV(), Units.cpp:30
+        std::vector<double> box, mass; std::vector<unsigned char> flags;
+        while (!tb.done())
+        {
+            const size_t n = tb.frontierSize();
+            if (!tb.frontierNeedsDecision()) { tb.subdivide(nullptr); continue; }
+            flags.assign(n, always ? 1 : 0);
+            if (!always)
+            {
+                box.resize(6 * n); mass.resize(n); tb.frontierBoxes(box.data());
+                check(skg_sample_boxes(e, (int64_t)n, box.data(), (int)geoms.size(), geoms.data(), norms.data(), _Nrandom,
+                                       seed + 7919ull * (uint64_t)tb.frontierLevel(), mass.data()));
+                for (size_t q = 0; q < n; q++)
+                {
+                    const double* b = &box[6 * q]; const double vol = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]);
+                    if (_maxMassFraction > 0 && mass[q] / total >= _maxMassFraction) flags[q] = 1;                      // :197-201
+                    if (_maxOpticalDepth > 0 && kappaV * mass[q] / std::pow(vol, 2. / 3.) >= _maxOpticalDepth) flags[q] = 1;   // :204-208
+                }
+            }
+            tb.subdivide(flags.data());
+        }
+        tb.finish((int)_search);
+        _t = tb.tables();
+    }
+    catch (std::runtime_error& ex) { SKIRT_FATAL(ex.what()); }
+    _cellNode.assign(_t.Ncells, 0);
+    for (int l = 0; l < _t.Nnodes; l++) if (_t.cell[l] >= 0) _cellNode[_t.cell[l]] = l;
+}
+
+void TreeDustGrid::upload(skg_engine* e) const
+{
+    if (_t.Nnodes == 0) SKIRT_FATAL("the tree has not been built");
+    check(skg_grid_tree(e, _kind, (int)_search, _t.Nnodes, _t.box.data(), _t.child0.data(), _t.parent.data(), _t.cell.data(), _t.dir.data(),
+                        _t.nbrStart.empty() ? nullptr : _t.nbrStart.data(), _t.nbrIds.empty() ? nullptr : _t.nbrIds.data()));
+}
+
+// ---- adaptive mesh -------------------------------------------------------------------------------------------------------
+void AdaptiveMeshDustGrid::setup()
+{
+    BoxDustGrid::setup();
+    if (!_file.empty())
+    {
+        // AdaptiveMeshAsciiFile::read, AdaptiveMeshAsciiFile.cpp:43-100
+        std::ifstream in(_file);
+        if (!in) SKIRT_FATAL("Could not open the adaptive mesh data file " + _file);
+        _nxyz.clear(); _values.clear();
+        std::string line;
+        while (std::getline(in, line))
+        {
+            std::istringstream is(line); std::string first;
+            if (!(is >> first) || first[0] == '#') continue;
+            if (first[0] == '!')
+            {
+                int n[3] = {0, 0, 0}; int have = 0;
+                if (first.size() > 1) { n[have++] = std::atoi(first.c_str() + 1); }
+                while (have < 3 && (is >> n[have])) have++;
+                if (n[0] < 1 || n[1] < 1 || n[2] < 1) SKIRT_FATAL("Invalid nonleaf line in mesh data");
+                _nxyz.insert(_nxyz.end(), n, n + 3); _values.push_back(0.0);
+            }
+            else
+            {
+                std::vector<std::string> cols{first}; std::string w; while (is >> w) cols.push_back(w);
+                if (_densityIndex < 0) SKIRT_FATAL("Field index out of range");
+                if (_densityIndex >= (int)cols.size()) SKIRT_FATAL("Insufficient number of field values in mesh data");
+                char* end = nullptr; const double v = std::strtod(cols[_densityIndex].c_str(), &end);
+                if (!end || *end) SKIRT_FATAL("Invalid leaf line in mesh data");
+                _nxyz.insert(_nxyz.end(), {0, 0, 0}); _values.push_back(v);
+            }
+        }
+    }
+    if (_nxyz.empty() || _nxyz.size() != 3 * _values.size()) SKIRT_FATAL("Reached end of file in mesh data before all nodes were read");
+    try { _t = skirt::buildAdaptiveMesh(_ext, _nxyz.data(), _values.size()); }
+    catch (std::runtime_error& ex) { SKIRT_FATAL(ex.what()); }
+    _cellNode.assign(_t.Ncells, 0);
+    for (int l = 0; l < _t.Nnodes; l++) if (_t.cell[l] >= 0) _cellNode[_t.cell[l]] = l;
+}
+
+void AdaptiveMeshDustGrid::upload(skg_engine* e) const
+{ check(skg_grid_amesh(e, _t.Nnodes, _t.box.data(), _t.nxyz.data(), _t.child0.data(), _t.cell.data(), _t.wallNbr.data())); }
+
+// ---- Voronoi ---------------------------------------------------------------------------------------------------------------
+void VoronoiDustGrid::setup()
+{
+    BoxDustGrid::setup();
+    if (!_file.empty())
+    {
+        std::ifstream in(_file);
+        if (!in) SKIRT_FATAL("Could not open the Voronoi particle file " + _file);
+        _particles.clear();
+        std::string line; double x, y, z;
+        while (std::getline(in, line)) { if (line.empty() || line[0] == '#') continue; std::istringstream is(line); if (is >> x >> y >> z) { _particles.push_back(x); _particles.push_back(y); _particles.push_back(z); } }
+    }
+    // VoronoiMesh.cpp:262-263: particles outside of the domain are ignored
+    std::vector<double> inside;
+    for (size_t q = 0; q + 2 < _particles.size(); q += 3)
+    {
+        const double* p = &_particles[q];
+        if (p[0] >= _ext[0] && p[0] <= _ext[1] && p[1] >= _ext[2] && p[1] <= _ext[3] && p[2] >= _ext[4] && p[2] <= _ext[5]) inside.insert(inside.end(), p, p + 3);
+    }
+    if (inside.empty()) SKIRT_FATAL("a Voronoi grid needs at least one particle inside its extent");
+    try { _t = skirt::buildVoronoiMesh(_ext, inside.data(), inside.size() / 3); }
+    catch (std::runtime_error& ex) { SKIRT_FATAL(ex.what()); }
+}
+
+void VoronoiDustGrid::upload(skg_engine* e) const
+{
+    check(skg_grid_voronoi(e, _t.Ncells, _t.particles.data(), _t.nbrStart.data(), _t.nbrIds.data(), _ext, _t.nb, _t.blkStart.data(), _t.blkIds.data(),
+                           _t.blkTree.data(), (int)_t.kdM.size(), _t.kdM.data(), _t.kdAxis.data(), _t.kdUp.data(), _t.kdLeft.data(), _t.kdRight.data(),
+                           _t.cellBox.data()));
+}
+
 // DustSystem::setupSelfAfter: density table rho(m,h) (DustSystem.cpp:93-177) and the kappa tables per component.
 // The reference averages 100 random samples per cell; a deterministic nsub^3 lattice is used here (set-up only).
-void DustSystem::setup(const WavelengthGrid& lg)
+void DustSystem::setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed)
 {
     if (!_grid) SKIRT_FATAL("Dust grid was not set");
     if (_comps.empty()) SKIRT_FATAL("There are no dust components");
     _grid->setup();
     _Nlambda = lg.Nlambda();
-    const int N = _grid->numCells(), C = (int)_comps.size();
+    const int C = (int)_comps.size();
     _kabs.resize((size_t)C * _Nlambda);
-    _rho.assign((size_t)N * C, 0.0); _kext.resize((size_t)C * _Nlambda); _ksca.resize((size_t)C * _Nlambda); _g.resize((size_t)C * _Nlambda);
+    _kext.resize((size_t)C * _Nlambda); _ksca.resize((size_t)C * _Nlambda); _g.resize((size_t)C * _Nlambda);
+    std::vector<double> own;
+    const bool meshDust = _grid->ownDensity(own);       // AdaptiveMeshDustDistribution: the mesh's own density field, one component
+    if (meshDust)
+    {
+        if (C != 1 || !_comps[0]->mix) SKIRT_FATAL("an adaptive mesh dust distribution has exactly one dust component with a mix");
+        _comps[0]->mix->setup(lg);
+        for (int ell = 0; ell < _Nlambda; ell++)
+        { _kabs[ell] = _comps[0]->mix->kappaabsv[ell]; _kext[ell] = _comps[0]->mix->kappaext(ell); _ksca[ell] = _comps[0]->mix->kappascav[ell]; _g[ell] = _comps[0]->mix->asymmparv[ell]; }
+        _rho = own;
+        return;
+    }
+    // mass normalisation of every component (FaceOnDustCompNormalization.cpp:67-74) and its optical properties
+    std::vector<double> norms(C); std::vector<skg_source> geoms;
     for (int h = 0; h < C; h++)
     {
         DustComp& c = *_comps[h];
@@ -28,8 +164,6 @@ void DustSystem::setup(const WavelengthGrid& lg)
         c.geometry->setup(); c.mix->setup(lg);
         for (int ell = 0; ell < _Nlambda; ell++)
         { _kabs[(size_t)h * _Nlambda + ell] = c.mix->kappaabsv[ell]; _kext[(size_t)h * _Nlambda + ell] = c.mix->kappaext(ell); _ksca[(size_t)h * _Nlambda + ell] = c.mix->kappascav[ell]; _g[(size_t)h * _Nlambda + ell] = c.mix->asymmparv[ell]; }
-        // FaceOnDustCompNormalization.cpp:67-74: rho scale = tau / (SigmaZ * kappaext(lambda)); kappaext at lambda by
-        // log-log interpolation on the simulation grid for panchromatic grids, the grid value itself for oligochromatic ones
         double kv;
         if (_Nlambda == 1) kv = c.mix->kappaext(0);
         else
@@ -40,7 +174,25 @@ void DustSystem::setup(const WavelengthGrid& lg)
             double t = (std::log10(lam) - std::log10(lv[i])) / (std::log10(lv[i + 1]) - std::log10(lv[i]));
             kv = std::pow(10.0, std::log10(c.mix->kappaext((int)i)) + t * (std::log10(c.mix->kappaext((int)i + 1)) - std::log10(c.mix->kappaext((int)i))));
         }
-        const double scale = c.norm->opticalDepth() / (c.geometry->SigmaZ() * kv);
+        norms[h] = c.norm->opticalDepth() / (c.geometry->SigmaZ() * kv);
+        geoms.push_back(c.geometry->sampler());
+    }
+    if (_grid->densityOnDevice())
+    {
+        // tree / Voronoi grids: the grid is grown (tree) and uploaded, then DustSystem::setSampleDensityBody (DustSystem.cpp:152-177)
+        // runs on the device: the mean of _Nrandom random positions per cell
+        _grid->build(e, geoms, norms, seed);
+        _grid->upload(e);
+        _rho.assign((size_t)_grid->numCells() * C, 0.0);
+        check(skg_sample_density(e, C, geoms.data(), norms.data(), _Nrandom, seed, _rho.data()));
+        return;
+    }
+    const int N = _grid->numCells();
+    _rho.assign((size_t)N * C, 0.0);
+    for (int h = 0; h < C; h++)
+    {
+        DustComp& c = *_comps[h];
+        const double scale = norms[h];
         const int ns = _nsub;
         for (int m = 0; m < N; m++)
         {
@@ -81,8 +233,8 @@ void MonteCarloSimulation::setup()
     if (!_is) SKIRT_FATAL("Instrument system was not set");
     _lambdagrid->setup();
     _ss->setup(*_lambdagrid);
-    if (_ds) _ds->setup(*_lambdagrid);
     check(skg_engine_create(_device, &_engine));
+    if (_ds) _ds->setup(*_lambdagrid, _engine, (uint64_t)_seed);
     if (_ds) _ds->upload(_engine);
     _ss->upload(_engine);
     if (!_ds)

@@ -15,6 +15,7 @@
 #include <string>
 #include <vector>
 #include "../../include/skirtgpu.h"
+#include "GridBuilders.hpp"
 
 namespace skirt
 {
@@ -257,7 +258,7 @@ public:
     skg_source sampler() const override
     {
         skg_source s{}; s.geometry = SKG_GEOM_SERSIC; s.p[0] = _reff; s.p[1] = _q;
-        s.ntab = (int)_fn->sv.size(); s.rv = _fn->sv.data(); s.Xv = _fn->Mv.data();
+        s.ntab = (int)_fn->sv.size(); s.rv = _fn->sv.data(); s.Xv = _fn->Mv.data(); s.Sv = _fn->Sv.data();
         return s;
     }
 private:
@@ -371,6 +372,95 @@ public:
     // set-up side: stratified sample points and volume of cell m (DustSystem::setSampleDensityBody, DustSystem.cpp:152-177,
     // uses random points; the engine only sees the resulting table)
     virtual void cellBox(int m, double b[6]) const = 0;
+    // grids that need the engine to come into being or to sample the dust density (tree, Voronoi), or that bring their own
+    // density field (adaptive mesh):
+    virtual bool densityOnDevice() const { return false; }      // DustSystem::setSampleDensityBody through skg_sample_density
+    virtual bool ownDensity(std::vector<double>&) const { return false; }
+    virtual void build(skg_engine*, const std::vector<skg_source>&, const std::vector<double>&, uint64_t) {}
+    virtual std::vector<double> volumes() const
+    { std::vector<double> v(numCells()); for (int m = 0; m < numCells(); m++) { double b[6]; cellBox(m, b); v[m] = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]); } return v; }
+};
+
+class BoxDustGrid : public DustGrid
+{
+public:
+    void setMinX(double v) { _ext[0] = v; } void setMaxX(double v) { _ext[1] = v; }
+    void setMinY(double v) { _ext[2] = v; } void setMaxY(double v) { _ext[3] = v; }
+    void setMinZ(double v) { _ext[4] = v; } void setMaxZ(double v) { _ext[5] = v; }
+    void setup() override
+    {
+        if (_ext[1] <= _ext[0]) SKIRT_FATAL("The extent of the box should be positive in the X direction");
+        if (_ext[3] <= _ext[2]) SKIRT_FATAL("The extent of the box should be positive in the Y direction");
+        if (_ext[5] <= _ext[4]) SKIRT_FATAL("The extent of the box should be positive in the Z direction");
+    }
+protected:
+    double _ext[6] = {0, 0, 0, 0, 0, 0};
+};
+
+// TreeDustGrid / OctTreeDustGrid / BinTreeDustGrid (TreeDustGrid.cpp:20-37 defaults, :50-233): grown level by level by
+// skirt::TreeBuilder (GridBuilders.cpp), the dust mass of the candidate nodes estimated on the GPU (skg_sample_boxes)
+class TreeDustGrid : public BoxDustGrid
+{
+public:
+    enum SearchMethod { TopDown = 0, Neighbor = 1, Bookkeeping = 2 };
+    explicit TreeDustGrid(int kind) : _kind(kind) {}
+    void setMinLevel(int v) { _minlevel = v; } void setMaxLevel(int v) { _maxlevel = v; }
+    void setSearchMethod(SearchMethod v) { _search = v; }
+    void setSampleCount(int v) { _Nrandom = v; }
+    void setMaxOpticalDepth(double v) { _maxOpticalDepth = v; }
+    void setMaxMassFraction(double v) { _maxMassFraction = v; }
+    void setMaxDensDispFraction(double v) { if (v != 0) SKIRT_FATAL("the density dispersion criterion is not supported by this host"); }
+    bool densityOnDevice() const override { return true; }
+    void build(skg_engine* e, const std::vector<skg_source>& geoms, const std::vector<double>& norms, uint64_t seed) override;
+    int numCells() const override { return _t.Ncells; }
+    void upload(skg_engine* e) const override;
+    void cellBox(int m, double b[6]) const override { const double* q = &_t.box[6 * (size_t)_cellNode[m]]; for (int c = 0; c < 6; c++) b[c] = q[c]; }
+    const skirt::TreeTables& tables() const { return _t; }
+private:
+    int _kind, _minlevel = 2, _maxlevel = 6, _Nrandom = 100; SearchMethod _search = Neighbor;
+    double _maxOpticalDepth = 0, _maxMassFraction = 1e-6;
+    skirt::TreeTables _t; std::vector<int> _cellNode;
+};
+class OctTreeDustGrid : public TreeDustGrid { public: OctTreeDustGrid() : TreeDustGrid(0) {} };
+class BinTreeDustGrid : public TreeDustGrid { public: BinTreeDustGrid() : TreeDustGrid(1) {} };
+
+// AdaptiveMeshDustGrid + AdaptiveMeshDustDistribution over an adaptive mesh data file in the format of
+// AdaptiveMeshAsciiFile (AdaptiveMeshAsciiFile.cpp:43-100): "! Nx Ny Nz" for a nonleaf, the field values for a leaf
+class AdaptiveMeshDustGrid : public BoxDustGrid
+{
+public:
+    void setAdaptiveMeshFile(const std::string& path) { _file = path; }
+    void setMesh(const std::vector<int>& nxyz, const std::vector<double>& values) { _nxyz = nxyz; _values = values; }
+    void setDensityIndex(int v) { _densityIndex = v; }
+    void setDensityUnits(double v) { _units = v; }
+    void setup() override;
+    bool ownDensity(std::vector<double>& rho) const override
+    { rho.resize(_t.Ncells); for (int m = 0; m < _t.Ncells; m++) rho[m] = std::max(_values[_t.fileIndex[m]], 0.0) * _units; return true; }
+    int numCells() const override { return _t.Ncells; }
+    void upload(skg_engine* e) const override;
+    void cellBox(int m, double b[6]) const override { const double* q = &_t.box[6 * (size_t)_cellNode[m]]; for (int c = 0; c < 6; c++) b[c] = q[c]; }
+    std::vector<double> volumes() const override { return _t.volume; }
+private:
+    std::string _file; int _densityIndex = 0; double _units = 1;
+    std::vector<int> _nxyz; std::vector<double> _values;
+    skirt::AMeshTables _t; std::vector<int> _cellNode;
+};
+
+// VoronoiDustGrid over particle positions read from a text file (x y z per line) or set directly
+class VoronoiDustGrid : public BoxDustGrid
+{
+public:
+    void setParticleFile(const std::string& path) { _file = path; }
+    void setParticles(const std::vector<double>& xyz) { _particles = xyz; }
+    void setup() override;
+    bool densityOnDevice() const override { return true; }
+    int numCells() const override { return _t.Ncells; }
+    void upload(skg_engine* e) const override;
+    void cellBox(int m, double b[6]) const override { for (int c = 0; c < 6; c++) b[c] = _t.cellBox[6 * (size_t)m + c]; }
+    std::vector<double> volumes() const override { return _t.volume; }
+private:
+    std::string _file; std::vector<double> _particles;
+    skirt::VoronoiTables _t;
 };
 
 class CartesianDustGrid : public DustGrid          // CartesianDustGrid.cpp:28-43
@@ -428,20 +518,21 @@ class DustSystem
 public:
     void setDustGrid(DustGrid* g) { _grid.reset(g); }
     void addComponent(DustComp* c) { _comps.emplace_back(c); }
-    void setSampleLattice(int n) { _nsub = n; }         // stands in for setSampleCount: nsub^3 stratified points per cell
+    void setSampleLattice(int n) { _nsub = n; }         // Cartesian grids: nsub^3 stratified points per cell stand in for setSampleCount
+    void setSampleCount(int n) { _Nrandom = n; }        // tree / Voronoi grids: random positions per cell, drawn on the device
     void setStoreAbsorptionRates(bool v) { _storeabs = v; }
     bool storeabsorptionrates() const { return _storeabs; }
     int Ncells() const { return _grid->numCells(); }
     int Ncomp() const { return (int)_comps.size(); }
     DustGrid* dustGrid() const { return _grid.get(); }
-    void setup(const WavelengthGrid& lg);
+    void setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed);
     void upload(skg_engine* e) const;
     const std::vector<double>& rho() const { return _rho; }
     const std::vector<double>& kappaabs() const { return _kabs; }       // [Ncomp*Nlambda]
-    std::vector<double> volumes() const { std::vector<double> v(Ncells()); for (int m = 0; m < Ncells(); m++) { double b[6]; _grid->cellBox(m, b); v[m] = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]); } return v; }
+    std::vector<double> volumes() const { return _grid->volumes(); }
 private:
     std::unique_ptr<DustGrid> _grid; std::vector<std::unique_ptr<DustComp>> _comps;
-    int _nsub = 2; bool _storeabs = false; int _Nlambda = 0;
+    int _nsub = 2, _Nrandom = 100; bool _storeabs = false; int _Nlambda = 0;
     std::vector<double> _rho, _kext, _ksca, _g, _kabs;
 };
 

@@ -8,7 +8,8 @@
 //   sim oligo|pan ; packages N ; seed S ; minweightreduction f ; minscatt n ; scattbias xi ; emissionbias xi
 //   wavelengths l1 l2 ...          | loggrid min max points
 //   box xmin xmax ymin ymax zmin zmax
-//   grid cartesian nx ny nz lin|pow r|sympow r  (x3)
+//   grid cartesian nx ny nz lin|pow r|sympow r  (x3) | grid octtree|bintree minLevel maxLevel search maxMassFraction [samples [maxTau]]
+//        | grid amesh <file> densityUnits [index] (+ meshdust) | grid voronoi <particle file>
 //   dustmix interstellar <file> | dustmix table kabs ksca g      (one wavelength)
 //   dust tau lambda expdisk hR hz Rmax zmax
 //   stellar L1[,L2,...]|bb:T:Lbol expdisk hR hz Rmax zmax | sersic n Reff q
@@ -99,7 +100,31 @@ int main(int argc, char** argv)
             else if (key == "grid")
             {
                 std::string kind; in >> kind;
-                if (kind != "cartesian") SKIRT_FATAL("this driver builds Cartesian grids; tree, Voronoi and adaptive-mesh grids are handed to the engine as flattened tables");
+                auto setBox = [&](BoxDustGrid* g) { g->setMinX(box[0]); g->setMaxX(box[1]); g->setMinY(box[2]); g->setMaxY(box[3]); g->setMinZ(box[4]); g->setMaxZ(box[5]); };
+                if (kind == "octtree" || kind == "bintree")
+                {
+                    // grid octtree|bintree minLevel maxLevel search(0 TopDown, 1 Neighbor, 2 Bookkeeping) maxMassFraction [sampleCount [maxOpticalDepth]]
+                    int minl, maxl, search; double mf; int samples = 100; double maxtau = 0;
+                    in >> minl >> maxl >> search >> mf; in >> samples >> maxtau;
+                    TreeDustGrid* g = kind == "octtree" ? (TreeDustGrid*)new OctTreeDustGrid() : (TreeDustGrid*)new BinTreeDustGrid();
+                    setBox(g); g->setMinLevel(minl); g->setMaxLevel(maxl); g->setSearchMethod((TreeDustGrid::SearchMethod)search);
+                    g->setMaxMassFraction(mf); g->setSampleCount(samples); g->setMaxOpticalDepth(maxtau);
+                    ds->setDustGrid(g); continue;
+                }
+                if (kind == "amesh")
+                {
+                    // grid amesh <adaptive mesh data file> densityUnits [densityIndex]; the dust is the mesh's own density field
+                    std::string file; double units; int index = 0; in >> file >> units; in >> index;
+                    auto* g = new AdaptiveMeshDustGrid(); setBox(g); g->setAdaptiveMeshFile(file); g->setDensityUnits(units); g->setDensityIndex(index);
+                    ds->setDustGrid(g); continue;
+                }
+                if (kind == "voronoi")
+                {
+                    std::string file; in >> file;           // grid voronoi <particle file: x y z per line>
+                    auto* g = new VoronoiDustGrid(); setBox(g); g->setParticleFile(file);
+                    ds->setDustGrid(g); continue;
+                }
+                if (kind != "cartesian") SKIRT_FATAL("unknown dust grid " + kind);
                 int nx, ny, nz; in >> nx >> ny >> nz;
                 auto* g = new CartesianDustGrid();
                 g->setMinX(box[0]); g->setMaxX(box[1]); g->setMinY(box[2]); g->setMaxY(box[3]); g->setMinZ(box[4]); g->setMaxZ(box[5]);
@@ -107,6 +132,14 @@ int main(int argc, char** argv)
                 ds->setDustGrid(g);
             }
             else if (key == "dustmix") { in >> mixKind; if (mixKind == "interstellar") in >> mixFile; else in >> mixv[0] >> mixv[1] >> mixv[2]; }
+            else if (key == "meshdust")
+            {
+                // meshdust: the dust component of an adaptive mesh's own density field (MeshDustComponent), with the current mix
+                auto* c = new DustComp();
+                if (mixKind == "interstellar") c->setMix(new InterstellarDustMix(mixFile));
+                else { auto* m = new TableDustMix(); m->setTable({0.55e-6}, {mixv[0]}, {mixv[1]}, {mixv[2]}); c->setMix(m); }
+                ds->addComponent(c);
+            }
             else if (key == "dust")
             {
                 double tau, lam; in >> tau >> lam;
