@@ -92,7 +92,8 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
                             const int hint = job.cellHint();
                             if (w.start(grid, ctr, job.rx, job.ry, job.rz, job.dx, job.dy, job.dz, en, hint))
                             {
-                                if (hint < 0) job.noteStart(w.locator());
+                                // (a ray that had to be moved into the grid starts OUTSIDE: its locator is not where the packet lies)
+                                if (hint < 0 && en.n == 0) job.noteStart(w.locator());
                                 bool cont = true;
                                 for (int q = 0; q < en.n && cont; q++) if (en.ds[q] > 0) cont = job.outside(en.ds[q]);
                                 if (cont) state = 1;
@@ -164,7 +165,11 @@ __device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Co
     }
     else if (KIND == GRID_TREE) runJobsStep<TreeWalkerT<Job::kTreeHints>>(G.tree, ctr, job, n, workCounter, refill);
     else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter, refill);
+#ifdef SKG_VORO_MC_EXACT
+    else runJobsStep<VoroWalkerT<true>>(G.voro, ctr, job, n, workCounter, refill);                   // experiment: exact walker everywhere
+#else
     else runJobsStep<VoroWalkerT<!Job::kCartFast>>(G.voro, ctr, job, n, workCounter, refill);      // kCartFast marks the shooting stages
+#endif
 }
 
 }   // namespace skg

@@ -135,11 +135,20 @@ void VoronoiDustGrid::upload(skg_engine* e) const
 
 // DustSystem::setupSelfAfter: density table rho(m,h) (DustSystem.cpp:93-177) and the kappa tables per component.
 // The reference averages 100 random samples per cell; a deterministic nsub^3 lattice is used here (set-up only).
-void DustSystem::setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed)
+// the part of the set-up that needs no device: property validation, meshes, the tessellation / mesh of file-based grids
+void DustSystem::presetup(const WavelengthGrid& lg)
 {
+    if (_presetup) return;
     if (!_grid) SKIRT_FATAL("Dust grid was not set");
     if (_comps.empty()) SKIRT_FATAL("There are no dust components");
     _grid->setup();
+    for (auto& c : _comps) { if (c->geometry) c->geometry->setup(); if (c->mix) c->mix->setup(lg); }
+    _presetup = true;
+}
+
+void DustSystem::setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed)
+{
+    presetup(lg);
     _Nlambda = lg.Nlambda();
     const int C = (int)_comps.size();
     _kabs.resize((size_t)C * _Nlambda);
@@ -149,7 +158,6 @@ void DustSystem::setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed)
     if (meshDust)
     {
         if (C != 1 || !_comps[0]->mix) SKIRT_FATAL("an adaptive mesh dust distribution has exactly one dust component with a mix");
-        _comps[0]->mix->setup(lg);
         for (int ell = 0; ell < _Nlambda; ell++)
         { _kabs[ell] = _comps[0]->mix->kappaabsv[ell]; _kext[ell] = _comps[0]->mix->kappaext(ell); _ksca[ell] = _comps[0]->mix->kappascav[ell]; _g[ell] = _comps[0]->mix->asymmparv[ell]; }
         _rho = own;
@@ -161,7 +169,6 @@ void DustSystem::setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed)
     {
         DustComp& c = *_comps[h];
         if (!c.geometry || !c.mix || !c.norm) SKIRT_FATAL("dust component is incomplete");
-        c.geometry->setup(); c.mix->setup(lg);
         for (int ell = 0; ell < _Nlambda; ell++)
         { _kabs[(size_t)h * _Nlambda + ell] = c.mix->kappaabsv[ell]; _kext[(size_t)h * _Nlambda + ell] = c.mix->kappaext(ell); _ksca[(size_t)h * _Nlambda + ell] = c.mix->kappascav[ell]; _g[(size_t)h * _Nlambda + ell] = c.mix->asymmparv[ell]; }
         double kv;
@@ -233,6 +240,7 @@ void MonteCarloSimulation::setup()
     if (!_is) SKIRT_FATAL("Instrument system was not set");
     _lambdagrid->setup();
     _ss->setup(*_lambdagrid);
+    if (_ds) _ds->presetup(*_lambdagrid);            // validation and host-only set-up before a device is asked for
     check(skg_engine_create(_device, &_engine));
     if (_ds) _ds->setup(*_lambdagrid, _engine, (uint64_t)_seed);
     if (_ds) _ds->upload(_engine);

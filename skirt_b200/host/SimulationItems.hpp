@@ -525,6 +525,7 @@ public:
     int Ncells() const { return _grid->numCells(); }
     int Ncomp() const { return (int)_comps.size(); }
     DustGrid* dustGrid() const { return _grid.get(); }
+    void presetup(const WavelengthGrid& lg);
     void setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed);
     void upload(skg_engine* e) const;
     const std::vector<double>& rho() const { return _rho; }
@@ -532,7 +533,7 @@ public:
     std::vector<double> volumes() const { return _grid->volumes(); }
 private:
     std::unique_ptr<DustGrid> _grid; std::vector<std::unique_ptr<DustComp>> _comps;
-    int _nsub = 2, _Nrandom = 100; bool _storeabs = false; int _Nlambda = 0;
+    int _nsub = 2, _Nrandom = 100; bool _storeabs = false, _presetup = false; int _Nlambda = 0;
     std::vector<double> _rho, _kext, _ksca, _g, _kabs;
 };
 

@@ -303,3 +303,47 @@ def zscores(mean_a, sem_a, mean_b, sem_b):
     sig = np.sqrt(sem_a ** 2 + sem_b ** 2)
     ok = sig > 0
     return (mean_a - mean_b)[ok] / sig[ok]
+
+
+# ---- the Monte Carlo gate of SURVEY.md 8d(ii) ---------------------------------------------------------------------------------
+def mc_gate(a, r, label, signal=0.15, min_bins=0.0, total_sigma=3.5, total_rel=0.01):
+    """a[Ba, ...], r[Br, ...]: the same output from Ba engine batches and Br reference batches (>= 16 each).
+    Contract: z-scores per bin with sigma^2 = sem_gpu^2 + sem_ref^2; |z| < 3 for 99.7 % of the bins with signal and no
+    systematic offset, totals consistent.  The 99.7 % is the Gaussian figure: with the sems estimated from B batches, z
+    follows Student's t with the Welch-Satterthwaite degrees of freedom of the bin (2B-2 when both sides are equally noisy,
+    B-1 when one side dominates), so a bin lies beyond 3 sigma with probability p_i = 2 sf_t(3, dof_i) (0.5 % ... 0.9 % at
+    B = 16) and E = sum p_i such bins are expected.  Bins are not independent (the packets of a batch cross many cells), which
+    widens the scatter of that count beyond the binomial: allowed are E + 5 sqrt(E) + 2.  No bin may lie beyond the value that the
+    largest of N Student-t deviates exceeds once in a thousand trials (5.5 sigma at least).
+    A systematic offset is a mean z beyond max(0.15, 3.5/sqrt(N)).  The batch totals must agree within total_sigma
+    (Welch) and total_rel relative -- the test with power against a bias, since the bins of a total add coherently."""
+    from scipy import stats
+    a = np.asarray(a, dtype=np.float64).reshape(len(a), -1); r = np.asarray(r, dtype=np.float64).reshape(len(r), -1)
+    scale = float(np.max(np.abs(r))) or 1.0          # (the squares of very small luminosities would underflow)
+    a = a / scale; r = r / scale
+    Ba, Br = len(a), len(r)
+    assert Ba >= 16 and Br >= 16, f"{label}: the gate needs at least 16 batches on both sides ({Ba}, {Br})"
+    ta, tr = a.sum(1), r.sum(1)
+    zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / Ba + tr.var(ddof=1) / Br)
+    assert abs(zt) < total_sigma and abs(ta.mean() / tr.mean() - 1) < total_rel, \
+        f"{label}: totals differ by {zt:.2f} sigma (gpu {ta.mean():.6g}, reference {tr.mean():.6g})"
+    if a.shape[1] < 2:
+        return dict(zt=zt)
+    ma, mr = a.mean(0), r.mean(0); sa, sr_ = a.std(0, ddof=1) / np.sqrt(Ba), r.std(0, ddof=1) / np.sqrt(Br)
+    # bins with signal: batch mean known to better than 15 % on both sides (sparser bins have skewed, far-from-Gaussian batch statistics)
+    ok = (sa > 0) & (sr_ > 0) & (sa < signal * ma) & (sr_ < signal * mr)
+    N = int(ok.sum())
+    assert N >= max(1, min_bins * a.shape[1]), f"{label}: only {N} of {a.shape[1]} bins carry signal"
+    va, vr = sa[ok] ** 2, sr_[ok] ** 2
+    z = (ma[ok] - mr[ok]) / np.sqrt(va + vr)
+    fa, fr = va / (va + vr), vr / (va + vr)          # (scale-free: the luminosities themselves may be ~1e-300 squared)
+    dof = 1.0 / (fa ** 2 / (Ba - 1) + fr ** 2 / (Br - 1))
+    E = float(np.sum(2 * stats.t.sf(3.0, dof)))
+    allowed = int(np.ceil(E + 5 * np.sqrt(E) + 2))
+    nout = int(np.sum(np.abs(z) >= 3))
+    assert nout <= allowed, f"{label}: {nout} of {N} bins beyond 3 sigma ({E:.1f} expected, {allowed} allowed)"
+    zmax = max(5.5, float(stats.t.isf(0.5e-3 / N, float(np.min(dof)))))
+    assert np.max(np.abs(z)) < zmax, f"{label}: a bin differs by {np.max(np.abs(z)):.1f} sigma (limit {zmax:.1f} for {N} bins)"
+    lim = max(0.15, 3.5 / np.sqrt(N))
+    assert abs(z.mean()) < lim, f"{label}: systematic offset, mean z = {z.mean():.3f} over {N} bins (limit {lim:.3f})"
+    return dict(zt=zt, z=z, bins=N, outliers=nout)

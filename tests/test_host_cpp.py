@@ -103,3 +103,54 @@ def test_pan_flow_through_the_cpp_host(tmp_path):
     assert 0.7 < sed.sum() / Lstar < 1.3
     assert 0.02 < labs.sum() / Lstar < 0.6
     assert sed[-8:].sum() > 0 and sed[:5].sum() > 0
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(RUN), reason="skirt_b200_run not built")
+@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi"])
+def test_other_grids_through_the_cpp_host(tmp_path, engine, kind):
+    """the C++ host builds tree / adaptive-mesh / Voronoi grids itself (skirt_b200/host/GridBuilders.cpp; tree subdivision and
+    cell densities sampled on the device) and shoots through them; the Python mirror does the same through libskirthost.so:
+    the two product-side hosts agree on the detected and absorbed luminosity"""
+    from skirt_b200 import configs, hostlib, simulation as sim
+    mixline = f"dustmix table {common.MIX_V['kabs']!r} {common.MIX_V['ksca']!r} {common.MIX_V['g']!r}"
+    dust = f"dust 1.0 0.55e-6 expdisk {4000*PC!r} {140*PC!r} 0 0"
+    b = common.C1_BOX
+    lg = sim.OligoWavelengthGrid([0.55e-6])
+    mix = sim.TableDustMix(common.MIX_V["kabs"], common.MIX_V["ksca"], common.MIX_V["g"])
+    comp = sim.DustComp(sim.ExpDiskGeometry(4000 * PC, 140 * PC), mix, 1.0, 0.55e-6)
+    if kind in ("octtree", "bintree"):
+        lo, hi = (2, 5) if kind == "octtree" else (6, 14)
+        grid_line = f"grid {kind} {lo} {hi} 1 1e-4 50"
+        cls = sim.OctTreeDustGrid if kind == "octtree" else sim.BinTreeDustGrid
+        grid = cls(b[0], b[1], b[2], b[3], b[4], b[5], lo, hi, "Neighbor", 50, 0.0, 1e-4)
+    elif kind == "amesh":
+        nxyz, val = configs.synthetic_amesh(root=4, depth=3, frac=2e-3)
+        f = tmp_path / "mesh.txt"
+        f.write_text("# synthetic adaptive mesh\n" + "\n".join(f"! {n[0]} {n[1]} {n[2]}" if n[0] else repr(float(v)) for n, v in zip(nxyz, val)) + "\n")
+        grid_line = f"grid amesh {f} 1e-24"; dust = "meshdust"
+        grid = sim.AdaptiveMeshDustGrid(b[0], b[1], b[2], b[3], b[4], b[5], nxyz, val, densityUnits=1e-24)
+        comp = sim.DustComp(None, mix, 1.0, 0.55e-6)
+    else:
+        if not hostlib.voronoi_available():
+            pytest.skip("libskirthost.so was built without Voro++")
+        pts = common.voronoi_particles(3000)
+        f = tmp_path / "particles.txt"; np.savetxt(f, pts, fmt="%.17g")
+        grid_line = f"grid voronoi {f}"
+        grid = sim.VoronoiDustGrid(b[0], b[1], b[2], b[3], b[4], b[5], pts)
+    text = "\n".join(["sim oligo", "packages 200000.0", "seed 4357", "wavelengths 0.55e-6", common.box_line(b), grid_line, "storeabs 1", mixline, dust,
+                      f"stellar 1.0 expdisk {4000*PC!r} {350*PC!r} 0 0", f"instrument sed s88 {1e7*PC!r} {float(np.radians(88))!r} 0 0"]) + "\n"
+    r = run(tmp_path, text)
+    assert r.returncode == 0, r.stderr
+    st = json.loads(r.stdout.strip().splitlines()[-1])
+    sed = np.fromfile(tmp_path / "out_s88_sed.f64"); labs = np.fromfile(tmp_path / "out_Labs.f64")
+    # the same configuration through the Python mirror (its own tree: the device samples differ, the grids are statistically alike)
+    ds = sim.DustSystem(grid, [comp], lg)
+    ss = sim.StellarSystem([sim.StellarComp(sim.ExpDiskGeometry(4000 * PC, 350 * PC), [1.0])])
+    ins = sim.InstrumentSystem([sim.SEDInstrument("s88", 1e7 * PC, float(np.radians(88)))])
+    m = sim.MonteCarloSimulation(lg, ss, ds, ins, packages=2e5, storeAbsorption=True, engine=engine).setup()
+    engine.reset_results(); m.runstellaremission()
+    assert abs(st["cells"] / engine.Ncells - 1) < (0.15 if kind in ("octtree", "bintree") else 1e-12)
+    assert st["packets"] == 200000 and labs.size == st["cells"]
+    assert abs(sed[0] / engine.fetch_sed(0)[0] - 1) < 0.03, f"{kind}: SED {sed[0]} vs {engine.fetch_sed(0)[0]}"
+    assert abs(labs.sum() / engine.fetch_labs().sum() - 1) < 0.03

@@ -251,3 +251,41 @@ def test_one_pass_on_the_full_size_grid(engine):
     assert common.paths_bit_identical(a, b)
     waste = b["slab_records"] / max(len(a["m"]), 1) - 1
     assert 0 <= waste < 0.12, f"slabs waste {waste:.1%}"
+
+
+@pytest.mark.parametrize("case", ["cart_lin_100", "cart_sympow_100", "octtree_level8", "amesh_depth6", "voronoi_1e5"])
+def test_full_size_grids_bit_exact_against_the_reference(engine, case):
+    """fixed rays at the sizes of BASELINE.json's configurations, against the reference's own DustGrid::path() +
+    fillOpticalDepth (oracle/_ref, RefSim.path_batch): Cartesian 100^3 with linear and symmetric power-law meshes (C1/C2),
+    an octree down to level 8 (C3), an adaptive mesh refined to depth 6 (C5) and a Voronoi mesh of 1e5 cells (C4's type).
+    Cell sequences, counts, ds, s, dtau and tau bit-identical; the one-pass interface as well."""
+    import os
+    from oracle import skirtref as sr
+    from skirt_b200 import configs
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    thr = os.cpu_count() or 1
+    kw = {}
+    if case.startswith("cart"):
+        mesh = "lin" if "lin" in case else "sympow 30"
+        spec = common.spec_c1(n=100, threads=thr, dustsamples=2, grid=f"grid cartesian 100 100 100 {mesh} {mesh} {mesh}")
+    elif case == "octtree_level8":
+        spec = common.spec_grid("octtree", search=1, minlevel=2, maxlevel=8, massfrac=2e-6, threads=thr)
+    elif case == "amesh_depth6":
+        spec = common.spec_grid("amesh", threads=thr); kw["amesh"] = configs.synthetic_amesh(root=8, depth=6, frac=2e-5)
+    else:
+        spec = common.spec_grid("voronoi", threads=thr); kw["particles"] = configs.sph_particles(100000)
+    S = sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw).setup()
+    tables, medium = S.grid_tables(), S.medium()
+    engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
+    assert engine.Ncells >= (10 ** 6 if case.startswith("cart") else 10 ** 5)
+    r, k = common.rays(30000, common.C1_BOX, 4242)
+    ra, ka = common.adversarial_rays(common.C1_BOX)
+    r = np.concatenate([r, ra]); k = np.concatenate([k, ka])
+    ref = S.path_batch(r, k, ell=0, nthreads=thr)
+    got = engine.path_batch(r, k, ell=0)
+    assert len(ref["m"]) > 10 * len(r)
+    assert common.paths_bit_identical(got, ref), case
+    one = engine.path_batch_onepass(r, k, ell=0)
+    assert common.paths_bit_identical(one, ref), case + " (one pass)"
+    assert engine.stuck_counts()[1] == 0
