@@ -82,6 +82,17 @@ int skg_num_cells(skg_engine* e);
 int skg_medium(skg_engine* e, int Ncells, int Ncomp, int Nlambda, const double* rho, const double* kext,
                const double* ksca, const double* g);
 
+/* Polarisation: the Mueller matrix coefficients of every dust component, DustMix::addpolarization
+ * (DustMix.cpp:325-361; e.g. ElectronDustMix.cpp:41-59): S11, S12, S33, S34 [(h*Nlambda + ell)*Ntheta + t] on the scattering
+ * angles theta_t = t*pi/(Ntheta-1).  Call after skg_medium (a new medium is unpolarised) and before skg_instruments.
+ * The engine derives the cumulative distribution of theta and the phase-function normalisation (DustMix.cpp:96-123);
+ * the shooting phases then carry a Stokes vector per packet (StokesVector.cpp), sample the scattering angles from the
+ * Mueller matrix (DustMix::scatteringDirectionAndPolarization, DustMix.cpp:584-605, sampleTheta / samplePhi :716-731),
+ * weight the peel-off by the polarised phase function (:648-662) and record Stokes Q, U, V in FullInstruments
+ * (scatteringPeelOffPolarization :619-644, FullInstrument.cpp:136-141,165-170).  Like the reference (DustSystem.cpp:74)
+ * either every component supports polarisation or none. */
+int skg_medium_polarization(skg_engine* e, int Ntheta, const double* S11, const double* S12, const double* S33, const double* S34);
+
 /* ---- deterministic geometry: batched DustGrid::path() + DustGridPath::fillOpticalDepth() ------------ */
 /* Replaces DustSystem::fillOpticalDepth (DustSystem.cpp:959-980) for n rays at once.
  * Step 1 counts the segments of every ray and returns CSR offsets (offsets[n+1], int64) and the total;
@@ -173,6 +184,8 @@ enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3, SKG_INSTR_F
 /* FullInstrument (FullInstrument.cpp:107-172, unpolarised part): one data cube + SED per channel, in this order */
 enum { SKG_CHAN_TRANSPARENT = 0, SKG_CHAN_STELLAR_DIRECT = 1, SKG_CHAN_STELLAR_SCATTERED = 2, SKG_CHAN_DUST_DIRECT = 3,
        SKG_CHAN_DUST_SCATTERED = 4, SKG_CHAN_SCATTERING_LEVEL1 = 5 /* + (level - 1), level = 1..scatteringLevels */ };
+/* with a polarised medium three more channels follow the scattering levels: Stokes Q, U, V of the total flux
+ * (FullInstrument::_ftotQv/_ftotUv/_ftotVv): channel 5 + scatteringLevels + {0, 1, 2} */
 typedef struct skg_instrument
 {
     int kind;

@@ -100,6 +100,7 @@ namespace
     {
     public:
         std::vector<double> kabs, ksca, g;
+        int Ntheta = 0; std::vector<double> S11, S12, S33, S34;     // optional Mueller matrix coefficients [Nlambda*Ntheta]
         void setupSelfBefore()
         {
             DustMix::setupSelfBefore();
@@ -107,6 +108,14 @@ namespace
             Array a(n), s(n), gg(n);
             for (int i = 0; i < n; i++) { a[i] = kabs[i]; s[i] = ksca[i]; gg[i] = g[i]; }
             addpopulation(1.0, a, s, gg);   // mu = 1 so that sigma == kappa, as InterstellarDustMix.cpp:58
+            if (Ntheta > 0)
+            {
+                // a polarised mix, like ElectronDustMix.cpp:59 / MultiGrainDustMix: DustMix::addpolarization (DustMix.cpp:325-361)
+                Table<2> t11(n, Ntheta), t12(n, Ntheta), t33(n, Ntheta), t34(n, Ntheta);
+                for (int i = 0; i < n; i++) for (int t = 0; t < Ntheta; t++)
+                { t11(i,t) = S11[(size_t)i*Ntheta+t]; t12(i,t) = S12[(size_t)i*Ntheta+t]; t33(i,t) = S33[(size_t)i*Ntheta+t]; t34(i,t) = S34[(size_t)i*Ntheta+t]; }
+                addpolarization(t11, t12, t33, t34);
+            }
         }
     };
 
@@ -232,7 +241,7 @@ namespace
     {
         std::istringstream all(spec);
         std::string line;
-        double packages = 1e6, mwr = 1e4, minscatt = 0, xi = 0.5, ebias = 0.5;
+        double packages = 1e6, mwr = 1e4, minscatt = 0, xi = 0.5, ebias = 0.5; int contscatt = 0;
         int threads = 1, seed = 4357, dustsamples = 100, storeabs = 0, selfabs = 0, unitsys = 0, fluxstyle = 0;
         std::vector<std::string> lines;
         while (std::getline(all, line)) if (!line.empty() && line[0] != '#') lines.push_back(line);
@@ -256,6 +265,7 @@ namespace
             else if (key == "minweightreduction") in >> mwr;
             else if (key == "minscatt") in >> minscatt;
             else if (key == "scattbias") in >> xi;
+            else if (key == "continuousscattering") in >> contscatt;
             else if (key == "emissionbias") in >> ebias;
             else if (key == "dustsamples") in >> dustsamples;
             else if (key == "storeabs") in >> storeabs;
@@ -363,7 +373,7 @@ namespace
         // assemble the hierarchy the way the ski file would
         S->mc->parallelFactory()->setMaxThreadCount(threads);
         S->mc->random()->setSeed(seed);
-        S->mc->setPackages(packages); S->mc->setMinWeightReduction(mwr); S->mc->setMinScattEvents(minscatt); S->mc->setScattBias(xi);
+        S->mc->setPackages(packages); S->mc->setMinWeightReduction(mwr); S->mc->setMinScattEvents(minscatt); S->mc->setScattBias(xi); S->mc->setContinuousScattering(contscatt != 0);
         S->ss->setEmissionBias(ebias);
         S->mc->setInstrumentSystem(S->is);
         Units* units = unitsys == 1 ? (Units*)new StellarUnits() : unitsys == 2 ? (Units*)new ExtragalacticUnits() : (Units*)new SIUnits();
@@ -441,6 +451,11 @@ int skr_set_luminosities(void* h, int comp, const double* L, int n)
 int skr_set_mix(void* h, int comp, const double* kabs, const double* ksca, const double* g, int n)
 { Sim* S = (Sim*)h; if (comp < 0 || comp >= (int)S->mixes.size()) return 1;
   S->mixes[comp]->kabs.assign(kabs, kabs+n); S->mixes[comp]->ksca.assign(ksca, ksca+n); S->mixes[comp]->g.assign(g, g+n); return 0; }
+// Mueller matrix coefficients of dust component `comp`: S11, S12, S33, S34 [Nlambda*Ntheta] (theta = t*pi/(Ntheta-1))
+int skr_set_mueller(void* h, int comp, int Ntheta, int Nlambda, const double* S11, const double* S12, const double* S33, const double* S34)
+{ Sim* S = (Sim*)h; if (comp < 0 || comp >= (int)S->mixes.size() || Ntheta < 2) return 1;
+  size_t n = (size_t)Ntheta * Nlambda; TableDustMix* m = S->mixes[comp]; m->Ntheta = Ntheta;
+  m->S11.assign(S11, S11+n); m->S12.assign(S12, S12+n); m->S33.assign(S33, S33+n); m->S34.assign(S34, S34+n); return 0; }
 int skr_set_particles(void* h, const double* xyz, int n)
 { Sim* S = (Sim*)h; if (!S->vfile) return 1; S->vfile->xyz.assign(xyz, xyz+3*(size_t)n); return 0; }
 int skr_set_amesh(void* h, const int* nxyz, const double* val, int n)
@@ -698,6 +713,7 @@ int skr_reset(void* h, int seed)
                 for (Array* a : {&f->_ftrav, &f->_Ftrav, &f->_fstrdirv, &f->_Fstrdirv, &f->_fstrscav, &f->_Fstrscav, &f->_fdusdirv, &f->_Fdusdirv,
                                  &f->_fdusscav, &f->_Fdusscav}) if (a->size()) *a = 0.0;
                 for (int n = 0; n < f->_Nscatt; n++) { f->_fstrscavv[n] = 0.0; f->_Fstrscavv[n] = 0.0; }
+                for (Array* a : {&f->_ftotQv, &f->_FtotQv, &f->_ftotUv, &f->_FtotUv, &f->_ftotVv, &f->_FtotVv}) if (a->size()) *a = 0.0;
             }
         }
         if (S->ds)
@@ -754,7 +770,13 @@ int skr_get_full_channel(void* h, int i, int c, double* frame, double* sed)
     case 2: fa = &f->_fstrscav; sa = &f->_Fstrscav; break;
     case 3: fa = &f->_fdusdirv; sa = &f->_Fdusdirv; break;
     case 4: fa = &f->_fdusscav; sa = &f->_Fdusscav; break;
-    default: if (c - 5 >= f->_Nscatt) return 1; fa = &f->_fstrscavv[c - 5]; sa = &f->_Fstrscavv[c - 5];
+    default:
+        if (c - 5 < f->_Nscatt) { fa = &f->_fstrscavv[c - 5]; sa = &f->_Fstrscavv[c - 5]; break; }
+        // the Stokes Q, U, V arrays of a simulation with polarisation follow the scattering levels (FullInstrument.cpp:79-87)
+        if (!f->_polarization || c - 5 - f->_Nscatt > 2) return 1;
+        if (c - 5 - f->_Nscatt == 0) { fa = &f->_ftotQv; sa = &f->_FtotQv; }
+        else if (c - 5 - f->_Nscatt == 1) { fa = &f->_ftotUv; sa = &f->_FtotUv; }
+        else { fa = &f->_ftotVv; sa = &f->_FtotVv; }
     }
     if (frame) for (size_t j = 0; j < fa->size(); j++) frame[j] = (*fa)[j];
     if (sed) for (size_t j = 0; j < sa->size(); j++) sed[j] = (*sa)[j];

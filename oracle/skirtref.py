@@ -49,7 +49,7 @@ def _f64(a):
 class RefSim:
     """One reference simulation hierarchy (MonteCarloSimulation + children) built from a spec."""
 
-    def __init__(self, spec, luminosities=None, mixes=None, particles=None, amesh=None):
+    def __init__(self, spec, luminosities=None, mixes=None, particles=None, amesh=None, mueller=None):
         L = lib()
         self.h = C.c_void_p(L.skr_create(spec.encode()))
         if not self.h:
@@ -62,6 +62,12 @@ class RefSim:
             kabs, ksca, g = _f64(kabs), _f64(ksca), _f64(g)
             self._chk(L.skr_set_mix(self.h, i, kabs.ctypes.data_as(C.c_void_p), ksca.ctypes.data_as(C.c_void_p),
                                     g.ctypes.data_as(C.c_void_p), len(g)))
+        for i, mu in enumerate(mueller or []):
+            if mu is None:
+                continue
+            S11, S12, S33, S34 = (_f64(v) for v in mu)       # each [Nlambda, Ntheta]
+            self._chk(L.skr_set_mueller(self.h, i, S11.shape[1], S11.shape[0], S11.ctypes.data_as(C.c_void_p), S12.ctypes.data_as(C.c_void_p),
+                                        S33.ctypes.data_as(C.c_void_p), S34.ctypes.data_as(C.c_void_p)))
         if particles is not None:
             p = _f64(particles)
             self._chk(L.skr_set_particles(self.h, p.ctypes.data_as(C.c_void_p), len(p)))

@@ -193,6 +193,13 @@ class Engine:
         self._chk(self._lib.skg_medium(self.h, Ncells, Ncomp, Nlambda, _vp(rho), _vp(kext), _vp(ksca), _vp(g)))
         self.Nlambda = Nlambda
         self.Ncomp = Ncomp
+        self.polarized = False
+
+    def medium_polarization(self, S11, S12, S33, S34):
+        """skg_medium_polarization: Mueller matrix coefficients [Ncomp, Nlambda, Ntheta] of every dust component"""
+        a = [np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(self.Ncomp, self.Nlambda, -1)) for v in (S11, S12, S33, S34)]
+        self._chk(self._lib.skg_medium_polarization(self.h, a[0].shape[2], _vp(a[0]), _vp(a[1]), _vp(a[2]), _vp(a[3])))
+        self.polarized = True
 
     # ---- deterministic geometry ------------------------------------------------------------------
     def path_batch(self, r, k, ell=None):

@@ -379,6 +379,7 @@ int skg_medium(skg_engine* eh, int Ncells, int Ncomp, int Nlambda, const double*
         e.gasym.upload(g ? g : zeros.data(), sizeof(double) * (size_t)Ncomp * Nlambda, e.stream);
         e.med.rho = e.rho.as<double>(); e.med.kext = e.kext.as<double>(); e.med.ksca = e.ksca.as<double>(); e.med.g = e.gasym.as<double>();
         e.med.Ncells = Ncells; e.med.Ncomp = Ncomp; e.med.Nlambda = Nlambda;
+        e.med.Ntheta = 0; e.med.S11 = e.med.S12 = e.med.S33 = e.med.S34 = e.med.thetaX = e.med.pfnorm = nullptr;    // a new medium starts unpolarised
         e.haveDustLib = false;       // the dust library tables belong to the previous medium
         e.sync();
     });
@@ -547,6 +548,8 @@ int skg_stuck_counts(skg_engine* eh, int64_t* escaped, int64_t* terminated)
 // ---- Monte Carlo -----------------------------------------------------------------------------------------
 int skg_sources(skg_engine* eh, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias)
 { return guarded([&]{ mcSetSources(E(eh), Ncomp, comps, Nlambda, L, emissionBias); }); }
+int skg_medium_polarization(skg_engine* eh, int Ntheta, const double* S11, const double* S12, const double* S33, const double* S34)
+{ return guarded([&]{ mcSetPolarization(E(eh), Ntheta, S11, S12, S33, S34); }); }
 int skg_instruments(skg_engine* eh, int n, const skg_instrument* instr)
 { return guarded([&]{ mcSetInstruments(E(eh), n, instr); }); }
 int skg_run_stellar(skg_engine* eh, const skg_mc_params* p, skg_mc_stats* stats)

@@ -52,6 +52,8 @@ struct InstrDev
     double* frame; double* sed;     // device accumulators (frame: Nxp*Nyp*Nlambda, sed: Nlambda)
     // FullInstrument: Nchan = 5 + Nscatt channels, channel-major: chanFrame[(c*Nlambda + ell)*Nxp*Nyp + l], chanSed[c*Nlambda + ell]
     int Nchan, Nscatt; double* chanFrame; double* chanSed;
+    int pol;                        // FullInstrument of a simulation with polarisation: channels Nchan-3 .. Nchan-1 are Stokes Q, U, V
+    double kyx, kyy, kyz;           // DistantInstrument::bfky (DistantInstrument.cpp:47-49): the frame's y axis in model coordinates
 };
 
 struct Engine
@@ -66,6 +68,7 @@ struct Engine
     std::vector<DevBuf*> gridBufs;
     Medium med{};
     DevBuf rho, kext, ksca, gasym;
+    DevBuf mueller[4], thetaX, pfnorm;     // polarisation tables (skg_medium_polarization)
     DevBuf counters;                    // Counters
     DevBuf scratchR, scratchK, scratchEll, scratchDist, scratchCounts, scratchOffsets, scratchCub, scratchOut[5], scratchTau, scratchM, scratchWork;
 
@@ -81,8 +84,9 @@ struct Engine
     DevBuf dustLv, dustCdf, dustLtot;       // per-wavelength cell luminosities of a dust phase, their CDFs and totals
     DevBuf labsT;                           // scratch for the (m,ell) row-major copy handed to the host
     int instrNlambda = 0;                   // number of wavelengths the detector arrays were allocated for
+    bool instrPol = false;                  // whether they were allocated for a polarised medium (FullInstrument Q, U, V)
     DevBuf instrGroupedDev, groupsDev; int Ngroups = 0, maxGroupCount = 0;    // instruments ordered by line of sight + the groups
-    DevBuf mcPool, mcLists, mcCounts, mcEllList; int* mcHostCounts = nullptr;   // packet pool of the wavefront shooter
+    DevBuf mcPool, mcPolPool, mcLists, mcCounts, mcEllList; int* mcHostCounts = nullptr;   // packet pool of the wavefront shooter
     void* nccl = nullptr; int rank = 0, nranks = 1;
     // what each accumulator holds with respect to the other processes (skg_allreduce): nothing since the last reset,
     // rank-local additions only, the sum over all ranks, or the sum over all ranks plus later rank-local additions
@@ -118,6 +122,7 @@ void exclusiveScan(Engine& e, int64_t n, const int* d_counts, int64_t* d_offsets
 // Monte Carlo (mc_kernels.cu)
 void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias);
 void mcSetInstruments(Engine& e, int n, const skg_instrument* instr);
+void mcSetPolarization(Engine& e, int Ntheta, const double* S11, const double* S12, const double* S33, const double* S34);
 void mcRunStellar(Engine& e, const skg_mc_params& p, skg_mc_stats* stats);
 void mcResetResults(Engine& e);
 double mcLabsTotal(Engine& e, int which);     // sum over the whole (stellar: 0, dust: 1) absorption table, on the device

@@ -53,6 +53,15 @@ __device__ __forceinline__ void storePacket(Packet* p, const Packet& r)
         asm volatile("st.global.v4.f64 [%0], {%1, %2, %3, %4};" :: "l"(reinterpret_cast<double*>(p) + 4 * i), "d"(w[4 * i]), "d"(w[4 * i + 1]), "d"(w[4 * i + 2]), "d"(w[4 * i + 3]) : "memory");
 }
 
+// Stokes state of a packet in a simulation with polarisation (StokesVector.hpp:88-90: Q, U, V relative to I, the normal
+// to the last scattering plane, and whether a scattering plane exists yet); one 64-byte record per pool slot, in a pool
+// of its own that exists only when the medium is polarised (skg_medium_polarization)
+struct __align__(32) PolState
+{
+    double Q, U, V, nx, ny, nz;
+    int polarized, pad; double pad2;
+};
+
 // instruments that look along the same direction share one peel-off traversal
 struct ObsGroup { double kx, ky, kz; int first, count; };
 
@@ -74,6 +83,7 @@ struct McDev
     unsigned long long NppInt;
     PacketPool pool;        // packets of this iteration, compact: [0, nAlive)
     PacketPool poolNext;    // survivors of the absorb stage are written here, compact again
+    PolState* pol; PolState* polNext;       // the packets' Stokes states, same slots (null: no polarisation)
     // dust emission phases (PanMonteCarloSimulation.cpp:187-342)
     int phase;              // SKG_PHASE_*
     unsigned rngKind;       // Philox stream kind, so that the phases of one simulation never share deviates
@@ -229,6 +239,107 @@ __device__ __forceinline__ int warpAppendPosition(bool take, int* count)
     if (lane == __ffs(mask) - 1) base = atomicAdd(count, __popc(mask));
     base = __shfl_sync(active, base, __ffs(mask) - 1);
     return take ? base + __popc(mask & ((1u << lane) - 1)) : -1;
+}
+
+// ---- polarisation: StokesVector (StokesVector.cpp) and the Mueller-matrix parts of DustMix (DustMix.cpp:540-731) ------------
+__device__ __forceinline__ void stokesUnpolarized(PolState& s) { s.Q = s.U = s.V = 0; s.nx = s.ny = s.nz = 0; s.polarized = 0; s.pad = 0; s.pad2 = 0; }
+__device__ __forceinline__ double stokesLinearDegree(const PolState& s) { return sqrt(s.Q * s.Q + s.U * s.U); }                      // StokesVector.cpp:38-41
+__device__ __forceinline__ double stokesAngle(const PolState& s) { return (s.U == 0 && s.Q == 0) ? 0.0 : 0.5 * atan2(s.U, s.Q); }     // :45-51
+
+// StokesVector::rotateStokes, StokesVector.cpp:55-92
+__device__ __forceinline__ void stokesRotate(PolState& s, double phi, double kx, double ky, double kz)
+{
+    if (!s.polarized)
+    {
+        // first scattering: generate the normal to the scattering plane (the Bianchi formula with phi = 0, theta = 90 deg)
+        if (fabs(kz) > 0.99999) { s.nx = 1; s.ny = 0; s.nz = 0; }
+        else { const double nz = sqrt((1.0 - kz) * (1.0 + kz)); s.nx = -kx * kz / nz; s.ny = -ky * kz / nz; s.nz = nz; }
+        s.polarized = 1;
+    }
+    else
+    {
+        const double c2 = cos(2.0 * phi), s2 = sin(2.0 * phi);
+        const double Q = c2 * s.Q + s2 * s.U, U = -s2 * s.Q + c2 * s.U;
+        s.Q = Q; s.U = U;
+    }
+    // Rodrigues' rotation of the stored scattering plane about k, then renormalised
+    const double c = cos(phi), sn = sin(phi);
+    const double cx = ky * s.nz - kz * s.ny, cy = kz * s.nx - kx * s.nz, cz = kx * s.ny - ky * s.nx;       // Vec::cross(k, normal)
+    double nx = s.nx * c + cx * sn, ny = s.ny * c + cy * sn, nz = s.nz * c + cz * sn;
+    const double norm = sqrt(nx * nx + ny * ny + nz * nz);                                                 // Direction(Vec) stores as is; /= norm()
+    s.nx = nx / norm; s.ny = ny / norm; s.nz = nz / norm;
+}
+
+// StokesVector::applyMueller (:96-105) followed by setPolarized (:13-27)
+__device__ __forceinline__ void stokesMueller(PolState& s, double S11, double S12, double S33, double S34)
+{
+    const double I = S11 * 1. + S12 * s.Q, Q = S12 * 1. + S11 * s.Q, U = S33 * s.U + S34 * s.V, V = -S34 * s.U + S33 * s.V;
+    if (I != 0.0) { s.Q = Q / I; s.U = U / I; s.V = V / I; s.polarized = 1; }
+    else stokesUnpolarized(s);
+}
+
+// indexForTheta, DustMix.cpp:543-551
+__device__ __forceinline__ int indexForTheta(double theta, int Ntheta)
+{
+    const double dt = M_PI / (Ntheta - 1);
+    int t = static_cast<int>(theta / dt + 0.5);
+    return t < 0 ? 0 : (t >= Ntheta ? Ntheta - 1 : t);
+}
+
+// angleBetweenScatteringPlanes(np, kc, kn), DustMix.cpp:557-567
+__device__ __forceinline__ double anglePlanes(double npx, double npy, double npz, double kcx, double kcy, double kcz, double knx, double kny, double knz)
+{
+    double ncx = kcy * knz - kcz * kny, ncy = kcz * knx - kcx * knz, ncz = kcx * kny - kcy * knx;          // cross(kc, kn)
+    const double norm = sqrt(ncx * ncx + ncy * ncy + ncz * ncz);
+    ncx /= norm; ncy /= norm; ncz /= norm;
+    const double cosphi = npx * ncx + npy * ncy + npz * ncz;
+    const double ax = npy * ncz - npz * ncy, ay = npz * ncx - npx * ncz, az = npx * ncy - npy * ncx;       // cross(np, nc)
+    const double sinphi = ax * kcx + ay * kcy + az * kcz;
+    const double phi = atan2(sinphi, cosphi);
+    return isfinite(phi) ? phi : 0.0;
+}
+
+// angleBetweenScatteringAndInstrumentReference(n, knew, ky), DustMix.cpp:573-579
+__device__ __forceinline__ double angleInstrument(double nx, double ny, double nz, double kx, double ky, double kz, double yx, double yy, double yz)
+{
+    const double cosalpha = nx * yx + ny * yy + nz * yz;
+    const double ax = ny * yz - nz * yy, ay = nz * yx - nx * yz, az = nx * yy - ny * yx;                   // cross(n, ky)
+    return atan2(ax * kx + ay * ky + az * kz, cosalpha);
+}
+
+// Random::cdf(xv, Xv) (Random.cpp:131-136) for the tabulated theta distribution of (component, wavelength): DustMix::sampleTheta
+__device__ __forceinline__ double sampleTheta(const Medium& med, int h, int ell, double X)
+{
+    const int Nt = med.Ntheta;
+    const double* Xv = med.thetaX + ((size_t)h * med.Nlambda + ell) * Nt;
+    const int i = locateClip(Xv, X, Nt);
+    const double dt = M_PI / (Nt - 1);
+    const double x1 = Xv[i], x2 = Xv[i + 1];
+    return i * dt + ((X - x1) / (x2 - x1)) * ((i + 1) * dt - i * dt);              // NR::interpolate_linlin
+}
+
+// DustMix::samplePhi (DustMix.cpp:723-731): the azimuth distribution 1 + 2 PF' cos 2(phi - polAngle) as the cumulative
+// table phiX[f] = phi/2pi + PF cos(2 polAngle) sin(2 phi) + PF sin(2 polAngle) (1 - cos 2 phi) on Nphi = 361 points,
+// evaluated where the bisection of NR::locate_clip asks for it instead of being stored
+__device__ __forceinline__ double samplePhi(const Medium& med, int h, int ell, double theta, double polDegree, double polAngle, double X)
+{
+    const int Nphi = 361;
+    const int t = indexForTheta(theta, med.Ntheta);
+    const size_t o = ((size_t)h * med.Nlambda + ell) * med.Ntheta + t;
+    const double PF = polDegree * med.S12[o] / med.S11[o] / (4 * M_PI);
+    const double A = cos(2 * polAngle) * PF, B = sin(2 * polAngle) * PF;
+    const double df = 2 * M_PI / (Nphi - 1);
+    auto phiX = [&](int f) { const double phi = f * df; return phi / (2 * M_PI) + A * sin(2 * phi) + B * (1 - cos(2 * phi)); };
+    int i;
+    if (X < phiX(0)) i = 0;                                                         // NR::locate_clip, NR.hpp:146-151
+    else
+    {
+        int jl = -1, ju = Nphi - 1;                                                 // locate_basic over the first n-1 entries
+        while (ju - jl > 1) { const int jm = (ju + jl) >> 1; if (X < phiX(jm)) ju = jm; else jl = jm; }
+        i = jl;
+    }
+    const double x1 = phiX(i), x2 = phiX(i + 1);
+    return i * df + ((X - x1) / (x2 - x1)) * ((i + 1) * df - i * df);
 }
 
 // ---- samplers ------------------------------------------------------------------------------------------

@@ -129,6 +129,7 @@ __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev
         Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
         pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.pad = 0;
         storePacket(q + slot, pk);
+        if (P.pol) { PolState ps; stokesUnpolarized(ps); P.pol[slot] = ps; }       // PhotonPackage::launch: setUnpolarized()
     }
     flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
 }
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(128) launchDustStage(const __grid_constant__ G
         Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
         pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.pad = 0;
         storePacket(q + slot, pk);
+        if (P.pol) { PolState ps; stokesUnpolarized(ps); P.pol[slot] = ps; }       // PhotonPackage::launch: setUnpolarized()
     }
     flushStats(ctr, 0, 0, 0, nPackets, 0, 0);
 }
@@ -244,7 +246,7 @@ __device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, doub
 // stellar / dust emission, direct / scattered -- plus the transparent channel (unextincted direct stellar light) and
 // the channel of its scattering level.  Kept out of line: it runs once per peel-off ray, outside the crossing loop.
 static __device__ __noinline__ int detectFull(const InstrDev& I, int Nlambda, double x, double y, double z, int ell,
-                                              double L, double Lextf, int nscatt, bool stellar)
+                                              double L, double Lextf, int nscatt, bool stellar, double sQ = 0, double sU = 0, double sV = 0)
 {
     const int l = pixelOnDetector(I, x, y, z);
     const size_t Nf = (size_t)I.Nxp * I.Nyp;
@@ -260,11 +262,14 @@ static __device__ __noinline__ int detectFull(const InstrDev& I, int Nlambda, do
         else { add(SKG_CHAN_STELLAR_SCATTERED, Lextf); if (nscatt <= I.Nscatt) add(SKG_CHAN_SCATTERING_LEVEL1 + nscatt - 1, Lextf); }
     }
     else add(nscatt == 0 ? SKG_CHAN_DUST_DIRECT : SKG_CHAN_DUST_SCATTERED, Lextf);
+    // Stokes Q, U, V of the total flux (FullInstrument.cpp:136-141,165-170); packets without a scattering carry none
+    if (I.pol && (sQ != 0 || sU != 0 || sV != 0))
+    { const int c0 = SKG_CHAN_SCATTERING_LEVEL1 + I.Nscatt; add(c0, Lextf * sQ); add(c0 + 1, Lextf * sU); add(c0 + 2, Lextf * sV); }
     return n;
 }
 
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
-template<int KIND, bool SINGLE> struct PeelJob
+template<int KIND, bool SINGLE, bool POL> struct PeelJob
 {
     static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = true; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_PEEL_BATCHES;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
@@ -309,7 +314,33 @@ template<int KIND, bool SINGLE> struct PeelJob
             const double kx = pk.kx, ky = pk.ky, kz = pk.kz;
             const double cosalpha = kx * g.kx + ky * g.ky + kz * g.kz;          // Direction::dot
             double w = 0;
-            if (SINGLE)
+            if constexpr (POL)
+            {
+                // DustMix::phaseFunctionValue with polarisation, DustMix.cpp:650-662, summed over the components weighted by
+                // kappasca*rho (MonteCarloSimulation.cpp:325-336); the Stokes vector for each instrument follows in finish()
+                const PolState ps = P.pol[slot];
+                const double phi = anglePlanes(ps.nx, ps.ny, ps.nz, kx, ky, kz, g.kx, g.ky, g.kz);
+                const double theta = acos(cosalpha);
+                const int t = indexForTheta(theta, P.med.Ntheta);
+                const double polDegree = stokesLinearDegree(ps), polAngle = stokesAngle(ps);
+                double wv[8]; wv[0] = 1.0;
+                if (!SINGLE)
+                {
+                    int mcell = whichCellMC<KIND>(G, cart, rx, ry, rz);
+                    if (mcell == -1) return 0;
+                    double sum = 0;
+                    for (int c = 0; c < Ncomp && c < 8; c++)
+                    { wv[c] = __ldg(P.med.ksca + (size_t)c * Nlambda + ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c); sum += wv[c]; }
+                    if (sum <= 0) return 0;
+                    for (int c = 0; c < Ncomp && c < 8; c++) wv[c] /= sum;
+                }
+                for (int c = 0; c < Ncomp && c < 8; c++)
+                {
+                    const size_t o = ((size_t)c * Nlambda + ell) * P.med.Ntheta + t;
+                    w += wv[c] * (P.med.pfnorm[(size_t)c * Nlambda + ell] * (P.med.S11[o] + polDegree * P.med.S12[o] * cos(2. * (phi - polAngle))));
+                }
+            }
+            else if (SINGLE)
             {
                 // one component: weight 1 (MonteCarloSimulation.cpp:325-326); DustMix::phaseFunctionValue (HG), DustMix.cpp:665-668
                 const double gg = __ldg(P.med.g + ell);
@@ -343,6 +374,42 @@ template<int KIND, bool SINGLE> struct PeelJob
         if (!P.med.rho) return 2;                                   // Instrument::opticalDepth: 0 without dust
         nPaths++;
         return 1;
+    }
+    // The Stokes vector of a scattering peel-off packet as instrument I records it: per component
+    // DustMix::scatteringPeelOffPolarization (DustMix.cpp:619-644) weighted by w_h = wv[h] * phaseFunctionValue, summed and
+    // normalised by I = sum w_h (MonteCarloSimulation.cpp:337-352, PhotonPackage::setPolarized).  Out of line: once per detection.
+    __device__ __noinline__ void peelStokes(const InstrDev& I, const ObsGroup& g, const Packet& pk, const PolState& pp, double& sQ, double& sU, double& sV) const
+    {
+        const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda, Nt = P.med.Ntheta;
+        const double kx = pk.kx, ky = pk.ky, kz = pk.kz;
+        const double cosalpha = kx * g.kx + ky * g.ky + kz * g.kz;
+        const double theta = acos(cosalpha); const int t = indexForTheta(theta, Nt);
+        const double phi0 = anglePlanes(pp.nx, pp.ny, pp.nz, kx, ky, kz, g.kx, g.ky, g.kz);
+        const double polDegree = stokesLinearDegree(pp), polAngle = stokesAngle(pp);
+        double wv[8]; wv[0] = 1.0;
+        if (Ncomp > 1)
+        {
+            const int mcell = whichCellMC<KIND>(G, cart, pk.x, pk.y, pk.z);
+            double sum = 0;
+            for (int c = 0; c < Ncomp && c < 8; c++)
+            { wv[c] = mcell >= 0 ? __ldg(P.med.ksca + (size_t)c * Nlambda + pk.ell) * __ldg(P.med.rho + (size_t)mcell * Ncomp + c) : 0.0; sum += wv[c]; }
+            for (int c = 0; c < Ncomp && c < 8; c++) wv[c] = sum > 0 ? wv[c] / sum : 0.0;
+        }
+        double Isum = 0, Q = 0, U = 0, V = 0;
+        for (int c = 0; c < Ncomp && c < 8; c++)
+        {
+            const size_t o = ((size_t)c * Nlambda + pk.ell) * Nt + t;
+            const double w = wv[c] * (P.med.pfnorm[(size_t)c * Nlambda + pk.ell] * (P.med.S11[o] + polDegree * P.med.S12[o] * cos(2. * (phi0 - polAngle))));
+            PolState sv = pp;
+            stokesRotate(sv, 0.0, kx, ky, kz);                                        // generates the normal at a first scattering
+            const double phi = anglePlanes(sv.nx, sv.ny, sv.nz, kx, ky, kz, g.kx, g.ky, g.kz);
+            stokesRotate(sv, phi, kx, ky, kz);                                        // into the peel-off scattering plane
+            stokesMueller(sv, P.med.S11[o], P.med.S12[o], P.med.S33[o], P.med.S34[o]);
+            const double alpha = angleInstrument(sv.nx, sv.ny, sv.nz, g.kx, g.ky, g.kz, I.kyx, I.kyy, I.kyz);
+            stokesRotate(sv, alpha, kx, ky, kz);                                      // into the instrument's frame
+            Isum += w; Q += w * sv.Q; U += w * sv.U; V += w * sv.V;
+        }
+        if (Isum != 0.0) { sQ = Q / Isum; sU = U / Isum; sV = V / Isum; }
     }
     __device__ __forceinline__ int cellHint() const { return hint; }
     // the first traversal from a position establishes where it lies: remembered in the packet record for the next ones
@@ -378,7 +445,9 @@ template<int KIND, bool SINGLE> struct PeelJob
             if (I.kind == SKG_INSTR_FULL)
             {
                 const int ns = q->fresh ? 0 : q->nscatt + 1;
-                nDet += detectFull(I, P.med.Nlambda, px, py, pz, ell, Lw, Lextf, ns, P.phase == SKG_PHASE_STELLAR); continue;
+                double sQ = 0, sU = 0, sV = 0;
+                if constexpr (POL) { if (I.pol && !q->fresh) peelStokes(I, g, *q, P.pol[item / P.Ngroups], sQ, sU, sV); }
+                nDet += detectFull(I, P.med.Nlambda, px, py, pz, ell, Lw, Lextf, ns, P.phase == SKG_PHASE_STELLAR, sQ, sU, sV); continue;
             }
             // SEDInstrument::detect SEDInstrument.cpp:32-42, FrameInstrument::detect FrameInstrument.cpp:32-47, SimpleInstrument.cpp:33-49
             // (the SED bins are served by collective(): one address per wavelength, summed over the converged warp)
@@ -408,21 +477,21 @@ template<int KIND, bool SINGLE> struct PeelJob
     __device__ __forceinline__ void periodic() {}
 };
 
-template<int KIND, bool SINGLE>
+template<int KIND, bool SINGLE, bool POL>
 __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PEEL_MINBLOCKS : SKG_OTHER_MINBLOCKS) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                  int nAlive, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
-    PeelJob<KIND, SINGLE> job(G, cart, P);
+    PeelJob<KIND, SINGLE, POL> job(G, cart, P);
     runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, P.peelRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
     flushStageSegments(&ctr->peelSegments, job.nSeg);
 }
 
 // scatter (packets that come from an interaction) + escape/absorption + termination + interaction sampling
-template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
+template<int KIND, bool SINGLE, bool STORE, bool POL> struct AbsorbJob
 {
     static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_MC_BATCHES;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
@@ -475,14 +544,34 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
                     hmix = locateClip(Xv, rng.uniform(), Ncomp + 1);
                 }
             }
-            // DustMix::scatteringDirectionAndPolarization (HG branch), DustMix.cpp:607-614
-            double g = __ldg(P.med.g + (size_t)hmix * Nlambda + ell);
-            if (fabs(g) < 1e-6) randomDirection(rng, dx, dy, dz);
+            if constexpr (POL)
+            {
+                // DustMix::scatteringDirectionAndPolarization with polarisation, DustMix.cpp:586-605
+                PolState ps = P.pol[slot];
+                const double theta = sampleTheta(P.med, hmix, ell, rng.uniform());
+                const double phi = samplePhi(P.med, hmix, ell, theta, stokesLinearDegree(ps), stokesAngle(ps), rng.uniform());
+                stokesRotate(ps, phi, dx, dy, dz);                                    // the Stokes vector and the scattering plane
+                const size_t o = ((size_t)hmix * Nlambda + ell) * P.med.Ntheta + indexForTheta(theta, P.med.Ntheta);
+                stokesMueller(ps, P.med.S11[o], P.med.S12[o], P.med.S33[o], P.med.S34[o]);
+                // the propagation direction turns by theta in the scattering plane: k cos(theta) + (normal x k) sin(theta)
+                const double ct = cos(theta), st = sin(theta);
+                const double cx = ps.ny * dz - ps.nz * dy, cy = ps.nz * dx - ps.nx * dz, cz = ps.nx * dy - ps.ny * dx;
+                double nx = dx * ct + cx * st, ny = dy * ct + cy * st, nz = dz * ct + cz * st;
+                const double norm = sqrt(nx * nx + ny * ny + nz * nz);
+                dx = nx / norm; dy = ny / norm; dz = nz / norm;
+                P.pol[slot] = ps;
+            }
             else
             {
-                double f = ((1.0 - g) * (1.0 + g)) / (1.0 - g + 2.0 * g * rng.uniform());
-                double costheta = (1.0 + g * g - f * f) / (2.0 * g);
-                scatterDirection(rng, costheta, dx, dy, dz);
+                // DustMix::scatteringDirectionAndPolarization (HG branch), DustMix.cpp:607-614
+                double g = __ldg(P.med.g + (size_t)hmix * Nlambda + ell);
+                if (fabs(g) < 1e-6) randomDirection(rng, dx, dy, dz);
+                else
+                {
+                    double f = ((1.0 - g) * (1.0 + g)) / (1.0 - g + 2.0 * g * rng.uniform());
+                    double costheta = (1.0 + g * g - f * f) / (2.0 * g);
+                    scatterDirection(rng, costheta, dx, dy, dz);
+                }
             }
             nScatt++;
             // the scattered packet goes back to its record (new direction, one more scattering, stream position): the walk
@@ -600,19 +689,20 @@ template<int KIND, bool SINGLE, bool STORE> struct AbsorbJob
             Packet pk = loadPacket(P.pool + slot);
             pk.L = Lout; pk.target = target; pk.rngCtr = rngOut; pk.fresh = 0; pk.pad = 0;
             storePacket(P.poolNext + pos, pk);
+            if constexpr (POL) P.polNext[pos] = P.pol[slot];
         }
     }
     __device__ __forceinline__ void periodic() {}
 };
 
-template<int KIND, bool SINGLE, bool STORE>
+template<int KIND, bool SINGLE, bool STORE, bool POL>
 __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_ABSORB_MINBLOCKS : SKG_OTHER_MINBLOCKS) absorbStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                    int nAlive, int* __restrict__ counts, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
-    AbsorbJob<KIND, SINGLE, STORE> job(G, cart, P, counts);
+    AbsorbJob<KIND, SINGLE, STORE, POL> job(G, cart, P, counts);
     runJobs<KIND>(G, cart, ctr, job, nAlive, work, P.refill);
     flushStats(ctr, job.nSeg, job.nPaths, job.nScatt, 0, job.nAbs, 0);
 }
@@ -792,6 +882,33 @@ void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, co
     e.sync();
 }
 
+// DustMix::addpolarization + the derived tables of DustMix::setupSelfAfter (DustMix.cpp:96-123)
+void mcSetPolarization(Engine& e, int Ntheta, const double* S11, const double* S12, const double* S33, const double* S34)
+{
+    if (!e.med.rho) throw Error("skg_medium_polarization needs skg_medium first");
+    if (Ntheta < 2 || !S11 || !S12 || !S33 || !S34) throw Error("skg_medium_polarization: bad arguments");
+    const int C = e.med.Ncomp, Nl = e.med.Nlambda; const size_t n = (size_t)C * Nl * Ntheta;
+    const double* src[4] = {S11, S12, S33, S34};
+    for (int q = 0; q < 4; q++) e.mueller[q].upload(src[q], sizeof(double) * n, e.stream);
+    std::vector<double> thetaX(n, 0.0), pfnorm((size_t)C * Nl, 0.0);
+    const double dt = M_PI / (Ntheta - 1);
+    for (int h = 0; h < C; h++) for (int ell = 0; ell < Nl; ell++)
+    {
+        const double* s11 = S11 + ((size_t)h * Nl + ell) * Ntheta; double* X = thetaX.data() + ((size_t)h * Nl + ell) * Ntheta;
+        // NR::cdf(_thetaXvv[ell], _Ntheta-1, t -> S11(ell,t+1) sin(theta_{t+1}) dt), NR.hpp:388-394
+        X[0] = 0; for (int t = 0; t < Ntheta - 1; t++) X[t + 1] = X[t] + s11[t + 1] * std::sin((t + 1) * dt) * dt;
+        const double norm = X[Ntheta - 1];
+        if (!(norm > 0)) throw Error("the Mueller coefficient S11 must be positive");
+        for (int t = 0; t < Ntheta; t++) X[t] /= norm;
+        double sum = 0; for (int t = 0; t < Ntheta; t++) sum += s11[t] * std::sin(t * dt) * dt;
+        pfnorm[(size_t)h * Nl + ell] = 2.0 / sum;
+    }
+    e.thetaX.upload(thetaX.data(), sizeof(double) * n, e.stream); e.pfnorm.upload(pfnorm.data(), sizeof(double) * pfnorm.size(), e.stream);
+    e.med.S11 = e.mueller[0].as<double>(); e.med.S12 = e.mueller[1].as<double>(); e.med.S33 = e.mueller[2].as<double>(); e.med.S34 = e.mueller[3].as<double>();
+    e.med.thetaX = e.thetaX.as<double>(); e.med.pfnorm = e.pfnorm.as<double>(); e.med.Ntheta = Ntheta;
+    e.sync();
+}
+
 void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
 {
     if (n < 0 || (n > 0 && !instr)) throw Error("skg_instruments: bad arguments");
@@ -817,6 +934,8 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             else if (theta >= M_PI - eps) { d.kobsx = 0; d.kobsy = 0; d.kobsz = -1; }
             else { double st = std::sin(theta); d.kobsx = st * std::cos(phi); d.kobsy = st * std::sin(phi); d.kobsz = std::cos(theta); }
         }
+        // DistantInstrument::bfky, DistantInstrument.cpp:47-49
+        d.kyx = -d.cosphi * d.costheta * d.cospa - d.sinphi * d.sinpa; d.kyy = -d.sinphi * d.costheta * d.cospa + d.cosphi * d.sinpa; d.kyz = d.sintheta * d.cospa;
         if (s.kind != SKG_INSTR_SED)
         {
             // SingleFrameInstrument::setupSelfBefore, SingleFrameInstrument.cpp:26-42
@@ -825,7 +944,7 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             d.Nxp = s.Nxp; d.Nyp = s.Nyp;
             d.xpmin = s.xpc - 0.5 * s.fovxp; d.xpsiz = s.fovxp / s.Nxp;
             d.ypmin = s.ypc - 0.5 * s.fovyp; d.ypsiz = s.fovyp / s.Nyp;
-            if (s.kind == SKG_INSTR_FULL) { d.Nscatt = s.scatteringLevels; d.Nchan = 5 + d.Nscatt; }
+            if (s.kind == SKG_INSTR_FULL) { d.Nscatt = s.scatteringLevels; d.pol = e.med.Ntheta > 0 ? 1 : 0; d.Nchan = 5 + d.Nscatt + (d.pol ? 3 : 0); }
             DevBuf* f = new DevBuf(); e.instrBufs.push_back(f);
             size_t bytes = sizeof(double) * (size_t)s.Nxp * s.Nyp * e.med.Nlambda * (s.kind == SKG_INSTR_FULL ? d.Nchan : 1);
             f->ensure(bytes); SKG_CUDA(cudaMemsetAsync(f->p, 0, bytes, e.stream));
@@ -852,6 +971,7 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             { used[j] = 1; grouped.push_back(e.instr[j]); g.count++; }
         groups.push_back(g);
     }
+    e.instrPol = e.med.Ntheta > 0;
     e.maxGroupCount = 0; for (const ObsGroup& g : groups) e.maxGroupCount = std::max(e.maxGroupCount, g.count);
     e.Ngroups = (int)groups.size(); e.instrNlambda = e.med.Nlambda; e.accInstr = Engine::ACC_ZERO;
     e.instrGroupedDev.upload(grouped.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
@@ -933,7 +1053,8 @@ template<int KIND>
 static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned long long total, int pool, size_t smem, bool cartSmem)
 {
     Packet* poolA = e.mcPool.as<Packet>(); Packet* poolB = poolA + pool;
-    const bool single = P.med.Ncomp == 1, store = P.labs != nullptr;
+    PolState* polA = P.med.Ntheta > 0 ? e.mcPolPool.as<PolState>() : nullptr; PolState* polB = polA ? polA + pool : nullptr;
+    const bool single = P.med.Ncomp == 1, store = P.labs != nullptr, pol = P.med.Ntheta > 0;
     int* counts = e.mcCounts.as<int>();      // [0] survivors, [2..4] work counters of the three traversal stages
     auto blocksFor = [&](long long n) { return (int)std::max<long long>(1, std::min<long long>((n + 127) / 128, (long long)e.smCount * 16)); };
     for (cudaEvent_t& ev : e.mcEvents) if (!ev) SKG_CUDA(cudaEventCreate(&ev));
@@ -947,7 +1068,7 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
     auto addMs = [&](int stage, cudaEvent_t a, cudaEvent_t b) { float ms = 0; SKG_CUDA(cudaEventElapsedTime(&ms, a, b)); e.stageMs[stage] += ms; };
     while (true)
     {
-        P.pool = poolA; P.poolNext = poolB;
+        P.pool = poolA; P.poolNext = poolB; P.pol = polA; P.polNext = polB;
         int nLaunch = (int)std::min<unsigned long long>((unsigned long long)(pool - nAlive), total - launched);
         SKG_CUDA(cudaEventRecord(ev[0], e.stream));
         if (nLaunch > 0)
@@ -963,17 +1084,23 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
         if (P.Ngroups > 0 && P.phase != SKG_PHASE_DUST_SELFABS)
         {
             const int nb = blocksFor((long long)nAlive * P.Ngroups);
-            if (single) peelStage<KIND, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
-            else peelStage<KIND, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+            if (pol) { if (single) peelStage<KIND, true, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+                       else peelStage<KIND, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2); }
+            else if (single) peelStage<KIND, true, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+            else peelStage<KIND, false, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
             e.launches++;
         }
         SKG_CUDA(cudaEventRecord(ev[2], e.stream));
         {
             const int nb = blocksFor(nAlive);
-            if (single && store) absorbStage<KIND, true, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
-            else if (single) absorbStage<KIND, true, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
-            else if (store) absorbStage<KIND, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
-            else absorbStage<KIND, false, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3);
+#define SKG_ABSORB(S1, S2, S3) absorbStage<KIND, S1, S2, S3><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts, counts + 3)
+            if (pol) { if (single && store) SKG_ABSORB(true, true, true); else if (single) SKG_ABSORB(true, false, true);
+                       else if (store) SKG_ABSORB(false, true, true); else SKG_ABSORB(false, false, true); }
+            else if (single && store) SKG_ABSORB(true, true, false);
+            else if (single) SKG_ABSORB(true, false, false);
+            else if (store) SKG_ABSORB(false, true, false);
+            else SKG_ABSORB(false, false, false);
+#undef SKG_ABSORB
             e.launches++;
         }
         SKG_CUDA(cudaEventRecord(ev[3], e.stream));
@@ -993,7 +1120,7 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
             SKG_CUDA(cudaEventRecord(ev[5], e.stream));
             propagatePending = true;
         }
-        std::swap(poolA, poolB);
+        std::swap(poolA, poolB); std::swap(polA, polB);
         nAlive = nSurv;
     }
     SKG_CUDA(cudaGetLastError());
@@ -1153,6 +1280,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     if (p.scattBias < 0 || p.scattBias > 1) throw Error("scattBias should be between 0 and 1");
     if (e.med.Ncomp > 8) throw Error("at most 8 dust components are supported");
     if (e.med.rho && e.med.Ncells != e.Ncells) throw Error("the medium has " + std::to_string(e.med.Ncells) + " cells but the grid has " + std::to_string(e.Ncells) + ": call skg_medium again");
+    if (!e.instr.empty() && e.instrPol != (e.med.Ntheta > 0)) throw Error("the instruments were set up before the polarisation of the medium changed: call skg_instruments again");
     if (!e.instr.empty() && e.instrNlambda != Nlambda) throw Error("the instruments were set up for " + std::to_string(e.instrNlambda) + " wavelengths but the medium has " + std::to_string(Nlambda) + ": call skg_instruments again");
     if (!(p.packages >= 0) || p.packages > 1e15) throw Error("Number of photon packages is negative or larger than implementation limit of 1e15");
     McDev P{};
@@ -1214,6 +1342,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
         pool = std::max(pool, 1);
         if ((long long)pool * std::max(1, e.Ngroups) > 2000000000LL) throw Error("packet pool times observer directions exceeds the 32-bit work index: lower poolPackets");
         e.mcPool.ensure(2 * sizeof(Packet) * (size_t)pool);       // two pools: the stages ping-pong between them
+        if (P.med.Ntheta > 0) e.mcPolPool.ensure(2 * sizeof(PolState) * (size_t)pool);
         e.mcCounts.ensure(sizeof(int) * 8);
         if (!e.mcHostCounts) SKG_CUDA(cudaMallocHost(&e.mcHostCounts, 2 * sizeof(int)));
 
@@ -1226,12 +1355,14 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
             if (!e.attrStages)
             {
                 const int cap = 96 * 1024;
-                SKG_CUDA(cudaFuncSetAttribute(peelStage<GRID_CART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-                SKG_CUDA(cudaFuncSetAttribute(peelStage<GRID_CART, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-                SKG_CUDA(cudaFuncSetAttribute(absorbStage<GRID_CART, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+#define SKG_ATTR(F) SKG_CUDA(cudaFuncSetAttribute(F, cudaFuncAttributeMaxDynamicSharedMemorySize, cap))
+                SKG_ATTR((peelStage<GRID_CART, true, false>)); SKG_ATTR((peelStage<GRID_CART, false, false>));
+                SKG_ATTR((peelStage<GRID_CART, true, true>)); SKG_ATTR((peelStage<GRID_CART, false, true>));
+                SKG_ATTR((absorbStage<GRID_CART, true, true, false>)); SKG_ATTR((absorbStage<GRID_CART, true, false, false>));
+                SKG_ATTR((absorbStage<GRID_CART, false, true, false>)); SKG_ATTR((absorbStage<GRID_CART, false, false, false>));
+                SKG_ATTR((absorbStage<GRID_CART, true, true, true>)); SKG_ATTR((absorbStage<GRID_CART, true, false, true>));
+                SKG_ATTR((absorbStage<GRID_CART, false, true, true>)); SKG_ATTR((absorbStage<GRID_CART, false, false, true>));
+#undef SKG_ATTR
                 SKG_CUDA(cudaFuncSetAttribute(propagateStage<GRID_CART, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
                 SKG_CUDA(cudaFuncSetAttribute(propagateStage<GRID_CART, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
                 e.attrStages = true;

@@ -94,6 +94,13 @@ struct Medium
     const double* rho;              // [Ncells*Ncomp]
     const double* kext; const double* ksca; const double* g;    // [Ncomp*Nlambda]
     int Ncells, Ncomp, Nlambda;
+    // polarisation (DustMix::addpolarization, DustMix.cpp:325-361): Mueller matrix coefficients [Ncomp*Nlambda*Ntheta] on
+    // theta_t = t*pi/(Ntheta-1), the cumulative distribution of theta per wavelength and the phase function normalisation
+    // (DustMix.cpp:96-123); Ntheta == 0: no polarisation (Henyey-Greenstein scattering)
+    const double* S11; const double* S12; const double* S33; const double* S34;
+    const double* thetaX;           // [Ncomp*Nlambda*Ntheta]
+    const double* pfnorm;           // [Ncomp*Nlambda]
+    int Ntheta;
 };
 
 // counters updated by the kernels (device memory, one instance per engine)

@@ -237,9 +237,25 @@ class InterstellarDustMix:
 
 
 class TableDustMix:
+    mueller = None          # (S11, S12, S33, S34), each [Nlambda, Ntheta], for mixes that support polarisation
+
     def __init__(self, kappaabs, kappasca, asymmpar):
         self.kappaabs = np.atleast_1d(np.asarray(kappaabs, dtype=np.float64)); self.kappasca = np.atleast_1d(np.asarray(kappasca, dtype=np.float64))
         self.asymmpar = np.atleast_1d(np.asarray(asymmpar, dtype=np.float64)); self.kappaext = self.kappaabs + self.kappasca
+
+
+class ElectronDustMix(TableDustMix):
+    """ElectronDustMix (ElectronDustMix.cpp:19-60): Thomson scattering by electrons -- constant cross section, no absorption,
+    and the Mueller matrix of equation (C.7) of Wolf 2003 on 181 scattering angles: S11 = (cos^2 + 1)/2, S12 = (cos^2 - 1)/2,
+    S33 = cos, S34 = 0.  kappa = sigma_Thomson / m_electron (Units.cpp)."""
+    SIGMA_THOMSON, M_ELECTRON = 6.652458734e-29, 9.10938215e-31      # Units.cpp:24,30
+
+    def __init__(self, lambdagrid, Ntheta=181):
+        n = lambdagrid.Nlambda
+        super().__init__(np.zeros(n), np.full(n, self.SIGMA_THOMSON / self.M_ELECTRON), np.zeros(n))
+        ct = np.cos(np.arange(Ntheta) * (math.pi / (Ntheta - 1)))
+        row = lambda v: np.tile(v, (n, 1))
+        self.mueller = (row(0.5 * (ct * ct + 1.)), row(0.5 * (ct * ct - 1.)), row(ct), row(np.zeros(Ntheta)))
 
 
 # ---- dust grids ---------------------------------------------------------------------------------------------------
@@ -632,6 +648,11 @@ class MonteCarloSimulation:
         self.ds.sample_on_device(e, self.seed)
         m = self.ds.medium()
         e.medium(m["rho"], m["kext"], m["ksca"], m["g"])
+        mu = [getattr(c.mix, "mueller", None) for c in self.ds.comps]
+        if any(v is not None for v in mu):
+            if not all(v is not None for v in mu):          # DustSystem.cpp:74-75
+                raise FatalError("All dust mixes must consistenly support polarization, or not support polarization")
+            e.medium_polarization(*[np.array([v[q] for v in mu]) for q in range(4)])
         e.sources([c.geometry.sampler() for c in self.ss.comps], self.ss.luminosities(), self.ss.emissionBias)
         e.instruments([i.d for i in self.isys.instruments])
         self._setup = True

@@ -325,13 +325,13 @@ def mc_gate(a, r, label, signal=0.15, min_bins=0.0, total_sigma=3.5, total_rel=0
     assert Ba >= 16 and Br >= 16, f"{label}: the gate needs at least 16 batches on both sides ({Ba}, {Br})"
     ta, tr = a.sum(1), r.sum(1)
     zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / Ba + tr.var(ddof=1) / Br)
-    assert abs(zt) < total_sigma and abs(ta.mean() / tr.mean() - 1) < total_rel, \
+    assert abs(zt) < total_sigma and (total_rel is None or abs(ta.mean() / tr.mean() - 1) < total_rel), \
         f"{label}: totals differ by {zt:.2f} sigma (gpu {ta.mean():.6g}, reference {tr.mean():.6g})"
     if a.shape[1] < 2:
         return dict(zt=zt)
     ma, mr = a.mean(0), r.mean(0); sa, sr_ = a.std(0, ddof=1) / np.sqrt(Ba), r.std(0, ddof=1) / np.sqrt(Br)
     # bins with signal: batch mean known to better than 15 % on both sides (sparser bins have skewed, far-from-Gaussian batch statistics)
-    ok = (sa > 0) & (sr_ > 0) & (sa < signal * ma) & (sr_ < signal * mr)
+    ok = (sa > 0) & (sr_ > 0) & (sa < signal * np.abs(ma)) & (sr_ < signal * np.abs(mr))       # (Stokes Q, U, V are signed)
     N = int(ok.sum())
     assert N >= max(1, min_bins * a.shape[1]), f"{label}: only {N} of {a.shape[1]} bins carry signal"
     va, vr = sa[ok] ** 2, sr_[ok] ** 2
