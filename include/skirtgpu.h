@@ -212,6 +212,7 @@ typedef struct skg_mc_params
     uint64_t streamOffset;      /* first global packet index of this engine (disjoint Philox counters per GPU) */
     int ellBegin, ellEnd;       /* wavelength range [ellBegin, ellEnd) to shoot */
     int poolPackets;            /* packets in flight on the device at a time (0: default 2^22) */
+    int continuousScattering;   /* MonteCarloSimulation::continuousScattering (MonteCarloSimulation.cpp:287,291,367-434), default 0 */
 } skg_mc_params;
 typedef struct skg_mc_stats
 {

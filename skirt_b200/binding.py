@@ -46,7 +46,7 @@ class SkgMcParams(C.Structure):
     _fields_ = [("packages", C.c_double), ("luminosityScale", C.c_double), ("minWeightReduction", C.c_double),
                 ("minScattEvents", C.c_double), ("scattBias", C.c_double), ("storeAbsorption", C.c_int),
                 ("seed", C.c_uint64), ("streamOffset", C.c_uint64), ("ellBegin", C.c_int), ("ellEnd", C.c_int),
-                ("poolPackets", C.c_int)]
+                ("poolPackets", C.c_int), ("continuousScattering", C.c_int)]
 
 
 class SkgMcStats(C.Structure):
@@ -348,8 +348,9 @@ class Engine:
         self._chk(self._lib.skg_instruments(self.h, len(instr), arr))
 
     def run_stellar(self, packages, total_packages=None, min_weight_reduction=1e4, min_scatt_events=0.0, scatt_bias=0.5,
-                    store_absorption=False, seed=4357, stream_offset=0, ell_begin=0, ell_end=None, pool_packets=0):
+                    store_absorption=False, seed=4357, stream_offset=0, ell_begin=0, ell_end=None, pool_packets=0, continuous_scattering=False):
         p = SkgMcParams()
+        p.continuousScattering = int(bool(continuous_scattering))
         p.packages = float(packages)
         p.luminosityScale = float(total_packages if total_packages is not None else packages)
         p.minWeightReduction = float(min_weight_reduction); p.minScattEvents = float(min_scatt_events)

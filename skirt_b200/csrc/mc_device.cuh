@@ -78,6 +78,7 @@ struct McDev
     double* labs;           // [Nlambda*Ncells] (wavelength-major on the device) or null
     double Lscale;          // total packets per wavelength over all engines
     double minWeightReduction, minfs, xi;
+    int contScatt;          // MonteCarloSimulation::continuousScattering: peel-off from every path segment instead of the interaction points
     uint64_t seed, streamOffset;
     const int* ellList;     // wavelength indices with nonzero luminosity, in shooting order
     unsigned long long NppInt;

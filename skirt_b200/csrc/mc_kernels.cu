@@ -296,6 +296,7 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
         const Packet pk = loadPacket(P.pool + slot);
         double L = pk.L;
         if (!(L > 0)) return 0;                                 // MonteCarloSimulation.cpp:281
+        if (P.contScatt && !pk.fresh) return 0;                 // continuous scattering: no peel-off at the interaction points (:291)
         rx = pk.x; ry = pk.y; rz = pk.z;
         ell = pk.ell; hint = KIND == GRID_CART ? -1 : pk.hint;
         // which instruments of this direction record the packet?  FrameInstrument ignores packets that map outside
@@ -486,6 +487,158 @@ __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PEEL_MINBLOCKS : 
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
     PeelJob<KIND, SINGLE, POL> job(G, cart, P);
     runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, P.peelRefill);
+    flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
+    flushStageSegments(&ctr->peelSegments, job.nSeg);
+}
+
+// MonteCarloSimulation::continuouspeeloffscattering (MonteCarloSimulation.cpp:367-434; continuousScattering = true): instead of
+// one peel-off at every interaction point, EVERY segment of the packet's path sends a peel-off packet from a random
+// position inside it towards every instrument, weighted by the fraction of the luminosity scattered in that segment,
+// albedo * exp(-tau_start) * (-expm1(-dtau)), and by the phase function.  One item per (packet, observer direction): the
+// packet's own path is walked by the scheduler, and each of its segments walks the peel-off ray with a second, nested
+// walker.  Far more traversals per packet than the standard mode -- as in the reference.
+template<int KIND> struct WalkerOf;
+template<> struct WalkerOf<GRID_CART> { typedef CartFastWalkerT<false> type; };
+template<> struct WalkerOf<GRID_TREE> { typedef TreeWalkerT<SKG_TREE_HINTS_MC> type; };
+template<> struct WalkerOf<GRID_AMESH> { typedef AMeshWalker type; };
+template<> struct WalkerOf<GRID_VORO> { typedef VoroWalkerT<false> type; };
+
+template<int KIND, bool SINGLE, bool POL> struct ContPeelJob
+{
+    static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = false; static constexpr int kBatches = 1;
+    const GridSetMC& G; const CartGrid& cart; const McDev& P; Counters* ctr;
+    double rx, ry, rz, dx, dy, dz;
+    double L, tau, sacc, w0; int item, ell, hint; Philox rng;
+    unsigned nSeg = 0, nPaths = 0, nDet = 0;
+    __device__ ContPeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_, Counters* ctr_) : G(G_), cart(c_), P(P_), ctr(ctr_) {}
+
+    // the phase function towards the observer for dust component c (HG: DustMix.cpp:665-668; polarised: :650-662)
+    __device__ __forceinline__ double phase(int c, const Packet& pk, const ObsGroup& g) const
+    {
+        const int Nlambda = P.med.Nlambda;
+        const double cosalpha = pk.kx * g.kx + pk.ky * g.ky + pk.kz * g.kz;
+        if constexpr (POL)
+        {
+            const PolState ps = P.pol[item / P.Ngroups];
+            const double phi = anglePlanes(ps.nx, ps.ny, ps.nz, pk.kx, pk.ky, pk.kz, g.kx, g.ky, g.kz);
+            const size_t o = ((size_t)c * Nlambda + ell) * P.med.Ntheta + indexForTheta(acos(cosalpha), P.med.Ntheta);
+            return P.med.pfnorm[(size_t)c * Nlambda + ell] * (P.med.S11[o] + stokesLinearDegree(ps) * P.med.S12[o] * cos(2. * (phi - stokesAngle(ps))));
+        }
+        const double gg = __ldg(P.med.g + (size_t)c * Nlambda + ell);
+        const double tt = 1.0 + gg * gg - 2 * gg * cosalpha;
+        return (1.0 - gg) * (1.0 + gg) / sqrt(tt * tt * tt);
+    }
+    __device__ __forceinline__ int begin(int it)
+    {
+        item = it;
+        const Packet pk = loadPacket(P.pool + it / P.Ngroups);
+        L = pk.L;
+        if (!(L > 0) || !P.med.rho) return 0;
+        rx = pk.x; ry = pk.y; rz = pk.z; dx = pk.kx; dy = pk.ky; dz = pk.kz;
+        ell = pk.ell; hint = KIND == GRID_CART ? -1 : pk.hint;
+        tau = 0; sacc = 0;
+        w0 = SINGLE ? phase(0, pk, P.groups[it % P.Ngroups]) : 0.0;
+        // the positions inside the segments come from a Philox stream of their own: (packet, scattering order, direction)
+        rng.init(P.seed, pk.id, P.rngKind + 8u); rng.c2 = ((unsigned)pk.nscatt * (unsigned)P.Ngroups + (unsigned)(it % P.Ngroups)) << 10;
+        nPaths++;
+        return 1;
+    }
+    __device__ __forceinline__ int cellHint() const { return hint; }
+    __device__ __forceinline__ void noteStart(int) {}
+    __device__ __forceinline__ bool outside(double ds) { nSeg++; sacc += ds; return true; }
+    template<int U> __device__ __forceinline__ bool segmentU(int m, double ds) { return segment(m, ds); }
+    template<int U> __device__ __forceinline__ void idleU() {}
+    __device__ __noinline__ bool segment(int m, double ds)
+    {
+        nSeg++;
+        const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
+        const ObsGroup& g = P.groups[item % P.Ngroups];
+        const Packet* q = P.pool + item / P.Ngroups;
+        // scattering and extinction opacity of the cell, and the phase function averaged over the components (:392-405, :418-428)
+        double ksca = 0.0, kext = 0.0, w = 0.0;
+        if (SINGLE) { const double rho = __ldg(P.med.rho + m); ksca = rho * __ldg(P.med.ksca + ell); kext = rho * __ldg(P.med.kext + ell); w = w0; }
+        else
+        {
+            const Packet pk = loadPacket(q);
+            for (int h = 0; h < Ncomp; h++)
+            {
+                const double rho = __ldg(P.med.rho + (size_t)m * Ncomp + h), ks = rho * __ldg(P.med.ksca + (size_t)h * Nlambda + ell);
+                ksca += ks; kext += rho * __ldg(P.med.kext + (size_t)h * Nlambda + ell);
+                if (ks > 0) w += ks * phase(h, pk, g);
+            }
+            if (ksca > 0) w /= ksca;
+        }
+        const double dtau = kext * ds;
+        if (ksca > 0.0)
+        {
+            const double albedo = ksca / kext;
+            const double factorm = albedo * exp(-tau) * (-expm1(-dtau));
+            const double s = sacc + rng.uniform() * ds;
+            const double px = rx + s * dx, py = ry + s * dy, pz = rz + s * dz;             // bfrnew
+            // which instruments of this direction record a packet from there?  (FrameInstrument.cpp:36)
+            bool need = false;
+            for (int c = 0; c < g.count; c++)
+            { const InstrDev& I = P.instr[g.first + c]; if (I.kind != SKG_INSTR_FRAME || pixelOnDetector(I, px, py, pz) >= 0) { need = true; break; } }
+            if (need)
+            {
+                // Instrument::opticalDepth of the peel-off packet: a traversal of its own, with a second walker
+                typedef typename WalkerOf<KIND>::type W2;
+                W2 w2; Entry en; double tau2 = 0;
+                const int loc = KIND == GRID_TREE ? __ldg(G.tree.cellNode + m) : (KIND == GRID_AMESH ? __ldg(G.amesh.cellNode + m) : (KIND == GRID_VORO ? m : -1));
+                bool ok;
+                if constexpr (KIND == GRID_CART) ok = w2.start(cart, ctr, px, py, pz, g.kx, g.ky, g.kz, en, -1);
+                else if constexpr (KIND == GRID_TREE) ok = w2.start(G.tree, ctr, px, py, pz, g.kx, g.ky, g.kz, en, loc);
+                else if constexpr (KIND == GRID_AMESH) ok = w2.start(G.amesh, ctr, px, py, pz, g.kx, g.ky, g.kz, en, loc);
+                else ok = w2.start(G.voro, ctr, px, py, pz, g.kx, g.ky, g.kz, en, loc);
+                if (ok)
+                {
+                    nPaths++;
+                    while (w2.alive)
+                    {
+                        int m2; double ds2; bool seg;
+                        if constexpr (KIND == GRID_CART) seg = w2.step(cart, ctr, m2, ds2);
+                        else if constexpr (KIND == GRID_TREE) seg = w2.step(G.tree, ctr, m2, ds2);
+                        else if constexpr (KIND == GRID_AMESH) seg = w2.step(G.amesh, ctr, m2, ds2);
+                        else seg = w2.step(G.voro, ctr, m2, ds2);
+                        if (seg) { nSeg++; tau2 += KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda}(m2) * ds2; }
+                    }
+                }
+                const double Lw = L * (factorm * w);                                       // launchScatteringPeelOff(pp, bfrnew, bfkobs, factorm*I)
+                const double Lextf = Lw * exp(-tau2);
+                for (int c = 0; c < g.count; c++)
+                {
+                    const InstrDev& I = P.instr[g.first + c];
+                    if (I.kind == SKG_INSTR_FULL)
+                    {
+                        double sQ = 0, sU = 0, sV = 0;
+                        if constexpr (POL) { if (I.pol) { PeelJob<KIND, SINGLE, POL> pj(G, cart, P); pj.peelStokes(I, g, loadPacket(q), P.pol[item / P.Ngroups], sQ, sU, sV); } }
+                        nDet += detectFull(I, Nlambda, px, py, pz, ell, Lw, Lextf, q->nscatt + 1, P.phase == SKG_PHASE_STELLAR, sQ, sU, sV); continue;
+                    }
+                    if (I.kind != SKG_INSTR_FRAME) { atomicAdd(I.sed + ell, Lextf); nDet++; }
+                    if (I.kind != SKG_INSTR_SED)
+                    {
+                        const int l = pixelOnDetector(I, px, py, pz);
+                        if (l >= 0) { atomicAdd(I.frame + (size_t)l + (size_t)ell * I.Nxp * I.Nyp, Lextf); nDet++; }
+                    }
+                }
+            }
+        }
+        tau += dtau; sacc += ds;
+        return true;
+    }
+    __device__ __forceinline__ void finish() {}
+    __device__ __forceinline__ void collective(bool) {}
+    __device__ __forceinline__ void periodic() {}
+};
+
+template<int KIND, bool SINGLE, bool POL>
+__global__ void __launch_bounds__(128, 3) contPeelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem, int nAlive, int* work)
+{
+    extern __shared__ double smem[];
+    CartGrid cart = G.cart;
+    if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
+    ContPeelJob<KIND, SINGLE, POL> job(G, cart, P, ctr);
+    runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, 8);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
     flushStageSegments(&ctr->peelSegments, job.nSeg);
 }
@@ -1103,6 +1256,19 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
 #undef SKG_ABSORB
             e.launches++;
         }
+        if (P.contScatt && P.Ngroups > 0 && P.phase != SKG_PHASE_DUST_SELFABS && P.med.rho)
+        {
+            // continuous scattering: every segment of every packet's path peels off.  After the absorb stage, which has scattered the
+            // packets that come from an interaction (new direction, Stokes state and scattering count are back in their records of
+            // the current pool, whose luminosities are still those before escape and absorption): the reference walks the NEW
+            // direction, fillOpticalDepth -> continuouspeeloffscattering (MonteCarloSimulation.cpp:286-287).  Timed with the absorb stage.
+            const int nb = blocksFor((long long)nAlive * P.Ngroups);
+            if (pol) { if (single) contPeelStage<KIND, true, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 5);
+                       else contPeelStage<KIND, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 5); }
+            else if (single) contPeelStage<KIND, true, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 5);
+            else contPeelStage<KIND, false, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 5);
+            e.launches++;
+        }
         SKG_CUDA(cudaEventRecord(ev[3], e.stream));
         SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
         SKG_CUDA(cudaGetLastError());
@@ -1321,7 +1487,7 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     if (!e.instr.empty() && phase != SKG_PHASE_DUST_SELFABS) e.touched(e.accInstr);
     P.NppInt = (unsigned long long)std::ceil(p.packages);
     P.Lscale = p.luminosityScale > 0 ? p.luminosityScale : (double)P.NppInt;
-    P.minWeightReduction = p.minWeightReduction; P.minfs = p.minScattEvents; P.xi = p.scattBias;
+    P.minWeightReduction = p.minWeightReduction; P.minfs = p.minScattEvents; P.xi = p.scattBias; P.contScatt = p.continuousScattering != 0;
     P.seed = p.seed; P.streamOffset = p.streamOffset;
 
     // wavelengths with luminosity, in shooting order (the reference skips the others, MonteCarloSimulation.cpp:269,298)
@@ -1358,6 +1524,8 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
 #define SKG_ATTR(F) SKG_CUDA(cudaFuncSetAttribute(F, cudaFuncAttributeMaxDynamicSharedMemorySize, cap))
                 SKG_ATTR((peelStage<GRID_CART, true, false>)); SKG_ATTR((peelStage<GRID_CART, false, false>));
                 SKG_ATTR((peelStage<GRID_CART, true, true>)); SKG_ATTR((peelStage<GRID_CART, false, true>));
+                SKG_ATTR((contPeelStage<GRID_CART, true, false>)); SKG_ATTR((contPeelStage<GRID_CART, false, false>));
+                SKG_ATTR((contPeelStage<GRID_CART, true, true>)); SKG_ATTR((contPeelStage<GRID_CART, false, true>));
                 SKG_ATTR((absorbStage<GRID_CART, true, true, false>)); SKG_ATTR((absorbStage<GRID_CART, true, false, false>));
                 SKG_ATTR((absorbStage<GRID_CART, false, true, false>)); SKG_ATTR((absorbStage<GRID_CART, false, false, false>));
                 SKG_ATTR((absorbStage<GRID_CART, true, true, true>)); SKG_ATTR((absorbStage<GRID_CART, true, false, true>));

@@ -274,7 +274,7 @@ skg_mc_stats MonteCarloSimulation::runstellaremission()
     double npr = std::ceil(_packages / _nranks);
     p.packages = npr; p.luminosityScale = npr * _nranks;
     p.minWeightReduction = _minWeightReduction; p.minScattEvents = _minfs; p.scattBias = _xi;
-    p.storeAbsorption = _ds && _ds->storeabsorptionrates();
+    p.storeAbsorption = _ds && _ds->storeabsorptionrates(); p.continuousScattering = _continuousScattering;
     p.seed = (uint64_t)_seed; p.streamOffset = (uint64_t)(_rank * npr);
     p.ellBegin = 0; p.ellEnd = _lambdagrid->Nlambda();
     skg_mc_stats st{};

@@ -639,6 +639,7 @@ public:
     void setMinWeightReduction(double v) { if (v < 1e3) SKIRT_FATAL("The minimum weight reduction factor should be larger than 1000"); _minWeightReduction = v; }
     void setMinScattEvents(double v) { if (v < 0 || v > 1000) SKIRT_FATAL("The minimum number of forced scattering events should be between 0 and 1000"); _minfs = v; }
     void setScattBias(double v) { if (v < 0 || v > 1) SKIRT_FATAL("The scattering bias should be between 0 and 1"); _xi = v; }
+    void setContinuousScattering(bool v) { _continuousScattering = v; }
     void setSeed(int v) { _seed = v; }                                   // Random::setSeed
     void setDevice(int v) { _device = v; }
     // rank/size of the process group and the NCCL id shared by its members (replaces PeerToPeerCommunicator)
@@ -669,6 +670,7 @@ private:
     std::unique_ptr<WavelengthGrid> _lambdagrid; std::unique_ptr<StellarSystem> _ss; std::unique_ptr<DustSystem> _ds; std::unique_ptr<InstrumentSystem> _is;
     double _packages = 1e6, _minWeightReduction = 1e4, _minfs = 0, _xi = 0.5; int _seed = 4357, _device = 0;
     int _rank = 0, _nranks = 1; const void* _uid = nullptr;
+    bool _continuousScattering = false;
     bool _dustemission = false, _selfabsorption = false; int _cycles = 0; double _dustBias = 0.5, _dustBoost = 1.0; int _phaseCounter = 0;
     skg_mc_stats shootDust(int phase, double packages);
     skg_engine* _engine = nullptr; std::vector<double> _Labs;

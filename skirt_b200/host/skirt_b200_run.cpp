@@ -83,6 +83,7 @@ int main(int argc, char** argv)
             else if (key == "emissionbias") { double v; in >> v; ss->setEmissionBias(v); }
             else if (key == "storeabs") { int v; in >> v; ds->setStoreAbsorptionRates(v != 0); }
             else if (key == "lattice") { int v; in >> v; ds->setSampleLattice(v); }
+            else if (key == "continuousscattering") { int v; in >> v; sim.setContinuousScattering(v != 0); }
             else if (key == "dustemission") { int v; in >> v; sim.setDustEmission(v != 0); }
             else if (key == "selfabs") { int v; in >> v; sim.setSelfAbsorption(v != 0); }
             else if (key == "cycles") { int v; in >> v; sim.setCycles(v); }

@@ -624,10 +624,11 @@ class MonteCarloSimulation:
     """MonteCarloSimulation (MonteCarloSimulation.cpp:31-36 defaults): owns the engine(s) and drives the
     photon shooting phases.  `packages` is the number of packets per wavelength, like the ski property."""
     def __init__(self, wavelengthGrid, stellarSystem, dustSystem, instrumentSystem, packages=1e6, minWeightReduction=1e4,
-                 minScattEvents=0.0, scattBias=0.5, seed=4357, storeAbsorption=False, device=0, rank=0, nranks=1, engine=None):
+                 minScattEvents=0.0, scattBias=0.5, seed=4357, storeAbsorption=False, device=0, rank=0, nranks=1, engine=None, continuousScattering=False):
         self.lambdagrid, self.ss, self.ds, self.isys = wavelengthGrid, stellarSystem, dustSystem, instrumentSystem
         self.packages = float(packages); self.mwr = float(minWeightReduction); self.minfs = float(minScattEvents)
         self.xi = float(scattBias); self.seed = int(seed); self.storeabs = bool(storeAbsorption)
+        self.continuousScattering = bool(continuousScattering)       # MonteCarloSimulation::setContinuousScattering
         if self.packages < 0:
             raise FatalError("Number of photon packages is negative")
         if self.packages > 1e15:
@@ -670,7 +671,7 @@ class MonteCarloSimulation:
         npr, offset, total = shard_packets(self.packages, self.rank, self.nranks)
         st = self.engine.run_stellar(npr, total_packages=total, min_weight_reduction=self.mwr,
                                      min_scatt_events=self.minfs, scatt_bias=self.xi, store_absorption=self.storeabs,
-                                     seed=self.seed, stream_offset=offset)
+                                     seed=self.seed, stream_offset=offset, continuous_scattering=self.continuousScattering)
         self.stats_log.append(("stellar", st))
         # the stellar absorption table is summed over the processes once, here (the reference does it when the first dust
         # emission spectra are made: PanDustSystem::calculatedustemission(true) -> sumResults(true), PanDustSystem.cpp:383-404);
