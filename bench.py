@@ -340,26 +340,41 @@ def main_engine(args):
     # the root, which alone writes the output; PeerToPeerCommunicator.cpp:36-50): the other ranks upload their tables, shoot
     # their share and take part in the reductions
     root = rank == 0
+    # The read-back is pipelined (skg_results_snapshot + skg_fetch_snapshot_async): step i's arrays travel to page-locked host
+    # memory on a second stream while step i+1 uploads and shoots; two sets of host buffers alternate, so a consumer can
+    # still read the previous set.  Every transfer is complete before the clock stops (results_end after the last step).
+    def read_back(slot):
+        if root or world > 1:
+            return sim.results_begin(slot)          # every rank takes part in the reduction of the detector arrays
+        return None
+    for slot in (0, 1):                             # allocates both sets of page-locked buffers (set-up, untimed)
+        read_back(slot)
     if root:
-        sim.results(pinned=True)        # allocates the page-locked result buffers once (set-up, outside the timed steps)
+        sim.results_end()
     d2h = 0
     e2e_times = []
-    for _ in range(e2e_steps):
-        barrier()
-        w0 = time.perf_counter()
+    barrier()
+    w_prev = time.perf_counter()
+    for i in range(e2e_steps):
         e.set_grid(tabs); e.medium(med["rho"], med["kext"], med["ksca"], med["g"])
         e.sources(comps, Lum, sim.ss.emissionBias); e.instruments(instr)
         if pan_dust:
             sim.setup_dust_library(sim.ds.grid.volumes())
         shoot()
+        bufs = read_back(i & 1)
         if root:
-            res = sim.results(pinned=True)
-            d2h = sum(v.nbytes for v in res.values())
-        elif world > 1:
-            e.allreduce(4)              # the detector arrays: every rank takes part in the reduction the root's read triggers
-        torch.cuda.synchronize()
-        barrier()
-        e2e_times.append(time.perf_counter() - w0)
+            d2h = sum(v.nbytes for v in bufs.values())
+        if i == e2e_steps - 1:
+            t_a = time.perf_counter()
+            if root:
+                sim.results_end()
+            t_b = time.perf_counter()
+            torch.cuda.synchronize()
+            t_c = time.perf_counter()
+            barrier()
+            print(f"[bench] e2e tail: results_end {1e3 * (t_b - t_a):.1f} ms, sync {1e3 * (t_c - t_b):.1f} ms, barrier {1e3 * (time.perf_counter() - t_c):.1f} ms", file=sys.stderr)
+        w_now = time.perf_counter()
+        e2e_times.append(w_now - w_prev); w_prev = w_now
 
     # ---- reduce over ranks
     def maxr(v):
@@ -417,7 +432,8 @@ def main_engine(args):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "s_per_step": e2e_times, "of_device_value": e2e_value / value,
                     "what": "skg_grid_*+skg_medium+skg_sources+skg_instruments from host arrays (every rank), the shooting phases, "
-                            "skg_fetch_frame/sed/labs into page-locked host arrays (on the root rank, after the reduction)"},
+                            "skg_results_snapshot + skg_fetch_snapshot_async of frame/SED/absorption table into page-locked host arrays (root rank, after "
+                            "the reduction), overlapped with the next step; the series ends with every transfer complete"},
             "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": wall, "setup_s": setup_s,
             "roofline": roofline,
             "stage_ms_per_step": dict(stage_ms, kernel_ms=st["kernel_ms"]),

@@ -269,6 +269,15 @@ int skg_reset_results(skg_engine* e);
 int skg_fetch_frame(skg_engine* e, int instrument, double* frame, int add);
 int skg_fetch_sed(skg_engine* e, int instrument, double* sed, int add);
 int skg_fetch_labs(skg_engine* e, double* labs /* [Ncells*Nlambda] */, int add);
+/* Results to the host WHILE the engine goes on (the next phase, the next simulation of a series): skg_results_snapshot
+ * copies every accumulator into a shadow array on the engine's stream (device to device; the absorption tables already in
+ * the (m, ell) layout of the host interface), skg_fetch_snapshot_async moves one shadow to host memory -- page-locked, see
+ * skg_host_alloc -- on a second stream, and skg_fetch_snapshot_wait returns when every such transfer has landed.
+ * which / part as for skg_device_accumulators (0 stellar Labs, -1 dust Labs, i+1 instrument i; part 0 frame(s), 1 SED(s));
+ * *count (may be NULL) receives the number of doubles; host == NULL only queries it. */
+int skg_results_snapshot(skg_engine* e);
+int skg_fetch_snapshot_async(skg_engine* e, int which, int part, double* host, int64_t* count);
+int skg_fetch_snapshot_wait(skg_engine* e);
 /* device views of the accumulators, for collectives issued by the host (NCCL through torch.distributed);
  * note that the absorption table is wavelength-major on the device: labs[ell*Ncells + m] */
 int skg_device_accumulators(skg_engine* e, int which /*0 labs, -1 dust labs, 1.. instruments*/, int part /*0 frame,1 sed*/,

@@ -465,6 +465,19 @@ class Engine:
         self._chk(self._lib.skg_fetch_labs(self.h, _vp(a), 0))
         return a
 
+    def results_snapshot(self):
+        """skg_results_snapshot: shadow copies of every accumulator, to be fetched while the engine goes on"""
+        self._chk(self._lib.skg_results_snapshot(self.h))
+
+    def fetch_snapshot_async(self, which, part, out=None):
+        """starts the transfer of one shadow array into `out` (page-locked, see pinned_empty); returns the element count"""
+        n = C.c_int64()
+        self._chk(self._lib.skg_fetch_snapshot_async(self.h, int(which), int(part), _vp(out), C.byref(n)))
+        return n.value
+
+    def fetch_snapshot_wait(self):
+        self._chk(self._lib.skg_fetch_snapshot_wait(self.h))
+
     def device_accumulator(self, which, part=0):
         p = C.c_void_p(); n = C.c_int64()
         self._chk(self._lib.skg_device_accumulators(self.h, int(which), int(part), C.byref(p), C.byref(n)))

@@ -36,15 +36,33 @@ Engine::~Engine()
     freeGrid();
     for (DevBuf* b : sourceBufs) delete b;
     for (DevBuf* b : instrBufs) delete b;
+    for (DevBuf* b : spareBufs) delete b;
+    for (Shadow& sh : shadows) delete sh.buf;
+    if (copyStream) cudaStreamDestroy(copyStream);
+    if (snapEvent) cudaEventDestroy(snapEvent);
     if (mcHostCounts) cudaFreeHost(mcHostCounts);
     for (cudaEvent_t ev : mcEvents) if (ev) cudaEventDestroy(ev);
     if (stream) cudaStreamDestroy(stream);
 }
 
+DevBuf* Engine::takeBuf(size_t bytes)
+{
+    int best = -1;
+    for (int i = 0; i < (int)spareBufs.size(); i++)
+        if (spareBufs[i]->bytes >= bytes && (best < 0 || spareBufs[i]->bytes < spareBufs[best]->bytes)) best = i;
+    if (best < 0) return new DevBuf();
+    DevBuf* b = spareBufs[best]; spareBufs.erase(spareBufs.begin() + best);
+    return b;
+}
+void Engine::recycle(std::vector<DevBuf*>& list)
+{
+    for (DevBuf* b : list) { if (spareBufs.size() < 256) spareBufs.push_back(b); else delete b; }
+    list.clear();
+}
+
 void Engine::freeGrid()
 {
-    for (DevBuf* b : gridBufs) delete b;
-    gridBufs.clear();
+    recycle(gridBufs);
     gridKind = GRID_NONE; Ncells = 0;
 }
 
@@ -58,7 +76,7 @@ Counters Engine::readCounters()
 
 template<class T> static const T* up(Engine& e, const T* host, size_t n)
 {
-    DevBuf* b = new DevBuf(); e.gridBufs.push_back(b);
+    DevBuf* b = e.takeBuf(n * sizeof(T)); e.gridBufs.push_back(b);
     b->upload(host, n * sizeof(T), e.stream);
     return b->as<T>();
 }
@@ -646,5 +664,63 @@ int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr,
         else { *d_ptr = d.sed; *count = d.sed ? e.instrNlambda : 0; }
     });
 }
+
+// ---- results to the host while the next phase runs ------------------------------------------------------------------------
+// skg_results_snapshot copies every accumulator into a shadow array on the engine's stream (the absorption tables straight
+// into the reference's (m, ell) layout); skg_fetch_snapshot_async moves a shadow to (page-locked) host memory on a second
+// stream, so that the transfer overlaps whatever the engine does next; skg_fetch_snapshot_wait completes the transfers.
+int skg_results_snapshot(skg_engine* eh)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (!e.copyStream) SKG_CUDA(cudaStreamCreateWithFlags(&e.copyStream, cudaStreamNonBlocking));
+        if (!e.snapEvent) SKG_CUDA(cudaEventCreateWithFlags(&e.snapEvent, cudaEventDisableTiming));
+        SKG_CUDA(cudaStreamSynchronize(e.copyStream));          // transfers of the previous snapshot must not be overwritten
+        size_t used = 0;
+        auto shadow = [&](int which, int part, int64_t count) -> DevBuf*
+        {
+            if (used == e.shadows.size()) e.shadows.push_back({which, part, count, new DevBuf()});
+            Engine::Shadow& sh = e.shadows[used++]; sh.which = which; sh.part = part; sh.count = count;
+            sh.buf->ensure(sizeof(double) * (size_t)std::max<int64_t>(count, 1));
+            return sh.buf;
+        };
+        for (int which : {0, -1})
+        {
+            DevBuf& src = which ? e.labsDust : e.labs;
+            if (!src.p || !e.labsCount) continue;
+            DevBuf* dst = shadow(which, 0, e.labsCount);
+            mcTransposeLabs(e, src.as<double>(), dst->as<double>());
+        }
+        for (size_t i = 0; i < e.instr.size(); i++)
+        {
+            const InstrDev& d = e.instr[i]; const int64_t Nl = e.instrNlambda, Nf = (int64_t)d.Nxp * d.Nyp;
+            const double* srcs[2] = {d.kind == SKG_INSTR_FULL ? d.chanFrame : d.frame, d.kind == SKG_INSTR_FULL ? d.chanSed : d.sed};
+            const int64_t counts[2] = {Nf * Nl * (d.kind == SKG_INSTR_FULL ? d.Nchan : 1), Nl * (d.kind == SKG_INSTR_FULL ? d.Nchan : 1)};
+            for (int part = 0; part < 2; part++)
+                if (srcs[part]) SKG_CUDA(cudaMemcpyAsync(shadow((int)i + 1, part, counts[part])->p, srcs[part], sizeof(double) * counts[part], cudaMemcpyDeviceToDevice, e.stream));
+        }
+        for (size_t q = used; q < e.shadows.size(); q++) e.shadows[q].count = 0;
+        SKG_CUDA(cudaEventRecord(e.snapEvent, e.stream));
+    });
+}
+int skg_fetch_snapshot_async(skg_engine* eh, int which, int part, double* host, int64_t* count)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (!e.snapEvent) throw Error("skg_results_snapshot has not been called");
+        for (const Engine::Shadow& sh : e.shadows)
+            if (sh.which == which && sh.part == part && sh.count > 0)
+            {
+                if (count) *count = sh.count;
+                if (!host) return;
+                SKG_CUDA(cudaStreamWaitEvent(e.copyStream, e.snapEvent, 0));
+                SKG_CUDA(cudaMemcpyAsync(host, sh.buf->p, sizeof(double) * (size_t)sh.count, cudaMemcpyDeviceToHost, e.copyStream));
+                return;
+            }
+        throw Error("no such accumulator in the snapshot");
+    });
+}
+int skg_fetch_snapshot_wait(skg_engine* eh)
+{ return guarded([&]{ Engine& e = E(eh); if (e.copyStream) SKG_CUDA(cudaStreamSynchronize(e.copyStream)); }); }
 
 }   // extern "C"

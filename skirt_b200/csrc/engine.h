@@ -66,6 +66,9 @@ struct Engine
     CartGrid cart{}; TreeGrid tree{}; AMeshGrid amesh{}; VoroGrid voro{};
     int Ncells = 0;
     std::vector<DevBuf*> gridBufs;
+    // device arrays of replaced tables are kept for the next upload of that size: a series of simulations re-uploads its
+    // tables without cudaFree (which would wait for the result transfers of skg_fetch_snapshot_async)
+    std::vector<DevBuf*> spareBufs; DevBuf* takeBuf(size_t bytes); void recycle(std::vector<DevBuf*>& list);
     Medium med{};
     DevBuf rho, kext, ksca, gasym;
     DevBuf mueller[4], thetaX, pfnorm;     // polarisation tables (skg_medium_polarization)
@@ -96,6 +99,9 @@ struct Engine
     // opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: set once per engine
     bool attrPath = false, attrFill = false, attrStages = false;
     DevBuf scalarDev;                       // one double: device-side totals (skg_labs_dust_total)
+    // skg_results_snapshot: copies of the accumulators that a second stream hands to the host while the next phase runs
+    struct Shadow { int which, part; int64_t count; DevBuf* buf; };
+    std::vector<Shadow> shadows; cudaStream_t copyStream = nullptr; cudaEvent_t snapEvent = nullptr;
     double stageMs[4] = {0, 0, 0, 0}; uint64_t mcIterations = 0;     // launch, peel, absorb, propagate device time of the last phase
     cudaEvent_t mcEvents[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     uint64_t launches = 0;              // kernels launched by this engine (skg_launch_count)
@@ -128,6 +134,7 @@ void mcResetResults(Engine& e);
 double mcLabsTotal(Engine& e, int which);     // sum over the whole (stellar: 0, dust: 1) absorption table, on the device
 void destroyComm(Engine& e);                  // comm.cu
 void mcFetchLabs(Engine& e, double* host, int add, int which);
+void mcTransposeLabs(Engine& e, const double* src, double* dst);      // wavelength-major device table -> (m, ell) row-major, on the engine's stream
 void mcLabsBolometric(Engine& e, double* host);
 void mcDustLibrary(Engine& e, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda);
 double* mcDustCellLuminosities(Engine& e);

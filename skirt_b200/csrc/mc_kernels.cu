@@ -986,10 +986,10 @@ static SourceDev makeSourceDev(Engine& e, const skg_source& c, std::vector<DevBu
         if (c.ntab < 2 || !c.rv || !c.Xv) throw Error("Sersic geometry needs the tabulated inverse mass function");
         if (needProfile && !c.Sv) throw Error("Sersic geometry needs the tabulated profile S(s) for density sampling");
         if (c.p[1] == 0) s.p[1] = 1.0;
-        DevBuf* a = new DevBuf(); DevBuf* b = new DevBuf(); bufs.push_back(a); bufs.push_back(b);
+        DevBuf* a = e.takeBuf(sizeof(double) * c.ntab); DevBuf* b = e.takeBuf(sizeof(double) * c.ntab); bufs.push_back(a); bufs.push_back(b);
         a->upload(c.rv, sizeof(double) * c.ntab, e.stream); b->upload(c.Xv, sizeof(double) * c.ntab, e.stream);
         s.ntab = c.ntab; s.rv = a->as<double>(); s.Xv = b->as<double>();
-        if (c.Sv) { DevBuf* d = new DevBuf(); bufs.push_back(d); d->upload(c.Sv, sizeof(double) * c.ntab, e.stream); s.Sv = d->as<double>(); }
+        if (c.Sv) { DevBuf* d = e.takeBuf(sizeof(double) * c.ntab); bufs.push_back(d); d->upload(c.Sv, sizeof(double) * c.ntab, e.stream); s.Sv = d->as<double>(); }
         s.rho0 = 1.0 / (c.p[0] * c.p[0] * c.p[0]);      // SersicGeometry.cpp:44
     }
     else throw Error("unsupported source geometry (no CPU fallback): " + std::to_string(c.geometry));
@@ -1012,8 +1012,8 @@ static SourceDev makeSourceDev(Engine& e, const skg_source& c, std::vector<DevBu
 void mcSetSources(Engine& e, int Ncomp, const skg_source* comps, int Nlambda, const double* L, double emissionBias)
 {
     if (Ncomp < 1 || !comps || Nlambda < 1 || !L) throw Error("skg_sources: bad arguments");
-    for (DevBuf* b : e.sourceBufs) delete b;       // (the wavelength count is checked against the medium when a phase starts)
-    e.sourceBufs.clear(); e.sources.clear();
+    e.recycle(e.sourceBufs);                       // (the wavelength count is checked against the medium when a phase starts)
+    e.sources.clear();
     for (int h = 0; h < Ncomp; h++) e.sources.push_back(makeSourceDev(e, comps[h], e.sourceBufs, false));
     e.sourcesDev.upload(e.sources.data(), sizeof(SourceDev) * Ncomp, e.stream);
     // StellarSystem::setupSelfAfter, StellarSystem.cpp:35-52: total luminosities and per-wavelength CDFs
@@ -1066,8 +1066,7 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
 {
     if (n < 0 || (n > 0 && !instr)) throw Error("skg_instruments: bad arguments");
     if (!e.med.Nlambda) throw Error("skg_instruments needs skg_medium first (number of wavelengths)");
-    for (DevBuf* b : e.instrBufs) delete b;
-    e.instrBufs.clear(); e.instr.clear();
+    e.recycle(e.instrBufs); e.instr.clear();
     for (int i = 0; i < n; i++)
     {
         const skg_instrument& s = instr[i];
@@ -1098,15 +1097,15 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             d.xpmin = s.xpc - 0.5 * s.fovxp; d.xpsiz = s.fovxp / s.Nxp;
             d.ypmin = s.ypc - 0.5 * s.fovyp; d.ypsiz = s.fovyp / s.Nyp;
             if (s.kind == SKG_INSTR_FULL) { d.Nscatt = s.scatteringLevels; d.pol = e.med.Ntheta > 0 ? 1 : 0; d.Nchan = 5 + d.Nscatt + (d.pol ? 3 : 0); }
-            DevBuf* f = new DevBuf(); e.instrBufs.push_back(f);
             size_t bytes = sizeof(double) * (size_t)s.Nxp * s.Nyp * e.med.Nlambda * (s.kind == SKG_INSTR_FULL ? d.Nchan : 1);
+            DevBuf* f = e.takeBuf(bytes); e.instrBufs.push_back(f);
             f->ensure(bytes); SKG_CUDA(cudaMemsetAsync(f->p, 0, bytes, e.stream));
             if (s.kind == SKG_INSTR_FULL) d.chanFrame = f->as<double>(); else d.frame = f->as<double>();
         }
         if (s.kind != SKG_INSTR_FRAME)
         {
-            DevBuf* f = new DevBuf(); e.instrBufs.push_back(f);
             size_t bytes = sizeof(double) * e.med.Nlambda * (s.kind == SKG_INSTR_FULL ? d.Nchan : 1);
+            DevBuf* f = e.takeBuf(bytes); e.instrBufs.push_back(f);
             f->ensure(bytes); SKG_CUDA(cudaMemsetAsync(f->p, 0, bytes, e.stream));
             if (s.kind == SKG_INSTR_FULL) d.chanSed = f->as<double>(); else d.sed = f->as<double>();
         }
@@ -1177,6 +1176,14 @@ double mcLabsTotal(Engine& e, int which)
     return total;
 }
 
+void mcTransposeLabs(Engine& e, const double* src, double* dst)
+{
+    const int Nl = e.NlambdaSrc ? e.NlambdaSrc : e.med.Nlambda, Nc = e.Ncells;
+    dim3 grid((Nc + 31) / 32, (Nl + 31) / 32), block(32, 8);
+    transposeLabs<<<grid, block, 0, e.stream>>>(src, dst, Nc, Nl);
+    e.launches++; SKG_CUDA(cudaGetLastError());
+}
+
 void mcFetchLabs(Engine& e, double* host, int add, int which)
 {
     DevBuf& src = which ? e.labsDust : e.labs;
@@ -1200,6 +1207,11 @@ void mcLabsBolometric(Engine& e, double* host)
     sumOverWavelengths<<<(e.Ncells + 127) / 128, 128, 0, e.stream>>>(e.labs.as<double>(), e.labsDust.as<double>(), e.scratchTau.as<double>(), e.Ncells, Nl);
     e.launches++; SKG_CUDA(cudaGetLastError());
     SKG_CUDA(cudaMemcpyAsync(host, e.scratchTau.p, sizeof(double) * e.Ncells, cudaMemcpyDeviceToHost, e.stream)); e.sync();
+}
+
+__global__ void publishCounts(const int* __restrict__ counts, int* hostCounts)
+{
+    if (threadIdx.x < 2) { reinterpret_cast<volatile int*>(hostCounts)[threadIdx.x] = counts[threadIdx.x]; __threadfence_system(); }
 }
 
 template<int KIND>
@@ -1270,7 +1282,9 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
             e.launches++;
         }
         SKG_CUDA(cudaEventRecord(ev[3], e.stream));
-        SKG_CUDA(cudaMemcpyAsync(hostCounts, counts, 2 * sizeof(int), cudaMemcpyDeviceToHost, e.stream));
+        // the survivor count travels as a store into mapped page-locked memory, not as a copy: a copy would queue on the
+        // device-to-host copy engine behind a result transfer of skg_fetch_snapshot_async that is still in flight
+        publishCounts<<<1, 32, 0, e.stream>>>(counts, hostCounts); e.launches++;
         SKG_CUDA(cudaGetLastError());
         e.sync();
         if (propagatePending) { addMs(3, ev[4], ev[5]); propagatePending = false; }

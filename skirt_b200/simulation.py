@@ -784,6 +784,39 @@ class MonteCarloSimulation:
             out["Labs"] = self.engine.fetch_labs(dest("labs", (self.engine.Ncells, Nl)))
         return out
 
+    def results_begin(self, slot=0):
+        """starts moving every result array to page-locked host memory while the engine goes on (skg_results_snapshot +
+        skg_fetch_snapshot_async): the detector arrays are summed over the ranks first, like results().  `slot` selects one
+        of several sets of host buffers, so that a consumer can still read the previous set.  results_end() completes."""
+        e = self.engine
+        if self.nranks > 1:
+            ms = e.allreduce(REDUCE_INSTRUMENTS)
+            if ms:
+                self.comm_ms["instruments"] = ms
+        if self.rank != 0:
+            return None
+        e.results_snapshot()
+        bufs = self.__dict__.setdefault("_async", {}).setdefault(slot, {})
+        Nl = self.lambdagrid.Nlambda
+        wanted = [(("Labs",), 0, 0)] if self.storeabs else []
+        for i, ins in enumerate(self.isys.instruments):
+            if ins.kind != INSTR_SED:
+                wanted.append(((ins.name + "_frame",), i + 1, 0))
+            if ins.kind != INSTR_FRAME:
+                wanted.append(((ins.name + "_sed",), i + 1, 1))
+        for (name,), which, part in wanted:
+            n = e.fetch_snapshot_async(which, part, None)
+            if name not in bufs or bufs[name].size != n:
+                bufs[name] = e.pinned_empty((n,))
+            e.fetch_snapshot_async(which, part, bufs[name])
+        self._async_slot = slot
+        return bufs
+
+    def results_end(self):
+        """waits for the transfers of results_begin(); returns that set of host arrays (flat; Labs is (m, ell) row-major)"""
+        self.engine.fetch_snapshot_wait()
+        return self.__dict__.get("_async", {}).get(getattr(self, "_async_slot", 0), {})
+
     def write(self, outdir, prefix="", units=None):
         """InstrumentSystem::write() (MonteCarloSimulation.cpp:553-557): calibrates the reduced detector arrays and
         writes the FITS data cubes / SED text files of every instrument (skirt_b200/output.py); rank 0 only, like

@@ -236,3 +236,29 @@ def test_c3_configuration_against_reference_runs(engine):
         out = common.mc_gate(gpu[i], ref[i], f"C3/frame i={i}")
         assert out["bins"] > 200
     common.mc_gate(np.array(gpu_l)[:, None], np.array(ref_l)[:, None], "C3/labs total")
+
+
+def test_results_snapshot_travels_while_the_engine_goes_on(engine):
+    """skg_results_snapshot / skg_fetch_snapshot_async: the shadow copies hold the arrays of the moment of the snapshot, bit for
+    bit what the blocking fetches return, also when the engine has reset and refilled its accumulators in the meantime"""
+    tables, medium, g = common.load_golden_mc()
+    cfg = common.cfg_c1(n=24, packages=5e4, storeabs=1)
+    common.setup_engine(engine, cfg, tables, medium, g["L"])
+    engine.reset_results()
+    engine.run_stellar(5e4, store_absorption=True, seed=77)
+    want = {(1, 0): engine.fetch_frame(0).ravel(), (2, 1): engine.fetch_sed(1).ravel(), (0, 0): engine.fetch_labs().ravel()}
+    engine.results_snapshot()
+    host = {}
+    for key in want:
+        n = engine.fetch_snapshot_async(key[0], key[1], None)
+        assert n == want[key].size
+        host[key] = engine.pinned_empty((n,))
+        engine.fetch_snapshot_async(key[0], key[1], host[key])
+    engine.reset_results()                                   # the engine goes on: the accumulators change under the transfer
+    engine.run_stellar(5e4, store_absorption=True, seed=78)
+    engine.fetch_snapshot_wait()
+    for key in want:
+        assert np.array_equal(host[key], want[key]), key
+    assert not np.array_equal(engine.fetch_labs().ravel(), want[(0, 0)])
+    with pytest.raises(Exception):
+        engine.fetch_snapshot_async(9, 0, None)              # no such accumulator
