@@ -200,6 +200,18 @@ def traversal_leg(engine, torch, ext, ncomp, nrays, reps=5, warm=3):
     r = (c + (torch.rand((nrays, 3), generator=g, dtype=torch.float64, device="cuda") - 0.5) * w * 1.2).contiguous()
     k = torch.randn((nrays, 3), generator=g, dtype=torch.float64, device="cuda")
     k = (k / k.norm(dim=1, keepdim=True)).contiguous()
+    if os.environ.get("SKG_BENCH_SORT_RAYS"):
+        # experiment: the same rays handed over in Morton order of their start point (+ direction octant), the order a caller
+        # that bins its rays by cell would use -- shows what ray coherence is worth to the walkers
+        q = ((r - box[0::2]) / w).clamp(0, 1 - 1e-9).mul(64).to(torch.int64)
+        def spread(v):
+            o = torch.zeros_like(v)
+            for b in range(6):
+                o |= ((v >> b) & 1) << (3 * b)
+            return o
+        key = ((spread(q[:, 0]) | (spread(q[:, 1]) << 1) | (spread(q[:, 2]) << 2)) << 3) | ((k[:, 0] < 0).long() | ((k[:, 1] < 0).long() << 1) | ((k[:, 2] < 0).long() << 2))
+        order = torch.argsort(key)
+        r = r[order].contiguous(); k = k[order].contiguous()
     ell = torch.zeros(1, dtype=torch.int32, device="cuda")
     off = torch.zeros(nrays + 1, dtype=torch.int64, device="cuda")
     torch.cuda.synchronize()

@@ -113,8 +113,7 @@ static double labsTotal(Engine& e, int which)
     if (state == Engine::ACC_GLOBAL) SKG_NCCL(nccl.broadcast(e.scalarDev.p, e.scalarDev.p, 1, ncclDouble, 0, comm, e.stream));
     else SKG_NCCL(nccl.allReduce(e.scalarDev.p, e.scalarDev.p, 1, ncclDouble, ncclSum, comm, e.stream));
     double total = 0;
-    SKG_CUDA(cudaMemcpyAsync(&total, e.scalarDev.p, sizeof(double), cudaMemcpyDeviceToHost, e.stream));
-    e.sync();
+    e.readSmall(&total, e.scalarDev.p, sizeof(double));
     return total;
 }
 

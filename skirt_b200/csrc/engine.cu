@@ -41,6 +41,7 @@ Engine::~Engine()
     if (copyStream) cudaStreamDestroy(copyStream);
     if (snapEvent) cudaEventDestroy(snapEvent);
     if (mcHostCounts) cudaFreeHost(mcHostCounts);
+    if (smallHost) cudaFreeHost(smallHost);
     for (cudaEvent_t ev : mcEvents) if (ev) cudaEventDestroy(ev);
     if (stream) cudaStreamDestroy(stream);
 }
@@ -66,11 +67,26 @@ void Engine::freeGrid()
     gridKind = GRID_NONE; Ncells = 0;
 }
 
+__global__ void publishWords(const unsigned long long* __restrict__ src, unsigned long long* host, int n)
+{
+    if ((int)threadIdx.x < n) reinterpret_cast<volatile unsigned long long*>(host)[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+void Engine::readSmall(void* dst, const void* devSrc, size_t bytes)
+{
+    if (bytes > 512 || bytes % 8) throw Error("readSmall: at most 512 bytes in 8-byte words");
+    if (!smallHost) SKG_CUDA(cudaMallocHost(&smallHost, 512));
+    publishWords<<<1, 64, 0, stream>>>(static_cast<const unsigned long long*>(devSrc), static_cast<unsigned long long*>(smallHost), (int)(bytes / 8));
+    SKG_CUDA(cudaGetLastError());
+    sync();
+    std::memcpy(dst, smallHost, bytes);
+}
+
 Counters Engine::readCounters()
 {
+    static_assert(sizeof(Counters) % 8 == 0 && sizeof(Counters) <= 512, "Counters travel through readSmall");
     Counters c;
-    SKG_CUDA(cudaMemcpyAsync(&c, counters.p, sizeof(Counters), cudaMemcpyDeviceToHost, stream));
-    sync();
+    readSmall(&c, counters.p, sizeof(Counters));
     return c;
 }
 

@@ -68,6 +68,9 @@ struct Engine
     std::vector<DevBuf*> gridBufs;
     // device arrays of replaced tables are kept for the next upload of that size: a series of simulations re-uploads its
     // tables without cudaFree (which would wait for the result transfers of skg_fetch_snapshot_async)
+    // a few words from the device: stored by a one-warp kernel into mapped page-locked memory rather than copied, so that
+    // the read does not queue on the device-to-host copy engine behind a result transfer in flight (<= 512 bytes, 8-byte words)
+    void readSmall(void* dst, const void* devSrc, size_t bytes); void* smallHost = nullptr;
     std::vector<DevBuf*> spareBufs; DevBuf* takeBuf(size_t bytes); void recycle(std::vector<DevBuf*>& list);
     Medium med{};
     DevBuf rho, kext, ksca, gasym;

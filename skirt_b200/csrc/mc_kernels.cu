@@ -1171,8 +1171,7 @@ double mcLabsTotal(Engine& e, int which)
     sumArray<<<e.smCount * 4, 256, 0, e.stream>>>(src.as<double>(), (size_t)e.labsCount, e.scalarDev.as<double>());
     e.launches++; SKG_CUDA(cudaGetLastError());
     double total = 0;
-    SKG_CUDA(cudaMemcpyAsync(&total, e.scalarDev.p, sizeof(double), cudaMemcpyDeviceToHost, e.stream));
-    e.sync();
+    e.readSmall(&total, e.scalarDev.p, sizeof(double));
     return total;
 }
 

@@ -91,13 +91,26 @@ __device__ __forceinline__ double cellWord(int m) { return __longlong_as_double(
 // The rings are lane-interleaved in shared memory -- entry q of lane l lives at [q][l] -- so that every access of a
 // warp is bank-conflict free whatever ring positions its lanes are at: per warp ds[12][32], rho[12][32] (f64) and
 // m[12][32] (i32).
+// 1: a group of four records (160 contiguous bytes) is assembled in shared memory and leaves as ONE bulk copy of the async proxy
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP) instead of five 256-bit stores through the load/store pipe
+#ifndef SKG_FILL_BULK
+#define SKG_FILL_BULK 0
+#endif
+__device__ __forceinline__ void sts2F64(unsigned a, double v0, double v1) { asm volatile("st.shared.v2.f64 [%0], {%1, %2};" :: "r"(a), "d"(v0), "d"(v1) : "memory"); }
+__device__ __forceinline__ void bulkStore(void* gdst, unsigned ssrc, unsigned bytes)
+{ asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(ssrc), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulkCommit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulkWaitRead() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fenceProxyAsyncShared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 struct RecordJobStaged : RayJobBase
 {
     static constexpr int kBatches = 1;              // the ring holds three periods
     static constexpr bool kCartRegBorders = true, kCartTinySelect = false; static constexpr bool kTreeHints = SKG_TREE_HINTS_PATH, kCartRhoAhead = true;       // the record kernel is bound by the load/store pipe
     static constexpr unsigned RHO_OFF = SKG_RING * 32 * 8, M_OFF = 2 * SKG_RING * 32 * 8;
     static constexpr size_t bytesPerWarp() { return (size_t)SKG_RING * 32 * (8 + 8 + 4); }
-    static constexpr size_t bytesPerWarpAll() { return bytesPerWarp() + 32 * 4; }      // + the ray index of every lane
+    static constexpr size_t bytesPerWarpAll() { return bytesPerWarp() + 32 * 4 + (SKG_FILL_BULK ? 32 * 160 : 0); }      // + the ray index of every lane (+ a 160-byte group)
+    unsigned stage;             // SKG_FILL_BULK: shared-window address of this lane's 160-byte group
 
     const int64_t* offsets; const int* ell; int ellStride; Medium med;
     skg_segment* seg;
@@ -114,6 +127,7 @@ struct RecordJobStaged : RayJobBase
         const int lane = threadIdx.x & 31;
         const unsigned w = (unsigned)__cvta_generic_to_shared(warpBase);
         rb = w + 8u * lane; rbM = w + M_OFF + 4u * lane; rbItem = w + (unsigned)bytesPerWarp() + 4u * lane;
+        stage = w + (unsigned)bytesPerWarp() + 128u + 160u * lane;
         o = f = ready = 0; sacc = tacc = 0; optical = async = false; kext0 = 0; qo = qf = 0; out0 = nullptr;
     }
 
@@ -169,6 +183,16 @@ struct RecordJobStaged : RayJobBase
         const double a0 = tacc + t0, a1 = a0 + t1, a2 = a1 + t2, a3 = a2 + t3;
         sacc = s3; tacc = a3;
         double* out = out0 + 5 * (size_t)f;      // 4 records x 5 words
+#if SKG_FILL_BULK
+        bulkWaitRead();                          // the previous group has left this lane's staging bytes
+        sts2F64(stage, cellWord(m0), d0); sts2F64(stage + 16, s0, t0); sts2F64(stage + 32, a0, cellWord(m1)); sts2F64(stage + 48, d1, s1);
+        sts2F64(stage + 64, t1, a1); sts2F64(stage + 80, cellWord(m2), d2); sts2F64(stage + 96, s2, t2); sts2F64(stage + 112, a2, cellWord(m3));
+        sts2F64(stage + 128, d3, s3); sts2F64(stage + 144, t3, a3);
+        fenceProxyAsyncShared();
+        bulkStore(out, stage, 160u); bulkCommit();
+        f += 4; qf = q + 1024 == 256 * SKG_RING ? 0 : q + 1024;
+        return;
+#endif
         store4(out, cellWord(m0), d0, s0, t0);
         store4(out + 4, a0, cellWord(m1), d1, s1);
         store4(out + 8, t1, a1, cellWord(m2), d2);
@@ -188,6 +212,9 @@ struct RecordJobStaged : RayJobBase
     __device__ __forceinline__ void finish()
     {
         asyncCommit(); asyncWaitAll(); emit(o); ready = o;
+#if SKG_FILL_BULK
+        bulkWaitRead();
+#endif
         if (lengths)
         {
             // one-pass mode: report the length; the ray's slab [offsets[i], offsets[i+1]) must have held it
@@ -226,7 +253,7 @@ __global__ void __launch_bounds__(128) pathFillKernel(const __grid_constant__ Gr
     size_t skip = (KIND == GRID_CART && cartSmem) ? SKG_CART_SMEM_DOUBLES(G.cart) : 0;
     RecordJobStaged job; job.r = r; job.k = k; job.offsets = offsets; job.ell = ell; job.ellStride = ellStride; job.med = med;
     job.seg = segments; job.lengths = lengths; job.overflow = &ctr->errors;
-    job.bind(reinterpret_cast<char*>(smem + skip) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarpAll());
+    job.bind(reinterpret_cast<char*>(smem + ((skip + 1) & ~(size_t)1)) + (threadIdx.x >> 5) * RecordJobStaged::bytesPerWarpAll());      // 16-byte aligned
     runJobs<KIND>(G, cart, ctr, job, n, work, refill);
 }
 
@@ -347,7 +374,7 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
     if (d_ell && !e.med.rho) throw Error("skg_path_fill with wavelength indices needs skg_medium first");
     if (d_ell && e.med.Ncells != e.Ncells) throw Error("the medium has " + std::to_string(e.med.Ncells) + " cells but the grid has " + std::to_string(e.Ncells) + ": call skg_medium again");
     LaunchCfg c = cfgFor(e, n); GridSet G = gridSet(e);
-    c.smem += 4 * RecordJobStaged::bytesPerWarpAll();
+    c.smem += 4 * RecordJobStaged::bytesPerWarpAll() + 8;
     if (const char* pad = getenv("SKG_FILL_SMEM_PAD")) c.smem += (size_t)atoi(pad);      // experiment: limits resident CTAs
     if (!e.attrFill)
     {
