@@ -50,7 +50,8 @@ int skg_grid_cartesian(skg_engine* e, const double* xv, int Nx, const double* yv
 
 /* TreeDustGrid (TreeDustGrid.cpp:50-164): the node vector _tree flattened in id order.
  *   kind   : 0 OctTreeDustGrid, 1 BinTreeDustGrid
- *   search : 0 TopDown, 1 Neighbor, 2 Bookkeeping (TreeDustGrid.hpp:155; Bookkeeping is octree-only)
+ *   search : 0 TopDown, 1 Neighbor, 2 Bookkeeping (TreeDustGrid.hpp:155; Bookkeeping is octree-only);
+ *            3 the traversal of ParticleTreeDustGrid (ParticleTreeDustGrid.cpp:262-320: its own wall selection, top-down search)
  *   box[6*l..] = xmin,ymin,zmin,xmax,ymax,zmax of node l (TreeNode : Box)
  *   child0[l]  = id of the first child (children have consecutive ids, OctTreeNode.cpp:38-49), -1 for leaves
  *   parent[l]  = id of the father, -1 for the root;  cell[l] = _cellnumberv[l] (m for leaves, else -1)

@@ -32,6 +32,10 @@ int skh_tree_frontier_boxes(skh_tree* t, double* box6 /* [6*size] xmin,ymin,zmin
 int skh_tree_subdivide(skh_tree* t, const unsigned char* flags /* [size] */);
 /* search: 0 TopDown, 1 Neighbor (builds the sorted neighbour lists), 2 Bookkeeping (octree only) */
 int skh_tree_finish(skh_tree* t, int search, int* Nnodes, int* Ncells, int64_t* Nneighbours);
+/* ParticleTreeDustGrid::setupSelfBefore (ParticleTreeDustGrid.cpp:76-152): an octree (kind 0) or binary tree (kind 1) grown around
+ * particles[3n] -- added in order, a leaf holding a particle is subdivided until the two are apart -- plus extraLevels subdivisions
+ * of every leaf.  The tables (skh_tree_tables; no neighbour lists) go to skg_grid_tree with search = 3. */
+int skh_ptree_build(int kind, const double* extent6, const double* particles, int64_t n, int extraLevels, skh_tree** out, int* Nnodes, int* Ncells);
 int skh_tree_tables(skh_tree* t, double* box, int* child0, int* parent, int* cell, int* dir, int* level, int* nbrStart, int* nbrIds);
 
 /* ---- adaptive mesh ---------------------------------------------------------------------------------------------------

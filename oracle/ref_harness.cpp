@@ -55,6 +55,8 @@
 #include "LinMesh.hpp"
 #include "LogWavelengthGrid.hpp"
 #include "OctTreeDustGrid.hpp"
+#include "ParticleTreeDustGrid.hpp"
+#include "DustParticleInterface.hpp"
 #include "OctTreeNode.hpp"
 #include "OligoDustSystem.hpp"
 #include "OligoMonteCarloSimulation.hpp"
@@ -132,6 +134,16 @@ namespace
         }
     };
 
+    // the dust distribution of the geometry components that also hands out a list of particle positions: what
+    // ParticleTreeDustGrid asks its distribution for (DustParticleInterface; SPHDustDistribution in a real ski file)
+    class ParticleCompDustDistribution : public CompDustDistribution, public DustParticleInterface
+    {
+    public:
+        std::vector<double> xyz;
+        int numParticles() const { return (int)(xyz.size() / 3); }
+        Vec particleCenter(int i) const { return Vec(xyz[3*(size_t)i], xyz[3*(size_t)i+1], xyz[3*(size_t)i+2]); }
+    };
+
     class MemVoronoiMeshFile : public VoronoiMeshFile
     {
     public:
@@ -172,9 +184,9 @@ namespace
         std::vector<TableDustMix*> mixes;
         Geometry* lastGeom = 0;         // most recently created geometry (target for decorators)
         std::function<void(Geometry*)> lastGeomSetter;
-        MemVoronoiMeshFile* vfile = 0;
+        MemVoronoiMeshFile* vfile = 0; ParticleCompDustDistribution* pdd = 0;
         MemAdaptiveMeshFile* afile = 0;
-        int gridKind = -1;              // 0 cartesian, 1 octtree, 2 bintree, 3 voronoi, 4 adaptive mesh
+        int gridKind = -1;              // 0 cartesian, 1 octtree, 2 bintree, 3 voronoi, 4 adaptive mesh, 5 particle tree (oct), 6 particle tree (bin)
         // flattened adaptive mesh numbering
         std::vector<const AdaptiveMeshNode*> amNodes; std::unordered_map<const AdaptiveMeshNode*, int> amIndex;
         // flattened voronoi kd nodes
@@ -315,6 +327,15 @@ namespace
                     S->grid = g; S->gridKind = 3;
                 }
                 else if (kind == "amesh") { S->grid = new AdaptiveMeshDustGrid(); S->gridKind = 4; }
+                else if (kind == "particletree")
+                {
+                    // grid particletree <oct|bin> <extraLevels>; the particles come through skr_set_particles
+                    std::string tt; int extra; in >> tt >> extra;
+                    ParticleTreeDustGrid* g = new ParticleTreeDustGrid(); setBox(g, S->box);
+                    g->setTreeType(tt == "bin" ? ParticleTreeDustGrid::BinTree : ParticleTreeDustGrid::OctTree); g->setExtraLevels(extra);
+                    S->grid = g; S->gridKind = tt == "bin" ? 6 : 5;
+                    S->pdd = new ParticleCompDustDistribution(); S->cdd = S->pdd;
+                }
                 else throw std::runtime_error("unknown grid " + kind);
                 S->grid->setWriteGrid(false);
             }
@@ -457,7 +478,8 @@ int skr_set_mueller(void* h, int comp, int Ntheta, int Nlambda, const double* S1
   size_t n = (size_t)Ntheta * Nlambda; TableDustMix* m = S->mixes[comp]; m->Ntheta = Ntheta;
   m->S11.assign(S11, S11+n); m->S12.assign(S12, S12+n); m->S33.assign(S33, S33+n); m->S34.assign(S34, S34+n); return 0; }
 int skr_set_particles(void* h, const double* xyz, int n)
-{ Sim* S = (Sim*)h; if (!S->vfile) return 1; S->vfile->xyz.assign(xyz, xyz+3*(size_t)n); return 0; }
+{ Sim* S = (Sim*)h; if (S->pdd) { S->pdd->xyz.assign(xyz, xyz+3*(size_t)n); return 0; }
+  if (!S->vfile) return 1; S->vfile->xyz.assign(xyz, xyz+3*(size_t)n); return 0; }
 int skr_set_amesh(void* h, const int* nxyz, const double* val, int n)
 { Sim* S = (Sim*)h; if (!S->afile) return 1; S->afile->nxyz.assign(nxyz, nxyz+3*(size_t)n); S->afile->val.assign(val, val+n); return 0; }
 
@@ -518,26 +540,32 @@ void skr_cart_axes(void* h, double* xv, double* yv, double* zv)
   for (int i = 0; i <= g->_Nx; i++) xv[i] = g->_xv[i]; for (int i = 0; i <= g->_Ny; i++) yv[i] = g->_yv[i]; for (int i = 0; i <= g->_Nz; i++) zv[i] = g->_zv[i]; }
 
 // ---- tree -------------------------------------------------------------------------------------
+// the node vector, the cell numbers and eps of a TreeDustGrid or a ParticleTreeDustGrid
+static void treeParts(Sim* S, std::vector<TreeNode*>*& tree, std::vector<int>*& cellnumber, double& eps)
+{
+    if (S->gridKind >= 5) { ParticleTreeDustGrid* g = (ParticleTreeDustGrid*)S->grid; tree = &g->_tree; cellnumber = &g->_cellnumberv; eps = g->_eps; }
+    else { TreeDustGrid* g = (TreeDustGrid*)S->grid; tree = &g->_tree; cellnumber = &g->_cellnumberv; eps = g->_eps; }
+}
 void skr_tree_sizes(void* h, int* nnodes, int* nnbr, double* eps)
 {
-    TreeDustGrid* g = (TreeDustGrid*)((Sim*)h)->grid;
-    *nnodes = g->_Nnodes; long total = 0;
-    for (int l = 0; l < g->_Nnodes; l++) for (auto& v : g->_tree[l]->_neighbors) total += v.size();
-    *nnbr = (int)total; *eps = g->_eps;
+    std::vector<TreeNode*>* tree; std::vector<int>* cn; treeParts((Sim*)h, tree, cn, *eps);
+    *nnodes = (int)tree->size(); long total = 0;
+    for (TreeNode* n : *tree) for (auto& v : n->_neighbors) total += v.size();
+    *nnbr = (int)total;
 }
 // box[6N] = xmin,ymin,zmin,xmax,ymax,zmax; child0[N]; parent[N]; cell[N]; dir[N]; nbrStart[6N+1]; nbrIds[]
 int skr_tree_tables(void* h, double* box, int* child0, int* parent, int* cell, int* dir, int* nbrStart, int* nbrIds)
 {
-    Sim* S = (Sim*)h; TreeDustGrid* g = (TreeDustGrid*)S->grid;
-    int N = g->_Nnodes; int pos = 0;
+    Sim* S = (Sim*)h; std::vector<TreeNode*>* tree; std::vector<int>* cn; double eps; treeParts(S, tree, cn, eps);
+    int N = (int)tree->size(); int pos = 0;
     for (int l = 0; l < N; l++)
     {
-        TreeNode* n = g->_tree[l];
+        TreeNode* n = (*tree)[l];
         if (n->id() != l) { lastError = "node id mismatch"; return 1; }
         box[6*l+0] = n->xmin(); box[6*l+1] = n->ymin(); box[6*l+2] = n->zmin();
         box[6*l+3] = n->xmax(); box[6*l+4] = n->ymax(); box[6*l+5] = n->zmax();
         parent[l] = n->father() ? n->father()->id() : -1;
-        cell[l] = g->_cellnumberv[l];
+        cell[l] = (*cn)[l];
         child0[l] = n->ynchildless() ? -1 : n->child(0)->id();
         if (!n->ynchildless())
             for (size_t c = 0; c < n->children().size(); c++)

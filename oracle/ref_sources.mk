@@ -5,7 +5,7 @@ REF_CPP := Array.cpp ProcessManager.cpp \
  SequentialAssigner.cpp StaggeredAssigner.cpp RootAssigner.cpp ProcessCommunicator.cpp PeerToPeerCommunicator.cpp \
  Random.cpp Position.cpp Direction.cpp StokesVector.cpp PhotonPackage.cpp DustGridPath.cpp \
  DustGrid.cpp BoxDustGrid.cpp CartesianDustGrid.cpp Mesh.cpp MoveableMesh.cpp LinMesh.cpp SymPowMesh.cpp PowMesh.cpp \
- TreeDustGrid.cpp OctTreeDustGrid.cpp BinTreeDustGrid.cpp TreeNode.cpp OctTreeNode.cpp BinTreeNode.cpp \
+ TreeDustGrid.cpp ParticleTreeDustGrid.cpp OctTreeDustGrid.cpp BinTreeDustGrid.cpp TreeNode.cpp OctTreeNode.cpp BinTreeNode.cpp \
  BaryOctTreeNode.cpp BaryBinTreeNode.cpp TreeNodeBoxDensityCalculator.cpp TreeNodeSampleDensityCalculator.cpp \
  VoronoiDustGrid.cpp VoronoiMeshFile.cpp AdaptiveMesh.cpp AdaptiveMeshNode.cpp \
  AdaptiveMeshFile.cpp AdaptiveMeshDustGrid.cpp AdaptiveMeshDustDistribution.cpp BoxDustDistribution.cpp MeshDustComponent.cpp SpheroidalGeometryDecorator.cpp \

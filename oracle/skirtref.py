@@ -165,7 +165,7 @@ class RefSim:
             xv, yv, zv = np.zeros(n[0]+1), np.zeros(n[1]+1), np.zeros(n[2]+1)
             L.skr_cart_axes(self.h, vp(xv), vp(yv), vp(zv))
             return dict(kind="cartesian", xv=xv, yv=yv, zv=zv)
-        if k in (1, 2):
+        if k in (1, 2, 5, 6):           # 5, 6: ParticleTreeDustGrid (octree / binary tree) -- same node tables, its own traversal
             nn = C.c_int(); nb = C.c_int(); eps = C.c_double()
             L.skr_tree_sizes(self.h, C.byref(nn), C.byref(nb), C.byref(eps))
             N = nn.value
@@ -173,8 +173,8 @@ class RefSim:
             cell = np.zeros(N, np.int32); sdir = np.zeros(N, np.int32)
             nbrStart = np.zeros(6*N+1, np.int32); nbrIds = np.zeros(max(nb.value, 1), np.int32)
             self._chk(L.skr_tree_tables(self.h, vp(box), vp(child0), vp(parent), vp(cell), vp(sdir), vp(nbrStart), vp(nbrIds)))
-            search = int(self.spec_value("grid")[3])
-            return dict(kind="octtree" if k == 1 else "bintree", search=search, eps=eps.value, box=box, child0=child0,
+            search = 3 if k >= 5 else int(self.spec_value("grid")[3])
+            return dict(kind="octtree" if k in (1, 5) else "bintree", search=search, eps=eps.value, box=box, child0=child0,
                         parent=parent, cell=cell, dir=sdir, nbrStart=nbrStart, nbrIds=nbrIds[:nb.value])
         if k == 4:
             nn = C.c_int(); eps = C.c_double()

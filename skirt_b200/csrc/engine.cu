@@ -188,7 +188,7 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
         Engine& e = E(eh);
         if (N < 1 || !box || !child0 || !parent || !cell) throw Error("tree grid tables missing");
         if (kind != 0 && kind != 1) throw Error("tree kind must be 0 (octree) or 1 (binary tree)");
-        if (search < 0 || search > 2) throw Error("invalid search method");
+        if (search < 0 || search > 3) throw Error("invalid search method");
         if (search == 2 && kind != 0) throw Error("Bookkeeping method is not compatible with binary tree");   // BinTreeDustGrid.cpp:19-25
         if (search == 1 && (!nbrStart || !nbrIds)) throw Error("Neighbor search needs the neighbour lists");
         if (kind == 1 && !dir) throw Error("binary tree needs the split directions");

@@ -531,6 +531,32 @@ template<bool HINT> struct TreeWalkerT
         const double xnext = nx ? bx[0] : bx[3];
         const double ynext = ny ? bx[1] : bx[4];
         const double znext = nz ? bx[2] : bx[5];
+        if (g.search == 3)
+        {
+            // ParticleTreeDustGrid::path (ParticleTreeDustGrid.cpp:262-320): unguarded divisions, the nearest wall among the
+            // strictly positive distances, a segment only when there is one, then always a search from the root
+            const double px = (xnext - x) / kx, py = (ynext - y) / ky, pz = (znext - z) / kz;
+            ds = SKG_DBL_MAX;
+            if (px > 0 && px < ds) ds = px;
+            if (py > 0 && py < ds) ds = py;
+            if (pz > 0 && pz < ds) ds = pz;
+            const bool emit = ds < SKG_DBL_MAX;
+            if (!emit) ds = 0;
+            mseg = cellv;
+            const double eps = g.eps;
+            x += (ds + eps) * kx; y += (ds + eps) * ky; z += (ds + eps) * kz;
+            const int oldnode = node;
+            node = treeWhichNode(g, x, y, z);
+            if (node == oldnode)
+            {
+                atomicAdd(&ctr->stuckEscaped, 1ull);
+                x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
+                node = treeWhichNodeCold(g, x, y, z);
+                if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
+            }
+            if (node < 0) alive = false; else loadNode(g, true);
+            return emit;
+        }
         const double dsx = (fabs(kx) > 1e-15) ? divInvariant(xnext - x, kx, rkx) : SKG_DBL_MAX;
         const double dsy = (fabs(ky) > 1e-15) ? divInvariant(ynext - y, ky, rky) : SKG_DBL_MAX;
         const double dsz = (fabs(kz) > 1e-15) ? divInvariant(znext - z, kz, rkz) : SKG_DBL_MAX;

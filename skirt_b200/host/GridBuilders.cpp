@@ -146,7 +146,7 @@ void TreeBuilder::addNeighbors(int l)
 void TreeBuilder::finish(int search)
 {
     if (!done()) throw std::runtime_error("the tree has not been subdivided down to its last level");
-    if (search < 0 || search > 2) throw std::runtime_error("invalid search method");
+    if (search < 0 || search > 3) throw std::runtime_error("invalid search method");
     if (search == 2 && _kind != 0) throw std::runtime_error("Bookkeeping method is not compatible with binary tree");     // BinTreeDustGrid.cpp:19-25
     const int N = (int)_t.child0.size();
     _t.Nnodes = N; _t.search = search;
@@ -177,6 +177,50 @@ void TreeBuilder::finish(int search)
     for (size_t q = 0; q < 6 * (size_t)N; q++) { _t.nbrStart[q] = (int)_t.nbrIds.size(); _t.nbrIds.insert(_t.nbrIds.end(), _nbr[q].begin(), _nbr[q].end()); }
     _t.nbrStart[6 * (size_t)N] = (int)_t.nbrIds.size();
     std::vector<std::vector<int>>().swap(_nbr);
+}
+
+// TreeNode::whichnode(Vec) (TreeNode.cpp:70-80) from a given node: closed-box test, then OctTreeNode::child (OctTreeNode.cpp:184-189)
+// or BinTreeNode::child (BinTreeNode.cpp:326-335) down to a leaf
+int TreeBuilder::whichNodeFrom(int start, double x, double y, double z) const
+{
+    const double* b = &_t.box[6 * (size_t)start];
+    if (!(x >= b[0] && x <= b[3] && y >= b[1] && y <= b[4] && z >= b[2] && z <= b[5])) return -1;
+    int l = start;
+    while (_t.child0[l] >= 0)
+    {
+        const int c0 = _t.child0[l]; const double* c = &_t.box[6 * (size_t)c0];      // child 0: its max corner is the split point
+        if (_kind == 0) l = c0 + (x < c[3] ? 0 : 1) + (y < c[4] ? 0 : 2) + (z < c[5] ? 0 : 4);
+        else { const int d = _t.dir[l]; const double v = d == 0 ? x : d == 1 ? y : z; l = c0 + (v < c[3 + d] ? 0 : 1); }
+    }
+    return l;
+}
+
+// addParticleToNode (ParticleTreeDustGrid.cpp:36-72); returns the level of the leaf that received the particle, -1 if outside
+int TreeBuilder::addParticle(int p, int start, const double* xyz, std::vector<int>& particlev)
+{
+    const int node = whichNodeFrom(start, xyz[3 * (size_t)p], xyz[3 * (size_t)p + 1], xyz[3 * (size_t)p + 2]);
+    if (node < 0) return -1;
+    if (particlev[node] < 0) { particlev[node] = p; return _t.level[node]; }
+    if (_t.level[node] > 1000) throw std::runtime_error("two particles share a position: the particle tree cannot separate them");
+    createChildren(node);
+    particlev.resize(_t.child0.size(), -1);
+    addParticle(particlev[node], node, xyz, particlev);
+    return addParticle(p, node, xyz, particlev);
+}
+
+void TreeBuilder::addParticles(const double* xyz, size_t n, int extraLevels)
+{
+    if (_t.child0.size() != 1) throw std::runtime_error("particles are added to a tree that is still its root node");
+    if (!xyz && n) throw std::runtime_error("null particle list");
+    std::vector<int> particlev(1, -1);
+    for (size_t i = 0; i < n; i++) addParticle((int)i, 0, xyz, particlev);
+    for (int e = 0; e < extraLevels; e++)
+    {
+        const int N = (int)_t.child0.size();
+        for (int l = 0; l < N; l++) if (_t.child0[l] < 0) createChildren(l);
+    }
+    _frontier.clear();
+    finish(3);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -5,6 +5,7 @@
 //   TreeBuilder          TreeDustGrid::setupSelfBefore (TreeDustGrid.cpp:50-164), subdivide (:168-233),
 //                        OctTreeNode / BinTreeNode::createchildren + addneighbors (OctTreeNode.cpp:38-180,
 //                        BinTreeNode.cpp:40-330), TreeNode::sortneighbors (TreeNode.cpp:104-158)
+//                        ParticleTreeDustGrid::setupSelfBefore (ParticleTreeDustGrid.cpp:36-152) for trees grown around particles
 //   AdaptiveMeshBuilder  AdaptiveMesh::AdaptiveMesh (AdaptiveMesh.cpp:21-57), AdaptiveMeshNode (AdaptiveMeshNode.cpp:14-80)
 //   VoronoiBuilder       VoronoiMesh::buildMesh / buildTree (VoronoiMesh.cpp:310-393) on top of the Voro++ library
 //
@@ -41,9 +42,15 @@ public:
     void frontierBoxes(double* box6) const;     // [6 * frontierSize()]
     void subdivide(const unsigned char* flags); // flags[frontierSize()] (ignored unless frontierNeedsDecision())
     void finish(int search);                    // cell numbers; neighbour lists when search == 1 (Neighbor)
+    // ParticleTreeDustGrid::setupSelfBefore (ParticleTreeDustGrid.cpp:76-152) on a tree that is still its root: the particles
+    // are added one by one, a leaf that already holds one is subdivided until the two sit in different leaves; then
+    // extraLevels more subdivisions of every leaf; finishes the tables with search = 3 (that grid's own traversal)
+    void addParticles(const double* xyz, size_t n, int extraLevels);
     const TreeTables& tables() const { return _t; }
 private:
     void createChildren(int l);
+    int whichNodeFrom(int start, double x, double y, double z) const;
+    int addParticle(int p, int start, const double* xyz, std::vector<int>& particlev);
     void addNeighbors(int l);
     void makeNeighbors(int wall1, int node1, int node2);
     void deleteNeighbor(int node, int wall, int other);

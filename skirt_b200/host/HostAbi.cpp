@@ -40,6 +40,10 @@ int skh_tree_finish(skh_tree* t, int search, int* Nnodes, int* Ncells, int64_t* 
                       if (Nnodes) *Nnodes = T.Nnodes;
                       if (Ncells) *Ncells = T.Ncells;
                       if (Nneighbours) *Nneighbours = (int64_t)T.nbrIds.size(); }); }
+int skh_ptree_build(int kind, const double* extent6, const double* particles, int64_t n, int extraLevels, skh_tree** out, int* Nnodes, int* Ncells)
+{ return guarded([&]{ if (!extent6 || !out || n < 0 || extraLevels < 0) throw std::runtime_error("bad arguments"); skh_tree* t = new skh_tree(kind, extent6, 0, 2);      // (the level limits of TreeDustGrid play no role here)
+                      try { t->b.addParticles(particles, (size_t)n, extraLevels); } catch (...) { delete t; throw; }
+                      *out = t; if (Nnodes) *Nnodes = t->b.tables().Nnodes; if (Ncells) *Ncells = t->b.tables().Ncells; }); }
 int skh_tree_tables(skh_tree* t, double* box, int* child0, int* parent, int* cell, int* dir, int* level, int* nbrStart, int* nbrIds)
 { return guarded([&]{ if (!t) throw std::runtime_error("null tree"); const skirt::TreeTables& T = t->b.tables();
                       if (T.Nnodes == 0) throw std::runtime_error("skh_tree_finish has not been called");

@@ -58,6 +58,38 @@ void TreeDustGrid::upload(skg_engine* e) const
                         _t.nbrStart.empty() ? nullptr : _t.nbrStart.data(), _t.nbrIds.empty() ? nullptr : _t.nbrIds.data()));
 }
 
+// ---- particle tree ---------------------------------------------------------------------------------------------------------
+static void readParticleFile(const std::string& file, std::vector<double>& xyz, const char* what)
+{
+    std::ifstream in(file);
+    if (!in) SKIRT_FATAL(std::string("Could not open the ") + what + " particle file " + file);
+    xyz.clear();
+    std::string line; double x, y, z;
+    while (std::getline(in, line)) { if (line.empty() || line[0] == '#') continue; std::istringstream is(line); if (is >> x >> y >> z) { xyz.push_back(x); xyz.push_back(y); xyz.push_back(z); } }
+}
+
+void ParticleTreeDustGrid::setup()
+{
+    BoxDustGrid::setup();
+    if (_extra < 0) SKIRT_FATAL("The number of extra levels should not be negative");
+    if (!_file.empty()) readParticleFile(_file, _particles, "tree");
+    try
+    {
+        skirt::TreeBuilder tb((int)_kind, _ext, 0, 2);          // (the level limits of TreeDustGrid play no role here)
+        tb.addParticles(_particles.data(), _particles.size() / 3, _extra);
+        _t = tb.tables();
+    }
+    catch (std::runtime_error& ex) { SKIRT_FATAL(ex.what()); }
+    _cellNode.assign(_t.Ncells, 0);
+    for (int l = 0; l < _t.Nnodes; l++) if (_t.cell[l] >= 0) _cellNode[_t.cell[l]] = l;
+}
+
+void ParticleTreeDustGrid::upload(skg_engine* e) const
+{
+    if (_t.Nnodes == 0) SKIRT_FATAL("the tree has not been built");
+    check(skg_grid_tree(e, (int)_kind, 3, _t.Nnodes, _t.box.data(), _t.child0.data(), _t.parent.data(), _t.cell.data(), _t.dir.data(), nullptr, nullptr));
+}
+
 // ---- adaptive mesh -------------------------------------------------------------------------------------------------------
 void AdaptiveMeshDustGrid::setup()
 {

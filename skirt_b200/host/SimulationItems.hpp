@@ -424,6 +424,27 @@ private:
 class OctTreeDustGrid : public TreeDustGrid { public: OctTreeDustGrid() : TreeDustGrid(0) {} };
 class BinTreeDustGrid : public TreeDustGrid { public: BinTreeDustGrid() : TreeDustGrid(1) {} };
 
+// ParticleTreeDustGrid (ParticleTreeDustGrid.cpp:76-152): an octree or binary tree grown around particle positions (one per
+// line of a text file, or given directly); every leaf ends up with at most one particle; its own traversal (search = 3)
+class ParticleTreeDustGrid : public BoxDustGrid
+{
+public:
+    enum TreeType { OctTree = 0, BinTree = 1 };
+    void setTreeType(TreeType v) { _kind = v; }
+    void setExtraLevels(int v) { _extra = v; }
+    void setParticleFile(const std::string& path) { _file = path; }
+    void setParticles(const std::vector<double>& xyz) { _particles = xyz; }
+    void setup() override;
+    bool densityOnDevice() const override { return true; }
+    int numCells() const override { return _t.Ncells; }
+    void upload(skg_engine* e) const override;
+    void cellBox(int m, double b[6]) const override { const double* q = &_t.box[6 * (size_t)_cellNode[m]]; for (int c = 0; c < 6; c++) b[c] = q[c]; }
+    const skirt::TreeTables& tables() const { return _t; }
+private:
+    TreeType _kind = OctTree; int _extra = 0; std::string _file; std::vector<double> _particles;
+    skirt::TreeTables _t; std::vector<int> _cellNode;
+};
+
 // AdaptiveMeshDustGrid + AdaptiveMeshDustDistribution over an adaptive mesh data file in the format of
 // AdaptiveMeshAsciiFile (AdaptiveMeshAsciiFile.cpp:43-100): "! Nx Ny Nz" for a nonleaf, the field values for a leaf
 class AdaptiveMeshDustGrid : public BoxDustGrid

@@ -9,7 +9,7 @@
 //   wavelengths l1 l2 ...          | loggrid min max points
 //   box xmin xmax ymin ymax zmin zmax
 //   grid cartesian nx ny nz lin|pow r|sympow r  (x3) | grid octtree|bintree minLevel maxLevel search maxMassFraction [samples [maxTau]]
-//        | grid amesh <file> densityUnits [index] (+ meshdust) | grid voronoi <particle file>
+//        | grid amesh <file> densityUnits [index] (+ meshdust) | grid voronoi <particle file> | grid particletree oct|bin <particle file> [extraLevels]
 //   dustmix interstellar <file> | dustmix table kabs ksca g      (one wavelength)
 //   dust tau lambda expdisk hR hz Rmax zmax
 //   stellar L1[,L2,...]|bb:T:Lbol expdisk hR hz Rmax zmax | sersic n Reff q
@@ -123,6 +123,13 @@ int main(int argc, char** argv)
                 {
                     std::string file; in >> file;           // grid voronoi <particle file: x y z per line>
                     auto* g = new VoronoiDustGrid(); setBox(g); g->setParticleFile(file);
+                    ds->setDustGrid(g); continue;
+                }
+                if (kind == "particletree")
+                {
+                    std::string tt, file; int extra = 0; in >> tt >> file; in >> extra;      // grid particletree oct|bin <particle file> [extraLevels]
+                    auto* g = new ParticleTreeDustGrid(); setBox(g); g->setParticleFile(file); g->setExtraLevels(extra);
+                    g->setTreeType(tt == "bin" ? ParticleTreeDustGrid::BinTree : ParticleTreeDustGrid::OctTree);
                     ds->setDustGrid(g); continue;
                 }
                 if (kind != "cartesian") SKIRT_FATAL("unknown dust grid " + kind);

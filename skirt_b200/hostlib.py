@@ -104,6 +104,25 @@ class TreeBuilder:
         return t
 
 
+def build_particle_tree(kind, extent, particles, extraLevels=0):
+    """skh_ptree_build: the tree of ParticleTreeDustGrid (ParticleTreeDustGrid.cpp:76-152) around particles[n,3]; kind 0 octree, 1 binary
+    tree; tables for skg_grid_tree with search = 3"""
+    L = load_library()
+    ext = np.ascontiguousarray(extent, dtype=np.float64)
+    pts = np.ascontiguousarray(particles, dtype=np.float64).reshape(-1, 3)
+    h = C.c_void_p(); nn = C.c_int(); nc = C.c_int()
+    _chk(L.skh_ptree_build(int(kind), _p(ext), _p(pts), C.c_int64(len(pts)), int(extraLevels), C.byref(h), C.byref(nn), C.byref(nc)))
+    try:
+        N = nn.value
+        t = dict(kind="octtree" if int(kind) == 0 else "bintree", search=3, box=np.zeros(6 * N), child0=np.zeros(N, np.int32),
+                 parent=np.zeros(N, np.int32), cell=np.zeros(N, np.int32), dir=np.zeros(N, np.int32), level=np.zeros(N, np.int32))
+        _chk(L.skh_tree_tables(h, _p(t["box"]), _p(t["child0"]), _p(t["parent"]), _p(t["cell"]), _p(t["dir"]), _p(t["level"]), None, None))
+    finally:
+        L.skh_tree_destroy(h)
+    t["Ncells"] = nc.value
+    return t
+
+
 def build_adaptive_mesh(extent, nxyz):
     """skh_amesh_*: tables of skg_grid_amesh + cell volumes and, per cell, the index of its line in the input sequence"""
     L = load_library()

@@ -376,6 +376,25 @@ class BinTreeDustGrid(OctTreeDustGrid):
     kind = 1
 
 
+class ParticleTreeDustGrid(_BoxDustGrid):
+    """ParticleTreeDustGrid (ParticleTreeDustGrid.cpp:76-152): an octree or binary tree grown around a set of particles -- every
+    leaf ends up with at most one -- plus extraLevels subdivisions of every leaf; its own traversal (search = 3)."""
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, particles, treeType="OctTree", extraLevels=0):
+        self._set_extent(minX, maxX, minY, maxY, minZ, maxZ)
+        if treeType not in ("OctTree", "BinTree"):
+            raise FatalError(f"unknown tree type {treeType}")
+        if extraLevels < 0:
+            raise FatalError("The number of extra levels should not be negative")
+        from . import hostlib
+        self.kind = 0 if treeType == "OctTree" else 1
+        self._t = hostlib.build_particle_tree(self.kind, self.extent, np.asarray(particles, dtype=np.float64).reshape(-1, 3), extraLevels)
+
+    def build(self, *a, **k):
+        return self
+
+    volumes = OctTreeDustGrid.volumes
+
+
 class AdaptiveMeshDustGrid(_BoxDustGrid):
     """AdaptiveMeshDustGrid + AdaptiveMeshDustDistribution: the mesh comes as the node sequence of an adaptive mesh file
     (AdaptiveMeshAsciiFile.cpp:43-100: depth first, one (Nx, Ny, Nz) per non-leaf and one density value per leaf); the

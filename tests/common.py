@@ -159,6 +159,8 @@ def spec_grid(kind, search=1, box=C1_BOX, minlevel=2, maxlevel=5, massfrac=2e-4,
         lines = head + ["grid voronoi file", "dustsamples 10", stellar, dust, instr]
     elif kind == "amesh":
         lines = head + ["grid amesh", "ameshdust 1e-24", stellar, instr]
+    elif kind in ("particletree_oct", "particletree_bin"):      # maxlevel doubles as the number of extra levels (0 or 1 in the tests)
+        lines = head + [f"grid particletree {kind[-3:]} {0 if maxlevel > 1 else maxlevel}", "dustsamples 10", stellar, dust, instr]
     else:
         raise ValueError(kind)
     return "\n".join(lines + list(extra)) + "\n"

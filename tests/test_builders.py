@@ -41,6 +41,23 @@ def test_tree_builder_reproduces_the_reference_tree(kind, kw, search):
     assert mine["Ncells"] == int((child0 < 0).sum())
 
 
+@pytest.mark.parametrize("tt,extra", [("oct", 0), ("oct", 1), ("bin", 0), ("bin", 1)])
+def test_particle_tree_builder_reproduces_the_reference_tree(tt, extra):
+    """ParticleTreeDustGrid: node ids follow the order in which the particles are added (ParticleTreeDustGrid.cpp:36-72)"""
+    pts = common.voronoi_particles(3000, seed=5)
+    pts[7] = [9e30, 0, 0]                        # a particle outside the box is skipped (whichnode returns 0)
+    ref = _ref(common.spec_grid("particletree_" + tt, maxlevel=extra), particles=pts).grid_tables()
+    mine = hostlib.build_particle_tree(0 if tt == "oct" else 1, common.C1_BOX, pts, extra)
+    assert ref["search"] == 3 and mine["search"] == 3
+    for k in ("box", "child0", "parent", "cell"):
+        assert np.array_equal(np.asarray(mine[k]).ravel(), np.asarray(ref[k]).ravel()), f"{tt}: {k} differs from the reference"
+    inner = ref["child0"] >= 0
+    assert np.array_equal(mine["dir"][inner], np.asarray(ref["dir"])[inner])
+    assert mine["Ncells"] == int((ref["child0"] < 0).sum()) >= 2999
+    with pytest.raises(hostlib.HostError, match="share a position"):
+        hostlib.build_particle_tree(0, common.C1_BOX, np.zeros((2, 3)), 0)
+
+
 def test_tree_builder_validation():
     with pytest.raises(hostlib.HostError, match="Maximum tree level should be larger"):
         hostlib.TreeBuilder(0, common.C1_BOX, 3, 3)

@@ -65,7 +65,7 @@ def test_streams_are_reproducible_and_disjoint(engine):
     assert out[0] != out[2]                              # disjoint Philox counters -> a different realisation
 
 
-@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi"])
+@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi", "particletree_oct"])
 def test_other_grids_against_reference_runs(engine, kind):
     """the same 3-sigma gate on the hierarchical / unstructured grids, against runs of the reference's own code
     (oracle/_ref travels to the GPU box as a prebuilt library; skipped where it is absent)"""
@@ -77,7 +77,7 @@ def test_other_grids_against_reference_runs(engine, kind):
     kw = {}
     if kind == "amesh":
         kw["amesh"] = common.make_amesh(max_depth=3)
-    if kind == "voronoi":
+    if kind in ("voronoi", "particletree_oct"):
         kw["particles"] = common.voronoi_particles(3000)
     spec = common.spec_grid(kind, search=1, maxlevel=4 if kind == "octtree" else 10, packages=1e5, threads=os.cpu_count() or 1, extra=extra)
     S = sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw).setup()

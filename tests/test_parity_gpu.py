@@ -159,7 +159,7 @@ def test_large_batch_offsets_are_consistent(engine):
     np.testing.assert_allclose(got["s"][off[1:] - 1], t, rtol=1e-8)      # the tree walker adds eps = 1e-12 x diagonal per crossing
 
 
-@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi"])
+@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi", "particletree_oct", "particletree_bin"])
 def test_deep_grids_against_the_reference(engine, kind):
     """grids deep enough for every part of the per-node crossing records -- walls with up to 16 neighbours, edge-touching ones included (wall-bin
     tables of several resolutions), root descents through several levels, Voronoi cells with up to 30+ neighbours --
@@ -172,11 +172,18 @@ def test_deep_grids_against_the_reference(engine, kind):
     kw = {}
     if kind == "amesh":
         kw["amesh"] = common.make_amesh(root=(4, 4, 4), max_depth=4, frac=1e-4)
-    if kind == "voronoi":
+    if kind == "voronoi" or kind.startswith("particletree"):
         kw["particles"] = common.voronoi_particles(20000)
-    spec = common.spec_grid(kind, search=1, minlevel=2, maxlevel=7 if kind == "octtree" else 16, massfrac=2e-5, threads=os.cpu_count() or 1)
+    maxlevel = {"octtree": 7, "particletree_oct": 1, "particletree_bin": 0}.get(kind, 16)       # (particle trees: the number of extra levels)
+    spec = common.spec_grid(kind, search=1, minlevel=2, maxlevel=maxlevel, massfrac=2e-5, threads=os.cpu_count() or 1)
     S = sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw).setup()
     tables, medium = S.grid_tables(), S.medium()
+    if kind.startswith("particletree"):
+        # the product-side builder (skh_ptree_build) grows the same tree from the same particles: traverse ITS tables
+        from skirt_b200 import hostlib
+        mine = hostlib.build_particle_tree(0 if kind.endswith("oct") else 1, common.C1_BOX, kw["particles"], maxlevel)
+        assert np.array_equal(mine["cell"], tables["cell"])
+        tables = dict(mine, eps=tables["eps"])
     engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
     r, k = common.rays(40000, common.C1_BOX, 515)
     # rays inside the planes x = 0 / z = 0 and along the axes: positions on cell faces, |k_a| <= 1e-15 components
