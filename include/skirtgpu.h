@@ -181,12 +181,20 @@ int skg_sample_boxes(skg_engine* e, int64_t n, const double* box, int Ncomp, con
 int skg_sample_launch(skg_engine* e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
 
 /* ---- instruments: DistantInstrument / SingleFrameInstrument / Frame-, SED-, SimpleInstrument ---------- */
-enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3, SKG_INSTR_FULL = 4 };
+enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3, SKG_INSTR_FULL = 4, SKG_INSTR_MULTIFRAME = 5 };
 /* FullInstrument (FullInstrument.cpp:107-172, unpolarised part): one data cube + SED per channel, in this order */
 enum { SKG_CHAN_TRANSPARENT = 0, SKG_CHAN_STELLAR_DIRECT = 1, SKG_CHAN_STELLAR_SCATTERED = 2, SKG_CHAN_DUST_DIRECT = 3,
        SKG_CHAN_DUST_SCATTERED = 4, SKG_CHAN_SCATTERING_LEVEL1 = 5 /* + (level - 1), level = 1..scatteringLevels */ };
 /* with a polarised medium three more channels follow the scattering levels: Stokes Q, U, V of the total flux
  * (FullInstrument::_ftotQv/_ftotUv/_ftotVv): channel 5 + scatteringLevels + {0, 1, 2} */
+/* MultiFrameInstrument (MultiFrameInstrument.cpp:85-99) + InstrumentFrame (InstrumentFrame.cpp:153-187): one frame per
+ * wavelength, each with its own pixel grid; a packet of wavelength ell is recorded in frame ell only, in the total array
+ * (writeTotal) and -- stellar packets -- in the array of the stellar component that emitted it (writeStellarComps) */
+typedef struct skg_instrument_frame
+{
+    int Nxp, Nyp;
+    double fovxp, fovyp, xpc, ypc;
+} skg_instrument_frame;
 typedef struct skg_instrument
 {
     int kind;
@@ -194,8 +202,13 @@ typedef struct skg_instrument
     int Nxp, Nyp;                                                /* SingleFrameInstrument */
     double fovxp, fovyp, xpc, ypc;
     int scatteringLevels;                                        /* FullInstrument::setScatteringLevels (0 for the other kinds) */
+    int writeTotal, writeStellarComps;                           /* MultiFrameInstrument only */
+    const skg_instrument_frame* frames;                          /* MultiFrameInstrument only: one per wavelength of the medium; else NULL */
 } skg_instrument;
 int skg_instruments(skg_engine* e, int n, const skg_instrument* instr);
+/* one frame of a MultiFrameInstrument: which = -1 the total flux, k >= 0 the flux of stellar component k (InstrumentFrame's
+ * _ftotv / _fcompvv[k]); frame[Nxp*Nyp] of frame ell; add as for skg_fetch_frame */
+int skg_fetch_multiframe(skg_engine* e, int instrument, int which, int ell, double* frame, int add);
 /* detector arrays of one FullInstrument channel (replace FullInstrument's private _f*v / _F*v arrays); add as for skg_fetch_frame */
 int skg_fetch_frame_channel(skg_engine* e, int instrument, int channel, double* frame, int add);
 int skg_fetch_sed_channel(skg_engine* e, int instrument, int channel, double* sed, int add);

@@ -54,6 +54,8 @@
 #include "InterstellarDustMix.hpp"
 #include "LinMesh.hpp"
 #include "LogWavelengthGrid.hpp"
+#include "MultiFrameInstrument.hpp"
+#include "InstrumentFrame.hpp"
 #include "OctTreeDustGrid.hpp"
 #include "ParticleTreeDustGrid.hpp"
 #include "DustParticleInterface.hpp"
@@ -376,6 +378,20 @@ namespace
                 std::string kind, name; double d, inc, az, pa; in >> kind >> name >> d >> inc >> az >> pa;
                 DistantInstrument* di = 0;
                 if (kind == "sed") di = new SEDInstrument();
+                else if (kind == "multiframe")
+                {
+                    // instrument multiframe <name> d inc az pa <writeTotal> <writeStellarComps> <N>  then N x (nx fovx ny fovy xc yc)
+                    int wt, wc, n; in >> wt >> wc >> n;
+                    MultiFrameInstrument* mf = new MultiFrameInstrument(); mf->setWriteTotal(wt != 0); mf->setWriteStellarComps(wc != 0);
+                    for (int q = 0; q < n; q++)
+                    {
+                        int nx, ny; double fx, fy, xc, yc; in >> nx >> fx >> ny >> fy >> xc >> yc;
+                        InstrumentFrame* fr = new InstrumentFrame(); fr->setPixelsX(nx); fr->setFieldOfViewX(fx); fr->setPixelsY(ny); fr->setFieldOfViewY(fy);
+                        fr->setCenterX(xc); fr->setCenterY(yc);
+                        mf->insertFrame(q, fr);
+                    }
+                    di = mf;
+                }
                 else
                 {
                     int nx, ny; double fx, fy; in >> nx >> fx >> ny >> fy;
@@ -736,6 +752,8 @@ int skr_reset(void* h, int seed)
             if (FrameInstrument* f = dynamic_cast<FrameInstrument*>(ins)) f->_ftotv = 0.0;
             if (SEDInstrument* f = dynamic_cast<SEDInstrument*>(ins)) f->_Ftotv = 0.0;
             if (SimpleInstrument* f = dynamic_cast<SimpleInstrument*>(ins)) { f->_ftotv = 0.0; f->_Ftotv = 0.0; }
+            if (MultiFrameInstrument* mf = dynamic_cast<MultiFrameInstrument*>(ins))
+                for (InstrumentFrame* fr : mf->_frames) { if (fr->_ftotv.size()) fr->_ftotv = 0.0; for (size_t k = 0; k < fr->_fcompvv.size(0); k++) fr->_fcompvv[k] = 0.0; }
             if (FullInstrument* f = dynamic_cast<FullInstrument*>(ins))
             {
                 for (Array* a : {&f->_ftrav, &f->_Ftrav, &f->_fstrdirv, &f->_Fstrdirv, &f->_fstrscav, &f->_Fstrscav, &f->_fdusdirv, &f->_Fdusdirv,
@@ -809,6 +827,17 @@ int skr_get_full_channel(void* h, int i, int c, double* frame, double* sed)
     if (frame) for (size_t j = 0; j < fa->size(); j++) frame[j] = (*fa)[j];
     if (sed) for (size_t j = 0; j < sa->size(); j++) sed[j] = (*sa)[j];
     return 0;
+}
+// raw array of one frame of a MultiFrameInstrument: which = -1 total, k >= 0 stellar component k; returns the number of pixels (out may be null)
+long skr_get_multiframe(void* h, int i, int which, int ell, double* out)
+{
+    MultiFrameInstrument* mf = dynamic_cast<MultiFrameInstrument*>(((Sim*)h)->is->instruments()[i]);
+    if (!mf || ell < 0 || ell >= mf->_frames.size()) return -1;
+    InstrumentFrame* fr = mf->_frames[ell];
+    const Array* a = which < 0 ? &fr->_ftotv : (which < (int)fr->_fcompvv.size(0) ? &fr->_fcompvv[which] : 0);
+    if (!a) return -1;
+    if (out) for (size_t j = 0; j < a->size(); j++) out[j] = (*a)[j];
+    return (long)a->size();
 }
 // instrument geometry as the reference derived it (DistantInstrument.cpp:27-50, SingleFrameInstrument.cpp)
 void skr_get_instrument_geometry(void* h, int i, double* out /*[16]*/)

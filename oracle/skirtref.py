@@ -265,6 +265,16 @@ class RefSim:
             out.append(dict(frame=frame, sed=sed, geometry=geo))
         return out
 
+    def multiframe(self, i, which, ell):
+        """raw array of one frame of a MultiFrameInstrument (which = -1: total flux, k >= 0: stellar component k)"""
+        L = lib(); L.skr_get_multiframe.restype = C.c_long
+        n = L.skr_get_multiframe(self.h, int(i), int(which), int(ell), None)
+        if n < 0:
+            raise RefError("no such multi-frame array")
+        a = np.zeros(n)
+        L.skr_get_multiframe(self.h, int(i), int(which), int(ell), a.ctypes.data_as(C.c_void_p))
+        return a
+
     def full_channel(self, i, c, nframe):
         """raw (uncalibrated) data cube and SED of one FullInstrument channel"""
         frame = np.zeros(nframe); sed = np.zeros(self.Nlambda)

@@ -13,7 +13,7 @@ _lib = None
 
 SKG_HOST, SKG_DEVICE = 0, 1
 GEOM_EXPDISK, GEOM_SERSIC = 1, 2
-INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL = 1, 2, 3, 4
+INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, INSTR_MULTIFRAME = 1, 2, 3, 4, 5
 # FullInstrument channels (include/skirtgpu.h SKG_CHAN_*): scattering level n is channel CHAN_LEVEL1 + n - 1
 CHAN_TRANSPARENT, CHAN_STELLAR_DIRECT, CHAN_STELLAR_SCATTERED, CHAN_DUST_DIRECT, CHAN_DUST_SCATTERED, CHAN_LEVEL1 = 0, 1, 2, 3, 4, 5
 PHASE_STELLAR, PHASE_DUST_SELFABS, PHASE_DUST_EMISSION = 0, 1, 2
@@ -34,12 +34,17 @@ class SkgSource(C.Structure):
                 ("ntab", C.c_int), ("rv", C.c_void_p), ("Xv", C.c_void_p), ("Sv", C.c_void_p)]
 
 
+class SkgInstrumentFrame(C.Structure):
+    _fields_ = [("Nxp", C.c_int), ("Nyp", C.c_int), ("fovxp", C.c_double), ("fovyp", C.c_double), ("xpc", C.c_double), ("ypc", C.c_double)]
+
+
 class SkgInstrument(C.Structure):
     _fields_ = [("kind", C.c_int), ("distance", C.c_double), ("inclination", C.c_double),
                 ("azimuth", C.c_double), ("positionAngle", C.c_double),
                 ("Nxp", C.c_int), ("Nyp", C.c_int),
                 ("fovxp", C.c_double), ("fovyp", C.c_double), ("xpc", C.c_double), ("ypc", C.c_double),
-                ("scatteringLevels", C.c_int)]
+                ("scatteringLevels", C.c_int), ("writeTotal", C.c_int), ("writeStellarComps", C.c_int),
+                ("frames", C.POINTER(SkgInstrumentFrame))]
 
 
 class SkgMcParams(C.Structure):
@@ -335,7 +340,7 @@ class Engine:
         return r, k, L
 
     def instruments(self, instr):
-        arr = (SkgInstrument * len(instr))()
+        arr = (SkgInstrument * len(instr))(); keep = []
         for i, d in enumerate(instr):
             a = arr[i]
             a.kind = int(d["kind"]); a.distance = float(d["distance"]); a.inclination = float(d["inclination"])
@@ -344,6 +349,15 @@ class Engine:
             a.fovxp = float(d.get("fovxp", 0.0)); a.fovyp = float(d.get("fovyp", 0.0))
             a.xpc = float(d.get("xpc", 0.0)); a.ypc = float(d.get("ypc", 0.0))
             a.scatteringLevels = int(d.get("scatteringLevels", 0))
+            a.writeTotal = int(bool(d.get("writeTotal", True))); a.writeStellarComps = int(bool(d.get("writeStellarComps", False)))
+            if d.get("frames") is not None:         # MultiFrameInstrument: one dict(Nxp, Nyp, fovxp, fovyp[, xpc, ypc]) per wavelength
+                fr = (SkgInstrumentFrame * len(d["frames"]))()
+                if len(d["frames"]) != self.Nlambda:
+                    raise EngineError("Number of instrument frames must equal number of wavelengths")
+                for q, f in enumerate(d["frames"]):
+                    fr[q].Nxp = int(f["Nxp"]); fr[q].Nyp = int(f["Nyp"]); fr[q].fovxp = float(f["fovxp"]); fr[q].fovyp = float(f["fovyp"])
+                    fr[q].xpc = float(f.get("xpc", 0.0)); fr[q].ypc = float(f.get("ypc", 0.0))
+                keep.append(fr); a.frames = fr
         self._instr = list(instr)
         self._chk(self._lib.skg_instruments(self.h, len(instr), arr))
 
@@ -464,6 +478,13 @@ class Engine:
         a = np.zeros((self.Ncells, self.Nlambda)) if out is None else out
         self._chk(self._lib.skg_fetch_labs(self.h, _vp(a), 0))
         return a
+
+    def fetch_multiframe(self, i, which, ell):
+        """one frame of a MultiFrameInstrument: which = -1 the total flux, k >= 0 stellar component k; [Nyp, Nxp] of frame ell"""
+        f = self._instr[i]["frames"][ell]
+        out = np.zeros((int(f["Nyp"]), int(f["Nxp"])))
+        self._chk(self._lib.skg_fetch_multiframe(self.h, int(i), int(which), int(ell), _vp(out), 0))
+        return out
 
     def results_snapshot(self):
         """skg_results_snapshot: shadow copies of every accumulator, to be fetched while the engine goes on"""

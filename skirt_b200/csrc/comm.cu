@@ -86,7 +86,7 @@ static void allreduce(Engine& e, int which, double* elapsedMs)
         for (const InstrDev& d : e.instr)
         {
             const size_t Nf = (size_t)d.Nxp * d.Nyp;
-            if (d.frame) SKG_NCCL(nccl.allReduce(d.frame, d.frame, Nf * Nl, ncclDouble, ncclSum, comm, e.stream));
+            if (d.frame) SKG_NCCL(nccl.allReduce(d.frame, d.frame, (size_t)d.frameCount, ncclDouble, ncclSum, comm, e.stream));
             if (d.sed) SKG_NCCL(nccl.allReduce(d.sed, d.sed, Nl, ncclDouble, ncclSum, comm, e.stream));
             if (d.chanFrame) SKG_NCCL(nccl.allReduce(d.chanFrame, d.chanFrame, Nf * Nl * d.Nchan, ncclDouble, ncclSum, comm, e.stream));
             if (d.chanSed) SKG_NCCL(nccl.allReduce(d.chanSed, d.chanSed, Nl * d.Nchan, ncclDouble, ncclSum, comm, e.stream));

@@ -622,7 +622,7 @@ int skg_fetch_frame(skg_engine* eh, int i, double* frame, int add)
     return guarded([&]{
         Engine& e = E(eh);
         if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].frame) throw Error("instrument has no frame");
-        fetchArray(e, e.instr[i].frame, (int64_t)e.instr[i].Nxp * e.instr[i].Nyp * e.instrNlambda, frame, add);
+        fetchArray(e, e.instr[i].frame, (int64_t)e.instr[i].frameCount, frame, add);      // (a MultiFrameInstrument: all its slabs; see skg_fetch_multiframe)
     });
 }
 int skg_fetch_sed(skg_engine* eh, int i, double* sed, int add)
@@ -631,6 +631,20 @@ int skg_fetch_sed(skg_engine* eh, int i, double* sed, int add)
         Engine& e = E(eh);
         if (i < 0 || i >= (int)e.instr.size() || !e.instr[i].sed) throw Error("instrument has no SED");
         fetchArray(e, e.instr[i].sed, e.instrNlambda, sed, add);
+    });
+}
+int skg_fetch_multiframe(skg_engine* eh, int i, int which, int ell, double* frame, int add)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        if (i < 0 || i >= (int)e.instr.size() || e.instr[i].kind != SKG_INSTR_MULTIFRAME) throw Error("not a multi-frame instrument");
+        const InstrDev& d = e.instr[i];
+        if (ell < 0 || ell >= e.instrNlambda) throw Error("wavelength index out of range");
+        const int slab = which < 0 ? d.mfTotal : (which < d.mfNcomp && d.mfComp0 >= 0 ? d.mfComp0 + which : -1);
+        if (slab < 0) throw Error(which < 0 ? "the instrument does not record the total flux" : "the instrument does not record this stellar component");
+        FrameDev f;
+        SKG_CUDA(cudaMemcpyAsync(&f, d.frames + ell, sizeof(FrameDev), cudaMemcpyDeviceToHost, e.stream)); e.sync();
+        fetchArray(e, d.frame + (size_t)slab * d.mfPixels + f.offset, (int64_t)f.Nxp * f.Nyp, frame, add);
     });
 }
 int skg_fetch_frame_channel(skg_engine* eh, int i, int c, double* frame, int add)
@@ -676,7 +690,7 @@ int skg_device_accumulators(skg_engine* eh, int which, int part, double** d_ptr,
             else { *d_ptr = d.chanSed; *count = (int64_t)e.instrNlambda * d.Nchan; }
             return;
         }
-        if (part == 0) { *d_ptr = d.frame; *count = d.frame ? (int64_t)d.Nxp * d.Nyp * e.instrNlambda : 0; }
+        if (part == 0) { *d_ptr = d.frame; *count = d.frame ? (int64_t)d.frameCount : 0; }
         else { *d_ptr = d.sed; *count = d.sed ? e.instrNlambda : 0; }
     });
 }
@@ -711,7 +725,7 @@ int skg_results_snapshot(skg_engine* eh)
         {
             const InstrDev& d = e.instr[i]; const int64_t Nl = e.instrNlambda, Nf = (int64_t)d.Nxp * d.Nyp;
             const double* srcs[2] = {d.kind == SKG_INSTR_FULL ? d.chanFrame : d.frame, d.kind == SKG_INSTR_FULL ? d.chanSed : d.sed};
-            const int64_t counts[2] = {Nf * Nl * (d.kind == SKG_INSTR_FULL ? d.Nchan : 1), Nl * (d.kind == SKG_INSTR_FULL ? d.Nchan : 1)};
+            const int64_t counts[2] = {d.kind == SKG_INSTR_FULL ? Nf * Nl * d.Nchan : (int64_t)d.frameCount, Nl * (d.kind == SKG_INSTR_FULL ? d.Nchan : 1)};
             for (int part = 0; part < 2; part++)
                 if (srcs[part]) SKG_CUDA(cudaMemcpyAsync(shadow((int)i + 1, part, counts[part])->p, srcs[part], sizeof(double) * counts[part], cudaMemcpyDeviceToDevice, e.stream));
         }

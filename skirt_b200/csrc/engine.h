@@ -43,6 +43,8 @@ struct SourceDev
     double rho0;                                // density normalisation of the bare geometry
 };
 
+// one InstrumentFrame of a MultiFrameInstrument (InstrumentFrame.cpp:29-44): its pixel grid and where its pixels start in a slab
+struct FrameDev { int Nxp, Nyp; double xpmin, ypmin, xpsiz, ypsiz; long long offset; };
 struct InstrDev
 {
     int kind;
@@ -54,6 +56,10 @@ struct InstrDev
     int Nchan, Nscatt; double* chanFrame; double* chanSed;
     int pol;                        // FullInstrument of a simulation with polarisation: channels Nchan-3 .. Nchan-1 are Stokes Q, U, V
     double kyx, kyy, kyz;           // DistantInstrument::bfky (DistantInstrument.cpp:47-49): the frame's y axis in model coordinates
+    long long frameCount;           // doubles in `frame`
+    // MultiFrameInstrument: `frame` holds slabs of mfPixels doubles (the frames of all wavelengths one after the other): the total
+    // flux (slab mfTotal, -1: not recorded) and one slab per stellar component (from slab mfComp0, -1: not recorded)
+    const FrameDev* frames; long long mfPixels; int mfTotal, mfComp0, mfNcomp;
 };
 
 struct Engine

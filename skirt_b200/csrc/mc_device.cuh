@@ -29,7 +29,8 @@ struct __align__(32) Packet
     unsigned long long id;      // Philox stream id of the packet
     int ell, nscatt; unsigned rngCtr; int fresh;
     int hint;                   // the walker's locator of the packet's position (tree / adaptive-mesh leaf node, Voronoi cell) when a
-    int pad;                    // traversal has established it, else -1: the next traversal from this position skips the point location
+                                // traversal has established it, else -1: the next traversal from this position skips the point location
+    int comp;                   // PhotonPackage::stellarCompIndex(): the stellar component that emitted the packet, -1 for dust emission
 };
 typedef Packet* PacketPool;
 

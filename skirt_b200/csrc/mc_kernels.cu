@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(128) launchStage(const __grid_constant__ McDev
         }
         Packet* q = P.pool;
         Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
-        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.pad = 0;
+        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.comp = h;
         storePacket(q + slot, pk);
         if (P.pol) { PolState ps; stokesUnpolarized(ps); P.pol[slot] = ps; }       // PhotonPackage::launch: setUnpolarized()
     }
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(128) launchDustStage(const __grid_constant__ G
         randomDirection(rng, kx, ky, kz);
         Packet* q = P.pool;
         Packet pk; pk.x = x; pk.y = y; pk.z = z; pk.kx = kx; pk.ky = ky; pk.kz = kz;
-        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.pad = 0;
+        pk.L = L; pk.target = 0; pk.id = id; pk.ell = ell; pk.nscatt = 0; pk.rngCtr = rng.c2; pk.fresh = 1; pk.hint = -1; pk.comp = -1;
         storePacket(q + slot, pk);
         if (P.pol) { PolState ps; stokesUnpolarized(ps); P.pol[slot] = ps; }       // PhotonPackage::launch: setUnpolarized()
     }
@@ -240,6 +240,38 @@ __device__ __forceinline__ int pixelOnDetector(const InstrDev& I, double x, doub
     int j = (int)floor((yp - I.ypmin) / I.ypsiz);
     if (i < 0 || i >= I.Nxp || j < 0 || j >= I.Nyp) return -1;
     return i + I.Nxp * j;
+}
+
+// InstrumentFrame::pixelondetector (InstrumentFrame.cpp:153-171): the frame of the packet's wavelength, the instrument's angles
+__device__ __forceinline__ long long pixelOnMultiFrame(const InstrDev& I, int ell, double x, double y, double z)
+{
+    const FrameDev F = I.frames[ell];
+    double xpp = -I.sinphi * x + I.cosphi * y;
+    double ypp = -I.cosphi * I.costheta * x - I.sinphi * I.costheta * y + I.sintheta * z;
+    double xp = I.cospa * xpp - I.sinpa * ypp;
+    double yp = I.sinpa * xpp + I.cospa * ypp;
+    int i = (int)floor((xp - F.xpmin) / F.xpsiz);
+    int j = (int)floor((yp - F.ypmin) / F.ypsiz);
+    if (i < 0 || i >= F.Nxp || j < 0 || j >= F.Nyp) return -1;
+    return F.offset + i + F.Nxp * j;
+}
+// does this instrument look at a packet at (x, y, z) before any optical depth is computed?  Frame-type detectors drop packets
+// that map outside their frame first (FrameInstrument.cpp:36, InstrumentFrame.cpp:177); every other kind needs the optical depth
+__device__ __forceinline__ bool instrumentRecords(const InstrDev& I, int ell, double x, double y, double z)
+{
+    if (I.kind == SKG_INSTR_FRAME) return pixelOnDetector(I, x, y, z) >= 0;
+    if (I.kind == SKG_INSTR_MULTIFRAME) return pixelOnMultiFrame(I, ell, x, y, z) >= 0;
+    return true;
+}
+// InstrumentFrame::detect (InstrumentFrame.cpp:175-187); returns the number of detector updates
+__device__ __forceinline__ int detectMultiFrame(const InstrDev& I, int ell, double x, double y, double z, double Lextf, int comp)
+{
+    const long long l = pixelOnMultiFrame(I, ell, x, y, z);
+    if (l < 0) return 0;
+    int n = 0;
+    if (I.mfTotal >= 0) { atomicAdd(I.frame + (size_t)I.mfTotal * I.mfPixels + l, Lextf); n++; }
+    if (I.mfComp0 >= 0 && comp >= 0 && comp < I.mfNcomp) { atomicAdd(I.frame + (size_t)(I.mfComp0 + comp) * I.mfPixels + l, Lextf); n++; }
+    return n;
 }
 
 // FullInstrument::detect (FullInstrument.cpp:107-172, unpolarised part): the flux goes to the channel of its origin --
@@ -304,8 +336,7 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
         bool need = false;
         for (int c = 0; c < g.count; c++)
         {
-            const InstrDev& I = P.instr[g.first + c];
-            if (I.kind != SKG_INSTR_FRAME || pixelOnDetector(I, rx, ry, rz) >= 0) { need = true; break; }
+            if (instrumentRecords(P.instr[g.first + c], ell, rx, ry, rz)) { need = true; break; }
         }
         if (!need) return 0;
         const int Ncomp = P.med.Ncomp, Nlambda = P.med.Nlambda;
@@ -450,6 +481,7 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
                 if constexpr (POL) { if (I.pol && !q->fresh) peelStokes(I, g, *q, P.pol[item / P.Ngroups], sQ, sU, sV); }
                 nDet += detectFull(I, P.med.Nlambda, px, py, pz, ell, Lw, Lextf, ns, P.phase == SKG_PHASE_STELLAR, sQ, sU, sV); continue;
             }
+            if (I.kind == SKG_INSTR_MULTIFRAME) { nDet += detectMultiFrame(I, ell, px, py, pz, Lextf, P.phase == SKG_PHASE_STELLAR ? q->comp : -1); continue; }
             // SEDInstrument::detect SEDInstrument.cpp:32-42, FrameInstrument::detect FrameInstrument.cpp:32-47, SimpleInstrument.cpp:33-49
             // (the SED bins are served by collective(): one address per wavelength, summed over the converged warp)
             if (I.kind != SKG_INSTR_FRAME) nDet++;
@@ -471,7 +503,7 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
         {
             const bool has = fin && c < g.count;
             const InstrDev& I = P.instr[has ? g.first + c : 0];
-            const bool take = has && I.kind != SKG_INSTR_FRAME && I.kind != SKG_INSTR_FULL;
+            const bool take = has && I.kind != SKG_INSTR_FRAME && I.kind != SKG_INSTR_FULL && I.kind != SKG_INSTR_MULTIFRAME;
             warpConvergedAdd(take, take ? I.sed + ell : nullptr, sedAdd);
         }
     }
@@ -578,7 +610,7 @@ template<int KIND, bool SINGLE, bool POL> struct ContPeelJob
             // which instruments of this direction record a packet from there?  (FrameInstrument.cpp:36)
             bool need = false;
             for (int c = 0; c < g.count; c++)
-            { const InstrDev& I = P.instr[g.first + c]; if (I.kind != SKG_INSTR_FRAME || pixelOnDetector(I, px, py, pz) >= 0) { need = true; break; } }
+            if (instrumentRecords(P.instr[g.first + c], ell, px, py, pz)) { need = true; break; }
             if (need)
             {
                 // Instrument::opticalDepth of the peel-off packet: a traversal of its own, with a second walker
@@ -614,6 +646,7 @@ template<int KIND, bool SINGLE, bool POL> struct ContPeelJob
                         if constexpr (POL) { if (I.pol) { PeelJob<KIND, SINGLE, POL> pj(G, cart, P); pj.peelStokes(I, g, loadPacket(q), P.pol[item / P.Ngroups], sQ, sU, sV); } }
                         nDet += detectFull(I, Nlambda, px, py, pz, ell, Lw, Lextf, q->nscatt + 1, P.phase == SKG_PHASE_STELLAR, sQ, sU, sV); continue;
                     }
+                    if (I.kind == SKG_INSTR_MULTIFRAME) { nDet += detectMultiFrame(I, ell, px, py, pz, Lextf, P.phase == SKG_PHASE_STELLAR ? q->comp : -1); continue; }
                     if (I.kind != SKG_INSTR_FRAME) { atomicAdd(I.sed + ell, Lextf); nDet++; }
                     if (I.kind != SKG_INSTR_SED)
                     {
@@ -840,7 +873,7 @@ template<int KIND, bool SINGLE, bool STORE, bool POL> struct AbsorbJob
         if (pos >= 0)
         {
             Packet pk = loadPacket(P.pool + slot);
-            pk.L = Lout; pk.target = target; pk.rngCtr = rngOut; pk.fresh = 0; pk.pad = 0;
+            pk.L = Lout; pk.target = target; pk.rngCtr = rngOut; pk.fresh = 0;
             storePacket(P.poolNext + pos, pk);
             if constexpr (POL) P.polNext[pos] = P.pol[slot];
         }
@@ -1072,7 +1105,7 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
         const skg_instrument& s = instr[i];
         InstrDev d{};
         d.kind = s.kind;
-        if (s.kind < SKG_INSTR_FRAME || s.kind > SKG_INSTR_FULL) throw Error("unsupported instrument kind");
+        if (s.kind < SKG_INSTR_FRAME || s.kind > SKG_INSTR_MULTIFRAME) throw Error("unsupported instrument kind");
         if (s.kind == SKG_INSTR_FULL && (s.scatteringLevels < 0 || s.scatteringLevels > 1000)) throw Error("invalid number of scattering levels");
         if (s.distance <= 0) throw Error("Distance was not set");                    // DistantInstrument.cpp:32
         // DistantInstrument::setupSelfBefore, DistantInstrument.cpp:27-50
@@ -1088,6 +1121,43 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
         }
         // DistantInstrument::bfky, DistantInstrument.cpp:47-49
         d.kyx = -d.cosphi * d.costheta * d.cospa - d.sinphi * d.sinpa; d.kyy = -d.sinphi * d.costheta * d.cospa + d.cosphi * d.sinpa; d.kyz = d.sintheta * d.cospa;
+        d.frameCount = 0; d.frames = nullptr; d.mfPixels = 0; d.mfTotal = d.mfComp0 = -1; d.mfNcomp = 0;
+        if (s.kind == SKG_INSTR_MULTIFRAME)
+        {
+            // MultiFrameInstrument::setupSelfBefore (MultiFrameInstrument.cpp:22-29) + InstrumentFrame::setupSelfBefore (InstrumentFrame.cpp:29-44, :62-71):
+            // one frame per wavelength; the arrays of all frames share one allocation, slab by slab
+            if (!s.frames) throw Error("Number of instrument frames must equal number of wavelengths");
+            std::vector<FrameDev> fr(e.med.Nlambda);
+            long long off = 0;
+            for (int ell = 0; ell < e.med.Nlambda; ell++)
+            {
+                const skg_instrument_frame& f = s.frames[ell];
+                if (f.Nxp <= 0 || f.Nyp <= 0) throw Error("Number of pixels was not set");
+                if (f.fovxp <= 0 || f.fovyp <= 0) throw Error("Field of view was not set");
+                fr[ell] = FrameDev{f.Nxp, f.Nyp, f.xpc - 0.5 * f.fovxp, f.ypc - 0.5 * f.fovyp, f.fovxp / f.Nxp, f.fovyp / f.Nyp, off};
+                off += (long long)f.Nxp * f.Nyp;
+            }
+            int slabs = 0;
+            d.mfPixels = off; d.mfNcomp = (int)e.sources.size();
+            if (s.writeTotal) d.mfTotal = slabs++;
+            if (s.writeStellarComps)
+            {
+                if (d.mfNcomp < 1) throw Error("a MultiFrameInstrument that records the stellar components needs skg_sources first");
+                d.mfComp0 = slabs; slabs += d.mfNcomp;
+            }
+            DevBuf* fb = e.takeBuf(sizeof(FrameDev) * fr.size()); e.instrBufs.push_back(fb);
+            fb->upload(fr.data(), sizeof(FrameDev) * fr.size(), e.stream); SKG_CUDA(cudaStreamSynchronize(e.stream));      // (fr is a local)
+            d.frames = fb->as<FrameDev>();
+            d.frameCount = (long long)slabs * off;
+            if (d.frameCount > 0)
+            {
+                DevBuf* f = e.takeBuf(sizeof(double) * (size_t)d.frameCount); e.instrBufs.push_back(f);
+                f->ensure(sizeof(double) * (size_t)d.frameCount); SKG_CUDA(cudaMemsetAsync(f->p, 0, sizeof(double) * (size_t)d.frameCount, e.stream));
+                d.frame = f->as<double>();
+            }
+            e.instr.push_back(d);
+            continue;
+        }
         if (s.kind != SKG_INSTR_SED)
         {
             // SingleFrameInstrument::setupSelfBefore, SingleFrameInstrument.cpp:26-42
@@ -1100,7 +1170,7 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
             size_t bytes = sizeof(double) * (size_t)s.Nxp * s.Nyp * e.med.Nlambda * (s.kind == SKG_INSTR_FULL ? d.Nchan : 1);
             DevBuf* f = e.takeBuf(bytes); e.instrBufs.push_back(f);
             f->ensure(bytes); SKG_CUDA(cudaMemsetAsync(f->p, 0, bytes, e.stream));
-            if (s.kind == SKG_INSTR_FULL) d.chanFrame = f->as<double>(); else d.frame = f->as<double>();
+            if (s.kind == SKG_INSTR_FULL) d.chanFrame = f->as<double>(); else { d.frame = f->as<double>(); d.frameCount = (long long)s.Nxp * s.Nyp * e.med.Nlambda; }
         }
         if (s.kind != SKG_INSTR_FRAME)
         {
@@ -1138,7 +1208,7 @@ void mcResetResults(Engine& e)
     const size_t Nl = (size_t)e.instrNlambda;
     for (const InstrDev& d : e.instr)
     {
-        if (d.frame) SKG_CUDA(cudaMemsetAsync(d.frame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * Nl, e.stream));
+        if (d.frame) SKG_CUDA(cudaMemsetAsync(d.frame, 0, sizeof(double) * (size_t)d.frameCount, e.stream));
         if (d.sed) SKG_CUDA(cudaMemsetAsync(d.sed, 0, sizeof(double) * Nl, e.stream));
         if (d.chanFrame) SKG_CUDA(cudaMemsetAsync(d.chanFrame, 0, sizeof(double) * (size_t)d.Nxp * d.Nyp * Nl * d.Nchan, e.stream));
         if (d.chanSed) SKG_CUDA(cudaMemsetAsync(d.chanSed, 0, sizeof(double) * Nl * d.Nchan, e.stream));

@@ -177,6 +177,28 @@ void writeInstrument(const Instrument& ins, const WavelengthGrid& lg, const Unit
                      bool dustsystem, bool dustemission)
 {
     const skg_instrument d = ins.descriptor();
+    if (const MultiFrameInstrument* mf = dynamic_cast<const MultiFrameInstrument*>(&ins))
+    {
+        // InstrumentFrame::calibrateAndWriteDataFrames (InstrumentFrame.cpp:216-262): per wavelength, every array divided by
+        // dlambda * pixel solid angle * 4 pi d^2, converted to the output units, one FITS file per array
+        if ((int)mf->arrays.size() != lg.Nlambda()) SKIRT_FATAL("the detector arrays of instrument " + ins.name + " have not been fetched");
+        for (int ell = 0; ell < lg.Nlambda(); ell++)
+        {
+            const skg_instrument_frame& f = mf->frames()[ell];
+            const double xpsiz = f.fovxp / f.Nxp, ypsiz = f.fovyp / f.Nyp;
+            const double area = (2.0 * std::atan(xpsiz / (2.0 * d.distance))) * (2.0 * std::atan(ypsiz / (2.0 * d.distance)));
+            const double fourpid2 = 4.0 * M_PI * d.distance * d.distance;
+            const double factor = units.osurfacebrightness(lg.lambda(ell), 1.) / (lg.dlambda(ell) * area * fourpid2);
+            for (size_t q = 0; q < mf->arrays[ell].size(); q++)
+            {
+                std::vector<double> a = mf->arrays[ell][q];
+                for (double& v : a) v *= factor;
+                writeFITS(prefix + "_" + ins.name + "_" + mf->arrayNames[q] + "_" + std::to_string(ell) + ".fits", a, f.Nxp, f.Nyp, 1,
+                          units.olength(xpsiz), units.olength(ypsiz), f.xpc, f.ypc, units.usurfacebrightness(), units.ulength(), stamp);
+            }
+        }
+        return;
+    }
     if (const FullInstrument* fi = dynamic_cast<const FullInstrument*>(&ins))
     {
         // FullInstrument::write, FullInstrument.cpp:176-236: total = direct + scattered (+ dust); empty arrays are skipped as

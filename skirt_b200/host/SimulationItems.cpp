@@ -260,7 +260,11 @@ void StellarSystem::upload(skg_engine* e) const
 void InstrumentSystem::upload(skg_engine* e) const
 {
     std::vector<skg_instrument> d;
-    for (auto& i : _instruments) d.push_back(i->descriptor());
+    for (auto& i : _instruments)
+    {
+        const MultiFrameInstrument* mf = dynamic_cast<const MultiFrameInstrument*>(i.get());
+        d.push_back(mf ? mf->descriptorWithFrames() : i->descriptor());
+    }
     check(skg_instruments(e, (int)d.size(), d.data()));
 }
 
@@ -383,6 +387,22 @@ void MonteCarloSimulation::fetchResults()
                 check(skg_fetch_frame_channel(_engine, idx, c, f->fchanv[c].data(), 0));
                 check(skg_fetch_sed_channel(_engine, idx, c, f->Fchanv[c].data(), 0));
             }
+            idx++; continue;
+        }
+        if (MultiFrameInstrument* mf = dynamic_cast<MultiFrameInstrument*>(i.get()))
+        {
+            // the arrays InstrumentFrame::calibrateAndWriteData lists (InstrumentFrame.cpp:193-207): total, then stellar_k
+            std::vector<int> which; mf->arrayNames.clear();
+            if (d.writeTotal) { which.push_back(-1); mf->arrayNames.push_back("total"); }
+            if (d.writeStellarComps) for (int k = 0; k < _ss->Ncomp(); k++) { which.push_back(k); mf->arrayNames.push_back("stellar_" + std::to_string(k)); }
+            mf->arrays.assign(Nl, std::vector<std::vector<double>>());
+            for (int ell = 0; ell < Nl; ell++)
+                for (int w : which)
+                {
+                    const skg_instrument_frame& f = mf->frames()[ell];
+                    mf->arrays[ell].emplace_back((size_t)f.Nxp * f.Nyp, 0.0);
+                    check(skg_fetch_multiframe(_engine, idx, w, ell, mf->arrays[ell].back().data(), 0));
+                }
             idx++; continue;
         }
         if (d.kind != SKG_INSTR_SED) { i->ftotv.assign((size_t)d.Nxp * d.Nyp * Nl, 0.0); check(skg_fetch_frame(_engine, idx, i->ftotv.data(), 0)); }

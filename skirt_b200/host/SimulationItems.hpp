@@ -595,6 +595,7 @@ public:
     void setup(const WavelengthGrid& lg) { if (_comps.empty()) SKIRT_FATAL("There are no stellar components"); for (auto& c : _comps) c->setup(lg); _Nlambda = lg.Nlambda(); }
     void upload(skg_engine* e) const;
     double luminosity(int ell) const { double s = 0; for (auto& c : _comps) s += c->Lv[ell]; return s; }
+    int Ncomp() const { return (int)_comps.size(); }
 private:
     std::vector<std::unique_ptr<StellarComp>> _comps; double _emissionBias = 0.5; int _Nlambda = 0;
 };
@@ -631,6 +632,30 @@ public:
     int scatteringLevels() const { return d.scatteringLevels; }
     int channels() const override { return SKG_CHAN_SCATTERING_LEVEL1 + d.scatteringLevels; }
     std::vector<std::vector<double>> fchanv, Fchanv;     // [channel][...] raw detector arrays (filled by fetch)
+};
+
+// MultiFrameInstrument (MultiFrameInstrument.cpp) with its InstrumentFrame items (InstrumentFrame.cpp:22-44): one pixel grid per
+// wavelength; the total flux and / or the flux of every stellar component, one FITS file per array and wavelength
+struct InstrumentFrame
+{
+    void setPixelsX(int v) { f.Nxp = v; } void setPixelsY(int v) { f.Nyp = v; }
+    void setFieldOfViewX(double v) { f.fovxp = v; } void setFieldOfViewY(double v) { f.fovyp = v; }
+    void setCenterX(double v) { f.xpc = v; } void setCenterY(double v) { f.ypc = v; }
+    skg_instrument_frame f{};
+};
+class MultiFrameInstrument : public Instrument
+{
+public:
+    MultiFrameInstrument() { d.writeTotal = 1; }
+    int kind() const override { return SKG_INSTR_MULTIFRAME; }
+    void setWriteTotal(bool v) { d.writeTotal = v ? 1 : 0; } void setWriteStellarComps(bool v) { d.writeStellarComps = v ? 1 : 0; }
+    void addFrame(const InstrumentFrame& fr) { _frames.push_back(fr.f); }
+    const std::vector<skg_instrument_frame>& frames() const { return _frames; }
+    // filled by fetch: arrays[ell] = the arrays of frame ell in the order of InstrumentFrame::calibrateAndWriteData, with their names
+    std::vector<std::vector<std::vector<double>>> arrays; std::vector<std::string> arrayNames;
+    skg_instrument descriptorWithFrames() const { skg_instrument s = descriptor(); s.frames = _frames.data(); return s; }
+private:
+    std::vector<skg_instrument_frame> _frames;
 };
 
 class InstrumentSystem

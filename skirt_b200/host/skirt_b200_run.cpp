@@ -169,6 +169,20 @@ int main(int argc, char** argv)
             else if (key == "instrument")
             {
                 std::string kind, name; double d, inc, az, pa; in >> kind >> name >> d >> inc >> az >> pa;
+                if (kind == "multiframe")
+                {
+                    // instrument multiframe <name> d inc az pa <writeTotal> <writeStellarComps> <N>  then N x (nx fovx ny fovy xc yc)
+                    int wt, wc, n; in >> wt >> wc >> n;
+                    auto* mf = new MultiFrameInstrument(); mf->setWriteTotal(wt != 0); mf->setWriteStellarComps(wc != 0);
+                    mf->setInstrumentName(name); mf->setDistance(d); mf->setInclination(inc); mf->setAzimuth(az); mf->setPositionAngle(pa);
+                    for (int q = 0; q < n; q++)
+                    {
+                        InstrumentFrame fr; int nx, ny; double fx, fy, xc, yc; in >> nx >> fx >> ny >> fy >> xc >> yc;
+                        fr.setPixelsX(nx); fr.setFieldOfViewX(fx); fr.setPixelsY(ny); fr.setFieldOfViewY(fy); fr.setCenterX(xc); fr.setCenterY(yc);
+                        mf->addFrame(fr);
+                    }
+                    is->addInstrument(mf); continue;
+                }
                 Instrument* i = kind == "sed" ? (Instrument*)new SEDInstrument() : kind == "frame" ? (Instrument*)new FrameInstrument()
                               : kind == "full" ? (Instrument*)new FullInstrument() : (Instrument*)new SimpleInstrument();
                 i->setInstrumentName(name); i->setDistance(d); i->setInclination(inc); i->setAzimuth(az); i->setPositionAngle(pa);

@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from .simulation import FatalError, INSTR_FRAME, INSTR_SED, INSTR_FULL
+from .simulation import FatalError, INSTR_FRAME, INSTR_SED, INSTR_FULL, INSTR_MULTIFRAME
 
 _C = 2.99792458e8            # Units.cpp:17-22
 _AU = 1.49597871e11
@@ -293,6 +293,21 @@ def write_instruments(sim, results, outdir, prefix="", units=None, stamp=None):
             name = f"{prefix}{ins.name}_sed.dat"
             write_sed(os.path.join(outdir, name), lg, cols, names, units)
             out[name] = np.array(cols)
+            continue
+        if ins.kind == INSTR_MULTIFRAME:
+            # InstrumentFrame::calibrateAndWriteDataFrames (InstrumentFrame.cpp:216-262): one FITS file per array and wavelength
+            for ell, arrays in enumerate(results[ins.name + "_frames"]):
+                fd = d["frames"][ell]
+                xpsiz = fd["fovxp"] / fd["Nxp"]; ypsiz = fd["fovyp"] / fd["Nyp"]
+                area = (2.0 * math.atan(xpsiz / (2.0 * d["distance"]))) * (2.0 * math.atan(ypsiz / (2.0 * d["distance"])))
+                fourpid2 = 4.0 * math.pi * d["distance"] * d["distance"]
+                unitfactor = units.osurfacebrightness(lg.lambdav[ell], 1.0)
+                for fname, raw in arrays.items():
+                    cal = np.asarray(raw, dtype=np.float64) * (unitfactor / (lg.dlambdav[ell] * area * fourpid2))
+                    name = f"{prefix}{ins.name}_{fname}_{ell}.fits"
+                    write_fits(os.path.join(outdir, name), cal, fd["Nxp"], fd["Nyp"], 1, units.out("length", xpsiz), units.out("length", ypsiz),
+                               fd["xpc"], fd["ypc"], units.unit("surfacebrightness"), units.unit("length"), stamp)
+                    out[name] = cal
             continue
         if ins.kind != INSTR_SED:
             cube = calibrate_frames(results[ins.name + "_frame"], lg, d, units)

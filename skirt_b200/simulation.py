@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from .parallel import shard_packets
-from .binding import (Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, CHAN_LEVEL1,
+from .binding import (Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, INSTR_MULTIFRAME, CHAN_LEVEL1,
                       REDUCE_LABS_STELLAR, REDUCE_LABS_DUST, REDUCE_INSTRUMENTS)
 
 PC = 3.08567758e16          # Units.cpp:17-30
@@ -599,7 +599,7 @@ class _DistantInstrument:
         self.d = dict(kind=self.kind, name=instrumentName, distance=float(distance), inclination=float(inclination),
                       azimuth=float(azimuth), positionAngle=float(positionAngle), Nxp=int(pixelsX), Nyp=int(pixelsY),
                       fovxp=float(fieldOfViewX), fovyp=float(fieldOfViewY), xpc=float(centerX), ypc=float(centerY))
-        if self.kind != INSTR_SED and (pixelsX <= 0 or pixelsY <= 0):
+        if self.kind not in (INSTR_SED, INSTR_MULTIFRAME) and (pixelsX <= 0 or pixelsY <= 0):
             raise FatalError("Number of pixels was not set")
 
 
@@ -631,6 +631,27 @@ class FullInstrument(_DistantInstrument):
 
     def channel_names(self):
         return list(self.CHANNELS) + [f"scatteringlevel{n + 1}" for n in range(self.d["scatteringLevels"])]
+
+
+class InstrumentFrame:
+    """InstrumentFrame (InstrumentFrame.cpp:22-44): the pixel grid of one wavelength of a MultiFrameInstrument"""
+    def __init__(self, pixelsX, fieldOfViewX, pixelsY, fieldOfViewY, centerX=0.0, centerY=0.0):
+        if pixelsX <= 0 or pixelsY <= 0:
+            raise FatalError("Number of pixels was not set")
+        if fieldOfViewX <= 0 or fieldOfViewY <= 0:
+            raise FatalError("Field of view was not set")
+        self.d = dict(Nxp=int(pixelsX), Nyp=int(pixelsY), fovxp=float(fieldOfViewX), fovyp=float(fieldOfViewY), xpc=float(centerX), ypc=float(centerY))
+
+
+class MultiFrameInstrument(_DistantInstrument):
+    """MultiFrameInstrument (MultiFrameInstrument.cpp): one InstrumentFrame per wavelength, each with its own field of view and
+    resolution; records the total flux and / or the flux of every stellar component separately"""
+    kind = INSTR_MULTIFRAME
+
+    def __init__(self, instrumentName, distance, inclination, azimuth=0.0, positionAngle=0.0, frames=(), writeTotal=True, writeStellarComps=False):
+        super().__init__(instrumentName, distance, inclination, azimuth, positionAngle)
+        self.frames = list(frames)
+        self.d.update(frames=[f.d for f in self.frames], writeTotal=bool(writeTotal), writeStellarComps=bool(writeStellarComps))
 
 
 class InstrumentSystem:
@@ -794,6 +815,12 @@ class MonteCarloSimulation:
                     out[f"{ins.name}_{cname}_frame"] = self.engine.fetch_frame_channel(i, c).reshape(Nl, ins.d["Nyp"], ins.d["Nxp"])
                     out[f"{ins.name}_{cname}_sed"] = self.engine.fetch_sed_channel(i, c)
                 continue
+            if ins.kind == INSTR_MULTIFRAME:
+                # frames[ell] = {"total": [Nyp, Nxp], "stellar_k": ...} in the order InstrumentFrame::calibrateAndWriteData lists them
+                which = ([("total", -1)] if ins.d["writeTotal"] else []) + \
+                        ([(f"stellar_{k}", k) for k in range(len(self.ss.comps))] if ins.d["writeStellarComps"] else [])
+                out[ins.name + "_frames"] = [{nm: self.engine.fetch_multiframe(i, w, ell) for nm, w in which} for ell in range(Nl)]
+                continue
             if ins.kind != INSTR_SED:
                 n = ins.d["Nxp"] * ins.d["Nyp"] * Nl
                 out[ins.name + "_frame"] = self.engine.fetch_frame(i, dest(("f", i), (n,))).reshape(Nl, ins.d["Nyp"], ins.d["Nxp"])
@@ -820,8 +847,8 @@ class MonteCarloSimulation:
         wanted = [(("Labs",), 0, 0)] if self.storeabs else []
         for i, ins in enumerate(self.isys.instruments):
             if ins.kind != INSTR_SED:
-                wanted.append(((ins.name + "_frame",), i + 1, 0))
-            if ins.kind != INSTR_FRAME:
+                wanted.append(((ins.name + "_frame",), i + 1, 0))          # (a MultiFrameInstrument: all its slabs, flat)
+            if ins.kind not in (INSTR_FRAME, INSTR_MULTIFRAME):
                 wanted.append(((ins.name + "_sed",), i + 1, 1))
         for (name,), which, part in wanted:
             n = e.fetch_snapshot_async(which, part, None)

@@ -240,8 +240,14 @@ def ref_spec(cfg):
     if cfg.get("ameshdust"):
         lines.append(f"ameshdust {cfg['ameshdust']!r}")
     for ins in cfg["instruments"]:
-        kind = {1: "frame", 2: "sed", 3: "simple", 4: "full"}[ins["kind"]]
+        kind = {1: "frame", 2: "sed", 3: "simple", 4: "full", 5: "multiframe"}[ins["kind"]]
         w = f"instrument {kind} {ins['name']} {ins['distance']!r} {ins['inclination']!r} {ins.get('azimuth', 0.0)!r} {ins.get('positionAngle', 0.0)!r}"
+        if ins["kind"] == 5:
+            w += f" {int(ins.get('writeTotal', True))} {int(ins.get('writeStellarComps', False))} {len(ins['frames'])}"
+            for f in ins["frames"]:
+                w += f" {f['Nxp']} {f['fovxp']!r} {f['Nyp']} {f['fovyp']!r} {f.get('xpc', 0.0)!r} {f.get('ypc', 0.0)!r}"
+            lines.append(w)
+            continue
         if ins["kind"] != 2:
             w += f" {ins['Nxp']} {ins['fovxp']!r} {ins['Nyp']} {ins['fovyp']!r}"
         if ins["kind"] == 4:
