@@ -181,7 +181,7 @@ int skg_sample_boxes(skg_engine* e, int64_t n, const double* box, int Ncomp, con
 int skg_sample_launch(skg_engine* e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
 
 /* ---- instruments: DistantInstrument / SingleFrameInstrument / Frame-, SED-, SimpleInstrument ---------- */
-enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3, SKG_INSTR_FULL = 4, SKG_INSTR_MULTIFRAME = 5 };
+enum { SKG_INSTR_FRAME = 1, SKG_INSTR_SED = 2, SKG_INSTR_SIMPLE = 3, SKG_INSTR_FULL = 4, SKG_INSTR_MULTIFRAME = 5, SKG_INSTR_PERSPECTIVE = 6 };
 /* FullInstrument (FullInstrument.cpp:107-172, unpolarised part): one data cube + SED per channel, in this order */
 enum { SKG_CHAN_TRANSPARENT = 0, SKG_CHAN_STELLAR_DIRECT = 1, SKG_CHAN_STELLAR_SCATTERED = 2, SKG_CHAN_DUST_DIRECT = 3,
        SKG_CHAN_DUST_SCATTERED = 4, SKG_CHAN_SCATTERING_LEVEL1 = 5 /* + (level - 1), level = 1..scatteringLevels */ };
@@ -204,6 +204,10 @@ typedef struct skg_instrument
     int scatteringLevels;                                        /* FullInstrument::setScatteringLevels (0 for the other kinds) */
     int writeTotal, writeStellarComps;                           /* MultiFrameInstrument only */
     const skg_instrument_frame* frames;                          /* MultiFrameInstrument only: one per wavelength of the medium; else NULL */
+    /* PerspectiveInstrument (PerspectiveInstrument.cpp:36-108; distance and angles unused): Nxp x Nyp square pixels over a viewport
+     * of width fovxp centred on `view`, looking at `cross`hair with `up` upwards, the eye `focal` behind the viewport.  The peel-off
+     * direction is from the packet towards the eye (bfkobs(bfr), :290-304); the frame is fetched with skg_fetch_frame */
+    double viewX, viewY, viewZ, crossX, crossY, crossZ, upX, upY, upZ, focal;
 } skg_instrument;
 int skg_instruments(skg_engine* e, int n, const skg_instrument* instr);
 /* one frame of a MultiFrameInstrument: which = -1 the total flux, k >= 0 the flux of stellar component k (InstrumentFrame's

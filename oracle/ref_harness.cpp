@@ -55,6 +55,7 @@
 #include "LinMesh.hpp"
 #include "LogWavelengthGrid.hpp"
 #include "MultiFrameInstrument.hpp"
+#include "PerspectiveInstrument.hpp"
 #include "InstrumentFrame.hpp"
 #include "OctTreeDustGrid.hpp"
 #include "ParticleTreeDustGrid.hpp"
@@ -372,6 +373,15 @@ namespace
                 MeshDustComponent* mdc = new MeshDustComponent(); mdc->setDensityIndex(0); mdc->setMultiplierIndex(-1); mdc->setDensityFraction(1.0);
                 TableDustMix* mix = new TableDustMix(); mdc->setMix(mix); S->mixes.push_back(mix);
                 S->amdd->insertComponent(0, mdc);
+            }
+            else if (key == "perspective")
+            {
+                // perspective <name> Nx Ny width Vx Vy Vz Cx Cy Cz Ux Uy Uz focal
+                std::string name; int nx, ny; double w, v[10]; in >> name >> nx >> ny >> w; for (double& q : v) in >> q;
+                PerspectiveInstrument* pi = new PerspectiveInstrument(); pi->setInstrumentName(QString(name));
+                pi->setPixelsX(nx); pi->setPixelsY(ny); pi->setWidth(w); pi->setViewX(v[0]); pi->setViewY(v[1]); pi->setViewZ(v[2]);
+                pi->setCrossX(v[3]); pi->setCrossY(v[4]); pi->setCrossZ(v[5]); pi->setUpX(v[6]); pi->setUpY(v[7]); pi->setUpZ(v[8]); pi->setFocal(v[9]);
+                S->is->insertInstrument(S->is->instruments().size(), pi);
             }
             else if (key == "instrument")
             {
@@ -750,6 +760,7 @@ int skr_reset(void* h, int seed)
         for (Instrument* ins : S->is->instruments())
         {
             if (FrameInstrument* f = dynamic_cast<FrameInstrument*>(ins)) f->_ftotv = 0.0;
+            if (PerspectiveInstrument* f = dynamic_cast<PerspectiveInstrument*>(ins)) f->_ftotv = 0.0;
             if (SEDInstrument* f = dynamic_cast<SEDInstrument*>(ins)) f->_Ftotv = 0.0;
             if (SimpleInstrument* f = dynamic_cast<SimpleInstrument*>(ins)) { f->_ftotv = 0.0; f->_Ftotv = 0.0; }
             if (MultiFrameInstrument* mf = dynamic_cast<MultiFrameInstrument*>(ins))
@@ -790,6 +801,7 @@ void skr_instrument_sizes(void* h, int i, long* nframe, long* nsed)
 {
     Instrument* ins = ((Sim*)h)->is->instruments()[i]; *nframe = 0; *nsed = 0;
     if (FrameInstrument* f = dynamic_cast<FrameInstrument*>(ins)) *nframe = f->_ftotv.size();
+    if (PerspectiveInstrument* f = dynamic_cast<PerspectiveInstrument*>(ins)) *nframe = f->_ftotv.size();
     if (SEDInstrument* f = dynamic_cast<SEDInstrument*>(ins)) *nsed = f->_Ftotv.size();
     if (SimpleInstrument* f = dynamic_cast<SimpleInstrument*>(ins)) { *nframe = f->_ftotv.size(); *nsed = f->_Ftotv.size(); }
 }
@@ -798,6 +810,7 @@ void skr_get_instrument(void* h, int i, double* frame, double* sed)
     Instrument* ins = ((Sim*)h)->is->instruments()[i];
     const Array* fa = 0; const Array* sa = 0;
     if (FrameInstrument* f = dynamic_cast<FrameInstrument*>(ins)) fa = &f->_ftotv;
+    if (PerspectiveInstrument* f = dynamic_cast<PerspectiveInstrument*>(ins)) fa = &f->_ftotv;
     if (SEDInstrument* f = dynamic_cast<SEDInstrument*>(ins)) sa = &f->_Ftotv;
     if (SimpleInstrument* f = dynamic_cast<SimpleInstrument*>(ins)) { fa = &f->_ftotv; sa = &f->_Ftotv; }
     if (fa && frame) for (size_t j = 0; j < fa->size(); j++) frame[j] = (*fa)[j];
@@ -844,6 +857,7 @@ void skr_get_instrument_geometry(void* h, int i, double* out /*[16]*/)
 {
     Instrument* ins = ((Sim*)h)->is->instruments()[i];
     DistantInstrument* d = dynamic_cast<DistantInstrument*>(ins);
+    if (!d) { for (int j = 0; j < 16; j++) out[j] = 0; return; }
     out[0] = d->_costheta; out[1] = d->_sintheta; out[2] = d->_cosphi; out[3] = d->_sinphi; out[4] = d->_cospa; out[5] = d->_sinpa;
     out[6] = d->_bfkobs.kx(); out[7] = d->_bfkobs.ky(); out[8] = d->_bfkobs.kz();
     SingleFrameInstrument* f = dynamic_cast<SingleFrameInstrument*>(ins);

@@ -19,5 +19,5 @@ REF_CPP := Array.cpp ProcessManager.cpp \
  SersicFunction.cpp SpecialFunctions.cpp SpiralStructureGeometryDecorator.cpp \
  WavelengthGrid.cpp OligoWavelengthGrid.cpp PanWavelengthGrid.cpp LogWavelengthGrid.cpp \
  InstrumentSystem.cpp Instrument.cpp DistantInstrument.cpp SingleFrameInstrument.cpp FrameInstrument.cpp \
- SEDInstrument.cpp SimpleInstrument.cpp FullInstrument.cpp MultiFrameInstrument.cpp InstrumentFrame.cpp
+ SEDInstrument.cpp SimpleInstrument.cpp FullInstrument.cpp MultiFrameInstrument.cpp InstrumentFrame.cpp PerspectiveInstrument.cpp HomogeneousTransform.cpp
 REF_CC := $(filter-out v_base_wl.cc,$(notdir $(wildcard $(REF)/Voro/*.cc)))

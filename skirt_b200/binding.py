@@ -13,7 +13,7 @@ _lib = None
 
 SKG_HOST, SKG_DEVICE = 0, 1
 GEOM_EXPDISK, GEOM_SERSIC = 1, 2
-INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, INSTR_MULTIFRAME = 1, 2, 3, 4, 5
+INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, INSTR_MULTIFRAME, INSTR_PERSPECTIVE = 1, 2, 3, 4, 5, 6
 # FullInstrument channels (include/skirtgpu.h SKG_CHAN_*): scattering level n is channel CHAN_LEVEL1 + n - 1
 CHAN_TRANSPARENT, CHAN_STELLAR_DIRECT, CHAN_STELLAR_SCATTERED, CHAN_DUST_DIRECT, CHAN_DUST_SCATTERED, CHAN_LEVEL1 = 0, 1, 2, 3, 4, 5
 PHASE_STELLAR, PHASE_DUST_SELFABS, PHASE_DUST_EMISSION = 0, 1, 2
@@ -44,7 +44,9 @@ class SkgInstrument(C.Structure):
                 ("Nxp", C.c_int), ("Nyp", C.c_int),
                 ("fovxp", C.c_double), ("fovyp", C.c_double), ("xpc", C.c_double), ("ypc", C.c_double),
                 ("scatteringLevels", C.c_int), ("writeTotal", C.c_int), ("writeStellarComps", C.c_int),
-                ("frames", C.POINTER(SkgInstrumentFrame))]
+                ("frames", C.POINTER(SkgInstrumentFrame)),
+                ("viewX", C.c_double), ("viewY", C.c_double), ("viewZ", C.c_double), ("crossX", C.c_double), ("crossY", C.c_double),
+                ("crossZ", C.c_double), ("upX", C.c_double), ("upY", C.c_double), ("upZ", C.c_double), ("focal", C.c_double)]
 
 
 class SkgMcParams(C.Structure):
@@ -343,7 +345,9 @@ class Engine:
         arr = (SkgInstrument * len(instr))(); keep = []
         for i, d in enumerate(instr):
             a = arr[i]
-            a.kind = int(d["kind"]); a.distance = float(d["distance"]); a.inclination = float(d["inclination"])
+            a.kind = int(d["kind"]); a.distance = float(d.get("distance", 0.0)); a.inclination = float(d.get("inclination", 0.0))
+            for key in ("viewX", "viewY", "viewZ", "crossX", "crossY", "crossZ", "upX", "upY", "upZ", "focal"):      # PerspectiveInstrument
+                setattr(a, key, float(d.get(key, 0.0)))
             a.azimuth = float(d.get("azimuth", 0.0)); a.positionAngle = float(d.get("positionAngle", 0.0))
             a.Nxp = int(d.get("Nxp", 0)); a.Nyp = int(d.get("Nyp", 0))
             a.fovxp = float(d.get("fovxp", 0.0)); a.fovyp = float(d.get("fovyp", 0.0))

@@ -88,6 +88,7 @@ struct Engine
     int Nsources = 0; int NlambdaSrc = 0; double emissionBias = 0.5;
     std::vector<SourceDev> sources; DevBuf sourcesDev, lumDev, lumCdfDev, lumTotDev; std::vector<DevBuf*> sourceBufs;
     std::vector<double> lumHost, lumTotHost;
+    DevBuf perspDev; int Npersp = 0;        // PerspectiveInstruments (PerspDev), outside the observer groups
     std::vector<InstrDev> instr; DevBuf instrDev; std::vector<DevBuf*> instrBufs;
     DevBuf labs; int64_t labsCount = 0;    // absorbed luminosity, wavelength-major on the device: labs[ell*Ncells+m]
     DevBuf labsDust;                        // absorbed dust emission (self-absorption cycles), same layout

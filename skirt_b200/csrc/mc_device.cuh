@@ -65,6 +65,8 @@ struct __align__(32) PolState
 
 // instruments that look along the same direction share one peel-off traversal
 struct ObsGroup { double kx, ky, kz; int first, count; };
+// PerspectiveInstrument: eye position, world -> pixel transform (HomogeneousTransform::M, row vector convention), pixel size, data cube
+struct PerspDev { double Ex, Ey, Ez; double M[4][4]; int Nx, Ny; double s; double* frame; };
 
 struct McDev
 {
@@ -75,6 +77,7 @@ struct McDev
     const double* Lcdf;     // [Nlambda*(Nsources+1)]
     double emissionBias;
     const InstrDev* instr; int Ninstr;      // sorted by observer group
+    const PerspDev* persp; int Npersp;      // PerspectiveInstruments: one peel-off ray per packet each, towards the eye
     const ObsGroup* groups; int Ngroups; int maxGroupCount;     // largest number of instruments sharing one line of sight
     double* labs;           // [Nlambda*Ncells] (wavelength-major on the device) or null
     double Lscale;          // total packets per wavelength over all engines

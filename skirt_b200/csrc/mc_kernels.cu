@@ -301,7 +301,7 @@ static __device__ __noinline__ int detectFull(const InstrDev& I, int Nlambda, do
 }
 
 // One peel-off ray per (packet, observer direction): peeloffemission / peeloffscattering + Instrument::detect
-template<int KIND, bool SINGLE, bool POL> struct PeelJob
+template<int KIND, bool SINGLE, bool POL, bool PERSP = false> struct PeelJob
 {
     static constexpr bool kCartFast = SKG_MC_FAST; static constexpr bool kCartRegBorders = SKG_CART_REGBORDERS, kCartTinySelect = true; static constexpr bool kTreeHints = SKG_TREE_HINTS_MC, kCartRhoAhead = SKG_MC_RHO_AHEAD; static constexpr int kBatches = SKG_PEEL_BATCHES;
     const GridSetMC& G; const CartGrid& cart; const McDev& P;
@@ -317,23 +317,42 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
     double kext0, pendRho[kDepth], pendDs[kDepth];
     static constexpr bool single = SINGLE;  // one dust component: compile-time, no branch in the crossing loop
     double sedAdd;                          // what finish() leaves for collective(): the extincted luminosity for the SED bins
+    // PERSP (one item per packet and PerspectiveInstrument): the walk ends with the first segment beyond the distance to the viewport
+    // plane (DustGridPath::opticalDepth(kapparho, distance), DustGridPath.hpp:97-108); the pixel found in begin()
+    double sacc, smax; int pix;
     unsigned nSeg = 0, nPaths = 0, nDet = 0;
     __device__ PeelJob(const GridSetMC& G_, const CartGrid& c_, const McDev& P_) : G(G_), cart(c_), P(P_) {}
 
     __device__ __forceinline__ int begin(int it)
     {
         item = it;
-        const int slot = it / P.Ngroups;
-        const ObsGroup& g = P.groups[it % P.Ngroups];
+        const int ngroups = PERSP ? P.Npersp : P.Ngroups;
+        const int slot = it / ngroups;
+        ObsGroup gl; gl.first = 0; gl.count = 0;
+        const ObsGroup& g = PERSP ? gl : P.groups[it % ngroups];
         const Packet pk = loadPacket(P.pool + slot);
         double L = pk.L;
         if (!(L > 0)) return 0;                                 // MonteCarloSimulation.cpp:281
         if (P.contScatt && !pk.fresh) return 0;                 // continuous scattering: no peel-off at the interaction points (:291)
         rx = pk.x; ry = pk.y; rz = pk.z;
         ell = pk.ell; hint = KIND == GRID_CART ? -1 : pk.hint;
+        if constexpr (PERSP)
+        {
+            const PerspDev& V = P.persp[it % ngroups];
+            // PerspectiveInstrument::detect (PerspectiveInstrument.cpp:322-334): world -> pixel coordinates; packets that arrive outside
+            // the viewport or come from behind / very close to it are ignored before any optical depth is computed
+            const double xp = rx * V.M[0][0] + ry * V.M[1][0] + rz * V.M[2][0] + V.M[3][0], yp = rx * V.M[0][1] + ry * V.M[1][1] + rz * V.M[2][1] + V.M[3][1];
+            const double zp = rx * V.M[0][2] + ry * V.M[1][2] + rz * V.M[2][2] + V.M[3][2], wp = rx * V.M[0][3] + ry * V.M[1][3] + rz * V.M[2][3] + V.M[3][3];
+            const int i = (int)(xp / wp), j = (int)(yp / wp);
+            if (!(i >= 0 && i < V.Nx && j >= 0 && j < V.Ny && zp > V.s / 10.)) return 0;
+            pix = i + V.Nx * j; smax = zp; sacc = 0;
+            // bfkobs(bfr) (:290-304): from the packet towards the eye
+            const double ex = V.Ex - rx, ey = V.Ey - ry, ez = V.Ez - rz, D = sqrt(ex * ex + ey * ey + ez * ez);
+            if (D < 1e-20) { gl.kx = 0; gl.ky = 0; gl.kz = 1; } else { gl.kx = ex / D; gl.ky = ey / D; gl.kz = ez / D; }
+        }
         // which instruments of this direction record the packet?  FrameInstrument ignores packets that map outside
         // its frame before any optical depth is computed (FrameInstrument.cpp:36); SED/Simple always need tau
-        bool need = false;
+        bool need = PERSP;
         for (int c = 0; c < g.count; c++)
         {
             if (instrumentRecords(P.instr[g.first + c], ell, rx, ry, rz)) { need = true; break; }
@@ -445,25 +464,21 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
     }
     __device__ __forceinline__ int cellHint() const { return hint; }
     // the first traversal from a position establishes where it lies: remembered in the packet record for the next ones
-    __device__ __forceinline__ void noteStart(int loc) { if (KIND != GRID_CART) P.pool[item / P.Ngroups].hint = loc; }
-    __device__ __forceinline__ bool outside(double) { nSeg++; return true; }
+    __device__ __forceinline__ void noteStart(int loc) { if (KIND != GRID_CART) P.pool[item / (PERSP ? P.Npersp : P.Ngroups)].hint = loc; }
+    __device__ __forceinline__ bool outside(double d) { nSeg++; if constexpr (PERSP) { sacc += d; return !(sacc > smax); } return true; }
     template<int U> __device__ __forceinline__ bool segmentU(int m, double ds)
     {
         nSeg++;
         constexpr int q = U % kDepth;
         if (single) { tau += (kext0 * pendRho[q]) * pendDs[q]; pendRho[q] = __ldg(P.med.rho + m); pendDs[q] = ds; }
         else tau += KappaRho{P.med.rho, P.med.kext + ell, P.med.Ncomp, P.med.Nlambda}(m) * ds;
+        if constexpr (PERSP) { sacc += ds; return !(sacc > smax); }
         return true;
     }
     __device__ __forceinline__ bool segment(int m, double ds) { return segmentU<0>(m, ds); }
     template<int U> __device__ __forceinline__ void idleU() {}
     __device__ __forceinline__ void finish()
     {
-        const ObsGroup& g = P.groups[item % P.Ngroups];
-        // position and scattering count of the peel-off packet (launchEmissionPeelOff / launchScatteringPeelOff,
-        // PhotonPackage.cpp:34-62: 0 for emission, else previous scatterings + 1) from the packet record
-        const Packet* q = P.pool + item / P.Ngroups;
-        const double px = q->x, py = q->y, pz = q->z;
         if (single)
         {
 #pragma unroll
@@ -471,6 +486,19 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
         }
         const double Lextf = Lw * exp(-tau);
         sedAdd = Lextf;
+        if constexpr (PERSP)
+        {
+            // PerspectiveInstrument.cpp:336-350: the luminosity adjusted for the distance from the launch position to the viewport
+            const PerspDev& V = P.persp[item % P.Npersp];
+            const double r = V.s / (2. * smax), rar = r / atan(r);
+            atomicAdd(V.frame + (size_t)pix + (size_t)V.Nx * V.Ny * ell, Lextf * (rar * rar)); nDet++;
+            return;
+        }
+        const ObsGroup& g = P.groups[item % P.Ngroups];
+        // position and scattering count of the peel-off packet (launchEmissionPeelOff / launchScatteringPeelOff,
+        // PhotonPackage.cpp:34-62: 0 for emission, else previous scatterings + 1) from the packet record
+        const Packet* q = P.pool + item / P.Ngroups;
+        const double px = q->x, py = q->y, pz = q->z;
         for (int c = 0; c < g.count; c++)
         {
             const InstrDev& I = P.instr[g.first + c];
@@ -496,6 +524,7 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
     // maxCount instruments per observer direction, every lane taking part in every round
     __device__ __forceinline__ void collective(bool fin)
     {
+        if constexpr (PERSP) return;
         if (!__any_sync(0xffffffffu, fin)) return;
         const ObsGroup& g = P.groups[fin ? item % P.Ngroups : 0];
         const int rounds = P.maxGroupCount;
@@ -510,15 +539,15 @@ template<int KIND, bool SINGLE, bool POL> struct PeelJob
     __device__ __forceinline__ void periodic() {}
 };
 
-template<int KIND, bool SINGLE, bool POL>
+template<int KIND, bool SINGLE, bool POL, bool PERSP = false>
 __global__ void __launch_bounds__(128, KIND == GRID_CART ? SKG_PEEL_MINBLOCKS : SKG_OTHER_MINBLOCKS) peelStage(const __grid_constant__ GridSetMC G, const __grid_constant__ McDev P, Counters* ctr, bool cartSmem,
                                                  int nAlive, int* work)
 {
     extern __shared__ double smem[];
     CartGrid cart = G.cart;
     if (KIND == GRID_CART) cart = stageCart(G.cart, smem, cartSmem);
-    PeelJob<KIND, SINGLE, POL> job(G, cart, P);
-    runJobs<KIND>(G, cart, ctr, job, nAlive * P.Ngroups, work, P.peelRefill);
+    PeelJob<KIND, SINGLE, POL, PERSP> job(G, cart, P);
+    runJobs<KIND>(G, cart, ctr, job, nAlive * (PERSP ? P.Npersp : P.Ngroups), work, P.peelRefill);
     flushStats(ctr, job.nSeg, job.nPaths, 0, 0, 0, job.nDet);
     flushStageSegments(&ctr->peelSegments, job.nSeg);
 }
@@ -1100,12 +1129,69 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
     if (n < 0 || (n > 0 && !instr)) throw Error("skg_instruments: bad arguments");
     if (!e.med.Nlambda) throw Error("skg_instruments needs skg_medium first (number of wavelengths)");
     e.recycle(e.instrBufs); e.instr.clear();
+    std::vector<PerspDev> persp;
     for (int i = 0; i < n; i++)
     {
         const skg_instrument& s = instr[i];
         InstrDev d{};
         d.kind = s.kind;
-        if (s.kind < SKG_INSTR_FRAME || s.kind > SKG_INSTR_MULTIFRAME) throw Error("unsupported instrument kind");
+        if (s.kind < SKG_INSTR_FRAME || s.kind > SKG_INSTR_PERSPECTIVE) throw Error("unsupported instrument kind");
+        if (s.kind == SKG_INSTR_PERSPECTIVE)
+        {
+            // PerspectiveInstrument::setupSelfBefore, PerspectiveInstrument.cpp:36-108
+            if (s.Nxp <= 0 || s.Nyp <= 0) throw Error("Number of pixels was not set");
+            if (s.fovxp <= 0) throw Error("Viewport width was not set");
+            if (s.upX == 0 && s.upY == 0 && s.upZ == 0) throw Error("Upwards direction was not set");
+            if (s.focal <= 0) throw Error("Focal length was not set");
+            const double Vx = s.viewX, Vy = s.viewY, Vz = s.viewZ, Cx = s.crossX, Cy = s.crossY, Cz = s.crossZ, Ux = s.upX, Uy = s.upY, Uz = s.upZ, Fe = s.focal;
+            const double Gn = std::sqrt((Vx - Cx) * (Vx - Cx) + (Vy - Cy) * (Vy - Cy) + (Vz - Cz) * (Vz - Cz));
+            if (Gn < 1e-20) throw Error("Crosshair is too close to viewport origin");
+            const double a = (Vx - Cx) / Gn, b = (Vy - Cy) / Gn, c = (Vz - Cz) / Gn;
+            PerspDev V{}; V.Nx = s.Nxp; V.Ny = s.Nyp; V.s = s.fovxp / s.Nxp;
+            V.Ex = Vx + Fe * a; V.Ey = Vy + Fe * b; V.Ez = Vz + Fe * c;
+            // HomogeneousTransform (HomogeneousTransform.cpp): row-vector convention, every step post-multiplied
+            struct H
+            {
+                double M[4][4];
+                H() { for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) M[i][j] = i == j ? 1. : 0.; }
+                void cat(const H& t)
+                { H c0(*this); for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) M[i][j] = c0.M[i][0] * t.M[0][j] + c0.M[i][1] * t.M[1][j] + c0.M[i][2] * t.M[2][j] + c0.M[i][3] * t.M[3][j]; }
+                void translate(double x, double y, double z) { H t; t.M[3][0] = x; t.M[3][1] = y; t.M[3][2] = z; cat(t); }
+                void scale(double x, double y, double z) { H t; t.M[0][0] = x; t.M[1][1] = y; t.M[2][2] = z; cat(t); }
+                void rotateX(double co, double si) { H t; t.M[1][1] = co; t.M[2][2] = co; t.M[1][2] = -si; t.M[2][1] = si; cat(t); }
+                void rotateY(double co, double si) { H t; t.M[0][0] = co; t.M[2][2] = co; t.M[0][2] = -si; t.M[2][0] = si; cat(t); }
+                void rotateZ(double co, double si) { H t; t.M[0][0] = co; t.M[1][1] = co; t.M[0][1] = -si; t.M[1][0] = si; cat(t); }
+                void perspectiveZ(double f) { H t; t.M[2][3] = 1. / f; t.M[3][2] = -f; t.M[3][3] = 0.; cat(t); }
+            } T;
+            T.translate(-V.Ex, -V.Ey, -V.Ez);
+            double v = std::sqrt(b * b + c * c);
+            if (v > 0.3)
+            {
+                T.rotateX(c / v, -b / v); T.rotateY(v, -a);
+                const double k = (b * b + c * c) * Ux - a * b * Uy - a * c * Uz, l = c * Uy - b * Uz, u = std::sqrt(k * k + l * l);
+                T.rotateZ(l / u, -k / u);
+            }
+            else
+            {
+                v = std::sqrt(a * a + c * c);
+                T.rotateY(c / v, -a / v); T.rotateX(v, -b);
+                const double k = c * Ux - a * Uz, l = (a * a + c * c) * Uy - a * b * Ux - b * c * Uz, u = std::sqrt(k * k + l * l);
+                T.rotateZ(l / u, -k / u);
+            }
+            T.scale(1., 1., -1.);
+            T.perspectiveZ(Fe);
+            T.scale(1. / V.s, 1. / V.s, 1.);
+            T.translate(s.Nxp / 2., s.Nyp / 2., 0);
+            for (int i = 0; i < 4; i++) for (int j = 0; j < 4; j++) V.M[i][j] = T.M[i][j];
+            d.Nxp = s.Nxp; d.Nyp = s.Nyp; d.frames = nullptr; d.mfPixels = 0; d.mfTotal = d.mfComp0 = -1; d.mfNcomp = 0;
+            d.frameCount = (long long)s.Nxp * s.Nyp * e.med.Nlambda;
+            DevBuf* f = e.takeBuf(sizeof(double) * (size_t)d.frameCount); e.instrBufs.push_back(f);
+            f->ensure(sizeof(double) * (size_t)d.frameCount); SKG_CUDA(cudaMemsetAsync(f->p, 0, sizeof(double) * (size_t)d.frameCount, e.stream));
+            d.frame = f->as<double>(); V.frame = d.frame;
+            persp.push_back(V);
+            e.instr.push_back(d);
+            continue;
+        }
         if (s.kind == SKG_INSTR_FULL && (s.scatteringLevels < 0 || s.scatteringLevels > 1000)) throw Error("invalid number of scattering levels");
         if (s.distance <= 0) throw Error("Distance was not set");                    // DistantInstrument.cpp:32
         // DistantInstrument::setupSelfBefore, DistantInstrument.cpp:27-50
@@ -1184,8 +1270,11 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
     e.instrDev.upload(e.instr.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
     // observer groups: instruments with the same line of sight share one peel-off traversal per event
     std::vector<InstrDev> grouped; std::vector<ObsGroup> groups; std::vector<char> used(n, 0);
+    e.Npersp = (int)persp.size();
+    e.perspDev.upload(persp.data(), sizeof(PerspDev) * std::max<size_t>(persp.size(), 1), e.stream);
     for (int i = 0; i < n; i++)
     {
+        if (e.instr[i].kind == SKG_INSTR_PERSPECTIVE) used[i] = 1;       // not a line of sight: one ray per packet towards the eye
         if (used[i]) continue;
         ObsGroup g; g.kx = e.instr[i].kobsx; g.ky = e.instr[i].kobsy; g.kz = e.instr[i].kobsz; g.first = (int)grouped.size(); g.count = 0;
         for (int j = i; j < n; j++)
@@ -1322,6 +1411,16 @@ static void shootWavefront(Engine& e, const GridSetMC& G, McDev& P, unsigned lon
                        else peelStage<KIND, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2); }
             else if (single) peelStage<KIND, true, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
             else peelStage<KIND, false, false><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 2);
+            e.launches++;
+        }
+        if (P.Npersp > 0 && P.phase != SKG_PHASE_DUST_SELFABS)
+        {
+            // PerspectiveInstruments: one more peel-off ray per packet each, towards the eye
+            const int nb = blocksFor((long long)nAlive * P.Npersp);
+            if (pol) { if (single) peelStage<KIND, true, true, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 6);
+                       else peelStage<KIND, false, true, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 6); }
+            else if (single) peelStage<KIND, true, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 6);
+            else peelStage<KIND, false, false, true><<<nb, 128, smem, e.stream>>>(G, P, e.ctr(), cartSmem, nAlive, counts + 6);
             e.launches++;
         }
         SKG_CUDA(cudaEventRecord(ev[2], e.stream));
@@ -1551,6 +1650,8 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
     P.emissionBias = e.emissionBias;
     P.instr = e.instrGroupedDev.as<InstrDev>(); P.Ninstr = (int)e.instr.size();
     P.groups = e.groupsDev.as<ObsGroup>(); P.Ngroups = e.Ngroups; P.maxGroupCount = e.maxGroupCount;
+    P.persp = e.perspDev.as<PerspDev>(); P.Npersp = e.Npersp;
+    if (P.Npersp > 0 && p.continuousScattering) throw Error("continuous scattering with a PerspectiveInstrument is not supported");
     P.dustLv = e.dustLv.as<double>(); P.dustCdf = e.dustCdf.as<double>(); P.dustBias = dustBias;
     const bool store = phase == SKG_PHASE_STELLAR ? p.storeAbsorption != 0 : phase == SKG_PHASE_DUST_SELFABS;
     if (store)

@@ -177,6 +177,19 @@ void writeInstrument(const Instrument& ins, const WavelengthGrid& lg, const Unit
                      bool dustsystem, bool dustemission)
 {
     const skg_instrument d = ins.descriptor();
+    if (d.kind == SKG_INSTR_PERSPECTIVE)
+    {
+        // PerspectiveInstrument::write (PerspectiveInstrument.cpp:354-397): every sample times 1/(4 pi s^2) / dlambda, to output units
+        const double sp = d.fovxp / d.Nxp, front = 1. / (4. * M_PI * sp * sp);
+        const size_t Nf = (size_t)d.Nxp * d.Nyp;
+        if (ins.ftotv.size() != Nf * lg.Nlambda()) SKIRT_FATAL("the detector array of instrument " + ins.name + " has not been fetched");
+        std::vector<double> a = ins.ftotv;
+        for (int ell = 0; ell < lg.Nlambda(); ell++)
+            for (size_t l = 0; l < Nf; l++) a[l + Nf * ell] = units.osurfacebrightness(lg.lambda(ell), a[l + Nf * ell] * front / lg.dlambda(ell));
+        writeFITS(prefix + "_" + ins.name + "_total.fits", a, d.Nxp, d.Nyp, lg.Nlambda(), units.olength(sp), units.olength(sp), 0., 0.,
+                  units.usurfacebrightness(), units.ulength(), stamp);
+        return;
+    }
     if (const MultiFrameInstrument* mf = dynamic_cast<const MultiFrameInstrument*>(&ins))
     {
         // InstrumentFrame::calibrateAndWriteDataFrames (InstrumentFrame.cpp:216-262): per wavelength, every array divided by

@@ -406,7 +406,7 @@ void MonteCarloSimulation::fetchResults()
             idx++; continue;
         }
         if (d.kind != SKG_INSTR_SED) { i->ftotv.assign((size_t)d.Nxp * d.Nyp * Nl, 0.0); check(skg_fetch_frame(_engine, idx, i->ftotv.data(), 0)); }
-        if (d.kind != SKG_INSTR_FRAME) { i->Ftotv.assign(Nl, 0.0); check(skg_fetch_sed(_engine, idx, i->Ftotv.data(), 0)); }
+        if (d.kind != SKG_INSTR_FRAME && d.kind != SKG_INSTR_PERSPECTIVE) { i->Ftotv.assign(Nl, 0.0); check(skg_fetch_sed(_engine, idx, i->Ftotv.data(), 0)); }
         idx++;
     }
     if (_ds && _ds->storeabsorptionrates()) { _Labs.assign((size_t)_ds->Ncells() * Nl, 0.0); check(skg_fetch_labs(_engine, _Labs.data(), 0)); }

@@ -658,6 +658,18 @@ private:
     std::vector<skg_instrument_frame> _frames;
 };
 
+// PerspectiveInstrument (PerspectiveInstrument.cpp): a pinhole camera; setWidth is the viewport width (the pixels are square)
+class PerspectiveInstrument : public Instrument
+{
+public:
+    int kind() const override { return SKG_INSTR_PERSPECTIVE; }
+    void setWidth(double v) { d.fovxp = v; }
+    void setViewX(double v) { d.viewX = v; } void setViewY(double v) { d.viewY = v; } void setViewZ(double v) { d.viewZ = v; }
+    void setCrossX(double v) { d.crossX = v; } void setCrossY(double v) { d.crossY = v; } void setCrossZ(double v) { d.crossZ = v; }
+    void setUpX(double v) { d.upX = v; } void setUpY(double v) { d.upY = v; } void setUpZ(double v) { d.upZ = v; }
+    void setFocal(double v) { d.focal = v; }
+};
+
 class InstrumentSystem
 {
 public:

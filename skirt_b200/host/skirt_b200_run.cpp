@@ -166,6 +166,15 @@ int main(int argc, char** argv)
                 c->setGeometry(makeGeometry(in));
                 ss->addComponent(c);
             }
+            else if (key == "perspective")
+            {
+                // perspective <name> Nx Ny width Vx Vy Vz Cx Cy Cz Ux Uy Uz focal
+                std::string name; int nx, ny; double w, v[10]; in >> name >> nx >> ny >> w; for (double& q : v) in >> q;
+                auto* pi = new PerspectiveInstrument(); pi->setInstrumentName(name); pi->setPixelsX(nx); pi->setPixelsY(ny); pi->setWidth(w);
+                pi->setViewX(v[0]); pi->setViewY(v[1]); pi->setViewZ(v[2]); pi->setCrossX(v[3]); pi->setCrossY(v[4]); pi->setCrossZ(v[5]);
+                pi->setUpX(v[6]); pi->setUpY(v[7]); pi->setUpZ(v[8]); pi->setFocal(v[9]);
+                is->addInstrument(pi);
+            }
             else if (key == "instrument")
             {
                 std::string kind, name; double d, inc, az, pa; in >> kind >> name >> d >> inc >> az >> pa;

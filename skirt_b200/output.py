@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from .simulation import FatalError, INSTR_FRAME, INSTR_SED, INSTR_FULL, INSTR_MULTIFRAME
+from .simulation import FatalError, INSTR_FRAME, INSTR_SED, INSTR_FULL, INSTR_MULTIFRAME, INSTR_PERSPECTIVE
 
 _C = 2.99792458e8            # Units.cpp:17-22
 _AU = 1.49597871e11
@@ -308,6 +308,17 @@ def write_instruments(sim, results, outdir, prefix="", units=None, stamp=None):
                     write_fits(os.path.join(outdir, name), cal, fd["Nxp"], fd["Nyp"], 1, units.out("length", xpsiz), units.out("length", ypsiz),
                                fd["xpc"], fd["ypc"], units.unit("surfacebrightness"), units.unit("length"), stamp)
                     out[name] = cal
+            continue
+        if ins.kind == INSTR_PERSPECTIVE:
+            # PerspectiveInstrument::write (PerspectiveInstrument.cpp:354-397): every sample times 1/(4 pi s^2) / dlambda, to output units
+            sp = d["fovxp"] / d["Nxp"]
+            raw = np.array(results[ins.name + "_frame"], dtype=np.float64).reshape(lg.Nlambda, d["Nyp"], d["Nxp"])
+            front = 1.0 / (4.0 * math.pi * sp * sp)
+            cube = units.osurfacebrightness(lg.lambdav[:, None, None], raw * front / lg.dlambdav[:, None, None])
+            name = f"{prefix}{ins.name}_total.fits"
+            write_fits(os.path.join(outdir, name), cube, d["Nxp"], d["Nyp"], lg.Nlambda, units.out("length", sp), units.out("length", sp), 0.0, 0.0,
+                       units.unit("surfacebrightness"), units.unit("length"), stamp)
+            out[name] = cube
             continue
         if ins.kind != INSTR_SED:
             cube = calibrate_frames(results[ins.name + "_frame"], lg, d, units)

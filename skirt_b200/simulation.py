@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from .parallel import shard_packets
-from .binding import (Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, INSTR_MULTIFRAME, CHAN_LEVEL1,
+from .binding import (Engine, EngineError, GEOM_EXPDISK, GEOM_SERSIC, INSTR_FRAME, INSTR_SED, INSTR_SIMPLE, INSTR_FULL, INSTR_MULTIFRAME, INSTR_PERSPECTIVE, CHAN_LEVEL1,
                       REDUCE_LABS_STELLAR, REDUCE_LABS_DUST, REDUCE_INSTRUMENTS)
 
 PC = 3.08567758e16          # Units.cpp:17-30
@@ -654,6 +654,26 @@ class MultiFrameInstrument(_DistantInstrument):
         self.d.update(frames=[f.d for f in self.frames], writeTotal=bool(writeTotal), writeStellarComps=bool(writeStellarComps))
 
 
+class PerspectiveInstrument:
+    """PerspectiveInstrument (PerspectiveInstrument.cpp): a pinhole camera inside or near the model -- Nx x Ny square pixels over a
+    viewport of width `width` centred on `view`, looking at `cross`hair, `up` upwards, the eye `focal` behind the viewport."""
+    kind = INSTR_PERSPECTIVE
+
+    def __init__(self, instrumentName, pixelsX, pixelsY, width, viewX, viewY, viewZ, crossX, crossY, crossZ, upX, upY, upZ, focal):
+        if pixelsX <= 0 or pixelsY <= 0:
+            raise FatalError("Number of pixels was not set")
+        if width <= 0:
+            raise FatalError("Viewport width was not set")
+        if upX == 0 and upY == 0 and upZ == 0:
+            raise FatalError("Upwards direction was not set")
+        if focal <= 0:
+            raise FatalError("Focal length was not set")
+        self.name = instrumentName
+        self.d = dict(kind=self.kind, name=instrumentName, Nxp=int(pixelsX), Nyp=int(pixelsY), fovxp=float(width),
+                      viewX=float(viewX), viewY=float(viewY), viewZ=float(viewZ), crossX=float(crossX), crossY=float(crossY), crossZ=float(crossZ),
+                      upX=float(upX), upY=float(upY), upZ=float(upZ), focal=float(focal))
+
+
 class InstrumentSystem:
     def __init__(self, instruments):
         self.instruments = list(instruments)
@@ -824,7 +844,7 @@ class MonteCarloSimulation:
             if ins.kind != INSTR_SED:
                 n = ins.d["Nxp"] * ins.d["Nyp"] * Nl
                 out[ins.name + "_frame"] = self.engine.fetch_frame(i, dest(("f", i), (n,))).reshape(Nl, ins.d["Nyp"], ins.d["Nxp"])
-            if ins.kind != INSTR_FRAME:
+            if ins.kind not in (INSTR_FRAME, INSTR_PERSPECTIVE):
                 out[ins.name + "_sed"] = self.engine.fetch_sed(i, dest(("s", i), (Nl,)))
         if self.storeabs:
             out["Labs"] = self.engine.fetch_labs(dest("labs", (self.engine.Ncells, Nl)))
@@ -848,7 +868,7 @@ class MonteCarloSimulation:
         for i, ins in enumerate(self.isys.instruments):
             if ins.kind != INSTR_SED:
                 wanted.append(((ins.name + "_frame",), i + 1, 0))          # (a MultiFrameInstrument: all its slabs, flat)
-            if ins.kind not in (INSTR_FRAME, INSTR_MULTIFRAME):
+            if ins.kind not in (INSTR_FRAME, INSTR_MULTIFRAME, INSTR_PERSPECTIVE):
                 wanted.append(((ins.name + "_sed",), i + 1, 1))
         for (name,), which, part in wanted:
             n = e.fetch_snapshot_async(which, part, None)

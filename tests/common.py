@@ -240,6 +240,10 @@ def ref_spec(cfg):
     if cfg.get("ameshdust"):
         lines.append(f"ameshdust {cfg['ameshdust']!r}")
     for ins in cfg["instruments"]:
+        if ins["kind"] == 6:
+            lines.append(f"perspective {ins['name']} {ins['Nxp']} {ins['Nyp']} {ins['fovxp']!r} " +
+                         " ".join(repr(float(ins[k])) for k in ("viewX", "viewY", "viewZ", "crossX", "crossY", "crossZ", "upX", "upY", "upZ", "focal")))
+            continue
         kind = {1: "frame", 2: "sed", 3: "simple", 4: "full", 5: "multiframe"}[ins["kind"]]
         w = f"instrument {kind} {ins['name']} {ins['distance']!r} {ins['inclination']!r} {ins.get('azimuth', 0.0)!r} {ins.get('positionAngle', 0.0)!r}"
         if ins["kind"] == 5:

@@ -1,4 +1,5 @@
-"""GPU parity of MultiFrameInstrument (MultiFrameInstrument.cpp:85-99, InstrumentFrame.cpp:153-187): one frame per wavelength,
+"""GPU parity of the remaining instrument classes.  PerspectiveInstrument (PerspectiveInstrument.cpp:290-350): peel-off towards the eye
+of a pinhole camera, optical depth up to the viewport plane, perspective projection.  MultiFrameInstrument (MultiFrameInstrument.cpp:85-99, InstrumentFrame.cpp:153-187): one frame per wavelength,
 each with its own pixel grid, recording the total flux and the flux of every stellar component separately -- against runs of
 the reference's own MultiFrameInstrument (oracle/_ref), 16 batches on both sides through tests/common.mc_gate."""
 import os
@@ -75,3 +76,53 @@ def test_multiframe_instrument_errors_and_options(engine):
     assert a.shape == (12, 40) and a.sum() > 0 and b.sum() > 0
     with pytest.raises(EngineError, match="does not record this stellar component"):
         engine.fetch_multiframe(0, 2, 0)
+
+
+def _persp_cfg(threads):
+    cfg = common.cfg_c1(n=24, packages=1e5, tau=2.0, threads=threads)
+    cams = [dict(kind=6, name="outside", Nxp=32, Nyp=24, fovxp=16000 * PC, viewX=15000 * PC, viewY=4000 * PC, viewZ=6000 * PC,
+                 crossX=0.0, crossY=0.0, crossZ=0.0, upX=0.0, upY=0.0, upZ=1.0, focal=12000 * PC),
+            # a camera INSIDE the dusty disk looking along it: packets behind the viewport are ignored, the optical depth ends at its plane
+            dict(kind=6, name="inside", Nxp=24, Nyp=16, fovxp=3000 * PC, viewX=3000 * PC, viewY=500 * PC, viewZ=100 * PC,
+                 crossX=-2000 * PC, crossY=0.0, crossZ=0.0, upX=0.0, upY=0.0, upZ=1.0, focal=1500 * PC),
+            # looking straight down the z axis: the other branch of the rotation set-up (PerspectiveInstrument.cpp:77-87)
+            dict(kind=6, name="pole", Nxp=20, Nyp=20, fovxp=20000 * PC, viewX=0.0, viewY=0.0, viewZ=12000 * PC,
+                 crossX=0.0, crossY=0.0, crossZ=0.0, upX=0.0, upY=1.0, upZ=0.0, focal=9000 * PC)]
+    cfg["instruments"] = cams + [dict(kind=2, name="sed", distance=1e7 * PC, inclination=float(np.radians(60)))]
+    return cfg
+
+
+def test_perspective_instrument_against_reference_runs(engine):
+    from oracle import skirtref as sr
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    cfg = _persp_cfg(os.cpu_count() or 1)
+    S = common.make_ref(cfg).setup()
+    tables, medium, L = S.grid_tables(), S.medium(), S.luminosities()
+    common.setup_engine(engine, cfg, tables, medium, L)
+    Npp = S.packages_per_lambda()
+    B = 16
+    ref = {i: [] for i in range(4)}; gpu = {i: [] for i in range(4)}
+    for b in range(B):
+        S.reset(2300 + 1000 * b); S.run_stellar(); ins = S.instruments()
+        engine.reset_results(); engine.run_stellar(Npp, seed=160 + b)
+        for i in range(3):
+            ref[i].append(ins[i]["frame"].copy()); gpu[i].append(engine.fetch_frame(i).ravel())
+        ref[3].append(ins[3]["sed"].copy()); gpu[3].append(engine.fetch_sed(3))
+    for i, name in enumerate(("outside", "inside", "pole")):
+        assert gpu[i][0].size == ref[i][0].size and np.sum(gpu[i]) > 0
+        common.mc_gate(gpu[i], ref[i], f"perspective/{name}", min_bins=0.3)
+    common.mc_gate(gpu[3], ref[3], "perspective/sed")
+
+
+def test_perspective_instrument_errors(engine):
+    from skirt_b200.binding import EngineError
+    tables, medium, g = common.load_golden_mc()
+    cfg = _persp_cfg(1)
+    for change, msg in ((dict(fovxp=0.0), "Viewport width was not set"), (dict(upZ=0.0), "Upwards direction was not set"),
+                        (dict(focal=0.0), "Focal length was not set"), (dict(crossX=15000 * PC, crossY=4000 * PC, crossZ=6000 * PC), "Crosshair is too close")):
+        with pytest.raises(EngineError, match=msg):
+            common.setup_engine(engine, dict(cfg, instruments=[dict(cfg["instruments"][0], **change)]), tables, medium)
+    common.setup_engine(engine, dict(cfg, instruments=cfg["instruments"][:1]), tables, medium)
+    with pytest.raises(EngineError, match="continuous scattering with a PerspectiveInstrument"):
+        engine.run_stellar(1e3, seed=1, continuous_scattering=True)
