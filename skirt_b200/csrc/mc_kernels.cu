@@ -1267,11 +1267,11 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
         }
         e.instr.push_back(d);
     }
-    e.instrDev.upload(e.instr.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
+    if (n > 0) e.instrDev.upload(e.instr.data(), sizeof(InstrDev) * (size_t)n, e.stream);
     // observer groups: instruments with the same line of sight share one peel-off traversal per event
     std::vector<InstrDev> grouped; std::vector<ObsGroup> groups; std::vector<char> used(n, 0);
     e.Npersp = (int)persp.size();
-    e.perspDev.upload(persp.data(), sizeof(PerspDev) * std::max<size_t>(persp.size(), 1), e.stream);
+    if (!persp.empty()) { e.perspDev.upload(persp.data(), sizeof(PerspDev) * persp.size(), e.stream); SKG_CUDA(cudaStreamSynchronize(e.stream)); }     // (persp is a local)
     for (int i = 0; i < n; i++)
     {
         if (e.instr[i].kind == SKG_INSTR_PERSPECTIVE) used[i] = 1;       // not a line of sight: one ray per packet towards the eye
@@ -1285,8 +1285,8 @@ void mcSetInstruments(Engine& e, int n, const skg_instrument* instr)
     e.instrPol = e.med.Ntheta > 0;
     e.maxGroupCount = 0; for (const ObsGroup& g : groups) e.maxGroupCount = std::max(e.maxGroupCount, g.count);
     e.Ngroups = (int)groups.size(); e.instrNlambda = e.med.Nlambda; e.accInstr = Engine::ACC_ZERO;
-    e.instrGroupedDev.upload(grouped.data(), sizeof(InstrDev) * std::max(n, 1), e.stream);
-    e.groupsDev.upload(groups.data(), sizeof(ObsGroup) * std::max<size_t>(groups.size(), 1), e.stream);
+    if (!grouped.empty()) e.instrGroupedDev.upload(grouped.data(), sizeof(InstrDev) * grouped.size(), e.stream);
+    if (!groups.empty()) e.groupsDev.upload(groups.data(), sizeof(ObsGroup) * groups.size(), e.stream);
     e.sync();
 }
 
