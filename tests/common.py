@@ -336,8 +336,12 @@ def mc_gate(a, r, label, signal=0.15, min_bins=0.0, total_sigma=3.5, total_rel=0
     Ba, Br = len(a), len(r)
     assert Ba >= 16 and Br >= 16, f"{label}: the gate needs at least 16 batches on both sides ({Ba}, {Br})"
     ta, tr = a.sum(1), r.sum(1)
-    zt = (ta.mean() - tr.mean()) / np.sqrt(ta.var(ddof=1) / Ba + tr.var(ddof=1) / Br)
-    assert abs(zt) < total_sigma and (total_rel is None or abs(ta.mean() / tr.mean() - 1) < total_rel), \
+    st = np.sqrt(ta.var(ddof=1) / Ba + tr.var(ddof=1) / Br)
+    zt = (ta.mean() - tr.mean()) / st
+    # the relative bound applies as far as the statistics of the two batch sets resolve it: where 1 % is less than 2.5 sigma of
+    # the totals (small runs; the reference's threads draw different streams from run to run) the sigma gate alone decides
+    rel_bound = None if total_rel is None else max(total_rel, 2.5 * st / abs(tr.mean()))
+    assert abs(zt) < total_sigma and (rel_bound is None or abs(ta.mean() / tr.mean() - 1) < rel_bound), \
         f"{label}: totals differ by {zt:.2f} sigma (gpu {ta.mean():.6g}, reference {tr.mean():.6g})"
     if a.shape[1] < 2:
         return dict(zt=zt)
