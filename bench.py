@@ -372,6 +372,7 @@ def main_engine(args):
         e.sources(comps, Lum, sim.ss.emissionBias); e.instruments(instr)
         if pan_dust:
             sim.setup_dust_library(sim.ds.grid.volumes())
+        e.reset_results()               # every simulation of the series starts from empty accumulators (the previous snapshot is already taken)
         shoot()
         bufs = read_back(i & 1)
         if root:
