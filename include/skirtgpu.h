@@ -48,6 +48,16 @@ int skg_copy_to_host(skg_engine* e, const void* d_src, void* host, size_t bytes)
  * cell number m = k + Nz*j + Nz*Ny*i (CartesianDustGrid.cpp:326-329). */
 int skg_grid_cartesian(skg_engine* e, const double* xv, int Nx, const double* yv, int Ny, const double* zv, int Nz);
 
+/* The grids with symmetries.  Borders as the reference's setupSelfAfter leaves them:
+ *   Sphere1DDustGrid (Sphere1DDustGrid.cpp:24-33, path :111-186): rv[Nr+1] = mesh * maxR; cell m = i
+ *   Sphere2DDustGrid (Sphere2DDustGrid.cpp:27-75, path :230-345): rv[Nr+1], thetav[Ntheta+1] = mesh * pi and their cosines cv with
+ *       cv[0] = 1, cv[Ntheta] = -1 and exactly one border in the xy-plane (cv == 0; the reference inserts it when the mesh has
+ *       none); cell m = k + Ntheta*i
+ *   Cylinder2DDustGrid (Cylinder2DDustGrid.cpp:26-41, path :135-374): Rv[NR+1] = mesh * maxR, zv[Nz+1]; cell m = k + Nz*i */
+int skg_grid_sphere1d(skg_engine* e, int Nr, const double* rv);
+int skg_grid_sphere2d(skg_engine* e, int Nr, const double* rv, int Ntheta, const double* thetav, const double* cv);
+int skg_grid_cylinder2d(skg_engine* e, int NR, const double* Rv, int Nz, const double* zv);
+
 /* TreeDustGrid (TreeDustGrid.cpp:50-164): the node vector _tree flattened in id order.
  *   kind   : 0 OctTreeDustGrid, 1 BinTreeDustGrid
  *   search : 0 TopDown, 1 Neighbor, 2 Bookkeeping (TreeDustGrid.hpp:155; Bookkeeping is octree-only);

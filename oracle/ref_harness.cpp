@@ -45,6 +45,7 @@
 #include "DustSystem.hpp"
 #include "ExpDiskGeometry.hpp"
 #include "FaceOnDustCompNormalization.hpp"
+#include "DustMassDustCompNormalization.hpp"
 #include "FatalError.hpp"
 #include "FrameInstrument.hpp"
 #include "GeometricStellarComp.hpp"
@@ -58,6 +59,9 @@
 #include "PerspectiveInstrument.hpp"
 #include "InstrumentFrame.hpp"
 #include "OctTreeDustGrid.hpp"
+#include "Sphere1DDustGrid.hpp"
+#include "Sphere2DDustGrid.hpp"
+#include "Cylinder2DDustGrid.hpp"
 #include "ParticleTreeDustGrid.hpp"
 #include "DustParticleInterface.hpp"
 #include "OctTreeNode.hpp"
@@ -330,6 +334,26 @@ namespace
                     S->grid = g; S->gridKind = 3;
                 }
                 else if (kind == "amesh") { S->grid = new AdaptiveMeshDustGrid(); S->gridKind = 4; }
+                else if (kind == "sphere1d")
+                {
+                    double rmax; int n; in >> rmax >> n;            // grid sphere1d <maxR> <n> <mesh ...>
+                    Sphere1DDustGrid* g = new Sphere1DDustGrid(); g->setMaxR(rmax); g->setMeshR(makeMesh(in, n));
+                    S->grid = g; S->gridKind = 7;
+                }
+                else if (kind == "sphere2d")
+                {
+                    double rmax; int nr, nt; in >> rmax >> nr;      // grid sphere2d <maxR> <nr> <mesh ...> <ntheta> <mesh ...>
+                    Sphere2DDustGrid* g = new Sphere2DDustGrid(); g->setMaxR(rmax); g->setMeshR(makeMesh(in, nr));
+                    in >> nt; g->setMeshTheta(makeMesh(in, nt));
+                    S->grid = g; S->gridKind = 8;
+                }
+                else if (kind == "cylinder2d")
+                {
+                    double Rmax, zmin, zmax; int nR, nz; in >> Rmax >> zmin >> zmax >> nR;     // grid cylinder2d <maxR> <minZ> <maxZ> <nR> <mesh ...> <nz> <mesh ...>
+                    Cylinder2DDustGrid* g = new Cylinder2DDustGrid(); g->setMaxR(Rmax); g->setMinZ(zmin); g->setMaxZ(zmax); g->setMeshR(makeMesh(in, nR));
+                    in >> nz; g->setMeshZ(makeMesh(in, nz));
+                    S->grid = g; S->gridKind = 9;
+                }
                 else if (kind == "particletree")
                 {
                     // grid particletree <oct|bin> <extraLevels>; the particles come through skr_set_particles
@@ -358,6 +382,18 @@ namespace
                 DustComp* dc = new DustComp(); dc->setGeometry(g);
                 TableDustMix* mix = new TableDustMix(); dc->setMix(mix); S->mixes.push_back(mix);
                 FaceOnDustCompNormalization* nrm = new FaceOnDustCompNormalization(); nrm->setWavelength(lam); nrm->setOpticalDepth(tau);
+                dc->setNormalization(nrm);
+                S->cdd->insertComponent(S->cdd->components().size(), dc);
+            }
+            else if (key == "dustmass")
+            {
+                // dustmass <total dust mass> geometry...   (DustMassDustCompNormalization: works for any geometry, also spherical ones)
+                double mass; in >> mass;
+                Geometry* g = makeGeometry(S, in); g = maybeSpiral(g, in);
+                if (!S->cdd) S->cdd = new CompDustDistribution();
+                DustComp* dc = new DustComp(); dc->setGeometry(g);
+                TableDustMix* mix = new TableDustMix(); dc->setMix(mix); S->mixes.push_back(mix);
+                DustMassDustCompNormalization* nrm = new DustMassDustCompNormalization(); nrm->setDustMass(mass);
                 dc->setNormalization(nrm);
                 S->cdd->insertComponent(S->cdd->components().size(), dc);
             }
@@ -564,6 +600,26 @@ void skr_cart_dims(void* h, int* n) { CartesianDustGrid* g = (CartesianDustGrid*
 void skr_cart_axes(void* h, double* xv, double* yv, double* zv)
 { CartesianDustGrid* g = (CartesianDustGrid*)((Sim*)h)->grid;
   for (int i = 0; i <= g->_Nx; i++) xv[i] = g->_xv[i]; for (int i = 0; i <= g->_Ny; i++) yv[i] = g->_yv[i]; for (int i = 0; i <= g->_Nz; i++) zv[i] = g->_zv[i]; }
+
+// ---- grids with symmetries: the border arrays as setupSelfAfter left them ------------------------------
+// sizes[0] = bins along r / R, sizes[1] = bins along theta / z (0 for the 1D grid)
+void skr_sym_sizes(void* h, int* sizes)
+{
+    Sim* S = (Sim*)h; sizes[0] = sizes[1] = 0;
+    if (S->gridKind == 7) sizes[0] = ((Sphere1DDustGrid*)S->grid)->_Nr;
+    if (S->gridKind == 8) { Sphere2DDustGrid* g = (Sphere2DDustGrid*)S->grid; sizes[0] = g->_Nr; sizes[1] = g->_Ntheta; }
+    if (S->gridKind == 9) { Cylinder2DDustGrid* g = (Cylinder2DDustGrid*)S->grid; sizes[0] = g->_NR; sizes[1] = g->_Nz; }
+}
+void skr_sym_tables(void* h, double* v1, double* v2, double* cv)
+{
+    Sim* S = (Sim*)h;
+    if (S->gridKind == 7) { Sphere1DDustGrid* g = (Sphere1DDustGrid*)S->grid; for (int i = 0; i <= g->_Nr; i++) v1[i] = g->_rv[i]; }
+    if (S->gridKind == 8)
+    { Sphere2DDustGrid* g = (Sphere2DDustGrid*)S->grid; for (int i = 0; i <= g->_Nr; i++) v1[i] = g->_rv[i];
+      for (int k = 0; k <= g->_Ntheta; k++) { v2[k] = g->_thetav[k]; cv[k] = g->_cv[k]; } }
+    if (S->gridKind == 9)
+    { Cylinder2DDustGrid* g = (Cylinder2DDustGrid*)S->grid; for (int i = 0; i <= g->_NR; i++) v1[i] = g->_Rv[i]; for (int k = 0; k <= g->_Nz; k++) v2[k] = g->_zv[k]; }
+}
 
 // ---- tree -------------------------------------------------------------------------------------
 // the node vector, the cell numbers and eps of a TreeDustGrid or a ParticleTreeDustGrid

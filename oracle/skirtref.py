@@ -202,6 +202,15 @@ class RefSim:
                 t[key] = t[key][:nkd]
             t["nbrIds"] = t["nbrIds"][:nn]; t["blkIds"] = t["blkIds"][:nr]
             return t
+        if k in (7, 8, 9):
+            sizes = np.zeros(2, np.int32); L.skr_sym_sizes(self.h, vp(sizes))
+            v1 = np.zeros(sizes[0] + 1); v2 = np.zeros(sizes[1] + 1); cv = np.zeros(sizes[1] + 1)
+            L.skr_sym_tables(self.h, vp(v1), vp(v2), vp(cv))
+            if k == 7:
+                return dict(kind="sphere1d", rv=v1)
+            if k == 8:
+                return dict(kind="sphere2d", rv=v1, thetav=v2, cv=cv)
+            return dict(kind="cylinder2d", Rv=v1, zv=v2)
         raise RefError("no grid")
 
     def spec_value(self, key):

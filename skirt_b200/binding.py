@@ -181,6 +181,15 @@ class Engine:
             self.grid_amesh(t["box"], t["nxyz"], t["child0"], t["cell"], t["wallNbr"])
         elif kind == "voronoi":
             self.grid_voronoi(t)
+        elif kind == "sphere1d":
+            rv = _f64(t["rv"]); self._keep = (rv,)
+            self._chk(self._lib.skg_grid_sphere1d(self.h, len(rv) - 1, _vp(rv)))
+        elif kind == "sphere2d":
+            rv, th, cv = _f64(t["rv"]), _f64(t["thetav"]), _f64(t["cv"]); self._keep = (rv, th, cv)
+            self._chk(self._lib.skg_grid_sphere2d(self.h, len(rv) - 1, _vp(rv), len(th) - 1, _vp(th), _vp(cv)))
+        elif kind == "cylinder2d":
+            Rv, zv = _f64(t["Rv"]), _f64(t["zv"]); self._keep = (Rv, zv)
+            self._chk(self._lib.skg_grid_cylinder2d(self.h, len(Rv) - 1, _vp(Rv), len(zv) - 1, _vp(zv)))
         else:
             raise EngineError(f"unknown grid kind {kind}")
 

@@ -181,6 +181,55 @@ int skg_grid_cartesian(skg_engine* eh, const double* xv, int Nx, const double* y
     });
 }
 
+// ---- grids with symmetries ------------------------------------------------------------------------------------------------
+static void checkBorders(const double* v, int n, const char* what)
+{
+    if (!v || n < 1) throw Error(std::string("grid borders missing: ") + what);
+    for (int i = 0; i < n; i++) if (!(v[i + 1] > v[i])) throw Error(std::string("grid borders must increase: ") + what);
+}
+int skg_grid_sphere1d(skg_engine* eh, int Nr, const double* rv)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        checkBorders(rv, Nr, "radial");
+        if (!(rv[Nr] > 0)) throw Error("The outer radius of the grid should be positive");       // SphereDustGrid.cpp:21-26
+        e.freeGrid();
+        e.sym = SymGrid{}; e.sym.sub = 0; e.sym.N1 = Nr; e.sym.N2 = 0; e.sym.v1 = up(e, rv, Nr + 1); e.sym.rmax = rv[Nr];
+        e.gridKind = GRID_SYM; e.Ncells = Nr;
+        e.sync();
+    });
+}
+int skg_grid_sphere2d(skg_engine* eh, int Nr, const double* rv, int Ntheta, const double* thetav, const double* cv)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        checkBorders(rv, Nr, "radial"); checkBorders(thetav, Ntheta, "polar");
+        if (!cv) throw Error("grid borders missing: cosines of the polar borders");
+        if (!(rv[Nr] > 0)) throw Error("The outer radius of the grid should be positive");
+        // Sphere2DDustGrid::path needs a border in the xy-plane (Sphere2DDustGrid.cpp:39-72 inserts one when the mesh has none)
+        int zeros = 0; for (int k = 1; k < Ntheta; k++) if (cv[k] == 0.0) zeros++;
+        if (zeros != 1) throw Error("the polar borders need exactly one grid point at pi/2 (cosine exactly 0)");
+        e.freeGrid();
+        e.sym = SymGrid{}; e.sym.sub = 1; e.sym.N1 = Nr; e.sym.N2 = Ntheta; e.sym.v1 = up(e, rv, Nr + 1); e.sym.v2 = up(e, thetav, Ntheta + 1);
+        e.sym.cv = up(e, cv, Ntheta + 1); e.sym.rmax = rv[Nr];
+        e.gridKind = GRID_SYM; e.Ncells = Nr * Ntheta;
+        e.sync();
+    });
+}
+int skg_grid_cylinder2d(skg_engine* eh, int NR, const double* Rv, int Nz, const double* zv)
+{
+    return guarded([&]{
+        Engine& e = E(eh);
+        checkBorders(Rv, NR, "radial"); checkBorders(zv, Nz, "vertical");
+        if (!(Rv[NR] > 0)) throw Error("The outer radius of the grid should be positive");       // CylinderDustGrid.cpp
+        e.freeGrid();
+        e.sym = SymGrid{}; e.sym.sub = 2; e.sym.N1 = NR; e.sym.N2 = Nz; e.sym.v1 = up(e, Rv, NR + 1); e.sym.v2 = up(e, zv, Nz + 1);
+        e.sym.rmax = Rv[NR]; e.sym.zmin = zv[0]; e.sym.zmax = zv[Nz];
+        e.gridKind = GRID_SYM; e.Ncells = NR * Nz;
+        e.sync();
+    });
+}
+
 int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box, const int* child0,
                   const int* parent, const int* cell, const int* dir, const int* nbrStart, const int* nbrIds)
 {

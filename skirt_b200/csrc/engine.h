@@ -69,7 +69,7 @@ struct Engine
     int smCount = 148;
 
     int gridKind = GRID_NONE;
-    CartGrid cart{}; TreeGrid tree{}; AMeshGrid amesh{}; VoroGrid voro{};
+    CartGrid cart{}; TreeGrid tree{}; AMeshGrid amesh{}; VoroGrid voro{}; SymGrid sym{};
     int Ncells = 0;
     std::vector<DevBuf*> gridBufs;
     // device arrays of replaced tables are kept for the next upload of that size: a series of simulations re-uploads its

@@ -1137,4 +1137,256 @@ template<bool EXACT> struct VoroWalkerT
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------------
+// Grids with symmetries: Sphere1DDustGrid, Sphere2DDustGrid, Cylinder2DDustGrid
+// ---------------------------------------------------------------------------------------------------
+// Sphere2DDustGrid.cpp:175-226: smallest positive solution of x^2 + 2 b x + c = 0 (0: none) and friends
+__device__ __forceinline__ double symSmallestPositive(double b, double c)
+{
+    if (b * b > c)
+    {
+        if (b > 0) { if (c < 0) { double x1 = -b - sqrt(b * b - c); return c / x1; } }
+        else
+        {
+            double x2 = -b + sqrt(b * b - c);
+            if (c > 0) { double x1 = c / x2; if (x1 < x2) return x1; }
+            return x2;
+        }
+    }
+    return 0;
+}
+__device__ __forceinline__ double symSmallestPositive(double a, double b, double c)
+{
+    if (fabs(a) > 1e-9) return symSmallestPositive(b / a, c / a);
+    double x = -0.5 * c / b;
+    if (x > 0) return x;
+    return 0;
+}
+__device__ __forceinline__ double symFirstSphere(double x, double y, double z, double kx, double ky, double kz, double r)
+{ return symSmallestPositive(x * kx + y * ky + z * kz, (x * x + y * y + z * z) - r * r); }            // Vec::dot, Vec::norm2 (Vec.hpp)
+__device__ __forceinline__ double symFirstCone(double x, double y, double z, double kx, double ky, double kz, double c)
+{
+    if (c == 0) return -z / kz;
+    const double rk = x * kx + y * ky + z * kz, r2 = x * x + y * y + z * z;
+    return symSmallestPositive(c * c - kz * kz, c * c * rk - z * kz, c * c * r2 - z * z);
+}
+// Position::spherical, Position.cpp:91-106 (r and theta only)
+__device__ __forceinline__ void symSpherical(double x, double y, double z, double& r, double& theta)
+{
+    r = sqrt(x * x + y * y + z * z);
+    theta = r == 0 ? 0.0 : acos(z / r);
+}
+__device__ __forceinline__ int symWhichCell(const SymGrid& g, double x, double y, double z)
+{
+    if (g.sub == 0) return locateFail(g.v1, sqrt(x * x + y * y + z * z), g.N1 + 1);                    // Sphere1DDustGrid.cpp:81-84
+    if (g.sub == 1)                                                                                     // Sphere2DDustGrid.cpp:133-141
+    {
+        double r, theta; symSpherical(x, y, z, r, theta);
+        int i = locateFail(g.v1, r, g.N1 + 1); if (i < 0) return -1;
+        return locateClip(g.v2, theta, g.N2 + 1) + g.N2 * i;
+    }
+    int i = locateFail(g.v1, sqrt(x * x + y * y), g.N1 + 1), k = locateFail(g.v2, z, g.N2 + 1);         // Cylinder2DDustGrid.cpp:95-101
+    if (i < 0 || k < 0) return -1;
+    return k + g.N2 * i;
+}
+
+// The three path() bodies as state machines that yield one segment per step.
+//   Sphere1DDustGrid::path  Sphere1DDustGrid.cpp:111-186 (phase 0: inward towards the impact shell, phase 1: outward)
+//   Cylinder2DDustGrid::path Cylinder2DDustGrid.cpp:135-374 (the same two phases, upward or downward in z)
+//   Sphere2DDustGrid::path  Sphere2DDustGrid.cpp:230-345 (position-based: nearest of up to four cell boundaries)
+struct SymWalker
+{
+    static constexpr bool kPredicated = false;
+    static constexpr int kStepUnroll = 1;
+    double x, y, z, kx, ky, kz;     // Sphere2D: current position and direction; Cylinder2D: z and kz are the running height / its cosine
+    double p, q, qN, zN, kq;        // impact parameter, running and next radial path coordinates (Sphere1D, Cylinder2D); next z border
+    int i, k, imin; int phase;      // cell indices; phase 0 inward, 1 outward
+    bool alive;
+
+    __device__ __forceinline__ int locator() const { return -1; }
+
+    __device__ __forceinline__ bool start(const SymGrid& g, Counters*, double x0, double y0, double z0, double kx0, double ky0, double kz0, Entry& en, int = -1)
+    {
+        alive = false; en.n = 0;
+        x = x0; y = y0; z = z0; kx = kx0; ky = ky0; kz = kz0;
+        if (g.sub == 0)
+        {
+            const double rmax = g.rmax;
+            double r = sqrt(x * x + y * y + z * z);                 // Position::radius() = Vec::norm()
+            q = x * kx + y * ky + z * kz;
+            p = sqrt((r - q) * (r + q));
+            if (r > rmax)
+            {
+                if (q > 0.0 || p > rmax) return false;
+                r = rmax - 1e-8 * (g.v1[g.N1] - g.v1[g.N1 - 1]);
+                const double qmax = sqrt((rmax - p) * (rmax + p));
+                en.ds[en.n++] = qmax - q;
+                q = qmax;
+            }
+            i = locateClip(g.v1, r, g.N1 + 1);
+            phase = 1;
+            if (q < 0.0)
+            {
+                imin = locateClip(g.v1, p, g.N1 + 1);
+                const double rN = g.v1[i];
+                qN = -sqrt((rN - p) * (rN + p));
+                phase = i > imin ? 0 : 1;
+            }
+            if (phase == 1) { const double rN = g.v1[i + 1]; qN = sqrt((rN - p) * (rN + p)); }
+            alive = true;
+            return true;
+        }
+        if (g.sub == 2)
+        {
+            kq = sqrt(kx * kx + ky * ky);
+            if (kz == 0.0) kz = 1e-20;
+            if (kq == 0.0) kq = 1e-20;
+            double R = sqrt(x * x + y * y);                          // Position::cylradius()
+            q = (x * kx + y * ky) / kq;
+            const double p2 = (R - q) * (R + q);
+            p = sqrt(fmax(0.0, p2));
+            const double Rmax = g.rmax, zmin = g.zmin, zmax = g.zmax;
+            if (R >= Rmax)
+            {
+                if (q > 0.0 || p > Rmax) return false;
+                R = Rmax - 1e-8 * (g.v1[g.N1] - g.v1[g.N1 - 1]);
+                const double qmax = sqrt((Rmax - p) * (Rmax + p));
+                const double ds = (qmax - q) / kq;
+                en.ds[en.n++] = ds;
+                q = qmax;
+                z += kz * ds;
+            }
+            if (z < zmin)
+            {
+                if (kz <= 0.0) { en.n = 0; return false; }
+                const double ds = (zmin - z) / kz;
+                en.ds[en.n++] = ds;
+                q += kq * ds;
+                R = sqrt(p * p + q * q);
+                z = zmin + 1e-8 * (g.v2[1] - g.v2[0]);
+            }
+            else if (z > zmax)
+            {
+                if (kz >= 0.0) { en.n = 0; return false; }
+                const double ds = (zmax - z) / kz;
+                en.ds[en.n++] = ds;
+                q += kq * ds;
+                R = sqrt(p * p + q * q);
+                z = zmax - 1e-8 * (g.v2[g.N2] - g.v2[g.N2 - 1]);
+            }
+            if (isinf(R) || isnan(R) || isinf(z) || isnan(z) || R >= Rmax || z <= zmin || z >= zmax) { en.n = 0; return false; }
+            i = locateClip(g.v1, R, g.N1 + 1);
+            k = locateClip(g.v2, z, g.N2 + 1);
+            const bool up = kz >= 0.0;
+            zN = up ? g.v2[k + 1] : g.v2[k];
+            phase = 1;
+            if (q < 0.0)
+            {
+                imin = locateClip(g.v1, p, g.N1 + 1);
+                const double RN = g.v1[i];
+                qN = -sqrt((RN - p) * (RN + p));
+                phase = i > imin ? 0 : 1;
+            }
+            if (phase == 1) { const double RN = g.v1[i + 1]; qN = sqrt((RN - p) * (RN + p)); }
+            alive = true;
+            return true;
+        }
+        // Sphere2D
+        const double rmax = g.rmax, eps = 1e-11 * rmax;
+        const double r2 = x * x + y * y + z * z;
+        if (r2 > rmax * rmax)
+        {
+            const double ds = symFirstSphere(x, y, z, kx, ky, kz, rmax);
+            if (!(ds != 0)) return false;
+            en.ds[en.n++] = ds;
+            x += kx * (ds + eps); y += ky * (ds + eps); z += kz * (ds + eps);
+        }
+        else if (r2 == 0) { x += kx * eps; y += ky * eps; z += kz * eps; }
+        double r, theta; symSpherical(x, y, z, r, theta);
+        i = locateFail(g.v1, r, g.N1 + 1);
+        k = locateClip(g.v2, theta, g.N2 + 1);
+        alive = i < g.N1 && i >= 0;
+        return true;
+    }
+
+    __device__ __forceinline__ bool step(const SymGrid& g, Counters* ctr, int& mseg, double& ds)
+    {
+        if (g.sub == 0)
+        {
+            mseg = i; ds = qN - q;
+            if (phase == 0)
+            {
+                i--; q = qN;
+                const double rN = g.v1[i];
+                qN = -sqrt((rN - p) * (rN + p));
+                if (!(i > imin)) { phase = 1; const double rO = g.v1[i + 1]; qN = sqrt((rO - p) * (rO + p)); }
+            }
+            else
+            {
+                i++;
+                if (i >= g.N1 - 1) alive = false;           // (the reference never enters the outermost shell on the way out, Sphere1DDustGrid.cpp:178)
+                else { q = qN; const double rN = g.v1[i + 1]; qN = sqrt((rN - p) * (rN + p)); }
+            }
+            return ds > 0;                                  // DustGridPath::addSegment keeps only segments with ds > 0
+        }
+        if (g.sub == 2)
+        {
+            const bool up = kz >= 0.0;
+            mseg = k + g.N2 * i;
+            const double dsq = (qN - q) / kq, dsz = (zN - z) / kz;
+            if (dsq < dsz)
+            {
+                ds = dsq;
+                if (phase == 0)
+                {
+                    i--; q = qN; z += kz * ds;
+                    const double RN = g.v1[i];
+                    qN = -sqrt((RN - p) * (RN + p));
+                    if (!(i > imin)) { phase = 1; const double RO = g.v1[i + 1]; qN = sqrt((RO - p) * (RO + p)); }
+                }
+                else
+                {
+                    i++;
+                    if (i >= (up ? g.N1 : g.N1 - 1)) alive = false;     // (:258 upward, :353 downward: the reference's own asymmetry)
+                    else { q = qN; z += kz * ds; const double RN = g.v1[i + 1]; qN = sqrt((RN - p) * (RN + p)); }
+                }
+            }
+            else
+            {
+                ds = dsz;
+                if (up) { k++; if (k >= g.N2) alive = false; else { q += kq * ds; z = zN; zN = g.v2[k + 1]; } }
+                else { k--; if (k < 0) alive = false; else { q += kq * ds; z = zN; zN = g.v2[k]; } }
+            }
+            return ds > 0;
+        }
+        // Sphere2D
+        const double eps = 1e-11 * g.rmax;
+        int inext = i, knext = k;
+        ds = SKG_DBL_MAX;
+        if (i > 0) { const double s = symFirstSphere(x, y, z, kx, ky, kz, g.v1[i]); if (s > 0 && s < ds) { ds = s; inext = i - 1; knext = k; } }
+        { const double s = symFirstSphere(x, y, z, kx, ky, kz, g.v1[i + 1]); if (s > 0 && s < ds) { ds = s; inext = i + 1; knext = k; } }
+        if (k > 0) { const double s = symFirstCone(x, y, z, kx, ky, kz, g.cv[k]); if (s > 0 && s < ds) { ds = s; inext = i; knext = k - 1; } }
+        if (k < g.N2 - 1) { const double s = symFirstCone(x, y, z, kx, ky, kz, g.cv[k + 1]); if (s > 0 && s < ds) { ds = s; inext = i; knext = k + 1; } }
+        bool seg = false;
+        if (inext != i || knext != k)
+        {
+            mseg = k + g.N2 * i; seg = ds > 0;
+            x += kx * (ds + eps); y += ky * (ds + eps); z += kz * (ds + eps);
+            i = inext; k = knext;
+        }
+        else
+        {
+            // "No exit point found from dust grid cell" (:333-342): move a tiny bit along the path and locate again
+            atomicAdd(&ctr->stuckEscaped, 1ull);
+            x += kx * eps; y += ky * eps; z += kz * eps;
+            double r, theta; symSpherical(x, y, z, r, theta);
+            i = locateFail(g.v1, r, g.N1 + 1);
+            k = locateClip(g.v2, theta, g.N2 + 1);
+        }
+        alive = i < g.N1 && i >= 0;
+        return seg;
+    }
+};
+
 }   // namespace skg

@@ -14,7 +14,7 @@
 namespace skg
 {
 
-struct GridSetMC { CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro; };
+struct GridSetMC { CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro; SymGrid sym; };
 
 // Packet pool: one 96-byte record per in-flight photon packet (PhotonPackage, PhotonPackage.hpp:28,134-138;
 // unpolarised: position, direction, luminosity, wavelength index, number of scatterings) plus the engine's own
@@ -503,6 +503,7 @@ __device__ __forceinline__ int whichCellMC(const GridSetMC& G, const CartGrid& c
     if (KIND == GRID_CART) return cartWhichCell(cart, x, y, z);
     else if (KIND == GRID_TREE) { int node = treeWhichNode(G.tree, x, y, z); return node >= 0 ? G.tree.cell[node] : -1; }
     else if (KIND == GRID_AMESH) { int node = ameshWhichNode(G.amesh, x, y, z); return node >= 0 ? G.amesh.cell[node] : -1; }
+    else if (KIND == GRID_SYM) return symWhichCell(G.sym, x, y, z);
     else return voroCellIndex(G.voro, x, y, z);
 }
 

@@ -141,6 +141,35 @@ template<int KIND>
 __device__ __forceinline__ bool randomPositionInCell(const GridSetMC& G, int m, Philox& rng, double& x, double& y, double& z)
 {
     double b[6];
+    if (KIND == GRID_SYM)
+    {
+        const SymGrid& g = G.sym;
+        if (g.sub == 0)
+        {
+            // Sphere1DDustGrid::randomPositionInCell, Sphere1DDustGrid.cpp:99-105: a random direction, then the radius
+            double dx, dy, dz; randomDirection(rng, dx, dy, dz);
+            const double r = g.v1[m] + (g.v1[m + 1] - g.v1[m]) * rng.uniform();
+            x = r * dx; y = r * dy; z = r * dz;
+            return true;
+        }
+        const int i = m / g.N2, k = m % g.N2;
+        if (g.sub == 1)
+        {
+            // Sphere2DDustGrid::randomPositionInCell, Sphere2DDustGrid.cpp:157-167
+            const double ris = g.v1[i] * g.v1[i], ri1s = g.v1[i + 1] * g.v1[i + 1];
+            const double r = sqrt(ris + (ri1s - ris) * rng.uniform());
+            const double theta = g.v2[k] + (g.v2[k + 1] - g.v2[k]) * rng.uniform();
+            const double phi = 2.0 * M_PI * rng.uniform();
+            x = r * sin(theta) * cos(phi); y = r * sin(theta) * sin(phi); z = r * cos(theta);
+            return true;
+        }
+        // Cylinder2DDustGrid::randomPositionInCell, Cylinder2DDustGrid.cpp:120-128
+        const double Rr = g.v1[i] + (g.v1[i + 1] - g.v1[i]) * rng.uniform();
+        const double phi = 2.0 * M_PI * rng.uniform();
+        z = g.v2[k] + (g.v2[k + 1] - g.v2[k]) * rng.uniform();
+        x = Rr * cos(phi); y = Rr * sin(phi);
+        return true;
+    }
     if (KIND == GRID_CART)
     {
         const CartGrid& g = G.cart;
@@ -563,6 +592,7 @@ template<> struct WalkerOf<GRID_CART> { typedef CartFastWalkerT<false> type; };
 template<> struct WalkerOf<GRID_TREE> { typedef TreeWalkerT<SKG_TREE_HINTS_MC> type; };
 template<> struct WalkerOf<GRID_AMESH> { typedef AMeshWalker type; };
 template<> struct WalkerOf<GRID_VORO> { typedef VoroWalkerT<false> type; };
+template<> struct WalkerOf<GRID_SYM> { typedef SymWalker type; };
 
 template<int KIND, bool SINGLE, bool POL> struct ContPeelJob
 {
@@ -650,6 +680,7 @@ template<int KIND, bool SINGLE, bool POL> struct ContPeelJob
                 if constexpr (KIND == GRID_CART) ok = w2.start(cart, ctr, px, py, pz, g.kx, g.ky, g.kz, en, -1);
                 else if constexpr (KIND == GRID_TREE) ok = w2.start(G.tree, ctr, px, py, pz, g.kx, g.ky, g.kz, en, loc);
                 else if constexpr (KIND == GRID_AMESH) ok = w2.start(G.amesh, ctr, px, py, pz, g.kx, g.ky, g.kz, en, loc);
+                else if constexpr (KIND == GRID_SYM) ok = w2.start(G.sym, ctr, px, py, pz, g.kx, g.ky, g.kz, en, -1);
                 else ok = w2.start(G.voro, ctr, px, py, pz, g.kx, g.ky, g.kz, en, loc);
                 if (ok)
                 {
@@ -660,6 +691,7 @@ template<int KIND, bool SINGLE, bool POL> struct ContPeelJob
                         if constexpr (KIND == GRID_CART) seg = w2.step(cart, ctr, m2, ds2);
                         else if constexpr (KIND == GRID_TREE) seg = w2.step(G.tree, ctr, m2, ds2);
                         else if constexpr (KIND == GRID_AMESH) seg = w2.step(G.amesh, ctr, m2, ds2);
+                        else if constexpr (KIND == GRID_SYM) seg = w2.step(G.sym, ctr, m2, ds2);
                         else seg = w2.step(G.voro, ctr, m2, ds2);
                         if (seg) { nSeg++; tau2 += KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda}(m2) * ds2; }
                     }
@@ -1720,13 +1752,14 @@ static void runPhase(Engine& e, const skg_mc_params& p, int phase, double dustBi
                 e.attrStages = true;
             }
         }
-        GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro;
+        GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro; G.sym = e.sym;
         switch (e.gridKind)
         {
         case GRID_CART: shootWavefront<GRID_CART>(e, G, P, total, pool, smem, cartSmem); break;
         case GRID_TREE: shootWavefront<GRID_TREE>(e, G, P, total, pool, 0, false); break;
         case GRID_AMESH: shootWavefront<GRID_AMESH>(e, G, P, total, pool, 0, false); break;
         case GRID_VORO: shootWavefront<GRID_VORO>(e, G, P, total, pool, 0, false); break;
+        case GRID_SYM: shootWavefront<GRID_SYM>(e, G, P, total, pool, 0, false); break;
         default:
             if (e.med.rho || phase != SKG_PHASE_STELLAR) throw Error("no dust grid has been set");
             shootWavefront<GRID_CART>(e, G, P, total, pool, 0, false);      // no dust: only launch + emission peel-off run
@@ -1817,12 +1850,12 @@ void mcSampleDensity(Engine& e, int Ncomp, const skg_source* geoms, const double
         for (int h = 0; h < Ncomp; h++) dev.push_back(makeSourceDev(e, geoms[h], bufs, true));
         devGeoms.upload(dev.data(), sizeof(SourceDev) * Ncomp, e.stream); devNorm.upload(norm, sizeof(double) * Ncomp, e.stream);
         devRho.ensure(sizeof(double) * (size_t)e.Ncells * Ncomp);
-        GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro;
+        GridSetMC G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro; G.sym = e.sym;
         Counters before = e.readCounters();
         int blocks = std::max(1, std::min((e.Ncells + 127) / 128, e.smCount * 16));
 #define SKG_DENS(K) sampleDensityKernel<K><<<blocks, 128, 0, e.stream>>>(G, devGeoms.as<SourceDev>(), devNorm.as<double>(), e.Ncells, Ncomp, sampleCount, seed, devRho.as<double>(), e.ctr())
         switch (e.gridKind) { case GRID_CART: SKG_DENS(GRID_CART); break; case GRID_TREE: SKG_DENS(GRID_TREE); break;
-                              case GRID_AMESH: SKG_DENS(GRID_AMESH); break; default: SKG_DENS(GRID_VORO); }
+                              case GRID_AMESH: SKG_DENS(GRID_AMESH); break; case GRID_SYM: SKG_DENS(GRID_SYM); break; default: SKG_DENS(GRID_VORO); }
         e.launches++; SKG_CUDA(cudaGetLastError());
         SKG_CUDA(cudaMemcpyAsync(rho, devRho.p, sizeof(double) * (size_t)e.Ncells * Ncomp, cudaMemcpyDeviceToHost, e.stream));
         e.sync();

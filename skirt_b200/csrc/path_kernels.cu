@@ -14,7 +14,7 @@ namespace skg
 
 struct GridSet
 {
-    CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro;
+    CartGrid cart; TreeGrid tree; AMeshGrid amesh; VoroGrid voro; SymGrid sym;
 };
 
 // ---- jobs (see wavefront.cuh) ---------------------------------------------------------------------------
@@ -311,13 +311,14 @@ __global__ void __launch_bounds__(128) whichCellKernel(const __grid_constant__ G
         if (KIND == GRID_CART) res = cartWhichCell(G.cart, x, y, z);
         else if (KIND == GRID_TREE) { int node = treeWhichNode(G.tree, x, y, z); res = node >= 0 ? G.tree.cell[node] : -1; }
         else if (KIND == GRID_AMESH) { int node = ameshWhichNode(G.amesh, x, y, z); res = node >= 0 ? G.amesh.cell[node] : -1; }
+        else if (KIND == GRID_SYM) res = symWhichCell(G.sym, x, y, z);
         else res = voroCellIndex(G.voro, x, y, z);
         m[i] = res;
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-static GridSet gridSet(const Engine& e) { GridSet G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro; return G; }
+static GridSet gridSet(const Engine& e) { GridSet G; G.cart = e.cart; G.tree = e.tree; G.amesh = e.amesh; G.voro = e.voro; G.sym = e.sym; return G; }
 
 struct LaunchCfg { int blocks; size_t smem; bool cartSmem; int* work; int refill; };
 static LaunchCfg cfgFor(Engine& e, int64_t n)
@@ -357,6 +358,7 @@ static LaunchCfg cfgFor(Engine& e, int64_t n)
     case GRID_TREE:  { constexpr int K = GRID_TREE;  CALL; break; } \
     case GRID_AMESH: { constexpr int K = GRID_AMESH; CALL; break; } \
     case GRID_VORO:  { constexpr int K = GRID_VORO;  CALL; break; } \
+    case GRID_SYM:   { constexpr int K = GRID_SYM;   CALL; break; } \
     default: throw Error("no dust grid has been set"); }
 
 void launchPathCount(Engine& e, int64_t n, const double* d_r, const double* d_k, int* d_counts)
@@ -382,6 +384,7 @@ void launchPathFill(Engine& e, int64_t n, const double* d_r, const double* d_k, 
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_TREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_AMESH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_VORO>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
         if (const char* cv = getenv("SKG_FILL_CARVEOUT")) SKG_CUDA(cudaFuncSetAttribute(pathFillKernel<GRID_CART>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
         e.attrFill = true;
     }

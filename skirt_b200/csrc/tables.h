@@ -6,7 +6,7 @@
 namespace skg
 {
 
-enum GridKind { GRID_NONE = -1, GRID_CART = 0, GRID_TREE = 1, GRID_AMESH = 2, GRID_VORO = 3 };
+enum GridKind { GRID_NONE = -1, GRID_CART = 0, GRID_TREE = 1, GRID_AMESH = 2, GRID_VORO = 3, GRID_SYM = 4 };
 
 struct CartGrid
 {
@@ -71,6 +71,15 @@ struct AMeshGrid
     const int* cellNode;            // leaf node of every cell
     int N;
     double eps;
+};
+
+// The grids with symmetries: Sphere1DDustGrid (sub 0: radial borders rv), Sphere2DDustGrid (sub 1: rv and polar borders thetav with
+// their cosines cv, the xy-plane among them) and Cylinder2DDustGrid (sub 2: radial borders Rv in v1, vertical borders zv in v2)
+struct SymGrid
+{
+    int sub; int N1, N2;            // bins along the first (r / R) and second (theta / z; 0 for sub 0) coordinate
+    const double* v1; const double* v2; const double* cv;
+    double rmax, zmin, zmax;
 };
 
 struct VoroGrid

@@ -165,6 +165,7 @@ __device__ __forceinline__ void runJobs(const Grids& G, const CartGrid& cart, Co
     }
     else if (KIND == GRID_TREE) runJobsStep<TreeWalkerT<Job::kTreeHints>>(G.tree, ctr, job, n, workCounter, refill);
     else if (KIND == GRID_AMESH) runJobsStep<AMeshWalker>(G.amesh, ctr, job, n, workCounter, refill);
+    else if (KIND == GRID_SYM) runJobsStep<SymWalker>(G.sym, ctr, job, n, workCounter, refill);
 #ifdef SKG_VORO_MC_EXACT
     else runJobsStep<VoroWalkerT<true>>(G.voro, ctr, job, n, workCounter, refill);                   // experiment: exact walker everywhere
 #else

@@ -71,6 +71,20 @@ class LinMesh:
         return np.array([0.0 + i * ((1.0 - 0.0) / n) for i in range(n + 1)])
 
 
+class PowMesh:
+    """PowMesh (PowMesh.cpp; NR::powgrid, NR.hpp:189-204): bin widths in geometric progression, last / first = ratio"""
+    def __init__(self, numBins, ratio):
+        self.numBins = int(numBins); self.ratio = float(ratio)
+
+    def mesh(self):
+        import math
+        n, ratio = self.numBins, self.ratio
+        if n <= 1 or abs(ratio - 1.) < 1e-3:
+            return LinMesh(n).mesh()
+        q = math.pow(ratio, 1. / (n - 1)); qn = math.pow(q, n)
+        return np.array([0.0 + (1. - math.pow(q, i)) / (1. - qn) * 1.0 for i in range(n + 1)])
+
+
 class SymPowMesh:
     def __init__(self, numBins, ratio):
         self.numBins = int(numBins); self.ratio = float(ratio)
@@ -374,6 +388,74 @@ class OctTreeDustGrid(_BoxDustGrid):
 class BinTreeDustGrid(OctTreeDustGrid):
     """BinTreeDustGrid: k-d tree, split direction level % 3 (BinTreeNode.cpp:74-77)"""
     kind = 1
+
+
+class _SymmetricDustGrid:
+    """common part of the grids with symmetries: the border arrays are the whole state"""
+    _t = None
+
+    def build(self, *a, **k):
+        return self
+
+    def tables(self):
+        return self._t
+
+    def numCells(self):
+        return int(self._t["Ncells"])
+
+
+class Sphere1DDustGrid(_SymmetricDustGrid):
+    """Sphere1DDustGrid (Sphere1DDustGrid.cpp:24-33): spherical shells, borders meshR * maxR"""
+    def __init__(self, maxR, meshR):
+        if maxR <= 0:
+            raise FatalError("The outer radius of the grid should be positive")
+        self.rv = np.asarray(meshR.mesh(), dtype=np.float64) * float(maxR)
+        self._t = dict(kind="sphere1d", rv=self.rv, Ncells=len(self.rv) - 1)
+
+    def volumes(self):          # Sphere1DDustGrid.cpp:67-77
+        rL, rR = self.rv[:-1], self.rv[1:]
+        return 4.0 * np.pi / 3.0 * (rR - rL) * (rR * rR + rR * rL + rL * rL)
+
+
+class Sphere2DDustGrid(_SymmetricDustGrid):
+    """Sphere2DDustGrid (Sphere2DDustGrid.cpp:27-75): shells x polar bins; the polar borders get a grid point in the xy-plane"""
+    def __init__(self, maxR, meshR, meshTheta):
+        if maxR <= 0:
+            raise FatalError("The outer radius of the grid should be positive")
+        self.rv = np.asarray(meshR.mesh(), dtype=np.float64) * float(maxR)
+        thetav = np.asarray(meshTheta.mesh(), dtype=np.float64) * np.pi
+        cv = np.cos(thetav); cv[0] = 1.; cv[-1] = -1.
+        zero = [k for k in range(1, len(cv) - 1) if abs(cv[k]) < 1e-9]
+        if len(zero) > 1:
+            raise FatalError("There are multiple grid points very close to pi/2")
+        if zero:
+            cv[zero[0]] = 0.
+        else:
+            at = int(np.sum(cv > 0))                    # the borders with positive cosine keep their index, the others move up by one
+            thetav = np.insert(thetav, at, np.pi / 2); cv = np.insert(cv, at, 0.0)
+        self.thetav, self.cv = thetav, cv
+        self._t = dict(kind="sphere2d", rv=self.rv, thetav=thetav, cv=cv, Ncells=(len(self.rv) - 1) * (len(thetav) - 1))
+
+    def volumes(self):          # Sphere2DDustGrid.cpp:123-131, cell m = k + Ntheta*i
+        r3 = self.rv[1:] ** 3 - self.rv[:-1] ** 3
+        dc = np.cos(self.thetav[:-1]) - np.cos(self.thetav[1:])
+        return ((2.0 / 3.0) * np.pi * r3[:, None] * dc[None, :]).ravel()
+
+
+class Cylinder2DDustGrid(_SymmetricDustGrid):
+    """Cylinder2DDustGrid (Cylinder2DDustGrid.cpp:26-41): radial x vertical bins, cell m = k + Nz*i"""
+    def __init__(self, maxR, minZ, maxZ, meshR, meshZ):
+        if maxR <= 0:
+            raise FatalError("The outer radius of the grid should be positive")
+        if maxZ <= minZ:
+            raise FatalError("The extent of the cylinder should be positive in the Z direction")
+        self.Rv = np.asarray(meshR.mesh(), dtype=np.float64) * float(maxR)
+        self.zv = np.asarray(meshZ.mesh(), dtype=np.float64) * (float(maxZ) - float(minZ)) + float(minZ)
+        self._t = dict(kind="cylinder2d", Rv=self.Rv, zv=self.zv, Ncells=(len(self.Rv) - 1) * (len(self.zv) - 1))
+
+    def volumes(self):          # Cylinder2DDustGrid.cpp:85-93
+        dz = self.zv[1:] - self.zv[:-1]
+        return (np.pi * dz[None, :] * ((self.Rv[1:] - self.Rv[:-1]) * (self.Rv[1:] + self.Rv[:-1]))[:, None]).ravel()
 
 
 class ParticleTreeDustGrid(_BoxDustGrid):

@@ -146,6 +146,30 @@ def make_amesh(box=C1_BOX, root=(4, 4, 4), max_depth=4, frac=2e-3):
     return np.array(nxyz, dtype=np.int32), np.array(val, dtype=np.float64)
 
 
+# the grids with symmetries, as spec lines of the reference harness (radius 18 kpc; the C1 disk has hR = 4 kpc, hz = 140 pc)
+SYM_GRIDS = {
+    "sphere1d": f"sphere1d {18000*PC!r} 40 pow 30.0",
+    "sphere2d": f"sphere2d {18000*PC!r} 30 pow 20.0 16 lin",                  # 16 polar bins: a border at pi/2 exists
+    "sphere2d_odd": f"sphere2d {18000*PC!r} 24 lin 9 lin",                    # 9 polar bins: the reference inserts the border at pi/2
+    "cylinder2d": f"cylinder2d {18000*PC!r} {-3000*PC!r} {3000*PC!r} 36 pow 25.0 30 sympow 15.0",
+}
+
+
+SPHERE1D_DUST_MASS = 1e37          # kg: a V-band optical depth of order one through the centre of the Sersic sphere
+
+
+def sym_grid_mirror(kind):
+    """the same grid through the product's host mirror (skirt_b200.simulation)"""
+    from skirt_b200 import simulation as sim
+    if kind == "sphere1d":
+        return sim.Sphere1DDustGrid(18000 * PC, sim.PowMesh(40, 30.0))
+    if kind == "sphere2d":
+        return sim.Sphere2DDustGrid(18000 * PC, sim.PowMesh(30, 20.0), sim.LinMesh(16))
+    if kind == "sphere2d_odd":
+        return sim.Sphere2DDustGrid(18000 * PC, sim.LinMesh(24), sim.LinMesh(9))
+    return sim.Cylinder2DDustGrid(18000 * PC, -3000 * PC, 3000 * PC, sim.PowMesh(36, 25.0), sim.SymPowMesh(30, 15.0))
+
+
 def spec_grid(kind, search=1, box=C1_BOX, minlevel=2, maxlevel=5, massfrac=2e-4, packages=1e4, threads=1, extra=()):
     """Specs for the non-Cartesian grids; dust = C1's ExpDisk (or the mesh's own densities for amesh)."""
     head = ["sim oligo", f"threads {threads}", "seed 4357", f"packages {packages!r}", "wavelengths 0.55e-6", box_line(box)]
@@ -159,6 +183,10 @@ def spec_grid(kind, search=1, box=C1_BOX, minlevel=2, maxlevel=5, massfrac=2e-4,
         lines = head + ["grid voronoi file", "dustsamples 10", stellar, dust, instr]
     elif kind == "amesh":
         lines = head + ["grid amesh", "ameshdust 1e-24", stellar, instr]
+    elif kind in SYM_GRIDS:
+        if kind == "sphere1d":      # DustGrid.cpp:37: the grid's dimension must not be lower than the geometries' -> spherical stars and dust
+            stellar = f"stellar sersic 2.0 {1500*PC!r} 1.0"; dust = f"dustmass {SPHERE1D_DUST_MASS!r} sersic 1.5 {3000*PC!r} 1.0"
+        lines = head + ["grid " + SYM_GRIDS[kind], "dustsamples 10", stellar, dust, instr]
     elif kind in ("particletree_oct", "particletree_bin"):      # maxlevel doubles as the number of extra levels (0 or 1 in the tests)
         lines = head + [f"grid particletree {kind[-3:]} {0 if maxlevel > 1 else maxlevel}", "dustsamples 10", stellar, dust, instr]
     else:

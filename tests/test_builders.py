@@ -58,6 +58,19 @@ def test_particle_tree_builder_reproduces_the_reference_tree(tt, extra):
         hostlib.build_particle_tree(0, common.C1_BOX, np.zeros((2, 3)), 0)
 
 
+@pytest.mark.parametrize("kind", list(common.SYM_GRIDS))
+def test_symmetric_grid_mirrors_reproduce_the_reference_borders(kind):
+    """Sphere1D / Sphere2D / Cylinder2D: the border arrays (and the polar border the reference inserts at pi/2) are identical"""
+    ref = _ref(common.spec_grid(kind)).grid_tables()
+    mine = common.sym_grid_mirror(kind).tables()
+    assert mine["kind"] == ref["kind"]
+    for k in ref:
+        if k != "kind":
+            assert np.array_equal(np.asarray(mine[k]), np.asarray(ref[k])), f"{kind}: {k} differs from the reference"
+    if kind == "sphere2d_odd":
+        assert len(mine["thetav"]) == 11 and mine["cv"][5] == 0.0
+
+
 def test_tree_builder_validation():
     with pytest.raises(hostlib.HostError, match="Maximum tree level should be larger"):
         hostlib.TreeBuilder(0, common.C1_BOX, 3, 3)

@@ -65,7 +65,7 @@ def test_streams_are_reproducible_and_disjoint(engine):
     assert out[0] != out[2]                              # disjoint Philox counters -> a different realisation
 
 
-@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi", "particletree_oct"])
+@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi", "particletree_oct", "sphere1d", "sphere2d", "cylinder2d"])
 def test_other_grids_against_reference_runs(engine, kind):
     """the same 3-sigma gate on the hierarchical / unstructured grids, against runs of the reference's own code
     (oracle/_ref travels to the GPU box as a prebuilt library; skipped where it is absent)"""
@@ -82,9 +82,15 @@ def test_other_grids_against_reference_runs(engine, kind):
     spec = common.spec_grid(kind, search=1, maxlevel=4 if kind == "octtree" else 10, packages=1e5, threads=os.cpu_count() or 1, extra=extra)
     S = sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v(), **kw).setup()
     tables, medium, L = S.grid_tables(), S.medium(), S.luminosities()
+    if kind in common.SYM_GRIDS:
+        tables = common.sym_grid_mirror(kind).tables()          # the product's own host mirror of these grids
     Npp = S.packages_per_lambda()
     engine.set_grid(tables); engine.medium(medium["rho"], medium["kext"], medium["ksca"], medium["g"])
-    engine.sources([dict(geometry=1, p=[4000 * common.PC, 350 * common.PC, 0, 0, 0])], L, 0.5)
+    if kind == "sphere1d":
+        from skirt_b200 import simulation as sim
+        engine.sources([sim.SersicGeometry(2.0, 1500 * common.PC).sampler()], L, 0.5)
+    else:
+        engine.sources([dict(geometry=1, p=[4000 * common.PC, 350 * common.PC, 0, 0, 0])], L, 0.5)
     engine.instruments([dict(kind=2, distance=1e7 * common.PC, inclination=float(np.radians(88)))])
     B = 16
     ref_s, ref_l, gpu_s, gpu_l = [], [], [], []
