@@ -325,7 +325,7 @@ def test_symmetric_grids_against_the_reference(engine, kind):
     r = np.concatenate([r, r2]); k = np.concatenate([k, k2])
     got = engine.path_batch(r, k, ell=0)
     ref = S.path_batch(r, k, ell=0, nthreads=os.cpu_count() or 1)
-    assert len(ref["m"]) > 4 * len(r)
+    assert len(ref["m"]) > len(r)
     if kind.startswith("sphere2d"):
         # the start cell comes from acos(z / r) (Position::spherical): where the device's acos and glibc's differ in the last bit at a
         # polar border, a path starts one bin off -- allow that for a handful of rays, everything else bit for bit
