@@ -58,6 +58,58 @@ void TreeDustGrid::upload(skg_engine* e) const
                         _t.nbrStart.empty() ? nullptr : _t.nbrStart.data(), _t.nbrIds.empty() ? nullptr : _t.nbrIds.data()));
 }
 
+// ---- grids with symmetries ---------------------------------------------------------------------------------------------------
+void Sphere1DDustGrid::setup()
+{
+    if (_rmax <= 0) SKIRT_FATAL("The outer radius of the grid should be positive");           // SphereDustGrid.cpp:21-26
+    if (!_meshr) SKIRT_FATAL("the radial mesh was not set");
+    _N1 = _meshr->numBins(); _N2 = 0;
+    _v1 = _meshr->mesh(); for (double& v : _v1) v *= _rmax;
+    _volumes.resize(_N1);
+    for (int i = 0; i < _N1; i++) { const double rL = _v1[i], rR = _v1[i + 1]; _volumes[i] = 4.0 * M_PI / 3.0 * (rR - rL) * (rR * rR + rR * rL + rL * rL); }
+}
+void Sphere1DDustGrid::upload(skg_engine* e) const { check(skg_grid_sphere1d(e, _N1, _v1.data())); }
+
+void Sphere2DDustGrid::setup()
+{
+    if (_rmax <= 0) SKIRT_FATAL("The outer radius of the grid should be positive");
+    if (!_meshr || !_mesht) SKIRT_FATAL("the radial or the polar mesh was not set");
+    _N1 = _meshr->numBins();
+    _v1 = _meshr->mesh(); for (double& v : _v1) v *= _rmax;
+    _v2 = _mesht->mesh(); for (double& v : _v2) v *= M_PI;
+    _cv.resize(_v2.size()); for (size_t k = 0; k < _v2.size(); k++) _cv[k] = std::cos(_v2[k]);
+    _cv.front() = 1.; _cv.back() = -1.;
+    // Sphere2DDustGrid.cpp:39-72: path() needs a border in the xy-plane -- snap one that is there, insert one otherwise
+    int zeros = 0, at = -1;
+    for (size_t k = 1; k + 1 < _cv.size(); k++) if (std::fabs(_cv[k]) < 1e-9) { zeros++; at = (int)k; }
+    if (zeros > 1) SKIRT_FATAL("There are multiple grid points very close to pi/2");
+    if (zeros == 1) _cv[at] = 0.;
+    else
+    {
+        size_t pos = 0; while (pos < _cv.size() && _cv[pos] > 0) pos++;
+        _v2.insert(_v2.begin() + pos, M_PI_2); _cv.insert(_cv.begin() + pos, 0.);
+    }
+    _N2 = (int)_v2.size() - 1;
+    _volumes.resize((size_t)_N1 * _N2);
+    for (int i = 0; i < _N1; i++) for (int k = 0; k < _N2; k++)
+        _volumes[k + (size_t)_N2 * i] = (2.0 / 3.0) * M_PI * (std::pow(_v1[i + 1], 3) - std::pow(_v1[i], 3)) * (std::cos(_v2[k]) - std::cos(_v2[k + 1]));
+}
+void Sphere2DDustGrid::upload(skg_engine* e) const { check(skg_grid_sphere2d(e, _N1, _v1.data(), _N2, _v2.data(), _cv.data())); }
+
+void Cylinder2DDustGrid::setup()
+{
+    if (_Rmax <= 0) SKIRT_FATAL("The outer radius of the grid should be positive");
+    if (_zmax <= _zmin) SKIRT_FATAL("The extent of the cylinder should be positive in the Z direction");
+    if (!_meshR || !_meshz) SKIRT_FATAL("the radial or the vertical mesh was not set");
+    _N1 = _meshR->numBins(); _N2 = _meshz->numBins();
+    _v1 = _meshR->mesh(); for (double& v : _v1) v *= _Rmax;
+    _v2 = _meshz->mesh(); for (double& v : _v2) v = v * (_zmax - _zmin) + _zmin;
+    _volumes.resize((size_t)_N1 * _N2);
+    for (int i = 0; i < _N1; i++) for (int k = 0; k < _N2; k++)
+        _volumes[k + (size_t)_N2 * i] = M_PI * (_v2[k + 1] - _v2[k]) * (_v1[i + 1] - _v1[i]) * (_v1[i + 1] + _v1[i]);
+}
+void Cylinder2DDustGrid::upload(skg_engine* e) const { check(skg_grid_cylinder2d(e, _N1, _v1.data(), _N2, _v2.data())); }
+
 // ---- particle tree ---------------------------------------------------------------------------------------------------------
 static void readParticleFile(const std::string& file, std::vector<double>& xyz, const char* what)
 {

@@ -424,6 +424,46 @@ private:
 class OctTreeDustGrid : public TreeDustGrid { public: OctTreeDustGrid() : TreeDustGrid(0) {} };
 class BinTreeDustGrid : public TreeDustGrid { public: BinTreeDustGrid() : TreeDustGrid(1) {} };
 
+// Sphere1DDustGrid / Sphere2DDustGrid / Cylinder2DDustGrid (the grids with symmetries): the border arrays are the whole state
+class SymmetricDustGrid : public DustGrid
+{
+public:
+    bool densityOnDevice() const override { return true; }
+    int numCells() const override { return _N2 > 0 ? _N1 * _N2 : _N1; }
+    void cellBox(int, double b[6]) const override { for (int c = 0; c < 6; c++) b[c] = 0; }      // (no Cartesian box; densities are sampled on the device)
+    std::vector<double> volumes() const override { return _volumes; }
+protected:
+    int _N1 = 0, _N2 = 0; std::vector<double> _v1, _v2, _cv, _volumes;
+};
+class Sphere1DDustGrid : public SymmetricDustGrid                        // Sphere1DDustGrid.cpp:24-33, :67-77
+{
+public:
+    void setMaxR(double v) { _rmax = v; } void setMeshR(Mesh* m) { _meshr.reset(m); }
+    void setup() override;
+    void upload(skg_engine* e) const override;
+private:
+    double _rmax = 0; std::unique_ptr<Mesh> _meshr;
+};
+class Sphere2DDustGrid : public SymmetricDustGrid                        // Sphere2DDustGrid.cpp:27-75, :123-131
+{
+public:
+    void setMaxR(double v) { _rmax = v; } void setMeshR(Mesh* m) { _meshr.reset(m); } void setMeshTheta(Mesh* m) { _mesht.reset(m); }
+    void setup() override;
+    void upload(skg_engine* e) const override;
+private:
+    double _rmax = 0; std::unique_ptr<Mesh> _meshr, _mesht;
+};
+class Cylinder2DDustGrid : public SymmetricDustGrid                      // Cylinder2DDustGrid.cpp:26-41, :85-93
+{
+public:
+    void setMaxR(double v) { _Rmax = v; } void setMinZ(double v) { _zmin = v; } void setMaxZ(double v) { _zmax = v; }
+    void setMeshR(Mesh* m) { _meshR.reset(m); } void setMeshZ(Mesh* m) { _meshz.reset(m); }
+    void setup() override;
+    void upload(skg_engine* e) const override;
+private:
+    double _Rmax = 0, _zmin = 0, _zmax = 0; std::unique_ptr<Mesh> _meshR, _meshz;
+};
+
 // ParticleTreeDustGrid (ParticleTreeDustGrid.cpp:76-152): an octree or binary tree grown around particle positions (one per
 // line of a text file, or given directly); every leaf ends up with at most one particle; its own traversal (search = 3)
 class ParticleTreeDustGrid : public BoxDustGrid

@@ -125,6 +125,17 @@ int main(int argc, char** argv)
                     auto* g = new VoronoiDustGrid(); setBox(g); g->setParticleFile(file);
                     ds->setDustGrid(g); continue;
                 }
+                if (kind == "sphere1d" || kind == "sphere2d" || kind == "cylinder2d")
+                {
+                    // grid sphere1d <maxR> <n> <mesh> | grid sphere2d <maxR> <nr> <mesh> <ntheta> <mesh> | grid cylinder2d <maxR> <minZ> <maxZ> <nR> <mesh> <nz> <mesh>
+                    if (kind == "sphere1d") { double r; int n; in >> r >> n; auto* g = new Sphere1DDustGrid(); g->setMaxR(r); g->setMeshR(makeMesh(in, n)); ds->setDustGrid(g); }
+                    else if (kind == "sphere2d")
+                    { double r; int nr, nt; in >> r >> nr; auto* g = new Sphere2DDustGrid(); g->setMaxR(r); g->setMeshR(makeMesh(in, nr)); in >> nt; g->setMeshTheta(makeMesh(in, nt)); ds->setDustGrid(g); }
+                    else
+                    { double r, z0, z1; int nR, nz; in >> r >> z0 >> z1 >> nR; auto* g = new Cylinder2DDustGrid(); g->setMaxR(r); g->setMinZ(z0); g->setMaxZ(z1);
+                      g->setMeshR(makeMesh(in, nR)); in >> nz; g->setMeshZ(makeMesh(in, nz)); ds->setDustGrid(g); }
+                    continue;
+                }
                 if (kind == "particletree")
                 {
                     std::string tt, file; int extra = 0; in >> tt >> file; in >> extra;      // grid particletree oct|bin <particle file> [extraLevels]

@@ -47,7 +47,8 @@ def _compare(name, a, r, B, frac=0.97):
     common.mc_gate(a, r, name)
 
 
-@pytest.mark.parametrize("grid", [None, "grid octtree 2 4 1 0.0005 0 30", "grid amesh", "grid voronoi file"])
+@pytest.mark.parametrize("grid", [None, "grid octtree 2 4 1 0.0005 0 30", "grid amesh", "grid voronoi file",
+                                  "grid " + common.SYM_GRIDS["cylinder2d"], "grid " + common.SYM_GRIDS["sphere2d"]])
 def test_dust_selfabsorption_and_emission(engine, grid):
     S, p = _ref_pan(grid=grid)
     _engine_for(engine, S, p)

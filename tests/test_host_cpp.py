@@ -107,7 +107,7 @@ def test_pan_flow_through_the_cpp_host(tmp_path):
 
 @pytest.mark.gpu
 @pytest.mark.skipif(not os.path.exists(RUN), reason="skirt_b200_run not built")
-@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi"])
+@pytest.mark.parametrize("kind", ["octtree", "bintree", "amesh", "voronoi", "sphere2d_odd", "cylinder2d"])
 def test_other_grids_through_the_cpp_host(tmp_path, engine, kind):
     """the C++ host builds tree / adaptive-mesh / Voronoi grids itself (skirt_b200/host/GridBuilders.cpp; tree subdivision and
     cell densities sampled on the device) and shoots through them; the Python mirror does the same through libskirthost.so:
@@ -124,6 +124,8 @@ def test_other_grids_through_the_cpp_host(tmp_path, engine, kind):
         grid_line = f"grid {kind} {lo} {hi} 1 1e-4 50"
         cls = sim.OctTreeDustGrid if kind == "octtree" else sim.BinTreeDustGrid
         grid = cls(b[0], b[1], b[2], b[3], b[4], b[5], lo, hi, "Neighbor", 50, 0.0, 1e-4)
+    elif kind in common.SYM_GRIDS:
+        grid_line = "grid " + common.SYM_GRIDS[kind]; grid = common.sym_grid_mirror(kind)
     elif kind == "amesh":
         nxyz, val = configs.synthetic_amesh(root=4, depth=3, frac=2e-3)
         f = tmp_path / "mesh.txt"
