@@ -378,9 +378,9 @@ def mc_gate(a, r, label, signal=0.15, min_bins=0.0, total_sigma=3.5, total_rel=0
     ok = (sa > 0) & (sr_ > 0) & (sa < signal * np.abs(ma)) & (sr_ < signal * np.abs(mr))       # (Stokes Q, U, V are signed)
     N = int(ok.sum())
     assert N >= max(1, min_bins * a.shape[1]), f"{label}: only {N} of {a.shape[1]} bins carry signal"
-    va, vr = sa[ok] ** 2, sr_[ok] ** 2
-    z = (ma[ok] - mr[ok]) / np.sqrt(va + vr)
-    fa, fr = va / (va + vr), vr / (va + vr)          # (scale-free: the luminosities themselves may be ~1e-300 squared)
+    h = np.hypot(sa[ok], sr_[ok])                    # (no explicit squares: bins ~1e-170 x the brightest one would underflow)
+    z = (ma[ok] - mr[ok]) / h
+    fa, fr = (sa[ok] / h) ** 2, (sr_[ok] / h) ** 2
     dof = 1.0 / (fa ** 2 / (Ba - 1) + fr ** 2 / (Br - 1))
     E = float(np.sum(2 * stats.t.sf(3.0, dof)))
     allowed = int(np.ceil(E + 5 * np.sqrt(E) + 2))
