@@ -291,7 +291,7 @@ void DustSystem::setup(const WavelengthGrid& lg, skg_engine* e, uint64_t seed)
             double sum = 0;
             for (int a = 0; a < ns; a++) for (int bb = 0; bb < ns; bb++) for (int cc = 0; cc < ns; cc++)
                 sum += c.geometry->density(b[0] + (a + 0.5) / ns * (b[3] - b[0]), b[1] + (bb + 0.5) / ns * (b[4] - b[1]), b[2] + (cc + 0.5) / ns * (b[5] - b[2]));
-            _rho[(size_t)m * C + h] = scale * sum / (ns * ns * ns);
+            _rho[(size_t)m * C + h] = _grid->weight(m) * scale * sum / (ns * ns * ns);       // DustSystem.cpp:165-176
         }
     }
 }

@@ -376,6 +376,7 @@ public:
     // density field (adaptive mesh):
     virtual bool densityOnDevice() const { return false; }      // DustSystem::setSampleDensityBody through skg_sample_density
     virtual bool ownDensity(std::vector<double>&) const { return false; }
+    virtual double weight(int) const { return 1.0; }           // DustGrid::weight(m): TwoPhaseDustGrid's density multiplier
     virtual void build(skg_engine*, const std::vector<skg_source>&, const std::vector<double>&, uint64_t) {}
     virtual std::vector<double> volumes() const
     { std::vector<double> v(numCells()); for (int m = 0; m < numCells(); m++) { double b[6]; cellBox(m, b); v[m] = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]); } return v; }
@@ -548,10 +549,30 @@ public:
         int i = m / (Nz * Ny), j = (m / Nz) % Ny, k = m % Nz;          // CartesianDustGrid::box, :333-343
         b[0] = _xv[i]; b[1] = _yv[j]; b[2] = _zv[k]; b[3] = _xv[i + 1]; b[4] = _yv[j + 1]; b[5] = _zv[k + 1];
     }
-private:
+protected:
     double _xmin = 0, _xmax = 0, _ymin = 0, _ymax = 0, _zmin = 0, _zmax = 0;
     std::unique_ptr<Mesh> _meshx, _meshy, _meshz;
     std::vector<double> _xv, _yv, _zv;
+};
+
+// TwoPhaseDustGrid (TwoPhaseDustGrid.cpp:18-39): a Cartesian grid whose cells belong at random to a high- or a low-density phase
+class TwoPhaseDustGrid : public CartesianDustGrid
+{
+public:
+    void setFillingFactor(double v) { _ff = v; } void setContrast(double v) { _contrast = v; } void setSeed(uint64_t s) { _seed = s; }
+    void setup() override
+    {
+        CartesianDustGrid::setup();
+        if (_ff <= 0 || _ff >= 1) SKIRT_FATAL("the volume filling factor of the high-density medium should be between 0 and 1");
+        if (_contrast <= 0) SKIRT_FATAL("the density contrast between the high- and low-density medium should be positive");
+        const double den = _contrast * _ff + 1.0 - _ff;
+        _weightv.resize(numCells());
+        uint64_t x = _seed * 6364136223846793005ull + 1442695040888963407ull;      // (a 64-bit LCG; the reference draws from its Random)
+        for (double& w : _weightv) { x = x * 6364136223846793005ull + 1442695040888963407ull; w = ((x >> 11) * (1.0 / 9007199254740992.0)) < _ff ? _contrast / den : 1.0 / den; }
+    }
+    double weight(int m) const override { return m < 0 ? 0.0 : _weightv[m]; }
+private:
+    double _ff = 0, _contrast = 0; uint64_t _seed = 4357; std::vector<double> _weightv;
 };
 
 // ---- dust system --------------------------------------------------------------------------------------------------

@@ -143,9 +143,11 @@ int main(int argc, char** argv)
                     g->setTreeType(tt == "bin" ? ParticleTreeDustGrid::BinTree : ParticleTreeDustGrid::OctTree);
                     ds->setDustGrid(g); continue;
                 }
-                if (kind != "cartesian") SKIRT_FATAL("unknown dust grid " + kind);
+                if (kind != "cartesian" && kind != "twophase") SKIRT_FATAL("unknown dust grid " + kind);
                 int nx, ny, nz; in >> nx >> ny >> nz;
-                auto* g = new CartesianDustGrid();
+                CartesianDustGrid* g;
+                if (kind == "twophase") { double ff, contrast; in >> ff >> contrast; auto* t = new TwoPhaseDustGrid(); t->setFillingFactor(ff); t->setContrast(contrast); g = t; }   // grid twophase nx ny nz ff contrast <meshes>
+                else g = new CartesianDustGrid();
                 g->setMinX(box[0]); g->setMaxX(box[1]); g->setMinY(box[2]); g->setMaxY(box[3]); g->setMinZ(box[4]); g->setMaxZ(box[5]);
                 g->setMeshX(makeMesh(in, nx)); g->setMeshY(makeMesh(in, ny)); g->setMeshZ(makeMesh(in, nz));
                 ds->setDustGrid(g);

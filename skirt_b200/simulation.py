@@ -313,6 +313,24 @@ class TreeTablesDustGrid:
         return self._t
 
 
+class TwoPhaseDustGrid(CartesianDustGrid):
+    """TwoPhaseDustGrid (TwoPhaseDustGrid.cpp:18-39): a Cartesian grid whose cells belong at random to a high- or a low-density
+    phase; the density of cell m is multiplied by weight(m) = contrast / (contrast*ff + 1 - ff) with probability ff (the volume
+    filling factor of the high-density medium), else 1 / (contrast*ff + 1 - ff).  Traversal is CartesianDustGrid's."""
+    def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, meshX, meshY, meshZ, fillingFactor, contrast, seed=4357):
+        super().__init__(minX, maxX, minY, maxY, minZ, maxZ, meshX, meshY, meshZ)
+        if fillingFactor <= 0 or fillingFactor >= 1:
+            raise FatalError("the volume filling factor of the high-density medium should be between 0 and 1")
+        if contrast <= 0:
+            raise FatalError("the density contrast between the high- and low-density medium should be positive")
+        X = np.random.default_rng(seed).random(self.numCells())
+        den = contrast * fillingFactor + 1.0 - fillingFactor
+        self.weightv = np.where(X < fillingFactor, contrast / den, 1.0 / den)
+
+    def weights(self):
+        return self.weightv
+
+
 class _BoxDustGrid:
     def _set_extent(self, minX, maxX, minY, maxY, minZ, maxZ):
         if maxX <= minX:
@@ -555,6 +573,8 @@ class DustSystem:
                 dens += c.geometry.density(p[:, 0], p[:, 1], p[:, 2])
             cols.append(scale * dens / len(pts))
         self.rho = np.stack(cols, axis=1)
+        if hasattr(grid, "weights"):
+            self.rho = self.rho * grid.weights()[:, None]          # DustGrid::weight(m), DustSystem.cpp:165-176
 
     def norms(self):
         """mass normalisation of every component: FaceOnDustCompNormalization.cpp:67-74, tau / (SigmaZ * kappaext(lambda))"""

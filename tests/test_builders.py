@@ -125,3 +125,21 @@ def test_host_library_exports_its_header():
     assert len(names) >= 15
     for n in names:
         assert hasattr(L, n), f"{n} declared in skirthost.h but not exported"
+
+
+def test_two_phase_grid_weights():
+    """TwoPhaseDustGrid (TwoPhaseDustGrid.cpp:18-39): two weights, the high one in a fraction `fillingFactor` of the cells, volume mean 1;
+    the density table of the dust system carries them (DustSystem.cpp:165-176)"""
+    from skirt_b200 import simulation as sim
+    PC = common.PC
+    ext = [-1e4 * PC, 1e4 * PC] * 3
+    g = sim.TwoPhaseDustGrid(*ext, sim.LinMesh(20), sim.LinMesh(20), sim.LinMesh(20), fillingFactor=0.2, contrast=50.0)
+    w = g.weights(); hi, lo = 50.0 / (50 * 0.2 + 0.8), 1.0 / (50 * 0.2 + 0.8)
+    assert set(np.unique(w)) == {hi, lo} and abs((w == hi).mean() - 0.2) < 0.02 and abs(w.mean() - 1) < 0.1
+    plain = sim.CartesianDustGrid(*ext, sim.LinMesh(20), sim.LinMesh(20), sim.LinMesh(20))
+    lg = sim.OligoWavelengthGrid([0.55e-6]); mix = sim.TableDustMix(common.MIX_V["kabs"], common.MIX_V["ksca"], common.MIX_V["g"])
+    comp = sim.DustComp(sim.ExpDiskGeometry(4000 * PC, 140 * PC), mix, 1.0, 0.55e-6)
+    a, b = sim.DustSystem(g, [comp], lg).rho, sim.DustSystem(plain, [comp], lg).rho
+    np.testing.assert_allclose(a[:, 0], b[:, 0] * w, rtol=1e-15)
+    with pytest.raises(sim.FatalError, match="filling factor"):
+        sim.TwoPhaseDustGrid(*ext, sim.LinMesh(4), sim.LinMesh(4), sim.LinMesh(4), fillingFactor=1.0, contrast=2.0)
