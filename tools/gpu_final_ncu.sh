@@ -25,4 +25,10 @@ for line in sys.stdin.read().splitlines():
 full)
     $SMALL > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"$2" -s ${3:-4} -c ${4:-2} -f -o gpurun_out/r02_final_$5 $SMALL > gpurun_out/ncu.log 2>&1
     echo "ncu rc=$?"; tail -3 gpurun_out/ncu.log; python tools/ncu_summary.py gpurun_out/r02_final_$5.ncu-rep > gpurun_out/r02_final_$5_ncu.txt 2>&1; head -60 gpurun_out/r02_final_$5_ncu.txt ;;
+fullcfg)
+    # full <kernel regex> <skip> <count> <tag> <bench.py arguments...>: one full capture on another configuration
+    re=$2; sk=$3; ct=$4; tag=$5; shift 5
+    CMD="python bench.py --steps 1 --warmup 1 --skip-cpu $*"
+    $CMD > gpurun_out/plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"$re" -s $sk -c $ct -f -o gpurun_out/r02_final_$tag $CMD > gpurun_out/ncu.log 2>&1
+    echo "ncu rc=$?"; tail -3 gpurun_out/ncu.log; python tools/ncu_summary.py gpurun_out/r02_final_$tag.ncu-rep > gpurun_out/r02_final_${tag}_ncu.txt 2>&1; head -80 gpurun_out/r02_final_${tag}_ncu.txt ;;
 esac
