@@ -621,7 +621,9 @@ template<bool HINT> struct TreeWalkerT
                         }
                     }
                 }
-                if (node < 0) node = treeWhichNodeCold(g, x, y, z);
+                // (TreeNode::whichnode(Vec) of the root answers "none" for a point outside the root's box: the usual end of a
+                // path, decided here without the out-of-line call)
+                if (node < 0 && boxContains(g.box, x, y, z)) node = treeWhichNodeCold(g, x, y, z);
             }
             else node = treeWhichNode(g, x, y, z);
 
