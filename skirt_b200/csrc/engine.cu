@@ -338,6 +338,15 @@ int skg_grid_tree(skg_engine* eh, int kind, int search, int N, const double* box
                             }
                             hints.push_back(pick);
                         }
+                        // a wall shared by four finer siblings (the usual level transition of an octree): their ids follow from the
+                        // id of the first one and the bin, ids = base + sa*ia + sb*ib -- the walkers then need no table read at all
+                        // (bit 4 of the wall's meta; the record's `first` entry of such a wall holds the base)
+                        if (G == 2 && !dominant)
+                        {
+                            const int* h = hints.data() + hints.size() - 4;
+                            const int sa = w < 2 ? 2 : 1, sb = w < 4 ? 4 : 2;
+                            if (h[2] - h[0] == sa && h[1] - h[0] == sb && h[3] - h[0] == sa + sb) { r.hmeta |= 16u << (5 * w); r.first[w] = h[0]; }
+                        }
                     }
                 }
             }

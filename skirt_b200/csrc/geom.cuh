@@ -410,21 +410,26 @@ __device__ __forceinline__ bool boxContains(const double* b, double x, double y,
 __device__ __forceinline__ int treeWhichNode(const TreeGrid& g, double x, double y, double z)
 {
     if (!boxContains(g.box, x, y, z)) return -1;
-    int node = 0;
+    int node = 0, c0 = 0;
+    bool haveC0 = false;
     if (g.lookupG > 1)
     {
         // start below the root when the lattice cell's node strictly contains the point: the descent from the root
-        // necessarily passes through that node (all comparisons against its ancestors' split planes agree)
+        // necessarily passes through that node (all comparisons against its ancestors' split planes agree).  The node's
+        // child index is read together with its box, and its record (what the Neighbor walker reads next when the node is
+        // a leaf) is on its way into L1 meanwhile: one round trip after the lattice read instead of three in a row.
         const int G = g.lookupG;
         const int i = max(0, min(G - 1, (int)((x - g.box[0]) * g.lookupInv[0])));
         const int j = max(0, min(G - 1, (int)((y - g.box[1]) * g.lookupInv[1])));
         const int k = max(0, min(G - 1, (int)((z - g.box[2]) * g.lookupInv[2])));
         const int cand = __ldg(g.lookup + ((size_t)i * G + j) * G + k);
         const double* b = g.box + 6 * (size_t)cand;
-        if (x > __ldg(b) && x < __ldg(b + 3) && y > __ldg(b + 1) && y < __ldg(b + 4) && z > __ldg(b + 2) && z < __ldg(b + 5)) node = cand;
+        const int c0cand = __ldg(g.child0 + cand);
+        if (g.nodeRec) { prefetchL1(g.nodeRec + cand); prefetchL1(reinterpret_cast<const char*>(g.nodeRec + cand) + 64); }
+        if (x > __ldg(b) && x < __ldg(b + 3) && y > __ldg(b + 1) && y < __ldg(b + 4) && z > __ldg(b + 2) && z < __ldg(b + 5)) { node = cand; c0 = c0cand; haveC0 = true; }
     }
-    int c0;
-    while ((c0 = __ldg(g.child0 + node)) >= 0)
+    if (!haveC0) c0 = __ldg(g.child0 + node);
+    while (c0 >= 0)
     {
         const double* cb = g.box + 6 * (size_t)c0;
         if (g.kind == 0)
@@ -440,6 +445,7 @@ __device__ __forceinline__ int treeWhichNode(const TreeGrid& g, double x, double
             double v = d == 0 ? x : (d == 1 ? y : z);
             node = (v < cb[3 + d]) ? c0 : c0 + 1;
         }
+        c0 = __ldg(g.child0 + node);
     }
     return node;
 }
@@ -583,24 +589,35 @@ template<bool HINT> struct TreeWalkerT
                 // wall's edges), tests that neighbour: its id travels with the node's record, one dependent read.  A wall shared
                 // by several finer neighbours looks up (HINT) which of them covers the G x G wall bin r falls in and tests that
                 // one: when r lies strictly inside its box no other leaf can contain r, so it is the list's first match as well.
+                // Four finer siblings behind a wall (the usual level transition; tables.h, bit 4) need no table: the sibling
+                // covering r's quadrant of the wall follows from the id of the first one, in the shooting stages as well.
                 // Anything else (r on a box face, a neighbour finer than the bins resolve) searches the list in order.
                 // The shooting stages measured 6 % faster searching such walls in list order from the record's first neighbour
                 // (SKG_TREE_HINTS_MC), the path kernels 6-12 % faster with the table.
                 const int f0 = wall == 0 ? first[0] : wall == 1 ? first[1] : wall == 2 ? first[2] : wall == 3 ? first[3] : wall == 4 ? first[4] : first[5];
-                const unsigned wm = (hmeta >> (5 * wall)) & 15u;
+                const unsigned wm = (hmeta >> (5 * wall)) & 31u;
                 int cand = f0;
                 bool strict = false;
-                if (HINT && (wm & 9u) == 1u)
+                if ((wm & 9u) == 1u && (HINT || (wm & 16u)))
                 {
                     const int a = wall < 2 ? 1 : 0, b = wall < 4 ? 2 : 1;
                     const double pa = a == 1 ? y : x, pb = b == 2 ? z : y;
                     const double la = a == 1 ? bx[1] : bx[0], ha = a == 1 ? bx[4] : bx[3], lb = b == 2 ? bx[2] : bx[1], hb = b == 2 ? bx[5] : bx[4];
-                    const int G = 2 << ((wm >> 1) & 3u);
-                    int off = 0;            // ids of the multi-neighbour walls before this one
-                    for (int v = 0; v < 5; v++) { const unsigned vm = (hmeta >> (5 * v)) & 7u; off += (v < wall && (vm & 1u)) ? (4 << (vm & 6u)) : 0; }
-                    const int ia = max(0, min(G - 1, (int)((float)G * (float)(pa - la) / (float)(ha - la))));
-                    const int ib = max(0, min(G - 1, (int)((float)G * (float)(pb - lb) / (float)(hb - lb))));
-                    cand = __ldg(g.nbrHint + 4 * (size_t)hbase + off + G * ia + ib);
+                    if (wm & 16u)
+                    {
+                        // four finer siblings behind the wall: the one covering r's half of each in-plane axis, by arithmetic
+                        // (f0 holds the id of the first of them; verified like any other candidate below)
+                        cand = f0 + ((pa - la > ha - pa) ? (wall < 2 ? 2 : 1) : 0) + ((pb - lb > hb - pb) ? (wall < 4 ? 4 : 2) : 0);
+                    }
+                    else
+                    {
+                        const int G = 2 << ((wm >> 1) & 3u);
+                        int off = 0;            // ids of the multi-neighbour walls before this one
+                        for (int v = 0; v < 5; v++) { const unsigned vm = (hmeta >> (5 * v)) & 7u; off += (v < wall && (vm & 1u)) ? (4 << (vm & 6u)) : 0; }
+                        const int ia = max(0, min(G - 1, (int)((float)G * (float)(pa - la) / (float)(ha - la))));
+                        const int ib = max(0, min(G - 1, (int)((float)G * (float)(pb - lb) / (float)(hb - lb))));
+                        cand = __ldg(g.nbrHint + 4 * (size_t)hbase + off + G * ia + ib);
+                    }
                     strict = true;
                 }
                 node = -1;

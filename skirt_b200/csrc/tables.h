@@ -33,9 +33,10 @@ struct __align__(32) TreeNodeRec
     double box[6];
     int cell;
     int hbase;                  // nbrHint offset / 4 of the node's first wall-bin block
-    unsigned hmeta; int pad0;   // per wall w, bits 5w..5w+3: bit 0 = the wall has several neighbours, bits 1-2 = lg with G = 2 << lg,
-                                // bit 3 = the first neighbour covers at least half of the wall
-    int first[6];               // first neighbour of each wall, -1 when the list is empty
+    unsigned hmeta; int pad0;   // per wall w, bits 5w..5w+4: bit 0 = the wall has several neighbours, bits 1-2 = lg with G = 2 << lg,
+                                // bit 3 = the first neighbour covers at least half of the wall, bit 4 = the wall's four neighbours
+                                // are siblings whose ids are first[w] + sa*ia + sb*ib for the 2 x 2 wall bin (ia, ib)
+    int first[6];               // first neighbour of each wall (bit 4: the neighbour of bin (0, 0)), -1 when the list is empty
     int pad1[2];
 };
 
