@@ -445,6 +445,47 @@ int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* 
             }
             e.voro.rec = up(e, rec.data(), rec.size());
         }
+        {
+            // plane records of the shooting stages (tables.h)
+            std::vector<int> ps((size_t)N + 1, 0);
+            size_t slots = 0;
+            for (int m = 0; m < N; m++) { const int cnt = nbrStart[m + 1] - nbrStart[m]; ps[m] = (int)slots; slots += 1 + (size_t)cnt + ((size_t)cnt + 3) / 4; }
+            if (slots + 8 > 2147483647ull) throw Error("too many Voronoi neighbours for int32 record indices");
+            ps[N] = (int)slots;
+            std::vector<double> pl(4 * (slots + 8), 0.0);
+            auto pack = [](int lo, int hi) { const long long v = (long long)(unsigned)lo | ((long long)hi << 32); double d; std::memcpy(&d, &v, 8); return d; };
+            const double lo[3] = {extent[0], extent[2], extent[4]}, hi[3] = {extent[1], extent[3], extent[5]};
+            for (int m = 0; m < N; m++)
+            {
+                const int beg = nbrStart[m], cnt = nbrStart[m + 1] - beg;
+                double* h = pl.data() + 4 * (size_t)ps[m];
+                const double* pr = particles + 3 * (size_t)m;
+                h[0] = pr[0]; h[1] = pr[1]; h[2] = pr[2]; h[3] = pack(cnt, 0);
+                double* tags = h + 4 * (size_t)(cnt + 1);
+                for (int q = 0; q < cnt; q++)
+                {
+                    const int id = nbrIds[beg + q];
+                    double* s4 = h + 4 * (size_t)(q + 1);
+                    if (id >= 0)
+                    {
+                        // the bisector plane of p and p_i: n = p_i - p, n.(r - p) = |n|^2 / 2
+                        const double* pi = particles + 3 * (size_t)id;
+                        for (int c = 0; c < 3; c++) s4[c] = pi[c] - pr[c];
+                        s4[3] = 0.5 * (s4[0] * s4[0] + s4[1] * s4[1] + s4[2] * s4[2]);
+                        tags[q] = pack(id, ps[id]);
+                    }
+                    else
+                    {
+                        // walls -1 .. -6: xmin, xmax, ymin, ymax, zmin, zmax (VoronoiMesh.cpp:800-812), outward normal
+                        const int a = (-1 - id) >> 1; const bool upper = ((-1 - id) & 1) != 0;
+                        s4[a] = upper ? 1.0 : -1.0;
+                        s4[3] = upper ? hi[a] - pr[a] : pr[a] - lo[a];
+                        tags[q] = pack(id, 0);
+                    }
+                }
+            }
+            e.voro.planes = up(e, pl.data(), pl.size()); e.voro.planeStart = up(e, ps.data(), ps.size());
+        }
         // extent arrives as xmin,xmax,ymin,ymax,zmin,zmax (Box setters order); stored as min corner, max corner
         e.voro.ext[0] = extent[0]; e.voro.ext[1] = extent[2]; e.voro.ext[2] = extent[4];
         e.voro.ext[3] = extent[1]; e.voro.ext[4] = extent[3]; e.voro.ext[5] = extent[5];

@@ -1368,7 +1368,8 @@ double mcLabsTotal(Engine& e, int which)
 
 void mcTransposeLabs(Engine& e, const double* src, double* dst)
 {
-    const int Nl = e.NlambdaSrc ? e.NlambdaSrc : e.med.Nlambda, Nc = e.Ncells;
+    if (e.Ncells <= 0 || e.labsCount % e.Ncells) throw Error("the absorption table does not belong to the current grid");
+    const int Nc = e.Ncells, Nl = (int)(e.labsCount / e.Ncells);       // the table's own shape, not the sources'
     dim3 grid((Nc + 31) / 32, (Nl + 31) / 32), block(32, 8);
     transposeLabs<<<grid, block, 0, e.stream>>>(src, dst, Nc, Nl);
     e.launches++; SKG_CUDA(cudaGetLastError());
@@ -1378,7 +1379,9 @@ void mcFetchLabs(Engine& e, double* host, int add, int which)
 {
     DevBuf& src = which ? e.labsDust : e.labs;
     if (!src.p || e.labsCount == 0) throw Error(which ? "absorption of dust emission was not stored" : "absorption rates were not stored");
-    int Nl = e.NlambdaSrc ? e.NlambdaSrc : e.med.Nlambda, Nc = e.Ncells;
+    // (the table's own shape: sources left over from an earlier run may have another number of wavelengths)
+    if (e.Ncells <= 0 || e.labsCount % e.Ncells) throw Error("the absorption table does not belong to the current grid");
+    int Nc = e.Ncells, Nl = (int)(e.labsCount / e.Ncells);
     e.labsT.ensure(sizeof(double) * e.labsCount);
     dim3 grid((Nc + 31) / 32, (Nl + 31) / 32), block(32, 8);
     transposeLabs<<<grid, block, 0, e.stream>>>(src.as<double>(), e.labsT.as<double>(), Nc, Nl);

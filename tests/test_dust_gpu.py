@@ -81,6 +81,21 @@ def test_dust_selfabsorption_and_emission(engine, grid):
     _compare("dust frame", gpu_f, ref_f, B)
 
 
+def test_absorption_tables_keep_their_own_shape(engine):
+    """an engine reused after a run with another number of wavelengths: the absorption tables come back with the shape of the
+    medium they were filled under, not of the sources left over from the earlier run (found as an order dependence between the
+    Voronoi tests: one wavelength of sources, then the 25 wavelengths of the dust phases -- only the first slice arrived)"""
+    S, p = _ref_pan()
+    engine.sources([dict(geometry=1, p=[4000 * common.PC, 350 * common.PC, 0, 0, 0])], [[1.0]], 0.5)     # a one-wavelength run's
+    _engine_for(engine, S, p)
+    Lv = S.prepare_dust(True)
+    engine.reset_labs_dust()
+    engine.run_dust(1, Lv, 2000, seed=5)
+    a = engine.fetch_labs_dust()
+    assert a.shape[1] == 25 and (a.sum(0) > 0).sum() > 10
+    assert np.isclose(a.sum(), engine.labs_dust_total(), rtol=1e-9)           # (summed on the device, whatever the layout)
+
+
 def test_labs_bolometric_and_random_positions(engine):
     S, p = _ref_pan(packages=5e3)
     tables = _engine_for(engine, S, p)
