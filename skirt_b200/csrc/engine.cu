@@ -389,8 +389,11 @@ int skg_grid_amesh(skg_engine* eh, int N, const double* box, const int* nxyz, co
             {
                 AMeshNodeRec& r = rec[l];
                 for (int c = 0; c < 6; c++) { r.box[c] = box[6 * (size_t)l + c]; r.wallNbr[c] = wallNbr[6 * (size_t)l + c]; }
-                r.cell = cell[l]; r.child0 = child0[l]; r.nx = nxyz[3 * (size_t)l]; r.ny = nxyz[3 * (size_t)l + 1]; r.nz = nxyz[3 * (size_t)l + 2]; r.pad = 0;
+                r.cell = cell[l]; r.child0 = child0[l]; r.nx = nxyz[3 * (size_t)l]; r.ny = nxyz[3 * (size_t)l + 1]; r.nz = nxyz[3 * (size_t)l + 2]; r.parent = 0;
             }
+            // parents: the walkers climb from a wall's neighbour to the ancestor a root search would pass through
+            for (int l = 0; l < N; l++)
+                if (child0[l] >= 0) { const int64_t nc = (int64_t)nxyz[3 * (size_t)l] * nxyz[3 * (size_t)l + 1] * nxyz[3 * (size_t)l + 2]; for (int64_t c = 0; c < nc; c++) rec[child0[l] + c].parent = l; }
             e.amesh.nodeRec = up(e, rec.data(), (size_t)N);
         }
         e.amesh.N = N;

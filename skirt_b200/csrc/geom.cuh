@@ -761,17 +761,16 @@ struct AMeshRecWords
     __device__ __forceinline__ int nx() const { return lo(7); }
     __device__ __forceinline__ int ny() const { return hi(7); }
     __device__ __forceinline__ int nz() const { return lo(8); }
+    __device__ __forceinline__ int parent() const { return hi(8); }
 };
 
 // AdaptiveMeshNode::whichnode(Vec) from the root, AdaptiveMeshNode.cpp:132-142 (+ child :109-128).
 // Returns -1 when outside, -2 when the reference would throw "Can't locate the appropriate child node".
 // On success `rec` holds the record of the returned leaf (one dependent read per level: the child's record is both the
 // containment test of this level and the node of the next).
-__device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, double y, double z, AMeshRecWords& rec)
+// the descent of AdaptiveMeshNode::whichnode from `node`, whose record is in `rec`
+__device__ __forceinline__ int ameshDescend(const AMeshGrid& g, int node, double x, double y, double z, AMeshRecWords& rec)
 {
-    if (!boxContains(g.box, x, y, z)) return -1;
-    int node = 0;
-    rec.load(g.nodeRec);
     int c0;
     while ((c0 = rec.child0()) >= 0)
     {
@@ -795,8 +794,15 @@ __device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, doub
     }
     return node;
 }
+__device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, double y, double z, AMeshRecWords& rec)
+{
+    if (!boxContains(g.box, x, y, z)) return -1;
+    rec.load(g.nodeRec);
+    return ameshDescend(g, 0, x, y, z, rec);
+}
 __device__ __forceinline__ int ameshWhichNode(const AMeshGrid& g, double x, double y, double z)
 { AMeshRecWords rec; return ameshWhichNode(g, x, y, z, rec); }
+static __device__ __noinline__ int ameshWhichNodeCold(const AMeshGrid& g, double x, double y, double z) { return ameshWhichNode(g, x, y, z); }
 
 // AdaptiveMesh::path (AdaptiveMesh.cpp:297-367) one crossing at a time
 struct AMeshWalker
@@ -874,16 +880,40 @@ struct AMeshWalker
             rec.load(g.nodeRec + cand);
             if (rec.contains(x, y, z)) id = cand;
         }
-        if (id == -3) id = ameshWhichNode(g, x, y, z, rec);
+        if (id == -3)
+        {
+            // r lies beside the neighbour at the wall's centre -- in one of its siblings, when the wall borders finer cells --
+            // or the wall has none.  The reference searches from the root (AdaptiveMesh.cpp:341-342); a node whose box holds r
+            // strictly inside lies on that descent (r is in no sibling's closed box at any level above), so the search
+            // resumes from the nearest such ancestor of the neighbour: two or three dependent reads instead of one per level.
+            int from = -1;
+            if (cand >= 0)
+            {
+                int anc = rec.parent();
+                for (int climb = 0; climb < 3 && anc > 0; climb++)
+                {
+                    rec.load(g.nodeRec + anc);
+                    if (x > rec.w[0] && x < rec.w[3] && y > rec.w[1] && y < rec.w[4] && z > rec.w[2] && z < rec.w[5]) { from = anc; break; }
+                    anc = rec.parent();
+                }
+            }
+            if (from < 0)
+            {
+                if (boxContains(g.box, x, y, z)) { rec.load(g.nodeRec); from = 0; }
+                else id = -1;
+            }
+            if (from >= 0) id = ameshDescend(g, from, x, y, z, rec);
+        }
         if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
 
         if (id == oldnode)
         {
             atomicAdd(&ctr->stuckEscaped, 1ull);
             x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
-            id = ameshWhichNode(g, x, y, z, rec);
+            id = ameshWhichNodeCold(g, x, y, z);
             if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
             if (id == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); id = -1; }
+            if (id >= 0) rec.load(g.nodeRec + id);
         }
         if (id < 0) { node = id; alive = false; }
         else adopt(id, rec);

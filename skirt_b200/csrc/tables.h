@@ -61,7 +61,7 @@ struct __align__(32) AMeshNodeRec
 {
     double box[6];
     int cell, child0;
-    int nx, ny, nz; int pad;
+    int nx, ny, nz; int parent;     // (the root is its own parent's 0)
     int wallNbr[6];
 };
 
