@@ -173,6 +173,7 @@ template<bool REGB, bool TINYSEL, bool AHEAD = false> struct CartWalkerT
 {
     static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 4;       // crossings of a batch unrolled in the scheduler (wavefront.cuh): the step is ~100 instructions
+    static constexpr bool kSplitStep = false;
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;       // 1/k per axis (see divInvariant)
     double xE, yE, zE;          // the exit borders themselves: only the axis that was crossed is re-read
@@ -275,6 +276,7 @@ template<bool REGB, bool TINYSEL, bool AHEAD = false> struct CartWalkerT
 template<bool UNIFORM> struct CartFastWalkerT
 {
     static constexpr int kStepUnroll = SKG_FAST_UNROLL;
+    static constexpr bool kSplitStep = false;
     static constexpr bool kPredicated = true;       // provides stepLive(): the scheduler runs batches of crossings branch-free
     double tx, ty, tz, t;
     double rkx, rky, rkz, cx, cy, cz;               // UNIFORM: rk* hold the constant steps |w_a / k_a|, c* are unused
@@ -469,12 +471,21 @@ template<bool HINT> struct TreeWalkerT
 {
     static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;       // large step body: a plain loop (unrolling it costs more in instruction fetch than it gains)
+    // A crossing in two halves: step() finds the wall, moves the position and starts the read of the candidate node's record
+    // (into L1), resolve() tests the candidate and continues from it.  With kSplitStep the scheduler runs the job's work on
+    // the segment between the two, so that the dependent read overlaps it: +9 % on the adaptive mesh (C5), nothing on the
+    // trees (C3: peel-off stage -2 %, path records -4 %), where step() therefore resolves at once.
+#ifndef SKG_TREE_SPLIT
+#define SKG_TREE_SPLIT false
+#endif
+    static constexpr bool kSplitStep = SKG_TREE_SPLIT;
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
     double bx[6];               // box of the current node, carried over from the neighbour test that selected it
     int first[6];               // Neighbor search: first neighbour of each wall of the current node (TreeNodeRec)
     int hbase; unsigned hmeta;  // where its wall-bin blocks start, and which walls have one
     int node, cellv;
+    int pcand, pinfo;           // between step() and resolve(): the candidate node; bit 0 pending, bit 1 strict test, bits 2-4 the wall
     bool alive;
 
     // one node record: 96 bytes as three 256-bit reads
@@ -527,7 +538,7 @@ template<bool HINT> struct TreeWalkerT
             loadNode(g, true);
         }
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
-        alive = true;
+        alive = true; pinfo = 0; pcand = -1;
         return true;
     }
 
@@ -579,8 +590,7 @@ template<bool HINT> struct TreeWalkerT
             y += (ds + eps) * ky;
             z += (ds + eps) * kz;
 
-            const int oldnode = node;
-            bool haveBox = false, haveAll = false;
+            pinfo = 1 | (wall << 2); pcand = -1;
             if (g.search == 1)
             {
                 // TreeNode::whichnode(wall, r), TreeNode.cpp:84-93: first neighbour whose closed box contains r.
@@ -620,40 +630,10 @@ template<bool HINT> struct TreeWalkerT
                     }
                     strict = true;
                 }
-                node = -1;
-                if (cand >= 0)
-                {
-                    double w[12]; loadRec(g.nodeRec + cand, w);
-                    const bool ok = strict ? (x > w[0] && x < w[3] && y > w[1] && y < w[4] && z > w[2] && z < w[5]) : recContains(w, x, y, z);
-                    if (ok) { adopt(cand, w); haveAll = true; }
-                    else if (wm & 1u)
-                    {
-                        // in list order (from the second entry when the first one has just been tested)
-                        const int beg = __ldg(g.nbrStart + 6 * (size_t)oldnode + wall), end = __ldg(g.nbrStart + 6 * (size_t)oldnode + wall + 1);
-                        for (int q = strict ? beg : beg + 1; q < end; q++)
-                        {
-                            const int c2 = __ldg(g.nbrIds + q);
-                            loadRec(g.nodeRec + c2, w);
-                            if (recContains(w, x, y, z)) { adopt(c2, w); haveAll = true; break; }
-                        }
-                    }
-                }
-                // (TreeNode::whichnode(Vec) of the root answers "none" for a point outside the root's box: the usual end of a
-                // path, decided here without the out-of-line call)
-                if (node < 0 && boxContains(g.box, x, y, z)) node = treeWhichNodeCold(g, x, y, z);
+                pcand = cand; pinfo |= strict ? 2 : 0;
+                if (kSplitStep && cand >= 0) { prefetchL1(g.nodeRec + cand); prefetchL1(reinterpret_cast<const char*>(g.nodeRec + cand) + 64); }
             }
-            else node = treeWhichNode(g, x, y, z);
-
-            if (node == oldnode)
-            {
-                atomicAdd(&ctr->stuckEscaped, 1ull);
-                x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
-                node = treeWhichNodeCold(g, x, y, z);
-                haveBox = false; haveAll = false;
-                if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
-            }
-            if (node < 0) alive = false;
-            else if (!haveAll) loadNode(g, !haveBox);
+            if (!kSplitStep) resolve(g, ctr);
             return ds > 0;
         }
 
@@ -729,6 +709,56 @@ template<bool HINT> struct TreeWalkerT
         loadNode(g, true);
         return ds > 0;
     }
+
+    // second half of a TopDown / Neighbor crossing
+    __device__ __forceinline__ void resolve(const TreeGrid& g, Counters* ctr)
+    {
+        if (!(pinfo & 1)) return;
+        const bool strict = (pinfo & 2) != 0; const int wall = pinfo >> 2; const int cand = pcand;
+        pinfo = 0;
+        const unsigned wm = (hmeta >> (5 * wall)) & 31u;
+        {
+            const int oldnode = node;
+            bool haveBox = false, haveAll = false;
+            if (g.search == 1)
+            {
+                node = -1;
+                if (cand >= 0)
+                {
+                    double w[12]; loadRec(g.nodeRec + cand, w);
+                    const bool ok = strict ? (x > w[0] && x < w[3] && y > w[1] && y < w[4] && z > w[2] && z < w[5]) : recContains(w, x, y, z);
+                    if (ok) { adopt(cand, w); haveAll = true; }
+                    else if (wm & 1u)
+                    {
+                        // in list order (from the second entry when the first one has just been tested)
+                        const int beg = __ldg(g.nbrStart + 6 * (size_t)oldnode + wall), end = __ldg(g.nbrStart + 6 * (size_t)oldnode + wall + 1);
+                        for (int q = strict ? beg : beg + 1; q < end; q++)
+                        {
+                            const int c2 = __ldg(g.nbrIds + q);
+                            loadRec(g.nodeRec + c2, w);
+                            if (recContains(w, x, y, z)) { adopt(c2, w); haveAll = true; break; }
+                        }
+                    }
+                }
+                // (TreeNode::whichnode(Vec) of the root answers "none" for a point outside the root's box: the usual end of a
+                // path, decided here without the out-of-line call)
+                if (node < 0 && boxContains(g.box, x, y, z)) node = treeWhichNodeCold(g, x, y, z);
+            }
+            else node = treeWhichNode(g, x, y, z);
+
+            if (node == oldnode)
+            {
+                atomicAdd(&ctr->stuckEscaped, 1ull);
+                x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
+                node = treeWhichNodeCold(g, x, y, z);
+                haveBox = false; haveAll = false;
+                if (node == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); node = -1; }
+            }
+            if (node < 0) alive = false;
+            else if (!haveAll) loadNode(g, !haveBox);
+        }
+    }
+
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -809,11 +839,13 @@ struct AMeshWalker
 {
     static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;
+    static constexpr bool kSplitStep = true;    // see TreeWalkerT
     double x, y, z, kx, ky, kz;
     double rkx, rky, rkz;
     double bx[6];               // box of the current node (carried over from the neighbour test that selected it)
     int wn[6];                  // the node beyond each wall of the current leaf
     int node, cellv;
+    int pcand; bool pending;    // between step() and resolve(): the node beyond the wall just crossed
     bool alive;
 
     // continue from the leaf whose record has been read
@@ -847,7 +879,7 @@ struct AMeshWalker
             adopt(id, rec);
         }
         rkx = 1.0 / kx; rky = 1.0 / ky; rkz = 1.0 / kz;
-        alive = true;
+        alive = true; pending = false; pcand = -1;
         return true;
     }
 
@@ -871,8 +903,19 @@ struct AMeshWalker
         y += (ds + eps) * ky;
         z += (ds + eps) * kz;
 
+        pcand = wall == 0 ? wn[0] : wall == 1 ? wn[1] : wall == 2 ? wn[2] : wall == 3 ? wn[3] : wall == 4 ? wn[4] : wn[5];
+        pending = true;
+        if (pcand >= 0) { prefetchL1(g.nodeRec + pcand); prefetchL1(reinterpret_cast<const char*>(g.nodeRec + pcand) + 64); }
+        return ds > 0;
+    }
+
+    // second half of a crossing (see TreeWalkerT): the node beyond the wall, AdaptiveMesh.cpp:338-342
+    __device__ __forceinline__ void resolve(const AMeshGrid& g, Counters* ctr)
+    {
+        if (!pending) return;
+        pending = false;
         const int oldnode = node;
-        const int cand = wall == 0 ? wn[0] : wall == 1 ? wn[1] : wall == 2 ? wn[2] : wall == 3 ? wn[3] : wall == 4 ? wn[4] : wn[5];
+        const int cand = pcand;
         AMeshRecWords rec;
         int id = -3;
         if (cand >= 0)
@@ -904,20 +947,19 @@ struct AMeshWalker
             }
             if (from >= 0) id = ameshDescend(g, from, x, y, z, rec);
         }
-        if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
+        if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return; }
 
         if (id == oldnode)
         {
             atomicAdd(&ctr->stuckEscaped, 1ull);
             x = nextAfterAlong(x, kx); y = nextAfterAlong(y, ky); z = nextAfterAlong(z, kz);
             id = ameshWhichNodeCold(g, x, y, z);
-            if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return ds > 0; }
+            if (id == -2) { atomicAdd(&ctr->errors, 1ull); alive = false; return; }
             if (id == oldnode) { atomicAdd(&ctr->stuckTerminated, 1ull); id = -1; }
             if (id >= 0) rec.load(g.nodeRec + id);
         }
         if (id < 0) { node = id; alive = false; }
         else adopt(id, rec);
-        return ds > 0;
     }
 };
 
@@ -1056,6 +1098,7 @@ template<bool EXACT> struct VoroWalkerT
 {
     static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;
+    static constexpr bool kSplitStep = false;
     double x, y, z, kx, ky, kz;
     int mr, rr;                 // current cell and the first slot of its crossing record
     int guard;
@@ -1279,6 +1322,7 @@ struct SymWalker
 {
     static constexpr bool kPredicated = false;
     static constexpr int kStepUnroll = 1;
+    static constexpr bool kSplitStep = false;
     double x, y, z, kx, ky, kz;     // Sphere2D: current position and direction; Cylinder2D: z and kz are the running height / its cosine
     double p, q, qN, zN, kq;        // impact parameter, running and next radial path coordinates (Sphere1D, Cylinder2D); next z border
     int i, k, imin; int phase;      // cell indices; phase 0 inward, 1 outward

@@ -694,6 +694,9 @@ template<int KIND, bool SINGLE, bool POL> struct ContPeelJob
                         else if constexpr (KIND == GRID_SYM) seg = w2.step(G.sym, ctr, m2, ds2);
                         else seg = w2.step(G.voro, ctr, m2, ds2);
                         if (seg) { nSeg++; tau2 += KappaRho{P.med.rho, P.med.kext + ell, Ncomp, Nlambda}(m2) * ds2; }
+                        // (walkers whose crossing comes in two halves: geom.cuh, kSplitStep)
+                        if constexpr (KIND == GRID_TREE) w2.resolve(G.tree, ctr);
+                        else if constexpr (KIND == GRID_AMESH) w2.resolve(G.amesh, ctr);
                     }
                 }
                 const double Lw = L * (factorm * w);                                       // launchScatteringPeelOff(pp, bfrnew, bfkobs, factorm*I)

@@ -141,6 +141,9 @@ __device__ __forceinline__ void runJobsStep(const GridT& grid, Counters* ctr, Jo
                         int m; double ds;
                         const bool seg = w.step(grid, ctr, m, ds);
                         const bool cont = seg ? job.segment(m, ds) : true;
+                        // walkers that split a crossing: the read of the next node's record, started by step(), has been
+                        // travelling while the job worked on the segment (a walk the job ends needs no next node)
+                        if constexpr (Walker::kSplitStep) { if (cont) w.resolve(grid, ctr); }
                         if (!cont || !w.alive) state = 2;
                     }
                 }
