@@ -448,23 +448,25 @@ int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* 
             }
             e.voro.rec = up(e, rec.data(), rec.size());
         }
+        e.voro.planes = nullptr;
+        // plane records of the shooting stages (tables.h): the layout of the crossing records with normals in place of positions.
+        // Built where the table stays resident in L2 (126 MB): there the neighbour loop is bound by instructions and the
+        // planes' shorter loop pays (+31 % at 200 000 cells); a mesh whose records come from DRAM at every crossing measured
+        // 8 % slower with them (1e6 cells) and keeps walking the crossing records.  SKG_VORO_PLANES=0/1 overrides the rule.
+        bool wantPlanes = 32.0 * ((double)std::max(0, nbrStart[N]) + N) <= 128.0 * 1024 * 1024;
+        if (const char* v = getenv("SKG_VORO_PLANES")) wantPlanes = atoi(v) != 0;
+        if (wantPlanes)
         {
-            // plane records of the shooting stages (tables.h)
-            std::vector<int> ps((size_t)N + 1, 0);
-            size_t slots = 0;
-            for (int m = 0; m < N; m++) { const int cnt = nbrStart[m + 1] - nbrStart[m]; ps[m] = (int)slots; slots += 1 + (size_t)cnt + ((size_t)cnt + 3) / 4; }
-            if (slots + 8 > 2147483647ull) throw Error("too many Voronoi neighbours for int32 record indices");
-            ps[N] = (int)slots;
-            std::vector<double> pl(4 * (slots + 8), 0.0);
+            const size_t total = (size_t)std::max(0, nbrStart[N]);
+            std::vector<double> pl(4 * (total + N + 8), 0.0);
             auto pack = [](int lo, int hi) { const long long v = (long long)(unsigned)lo | ((long long)hi << 32); double d; std::memcpy(&d, &v, 8); return d; };
             const double lo[3] = {extent[0], extent[2], extent[4]}, hi[3] = {extent[1], extent[3], extent[5]};
             for (int m = 0; m < N; m++)
             {
                 const int beg = nbrStart[m], cnt = nbrStart[m + 1] - beg;
-                double* h = pl.data() + 4 * (size_t)ps[m];
+                double* h = pl.data() + 4 * ((size_t)beg + m);
                 const double* pr = particles + 3 * (size_t)m;
                 h[0] = pr[0]; h[1] = pr[1]; h[2] = pr[2]; h[3] = pack(cnt, 0);
-                double* tags = h + 4 * (size_t)(cnt + 1);
                 for (int q = 0; q < cnt; q++)
                 {
                     const int id = nbrIds[beg + q];
@@ -474,20 +476,19 @@ int skg_grid_voronoi(skg_engine* eh, int N, const double* particles, const int* 
                         // the bisector plane of p and p_i: n = p_i - p, n.(r - p) = |n|^2 / 2
                         const double* pi = particles + 3 * (size_t)id;
                         for (int c = 0; c < 3; c++) s4[c] = pi[c] - pr[c];
-                        s4[3] = 0.5 * (s4[0] * s4[0] + s4[1] * s4[1] + s4[2] * s4[2]);
-                        tags[q] = pack(id, ps[id]);
+                        s4[3] = pack(id, nbrStart[id] + id);
                     }
                     else
                     {
-                        // walls -1 .. -6: xmin, xmax, ymin, ymax, zmin, zmax (VoronoiMesh.cpp:800-812), outward normal
+                        // walls -1 .. -6: xmin, xmax, ymin, ymax, zmin, zmax (VoronoiMesh.cpp:800-812) at distance D along the axis: the
+                        // bisector plane towards the particle's mirror image, n = 2 D along the outward normal
                         const int a = (-1 - id) >> 1; const bool upper = ((-1 - id) & 1) != 0;
-                        s4[a] = upper ? 1.0 : -1.0;
-                        s4[3] = upper ? hi[a] - pr[a] : pr[a] - lo[a];
-                        tags[q] = pack(id, 0);
+                        s4[a] = upper ? 2.0 * (hi[a] - pr[a]) : -2.0 * (pr[a] - lo[a]);
+                        s4[3] = pack(id, 0);
                     }
                 }
             }
-            e.voro.planes = up(e, pl.data(), pl.size()); e.voro.planeStart = up(e, ps.data(), ps.size());
+            e.voro.planes = up(e, pl.data(), pl.size());
         }
         // extent arrives as xmin,xmax,ymin,ymax,zmin,zmax (Box setters order); stored as min corner, max corner
         e.voro.ext[0] = extent[0]; e.voro.ext[1] = extent[2]; e.voro.ext[2] = extent[4];

@@ -1070,30 +1070,43 @@ __device__ __forceinline__ int voroCellIndex(const VoroGrid& g, double x, double
     int k = cellIndex1(z, g.ext[2], g.ext[5], nb);
     size_t b = (size_t)i * nb * nb + (size_t)j * nb + k;
     int tree = __ldg(g.blkTree + b);
-    if (tree >= 0) return voroKdNearest(g, tree, x, y, z);
     int beg = __ldg(g.blkStart + b), end = __ldg(g.blkStart + b + 1);
+    // A block with a search tree (more than five cells, VoronoiMesh.cpp:371) answers with the nearest of its cells, which the
+    // tree search (Node::nearest) finds through ~25 dependent reads.  The same cell is the minimum over the block's list --
+    // independent reads, three round trips in all -- unless two cells are at bit-equal distance: only then does the order
+    // of the tree's comparisons decide, and the tree is searched.  (Blocks without tree: the reference's own loop, first minimum.)
+    if (tree >= 0 && (end - beg < 1 || end - beg > 64)) return voroKdNearest(g, tree, x, y, z);
     int m = -1;
     double mdist = SKG_DBL_MAX;
+    bool tie = false;
+#pragma unroll 4
     for (int q = beg; q < end; q++)
     {
         int id = __ldg(g.blkIds + q);
         double idist = voroSD(g, id, x, y, z);
-        if (idist < mdist) { m = id; mdist = idist; }
+        if (idist < mdist) { m = id; mdist = idist; tie = false; }
+        else if (idist == mdist) tie = true;
     }
+    if (tree >= 0 && tie) return voroKdNearest(g, tree, x, y, z);
     return m;
 }
 
 // VoronoiMesh::path (VoronoiMesh.cpp:749-844) one crossing at a time.
 // EXACT: the reference's arithmetic -- every candidate wall distance is the quotient si = n.(p - r) / n.k and the smallest
 // positive one wins, first in list order among equals (the deterministic-geometry entry points: bit-exact paths).
-// !EXACT (the photon shooting stages, whose results are Monte Carlo estimates): every candidate -- bisector planes and
-// domain walls alike -- is a plane {n, c} relative to the cell's particle p (tables.h, `planes`), its distance the fraction
-// num / den = (c - n.(r - p)) / n.k.  Candidates are compared as fractions, num_i * den_best < num_best * den_i (all
-// denominators positive), in the same list order with the same first-wins rule; only the winner is divided, and only the
-// winner's tag (neighbour id, its record) is read.  The loop body is six fused multiply-adds, two products and a compare,
-// branch-free -- the reference's arithmetic (the EXACT walker) costs three times that per neighbour.  Results agree with
-// the exact walker to rounding (tests: 1e-10 on optical depths); two candidates whose quotients differ by less than the
-// rounding of the products may swap, which moves a crossing by an ulp.
+// !EXACT (the photon shooting stages, whose results are Monte Carlo estimates), meshes whose records do not stay in L2
+// (no plane table): the crossing records with the candidates compared as fractions, num_i * den_best < num_best * den_i
+// (all denominators positive), in list order with the same first-wins rule; only the winner is divided.
+// !EXACT, meshes whose table stays in L2 (`planes`, built by the engine up to 128 MB): every candidate -- bisector planes and
+// domain walls alike -- is a normal n relative to the cell's particle p (tables.h, `planes`; a wall is the bisector towards
+// p's mirror image), its distance the fraction num / den = n.(n - 2 (r - p)) / 2 n.k.  Candidates are compared as fractions,
+// num_i * den_best < num_best * den_i (all denominators positive), in the same list order with the same first-wins rule;
+// only the winner is divided.  The loop body is three subtractions, six multiply-adds, two products and a compare,
+// branch-free -- the reference's arithmetic (the EXACT walker) costs twice that per neighbour, with a division and a
+// branch: C4 at 200 000 cells +31 %.  At 1e6 cells, where every crossing reads its 544 bytes from DRAM, the same loop
+// measured 8 % slower than the crossing records (profiles/r02_q_voronoi_planes.txt), hence the size rule.
+// Results agree with the exact walker to rounding (tests: 1e-10 on optical depths); two candidates whose quotients differ
+// by less than the rounding of the products may swap, which moves a crossing by an ulp.
 template<bool EXACT> struct VoroWalkerT
 {
     static constexpr bool kPredicated = false;
@@ -1123,8 +1136,8 @@ template<bool EXACT> struct VoroWalkerT
         alive = true;
         return true;
     }
-    // first slot of the crossing record (EXACT) / plane record (!EXACT) of a cell
-    static __device__ __forceinline__ int blockOf(const VoroGrid& g, int m) { return EXACT ? __ldg(g.nbrStart + m) + m : __ldg(g.planeStart + m); }
+    // first slot of the crossing record (EXACT) / plane record (!EXACT) of a cell: the two tables share their layout
+    static __device__ __forceinline__ int blockOf(const VoroGrid& g, int m) { return __ldg(g.nbrStart + m) + m; }
 
     static __device__ __forceinline__ void loadSlot(const double* p, double (&w)[4])
     { asm("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(w[0]), "=d"(w[1]), "=d"(w[2]), "=d"(w[3]) : "l"(p)); }
@@ -1138,13 +1151,12 @@ template<bool EXACT> struct VoroWalkerT
 #pragma unroll
         for (int u = 0; u < 4; u++) loadSlot(R + 4 * (u + 1), e[u]);        // the table ends with 8 spare slots
         const int cnt = (int)(__double_as_longlong(h[3]) & 0xffffffffll);
-        // the rest of the block (planes, then tags) into L1 while the first group is evaluated
-        const int slots = 1 + cnt + ((cnt + 3) >> 2);
-        for (int q0 = 5; q0 < slots; q0 += 4) prefetchL1(R + 4 * q0);
-        prefetchL1(R + 4 * (slots - 1));
-        const double qx = x - h[0], qy = y - h[1], qz = z - h[2];
-        double nb = 0.0, db = 1.0;              // best fraction nb / db (db > 0)
-        int best = -1;
+        // the rest of the block (typically 12 more slots = 3 lines): into L1 while the first group is evaluated
+        for (int q0 = 4; q0 < cnt; q0 += 4) prefetchL1(R + 4 * (q0 + 1));
+        const double qx2 = 2.0 * (x - h[0]), qy2 = 2.0 * (y - h[1]), qz2 = 2.0 * (z - h[2]);
+        double nb = 0.0, db = 1.0;              // best fraction nb / db (db > 0) = twice the distance
+        long long btag = 0;
+        bool have = false;
         for (int q0 = 0; q0 < cnt; q0 += 4)
         {
             if (q0)
@@ -1155,14 +1167,16 @@ template<bool EXACT> struct VoroWalkerT
 #pragma unroll
             for (int u = 0; u < 4; u++)
             {
-                const double num = __fma_rn(-e[u][0], qx, __fma_rn(-e[u][1], qy, __fma_rn(-e[u][2], qz, e[u][3])));
-                const double den = __fma_rn(e[u][0], kx, __fma_rn(e[u][1], ky, e[u][2] * kz));
+                // n.(n - 2 (r - p)) / n.k = twice the distance to the plane along the ray
+                const double nx = e[u][0], ny = e[u][1], nz = e[u][2];
+                const double num = __fma_rn(nx, nx - qx2, __fma_rn(ny, ny - qy2, nz * (nz - qz2)));
+                const double den = __fma_rn(nx, kx, __fma_rn(ny, ky, nz * kz));
                 // si > 0 && si < sq with si = num / den, sq = nb / db
-                const bool better = q0 + u < cnt && den > 0 && num > 0 && (best < 0 || num * db < nb * den);
-                if (better) { nb = num; db = den; best = q0 + u; }
+                const bool better = q0 + u < cnt && den > 0 && num > 0 && (!have || num * db < nb * den);
+                if (better) { nb = num; db = den; btag = __double_as_longlong(e[u][3]); have = true; }
             }
         }
-        if (best < 0)
+        if (!have)
         {
             // r += bfk*_eps  (Vec operator*(Vec,double))
             x += kx * eps; y += ky * eps; z += kz * eps;
@@ -1171,11 +1185,10 @@ template<bool EXACT> struct VoroWalkerT
             if (mr < 0) alive = false; else rr = blockOf(g, mr);
             return false;
         }
-        const long long tag = __ldg(reinterpret_cast<const long long*>(R + 4 * (size_t)(cnt + 1)) + best);
-        const double sq = nb / db;              // > 0 by construction
+        const double sq = 0.5 * (nb / db);      // > 0 by construction
         mseg = mr; ds = sq;
         x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
-        mr = (int)(tag & 0xffffffffll); rr = (int)(tag >> 32);
+        mr = (int)(btag & 0xffffffffll); rr = (int)(btag >> 32);
         if (mr < -6) { atomicAdd(&ctr->errors, 1ull); }
         if (mr < 0) alive = false;
         return true;
@@ -1183,9 +1196,11 @@ template<bool EXACT> struct VoroWalkerT
 
     __device__ __forceinline__ bool step(const VoroGrid& g, Counters* ctr, int& mseg, double& ds)
     {
-        if constexpr (!EXACT) return stepPlanes(g, ctr, mseg, ds);
+        // (warp-uniform: a property of the grid -- the engine builds plane records for meshes whose table stays in L2)
+        if constexpr (!EXACT) { if (g.planes) return stepPlanes(g, ctr, mseg, ds); }
         const double eps = g.eps;
-        double sq = SKG_DBL_MAX;                // best quotient; mq == NO_INDEX: none yet
+        double sq = SKG_DBL_MAX;                // EXACT: best quotient
+        double nb = 0.0, db = 1.0;              // !EXACT: best fraction nb / db (db > 0); mq == NO_INDEX: none yet
         const int NO_INDEX = -99;
         int mq = NO_INDEX, rq = 0;
         // the neighbour loop of VoronoiMesh.cpp:777-828 over the cell's crossing record (tables.h), four neighbours at a
@@ -1213,6 +1228,7 @@ template<bool EXACT> struct VoroWalkerT
                 if (q0 + u >= cnt) break;
                 const long long tag = __double_as_longlong(e[u][3]);
                 const int mi = (int)(tag & 0xffffffffll);
+                if (EXACT)
                 {
                     double si = 0;
                     if (mi >= 0)
@@ -1241,6 +1257,30 @@ template<bool EXACT> struct VoroWalkerT
                     }
                     if (si > 0 && si < sq) { sq = si; mq = mi; rq = (int)(tag >> 32); }
                 }
+                else
+                {
+                    // the candidate as a fraction num / den, den > 0 (a wall: (border - r_a) / k_a with the sign moved into num)
+                    double num, den;
+                    if (mi >= 0)
+                    {
+                        const double pix = e[u][0], piy = e[u][1], piz = e[u][2];
+                        const double nxv = pix - prx, nyv = piy - pry, nzv = piz - prz;
+                        den = nxv * kx + nyv * ky + nzv * kz;
+                        num = nxv * (0.5 * (pix + prx) - x) + nyv * (0.5 * (piy + pry) - y) + nzv * (0.5 * (piz + prz) - z);
+                    }
+                    else
+                    {
+                        if (mi < -6) { atomicAdd(&ctr->errors, 1ull); alive = false; return false; }
+                        const int a = (-1 - mi) >> 1;                                   // axis of the wall; odd ids are the lower faces
+                        const double ka = a == 0 ? kx : (a == 1 ? ky : kz), ra = a == 0 ? x : (a == 1 ? y : z);
+                        const double border = g.ext[a + (((-1 - mi) & 1) ? 3 : 0)];
+                        num = border - ra; den = ka;
+                        if (den < 0) { num = -num; den = -den; }
+                    }
+                    // si > 0 && si < sq with si = num / den, sq = nb / db
+                    const bool better = den > 0 && num > 0 && (mq == NO_INDEX || num * db < nb * den);
+                    if (better) { nb = num; db = den; mq = mi; rq = (int)(tag >> 32); }
+                }
             }
         }
         if (mq == NO_INDEX)
@@ -1252,6 +1292,7 @@ template<bool EXACT> struct VoroWalkerT
             if (mr < 0) alive = false; else rr = blockOf(g, mr);
             return false;
         }
+        if (!EXACT) sq = nb / db;
         mseg = mr; ds = sq;                     // sq > 0 by construction
         x += (sq + eps) * kx; y += (sq + eps) * ky; z += (sq + eps) * kz;
         mr = mq; rr = rq;

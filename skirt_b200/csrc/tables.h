@@ -94,12 +94,11 @@ struct VoroGrid
     // (neighbour count, 0)} followed by one slot per neighbour in list order {particle of the neighbour, (id, first slot of
     // the neighbour's own block)} -- a crossing reads one contiguous block instead of ids -> particle positions
     const double* rec;
-    // the same for the shooting stages (whose results are Monte Carlo estimates): every candidate wall of a cell -- the
-    // bisector planes towards its neighbours and the walls of the domain alike -- as a plane {n, c} in coordinates relative
-    // to the cell's particle, so that the distance along a ray is (c - n.(r - p)) / n.k for all of them.  Cell m owns the
-    // 32-byte slots from planeStart[m]: a header {particle of m, (neighbour count, 0)}, one plane slot per neighbour in list
-    // order, then the tags {id, planeStart[id]} of the neighbours, four to a slot (read for the winning wall only)
-    const double* planes; const int* planeStart;
+    // the same for the shooting stages (whose results are Monte Carlo estimates), same slots: the header {particle p of m,
+    // (neighbour count, 0)}, then per neighbour {n = p_i - p, (id, first slot of the neighbour's block)} -- the bisector plane
+    // is n.(r - p) = |n|^2 / 2, the distance along a ray (|n|^2 / 2 - n.(r - p)) / n.k.  A wall of the domain at distance D
+    // from p is the bisector towards p's mirror image: n = 2 D along the outward normal, so that one formula serves all
+    const double* planes;
     double ext[6];                  // xmin,ymin,zmin,xmax,ymax,zmax
     double eps;
     int N, nb;
