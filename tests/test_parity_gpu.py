@@ -222,6 +222,17 @@ def test_shooting_walker_agrees_with_the_exact_walker(engine, name):
             assert bad.sum() <= max(2, len(tau) // 500), f"{bad.sum()} of {len(tau)} rays differ"
 
 
+@pytest.mark.parametrize("planes", ["0", "1"])
+def test_both_voronoi_shooting_walkers(engine, planes, monkeypatch):
+    """the shooting stages walk plane records on Voronoi meshes whose table stays in L2 and the crossing records on larger ones
+    (skg_grid_voronoi; SKG_VORO_PLANES overrides the size rule): both against the reference's golden optical depths"""
+    monkeypatch.setenv("SKG_VORO_PLANES", planes)        # read when the grid is set
+    _, _, d = _setup(engine, "voronoi")
+    tau = engine.opticaldepth(d["r"], d["k"], 0, None, mc_walker=True)
+    np.testing.assert_allclose(tau, d["tau_inf"], rtol=1e-10, atol=1e-13 * float(np.max(d["tau_inf"])))
+    np.testing.assert_allclose(engine.opticaldepth(d["r"], d["k"], 0, None), d["tau_inf"], rtol=1e-12)       # (the exact walker does not depend on the switch)
+
+
 def test_shooting_walker_on_the_full_size_grid(engine):
     """2^18 rays through the 100^3 grid of C1/C2: exact and shooting walkers agree to 1e-10 on every optical depth"""
     from skirt_b200 import configs
