@@ -117,6 +117,22 @@ public:
 private:
     double _ratio = 1;
 };
+class LogMesh : public Mesh       // LogMesh.cpp:47-53; NR::zerologgrid, NR.hpp:283-289 (an anchored mesh: radial coordinates)
+{
+public:
+    void setCentralBinFraction(double tc) { if (tc <= 0 || tc >= 1) SKIRT_FATAL("The central bin width fraction should be within range ]0,1["); _tc = tc; }
+    std::vector<double> mesh() const override
+    {
+        if (_N <= 1) { LinMesh l; l.setNumBins(1); return l.mesh(); }
+        if (_tc <= 0 || _tc >= 1) SKIRT_FATAL("The central bin width fraction should be within range ]0,1[");
+        std::vector<double> v(_N + 1, 0.0);
+        const double logxmin = std::log10(_tc), dlogx = std::log10(1.0 / _tc) / (_N - 1);
+        for (int i = 0; i < _N; i++) v[i + 1] = std::pow(10, logxmin + i * dlogx);
+        return v;
+    }
+private:
+    double _tc = 0;
+};
 class SymPowMesh : public Mesh    // NR::sympowgrid, NR.hpp:225-261
 {
 public:

@@ -30,6 +30,7 @@ static Mesh* makeMesh(std::istringstream& in, int n)
     if (kind == "lin") m = new LinMesh();
     else if (kind == "pow") { auto* p = new PowMesh(); double r; in >> r; p->setRatio(r); m = p; }
     else if (kind == "sympow") { auto* p = new SymPowMesh(); double r; in >> r; p->setRatio(r); m = p; }
+    else if (kind == "log") { auto* p = new LogMesh(); double tc; in >> tc; p->setCentralBinFraction(tc); m = p; }
     else SKIRT_FATAL("unknown mesh " + kind);
     m->setNumBins(n);
     return m;

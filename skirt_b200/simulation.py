@@ -85,6 +85,23 @@ class PowMesh:
         return np.array([0.0 + (1. - math.pow(q, i)) / (1. - qn) * 1.0 for i in range(n + 1)])
 
 
+class LogMesh:
+    """LogMesh (LogMesh.cpp:47-53; NR::zerologgrid, NR.hpp:283-289): an anchored mesh for radial coordinates -- a first bin
+    [0, tc] of the given central bin fraction, the others distributed logarithmically between tc and 1"""
+    def __init__(self, numBins, centralBinFraction):
+        self.numBins = int(numBins); self.centralBinFraction = float(centralBinFraction)
+        if not (0 < self.centralBinFraction < 1):
+            raise FatalError("The central bin width fraction should be within range ]0,1[")
+
+    def mesh(self):
+        import math
+        n, tc = self.numBins, self.centralBinFraction
+        if n <= 1:
+            return LinMesh(1).mesh()
+        logxmin = math.log10(tc); dlogx = math.log10(1.0 / tc) / (n - 1)
+        return np.array([0.0] + [math.pow(10, logxmin + i * dlogx) for i in range(n)])
+
+
 class SymPowMesh:
     def __init__(self, numBins, ratio):
         self.numBins = int(numBins); self.ratio = float(ratio)

@@ -2,6 +2,8 @@
 the reference's own grid classes (oracle/_ref): for the same subdivision decisions / mesh file / particles the flattened
 tables -- node boxes and ids, cell numbers, neighbour lists IN THE REFERENCE'S ORDER, wall neighbours, Voro++ neighbour
 lists, block lists and search trees -- are identical.  CPU only."""
+import os
+
 import numpy as np
 import pytest
 
@@ -143,3 +145,47 @@ def test_two_phase_grid_weights():
     np.testing.assert_allclose(a[:, 0], b[:, 0] * w, rtol=1e-15)
     with pytest.raises(sim.FatalError, match="filling factor"):
         sim.TwoPhaseDustGrid(*ext, sim.LinMesh(4), sim.LinMesh(4), sim.LinMesh(4), fillingFactor=1.0, contrast=2.0)
+
+
+def _logmesh_golden():
+    """tests/golden/logmesh.txt: borders printed by the reference's own NR::zerologgrid (make_logmesh_golden.sh), hex floats"""
+    path = os.path.join(os.path.dirname(__file__), "golden", "logmesh.txt")
+    for line in open(path):
+        t = line.split()
+        yield int(t[0]), float.fromhex(t[1]), np.array([float.fromhex(x) for x in t[2:]])
+
+
+def test_logmesh_mirror_reproduces_the_reference_borders():
+    """LogMesh (LogMesh.cpp:47-53 -> NR::zerologgrid): the Python mirror, bit for bit, and its parameter check"""
+    from skirt_b200 import simulation as sim
+    cases = list(_logmesh_golden())
+    assert len(cases) == 20
+    for n, tc, want in cases:
+        got = sim.LogMesh(n, tc).mesh()
+        assert got.shape == (n + 1,) and np.array_equal(got, want), (n, tc)
+        assert got[0] == 0.0 and got[1] == pytest.approx(tc) and got[-1] == pytest.approx(1.0)
+    assert np.array_equal(sim.LogMesh(1, 0.5).mesh(), [0.0, 1.0])
+    with pytest.raises(sim.FatalError):
+        sim.LogMesh(10, 1.0)
+    # a radial mesh of a spherical grid
+    g = sim.Sphere1DDustGrid(18000 * common.PC, sim.LogMesh(30, 1e-3))
+    rv = g.tables()["rv"]
+    assert len(rv) == 31 and rv[0] == 0.0 and np.all(np.diff(rv) > 0) and rv[-1] == pytest.approx(18000 * common.PC)
+
+
+def test_logmesh_cpp_mirror_reproduces_the_reference_borders(tmp_path):
+    """the C++ host layer's LogMesh (skirt_b200/host/SimulationItems.hpp) against the same golden borders"""
+    import shutil, subprocess
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not cxx:
+        pytest.skip("no C++ compiler")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "m.cpp"
+    src.write_text('#include <cstdio>\n#include <cstdlib>\n#include "SimulationItems.hpp"\n'
+                   'int main(int argc, char** argv) { skirt::LogMesh m; m.setNumBins(std::atoi(argv[1])); m.setCentralBinFraction(std::strtod(argv[2], 0));\n'
+                   '  for (double v : m.mesh()) std::printf("%a\\n", v); return 0; }\n')
+    exe = tmp_path / "m"
+    subprocess.run([cxx, "-std=c++17", "-O2", f"-I{root}/skirt_b200/host", f"-I{root}/include", str(src), "-o", str(exe)], check=True)
+    for n, tc, want in list(_logmesh_golden())[::3]:
+        out = subprocess.run([str(exe), str(n), tc.hex()], check=True, capture_output=True, text=True).stdout.split()
+        assert np.array_equal([float.fromhex(x) for x in out], want), (n, tc)
