@@ -186,6 +186,13 @@ int skg_sample_density(skg_engine* e, int Ncomp, const skg_source* geometries, c
 int skg_sample_boxes(skg_engine* e, int64_t n, const double* box, int Ncomp, const skg_source* geometries, const double* norm,
                      int sampleCount, uint64_t seed, double* mass);
 
+/* The same samples, and besides the mass (bit-identical to skg_sample_boxes) the density dispersion of every box,
+ * dispersion[q] = (max - min) / max of the sampled total densities, 0 when max == 0
+ * (TreeNodeSampleDensityCalculator::densityDispersion, TreeNodeSampleDensityCalculator.cpp:62-67): what
+ * TreeDustGrid::subdivide compares with maxDensDispFraction (TreeDustGrid.cpp:215-221). */
+int skg_sample_boxes_dispersion(skg_engine* e, int64_t n, const double* box, int Ncomp, const skg_source* geometries,
+                                const double* norm, int sampleCount, uint64_t seed, double* mass, double* dispersion);
+
 /* n launches of StellarSystem::launch(pp, ell, 1.0) with the engine's samplers (the kernel the shooting phase uses):
  * positions r[3n], directions k[3n] and bias-weighted luminosities L[n]; for distribution-level checks */
 int skg_sample_launch(skg_engine* e, int ell, int n, uint64_t seed, double* r, double* k, double* L);

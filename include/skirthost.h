@@ -22,7 +22,7 @@ const char* skh_last_error(void);
 
 /* ---- octree / binary tree, grown level by level --------------------------------------------------------------------
  * kind 0 octree, 1 binary tree.  Loop: skh_tree_frontier -> (size > 0) -> skh_tree_frontier_boxes -> estimate the mass in
- * every box (skg_sample_boxes) -> skh_tree_subdivide(flags) ... until size == 0; then skh_tree_finish + skh_tree_tables.
+ * every box (skg_sample_boxes, or skg_sample_boxes_dispersion when maxDensDispFraction > 0) -> skh_tree_subdivide(flags) ... until size == 0; then skh_tree_finish + skh_tree_tables.
  * needsDecision is 0 for the levels <= minLevel (every node is subdivided: flags may be NULL). */
 typedef struct skh_tree skh_tree;
 int skh_tree_create(int kind, const double* extent6, int minLevel, int maxLevel, skh_tree** out);

@@ -335,12 +335,17 @@ class Engine:
         self._chk(self._lib.skg_sample_density(self.h, len(geometries), arr, _vp(nrm), int(sample_count), C.c_uint64(int(seed)), _vp(rho)))
         return rho
 
-    def sample_boxes(self, boxes, geometries, norm, sample_count=100, seed=4357):
+    def sample_boxes(self, boxes, geometries, norm, sample_count=100, seed=4357, dispersion=False):
         """skg_sample_boxes: dust mass in every box (TreeNodeSampleDensityCalculator on the device); boxes[n, 6] =
-        xmin,ymin,zmin,xmax,ymax,zmax"""
+        xmin,ymin,zmin,xmax,ymax,zmax.  dispersion=True: skg_sample_boxes_dispersion, returns (mass, densityDispersion)"""
         arr, keep = self._source_array(geometries)
         nrm = _f64(norm); b = _f64(boxes).reshape(-1, 6)
         mass = np.zeros(len(b))
+        if dispersion:
+            disp = np.zeros(len(b))
+            self._chk(self._lib.skg_sample_boxes_dispersion(self.h, C.c_int64(len(b)), _vp(b), len(geometries), arr, _vp(nrm),
+                                                            int(sample_count), C.c_uint64(int(seed)), _vp(mass), _vp(disp)))
+            return mass, disp
         self._chk(self._lib.skg_sample_boxes(self.h, C.c_int64(len(b)), _vp(b), len(geometries), arr, _vp(nrm), int(sample_count),
                                              C.c_uint64(int(seed)), _vp(mass)))
         return mass

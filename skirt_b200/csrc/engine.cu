@@ -698,7 +698,11 @@ int skg_sample_launch(skg_engine* eh, int ell, int n, uint64_t seed, double* r, 
 int skg_sample_density(skg_engine* eh, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* rho)
 { return guarded([&]{ mcSampleDensity(E(eh), Ncomp, geoms, norm, sampleCount, seed, rho); }); }
 int skg_sample_boxes(skg_engine* eh, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* mass)
-{ return guarded([&]{ mcSampleBoxes(E(eh), n, box, Ncomp, geoms, norm, sampleCount, seed, mass); }); }
+{ return guarded([&]{ mcSampleBoxes(E(eh), n, box, Ncomp, geoms, norm, sampleCount, seed, mass, nullptr); }); }
+int skg_sample_boxes_dispersion(skg_engine* eh, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount,
+                                uint64_t seed, double* mass, double* dispersion)
+{ return guarded([&]{ if (n > 0 && !dispersion) throw Error("skg_sample_boxes_dispersion: bad arguments");
+                      mcSampleBoxes(E(eh), n, box, Ncomp, geoms, norm, sampleCount, seed, mass, dispersion); }); }
 int skg_reset_results(skg_engine* eh) { return guarded([&]{ mcResetResults(E(eh)); }); }
 int skg_dust_library(skg_engine* eh, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda)
 { return guarded([&]{ if (!volumes || !kappaabs || !lambda || !dlambda) throw Error("skg_dust_library: null table"); mcDustLibrary(E(eh), volumes, kappaabs, lambda, dlambda); }); }

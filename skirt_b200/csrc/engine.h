@@ -149,7 +149,7 @@ void mcLabsBolometric(Engine& e, double* host);
 void mcDustLibrary(Engine& e, const double* volumes, const double* kappaabs, const double* lambda, const double* dlambda);
 double* mcDustCellLuminosities(Engine& e);
 void mcSampleDensity(Engine& e, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* rho);
-void mcSampleBoxes(Engine& e, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* mass);
+void mcSampleBoxes(Engine& e, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* mass, double* dispersion = nullptr);
 double mcAtomicRate(Engine& e, uint64_t n, int cells);
 void mcSampleLaunch(Engine& e, int ell, int n, uint64_t seed, double* r, double* k, double* L);
 void mcRunDust(Engine& e, const skg_mc_params& p, int phase, double emissionBias, int mem, const double* Lcell, skg_mc_stats* stats);

@@ -1874,42 +1874,58 @@ void mcSampleDensity(Engine& e, int Ncomp, const skg_source* geoms, const double
 // TreeNodeSampleDensityCalculator (TreeNodeSampleDensityCalculator.cpp:25-45) for a batch of boxes: one thread per box draws
 // sampleCount positions (Random::position(Box): x, y, z in this order) and averages the total density of the components;
 // mass = mean density x volume -- the quantity TreeDustGrid::subdivide compares with maxMassFraction (TreeDustGrid.cpp:197-201)
+// DISP: besides the mass (same operations in the same order, so the mass of a box does not depend on DISP) the spread of the
+// sampled densities, TreeNodeSampleDensityCalculator::densityDispersion (TreeNodeSampleDensityCalculator.cpp:62-67)
+template<bool DISP>
 __global__ void __launch_bounds__(128) sampleBoxesKernel(const double* __restrict__ box, int64_t n, const SourceDev* __restrict__ geoms,
                                                          const double* __restrict__ norm, int Ncomp, int sampleCount, unsigned long long seed,
-                                                         double* __restrict__ mass)
+                                                         double* __restrict__ mass, double* __restrict__ dispersion)
 {
     for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
     {
         const double* b = box + 6 * q;
         const double x0 = b[0], y0 = b[1], z0 = b[2], wx = b[3] - b[0], wy = b[4] - b[1], wz = b[5] - b[2];
         Philox rng; rng.init(seed, (unsigned long long)q, 9u);
-        double sum = 0;
+        double sum = 0, minrho = SKG_DBL_MAX, maxrho = 0;
         for (int s = 0; s < sampleCount; s++)
         {
             const double fx = rng.uniform(), fy = rng.uniform(), fz = rng.uniform();
             const double x = x0 + fx * wx, y = y0 + fy * wy, z = z0 + fz * wz;
-            for (int h = 0; h < Ncomp; h++) sum += norm[h] * geometryDensity(geoms[h], x, y, z);
+            double rho = 0;
+            for (int h = 0; h < Ncomp; h++)
+            {
+                const double d = geometryDensity(geoms[h], x, y, z);
+                sum += norm[h] * d;
+                if (DISP) rho += norm[h] * d;
+            }
+            if (DISP) { minrho = fmin(minrho, rho); maxrho = fmax(maxrho, rho); }
         }
         mass[q] = sum / sampleCount * (wx * wy * wz);
+        if (DISP) dispersion[q] = maxrho > 0 ? (maxrho - minrho) / maxrho : 0;
     }
 }
 
-void mcSampleBoxes(Engine& e, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* mass)
+void mcSampleBoxes(Engine& e, int64_t n, const double* box, int Ncomp, const skg_source* geoms, const double* norm, int sampleCount, uint64_t seed, double* mass, double* dispersion)
 {
     if (n < 0 || (n > 0 && (!box || !mass)) || Ncomp < 1 || Ncomp > 8 || !geoms || !norm) throw Error("skg_sample_boxes: bad arguments");
     if (sampleCount < 1) throw Error("Number of random samples must be at least 1");       // TreeDustGrid.cpp:60
     if (n == 0) return;
     std::vector<DevBuf*> bufs; std::vector<SourceDev> dev;
-    DevBuf devGeoms, devNorm, devBox, devMass;
+    DevBuf devGeoms, devNorm, devBox, devMass, devDisp;
     try
     {
         for (int h = 0; h < Ncomp; h++) dev.push_back(makeSourceDev(e, geoms[h], bufs, true));
         devGeoms.upload(dev.data(), sizeof(SourceDev) * Ncomp, e.stream); devNorm.upload(norm, sizeof(double) * Ncomp, e.stream);
         devBox.upload(box, sizeof(double) * 6 * (size_t)n, e.stream); devMass.ensure(sizeof(double) * (size_t)n);
+        if (dispersion) devDisp.ensure(sizeof(double) * (size_t)n);
         const int blocks = (int)std::max<int64_t>(1, std::min<int64_t>((n + 127) / 128, (int64_t)e.smCount * 16));
-        sampleBoxesKernel<<<blocks, 128, 0, e.stream>>>(devBox.as<double>(), n, devGeoms.as<SourceDev>(), devNorm.as<double>(), Ncomp, sampleCount, seed, devMass.as<double>());
+        if (dispersion)
+            sampleBoxesKernel<true><<<blocks, 128, 0, e.stream>>>(devBox.as<double>(), n, devGeoms.as<SourceDev>(), devNorm.as<double>(), Ncomp, sampleCount, seed, devMass.as<double>(), devDisp.as<double>());
+        else
+            sampleBoxesKernel<false><<<blocks, 128, 0, e.stream>>>(devBox.as<double>(), n, devGeoms.as<SourceDev>(), devNorm.as<double>(), Ncomp, sampleCount, seed, devMass.as<double>(), nullptr);
         e.launches++; SKG_CUDA(cudaGetLastError());
         SKG_CUDA(cudaMemcpyAsync(mass, devMass.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
+        if (dispersion) SKG_CUDA(cudaMemcpyAsync(dispersion, devDisp.p, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, e.stream));
         e.sync();
     }
     catch (...) { for (DevBuf* b : bufs) delete b; throw; }

@@ -17,13 +17,14 @@ void TreeDustGrid::build(skg_engine* e, const std::vector<skg_source>& geoms, co
     if (_Nrandom < 1) SKIRT_FATAL("Number of random samples must be at least 1");
     if (_maxOpticalDepth < 0.0) SKIRT_FATAL("The maximum mean optical depth should be positive");
     if (_maxMassFraction < 0.0) SKIRT_FATAL("The maximum mass fraction should be positive");
+    if (_maxDensDispFraction < 0.0) SKIRT_FATAL("The maximum density dispersion fraction should be positive");      // TreeDustGrid.cpp:63
     try
     {
         skirt::TreeBuilder tb(_kind, _ext, _minlevel, _maxlevel);
         double total = 0; for (double v : norms) total += v;                        // CompDustDistribution::mass
-        const bool always = _maxOpticalDepth == 0 && _maxMassFraction == 0;         // TreeDustGrid.cpp:192
+        const bool always = _maxOpticalDepth == 0 && _maxMassFraction == 0 && _maxDensDispFraction == 0;      // TreeDustGrid.cpp:192
         const double kappaV = 2600.0;                                               // Units::kappaV(), Units.cpp:30
-        std::vector<double> box, mass; std::vector<unsigned char> flags;
+        std::vector<double> box, mass, disp; std::vector<unsigned char> flags;
         while (!tb.done())
         {
             const size_t n = tb.frontierSize();
@@ -32,13 +33,20 @@ void TreeDustGrid::build(skg_engine* e, const std::vector<skg_source>& geoms, co
             if (!always)
             {
                 box.resize(6 * n); mass.resize(n); tb.frontierBoxes(box.data());
-                check(skg_sample_boxes(e, (int64_t)n, box.data(), (int)geoms.size(), geoms.data(), norms.data(), _Nrandom,
-                                       seed + 7919ull * (uint64_t)tb.frontierLevel(), mass.data()));
+                const uint64_t levelSeed = seed + 7919ull * (uint64_t)tb.frontierLevel();
+                if (_maxDensDispFraction > 0)
+                {
+                    disp.resize(n);
+                    check(skg_sample_boxes_dispersion(e, (int64_t)n, box.data(), (int)geoms.size(), geoms.data(), norms.data(), _Nrandom,
+                                                      levelSeed, mass.data(), disp.data()));
+                }
+                else check(skg_sample_boxes(e, (int64_t)n, box.data(), (int)geoms.size(), geoms.data(), norms.data(), _Nrandom, levelSeed, mass.data()));
                 for (size_t q = 0; q < n; q++)
                 {
                     const double* b = &box[6 * q]; const double vol = (b[3] - b[0]) * (b[4] - b[1]) * (b[5] - b[2]);
                     if (_maxMassFraction > 0 && mass[q] / total >= _maxMassFraction) flags[q] = 1;                      // :197-201
                     if (_maxOpticalDepth > 0 && kappaV * mass[q] / std::pow(vol, 2. / 3.) >= _maxOpticalDepth) flags[q] = 1;   // :204-208
+                    if (_maxDensDispFraction > 0 && disp[q] >= _maxDensDispFraction) flags[q] = 1;                      // :215-221
                 }
             }
             tb.subdivide(flags.data());

@@ -426,7 +426,7 @@ public:
     void setSampleCount(int v) { _Nrandom = v; }
     void setMaxOpticalDepth(double v) { _maxOpticalDepth = v; }
     void setMaxMassFraction(double v) { _maxMassFraction = v; }
-    void setMaxDensDispFraction(double v) { if (v != 0) SKIRT_FATAL("the density dispersion criterion is not supported by this host"); }
+    void setMaxDensDispFraction(double v) { _maxDensDispFraction = v; }
     bool densityOnDevice() const override { return true; }
     void build(skg_engine* e, const std::vector<skg_source>& geoms, const std::vector<double>& norms, uint64_t seed) override;
     int numCells() const override { return _t.Ncells; }
@@ -435,7 +435,7 @@ public:
     const skirt::TreeTables& tables() const { return _t; }
 private:
     int _kind, _minlevel = 2, _maxlevel = 6, _Nrandom = 100; SearchMethod _search = Neighbor;
-    double _maxOpticalDepth = 0, _maxMassFraction = 1e-6;
+    double _maxOpticalDepth = 0, _maxMassFraction = 1e-6, _maxDensDispFraction = 0;
     skirt::TreeTables _t; std::vector<int> _cellNode;
 };
 class OctTreeDustGrid : public TreeDustGrid { public: OctTreeDustGrid() : TreeDustGrid(0) {} };

@@ -105,12 +105,12 @@ int main(int argc, char** argv)
                 auto setBox = [&](BoxDustGrid* g) { g->setMinX(box[0]); g->setMaxX(box[1]); g->setMinY(box[2]); g->setMaxY(box[3]); g->setMinZ(box[4]); g->setMaxZ(box[5]); };
                 if (kind == "octtree" || kind == "bintree")
                 {
-                    // grid octtree|bintree minLevel maxLevel search(0 TopDown, 1 Neighbor, 2 Bookkeeping) maxMassFraction [sampleCount [maxOpticalDepth]]
-                    int minl, maxl, search; double mf; int samples = 100; double maxtau = 0;
-                    in >> minl >> maxl >> search >> mf; in >> samples >> maxtau;
+                    // grid octtree|bintree minLevel maxLevel search(0 TopDown, 1 Neighbor, 2 Bookkeeping) maxMassFraction [sampleCount [maxOpticalDepth [maxDensDispFraction]]]
+                    int minl, maxl, search; double mf; int samples = 100; double maxtau = 0, maxdisp = 0;
+                    in >> minl >> maxl >> search >> mf; in >> samples >> maxtau >> maxdisp;
                     TreeDustGrid* g = kind == "octtree" ? (TreeDustGrid*)new OctTreeDustGrid() : (TreeDustGrid*)new BinTreeDustGrid();
                     setBox(g); g->setMinLevel(minl); g->setMaxLevel(maxl); g->setSearchMethod((TreeDustGrid::SearchMethod)search);
-                    g->setMaxMassFraction(mf); g->setSampleCount(samples); g->setMaxOpticalDepth(maxtau);
+                    g->setMaxMassFraction(mf); g->setSampleCount(samples); g->setMaxOpticalDepth(maxtau); g->setMaxDensDispFraction(maxdisp);
                     ds->setDustGrid(g); continue;
                 }
                 if (kind == "amesh")

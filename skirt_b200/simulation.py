@@ -371,7 +371,8 @@ class OctTreeDustGrid(_BoxDustGrid):
     """TreeDustGrid / OctTreeDustGrid (TreeDustGrid.cpp:50-233; defaults TreeDustGrid.cpp:20-37): the tree is grown level by
     level by the native host library (skirt_b200/host/GridBuilders.cpp through hostlib), the dust mass of the candidate
     nodes of a level is estimated on the GPU (skg_sample_boxes = TreeNodeSampleDensityCalculator), and a node is subdivided
-    when it holds more than maxMassFraction of the dust mass or its mean optical depth exceeds maxOpticalDepth."""
+    when it holds more than maxMassFraction of the dust mass, its mean optical depth exceeds maxOpticalDepth, or its sampled
+    densities spread by more than maxDensDispFraction (skg_sample_boxes_dispersion)."""
     kind = 0
     KAPPA_V = 2600.0            # Units::kappaV(), Units.cpp:30
 
@@ -380,8 +381,13 @@ class OctTreeDustGrid(_BoxDustGrid):
         self._set_extent(minX, maxX, minY, maxY, minZ, maxZ)
         self.minLevel, self.maxLevel, self.sampleCount = int(minLevel), int(maxLevel), int(sampleCount)
         self.maxOpticalDepth, self.maxMassFraction = float(maxOpticalDepth), float(maxMassFraction)
-        if maxDensDispFraction:
-            raise FatalError("the density dispersion criterion is not supported by this host (TreeDustGrid.cpp:215-219)")
+        self.maxDensDispFraction = float(maxDensDispFraction)
+        if self.maxOpticalDepth < 0:
+            raise FatalError("The maximum mean optical depth should be positive")              # TreeDustGrid.cpp:61
+        if self.maxMassFraction < 0:
+            raise FatalError("The maximum mass fraction should be positive")                   # TreeDustGrid.cpp:62
+        if self.maxDensDispFraction < 0:
+            raise FatalError("The maximum density dispersion fraction should be positive")     # TreeDustGrid.cpp:63
         try:
             self.search = {"TopDown": 0, "Neighbor": 1, "Bookkeeping": 2}[searchMethod]
         except KeyError:
@@ -397,18 +403,23 @@ class OctTreeDustGrid(_BoxDustGrid):
         from . import hostlib
         tb = hostlib.TreeBuilder(self.kind, self.extent, self.minLevel, self.maxLevel)
         total = float(np.sum(norms))
-        always = self.maxOpticalDepth == 0 and self.maxMassFraction == 0
+        always = self.maxOpticalDepth == 0 and self.maxMassFraction == 0 and self.maxDensDispFraction == 0
 
         def decide(level, boxes):
             if always:
                 return np.ones(len(boxes), bool)
-            mass = engine.sample_boxes(boxes, geometries, norms, self.sampleCount, seed + 7919 * level)
+            if self.maxDensDispFraction > 0:
+                mass, disp = engine.sample_boxes(boxes, geometries, norms, self.sampleCount, seed + 7919 * level, dispersion=True)
+            else:
+                mass = engine.sample_boxes(boxes, geometries, norms, self.sampleCount, seed + 7919 * level)
             need = np.zeros(len(boxes), bool)
             if self.maxMassFraction > 0:
                 need |= mass / total >= self.maxMassFraction
             if self.maxOpticalDepth > 0:
                 vol = np.prod(boxes[:, 3:] - boxes[:, :3], axis=1)
                 need |= self.KAPPA_V * mass / vol ** (2. / 3.) >= self.maxOpticalDepth
+            if self.maxDensDispFraction > 0:
+                need |= disp >= self.maxDensDispFraction                                      # TreeDustGrid.cpp:215-221
             return need
         tb.grow(decide)
         self._t = tb.finish(self.search)
