@@ -23,7 +23,8 @@ def lib():
     global _lib
     if _lib is None:
         L = C.CDLL(LIB_PATH)
-        for name in ("orc_grid_cartesian", "orc_grid_tree", "orc_grid_amesh", "orc_grid_voronoi", "orc_medium"):
+        for name in ("orc_grid_cartesian", "orc_grid_tree", "orc_grid_amesh", "orc_grid_voronoi", "orc_grid_sphere1d", "orc_grid_sphere2d", "orc_grid_cylinder2d",
+                     "orc_medium"):
             getattr(L, name).restype = C.c_void_p
         L.orc_path_batch.restype = C.c_long
         L.orc_stuck.restype = C.c_long
@@ -70,6 +71,13 @@ class Oracle:
                                         _p(_i32(t["blkStart"])), _p(pad(t["blkIds"])), _p(_i32(t["blkTree"])), len(t["kdM"]),
                                         _p(pad(t["kdM"])), _p(pad(t["kdAxis"])), _p(pad(t["kdUp"])), _p(pad(t["kdLeft"])),
                                         _p(pad(t["kdRight"])), _p(cb))
+        elif kind == "sphere1d":
+            rv = _f64(t["rv"]); self.g = L.orc_grid_sphere1d(len(rv) - 1, _p(rv))
+        elif kind == "sphere2d":
+            rv, tv, cv = _f64(t["rv"]), _f64(t["thetav"]), _f64(t["cv"])
+            self.g = L.orc_grid_sphere2d(len(rv) - 1, _p(rv), len(tv) - 1, _p(tv), _p(cv))
+        elif kind == "cylinder2d":
+            Rv, zv = _f64(t["Rv"]), _f64(t["zv"]); self.g = L.orc_grid_cylinder2d(len(Rv) - 1, _p(Rv), len(zv) - 1, _p(zv))
         else:
             raise ValueError(kind)
         self.g = C.c_void_p(self.g)

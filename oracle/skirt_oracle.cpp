@@ -580,6 +580,255 @@ struct Voronoi : Grid
     void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
 };
 
+// =====================================================================================================
+// Sphere1DDustGrid: concentric shells, borders rv[0..Nr] (Sphere1DDustGrid.cpp:24-33)
+// =====================================================================================================
+struct Sphere1D : Grid
+{
+    std::vector<double> rv; int Nr;
+    int numCells() const override { return Nr; }
+    // Sphere1DDustGrid::whichcell, Sphere1DDustGrid.cpp:85-88
+    int whichcell(double x, double y, double z) const override { return locateFail(rv.data(), Nr + 1, std::sqrt(x * x + y * y + z * z)); }
+
+    // Sphere1DDustGrid::path, Sphere1DDustGrid.cpp:111-185.  The ray is described by its impact parameter p and the signed
+    // distance q to the point of closest approach; shell border rN is crossed at q = -/+ sqrt((rN-p)(rN+p)).  Kept as the
+    // reference has them: a ray from outside continues from q = +qmax (the far side), and the outward walk ends when it
+    // reaches shell Nr-1.
+    void path(Path& P) const override
+    {
+        P.clear();
+        const double x = P.rx, y = P.ry, z = P.rz, rmax = rv[Nr];
+        double r = std::sqrt(x * x + y * y + z * z);
+        double q = x * P.kx + y * P.ky + z * P.kz;
+        const double p = std::sqrt((r - q) * (r + q));
+        auto cross = [&](double rN) { return std::sqrt((rN - p) * (rN + p)); };
+        if (r > rmax)
+        {
+            if (q > 0.0 || p > rmax) { P.clear(); return; }
+            r = rmax - 1e-8 * (rv[Nr] - rv[Nr - 1]);
+            const double qmax = cross(rmax);
+            P.add(-1, qmax - q);
+            q = qmax;
+        }
+        int i = locateClip(rv.data(), Nr + 1, r);
+        if (q < 0.0)        // inward, down to the shell that holds the point of closest approach
+        {
+            const int imin = locateClip(rv.data(), Nr + 1, p);
+            while (i > imin) { const double qN = -cross(rv[i]); P.add(i, qN - q); q = qN; i--; }
+        }
+        for (;;)            // outward
+        {
+            const double qN = cross(rv[i + 1]);
+            P.add(i, qN - q);
+            if (++i >= Nr - 1) return;
+            q = qN;
+        }
+    }
+    void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
+};
+
+// =====================================================================================================
+// Sphere2DDustGrid: shells x polar bins, borders rv[0..Nr], thetav[0..Nt], cv = cos(thetav) with exact 1, 0, -1 at the
+// poles and in the xy-plane (Sphere2DDustGrid.cpp:27-75); m = k + Nt*i (:387-390)
+// =====================================================================================================
+// smallest positive root of x^2 + 2 b x + c = 0, 0 if none (Sphere2DDustGrid.cpp:188-215): the root of smaller magnitude is
+// taken as c / (the other root) so that it does not suffer cancellation
+double firstRoot(double b, double c)
+{
+    if (!(b * b > c)) return 0;
+    if (b > 0)
+    {
+        if (c < 0) { const double x1 = -b - std::sqrt(b * b - c); return c / x1; }
+        return 0;
+    }
+    const double x2 = -b + std::sqrt(b * b - c);
+    if (c > 0) { const double x1 = c / x2; if (x1 < x2) return x1; }
+    return x2;
+}
+// the same for a x^2 + 2 b x + c = 0 (Sphere2DDustGrid.cpp:218-224)
+double firstRoot(double a, double b, double c)
+{
+    if (std::fabs(a) > 1e-9) return firstRoot(b / a, c / a);
+    const double x = -0.5 * c / b;
+    return x > 0 ? x : 0;
+}
+
+struct Sphere2D : Grid
+{
+    std::vector<double> rv, thetav, cv; int Nr, Nt;
+    int numCells() const override { return Nr * Nt; }
+    // Position::spherical, Position.cpp:95-108 (phi is not needed)
+    static void spherical(double x, double y, double z, double& r, double& theta)
+    {
+        r = std::sqrt(x * x + y * y + z * z);
+        theta = r == 0 ? 0.0 : std::acos(z / r);
+    }
+    // Sphere2DDustGrid::whichcell, Sphere2DDustGrid.cpp:148-156
+    int whichcell(double x, double y, double z) const override
+    {
+        double r, theta; spherical(x, y, z, r, theta);
+        const int i = locateFail(rv.data(), Nr + 1, r);
+        if (i < 0) return -1;
+        return locateClip(thetav.data(), Nt + 1, theta) + Nt * i;
+    }
+
+    // Sphere2DDustGrid::path, Sphere2DDustGrid.cpp:249-358: from the current point the nearest crossing with the two spheres and
+    // the two cones of the cell (Sphere2DDustGrid.cpp:228-243) decides the next cell; the point is pushed eps beyond each wall
+    void path(Path& P) const override
+    {
+        const double rmax = rv[Nr], eps = 1e-11 * rmax;
+        P.clear();
+        double x = P.rx, y = P.ry, z = P.rz; const double kx = P.kx, ky = P.ky, kz = P.kz;
+        auto advance = [&](double d) { x += kx * d; y += ky * d; z += kz * d; };
+        auto sphere = [&](double rad) { return firstRoot(x * kx + y * ky + z * kz, (x * x + y * y + z * z) - rad * rad); };
+        auto cone = [&](double c)
+        {
+            return c ? firstRoot(c * c - kz * kz, c * c * (x * kx + y * ky + z * kz) - z * kz, c * c * (x * x + y * y + z * z) - z * z)
+                     : -z / kz;
+        };
+        const double r2 = x * x + y * y + z * z;
+        if (r2 > rmax * rmax)
+        {
+            const double ds = sphere(rmax);
+            if (!ds) { P.clear(); return; }
+            P.add(-1, ds);
+            advance(ds + eps);
+        }
+        else if (r2 == 0) advance(eps);
+
+        double r, theta; spherical(x, y, z, r, theta);
+        int i = locateFail(rv.data(), Nr + 1, r);
+        int k = locateClip(thetav.data(), Nt + 1, theta);
+        int inext = i, knext = k;
+        while (i < Nr && i >= 0)
+        {
+            double ds = DBL_MAX;
+            auto candidate = [&](double s, int in, int kn) { if (s > 0 && s < ds) { ds = s; inext = in; knext = kn; } };
+            if (i > 0) candidate(sphere(rv[i]), i - 1, k);
+            candidate(sphere(rv[i + 1]), i + 1, k);
+            if (k > 0) candidate(cone(cv[k]), i, k - 1);
+            if (k < Nt - 1) candidate(cone(cv[k + 1]), i, k + 1);
+            if (inext != i || knext != k)
+            {
+                P.add(k + Nt * i, ds);
+                advance(ds + eps);
+                i = inext; k = knext;
+            }
+            else        // "No exit point found from dust grid cell": a tiny step, the cell looked up again
+            {
+                stuck++;
+                advance(eps);
+                spherical(x, y, z, r, theta);
+                i = locateFail(rv.data(), Nr + 1, r);
+                k = locateClip(thetav.data(), Nt + 1, theta);
+            }
+        }
+    }
+    void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
+};
+
+// =====================================================================================================
+// Cylinder2DDustGrid: rings R x z, borders Rv[0..NR], zv[0..Nz]; m = k + Nz*i (Cylinder2DDustGrid.cpp:391-394)
+// =====================================================================================================
+struct Cylinder2D : Grid
+{
+    std::vector<double> Rv, zv; int NR, Nz;
+    int numCells() const override { return NR * Nz; }
+    // Cylinder2DDustGrid::whichcell, Cylinder2DDustGrid.cpp:101-107
+    int whichcell(double x, double y, double z) const override
+    {
+        const int i = locateFail(Rv.data(), NR + 1, std::sqrt(x * x + y * y));
+        const int k = locateFail(zv.data(), Nz + 1, z);
+        return (i < 0 || k < 0) ? -1 : k + Nz * i;
+    }
+
+    // Cylinder2DDustGrid::path, Cylinder2DDustGrid.cpp:135-385.  In the projection on the equatorial plane the ray is a line with
+    // impact parameter p and abscissa q (speed kq); the reference's four loops (up / down x inward / outward) differ only in
+    // which border is next on each axis, so they are one loop here with the two directions as parameters.
+    void path(Path& P) const override
+    {
+        P.clear();
+        const double kx = P.kx, ky = P.ky; double kz = P.kz;
+        double kq = std::sqrt(kx * kx + ky * ky);
+        if (kz == 0.0) kz = 1e-20;
+        if (kq == 0.0) kq = 1e-20;
+        const double x = P.rx, y = P.ry; double z = P.rz;
+        double R = std::sqrt(x * x + y * y);
+        double q = (x * kx + y * ky) / kq;
+        const double p2 = (R - q) * (R + q);
+        const double p = std::sqrt(std::max(0.0, p2));
+        const double Rmax = Rv[NR], zmin = zv[0], zmax = zv[Nz];
+        auto cross = [&](double RN) { return std::sqrt((RN - p) * (RN + p)); };
+
+        if (R >= Rmax)
+        {
+            if (q > 0.0 || p > Rmax) { P.clear(); return; }
+            R = Rmax - 1e-8 * (Rv[NR] - Rv[NR - 1]);
+            const double qmax = cross(Rmax);
+            const double ds = (qmax - q) / kq;
+            P.add(-1, ds);
+            q = qmax;
+            z += kz * ds;
+        }
+        if (z < zmin)
+        {
+            if (kz <= 0.0) { P.clear(); return; }
+            const double ds = (zmin - z) / kz;
+            P.add(-1, ds);
+            q += kq * ds;
+            R = std::sqrt(p * p + q * q);
+            z = zmin + 1e-8 * (zv[1] - zv[0]);
+        }
+        else if (z > zmax)
+        {
+            if (kz >= 0.0) { P.clear(); return; }
+            const double ds = (zmax - z) / kz;
+            P.add(-1, ds);
+            q += kq * ds;
+            R = std::sqrt(p * p + q * q);
+            z = zmax - 1e-8 * (zv[Nz] - zv[Nz - 1]);
+        }
+        if (std::isinf(R) || std::isnan(R) || std::isinf(z) || std::isnan(z) || R >= Rmax || z <= zmin || z >= zmax) { P.clear(); return; }
+
+        int i = locateClip(Rv.data(), NR + 1, R);
+        int k = locateClip(zv.data(), Nz + 1, z);
+        const bool up = kz >= 0.0;
+        const int dk = up ? 1 : -1, zside = up ? 1 : 0;
+        // the reference ends a downward path one ring early (i >= NR-1, Cylinder2DDustGrid.cpp:338; upward: i >= NR, :262)
+        const int iend = up ? NR : NR - 1;
+        // one step of either phase: returns false when the path has left the grid through the top, the bottom or the outer wall
+        auto walk = [&](bool inward, double qN) -> bool
+        {
+            const double zN = zv[k + zside];
+            const double dsq = (qN - q) / kq, dsz = (zN - z) / kz;
+            const int m = k + Nz * i;
+            if (dsq < dsz)
+            {
+                P.add(m, dsq);
+                if (inward) i--; else if (++i >= iend) return false;
+                q = qN;
+                z += kz * dsq;
+            }
+            else
+            {
+                P.add(m, dsz);
+                k += dk;
+                if (k >= Nz || k < 0) return false;
+                q += kq * dsz;
+                z = zN;
+            }
+            return true;
+        };
+        if (q < 0.0)
+        {
+            const int imin = locateClip(Rv.data(), NR + 1, p);
+            while (i > imin) if (!walk(true, -cross(Rv[i]))) return;
+        }
+        while (walk(false, cross(Rv[i + 1]))) {}
+    }
+    void randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const override;
+};
+
 }   // anonymous namespace
 
 // =====================================================================================================
@@ -646,6 +895,43 @@ void Voronoi::randomPositionInCell(int m, Rng& rng, double& x, double& y, double
         if (closest) return;
     }
     errors++;
+}
+// Random::direction(), Random.cpp:179-184 with Direction(theta, phi), Direction.cpp:12-40
+void randomDirection(Rng& rng, double& kx, double& ky, double& kz)
+{
+    const double theta = std::acos(2.0 * rng.uniform() - 1.0);
+    const double phi = 2.0 * M_PI * rng.uniform();
+    const double eps = 1e-8;
+    if (theta <= eps) { kx = ky = 0.0; kz = 1.0; }
+    else if (theta >= M_PI - eps) { kx = ky = 0.0; kz = -1.0; }
+    else { const double sintheta = std::sin(theta); kx = sintheta * std::cos(phi); ky = sintheta * std::sin(phi); kz = std::cos(theta); }
+}
+// Sphere1DDustGrid::randomPositionInCell, Sphere1DDustGrid.cpp:100-106: the direction first, then the radius
+void Sphere1D::randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const
+{
+    double kx, ky, kz; randomDirection(rng, kx, ky, kz);
+    const double r = rv[m] + (rv[m + 1] - rv[m]) * rng.uniform();
+    x = r * kx; y = r * ky; z = r * kz;
+}
+// Sphere2DDustGrid::randomPositionInCell, Sphere2DDustGrid.cpp:172-183 (r, theta, phi in this order; Position.cpp:32-45)
+void Sphere2D::randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const
+{
+    const int i = m / Nt, k = m % Nt;
+    const double ris = rv[i] * rv[i], ri1s = rv[i + 1] * rv[i + 1];
+    const double r = std::sqrt(ris + (ri1s - ris) * rng.uniform());
+    const double theta = thetav[k] + (thetav[k + 1] - thetav[k]) * rng.uniform();
+    const double phi = 2.0 * M_PI * rng.uniform();
+    const double costheta = std::cos(theta), sintheta = std::sin(theta), cosphi = std::cos(phi), sinphi = std::sin(phi);
+    x = r * sintheta * cosphi; y = r * sintheta * sinphi; z = r * costheta;
+}
+// Cylinder2DDustGrid::randomPositionInCell, Cylinder2DDustGrid.cpp:123-131 (R, phi, z in this order; Position.cpp:23-30)
+void Cylinder2D::randomPositionInCell(int m, Rng& rng, double& x, double& y, double& z) const
+{
+    const int i = m / Nz, k = m % Nz;
+    const double R = Rv[i] + (Rv[i + 1] - Rv[i]) * rng.uniform();
+    const double phi = 2.0 * M_PI * rng.uniform();
+    z = zv[k] + (zv[k + 1] - zv[k]) * rng.uniform();
+    x = R * std::cos(phi); y = R * std::sin(phi);
 }
 }   // anonymous namespace
 
@@ -715,6 +1001,16 @@ Grid* makeVoronoi(int N, const double* particles, const int* nbrStart, const int
     return g;
 }
 
+Grid* makeSphere1D(int Nr, const double* rv) { Sphere1D* g = new Sphere1D(); g->Nr = Nr; g->rv.assign(rv, rv + Nr + 1); return g; }
+Grid* makeSphere2D(int Nr, const double* rv, int Nt, const double* thetav, const double* cv)
+{
+    Sphere2D* g = new Sphere2D(); g->Nr = Nr; g->Nt = Nt;
+    g->rv.assign(rv, rv + Nr + 1); g->thetav.assign(thetav, thetav + Nt + 1); g->cv.assign(cv, cv + Nt + 1);
+    return g;
+}
+Grid* makeCylinder2D(int NR, const double* Rv, int Nz, const double* zv)
+{ Cylinder2D* g = new Cylinder2D(); g->NR = NR; g->Nz = Nz; g->Rv.assign(Rv, Rv + NR + 1); g->zv.assign(zv, zv + Nz + 1); return g; }
+
 }   // namespace orc
 
 // =====================================================================================================
@@ -734,6 +1030,9 @@ void* orc_grid_voronoi(int N, const double* particles, const int* nbrStart, cons
                        const int* blkStart, const int* blkIds, const int* blkTree, int Nkd, const int* kdM, const int* kdAxis,
                        const int* kdUp, const int* kdLeft, const int* kdRight, const double* cellBox)
 { return makeVoronoi(N, particles, nbrStart, nbrIds, extent, nb, blkStart, blkIds, blkTree, Nkd, kdM, kdAxis, kdUp, kdLeft, kdRight, cellBox); }
+void* orc_grid_sphere1d(int Nr, const double* rv) { return makeSphere1D(Nr, rv); }
+void* orc_grid_sphere2d(int Nr, const double* rv, int Nt, const double* thetav, const double* cv) { return makeSphere2D(Nr, rv, Nt, thetav, cv); }
+void* orc_grid_cylinder2d(int NR, const double* Rv, int Nz, const double* zv) { return makeCylinder2D(NR, Rv, Nz, zv); }
 void orc_grid_destroy(void* g) { delete (Grid*)g; }
 int orc_num_cells(void* g) { return ((Grid*)g)->numCells(); }
 long orc_stuck(void* g) { return ((Grid*)g)->stuck; }

@@ -76,6 +76,11 @@ Grid* makeVoronoi(int Ncells, const double* particles, const int* nbrStart, cons
                   const int* blkTree, int Nkd, const int* kdM, const int* kdAxis, const int* kdUp,
                   const int* kdLeft, const int* kdRight, const double* cellBox);
 
+// grids with symmetries (Sphere1DDustGrid.cpp, Sphere2DDustGrid.cpp, Cylinder2DDustGrid.cpp): the border arrays are the whole state
+Grid* makeSphere1D(int Nr, const double* rv);
+Grid* makeSphere2D(int Nr, const double* rv, int Ntheta, const double* thetav, const double* cv);
+Grid* makeCylinder2D(int NR, const double* Rv, int Nz, const double* zv);
+
 // ---------------------------------------------------------------------------------------------
 // medium (DustSystem density table + DustMix per-wavelength scalars)
 // ---------------------------------------------------------------------------------------------

@@ -406,3 +406,20 @@ def mc_gate(a, r, label, signal=0.15, min_bins=0.0, total_sigma=4.0, total_rel=0
     lim = max(0.15, 3.5 / np.sqrt(N), 4.0 * se)
     assert abs(z.mean()) < lim, f"{label}: systematic offset, mean z = {z.mean():.3f} over {N} bins (limit {lim:.3f}, standard error {se:.3f})"
     return dict(zt=zt, z=z, bins=N, outliers=nout)
+
+
+def sym_rays(R=18000 * PC, n=40000, seed=911):
+    """rays for the grids with symmetries: isotropic rays from inside and outside, plus rays from the origin, through the centre,
+    inside and parallel to the equatorial plane, along and parallel to the z axis, and from far outside"""
+    r, k = rays(n, [-R, R, -R, R, -R, R], seed, scale=1.3)
+    rng = np.random.default_rng(12)
+    r2 = (rng.random((3000, 3)) - 0.5) * 2 * R; k2 = rng.normal(size=(3000, 3))
+    r2[:400] = 0.0
+    k2[400:800] = -r2[400:800]
+    r2[800:1200, 2] = 0.0; k2[800:1200, 2] = 0.0
+    r2[1200:1600, :2] = 0.0; k2[1200:1600, :2] = 0.0
+    k2[1600:2000, 2] = 0.0
+    k2[2000:2400, :2] = 0.0
+    r2[2400:2700] *= 3.0
+    k2 /= np.linalg.norm(k2, axis=1, keepdims=True)
+    return np.concatenate([r, r2]), np.concatenate([k, k2])

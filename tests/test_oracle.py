@@ -52,3 +52,25 @@ def test_oracle_matches_reference_on_fresh_rays(kind):
     got = oracle_py.Oracle(tables, medium).path_batch(r, k, ell=0)
     assert common.paths_bit_identical(got, ref), kind
     assert np.array_equal(oracle_py.Oracle(tables, medium).whichcell(r[:4000]), S.whichcell(r[:4000]))
+
+
+@pytest.mark.skipif(not skirtref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("kind", ["sphere1d", "sphere2d", "sphere2d_odd", "cylinder2d"])
+def test_oracle_symmetric_grids_match_the_reference(kind):
+    """the restated Sphere1DDustGrid / Sphere2DDustGrid / Cylinder2DDustGrid walkers: paths, optical depths and cell lookups bit for bit on the rays
+    the GPU parity test uses (isotropic + through the centre, along the axes, in the equatorial plane, from the origin), on the
+    reference's own border tables and on those of the product's host mirror"""
+    S = skirtref.RefSim(common.spec_grid(kind), luminosities=[[1.0]], mixes=common.mix_v()).setup()
+    tables, medium = S.grid_tables(), S.medium()
+    r, k = common.sym_rays()
+    ref = S.path_batch(r, k, ell=0, nthreads=8)
+    assert len(ref["m"]) > len(r)
+    for t in (tables, common.sym_grid_mirror(kind).tables()):
+        o = oracle_py.Oracle(t, medium)
+        assert o.Ncells == S.Ncells
+        assert common.paths_bit_identical(o.path_batch(r, k, ell=0), ref), kind
+        assert np.array_equal(o.whichcell(r), S.whichcell(r))
+        assert np.array_equal(o.opticaldepth(r[:5000], k[:5000], 0), S.opticaldepth_batch(r[:5000], k[:5000], 0))
+    # randomPositionInCell: the same MT19937 stream, the same draws in the same order
+    S.reset(4357)
+    assert np.array_equal(S.random_positions(7, 2000), oracle_py.Oracle(tables, medium).random_positions(7, 4357, 2000))
