@@ -296,6 +296,36 @@ struct Tree : Grid
             return;
         }
 
+        if (search == 3)
+        {
+            // ParticleTreeDustGrid::path, ParticleTreeDustGrid.cpp:258-325 (search tag 3 in the tables): the nearest wall with a
+            // positive distance (plain divisions: a zero direction component gives +-inf or nan, which the comparisons discard),
+            // no segment when there is none, the next node always looked up from the root
+            while (node >= 0)
+            {
+                const double* nb = b(node);
+                const double dsx = (((kx < 0.0) ? nb[0] : nb[3]) - x) / kx;
+                const double dsy = (((ky < 0.0) ? nb[1] : nb[4]) - y) / ky;
+                const double dsz = (((kz < 0.0) ? nb[2] : nb[5]) - z) / kz;
+                double ds = DBL_MAX;
+                if (dsx > 0 && dsx < ds) ds = dsx;
+                if (dsy > 0 && dsy < ds) ds = dsy;
+                if (dsz > 0 && dsz < ds) ds = dsz;
+                if (ds < DBL_MAX) p.add(cell[node], ds); else ds = 0;
+                x += (ds + eps) * kx; y += (ds + eps) * ky; z += (ds + eps) * kz;
+                const int old = node;
+                node = whichnode(x, y, z);
+                if (node == old)
+                {
+                    stuck++;
+                    x = nextAlong(x, kx); y = nextAlong(y, ky); z = nextAlong(z, kz);
+                    node = whichnode(x, y, z);
+                    if (node == old) { stuck++; break; }
+                }
+            }
+            return;
+        }
+
         // Bookkeeping (octree only), :527-659: children of a node have ids 8q+1 .. 8q+8 relative order, so the
         // octant of node l within its father is ((l-1)%8)
         int l = node;

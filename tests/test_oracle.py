@@ -74,3 +74,20 @@ def test_oracle_symmetric_grids_match_the_reference(kind):
     # randomPositionInCell: the same MT19937 stream, the same draws in the same order
     S.reset(4357)
     assert np.array_equal(S.random_positions(7, 2000), oracle_py.Oracle(tables, medium).random_positions(7, 4357, 2000))
+
+
+@pytest.mark.skipif(not skirtref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("tt,extra", [("oct", 0), ("bin", 1)])
+def test_oracle_particle_tree_walker_matches_the_reference(tt, extra):
+    """ParticleTreeDustGrid::path (its own loop: nearest wall with a positive distance, search from the root;
+    ParticleTreeDustGrid.cpp:258-325), including rays parallel to coordinate planes and axes"""
+    pts = common.voronoi_particles(3000, seed=5)
+    S = skirtref.RefSim(common.spec_grid("particletree_" + tt, maxlevel=extra), luminosities=[[1.0]], mixes=common.mix_v(), particles=pts).setup()
+    tables, medium = S.grid_tables(), S.medium()
+    assert tables["search"] == 3
+    r, k = common.rays(20000, common.C1_BOX, 31)
+    k[:300, 0] = 0; k[300:600, 1] = 0; k[600:900, 2] = 0; k[900:1000, :2] = 0
+    k /= np.linalg.norm(k, axis=1, keepdims=True)
+    o = oracle_py.Oracle(tables, medium)
+    assert common.paths_bit_identical(o.path_batch(r, k, ell=0), S.path_batch(r, k, ell=0, nthreads=8))
+    assert np.array_equal(o.whichcell(r), S.whichcell(r))
