@@ -30,6 +30,12 @@ void skh_tree_destroy(skh_tree* t);
 int skh_tree_frontier(skh_tree* t, int* level, int64_t* size, int* needsDecision);
 int skh_tree_frontier_boxes(skh_tree* t, double* box6 /* [6*size] xmin,ymin,zmin,xmax,ymax,zmax */);
 int skh_tree_subdivide(skh_tree* t, const unsigned char* flags /* [size] */);
+/* the same with the barycentre of the dust in every frontier node (TreeNodeSampleDensityCalculator::barycenter,
+ * TreeNodeSampleDensityCalculator.cpp:48-58), barycenters[3*size] or null: an octree node is split at its barycentre
+ * (OctTreeDustGrid::barycentric, BaryOctTreeNode.cpp:27-30), a binary-tree node across the axis along which the barycentre is
+ * relatively nearest to a wall (BinTreeDustGrid::directionMethod Barycenter, BaryBinTreeNode.cpp:34-58).  Levels <= minLevel
+ * split regularly (TreeDustGrid.cpp:172-176). */
+int skh_tree_subdivide_at(skh_tree* t, const unsigned char* flags /* [size] */, const double* barycenters /* [3*size] */);
 /* search: 0 TopDown, 1 Neighbor (builds the sorted neighbour lists), 2 Bookkeeping (octree only) */
 int skh_tree_finish(skh_tree* t, int search, int* Nnodes, int* Ncells, int64_t* Nneighbours);
 /* ParticleTreeDustGrid::setupSelfBefore (ParticleTreeDustGrid.cpp:76-152): an octree (kind 0) or binary tree (kind 1) grown around

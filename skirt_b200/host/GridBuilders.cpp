@@ -40,7 +40,7 @@ void TreeBuilder::frontierBoxes(double* box6) const
 
 // OctTreeNode::createchildren (split at the centre, OctTreeNode.cpp:38-57) / BinTreeNode::createchildren (split across
 // level % 3, BinTreeNode.cpp:40-77); children get consecutive ids at the end of the node vector
-void TreeBuilder::createChildren(int l)
+void TreeBuilder::createChildren(int l, const double* bary)
 {
     const double b[6] = {_t.box[6 * (size_t)l], _t.box[6 * (size_t)l + 1], _t.box[6 * (size_t)l + 2], _t.box[6 * (size_t)l + 3], _t.box[6 * (size_t)l + 4], _t.box[6 * (size_t)l + 5]};
     const int id = (int)_t.child0.size();
@@ -53,7 +53,8 @@ void TreeBuilder::createChildren(int l)
     };
     if (_kind == 0)
     {
-        const double xc = 0.5 * (b[0] + b[3]), yc = 0.5 * (b[1] + b[4]), zc = 0.5 * (b[2] + b[5]);       // Box::center
+        // Box::center, or the barycentre of the node's dust (BaryOctTreeNode::createchildren, BaryOctTreeNode.cpp:27-30)
+        const double xc = bary ? bary[0] : 0.5 * (b[0] + b[3]), yc = bary ? bary[1] : 0.5 * (b[1] + b[4]), zc = bary ? bary[2] : 0.5 * (b[2] + b[5]);
         add(b[0], b[1], b[2], xc, yc, zc);   add(xc, b[1], b[2], b[3], yc, zc);
         add(b[0], yc, b[2], xc, b[4], zc);   add(xc, yc, b[2], b[3], b[4], zc);
         add(b[0], b[1], zc, xc, yc, b[5]);   add(xc, b[1], zc, b[3], yc, b[5]);
@@ -61,7 +62,16 @@ void TreeBuilder::createChildren(int l)
     }
     else
     {
-        const int dir = _t.level[l] % 3;
+        int dir = _t.level[l] % 3;
+        if (bary)
+        {
+            // BaryBinTreeNode::createchildren, BaryBinTreeNode.cpp:34-58: across the axis along which the barycentre is
+            // relatively nearest to a wall (the split itself stays at the centre)
+            const double dx = std::min(bary[0] - b[0], b[3] - bary[0]) / (b[3] - b[0]);
+            const double dy = std::min(bary[1] - b[1], b[4] - bary[1]) / (b[4] - b[1]);
+            const double dz = std::min(bary[2] - b[2], b[5] - bary[2]) / (b[5] - b[2]);
+            if (dx < dy) dir = dx < dz ? 0 : 2; else dir = dy < dz ? 1 : 2;
+        }
         _t.dir[l] = dir;
         if (dir == 0) { const double xc = 0.5 * (b[0] + b[3]); add(b[0], b[1], b[2], xc, b[4], b[5]); add(xc, b[1], b[2], b[3], b[4], b[5]); }
         else if (dir == 1) { const double yc = 0.5 * (b[1] + b[4]); add(b[0], b[1], b[2], b[3], yc, b[5]); add(b[0], yc, b[2], b[3], b[4], b[5]); }
@@ -70,7 +80,7 @@ void TreeBuilder::createChildren(int l)
 }
 
 // TreeDustGrid::subdivide (TreeDustGrid.cpp:168-233) for every childless node of the current level, in id order
-void TreeBuilder::subdivide(const unsigned char* flags)
+void TreeBuilder::subdivide(const unsigned char* flags, const double* bary)
 {
     std::vector<int> next;
     const bool always = _level <= _minLevel, decide = frontierNeedsDecision();
@@ -79,7 +89,7 @@ void TreeBuilder::subdivide(const unsigned char* flags)
     {
         if (!(always || (decide && flags[q]))) continue;
         const int l = _frontier[q];
-        createChildren(l);
+        createChildren(l, (bary && !always) ? bary + 3 * q : nullptr);       // forced levels split regularly, TreeDustGrid.cpp:172-176
         const int nchild = _kind == 0 ? 8 : 2;
         for (int c = 0; c < nchild; c++) next.push_back(_t.child0[l] + c);
     }

@@ -40,7 +40,9 @@ public:
     // level <= minLevel: every node of the level is subdivided; minLevel < level < maxLevel: the caller decides; level == maxLevel: none
     bool frontierNeedsDecision() const { return _level > _minLevel && _level < _maxLevel; }
     void frontierBoxes(double* box6) const;     // [6 * frontierSize()]
-    void subdivide(const unsigned char* flags); // flags[frontierSize()] (ignored unless frontierNeedsDecision())
+    // flags[frontierSize()] (ignored unless frontierNeedsDecision()); bary[3 * frontierSize()] or null: the barycentres of the dust
+    // in the nodes (TreeNodeSampleDensityCalculator::barycenter) for OctTreeDustGrid::barycentric / BinTreeDustGrid's Barycenter method
+    void subdivide(const unsigned char* flags, const double* bary = nullptr);
     void finish(int search);                    // cell numbers; neighbour lists when search == 1 (Neighbor)
     // ParticleTreeDustGrid::setupSelfBefore (ParticleTreeDustGrid.cpp:76-152) on a tree that is still its root: the particles
     // are added one by one, a leaf that already holds one is subdivided until the two sit in different leaves; then
@@ -48,7 +50,7 @@ public:
     void addParticles(const double* xyz, size_t n, int extraLevels);
     const TreeTables& tables() const { return _t; }
 private:
-    void createChildren(int l);
+    void createChildren(int l, const double* bary = nullptr);
     int whichNodeFrom(int start, double x, double y, double z) const;
     int addParticle(int p, int start, const double* xyz, std::vector<int>& particlev);
     void addNeighbors(int l);

@@ -35,6 +35,8 @@ int skh_tree_frontier_boxes(skh_tree* t, double* box6)
 { return guarded([&]{ if (!t || !box6) throw std::runtime_error("null argument"); t->b.frontierBoxes(box6); }); }
 int skh_tree_subdivide(skh_tree* t, const unsigned char* flags)
 { return guarded([&]{ if (!t) throw std::runtime_error("null tree"); t->b.subdivide(flags); }); }
+int skh_tree_subdivide_at(skh_tree* t, const unsigned char* flags, const double* barycenters)
+{ return guarded([&]{ if (!t) throw std::runtime_error("null tree"); t->b.subdivide(flags, barycenters); }); }
 int skh_tree_finish(skh_tree* t, int search, int* Nnodes, int* Ncells, int64_t* Nneighbours)
 { return guarded([&]{ if (!t) throw std::runtime_error("null tree"); t->b.finish(search); const skirt::TreeTables& T = t->b.tables();
                       if (Nnodes) *Nnodes = T.Nnodes;

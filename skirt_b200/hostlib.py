@@ -76,17 +76,28 @@ class TreeBuilder:
             _chk(self.L.skh_tree_frontier_boxes(self.h, _p(box)))
         return box
 
-    def subdivide(self, flags=None):
+    def subdivide(self, flags=None, barycenters=None):
         f = None if flags is None else np.ascontiguousarray(flags, dtype=np.uint8)
-        _chk(self.L.skh_tree_subdivide(self.h, _p(f)))
+        if barycenters is None:
+            _chk(self.L.skh_tree_subdivide(self.h, _p(f)))
+        else:
+            b = np.ascontiguousarray(barycenters, dtype=np.float64).reshape(-1, 3)
+            if f is not None and len(b) != len(f):
+                raise HostError("one barycentre per frontier node is needed")
+            _chk(self.L.skh_tree_subdivide_at(self.h, _p(f), _p(b)))
 
     def grow(self, decide):
-        """runs the whole subdivision loop"""
+        """runs the whole subdivision loop; decide(level, boxes) returns the flags, or (flags, barycenters[n, 3]) for
+        barycentric subdivision"""
         while True:
             level, n, need = self.frontier()
             if n == 0:
                 return
-            self.subdivide(decide(level, self.frontier_boxes()) if need else None)
+            d = decide(level, self.frontier_boxes()) if need else None
+            if isinstance(d, tuple):
+                self.subdivide(d[0], d[1])
+            else:
+                self.subdivide(d)
 
     def finish(self, search=1):
         nn = C.c_int(); nc = C.c_int(); nb = C.c_int64()

@@ -189,3 +189,60 @@ def test_logmesh_cpp_mirror_reproduces_the_reference_borders(tmp_path):
     for n, tc, want in list(_logmesh_golden())[::3]:
         out = subprocess.run([str(exe), str(n), tc.hex()], check=True, capture_output=True, text=True).stdout.split()
         assert np.array_equal([float.fromhex(x) for x in out], want), (n, tc)
+
+
+@pytest.mark.parametrize("kind,kw", [("octtree", dict(minlevel=2, maxlevel=5, massfrac=2e-4)),
+                                     ("bintree", dict(minlevel=4, maxlevel=12, massfrac=2e-4))])
+def test_tree_builder_reproduces_barycentric_reference_trees(kind, kw):
+    """OctTreeDustGrid::barycentric (nodes split at the barycentre of their dust, BaryOctTreeNode.cpp:27-30) and BinTreeDustGrid's
+    Barycenter direction method (BaryBinTreeNode.cpp:34-58) through skh_tree_subdivide_at: with the reference's own decisions and
+    split points (octree: read off its children; binary tree: a barycentre nearest to a wall along the axis the reference chose)
+    the tables and the neighbour lists are the reference's"""
+    spec = common.spec_grid(kind, search=1, **kw).replace(" 0 50\n", " 1 50\n")
+    ref = _ref(spec).grid_tables()
+    child0 = ref["child0"]; rbox = ref["box"].reshape(-1, 6); rdir = np.asarray(ref["dir"])
+    pos = {tuple(b): i for i, b in enumerate(rbox)}
+    tb = hostlib.TreeBuilder(0 if kind == "octtree" else 1, common.C1_BOX, kw["minlevel"], kw["maxlevel"])
+
+    def decide(level, boxes):
+        ids = np.array([pos[tuple(b)] for b in boxes]); flags = child0[ids] >= 0
+        bary = 0.5 * (boxes[:, :3] + boxes[:, 3:])
+        for q, (l, f) in enumerate(zip(ids, flags)):
+            if not f:
+                continue
+            if kind == "octtree":
+                bary[q] = rbox[child0[l], 3:]
+            else:
+                d = rdir[l]; bary[q, d] = boxes[q, d] + 0.01 * (boxes[q, d + 3] - boxes[q, d])
+        return flags, bary
+    tb.grow(decide)
+    mine = tb.finish(1)
+    for k in ("box", "child0", "parent", "cell", "nbrStart", "nbrIds"):
+        assert np.array_equal(np.asarray(mine[k]).ravel(), np.asarray(ref[k]).ravel()), f"{kind}: {k} differs from the reference"
+    inner = child0 >= 0
+    assert np.array_equal(mine["dir"][inner], rdir[inner])
+    if kind == "octtree":       # the splits really are off-centre
+        mid = 0.5 * (rbox[inner, :3] + rbox[inner, 3:])
+        assert (np.abs(rbox[child0[inner], 3:] - mid).max(axis=1) > 1e-6 * np.abs(rbox[0]).max()).mean() > 0.5
+    else:                       # and the directions do not simply alternate
+        assert (rdir[inner] != mine["level"][inner] % 3).any()
+
+
+def test_barycentric_direction_rule_ties():
+    """BaryBinTreeNode.cpp:44-54: strict comparisons, ties go to the later axis"""
+    def first_dir(bary):
+        tb = hostlib.TreeBuilder(1, [0., 1., 0., 1., 0., 1.], 0, 2)
+        tb.subdivide(None)                                      # level 0 <= minLevel: regular, across x
+        level, n, need = tb.frontier()
+        assert need and n == 2
+        boxes = tb.frontier_boxes()
+        b = boxes[:, :3] + np.asarray(bary) * (boxes[:, 3:] - boxes[:, :3])
+        tb.subdivide(np.ones(2, bool), b)
+        while tb.frontier()[1]:
+            tb.subdivide(None)                                  # the last level: nothing is subdivided
+        t = tb.finish(0)
+        return int(t["dir"][1])
+    assert first_dir([0.5, 0.5, 0.5]) == 2          # all equal -> z
+    assert first_dir([0.25, 0.5, 0.5]) == 0 and first_dir([0.5, 0.75, 0.5]) == 1 and first_dir([0.5, 0.5, 0.125]) == 2
+    assert first_dir([0.25, 0.25, 0.5]) == 1        # dx == dy < dz -> y
+    assert first_dir([0.25, 0.5, 0.25]) == 2        # dx == dz < dy -> z

@@ -91,3 +91,22 @@ def test_oracle_particle_tree_walker_matches_the_reference(tt, extra):
     o = oracle_py.Oracle(tables, medium)
     assert common.paths_bit_identical(o.path_batch(r, k, ell=0), S.path_batch(r, k, ell=0, nthreads=8))
     assert np.array_equal(o.whichcell(r), S.whichcell(r))
+
+
+BARY_CASES = [("octtree", 0, 5), ("octtree", 1, 5), ("octtree", 2, 5), ("bintree", 0, 12), ("bintree", 1, 12)]
+
+
+def barycentric_reference_tree(kind, search, maxlevel):
+    """a tree grown by the reference with OctTreeDustGrid::barycentric / BinTreeDustGrid's Barycenter direction method"""
+    spec = common.spec_grid(kind, search=search, maxlevel=maxlevel).replace(" 0 50\n", " 1 50\n")
+    return skirtref.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v()).setup()
+
+
+@pytest.mark.skipif(not skirtref.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("kind,search,maxlevel", BARY_CASES)
+def test_oracle_follows_barycentric_trees(kind, search, maxlevel):
+    S = barycentric_reference_tree(kind, search, maxlevel)
+    r, k = common.rays(20000, common.C1_BOX, 31)
+    o = oracle_py.Oracle(S.grid_tables(), S.medium())
+    assert common.paths_bit_identical(o.path_batch(r, k, ell=0), S.path_batch(r, k, ell=0, nthreads=8))
+    assert np.array_equal(o.whichcell(r[:5000]), S.whichcell(r[:5000]))

@@ -163,3 +163,22 @@ def test_tree_grown_on_the_dispersion_criterion(tmp_path, engine, kind):
     import json
     st = json.loads(r.stdout.strip().splitlines()[-1])
     assert abs(st["cells"] / grid.numCells() - 1) < 0.15
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,search,maxlevel", [("octtree", 0, 5), ("octtree", 1, 5), ("octtree", 2, 5), ("bintree", 0, 12), ("bintree", 1, 12)])
+def test_device_walkers_follow_barycentric_trees(engine, kind, search, maxlevel):
+    """trees grown by the reference with OctTreeDustGrid::barycentric / BinTreeDustGrid's Barycenter direction method (nodes split
+    off-centre / across non-alternating axes): the table-driven device walkers follow them bit for bit with every search method
+    (tools/check_barycentric.py is the same check as a script; its B200 output is profiles/r02_z_barycentric_gpu.txt)"""
+    from oracle import skirtref as sr
+    if not sr.available():
+        pytest.skip("oracle/_ref/libskirtref.so not present")
+    spec = common.spec_grid(kind, search=search, maxlevel=maxlevel).replace(" 0 50\n", " 1 50\n")
+    S = sr.RefSim(spec, luminosities=[[1.0]], mixes=common.mix_v()).setup()
+    t, med = S.grid_tables(), S.medium()
+    r, k = common.rays(20000, common.C1_BOX, 31)
+    ref = S.path_batch(r, k, ell=0, nthreads=os.cpu_count() or 1)
+    engine.set_grid(t); engine.medium(med["rho"], med["kext"], med["ksca"], med["g"])
+    assert common.paths_bit_identical(engine.path_batch(r, k, ell=0), ref)
+    assert np.array_equal(engine.whichcell(r[:5000]), S.whichcell(r[:5000]))
