@@ -308,6 +308,8 @@ def setup_engine(e, cfg, tables, medium, L=None):
 
 # ---- golden fixtures (tests/golden/*.npz, generated from the reference by tests/golden/make_golden.py) ---------
 GEOM_CASES = ["cart_lin", "cart_sympow", "octtree_s0", "octtree_s1", "octtree_s2", "bintree_s0", "bintree_s1", "amesh", "voronoi"]
+# fixtures of tests/golden/make_symmetric_golden.py: grids with symmetries, a particle tree, a barycentric octree
+GEOM_CASES_MORE = ["sphere1d", "sphere2d", "sphere2d_odd", "cylinder2d", "particletree_oct", "octtree_bary_s1"]
 
 
 def load_golden(name):

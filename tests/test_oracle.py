@@ -10,7 +10,7 @@ from oracle import oracle_py, skirtref
 pytestmark = pytest.mark.skipif(not oracle_py.available(), reason="oracle/liboracle.so not built")
 
 
-@pytest.mark.parametrize("name", common.GEOM_CASES)
+@pytest.mark.parametrize("name", common.GEOM_CASES + common.GEOM_CASES_MORE)
 def test_oracle_reproduces_golden_paths(name):
     tables, medium, d = common.load_golden(name)
     o = oracle_py.Oracle(tables, medium)
