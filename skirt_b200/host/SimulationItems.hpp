@@ -438,8 +438,21 @@ private:
     double _maxOpticalDepth = 0, _maxMassFraction = 1e-6, _maxDensDispFraction = 0;
     skirt::TreeTables _t; std::vector<int> _cellNode;
 };
-class OctTreeDustGrid : public TreeDustGrid { public: OctTreeDustGrid() : TreeDustGrid(0) {} };
-class BinTreeDustGrid : public TreeDustGrid { public: BinTreeDustGrid() : TreeDustGrid(1) {} };
+// Barycentric subdivision (OctTreeDustGrid.cpp:32-40, BinTreeDustGrid.cpp:41-52) needs the barycentre of a node's dust, which the
+// device's box sampler does not return: asked for, it is refused rather than silently replaced by the regular subdivision
+class OctTreeDustGrid : public TreeDustGrid
+{
+public:
+    OctTreeDustGrid() : TreeDustGrid(0) {}
+    void setBarycentric(bool v) { if (v) SKIRT_FATAL("barycentric subdivision is not supported by this host (use the regular octree)"); }
+};
+class BinTreeDustGrid : public TreeDustGrid
+{
+public:
+    enum DirectionMethod { Alternating = 0, Barycenter = 1 };
+    BinTreeDustGrid() : TreeDustGrid(1) {}
+    void setDirectionMethod(DirectionMethod v) { if (v != Alternating) SKIRT_FATAL("the Barycenter direction method is not supported by this host (use Alternating)"); }
+};
 
 // Sphere1DDustGrid / Sphere2DDustGrid / Cylinder2DDustGrid (the grids with symmetries): the border arrays are the whole state
 class SymmetricDustGrid : public DustGrid

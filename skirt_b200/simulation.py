@@ -377,8 +377,12 @@ class OctTreeDustGrid(_BoxDustGrid):
     KAPPA_V = 2600.0            # Units::kappaV(), Units.cpp:30
 
     def __init__(self, minX, maxX, minY, maxY, minZ, maxZ, minLevel=2, maxLevel=6, searchMethod="Neighbor", sampleCount=100,
-                 maxOpticalDepth=0.0, maxMassFraction=1e-6, maxDensDispFraction=0.0):
+                 maxOpticalDepth=0.0, maxMassFraction=1e-6, maxDensDispFraction=0.0, barycentric=False, directionMethod="Alternating"):
         self._set_extent(minX, maxX, minY, maxY, minZ, maxZ)
+        # OctTreeDustGrid::barycentric / BinTreeDustGrid::directionMethod (OctTreeDustGrid.cpp:32-40, BinTreeDustGrid.cpp:41-52) need
+        # the barycentre of a node's dust, which the device's box sampler does not return: refused, not silently replaced
+        if barycentric or directionMethod != "Alternating":
+            raise FatalError("barycentric subdivision is not supported by this host (regular subdivision only)")
         self.minLevel, self.maxLevel, self.sampleCount = int(minLevel), int(maxLevel), int(sampleCount)
         self.maxOpticalDepth, self.maxMassFraction = float(maxOpticalDepth), float(maxMassFraction)
         self.maxDensDispFraction = float(maxDensDispFraction)

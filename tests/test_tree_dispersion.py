@@ -182,3 +182,13 @@ def test_device_walkers_follow_barycentric_trees(engine, kind, search, maxlevel)
     engine.set_grid(t); engine.medium(med["rho"], med["kext"], med["ksca"], med["g"])
     assert common.paths_bit_identical(engine.path_batch(r, k, ell=0), ref)
     assert np.array_equal(engine.whichcell(r[:5000]), S.whichcell(r[:5000]))
+
+
+def test_barycentric_subdivision_is_refused_by_the_hosts():
+    """the host mirrors grow centre-split trees only: the option is an error, not a silent fallback"""
+    b = common.C1_BOX
+    with pytest.raises(sim.FatalError, match="barycentric subdivision is not supported"):
+        sim.OctTreeDustGrid(b[0], b[1], b[2], b[3], b[4], b[5], barycentric=True)
+    with pytest.raises(sim.FatalError, match="barycentric subdivision is not supported"):
+        sim.BinTreeDustGrid(b[0], b[1], b[2], b[3], b[4], b[5], directionMethod="Barycenter")
+    sim.BinTreeDustGrid(b[0], b[1], b[2], b[3], b[4], b[5], directionMethod="Alternating")
