@@ -55,6 +55,7 @@
 #include "InterstellarDustMix.hpp"
 #include "LinMesh.hpp"
 #include "LogWavelengthGrid.hpp"
+#include "NestedLogWavelengthGrid.hpp"
 #include "MultiFrameInstrument.hpp"
 #include "PerspectiveInstrument.hpp"
 #include "InstrumentFrame.hpp"
@@ -299,6 +300,13 @@ namespace
             {
                 double a, b; int n; in >> a >> b >> n;
                 LogWavelengthGrid* g = new LogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n);
+                S->plg = g;
+            }
+            else if (key == "nestedloggrid")      // min max points  zoom-min zoom-max zoom-points
+            {
+                double a, b, za, zb; int n, zn; in >> a >> b >> n >> za >> zb >> zn;
+                NestedLogWavelengthGrid* g = new NestedLogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n);
+                g->setMinWavelengthSubGrid(za); g->setMaxWavelengthSubGrid(zb); g->setPointsSubGrid(zn);
                 S->plg = g;
             }
             else if (key == "box") { for (int i = 0; i < 6; i++) in >> S->box[i]; }

@@ -18,7 +18,7 @@ REF_CPP := Array.cpp ProcessManager.cpp \
  StellarCompNormalization.cpp BolLuminosityStellarCompNormalization.cpp SED.cpp StellarSED.cpp SunSED.cpp BlackBodySED.cpp \
  Geometry.cpp GenGeometry.cpp AxGeometry.cpp SepAxGeometry.cpp SpheGeometry.cpp ExpDiskGeometry.cpp SersicGeometry.cpp \
  SersicFunction.cpp SpecialFunctions.cpp SpiralStructureGeometryDecorator.cpp \
- WavelengthGrid.cpp OligoWavelengthGrid.cpp PanWavelengthGrid.cpp LogWavelengthGrid.cpp \
+ WavelengthGrid.cpp OligoWavelengthGrid.cpp PanWavelengthGrid.cpp LogWavelengthGrid.cpp NestedLogWavelengthGrid.cpp \
  InstrumentSystem.cpp Instrument.cpp DistantInstrument.cpp SingleFrameInstrument.cpp FrameInstrument.cpp \
  SEDInstrument.cpp SimpleInstrument.cpp FullInstrument.cpp MultiFrameInstrument.cpp InstrumentFrame.cpp PerspectiveInstrument.cpp HomogeneousTransform.cpp
 REF_CC := $(filter-out v_base_wl.cc,$(notdir $(wildcard $(REF)/Voro/*.cc)))

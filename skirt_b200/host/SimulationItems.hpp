@@ -85,6 +85,51 @@ private:
     double _min = 0, _max = 0; int _points = 0;
 };
 
+// NestedLogWavelengthGrid.cpp:21-60: a low-resolution logarithmic grid whose points inside the zoom range are replaced by a
+// high-resolution logarithmic subgrid; bin widths as for every PanWavelengthGrid (PanWavelengthGrid.cpp:25-37)
+class NestedLogWavelengthGrid : public WavelengthGrid
+{
+public:
+    void setMinWavelength(double v) { _min = v; }
+    void setMaxWavelength(double v) { _max = v; }
+    void setPoints(int v) { _points = v; }
+    void setMinWavelengthSubGrid(double v) { _zoomMin = v; }
+    void setMaxWavelengthSubGrid(double v) { _zoomMax = v; }
+    void setPointsSubGrid(int v) { _zoomPoints = v; }
+    void setup() override
+    {
+        if (_points < 2) SKIRT_FATAL("the number of points in the low-resolution grid should be at least 2");
+        if (_zoomPoints < 2) SKIRT_FATAL("the number of points in the high-resolution subgrid should be at least 2");
+        if (_min <= 0) SKIRT_FATAL("the shortest wavelength should be positive");
+        if (_zoomMin <= _min || _zoomMax <= _zoomMin || _max <= _zoomMax)
+            SKIRT_FATAL("the high-resolution subgrid should be properly nested in the low-resolution grid");
+        auto loggrid = [](double xmin, double xmax, int n)                                  // NR::loggrid, NR.hpp:269-275
+        {
+            std::vector<double> xv(n + 1);
+            const double logxmin = std::log10(xmin), dlogx = std::log10(xmax / xmin) / n;
+            for (int i = 0; i <= n; i++) xv[i] = std::pow(10.0, logxmin + i * dlogx);
+            return xv;
+        };
+        const std::vector<double> low = loggrid(_min, _max, _points - 1), zoom = loggrid(_zoomMin, _zoomMax, _zoomPoints - 1);
+        _lambdav.clear();
+        for (double v : low) if (v < _zoomMin) _lambdav.push_back(v);
+        _lambdav.insert(_lambdav.end(), zoom.begin(), zoom.end());
+        for (double v : low) if (v > _zoomMax) _lambdav.push_back(v);
+        const int n = (int)_lambdav.size() - 1;
+        if (n + 1 < 3) SKIRT_FATAL("There must be at least three bins in a panchromatic wavelength grid");
+        _dlambdav.resize(n + 1);
+        for (int i = 0; i <= n; i++)
+        {
+            const double lo = i == 0 ? _lambdav[0] : std::sqrt(_lambdav[i - 1] * _lambdav[i]);
+            const double hi = i == n ? _lambdav[n] : std::sqrt(_lambdav[i] * _lambdav[i + 1]);
+            _dlambdav[i] = hi - lo;
+        }
+    }
+    bool issampledrange() const override { return true; }
+private:
+    double _min = 0, _max = 0, _zoomMin = 0, _zoomMax = 0; int _points = 0, _zoomPoints = 0;
+};
+
 // ---- one-dimensional meshes (Mesh subclasses; NR.hpp:171-261) -------------------------------------------
 class Mesh
 {

@@ -98,6 +98,12 @@ int main(int argc, char** argv)
             }
             else if (key == "wavelengths") { std::vector<double> lv; double v; while (in >> v) lv.push_back(v); auto* g = new OligoWavelengthGrid(); g->setWavelengths(lv); sim.setWavelengthGrid(g); }
             else if (key == "loggrid") { double a, b; int n; in >> a >> b >> n; auto* g = new LogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n); sim.setWavelengthGrid(g); }
+            else if (key == "nestedloggrid")
+            {
+                double a, b, za, zb; int n, zn; in >> a >> b >> n >> za >> zb >> zn;
+                auto* g = new NestedLogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n);
+                g->setMinWavelengthSubGrid(za); g->setMaxWavelengthSubGrid(zb); g->setPointsSubGrid(zn); sim.setWavelengthGrid(g);
+            }
             else if (key == "box") { for (double& v : box) in >> v; }
             else if (key == "grid")
             {

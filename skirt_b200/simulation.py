@@ -49,9 +49,15 @@ class LogWavelengthGrid:
             raise FatalError("the longest wavelength should be larger than the shortest")
         if points < 3:
             raise FatalError("There must be at least three bins in a panchromatic wavelength grid")
-        n = points - 1
-        logxmin = math.log10(minWavelength); dlogx = math.log10(maxWavelength / minWavelength) / n
-        self.lambdav = np.array([10.0 ** (logxmin + i * dlogx) for i in range(n + 1)])
+        self._finish(self._loggrid(minWavelength, maxWavelength, points - 1))
+
+    @staticmethod
+    def _loggrid(xmin, xmax, n):            # NR::loggrid, NR.hpp:269-275
+        logxmin = math.log10(xmin); dlogx = math.log10(xmax / xmin) / n
+        return np.array([10.0 ** (logxmin + i * dlogx) for i in range(n + 1)])
+
+    def _finish(self, lambdav):             # PanWavelengthGrid::setupSelfAfter, PanWavelengthGrid.cpp:25-37
+        self.lambdav = lambdav
         lo = np.concatenate([[self.lambdav[0]], np.sqrt(self.lambdav[:-1] * self.lambdav[1:])])
         hi = np.concatenate([np.sqrt(self.lambdav[:-1] * self.lambdav[1:]), [self.lambdav[-1]]])
         self.dlambdav = hi - lo
@@ -59,6 +65,26 @@ class LogWavelengthGrid:
     @property
     def Nlambda(self):
         return len(self.lambdav)
+
+
+class NestedLogWavelengthGrid(LogWavelengthGrid):
+    """NestedLogWavelengthGrid.cpp:21-60: a low-resolution logarithmic grid whose points inside [minWavelengthSubGrid,
+    maxWavelengthSubGrid] are replaced by a high-resolution logarithmic subgrid; bin widths as for every PanWavelengthGrid"""
+    def __init__(self, minWavelength, maxWavelength, points, minWavelengthSubGrid, maxWavelengthSubGrid, pointsSubGrid):
+        if points < 2:
+            raise FatalError("the number of points in the low-resolution grid should be at least 2")
+        if pointsSubGrid < 2:
+            raise FatalError("the number of points in the high-resolution subgrid should be at least 2")
+        if minWavelength <= 0:
+            raise FatalError("the shortest wavelength should be positive")
+        if minWavelengthSubGrid <= minWavelength or maxWavelengthSubGrid <= minWavelengthSubGrid or maxWavelength <= maxWavelengthSubGrid:
+            raise FatalError("the high-resolution subgrid should be properly nested in the low-resolution grid")
+        low = self._loggrid(minWavelength, maxWavelength, points - 1)
+        zoom = self._loggrid(minWavelengthSubGrid, maxWavelengthSubGrid, pointsSubGrid - 1)
+        lam = [v for v in low if v < minWavelengthSubGrid] + list(zoom) + [v for v in low if v > maxWavelengthSubGrid]
+        if len(lam) < 3:
+            raise FatalError("There must be at least three bins in a panchromatic wavelength grid")
+        self._finish(np.array(lam))
 
 
 # ---- 1-D meshes (Mesh / MoveableMesh subclasses; NR.hpp:171-261) ------------------------------------------

@@ -246,3 +246,47 @@ def test_barycentric_direction_rule_ties():
     assert first_dir([0.25, 0.5, 0.5]) == 0 and first_dir([0.5, 0.75, 0.5]) == 1 and first_dir([0.5, 0.5, 0.125]) == 2
     assert first_dir([0.25, 0.25, 0.5]) == 1        # dx == dy < dz -> y
     assert first_dir([0.25, 0.5, 0.25]) == 2        # dx == dz < dy -> z
+
+
+NESTED_CASES = [(1e-7, 1e-3, 12, 5e-6, 4e-5, 9), (9e-8, 2e-3, 50, 1e-6, 3e-6, 40), (1e-7, 1e-3, 2, 2e-7, 3e-7, 2), (1e-7, 1e-3, 30, 1.0000001e-7, 9.99e-4, 3)]
+
+
+def test_nested_log_wavelength_grid_mirrors(tmp_path):
+    """NestedLogWavelengthGrid (NestedLogWavelengthGrid.cpp:21-60): wavelengths and bin widths of the Python and the C++ mirror
+    bit for bit against the reference's own class (a pan simulation set up on it), and its property checks"""
+    import shutil, subprocess
+    from skirt_b200 import simulation as sim
+    from oracle import refspec, skirtref as sr
+    with pytest.raises(sim.FatalError, match="properly nested"):
+        sim.NestedLogWavelengthGrid(1e-7, 1e-3, 10, 1e-8, 1e-5, 5)
+    with pytest.raises(sim.FatalError, match="low-resolution grid should be at least 2"):
+        sim.NestedLogWavelengthGrid(1e-7, 1e-3, 1, 1e-6, 1e-5, 5)
+    with pytest.raises(sim.FatalError, match="high-resolution subgrid should be at least 2"):
+        sim.NestedLogWavelengthGrid(1e-7, 1e-3, 10, 1e-6, 1e-5, 1)
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    exe = None
+    if cxx:
+        src = tmp_path / "w.cpp"
+        src.write_text('#include <cstdio>\n#include <cstdlib>\n#include "SimulationItems.hpp"\n'
+                       'int main(int, char** a) { skirt::NestedLogWavelengthGrid g; g.setMinWavelength(std::strtod(a[1], 0)); g.setMaxWavelength(std::strtod(a[2], 0));\n'
+                       '  g.setPoints(std::atoi(a[3])); g.setMinWavelengthSubGrid(std::strtod(a[4], 0)); g.setMaxWavelengthSubGrid(std::strtod(a[5], 0));\n'
+                       '  g.setPointsSubGrid(std::atoi(a[6])); g.setup();\n'
+                       '  for (int i = 0; i < g.Nlambda(); i++) std::printf("%a %a\\n", g.lambda(i), g.dlambda(i)); return 0; }\n')
+        exe = tmp_path / "w"
+        subprocess.run([cxx, "-std=c++17", "-O2", f"-I{common.ROOT}/skirt_b200/host", f"-I{common.ROOT}/include", str(src), "-o", str(exe)], check=True)
+    spec = L = mixes = None
+    if sr.available():
+        spec, L, mixes = refspec.reference_spec(configs.c2_params(n=4, nlambda=8, packages=10), threads=1, dustsamples=1)
+    for args in NESTED_CASES:
+        g = sim.NestedLogWavelengthGrid(*args); n = g.Nlambda
+        assert np.all(np.diff(g.lambdav) > 0) and g.lambdav[0] == pytest.approx(args[0]) and g.lambdav[-1] == pytest.approx(args[1])
+        if exe:
+            out = subprocess.run([str(exe)] + [float(v).hex() if isinstance(v, float) else str(v) for v in args], check=True, capture_output=True, text=True).stdout.split()
+            vals = np.array([float.fromhex(x) for x in out]).reshape(-1, 2)
+            assert np.array_equal(vals[:, 0], g.lambdav) and np.array_equal(vals[:, 1], g.dlambdav)
+        if spec:
+            line = [l for l in spec.splitlines() if l.startswith("loggrid")][0]
+            S = sr.RefSim(spec.replace(line, "nestedloggrid %r %r %d %r %r %d" % args), luminosities=[np.ones(n).tolist() for _ in L],
+                          mixes=[(np.ones(n), np.ones(n), np.zeros(n)) for _ in mixes]).setup()
+            lam, dlam = S.wavelengths()
+            assert np.array_equal(lam, g.lambdav) and np.array_equal(dlam, g.dlambdav), args
