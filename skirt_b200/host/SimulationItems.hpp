@@ -130,6 +130,34 @@ private:
     double _min = 0, _max = 0, _zoomMin = 0, _zoomMax = 0; int _points = 0, _zoomPoints = 0;
 };
 
+// FileWavelengthGrid.cpp:22-47: the number of wavelengths, then the wavelengths in micron (divided by 1e6, sorted)
+class FileWavelengthGrid : public WavelengthGrid
+{
+public:
+    void setFilename(const std::string& v) { _filename = v; }
+    void setup() override
+    {
+        std::ifstream file(_filename);
+        if (!file.is_open()) SKIRT_FATAL("Could not open the data file " + _filename);
+        int n = 0; file >> n;
+        if (n < 3) SKIRT_FATAL("There must be at least three bins in a panchromatic wavelength grid");       // PanWavelengthGrid.cpp:30
+        _lambdav.resize(n);
+        for (int k = 0; k < n; k++) { file >> _lambdav[k]; _lambdav[k] /= 1e6; }
+        if (!file) SKIRT_FATAL("the data file " + _filename + " holds fewer wavelengths than it announces");
+        std::sort(_lambdav.begin(), _lambdav.end());
+        _dlambdav.resize(n);
+        for (int i = 0; i < n; i++)
+        {
+            const double lo = i == 0 ? _lambdav[0] : std::sqrt(_lambdav[i - 1] * _lambdav[i]);
+            const double hi = i == n - 1 ? _lambdav[n - 1] : std::sqrt(_lambdav[i] * _lambdav[i + 1]);
+            _dlambdav[i] = hi - lo;
+        }
+    }
+    bool issampledrange() const override { return true; }
+private:
+    std::string _filename;
+};
+
 // ---- one-dimensional meshes (Mesh subclasses; NR.hpp:171-261) -------------------------------------------
 class Mesh
 {

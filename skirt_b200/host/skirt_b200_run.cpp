@@ -98,6 +98,7 @@ int main(int argc, char** argv)
             }
             else if (key == "wavelengths") { std::vector<double> lv; double v; while (in >> v) lv.push_back(v); auto* g = new OligoWavelengthGrid(); g->setWavelengths(lv); sim.setWavelengthGrid(g); }
             else if (key == "loggrid") { double a, b; int n; in >> a >> b >> n; auto* g = new LogWavelengthGrid(); g->setMinWavelength(a); g->setMaxWavelength(b); g->setPoints(n); sim.setWavelengthGrid(g); }
+            else if (key == "filegrid") { std::string f; in >> f; auto* g = new FileWavelengthGrid(); g->setFilename(f); sim.setWavelengthGrid(g); }
             else if (key == "nestedloggrid")
             {
                 double a, b, za, zb; int n, zn; in >> a >> b >> n >> za >> zb >> zn;

@@ -87,6 +87,23 @@ class NestedLogWavelengthGrid(LogWavelengthGrid):
         self._finish(np.array(lam))
 
 
+class FileWavelengthGrid(LogWavelengthGrid):
+    """FileWavelengthGrid.cpp:22-47: the number of wavelengths, then the wavelengths in micron (divided by 1e6, sorted); bin widths
+    as for every PanWavelengthGrid.  (Restated from the reference text; its FilePaths machinery is not part of oracle/_ref, so
+    this class is checked against the stated rule, not against the reference's object.)"""
+    def __init__(self, filename):
+        try:
+            with open(filename) as f:
+                tokens = f.read().split()
+        except OSError:
+            raise FatalError("Could not open the data file " + str(filename))
+        n = int(tokens[0])
+        if n < 3 or len(tokens) < n + 1:
+            raise FatalError("There must be at least three bins in a panchromatic wavelength grid")
+        self.filename = filename
+        self._finish(np.sort(np.array([float(t) for t in tokens[1:n + 1]]) / 1e6))
+
+
 # ---- 1-D meshes (Mesh / MoveableMesh subclasses; NR.hpp:171-261) ------------------------------------------
 class LinMesh:
     def __init__(self, numBins):

@@ -290,3 +290,34 @@ def test_nested_log_wavelength_grid_mirrors(tmp_path):
                           mixes=[(np.ones(n), np.ones(n), np.zeros(n)) for _ in mixes]).setup()
             lam, dlam = S.wavelengths()
             assert np.array_equal(lam, g.lambdav) and np.array_equal(dlam, g.dlambdav), args
+
+
+def test_file_wavelength_grid_mirrors(tmp_path):
+    """FileWavelengthGrid (FileWavelengthGrid.cpp:22-47): micron -> m by division, sorted, PanWavelengthGrid bin widths; the
+    Python and the C++ mirror agree bit for bit"""
+    import shutil, subprocess
+    from skirt_b200 import simulation as sim
+    lam_um = np.array([0.55, 0.1, 2.2, 1000.0, 24.0, 0.3333333333333333])
+    f = tmp_path / "grid.dat"; f.write_text(f"{len(lam_um)}\n" + "\n".join(repr(float(v)) for v in lam_um) + "\n")
+    g = sim.FileWavelengthGrid(str(f))
+    assert np.array_equal(g.lambdav, np.sort(lam_um / 1e6)) and g.Nlambda == 6
+    mid = np.sqrt(g.lambdav[:-1] * g.lambdav[1:])
+    assert np.array_equal(g.dlambdav, np.concatenate([mid, g.lambdav[-1:]]) - np.concatenate([g.lambdav[:1], mid]))
+    assert g.dlambdav.sum() == pytest.approx(g.lambdav[-1] - g.lambdav[0], rel=1e-12)
+    with pytest.raises(sim.FatalError, match="Could not open the data file"):
+        sim.FileWavelengthGrid(str(tmp_path / "missing.dat"))
+    (tmp_path / "short.dat").write_text("2\n1.0\n2.0\n")
+    with pytest.raises(sim.FatalError, match="at least three bins"):
+        sim.FileWavelengthGrid(str(tmp_path / "short.dat"))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if not cxx:
+        return
+    src = tmp_path / "w.cpp"
+    src.write_text('#include <cstdio>\n#include "SimulationItems.hpp"\n'
+                   'int main(int, char** a) { skirt::FileWavelengthGrid g; g.setFilename(a[1]); g.setup();\n'
+                   '  for (int i = 0; i < g.Nlambda(); i++) std::printf("%a %a\\n", g.lambda(i), g.dlambda(i)); return 0; }\n')
+    exe = tmp_path / "w"
+    subprocess.run([cxx, "-std=c++17", "-O2", f"-I{common.ROOT}/skirt_b200/host", f"-I{common.ROOT}/include", str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(f)], check=True, capture_output=True, text=True).stdout.split()
+    vals = np.array([float.fromhex(x) for x in out]).reshape(-1, 2)
+    assert np.array_equal(vals[:, 0], g.lambdav) and np.array_equal(vals[:, 1], g.dlambdav)
