@@ -89,8 +89,8 @@ class NestedLogWavelengthGrid(LogWavelengthGrid):
 
 class FileWavelengthGrid(LogWavelengthGrid):
     """FileWavelengthGrid.cpp:22-47: the number of wavelengths, then the wavelengths in micron (divided by 1e6, sorted); bin widths
-    as for every PanWavelengthGrid.  (Restated from the reference text; its FilePaths machinery is not part of oracle/_ref, so
-    this class is checked against the stated rule, not against the reference's object.)"""
+    as for every PanWavelengthGrid.  (Restated from the reference text and checked against the stated rule: the test
+    harness does not build the reference's FilePaths machinery, so there is no reference object to compare with.)"""
     def __init__(self, filename):
         try:
             with open(filename) as f:
