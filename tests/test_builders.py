@@ -321,3 +321,14 @@ def test_file_wavelength_grid_mirrors(tmp_path):
     out = subprocess.run([str(exe), str(f)], check=True, capture_output=True, text=True).stdout.split()
     vals = np.array([float.fromhex(x) for x in out]).reshape(-1, 2)
     assert np.array_equal(vals[:, 0], g.lambdav) and np.array_equal(vals[:, 1], g.dlambdav)
+
+
+@pytest.mark.parametrize("kind", list(common.SYM_GRIDS))
+def test_symmetric_grid_mirrors_reproduce_the_golden_borders(kind):
+    """the same comparison against the committed fixtures (tests/golden/make_symmetric_golden.py), which needs no reference library"""
+    tables, _, _ = common.load_golden(kind)
+    mine = common.sym_grid_mirror(kind).tables()
+    assert mine["kind"] == tables["kind"]
+    for key in ("rv", "thetav", "cv", "Rv", "zv"):
+        if key in tables:
+            assert np.array_equal(np.asarray(mine[key]), np.asarray(tables[key])), f"{kind}: {key}"
