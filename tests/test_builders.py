@@ -332,3 +332,25 @@ def test_symmetric_grid_mirrors_reproduce_the_golden_borders(kind):
     for key in ("rv", "thetav", "cv", "Rv", "zv"):
         if key in tables:
             assert np.array_equal(np.asarray(mine[key]), np.asarray(tables[key])), f"{kind}: {key}"
+
+
+@pytest.mark.parametrize("name,kind,lo,hi,bary", [("octtree_s1", 0, 2, 4, False), ("bintree_s1", 1, 2, 10, False), ("octtree_bary_s1", 0, 2, 4, True)])
+def test_tree_builder_reproduces_the_golden_trees(name, kind, lo, hi, bary):
+    """the tree builder against the trees in the committed fixtures (no reference library needed): with the fixture's decisions
+    (and, for the barycentric octree, its split points) the node tables and neighbour lists are the reference's"""
+    ref, _, _ = common.load_golden(name)
+    child0 = np.asarray(ref["child0"]); rbox = np.asarray(ref["box"]).reshape(-1, 6)
+    pos = {tuple(b): i for i, b in enumerate(rbox)}
+    tb = hostlib.TreeBuilder(kind, common.C1_BOX, lo, hi)
+
+    def decide(level, boxes):
+        ids = np.array([pos[tuple(b)] for b in boxes]); flags = child0[ids] >= 0
+        if not bary:
+            return flags
+        pts = 0.5 * (boxes[:, :3] + boxes[:, 3:])
+        pts[flags] = rbox[child0[ids[flags]], 3:]
+        return flags, pts
+    tb.grow(decide)
+    mine = tb.finish(1)
+    for k in ("box", "child0", "parent", "cell", "nbrStart", "nbrIds"):
+        assert np.array_equal(np.asarray(mine[k]).ravel(), np.asarray(ref[k]).ravel()), f"{name}: {k} differs from the reference"
